@@ -1,0 +1,778 @@
+// ============================================================================================
+// oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Scalar C++ restatement of the reference hot path (the OptiX launch behind optixPathTracer,
+// optixMultiGPU and optixRaycasting).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library, and only as the checker or the CPU
+// baseline — never as the thing shipped.  The product (optix_raytracer_b200/csrc) has no CPU path.
+//
+// What is pinned and what is not
+//   * Integer / host parts — tea<4>, lcg, rnd (SDK/cuda/random.h:30-67), StaticWorkDistribution
+//     (SDK/sutil/WorkDistribution.h:50-81), Camera::UVWFrame (SDK/sutil/Camera.cpp:34-46) — are
+//     pinned bit-exactly against the reference's own headers compiled in place
+//     (oracle/ref_shim.cpp -> tests/golden/kat.json).
+//   * Ray/triangle intersection and BVH traversal live in the closed libnvoptix.so.1 (OptiX ABI
+//     87, not in /root/reference).  There is nothing to follow and no golden vector in the
+//     reference: PARITY UNPINNED for that part.  The oracle *defines* the contract instead
+//     (DESIGN.md "arithmetic contract"): Woop/Benthin/Wald watertight test in a fixed sequence of
+//     IEEE-754 binary32 operations, closest hit = min (t, instance, primitive ordinal), which makes
+//     the answer independent of the acceleration structure.  Small scenes are traced brute force.
+//   * Shading follows the reference device programs line by line (citations at each function),
+//     with every fused multiply-add named explicitly so the CUDA kernels (compiled -fmad=false)
+//     and this file (compiled -ffp-contract=off) produce identical bits.
+// ============================================================================================
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// vector helpers — semantics of SDK/sutil/vec_math.h:500-570 with the fma placement nvcc uses
+// ------------------------------------------------------------------------------------------
+struct f3 { float x, y, z; };
+static inline f3 mk(float x, float y, float z) { return {x, y, z}; }
+static inline f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline f3 operator*(f3 a, f3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+static inline f3 neg(f3 a) { return {-a.x, -a.y, -a.z}; }
+static inline float fm(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+// dot = fma(z,z, fma(y,y, x*x))
+static inline float dot(f3 a, f3 b) { return fm(a.z, b.z, fm(a.y, b.y, a.x * b.x)); }
+// cross component = fma(a1,b2, -(a2*b1))
+static inline f3 cross(f3 a, f3 b)
+{
+    return {fm(a.y, b.z, -(a.z * b.y)), fm(a.z, b.x, -(a.x * b.z)), fm(a.x, b.y, -(a.y * b.x))};
+}
+static inline float length(f3 v) { return sqrtf(dot(v, v)); }
+// vec_math.h normalize: v * (1.0f / sqrtf(dot(v,v)))
+static inline f3 normalize(f3 v) { float inv = 1.0f / sqrtf(dot(v, v)); return v * inv; }
+static inline float clampf(float x, float a, float b) { return fmaxf(a, fminf(x, b)); }
+static inline float get(const f3& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+// ------------------------------------------------------------------------------------------
+// RNG — SDK/cuda/random.h:30-67 (integer, bit-exact)
+// ------------------------------------------------------------------------------------------
+static inline uint32_t tea4(uint32_t val0, uint32_t val1)
+{
+    uint32_t a = val0, b = val1, sum = 0;
+    for (int round = 0; round < 4; ++round) {
+        sum += 0x9e3779b9u;
+        a += ((b << 4) + 0xa341316cu) ^ (b + sum) ^ ((b >> 5) + 0xc8013ea4u);
+        b += ((a << 4) + 0xad90777du) ^ (a + sum) ^ ((a >> 5) + 0x7e95761eu);
+    }
+    return a;
+}
+static inline uint32_t lcg(uint32_t& state)
+{
+    state = 1664525u * state + 1013904223u;
+    return state & 0x00FFFFFFu;
+}
+static inline float rnd(uint32_t& state) { return (float)lcg(state) / 16777216.0f; }
+
+// ------------------------------------------------------------------------------------------
+// deterministic sin/cos on [0, 2*pi] (arithmetic contract: Cody–Waite reduction by pi/2 in three
+// fma steps + degree-7/8 minimax polynomials, all fma; replaces the reference's fast-math
+// __sinf/__cosf of optixPathTracer.cu:149-159, which has no bit-reproducible CPU counterpart).
+// ------------------------------------------------------------------------------------------
+static inline void det_sincos(float phi, float& s, float& c)
+{
+    const float TWO_OVER_PI = 0.636619772f;
+    const float P1 = 1.5703125f, P2 = 4.837512969970703125e-4f, P3 = 7.54978995489188e-8f;
+    int k = (int)fm(phi, TWO_OVER_PI, 0.5f);
+    float fk = (float)k;
+    float r = fm(-fk, P1, phi);
+    r = fm(-fk, P2, r);
+    r = fm(-fk, P3, r);
+    float z = r * r;
+    float sp = fm(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fm(sp, z, -1.6666654611e-1f);
+    float sr = fm(sp * z, r, r);
+    float cp = fm(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fm(cp, z, 4.166664568298827e-2f);
+    float cr = fm(cp * z, z, fm(-0.5f, z, 1.0f));
+    switch (k & 3) {
+        case 0: s = sr; c = cr; break;
+        case 1: s = cr; c = -sr; break;
+        case 2: s = -sr; c = -cr; break;
+        default: s = -cr; c = sr; break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Rays, triangles, instances
+// ------------------------------------------------------------------------------------------
+struct Tri { f3 v0, v1, v2; };
+
+struct RayPrep {  // per-ray constants of the watertight test
+    f3 o;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+static inline RayPrep prep_ray(f3 o, f3 d)
+{
+    RayPrep r;
+    r.o = o;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz = 0;
+    float m = ax;
+    if (ay > m) { kz = 1; m = ay; }
+    if (az > m) { kz = 2; }
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    if (get(d, kz) < 0.0f) std::swap(kx, ky);
+    r.kx = kx; r.ky = ky; r.kz = kz;
+    r.Sx = get(d, kx) / get(d, kz);
+    r.Sy = get(d, ky) / get(d, kz);
+    r.Sz = 1.0f / get(d, kz);
+    return r;
+}
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013) in the contract's op order.
+// Returns true and (t, b1, b2) if tmin < t < tmax;  b1/b2 weight vertices 1/2 (OptiX convention,
+// SDK/cuda/LocalGeometry.h:94).  `det_sign` gets sign of the determinant (for face culling).
+static inline bool tri_hit(const RayPrep& r, const Tri& tr, float tmin, float tmax, float& t, float& b1, float& b2,
+                           float* det_out = nullptr)
+{
+    const f3 A = tr.v0 - r.o, B = tr.v1 - r.o, C = tr.v2 - r.o;
+    const float Akz = get(A, r.kz), Bkz = get(B, r.kz), Ckz = get(C, r.kz);
+    const float Ax = fm(-r.Sx, Akz, get(A, r.kx)), Ay = fm(-r.Sy, Akz, get(A, r.ky));
+    const float Bx = fm(-r.Sx, Bkz, get(B, r.kx)), By = fm(-r.Sy, Bkz, get(B, r.ky));
+    const float Cx = fm(-r.Sx, Ckz, get(C, r.kx)), Cy = fm(-r.Sy, Ckz, get(C, r.ky));
+    float U = fm(Cx, By, -(Cy * Bx));
+    float V = fm(Ax, Cy, -(Ay * Cx));
+    float W = fm(Bx, Ay, -(By * Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = (U + V) + W;
+    if (det == 0.0f) return false;
+    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    const float T = fm(W, Cz, fm(V, Bz, U * Az));
+    const float tt = T / det;
+    if (!(tt > tmin && tt < tmax)) return false;
+    t = tt;
+    b1 = V / det;
+    b2 = W / det;
+    if (det_out) *det_out = det;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Oracle acceleration structure: median-split binary BVH with deliberately generous box margins,
+// used only to make big scenes finish in seconds.  Because the hit rule is (t, ordinal)-minimal
+// over all triangles, the answer does not depend on this structure; tests cross-check it against
+// brute force.
+// ------------------------------------------------------------------------------------------
+struct BNode { f3 lo, hi; int left, right, first, count; };
+
+struct Geometry {
+    std::vector<Tri> tris;            // object space, ordinal = index
+    std::vector<uint32_t> sbt;        // per-triangle SBT offset (material), may be empty
+    std::vector<BNode> nodes;
+    std::vector<uint32_t> order;      // leaf triangle ordinals
+    bool brute = true;
+    uint64_t node_visits = 0, tri_tests = 0;  // single-thread instrumentation only
+};
+
+static void build_bvh(Geometry& g)
+{
+    const size_t n = g.tris.size();
+    g.nodes.clear();
+    g.order.resize(n);
+    for (size_t i = 0; i < n; ++i) g.order[i] = (uint32_t)i;
+    g.brute = n <= 64;  // default: tiny scenes are traced brute force (the exact definition)
+    if (n == 0) return;
+    std::vector<f3> cen(n), lo(n), hi(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Tri& t = g.tris[i];
+        lo[i] = mk(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)), fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
+        hi[i] = mk(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)), fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
+        cen[i] = (lo[i] + hi[i]) * 0.5f;
+    }
+    g.nodes.reserve(2 * n / 3 + 16);
+    struct Job { int node, first, count; };
+    std::vector<Job> stack;
+    g.nodes.push_back({});
+    stack.push_back({0, 0, (int)n});
+    while (!stack.empty()) {
+        Job j = stack.back();
+        stack.pop_back();
+        f3 blo = mk(INFINITY, INFINITY, INFINITY), bhi = mk(-INFINITY, -INFINITY, -INFINITY);
+        f3 clo = blo, chi = bhi;
+        for (int i = j.first; i < j.first + j.count; ++i) {
+            uint32_t p = g.order[i];
+            blo = mk(fminf(blo.x, lo[p].x), fminf(blo.y, lo[p].y), fminf(blo.z, lo[p].z));
+            bhi = mk(fmaxf(bhi.x, hi[p].x), fmaxf(bhi.y, hi[p].y), fmaxf(bhi.z, hi[p].z));
+            clo = mk(fminf(clo.x, cen[p].x), fminf(clo.y, cen[p].y), fminf(clo.z, cen[p].z));
+            chi = mk(fmaxf(chi.x, cen[p].x), fmaxf(chi.y, cen[p].y), fmaxf(chi.z, cen[p].z));
+        }
+        // generous conservative padding: 1e-4 relative to extent and coordinate magnitude
+        f3 ext = bhi - blo;
+        auto pad = [](float e, float a, float b) { return 1e-4f * (e + fmaxf(fabsf(a), fabsf(b))) + 1e-30f; };
+        f3 pd = mk(pad(ext.x, blo.x, bhi.x), pad(ext.y, blo.y, bhi.y), pad(ext.z, blo.z, bhi.z));
+        BNode& nd = g.nodes[j.node];
+        nd.lo = blo - pd;
+        nd.hi = bhi + pd;
+        nd.first = j.first;
+        nd.count = j.count;
+        nd.left = nd.right = -1;
+        if (j.count <= 4) continue;
+        f3 ce = chi - clo;
+        int axis = ce.x >= ce.y ? (ce.x >= ce.z ? 0 : 2) : (ce.y >= ce.z ? 1 : 2);
+        int mid = j.first + j.count / 2;
+        std::nth_element(g.order.begin() + j.first, g.order.begin() + mid, g.order.begin() + j.first + j.count,
+                         [&](uint32_t a, uint32_t b) {
+                             float ca = get(cen[a], axis), cb = get(cen[b], axis);
+                             return ca < cb || (ca == cb && a < b);
+                         });
+        int l = (int)g.nodes.size();
+        g.nodes.push_back({});
+        g.nodes.push_back({});
+        g.nodes[j.node].left = l;
+        g.nodes[j.node].right = l + 1;
+        g.nodes[j.node].count = 0;
+        stack.push_back({l, j.first, mid - j.first});
+        stack.push_back({l + 1, mid, j.first + j.count - mid});
+    }
+}
+
+struct HitRec { float t; uint32_t prim; float b1, b2; float det; };
+
+static inline bool box_hit(const BNode& n, f3 o, f3 inv, float tmin, float tmax)
+{
+    float t0 = tmin, t1 = tmax;
+    const float lo[3] = {n.lo.x, n.lo.y, n.lo.z}, hi[3] = {n.hi.x, n.hi.y, n.hi.z};
+    const float oo[3] = {o.x, o.y, o.z}, ii[3] = {inv.x, inv.y, inv.z};
+    for (int a = 0; a < 3; ++a) {
+        float ta = (lo[a] - oo[a]) * ii[a], tb = (hi[a] - oo[a]) * ii[a];
+        if (ta != ta || tb != tb) continue;  // 0*inf: origin on a slab plane of a parallel ray -> do not cull
+        float tn = fminf(ta, tb), tf = fmaxf(ta, tb);
+        tn = tn - fabsf(tn) * 1e-4f;
+        tf = tf + fabsf(tf) * 1e-4f;
+        t0 = fmaxf(t0, tn);
+        t1 = fminf(t1, tf);
+    }
+    return t0 <= t1;
+}
+
+// closest hit in one geometry, object space.  `best` carries the current closest (t, prim).
+template <bool ANY, bool STATS>
+static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32_t cull_flags)
+{
+    const RayPrep rp = prep_ray(o, d);
+    bool found = false;
+    auto test = [&](uint32_t p) {
+        float t, b1, b2, det;
+        if (STATS) g.tri_tests++;
+        // strict t < best.t, or equal t with a lower ordinal (order independence)
+        if (tri_hit(rp, g.tris[p], tmin, std::nextafterf(best.t, INFINITY), t, b1, b2, &det)) {
+            if (cull_flags) {
+                // OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1<<4): det<0 is back facing for
+                // counter-clockwise front faces seen along the ray in this formulation.
+                if ((cull_flags & 16u) && det < 0.0f) return;
+                if ((cull_flags & 32u) && det > 0.0f) return;
+            }
+            if (t < best.t || (t == best.t && found && p < best.prim)) {
+                best = {t, p, b1, b2, det};
+                found = true;
+            }
+        }
+    };
+    if (g.brute) {
+        for (uint32_t p = 0; p < g.tris.size(); ++p) {
+            test(p);
+            if (ANY && found) return true;
+        }
+        return found;
+    }
+    const f3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp) {
+        const BNode& n = g.nodes[stack[--sp]];
+        if (STATS) g.node_visits++;
+        if (!box_hit(n, o, inv, tmin, best.t * 1.0001f + 1e-30f)) continue;
+        if (n.left < 0) {
+            for (int i = n.first; i < n.first + n.count; ++i) {
+                test(g.order[i]);
+                if (ANY && found) return true;
+            }
+        } else {
+            stack[sp++] = n.left;
+            stack[sp++] = n.right;
+        }
+    }
+    return found;
+}
+
+// A scene = one geometry, optionally behind one or more instance transforms (IAS of the glTF path,
+// SDK/sutil/Scene.cpp:1134-1212).  Rays are carried into object space with the inverse 3x4 and `t`
+// is shared between spaces (OptiX semantics).
+struct Instance { float m[12]; float inv[12]; int geom; };
+
+struct Scene {
+    std::vector<Geometry> geoms;
+    std::vector<Instance> insts;  // empty => geoms[0] used directly (GAS handle launched directly)
+};
+
+// inverse of an affine 3x4 (row major), fixed op order: adjugate / det, then -Ainv*t
+static void invert34(const float* m, float* inv)
+{
+    const float a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const float c00 = fm(e, i, -(f * h)), c01 = fm(f, g, -(d * i)), c02 = fm(d, h, -(e * g));
+    const float det = fm(c, c02, fm(b, c01, a * c00));
+    const float r = 1.0f / det;
+    inv[0] = c00 * r;                     inv[1] = fm(c, h, -(b * i)) * r;   inv[2] = fm(b, f, -(c * e)) * r;
+    inv[4] = c01 * r;                     inv[5] = fm(a, i, -(c * g)) * r;   inv[6] = fm(c, d, -(a * f)) * r;
+    inv[8] = c02 * r;                     inv[9] = fm(b, g, -(a * h)) * r;   inv[10] = fm(a, e, -(b * d)) * r;
+    const float tx = m[3], ty = m[7], tz = m[11];
+    inv[3]  = -fm(inv[2], tz, fm(inv[1], ty, inv[0] * tx));
+    inv[7]  = -fm(inv[6], tz, fm(inv[5], ty, inv[4] * tx));
+    inv[11] = -fm(inv[10], tz, fm(inv[9], ty, inv[8] * tx));
+}
+static inline f3 xform_point(const float* m, f3 p)
+{
+    return mk(fm(m[2], p.z, fm(m[1], p.y, m[0] * p.x)) + m[3], fm(m[6], p.z, fm(m[5], p.y, m[4] * p.x)) + m[7],
+              fm(m[10], p.z, fm(m[9], p.y, m[8] * p.x)) + m[11]);
+}
+static inline f3 xform_vec(const float* m, f3 v)
+{
+    return mk(fm(m[2], v.z, fm(m[1], v.y, m[0] * v.x)), fm(m[6], v.z, fm(m[5], v.y, m[4] * v.x)),
+              fm(m[10], v.z, fm(m[9], v.y, m[8] * v.x)));
+}
+// normal object->world = transpose(inverse) * n
+static inline f3 xform_normal(const float* inv, f3 n)
+{
+    return mk(fm(inv[8], n.z, fm(inv[4], n.y, inv[0] * n.x)), fm(inv[9], n.z, fm(inv[5], n.y, inv[1] * n.x)),
+              fm(inv[10], n.z, fm(inv[6], n.y, inv[2] * n.x)));
+}
+
+struct SceneHit { float t; uint32_t inst, prim; float b1, b2; bool hit; };
+
+template <bool ANY, bool STATS = false>
+static SceneHit trace_scene(Scene& s, f3 o, f3 d, float tmin, float tmax, uint32_t cull_flags = 0)
+{
+    SceneHit r{tmax, 0xffffffffu, 0xffffffffu, 0.f, 0.f, false};
+    if (s.insts.empty()) {
+        HitRec b{tmax, 0, 0, 0, 0};
+        if (trace_geom<ANY, STATS>(s.geoms[0], o, d, tmin, b, cull_flags)) r = {b.t, 0, b.prim, b.b1, b.b2, true};
+        return r;
+    }
+    for (uint32_t k = 0; k < s.insts.size(); ++k) {
+        const Instance& in = s.insts[k];
+        HitRec b{r.t, 0, 0, 0, 0};
+        // a later instance only wins with strictly smaller t (lower instance index wins ties)
+        if (trace_geom<ANY, STATS>(s.geoms[in.geom], xform_point(in.inv, o), xform_vec(in.inv, d), tmin, b, cull_flags)) {
+            if (b.t < r.t) { r = {b.t, k, b.prim, b.b1, b.b2, true}; if (ANY) return r; }
+        }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// sRGB quantisation — SDK/cuda/helpers.h:36-64 (powf: libm here, fast-math on device => ±1 LSB)
+// ------------------------------------------------------------------------------------------
+static inline float to_srgb1(float c)
+{
+    float powed = powf(c, 1.0f / 2.4f);
+    return c < 0.0031308f ? 12.92f * c : fm(1.055f, powed, -0.055f);
+}
+static inline uint8_t quant8(float x)
+{
+    x = clampf(x, 0.0f, 1.0f);
+    uint32_t q = (uint32_t)(x * 256.0f);
+    return (uint8_t)(q < 255u ? q : 255u);
+}
+static inline void make_color(f3 c, uint8_t* out)
+{
+    out[0] = quant8(to_srgb1(clampf(c.x, 0.f, 1.f)));
+    out[1] = quant8(to_srgb1(clampf(c.y, 0.f, 1.f)));
+    out[2] = quant8(to_srgb1(clampf(c.z, 0.f, 1.f)));
+    out[3] = 255;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cornell path tracer — SDK/optixPathTracer/optixPathTracer.cu:249-413 (mode 0) and
+// SDK/optixMultiGPU/optixMultiGPU.cu:214-385 (mode 1: depth cap 3, no RR, sticky emitted/radiance)
+// ------------------------------------------------------------------------------------------
+struct PTParams {
+    uint32_t subframe_index;
+    int32_t width, height, spl;
+    float eye[3], U[3], V[3], W[3];
+    float light_corner[3], light_v1[3], light_v2[3], light_normal[3], light_emission[3];
+    float bg[3];
+    int32_t nmat;
+    const float* emission;  // nmat*3
+    const float* diffuse;   // nmat*3
+};
+
+struct Onb {
+    f3 t, b, n;
+    explicit Onb(f3 normal)  // optixPathTracer.cu:47-78
+    {
+        n = normal;
+        if (fabsf(n.x) > fabsf(n.z)) b = mk(-n.y, n.x, 0.0f);
+        else b = mk(0.0f, -n.z, n.y);
+        b = normalize(b);
+        t = cross(b, n);
+    }
+    f3 inverse_transform(f3 p) const
+    {
+        return mk(fm(p.z, n.x, fm(p.y, b.x, p.x * t.x)), fm(p.z, n.y, fm(p.y, b.y, p.x * t.y)),
+                  fm(p.z, n.z, fm(p.y, b.z, p.x * t.z)));
+    }
+};
+
+static inline f3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+
+// One pixel of one launch.  Returns the per-launch mean radiance (before the running-mean lerp);
+// counts traced segments (radiance + shadow) into *segs.
+static f3 pt_pixel(Scene& sc, const PTParams& P, int px, int py, int mode, uint64_t* segs)
+{
+    const int w = P.width, h = P.height;
+    const f3 eye = ld3(P.eye), U = ld3(P.U), V = ld3(P.V), W = ld3(P.W);
+    const f3 lc = ld3(P.light_corner), lv1 = ld3(P.light_v1), lv2 = ld3(P.light_v2), ln = ld3(P.light_normal),
+             le = ld3(P.light_emission);
+    uint32_t seed = tea4((uint32_t)(py * w + px), P.subframe_index);
+    f3 result = mk(0, 0, 0);
+    uint64_t nseg = 0;
+    Geometry& g0 = sc.geoms[0];
+    for (int i = 0; i < P.spl; ++i) {
+        const float jx = rnd(seed), jy = rnd(seed);
+        const float dx = fm(2.0f, ((float)px + jx) / (float)w, -1.0f);
+        const float dy = fm(2.0f, ((float)py + jy) / (float)h, -1.0f);
+        f3 dir = normalize(mk(fm(dy, V.x, dx * U.x) + W.x, fm(dy, V.y, dx * U.y) + W.y, fm(dy, V.z, dx * U.z) + W.z));
+        f3 org = eye;
+        f3 att = mk(1, 1, 1), emitted = mk(0, 0, 0), radiance = mk(0, 0, 0);
+        uint32_t pseed = seed;
+        int depth = 0;
+        bool count_emitted = true;
+        for (;;) {
+            SceneHit hit = trace_scene<false>(sc, org, dir, 0.01f, 1e16f);
+            ++nseg;
+            bool done;
+            if (!hit.hit) {  // __miss__radiance
+                radiance = ld3(P.bg);
+                if (mode == 0) emitted = mk(0, 0, 0);  // MultiGPU miss leaves prd.emitted untouched
+                done = true;
+            } else {  // __closesthit__radiance
+                const Tri& tr = g0.tris[hit.prim];
+                const uint32_t mat = g0.sbt.empty() ? 0u : g0.sbt[hit.prim];
+                const f3 N0 = normalize(cross(tr.v1 - tr.v0, tr.v2 - tr.v0));
+                // faceforward(N0, -dir, N0) = N0 * copysignf(1, dot(-dir, N0))
+                const f3 N = N0 * copysignf(1.0f, dot(neg(dir), N0));
+                const f3 Pp = mk(fm(hit.t, dir.x, org.x), fm(hit.t, dir.y, org.y), fm(hit.t, dir.z, org.z));
+                const bool emit_now = (mode == 0) ? (depth == 0) : count_emitted;
+                emitted = emit_now ? ld3(P.emission + 3 * mat) : mk(0, 0, 0);
+                const float z1 = rnd(pseed), z2 = rnd(pseed);
+                float s, c;
+                det_sincos(6.2831855f * z2, s, c);
+                const float r = sqrtf(z1);
+                f3 w_in = mk(r * c, r * s, 0.0f);
+                w_in.z = sqrtf(fmaxf(0.0f, fm(-w_in.y, w_in.y, fm(-w_in.x, w_in.x, 1.0f))));
+                Onb onb(N);
+                const f3 ndir = onb.inverse_transform(w_in);
+                att = att * ld3(P.diffuse + 3 * mat);
+                count_emitted = false;
+                const float l1 = rnd(pseed), l2 = rnd(pseed);
+                const f3 lp = mk(fm(lv2.x, l2, fm(lv1.x, l1, lc.x)), fm(lv2.y, l2, fm(lv1.y, l1, lc.y)),
+                                 fm(lv2.z, l2, fm(lv1.z, l1, lc.z)));
+                const f3 Ld = lp - Pp;
+                const float Ldist = length(Ld);
+                const f3 L = normalize(Ld);
+                const float nDl = dot(N, L);
+                const float LnDl = -dot(ln, L);
+                float weight = 0.0f;
+                if (nDl > 0.0f && LnDl > 0.0f) {
+                    ++nseg;
+                    SceneHit sh = trace_scene<true>(sc, Pp, L, 0.01f, Ldist - 0.01f);
+                    if (!sh.hit) {
+                        const float A = length(cross(lv1, lv2));
+                        weight = ((nDl * LnDl) * A) / ((3.14159265358979323846f * Ldist) * Ldist);
+                    }
+                }
+                if (mode == 0) radiance = le * weight;
+                else radiance = mk(fm(le.x, weight, radiance.x), fm(le.y, weight, radiance.y), fm(le.z, weight, radiance.z));
+                org = Pp;
+                dir = ndir;
+                done = false;
+            }
+            result = result + emitted;
+            result = mk(fm(radiance.x, att.x, result.x), fm(radiance.y, att.y, result.y), fm(radiance.z, att.z, result.z));
+            if (mode == 0) {
+                const float p = dot(att, mk(0.30f, 0.59f, 0.11f));
+                if (done || rnd(pseed) > p) break;
+                att = mk(att.x / p, att.y / p, att.z / p);
+            } else {
+                if (done || depth >= 3) break;
+            }
+            ++depth;
+        }
+    }
+    if (segs) *segs += nseg;
+    const float spl = (float)P.spl;
+    return mk(result.x / spl, result.y / spl, result.z / spl);
+}
+
+template <class F>
+static void parallel_rows(int rows, int threads, F fn)
+{
+    if (threads <= 1) { for (int y = 0; y < rows; ++y) fn(y, 0); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t] { for (int y; (y = next.fetch_add(1)) < rows;) fn(y, t); });
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI (ctypes)
+// ============================================================================================
+extern "C" {
+
+uint32_t orc_tea4(uint32_t v0, uint32_t v1) { return tea4(v0, v1); }
+uint32_t orc_lcg(uint32_t* state) { return lcg(*state); }
+float orc_rnd(uint32_t* state) { return rnd(*state); }
+void orc_sincos(float phi, float* s, float* c) { det_sincos(phi, *s, *c); }
+
+// SDK/sutil/WorkDistribution.h:50-81
+int orc_wd_num_samples(int w, int h, int ngpu)
+{
+    const int sw = 8 * ngpu, sh = 4;
+    const int cols = w / sw + (w % sw ? 1 : 0), rows = h / sh + (h % sh ? 1 : 0);
+    return rows * cols * 32;
+}
+void orc_wd_sample_pixel(int w, int h, int ngpu, int gpu, int sample, int* xy)
+{
+    (void)h;
+    const int sw = 8 * ngpu;
+    const int cols = w / sw + (w % sw ? 1 : 0);
+    const int strip = sample / 32;
+    const int sy = strip / cols, sx = strip - sy * cols;
+    const int in_tile = sample - strip * 32;
+    const int ty = in_tile / 8, tx = in_tile - ty * 8;
+    const int xoff = ((gpu + sy % ngpu) % ngpu) * 8;
+    xy[0] = sx * sw + tx + xoff;
+    xy[1] = sy * 4 + ty;
+}
+
+// SDK/sutil/Camera.cpp:34-46 (m_fod == 1)
+void orc_camera_uvw(const float* eye, const float* lookat, const float* up, float fovy, float aspect, float* uvw)
+{
+    // the reference's host vec_math is compiled by the host compiler without contraction
+    auto hdot = [](f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+    auto hcross = [](f3 a, f3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); };
+    auto hnorm = [&](f3 v) { float inv = 1.0f / sqrtf(hdot(v, v)); return v * inv; };
+    f3 W = (ld3(lookat) - ld3(eye)) * 1.0f;
+    float wlen = sqrtf(hdot(W, W));
+    f3 U = hnorm(hcross(W, ld3(up)));
+    f3 V = hnorm(hcross(U, W));
+    float vlen = wlen * tanf(0.5f * fovy * 3.14159265358979323846f / 180.0f);
+    V = V * vlen;
+    float ulen = vlen * aspect;
+    U = U * ulen;
+    uvw[0] = U.x; uvw[1] = U.y; uvw[2] = U.z; uvw[3] = V.x; uvw[4] = V.y; uvw[5] = V.z; uvw[6] = W.x; uvw[7] = W.y; uvw[8] = W.z;
+}
+
+void orc_make_color(const float* rgb, int n, uint8_t* out)
+{
+    for (int i = 0; i < n; ++i) make_color(ld3(rgb + 3 * i), out + 4 * i);
+}
+
+// ---- scenes ---------------------------------------------------------------------------------
+// verts: ntri*9 floats (object space).  sbt: per-triangle SBT offset or NULL.
+void* orc_scene_create(const float* verts, int64_t ntri, const uint32_t* sbt)
+{
+    Scene* s = new Scene();
+    s->geoms.emplace_back();
+    Geometry& g = s->geoms[0];
+    g.tris.resize((size_t)ntri);
+    for (int64_t i = 0; i < ntri; ++i) {
+        const float* v = verts + 9 * i;
+        g.tris[(size_t)i] = {mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8])};
+    }
+    if (sbt) g.sbt.assign(sbt, sbt + ntri);
+    build_bvh(g);
+    return s;
+}
+// add one instance of geometry 0 with a row-major 3x4 object->world transform
+void orc_scene_add_instance(void* scene, const float* m34)
+{
+    Scene* s = (Scene*)scene;
+    Instance in;
+    memcpy(in.m, m34, sizeof(in.m));
+    invert34(in.m, in.inv);
+    in.geom = 0;
+    s->insts.push_back(in);
+}
+void orc_scene_set_brute(void* scene, int brute)
+{
+    Scene* s = (Scene*)scene;
+    for (auto& g : s->geoms) g.brute = brute != 0 || g.nodes.empty();
+}
+void orc_scene_destroy(void* scene) { delete (Scene*)scene; }
+void orc_invert34(const float* m, float* inv) { invert34(m, inv); }
+
+// rays: n * 8 floats {ox,oy,oz,tmin,dx,dy,dz,tmax} (the reference Ray struct,
+// SDK/optixRaycasting/optixRaycastingKernels.h:35-41).  out: n * {t, prim, inst, b1, b2} as 5 x u32 bit patterns
+// (miss: t = -1, prim = inst = 0xffffffff).  any_hit: out[i*5] = 1/0 only.
+void orc_trace(void* scene, const float* rays, int64_t n, uint32_t* out, int any_hit, uint32_t ray_flags, int threads,
+               uint64_t* stats /* [2] node visits, tri tests (threads==1 only) or NULL */)
+{
+    Scene* s = (Scene*)scene;
+    const int chunk = 4096;
+    const int rows = (int)((n + chunk - 1) / chunk);
+    if (stats) for (auto& g : s->geoms) g.node_visits = g.tri_tests = 0;
+    parallel_rows(rows, stats ? 1 : threads, [&](int row, int) {
+        const int64_t b = (int64_t)row * chunk, e = std::min<int64_t>(n, b + chunk);
+        for (int64_t i = b; i < e; ++i) {
+            const float* r = rays + 8 * i;
+            uint32_t* o = out + 5 * i;
+            f3 org = mk(r[0], r[1], r[2]), dir = mk(r[4], r[5], r[6]);
+            if (any_hit) {
+                SceneHit h = stats ? trace_scene<true, true>(*s, org, dir, r[3], r[7], ray_flags & 0x30u)
+                                   : trace_scene<true, false>(*s, org, dir, r[3], r[7], ray_flags & 0x30u);
+                o[0] = h.hit ? 1u : 0u; o[1] = o[2] = o[3] = o[4] = 0;
+            } else {
+                SceneHit h = stats ? trace_scene<false, true>(*s, org, dir, r[3], r[7], ray_flags & 0x30u)
+                                   : trace_scene<false, false>(*s, org, dir, r[3], r[7], ray_flags & 0x30u);
+                float t = h.hit ? h.t : -1.0f;
+                memcpy(o, &t, 4);
+                o[1] = h.prim; o[2] = h.inst;
+                memcpy(o + 3, &h.b1, 4); memcpy(o + 4, &h.b2, 4);
+            }
+        }
+    });
+    if (stats) { stats[0] = stats[1] = 0; for (auto& g : s->geoms) { stats[0] += g.node_visits; stats[1] += g.tri_tests; } }
+}
+
+// ---- optixRaycasting helpers (SDK/optixRaycasting/optixRaycastingKernels.cu:42-115) ------------
+// host-side scalars exactly as createRaysOrthoOnDevice computes them (host compiler, no contraction)
+void orc_raycast_ortho_scalars(const float* bbmin, const float* bbmax, int width, int height, float padding, float* out5)
+{
+    const float sx = bbmax[0] - bbmin[0], sy = bbmax[1] - bbmin[1], sz = bbmax[2] - bbmin[2];
+    float dx = sx * (1 + 2 * padding) / width;
+    float dy = sy * (1 + 2 * padding) / height;
+    float x0 = bbmin[0] - sx * padding + dx / 2;
+    float y0 = bbmin[1] - sy * padding + dy / 2;
+    float z = bbmin[2] - fmaxf(sz, 1.0f) * .001f;
+    out5[0] = x0; out5[1] = y0; out5[2] = z; out5[3] = dx; out5[4] = dy;
+}
+// device kernel restated: origin = (x0 + ix*dx, y0 + iy*dy, z); nvcc contracts to fma(ix, dx, x0)
+void orc_raycast_create_rays(float* rays, int width, int height, float x0, float y0, float z, float dx, float dy)
+{
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            float* r = rays + 8 * ((size_t)y * width + x);
+            r[0] = fm((float)x, dx, x0); r[1] = fm((float)y, dy, y0); r[2] = z; r[3] = 0.0f;
+            r[4] = 0.0f; r[5] = 0.0f; r[6] = 1.0f; r[7] = 1e34f;
+        }
+}
+void orc_raycast_translate(float* rays, int64_t n, const float* off)
+{
+    for (int64_t i = 0; i < n; ++i) { rays[8 * i] += off[0]; rays[8 * i + 1] += off[1]; rays[8 * i + 2] += off[2]; }
+}
+// Closest hit + the reference's closest-hit program (SDK/optixRaycasting/optixRaycasting.cu:45-86):
+// Hit = {float(unsigned(t)) , N} with N the interpolated shading normal taken object->world and
+// normalised (SDK/cuda/LocalGeometry.h:94-131); miss = {-1,(1,0,0)}.  normals: per-triangle 9 floats
+// (already de-indexed by the caller) or NULL => geometric normal.
+void orc_raycast_hits(void* scene, const float* rays, int64_t n, const float* normals, float* hits /* n*4 */,
+                      uint32_t* ext /* n*5 or NULL */, int threads)
+{
+    Scene* s = (Scene*)scene;
+    std::vector<uint32_t> tmp;
+    if (!ext) { tmp.resize((size_t)n * 5); ext = tmp.data(); }
+    orc_trace(scene, rays, n, ext, 0, 0, threads, nullptr);
+    Geometry& g = s->geoms[0];
+    for (int64_t i = 0; i < n; ++i) {
+        float t; memcpy(&t, ext + 5 * i, 4);
+        float* h = hits + 4 * i;
+        if (t < 0.0f) { h[0] = -1.0f; h[1] = 1.0f; h[2] = 0.0f; h[3] = 0.0f; continue; }
+        const uint32_t prim = ext[5 * i + 1], inst = ext[5 * i + 2];
+        float b1, b2; memcpy(&b1, ext + 5 * i + 3, 4); memcpy(&b2, ext + 5 * i + 4, 4);
+        f3 N;
+        if (normals) {
+            const float* nn = normals + 9 * (size_t)prim;
+            const float b0 = (1.0f - b1) - b2;
+            // (1-b1-b2)*N0 + b1*N1 + b2*N2 with nvcc's contraction: fma(b2,N2, fma(b1,N1, b0*N0))
+            N = mk(fm(b2, nn[6], fm(b1, nn[3], b0 * nn[0])), fm(b2, nn[7], fm(b1, nn[4], b0 * nn[1])),
+                   fm(b2, nn[8], fm(b1, nn[5], b0 * nn[2])));
+        } else {
+            const Tri& tr = g.tris[prim];
+            N = cross(tr.v1 - tr.v0, tr.v2 - tr.v0);
+        }
+        if (!s->insts.empty()) N = xform_normal(s->insts[inst].inv, N);
+        N = normalize(N);
+        h[0] = (float)(unsigned int)t;  // the `const unsigned int t = optixGetRayTmax()` quirk
+        h[1] = N.x; h[2] = N.y; h[3] = N.z;
+    }
+}
+// shadeHitsKernel: 0.5*N + 0.5 (contracted: fma(0.5,N,0.5)), background 0.2
+void orc_raycast_shade(const float* hits, int64_t n, float* image /* n*3 */)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const float* h = hits + 4 * i;
+        float* o = image + 3 * i;
+        if (h[0] < 0.0f) { o[0] = o[1] = o[2] = 0.2f; }
+        else { o[0] = fm(0.5f, h[1], 0.5f); o[1] = fm(0.5f, h[2], 0.5f); o[2] = fm(0.5f, h[3], 0.5f); }
+    }
+}
+
+// ---- Cornell path tracer -----------------------------------------------------------------------
+struct orc_pt_params {
+    uint32_t subframe_index;
+    int32_t width, height, samples_per_launch;
+    float eye[3], U[3], V[3], W[3];
+    float light_corner[3], light_v1[3], light_v2[3], light_normal[3], light_emission[3];
+    float bg[3];
+    int32_t nmat;
+    int32_t mode;  // 0 = optixPathTracer (Russian roulette), 1 = optixMultiGPU (depth cap 3)
+};
+// Renders rows [y0,y1) x columns [x0,x1).  accum: width*height*4 floats, read for the running mean
+// when subframe_index > 0 and written (optixPathTracer.cu:310-319); frame: width*height*4 bytes.
+// Returns the number of traced segments.
+uint64_t orc_pathtrace(void* scene, const orc_pt_params* p, const float* emission, const float* diffuse, float* accum,
+                       uint8_t* frame, int x0, int y0, int x1, int y1, int threads)
+{
+    Scene* s = (Scene*)scene;
+    PTParams P;
+    P.subframe_index = p->subframe_index; P.width = p->width; P.height = p->height; P.spl = p->samples_per_launch;
+    memcpy(P.eye, p->eye, 12); memcpy(P.U, p->U, 12); memcpy(P.V, p->V, 12); memcpy(P.W, p->W, 12);
+    memcpy(P.light_corner, p->light_corner, 12); memcpy(P.light_v1, p->light_v1, 12); memcpy(P.light_v2, p->light_v2, 12);
+    memcpy(P.light_normal, p->light_normal, 12); memcpy(P.light_emission, p->light_emission, 12); memcpy(P.bg, p->bg, 12);
+    P.nmat = p->nmat; P.emission = emission; P.diffuse = diffuse;
+    const int T = std::max(1, threads);
+    std::vector<uint64_t> segs((size_t)T, 0);
+    parallel_rows(y1 - y0, T, [&](int row, int tid) {
+        const int y = y0 + row;
+        for (int x = x0; x < x1; ++x) {
+            f3 c = pt_pixel(*s, P, x, y, p->mode, &segs[(size_t)tid]);
+            const size_t idx = (size_t)y * P.width + x;
+            if (P.subframe_index > 0) {
+                const float a = 1.0f / (float)(P.subframe_index + 1);
+                const f3 prev = ld3(accum + 4 * idx);
+                // lerp(a,b,t) = a + t*(b-a)  -> fma(t, b-a, a)
+                c = mk(fm(a, c.x - prev.x, prev.x), fm(a, c.y - prev.y, prev.y), fm(a, c.z - prev.z, prev.z));
+            }
+            accum[4 * idx] = c.x; accum[4 * idx + 1] = c.y; accum[4 * idx + 2] = c.z; accum[4 * idx + 3] = 1.0f;
+            if (frame) make_color(c, frame + 4 * idx);
+        }
+    });
+    uint64_t tot = 0;
+    for (auto v : segs) tot += v;
+    return tot;
+}
+
+}  // extern "C"

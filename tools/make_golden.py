@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/kat.json from the REFERENCE's own code (oracle/_ref/libref_shim.so,
+built by oracle/Makefile from headers under /root/reference, compiled in place).
+
+Run in the build container only (needs /root/reference).  The JSON is committed; the GPU box and
+the CPU test-suite read the JSON, never the reference.  Floats are stored as uint32 bit patterns so
+the comparison is bit-exact.
+"""
+import ctypes, json, pathlib, random, struct, subprocess, sys
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "ref"])
+ref = ctypes.CDLL(str(ROOT / "oracle" / "_ref" / "libref_shim.so"))
+ref.ref_tea4.restype = ctypes.c_uint
+ref.ref_tea4.argtypes = [ctypes.c_uint, ctypes.c_uint]
+ref.ref_lcg.restype = ctypes.c_uint
+ref.ref_lcg.argtypes = [ctypes.POINTER(ctypes.c_uint)]
+ref.ref_rnd.restype = ctypes.c_float
+ref.ref_rnd.argtypes = [ctypes.POINTER(ctypes.c_uint)]
+ref.ref_wd_num_samples.restype = ctypes.c_int
+
+def fbits(x):
+    return struct.unpack("<I", struct.pack("<f", x))[0]
+
+def main():
+    rng = random.Random(20261018)
+    out = {"generator": "tools/make_golden.py via oracle/_ref/libref_shim.so",
+           "sources": ["SDK/cuda/random.h:30-67", "SDK/sutil/WorkDistribution.h:50-81",
+                       "SDK/sutil/Camera.cpp:34-46", "SDK/optixPathTracer/optixPathTracer.cpp:439"]}
+    # --- tea<4> + rnd streams
+    pairs = [(0, 0), (1, 0), (0, 1), (589823, 0), (12345, 7), (589823, 15), (0xFFFFFFFF, 0xFFFFFFFF)]
+    pairs += [(rng.randrange(1 << 32), rng.randrange(1 << 16)) for _ in range(57)]
+    tea = []
+    for v0, v1 in pairs:
+        seed = ref.ref_tea4(v0, v1)
+        st = ctypes.c_uint(seed)
+        draws = [fbits(ref.ref_rnd(ctypes.byref(st))) for _ in range(8)]
+        tea.append({"v0": v0, "v1": v1, "seed": seed, "rnd_bits": draws, "state_after": st.value})
+    out["tea4_rnd"] = tea
+    st = ctypes.c_uint(0)
+    out["lcg_from_0"] = [[ref.ref_lcg(ctypes.byref(st)), st.value] for _ in range(16)]
+    # --- StaticWorkDistribution
+    wd = []
+    for (w, h) in [(768, 768), (3840, 2160), (1920, 1080), (100, 37), (1, 1), (1040, 968)]:
+        for n in (1, 2, 3, 4, 8):
+            for gpu in sorted({0, n // 2, n - 1}):
+                ns = ref.ref_wd_num_samples(w, h, n, gpu)
+                samples = sorted({0, 1, 31, 32, 33, 1000 % ns, ns // 2, ns - 1} | {rng.randrange(ns) for _ in range(8)})
+                pix = []
+                for s in samples:
+                    xy = (ctypes.c_int * 2)()
+                    ref.ref_wd_sample_pixel(w, h, n, gpu, s, xy)
+                    pix.append([s, xy[0], xy[1]])
+                wd.append({"w": w, "h": h, "ngpu": n, "gpu": gpu, "num_samples": ns, "pixels": pix})
+    out["work_distribution"] = wd
+    # --- Camera::UVWFrame
+    cams = [([278.0, 273.0, -900.0], [278.0, 273.0, 330.0], [0.0, 1.0, 0.0], 35.0, 1.0),
+            ([278.0, 273.0, -900.0], [278.0, 273.0, 330.0], [0.0, 1.0, 0.0], 35.0, 3840.0 / 2160.0),
+            ([0.0, 1.0, -10.0], [0.0, 0.1, 0.0], [0.0, 1.0, 0.00000073], 45.0, 1920.0 / 1080.0),
+            ([1.5, 2.5, 3.5], [-0.25, 0.75, 0.1], [0.1, 0.9, 0.2], 60.0, 1.25)]
+    cam_out = []
+    for eye, lookat, up, fov, asp in cams:
+        f3 = ctypes.c_float * 3
+        uvw = (ctypes.c_float * 9)()
+        ref.ref_camera_uvw(f3(*eye), f3(*lookat), f3(*up), ctypes.c_float(fov), ctypes.c_float(asp), uvw)
+        cam_out.append({"eye": eye, "lookat": lookat, "up": up, "fov_y": fov, "aspect_bits": fbits(asp),
+                        "uvw_bits": [fbits(x) for x in uvw]})
+    out["camera_uvw"] = cam_out
+    n = (ctypes.c_float * 3)()
+    f3 = ctypes.c_float * 3
+    ref.ref_light_normal(f3(0.0, 0.0, 105.0), f3(-130.0, 0.0, 0.0), n)
+    out["cornell_light_normal_bits"] = [fbits(x) for x in n]
+    p = ROOT / "tests" / "golden" / "kat.json"
+    p.write_text(json.dumps(out) + "\n")
+    print("wrote", p, p.stat().st_size, "bytes")
+
+if __name__ == "__main__":
+    sys.exit(main())
