@@ -1,0 +1,303 @@
+/*
+ * b200rt.h — C ABI of libb200rt.so, the B200-native (sm_100a) replacement for the OptiX launch
+ * behind the optixPathTracer / optixMultiGPU / optixRaycasting samples of awegsche/OptiX_Raytracer.
+ *
+ * Every entry point replaces one call the reference makes through the OptiX function table
+ * (reference include/optix_stubs.h:198-229, include/optix_function_table.h:46-343); the reference
+ * call site is cited at each declaration.  Conventions follow the reference boundary:
+ *   - plain pointers and sizes only; device addresses are passed as uint64_t (CUdeviceptr);
+ *   - every function returns an int that is an OptixResult-compatible code (0 = success,
+ *     7001 invalid value, 7003 invalid operation, 7050 launch failure, 7800 not supported,
+ *     7900 CUDA error); no exception crosses the ABI (reference: OPTIX_CHECK, SDK/sutil/Exception.h:82-112);
+ *   - the caller owns every device buffer it passes in (vertices, temp, output, SBT, params, frame /
+ *     accum buffers); the library owns only its context and the per-context wavefront workspace;
+ *   - launches and builds are asynchronous on the given CUDA stream unless stated otherwise; the
+ *     caller synchronises (reference: CUDA_SYNC_CHECK after optixLaunch).
+ * There is no CPU path: every compute entry point fails with 7900 if no CUDA device is usable.
+ *
+ * Struct layouts marked "layout == Optix..." are field-for-field identical to the OptiX 8.0 type
+ * named (sizes asserted in csrc/api.cpp), so a reference host can pass its own structs by cast.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RT_SUCCESS 0
+#define B200RT_ERROR_INVALID_VALUE 7001
+#define B200RT_ERROR_HOST_OUT_OF_MEMORY 7002
+#define B200RT_ERROR_INVALID_OPERATION 7003
+#define B200RT_ERROR_LAUNCH_FAILURE 7050
+#define B200RT_ERROR_INVALID_DEVICE_CONTEXT 7051
+#define B200RT_ERROR_NOT_SUPPORTED 7800
+#define B200RT_ERROR_CUDA_ERROR 7900
+
+/* constants of reference include/optix_types.h:79-88 */
+#define B200RT_SBT_RECORD_HEADER_SIZE 32
+#define B200RT_SBT_RECORD_ALIGNMENT 16
+#define B200RT_ACCEL_BUFFER_BYTE_ALIGNMENT 128
+#define B200RT_INSTANCE_BYTE_ALIGNMENT 16
+
+/* enum values of reference include/optix_types.h:345-368,1014-1024,1293-1295,1376-1379 */
+#define B200RT_BUILD_INPUT_TYPE_TRIANGLES 0x2141
+#define B200RT_BUILD_INPUT_TYPE_INSTANCES 0x2143
+#define B200RT_VERTEX_FORMAT_FLOAT3 0x2121
+#define B200RT_INDICES_FORMAT_NONE 0
+#define B200RT_INDICES_FORMAT_UNSIGNED_SHORT3 0x2102
+#define B200RT_INDICES_FORMAT_UNSIGNED_INT3 0x2103
+#define B200RT_TRANSFORM_FORMAT_NONE 0
+#define B200RT_TRANSFORM_FORMAT_MATRIX_FLOAT12 0x21E1
+#define B200RT_BUILD_OPERATION_BUILD 0x2161
+#define B200RT_PROPERTY_TYPE_COMPACTED_SIZE 0x2181
+#define B200RT_BUILD_FLAG_ALLOW_COMPACTION (1u << 1)
+/* ray flags, reference include/optix_types.h:1794-1840 */
+#define B200RT_RAY_FLAG_NONE 0u
+#define B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT (1u << 2)
+#define B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1u << 4)
+#define B200RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES (1u << 5)
+
+typedef struct b200rt_context_t* b200rt_context;
+typedef uint64_t b200rt_deviceptr;         /* CUdeviceptr */
+typedef uint64_t b200rt_traversable;       /* OptixTraversableHandle: device address of the accel blob */
+typedef void* b200rt_stream;               /* cudaStream_t / CUstream */
+typedef void (*b200rt_log_cb)(unsigned int level, const char* tag, const char* message, void* cbdata);
+
+/* layout == OptixBuildInputTriangleArray (reference include/optix_types.h:632-705); the two micromap
+ * members at the tail are opaque padding here (unused on this path). */
+typedef struct b200rt_build_input_triangle_array {
+    const b200rt_deviceptr* vertexBuffers; /* host array of device pointers; [0] is used (no motion) */
+    unsigned int numVertices;
+    unsigned int vertexFormat;             /* B200RT_VERTEX_FORMAT_FLOAT3 */
+    unsigned int vertexStrideInBytes;      /* 0 => 12 */
+    b200rt_deviceptr indexBuffer;          /* 0 => unindexed */
+    unsigned int numIndexTriplets;
+    unsigned int indexFormat;
+    unsigned int indexStrideInBytes;       /* 0 => 3 * index size */
+    b200rt_deviceptr preTransform;         /* device 3x4 row-major float matrix or 0 */
+    const unsigned int* flags;             /* host array, one per SBT record (geometry flags) */
+    unsigned int numSbtRecords;
+    b200rt_deviceptr sbtIndexOffsetBuffer; /* per-primitive local SBT index, or 0 */
+    unsigned int sbtIndexOffsetSizeInBytes;   /* 1, 2 or 4 */
+    unsigned int sbtIndexOffsetStrideInBytes; /* 0 => size */
+    unsigned int primitiveIndexOffset;
+    unsigned int transformFormat;
+    char opaque_micromaps[240 - 96];
+} b200rt_build_input_triangle_array;
+
+/* layout == OptixBuildInputInstanceArray (reference include/optix_types.h:970-988) */
+typedef struct b200rt_build_input_instance_array {
+    b200rt_deviceptr instances;            /* device array of b200rt_instance (== OptixInstance, 80 B) */
+    unsigned int numInstances;
+    unsigned int instanceStride;           /* 0 => 80 */
+} b200rt_build_input_instance_array;
+
+/* layout == OptixBuildInput (reference include/optix_types.h:1032-1051), 1032 bytes */
+typedef struct b200rt_build_input {
+    unsigned int type;
+    union {
+        b200rt_build_input_triangle_array triangleArray;
+        b200rt_build_input_instance_array instanceArray;
+        char pad[1024];
+    };
+} b200rt_build_input;
+
+/* layout == OptixInstance (reference include/optix_types.h:1122-1147), 80 bytes */
+typedef struct b200rt_instance {
+    float transform[12];                   /* object->world, 3x4 row major */
+    unsigned int instanceId;
+    unsigned int sbtOffset;
+    unsigned int visibilityMask;
+    unsigned int flags;
+    b200rt_traversable traversableHandle;
+    unsigned int pad[2];
+} b200rt_instance;
+
+/* layout == OptixAccelBuildOptions (reference include/optix_types.h:1331-1346), 20 bytes */
+typedef struct b200rt_accel_build_options {
+    unsigned int buildFlags;
+    unsigned int operation;
+    struct { unsigned short numKeys, flags; float timeBegin, timeEnd; } motionOptions;
+} b200rt_accel_build_options;
+
+/* layout == OptixAccelBufferSizes (reference include/optix_types.h:1353-1368) */
+typedef struct b200rt_accel_buffer_sizes {
+    size_t outputSizeInBytes;
+    size_t tempSizeInBytes;
+    size_t tempUpdateSizeInBytes;
+} b200rt_accel_buffer_sizes;
+
+/* layout == OptixAccelEmitDesc (reference include/optix_types.h:1385-1392) */
+typedef struct b200rt_accel_emit_desc {
+    b200rt_deviceptr result;               /* device address that receives a size_t */
+    unsigned int type;                     /* B200RT_PROPERTY_TYPE_COMPACTED_SIZE */
+} b200rt_accel_emit_desc;
+
+/* layout == OptixShaderBindingTable (reference include/optix_types.h:2293-2328), 64 bytes */
+typedef struct b200rt_shader_binding_table {
+    b200rt_deviceptr raygenRecord;
+    b200rt_deviceptr exceptionRecord;
+    b200rt_deviceptr missRecordBase;
+    unsigned int missRecordStrideInBytes;
+    unsigned int missRecordCount;
+    b200rt_deviceptr hitgroupRecordBase;
+    unsigned int hitgroupRecordStrideInBytes;
+    unsigned int hitgroupRecordCount;
+    b200rt_deviceptr callablesRecordBase;
+    unsigned int callablesRecordStrideInBytes;
+    unsigned int callablesRecordCount;
+} b200rt_shader_binding_table;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context.  Replaces cudaFree(0) + optixInit + optixDeviceContextCreate/Destroy
+ * (reference SDK/optixPathTracer/optixPathTracer.cpp:555-573, SDK/sutil/Scene.cpp:800-815).
+ * log level / callback signature as OptixDeviceContextOptions (level 0 = off ... 4 = print).
+ * ------------------------------------------------------------------------------------------- */
+int b200rt_context_create(int cuda_device, b200rt_log_cb cb, void* cbdata, int level, b200rt_context* out);
+int b200rt_context_destroy(b200rt_context ctx);
+const char* b200rt_error_string(int code);     /* optixGetErrorString */
+const char* b200rt_error_name(int code);       /* optixGetErrorName */
+const char* b200rt_last_error_message(b200rt_context ctx); /* detail text of the last failure on this context */
+const char* b200rt_version(void);
+uint64_t b200rt_context_kernel_launches(b200rt_context ctx); /* kernels launched so far through this context */
+
+/* ---------------------------------------------------------------------------------------------
+ * Acceleration structures.  Replace optixAccelComputeMemoryUsage / optixAccelBuild /
+ * optixAccelCompact (reference SDK/optixPathTracer/optixPathTracer.cpp:627-684,
+ * SDK/sutil/Scene.cpp:970,1043-1054,1106,1195, SDK/imgui_test/triangle_gas.cpp:213-234).
+ * Triangle inputs give a GAS (all inputs of one call in one structure, SBT offsets accumulate over
+ * inputs like OptiX); one instance input gives an IAS over previously built GAS handles.
+ * outputBuffer must be 128-byte aligned; the returned handle is valid as long as outputBuffer is,
+ * and does not reference tempBuffer or the vertex/index buffers after the build has run on `stream`.
+ * The build records the exact size; emitted COMPACTED_SIZE properties are written on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+int b200rt_accel_compute_memory_usage(b200rt_context ctx, const b200rt_accel_build_options* options,
+                                      const b200rt_build_input* inputs, unsigned int num_inputs,
+                                      b200rt_accel_buffer_sizes* sizes);
+int b200rt_accel_build(b200rt_context ctx, b200rt_stream stream, const b200rt_accel_build_options* options,
+                       const b200rt_build_input* inputs, unsigned int num_inputs, b200rt_deviceptr temp_buffer,
+                       size_t temp_bytes, b200rt_deviceptr output_buffer, size_t output_bytes,
+                       b200rt_traversable* handle, const b200rt_accel_emit_desc* emitted, unsigned int num_emitted);
+int b200rt_accel_compact(b200rt_context ctx, b200rt_stream stream, b200rt_traversable input,
+                         b200rt_deviceptr output_buffer, size_t output_bytes, b200rt_traversable* handle);
+
+/* Introspection used by tests / bench (no OptiX equivalent): synchronous. */
+typedef struct b200rt_accel_info {
+    uint32_t kind;            /* 1 = GAS, 2 = IAS */
+    uint32_t num_triangles;
+    uint32_t num_nodes;       /* 8-wide nodes */
+    uint32_t num_instances;
+    uint64_t total_bytes;     /* exact (compacted) size */
+    float bounds[6];          /* object-space (GAS) / world-space (IAS) AABB */
+    uint32_t depth;           /* levels of the wide tree */
+    uint32_t reserved;
+} b200rt_accel_info;
+int b200rt_accel_get_info(b200rt_context ctx, b200rt_traversable handle, b200rt_accel_info* info);
+
+/* ---------------------------------------------------------------------------------------------
+ * optixPathTracer launch.  Replaces
+ *   optixLaunch(pipeline, stream, d_params, sizeof(Params), &sbt, width, height, 1)
+ * (reference SDK/optixPathTracer/optixPathTracer.cpp:488-511) together with the device programs
+ * __raygen__rg / __miss__radiance / __closesthit__radiance (SDK/optixPathTracer/optixPathTracer.cu:249-413).
+ * d_params: device copy of the reference's 152-byte Params (SDK/optixPathTracer/optixPathTracer.h:82-107);
+ * sbt: host struct whose records live on the device — miss record data = MissData{float4 bg_color},
+ * hit-group record data = HitGroupData{float3 emission_color; float3 diffuse_color; float4* vertices}
+ * (optixPathTracer.h:115-126), one record per material, selected by the per-primitive SBT index given to
+ * the accel build.  width/height are the launch dimensions.
+ * ------------------------------------------------------------------------------------------- */
+#define B200RT_PT_TERMINATE_RUSSIAN_ROULETTE 0 /* optixPathTracer.cu:294-297 */
+#define B200RT_PT_TERMINATE_DEPTH_CAP 1        /* optixMultiGPU.cu:271 */
+typedef struct b200rt_pt_stats {
+    uint64_t radiance_segments;  /* closest-hit rays traced */
+    uint64_t shadow_segments;    /* occlusion rays traced */
+    uint32_t iterations;         /* wavefront iterations (trace+shade pairs) */
+    uint32_t kernel_launches;    /* kernels launched by this call */
+} b200rt_pt_stats;
+typedef struct b200rt_pt_options {
+    uint32_t reserved0;
+    uint32_t collect_stats;      /* 1: fill *stats (synchronises the stream at the end of the launch) */
+    b200rt_pt_stats* stats;      /* host pointer or NULL */
+} b200rt_pt_options;
+int b200rt_launch_pathtracer(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
+                             const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height,
+                             const b200rt_pt_options* options);
+
+/* optixMultiGPU launch: optixLaunch(pipeline, stream, d_params, sizeof(Params)=168, &sbt, num_samples, 1, 1)
+ * (reference SDK/optixMultiGPU/optixMultiGPU.cpp:562-594) + programs of SDK/optixMultiGPU/optixMultiGPU.cu:214-385.
+ * d_params: device copy of the 168-byte Params (SDK/optixMultiGPU/optixMultiGPU.h:46-64); the pixel of sample i is
+ * params.sample_index_buffer[i] (int2).  SBT: 2 miss records, 2 hit-group records per material (even = radiance). */
+int b200rt_launch_multigpu(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
+                           const b200rt_shader_binding_table* sbt, unsigned int num_samples,
+                           const b200rt_pt_options* options);
+
+/* fillSamplesCUDA (reference SDK/optixMultiGPU/optixMultiGPU_kernels.cu:31-55): sample_indices[i] =
+ * StaticWorkDistribution(width,height,num_gpus).getSamplePixel(gpu_idx, i) as int2. */
+int b200rt_fill_samples(b200rt_context ctx, b200rt_stream stream, int gpu_idx, int num_gpus, int width, int height,
+                        b200rt_deviceptr sample_indices_int2, int num_samples);
+
+/* De-interleave after a gather (new; replaces the zero-copy writes of SDK/sutil/CUDAOutputBuffer.h:203-216):
+ * gathered = num_gpus consecutive blocks of num_samples float4 (rank-major, as ncclAllGather lays them out);
+ * writes accum (float4, width*height, may be 0) and frame (uchar4, make_color) in pixel order. */
+int b200rt_deinterleave(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr gathered_float4, int num_gpus,
+                        int num_samples, int width, int height, b200rt_deviceptr accum_float4,
+                        b200rt_deviceptr frame_uchar4);
+
+/* ---------------------------------------------------------------------------------------------
+ * optixRaycasting.  b200rt_launch_raycast replaces
+ *   optixLaunch(pipeline, stream, d_params, sizeof(Params)=24, &sbt, width, height, 1)
+ * (reference SDK/optixRaycasting/optixRaycasting.cpp:289-317) + __raygen__from_buffer /
+ * __miss__buffer_miss / __closesthit__buffer_hit (SDK/optixRaycasting/optixRaycasting.cu:45-86).
+ * d_params: device copy of {handle, Ray* rays, Hit* hits}; Ray = {float3 origin; float tmin; float3 dir;
+ * float tmax} (32 B), Hit = {float t; float3 geom_normal} (16 B) (optixRaycastingKernels.h:35-47).
+ * SBT hit-group record data = whitted::HitGroupData (352 B, SDK/cuda/whitted.h:44-48): the triangle-mesh
+ * BufferViews of its GeometryData are read for the shading normal (SDK/cuda/LocalGeometry.h:59-176).
+ * ext_hits (optional, 0 = none): n x {float t; uint32 prim; uint32 inst; float b1; float b2} with the
+ * un-truncated t, build-input-local primitive index, instance index, and OptiX barycentrics; miss: t=-1.
+ * ------------------------------------------------------------------------------------------- */
+int b200rt_launch_raycast(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
+                          const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height,
+                          b200rt_deviceptr ext_hits);
+/* createRaysOrthoOnDevice / translateRaysOnDevice / shadeHitsOnDevice
+ * (reference SDK/optixRaycasting/optixRaycastingKernels.cu:42-115); stream-ordered on `stream`. */
+int b200rt_create_rays_ortho(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr rays, int width, int height,
+                             const float bbmin[3], const float bbmax[3], float padding);
+int b200rt_translate_rays(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr rays, int count,
+                          const float offset[3]);
+int b200rt_shade_hits(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr image_float3, int count,
+                      b200rt_deviceptr hits);
+
+/* Generic ray queries over a traversable (the optixTrace semantics the launches are built from; used by the
+ * parity tests).  rays: n x Ray (32 B).  closest: ext hit records (20 B, as above).  any: n x uint32 (1 = occluded). */
+int b200rt_trace_closest(b200rt_context ctx, b200rt_stream stream, b200rt_traversable handle, b200rt_deviceptr rays,
+                         uint64_t n, unsigned int ray_flags, b200rt_deviceptr ext_hits);
+int b200rt_trace_any(b200rt_context ctx, b200rt_stream stream, b200rt_traversable handle, b200rt_deviceptr rays,
+                     uint64_t n, unsigned int ray_flags, b200rt_deviceptr occluded_u32);
+/* Instrumented closest-hit pass (not for timing): totals of 8-wide nodes fetched and triangles tested. */
+int b200rt_trace_stats(b200rt_context ctx, b200rt_stream stream, b200rt_traversable handle, b200rt_deviceptr rays,
+                       uint64_t n, uint64_t* nodes_fetched, uint64_t* tris_tested);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side sutil mirrors (pure host arithmetic, same results as the reference's host code).
+ * ------------------------------------------------------------------------------------------- */
+/* sutil::Camera::UVWFrame (reference SDK/sutil/Camera.cpp:34-46) */
+void b200rt_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fov_y_deg,
+                       float aspect, float U[3], float V[3], float W[3]);
+/* StaticWorkDistribution (reference SDK/sutil/WorkDistribution.h:50-81) */
+int b200rt_wd_num_samples(int width, int height, int num_gpus);
+void b200rt_wd_sample_pixel(int width, int height, int num_gpus, int gpu_idx, int sample_idx, int xy[2]);
+
+/* Procedural tessellated mesh for the synthetic multi-GPU configuration (BASELINE.json configs[4]; the
+ * reference has no such asset — SURVEY.md §8(d) C5).  Writes num_triangles*3 float4 vertices (w = 0), the
+ * layout optixPathTracer's HitGroupData::vertices uses, and num_triangles uint32 material indices. */
+int b200rt_generate_synthetic_mesh(b200rt_context ctx, b200rt_stream stream, uint64_t num_triangles, uint32_t seed,
+                                   b200rt_deviceptr vertices_float4, b200rt_deviceptr mat_indices_u32,
+                                   float bounds_out[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

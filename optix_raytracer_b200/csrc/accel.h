@@ -1,0 +1,60 @@
+// accel.h — in-memory layout of the acceleration-structure blob that lives in the caller's
+// outputBuffer (the opaque bytes optixAccelBuild writes in the reference,
+// SDK/optixPathTracer/optixPathTracer.cpp:650-664).  All offsets are relative to the blob base so
+// b200rt_accel_compact can move it (optixPathTracer.cpp:671-683).
+//
+//   GAS:  [AccelHeader 128 B][Node8 x num_nodes (80 B each)][TriRecord x num_tris (48 B each)]
+//   IAS:  [AccelHeader 128 B][InstanceRecord x num_instances (128 B each)]
+//
+// Node8 is an 8-wide BVH node with child boxes quantised to 8 bits on a per-node power-of-two grid
+// (compressed wide BVH, Ylitie/Karras/Laine 2017), fetched as 5 x 16-byte loads.  TriRecord is
+// three float4: the xyz are the object-space vertices exactly as supplied (the watertight test runs
+// on them, so results do not depend on the BVH), the w lanes carry the primitive index, SBT
+// offset | geometry flags, and the GAS-global ordinal used for tie-breaking.
+#pragma once
+#include <stdint.h>
+
+namespace b200rt {
+
+constexpr uint32_t ACCEL_MAGIC = 0x54523242u;  // "B2RT"
+constexpr uint32_t ACCEL_KIND_GAS = 1, ACCEL_KIND_IAS = 2;
+constexpr uint32_t NODE8_BYTES = 80, TRI_BYTES = 48, INSTREC_BYTES = 128, HEADER_BYTES = 128;
+
+struct AccelHeader {
+    uint32_t magic;
+    uint32_t kind;
+    uint32_t num_tris;
+    uint32_t num_nodes;      // written by the builder on the device
+    uint64_t nodes_off;
+    uint64_t tris_off;
+    uint64_t total_bytes;    // exact size after compaction
+    float bounds[6];         // lo xyz, hi xyz
+    uint32_t num_instances;
+    uint32_t depth;
+    uint64_t inst_off;
+    uint32_t max_nodes;      // node capacity of this (uncompacted) blob
+    uint32_t error;          // builder overflow flag
+    uint32_t pad[10];
+};
+static_assert(sizeof(AccelHeader) == HEADER_BYTES, "header must be 128 bytes");
+
+struct InstanceRecord {
+    float m[12];             // object -> world
+    float inv[12];           // world -> object
+    uint64_t gas;            // device address of the GAS blob
+    uint32_t instance_id;
+    uint32_t sbt_offset;
+    uint32_t mask;
+    uint32_t flags;
+    float wbounds[2];        // unused padding to 128 B
+};
+static_assert(sizeof(InstanceRecord) == INSTREC_BYTES, "instance record must be 128 bytes");
+
+// TriRecord w-lane packing
+constexpr uint32_t TRI_SBT_MASK = 0x00ffffffu;   // v1.w low 24 bits: GAS-local SBT index
+constexpr uint32_t TRI_FLAG_SHIFT = 24;          // v1.w high 8 bits: OptixGeometryFlags of its SBT record
+
+// extended hit record of the C ABI (b200rt.h): {t, prim, inst, b1, b2}
+struct ExtHit { float t; uint32_t prim; uint32_t inst; float b1; float b2; };
+
+}  // namespace b200rt

@@ -1,0 +1,984 @@
+// bvh_build.cu — acceleration-structure build on the GPU (sm_100a), replacing the closed
+// optixAccelComputeMemoryUsage / optixAccelBuild / optixAccelCompact the reference calls at
+// SDK/optixPathTracer/optixPathTracer.cpp:627-684, SDK/sutil/Scene.cpp:970,1043-1054,1106,1195 and
+// SDK/imgui_test/triangle_gas.cpp:213-234.
+//
+// Pipeline (all kernels hand written, no CUB/Thrust):
+//   1 gather      build inputs (strided float3 vertices, optional u16/u32 indices, optional 3x4
+//                 pre-transform, per-primitive SBT index) -> 48-byte triangle records + scene bounds
+//   2 morton      centroid -> 30/48/63-bit Morton key
+//   3 radix sort  LSD, 8-bit digits, stable (per-block histogram -> scan -> ranked scatter)
+//   4 hierarchy   Karras 2012 binary radix tree over the sorted keys (ties broken by position)
+//   5 refit       bottom-up AABBs with one atomic arrival counter per internal node
+//   6 collapse    level-synchronous, deterministic conversion to the 8-wide quantised layout of
+//                 accel.h (greedy surface-area expansion, octant-aware slot assignment, conservative
+//                 8-bit boxes), then the triangle records are written in leaf order
+// The blob is self-contained: nothing in it points into the temp or input buffers.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "accel.h"
+#include "common.h"
+#include "rt_math.cuh"
+
+namespace b200rt {
+
+// ---------------------------------------------------------------------------------------------
+// device-side description of one triangle build input
+// ---------------------------------------------------------------------------------------------
+struct DevInput {
+    const char* verts;
+    const char* indices;
+    const float* xform;
+    const char* sbt_index;
+    uint32_t vstride, istride, iformat;  // iformat: 0 none, 2 u16x3, 4 u32x3
+    uint32_t sbt_size, sbt_stride;
+    uint32_t prim_offset, sbt_base, num_sbt;
+    uint32_t tri_start, ntris;
+    uint32_t flags_off;                  // into the flat geometry-flag array
+    uint32_t pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// scan (exclusive, in place), templated on element type
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(T* data, size_t n, T* tile_sums)
+{
+    __shared__ T warp_sums[SCAN_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? data[base + i] : (T)0;
+        sum += v[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : (T)0;
+        T wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            T o = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off) wi += o;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - w;
+        if (lane == SCAN_THREADS / 32 - 1 && tile_sums) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    T run = warp_sums[warp] + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = run;
+        run += v[i];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(T* data, size_t n, const T* tile_offsets)
+{
+    const T off = tile_offsets[blockIdx.x];
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) data[base + i] += off;
+}
+
+template <typename T>
+static size_t scan_temp_elems(size_t n)
+{
+    size_t total = 0;
+    while (n > SCAN_TILE) {
+        n = div_up(n, SCAN_TILE);
+        total += n;
+    }
+    return total + 1;
+}
+
+// exclusive scan of data[0..n) in place; tmp must hold scan_temp_elems(n) elements
+template <typename T>
+static int exclusive_scan(b200rt_context ctx, T* data, size_t n, T* tmp, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    const unsigned tiles = div_up(n, SCAN_TILE);
+    if (tiles == 1) {
+        scan_tiles_kernel<T><<<1, SCAN_THREADS, 0, s>>>(data, n, (T*)nullptr);
+        B2_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    scan_tiles_kernel<T><<<tiles, SCAN_THREADS, 0, s>>>(data, n, tmp);
+    B2_LAUNCH_CHECK(ctx);
+    int rc = exclusive_scan<T>(ctx, tmp, tiles, tmp + tiles, s);
+    if (rc) return rc;
+    scan_add_kernel<T><<<tiles, SCAN_THREADS, 0, s>>>(data, n, tmp);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. gather
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t u)
+{
+    const uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+#endif
+}
+
+__global__ void init_bounds_kernel(uint32_t* b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) gather_tris_kernel(const DevInput* __restrict__ inputs, int num_inputs, uint32_t ntris,
+                                                           const uint32_t* __restrict__ geom_flags, float4* __restrict__ tri_tmp,
+                                                           uint32_t* __restrict__ bounds)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (g < ntris) {
+        int k = 0;
+        while (k + 1 < num_inputs && g >= inputs[k + 1].tri_start) ++k;
+        const DevInput in = inputs[k];
+        const uint32_t p = g - in.tri_start;
+        uint32_t i0, i1, i2;
+        if (in.iformat == 4) {
+            const uint32_t* ip = (const uint32_t*)(in.indices + (size_t)p * in.istride);
+            i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+        } else if (in.iformat == 2) {
+            const uint16_t* ip = (const uint16_t*)(in.indices + (size_t)p * in.istride);
+            i0 = ip[0]; i1 = ip[1]; i2 = ip[2];
+        } else {
+            i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2;
+        }
+        const float* a = (const float*)(in.verts + (size_t)i0 * in.vstride);
+        const float* b = (const float*)(in.verts + (size_t)i1 * in.vstride);
+        const float* c = (const float*)(in.verts + (size_t)i2 * in.vstride);
+        float3 v0 = f3(a[0], a[1], a[2]), v1 = f3(b[0], b[1], b[2]), v2 = f3(c[0], c[1], c[2]);
+        if (in.xform) {
+            v0 = xform_point(in.xform, v0);
+            v1 = xform_point(in.xform, v1);
+            v2 = xform_point(in.xform, v2);
+        }
+        uint32_t local_sbt = 0;
+        if (in.sbt_index) {
+            const char* sp = in.sbt_index + (size_t)p * in.sbt_stride;
+            local_sbt = in.sbt_size == 4 ? *(const uint32_t*)sp : (in.sbt_size == 2 ? *(const uint16_t*)sp : *(const uint8_t*)sp);
+        }
+        if (local_sbt >= in.num_sbt) local_sbt = in.num_sbt ? in.num_sbt - 1 : 0;
+        const uint32_t gf = geom_flags[in.flags_off + local_sbt] & 0xffu;
+        const uint32_t sbt = ((in.sbt_base + local_sbt) & TRI_SBT_MASK) | (gf << TRI_FLAG_SHIFT);
+        tri_tmp[3 * (size_t)g + 0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(in.prim_offset + p));
+        tri_tmp[3 * (size_t)g + 1] = make_float4(v1.x, v1.y, v1.z, __uint_as_float(sbt));
+        tri_tmp[3 * (size_t)g + 2] = make_float4(v2.x, v2.y, v2.z, __uint_as_float(g));
+        lo[0] = fminf(v0.x, fminf(v1.x, v2.x)); hi[0] = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+        lo[1] = fminf(v0.y, fminf(v1.y, v2.y)); hi[1] = fmaxf(v0.y, fmaxf(v1.y, v2.y));
+        lo[2] = fminf(v0.z, fminf(v1.z, v2.z)); hi[2] = fmaxf(v0.z, fmaxf(v1.z, v2.z));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float l = lo[a], h = hi[a];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, off));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, off));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(&bounds[a], float_to_ordered(l));
+            atomicMax(&bounds[3 + a], float_to_ordered(h));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. morton keys
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread3(uint64_t x)
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ tri_tmp, uint32_t ntris,
+                                                      const uint32_t* __restrict__ bounds, int bits_per_axis,
+                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ntris) return;
+    const float4 a = tri_tmp[3 * (size_t)g], b = tri_tmp[3 * (size_t)g + 1], c = tri_tmp[3 * (size_t)g + 2];
+    const float lox = ordered_to_float(bounds[0]), loy = ordered_to_float(bounds[1]), loz = ordered_to_float(bounds[2]);
+    const float hix = ordered_to_float(bounds[3]), hiy = ordered_to_float(bounds[4]), hiz = ordered_to_float(bounds[5]);
+    const float cx = 0.5f * (fminf(a.x, fminf(b.x, c.x)) + fmaxf(a.x, fmaxf(b.x, c.x)));
+    const float cy = 0.5f * (fminf(a.y, fminf(b.y, c.y)) + fmaxf(a.y, fmaxf(b.y, c.y)));
+    const float cz = 0.5f * (fminf(a.z, fminf(b.z, c.z)) + fmaxf(a.z, fmaxf(b.z, c.z)));
+    const float cells = (float)(1u << bits_per_axis);
+    const uint32_t maxc = (1u << bits_per_axis) - 1u;
+    auto quant = [&](float v, float lo, float hi) -> uint64_t {
+        const float ext = hi - lo;
+        float u = ext > 0.0f ? (v - lo) / ext : 0.0f;
+        u = fminf(fmaxf(u * cells, 0.0f), (float)maxc);
+        return (uint64_t)min((uint32_t)u, maxc);
+    };
+    const uint64_t key = (spread3(quant(cx, lox, hix)) << 2) | (spread3(quant(cy, loy, hiy)) << 1) | spread3(quant(cz, loz, hiz));
+    keys[g] = key;
+    vals[g] = g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. LSD radix sort, 8-bit digits, stable.  One block owns one tile of RS_TILE consecutive keys.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_IPT = 16, RS_TILE = RS_THREADS * RS_IPT;
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                              uint32_t* __restrict__ hist, uint32_t nblocks)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_IPT; ++i) {
+        const uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                                 uint64_t* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n,
+                                                                 int shift, const uint32_t* __restrict__ offs, uint32_t nblocks)
+{
+    __shared__ uint32_t wcount[RS_WARPS][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t wbase = blockIdx.x * RS_TILE + warp * (32 * RS_IPT);
+    uint64_t k[RS_IPT];
+    uint16_t rank[RS_IPT];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        const uint32_t idx = wbase + r * 32 + lane;
+        const bool valid = idx < n;
+        k[r] = valid ? kin[idx] : ~0ull;
+        const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+        const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
+        const uint32_t cnt = valid ? wcount[warp][d] : 0u;
+        rank[r] = (uint16_t)(cnt + __popc(m & lt));
+        __syncwarp();
+        if (valid && (m & lt) == 0u) wcount[warp][d] = cnt + __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;
+        uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = wcount[w][d];
+            wcount[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        const uint32_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
+            const uint32_t dst = wcount[warp][d] + rank[r];
+            kout[dst] = k[r];
+            vout[dst] = vin[idx];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. Karras hierarchy.  Node ids: internal i in [0, N-1), leaf at sorted position s is (N-1)+s.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ keys, int n, float4* __restrict__ box_lo,
+                                                      float4* __restrict__ box_hi, int* __restrict__ parent, int2* __restrict__ range)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const int left = (first == gamma) ? (n - 1 + gamma) : gamma;
+    const int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    box_lo[i].w = __int_as_float(left);
+    box_hi[i].w = __int_as_float(right);
+    parent[left] = i;
+    parent[right] = i;
+    if (i == 0) parent[0] = -1;
+    range[i] = make_int2(first, last - first + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. refit
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_boxes_kernel(const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
+                                                          float4* __restrict__ box_lo, float4* __restrict__ box_hi)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t g = vals[s];
+    const float4 a = tri_tmp[3 * g], b = tri_tmp[3 * g + 1], c = tri_tmp[3 * g + 2];
+    box_lo[n - 1 + s] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+    box_hi[n - 1 + s] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+}
+
+__global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float4* box_hi, const int* __restrict__ parent,
+                                                     uint32_t* __restrict__ arrive)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int node = parent[n - 1 + s];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&arrive[node], 1u) == 0u) return;  // first arrival: sibling subtree not ready yet
+        const volatile float4* vlo = box_lo;
+        const volatile float4* vhi = box_hi;
+        const int l = __float_as_int(vlo[node].w), r = __float_as_int(vhi[node].w);
+        const float llx = vlo[l].x, lly = vlo[l].y, llz = vlo[l].z, lhx = vhi[l].x, lhy = vhi[l].y, lhz = vhi[l].z;
+        const float rlx = vlo[r].x, rly = vlo[r].y, rlz = vlo[r].z, rhx = vhi[r].x, rhy = vhi[r].y, rhz = vhi[r].z;
+        box_lo[node] = make_float4(fminf(llx, rlx), fminf(lly, rly), fminf(llz, rlz), __int_as_float(l));
+        box_hi[node] = make_float4(fmaxf(lhx, rhx), fmaxf(lhy, rhy), fmaxf(lhz, rhz), __int_as_float(r));
+        node = parent[node];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 6. collapse to the 8-wide layout
+// ---------------------------------------------------------------------------------------------
+struct LevelInfo {  // device <-> host per level
+    uint32_t next_nodes;   // internal children produced by this level
+    uint32_t level_tris;   // triangles referenced by this level's leaves
+    uint32_t error;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ float box_area(const float4 lo, const float4 hi)
+{
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void __launch_bounds__(128) collapse_plan_kernel(uint32_t nwork, const uint32_t* __restrict__ work, int n,
+                                                             const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                                                             const int2* __restrict__ range, int* __restrict__ child_tmp,
+                                                             unsigned long long* __restrict__ counts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwork) return;
+    const int ninternal = n - 1;
+    int ids[8];
+    float area[8];
+    int cnt[8];
+    int m = 0;
+    auto push = [&](int id) {
+        ids[m] = id;
+        if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); }
+        else { cnt[m] = 1; area[m] = -1.0f; }
+        ++m;
+    };
+    const int root = (int)work[i];
+    if (root >= ninternal) push(root);  // single-triangle scene
+    else { push(__float_as_int(box_lo[root].w)); push(__float_as_int(box_hi[root].w)); }
+    // phase 1: open the largest inner subtree with more than 3 triangles; phase 2: split small multi-triangle leaves
+    for (int phase = 0; phase < 2; ++phase) {
+        while (m < 8) {
+            int best = -1;
+            float ba = -1.0f;
+            for (int k = 0; k < m; ++k) {
+                const bool inner = ids[k] < ninternal;
+                const bool ok = phase == 0 ? (inner && cnt[k] > 3) : inner;
+                if (ok && area[k] > ba) { ba = area[k]; best = k; }
+            }
+            if (best < 0) break;
+            const int id = ids[best];
+            const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
+            const int save = m;
+            m = best; push(l);
+            m = save; push(r);
+        }
+    }
+    uint32_t nint = 0, ntri = 0;
+    for (int k = 0; k < 8; ++k) {
+        if (k < m) {
+            child_tmp[(size_t)i * 8 + k] = ids[k];
+            if (ids[k] < ninternal && cnt[k] > 3) ++nint; else ntri += cnt[k];
+        } else child_tmp[(size_t)i * 8 + k] = -1;
+    }
+    counts[i] = ((unsigned long long)nint << 32) | ntri;
+}
+
+__global__ void collapse_totals_kernel(uint32_t nwork, const unsigned long long* __restrict__ excl,
+                                        const unsigned long long* __restrict__ last_count, LevelInfo* info)
+{
+    // excl[nwork-1] + original count of the last element (saved before the scan)
+    const unsigned long long tot = excl[nwork - 1] + *last_count;
+    info->next_nodes = (uint32_t)(tot >> 32);
+    info->level_tris = (uint32_t)(tot & 0xffffffffu);
+}
+
+__global__ void save_last_kernel(uint32_t nwork, const unsigned long long* __restrict__ counts, unsigned long long* last)
+{
+    *last = counts[nwork - 1];
+}
+
+__global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint32_t level_start, uint32_t next_level_start,
+                                                             uint32_t tri_cursor, uint32_t max_nodes, int n,
+                                                             const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                                                             const int2* __restrict__ range, const int* __restrict__ child_tmp,
+                                                             const unsigned long long* __restrict__ excl, uint32_t* __restrict__ next_work,
+                                                             uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out, LevelInfo* info)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwork) return;
+    const uint32_t node_index = level_start + i;
+    if (node_index >= max_nodes) { info->error = 1; return; }
+    const int ninternal = n - 1;
+    const unsigned long long ex = excl[i];
+    const uint32_t child_base = next_level_start + (uint32_t)(ex >> 32);
+    const uint32_t tri_base = tri_cursor + (uint32_t)(ex & 0xffffffffu);
+
+    int ids[8];
+    float4 clo[8], chi[8];
+    int m = 0;
+    float3 Lo = f3(INFINITY, INFINITY, INFINITY), Hi = f3(-INFINITY, -INFINITY, -INFINITY);
+    for (int k = 0; k < 8; ++k) {
+        const int id = child_tmp[(size_t)i * 8 + k];
+        if (id < 0) break;
+        ids[m] = id; clo[m] = box_lo[id]; chi[m] = box_hi[id];
+        Lo = f3(fminf(Lo.x, clo[m].x), fminf(Lo.y, clo[m].y), fminf(Lo.z, clo[m].z));
+        Hi = f3(fmaxf(Hi.x, chi[m].x), fmaxf(Hi.y, chi[m].y), fmaxf(Hi.z, chi[m].z));
+        ++m;
+    }
+    // conservative padding: 2^-16 of the largest extent on every side (covers the rounding of the
+    // slab arithmetic in traverse.cuh; see DESIGN.md "why box tests never cull a true hit")
+    const float maxext = fmaxf(fmaxf(Hi.x - Lo.x, Hi.y - Lo.y), Hi.z - Lo.z);
+    const float pad = fmaxf(maxext * 1.52587890625e-5f, 1e-30f);
+    const float3 P = f3(Lo.x - pad, Lo.y - pad, Lo.z - pad);
+    // grid exponent per axis: smallest e with 255 * 2^e >= padded extent
+    uint32_t eb[3];
+    float scale[3];
+    const float ext3[3] = {(Hi.x + pad) - P.x, (Hi.y + pad) - P.y, (Hi.z + pad) - P.z};
+    const float Pa[3] = {P.x, P.y, P.z};
+    const float Ha[3] = {Hi.x + pad, Hi.y + pad, Hi.z + pad};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float v = ext3[a] * (1.0000002f / 255.0f);
+        const uint32_t bits = __float_as_uint(v);
+        uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+        e = min(max(e, 1u), 254u);
+        while (e < 254u && fm(255.0f, __uint_as_float(e << 23), Pa[a]) < Ha[a]) ++e;
+        eb[a] = e;
+        scale[a] = __uint_as_float(e << 23);
+    }
+    // slot assignment: greedy, each child takes the free slot whose octant sign vector best matches
+    // its centroid offset (slot bit 4/2/1 set = child on the +x/+y/+z side)
+    const float3 ctr = f3(0.5f * (Lo.x + Hi.x), 0.5f * (Lo.y + Hi.y), 0.5f * (Lo.z + Hi.z));
+    int slot_of[8];
+    int child_in_slot[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
+    for (int k = 0; k < m; ++k) {
+        const float ox = 0.5f * (clo[k].x + chi[k].x) - ctr.x, oy = 0.5f * (clo[k].y + chi[k].y) - ctr.y,
+                    oz = 0.5f * (clo[k].z + chi[k].z) - ctr.z;
+        int bs = -1;
+        float bc = -INFINITY;
+        for (int s = 0; s < 8; ++s) {
+            if (child_in_slot[s] >= 0) continue;
+            const float c = ((s & 4) ? ox : -ox) + ((s & 2) ? oy : -oy) + ((s & 1) ? oz : -oz);
+            if (c > bc) { bc = c; bs = s; }
+        }
+        slot_of[k] = bs;
+        child_in_slot[bs] = k;
+    }
+    (void)slot_of;
+    uint32_t imask = 0;
+    uint32_t meta[8], qlo[3][8], qhi[3][8];
+    uint32_t int_k = 0, tri_off = 0;
+    for (int s = 0; s < 8; ++s) {
+        const int k = child_in_slot[s];
+        meta[s] = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; }
+        if (k < 0) continue;
+        const int id = ids[k];
+        const float lo3[3] = {clo[k].x - pad, clo[k].y - pad, clo[k].z - pad};
+        const float hi3[3] = {chi[k].x + pad, chi[k].y + pad, chi[k].z + pad};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int ql = (int)floorf((lo3[a] - Pa[a]) / scale[a]);
+            ql = min(max(ql, 0), 255);
+            while (ql > 0 && fm((float)ql, scale[a], Pa[a]) > lo3[a]) --ql;
+            int qh = (int)ceilf((hi3[a] - Pa[a]) / scale[a]);
+            qh = min(max(qh, 0), 255);
+            while (qh < 255 && fm((float)qh, scale[a], Pa[a]) < hi3[a]) ++qh;
+            qlo[a][s] = (uint32_t)ql;
+            qhi[a][s] = (uint32_t)qh;
+        }
+        int count, first;
+        if (id < ninternal) { const int2 r = range[id]; first = r.x; count = r.y; }
+        else { first = id - ninternal; count = 1; }
+        if (id < ninternal && count > 3) {
+            imask |= 1u << s;
+            meta[s] = (1u << 5) | (24u + (uint32_t)s);
+            next_work[(child_base - next_level_start) + int_k] = (uint32_t)id;
+            ++int_k;
+        } else {
+            const uint32_t unary = count == 1 ? 1u : (count == 2 ? 3u : 7u);
+            meta[s] = (unary << 5) | tri_off;
+            for (int j = 0; j < count; ++j) dest[first + j] = tri_base + tri_off + (uint32_t)j;
+            tri_off += (uint32_t)count;
+        }
+    }
+    auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    uint4* out = nodes_out + (size_t)node_index * 5;
+    out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+    out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+    out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    out[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+}
+
+__global__ void __launch_bounds__(256) scatter_tris_kernel(const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals,
+                                                            const uint32_t* __restrict__ dest, uint32_t n, float4* __restrict__ tris_out)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t g = vals[s];
+    const size_t d = dest[s];
+    tris_out[3 * d + 0] = tri_tmp[3 * g + 0];
+    tris_out[3 * d + 1] = tri_tmp[3 * g + 1];
+    tris_out[3 * d + 2] = tri_tmp[3 * g + 2];
+}
+
+__global__ void write_header_kernel(AccelHeader* h, AccelHeader v, const uint32_t* bounds)
+{
+    for (int a = 0; a < 6; ++a) v.bounds[a] = ordered_to_float(bounds[a]);
+    *h = v;
+}
+
+__global__ void set_root_work_kernel(uint32_t* work, uint32_t id) { work[0] = id; }
+
+// ---------------------------------------------------------------------------------------------
+// IAS
+// ---------------------------------------------------------------------------------------------
+__global__ void build_ias_kernel(const char* __restrict__ instances, uint32_t n, uint32_t stride, AccelHeader* h, InstanceRecord* recs)
+{
+    // one block; few instances on this path (one per glTF mesh node, SDK/sutil/Scene.cpp:1134-1155)
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const b200rt_instance* in = (const b200rt_instance*)(instances + (size_t)k * stride);
+        InstanceRecord r;
+        for (int j = 0; j < 12; ++j) r.m[j] = in->transform[j];
+        invert34(r.m, r.inv);
+        r.gas = in->traversableHandle;
+        r.instance_id = in->instanceId;
+        r.sbt_offset = in->sbtOffset;
+        r.mask = in->visibilityMask;
+        r.flags = in->flags;
+        r.wbounds[0] = r.wbounds[1] = 0.f;
+        recs[k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // bounds: serial pass (n is small on this path)
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t k = 0; k < n; ++k) {
+            const AccelHeader* g = (const AccelHeader*)recs[k].gas;
+            if (!g || g->magic != ACCEL_MAGIC || !g->num_tris) continue;
+            for (int c = 0; c < 8; ++c) {
+                const float3 p = f3(g->bounds[(c & 1) ? 3 : 0], g->bounds[(c & 2) ? 4 : 1], g->bounds[(c & 4) ? 5 : 2]);
+                const float3 w = xform_point(recs[k].m, p);
+                lo[0] = fminf(lo[0], w.x); lo[1] = fminf(lo[1], w.y); lo[2] = fminf(lo[2], w.z);
+                hi[0] = fmaxf(hi[0], w.x); hi[1] = fmaxf(hi[1], w.y); hi[2] = fmaxf(hi[2], w.z);
+            }
+        }
+        AccelHeader v;
+        memset(&v, 0, sizeof(v));
+        v.magic = ACCEL_MAGIC;
+        v.kind = ACCEL_KIND_IAS;
+        v.num_instances = n;
+        v.inst_off = HEADER_BYTES;
+        v.total_bytes = HEADER_BYTES + (uint64_t)n * INSTREC_BYTES;
+        for (int a = 0; a < 3; ++a) { v.bounds[a] = lo[a]; v.bounds[3 + a] = hi[a]; }
+        *h = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct BuildPlan {
+    uint32_t ntris = 0;
+    uint32_t num_inputs = 0;
+    uint32_t total_sbt = 0;
+    uint32_t max_nodes = 0;
+    uint32_t rs_blocks = 0;
+    int morton_bits = 21;
+    // temp offsets
+    size_t off_inputs, off_flags, off_bounds, off_level, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box_lo, off_box_hi,
+        off_parent, off_range, off_arrive, off_dest, off_hist, off_scan_tmp, off_work0, off_work1, off_child_tmp, off_counts, off_last;
+    size_t temp_bytes = 0, out_bytes = 0;
+};
+
+static uint32_t count_tris(const b200rt_build_input_triangle_array& t)
+{
+    return t.indexFormat != B200RT_INDICES_FORMAT_NONE && t.indexBuffer ? t.numIndexTriplets : t.numVertices / 3;
+}
+
+static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsigned num_inputs, BuildPlan& p)
+{
+    uint64_t n = 0, sbt = 0;
+    for (unsigned i = 0; i < num_inputs; ++i) {
+        B2_REQUIRE(ctx, inputs[i].type == B200RT_BUILD_INPUT_TYPE_TRIANGLES, "build input %u: only triangle inputs can be mixed in a GAS", i);
+        const auto& t = inputs[i].triangleArray;
+        B2_REQUIRE(ctx, t.vertexFormat == B200RT_VERTEX_FORMAT_FLOAT3, "build input %u: vertexFormat 0x%x not supported (FLOAT3 only)", i, t.vertexFormat);
+        B2_REQUIRE(ctx, t.indexFormat == B200RT_INDICES_FORMAT_NONE || t.indexFormat == B200RT_INDICES_FORMAT_UNSIGNED_SHORT3 ||
+                            t.indexFormat == B200RT_INDICES_FORMAT_UNSIGNED_INT3, "build input %u: bad indexFormat 0x%x", i, t.indexFormat);
+        B2_REQUIRE(ctx, t.numSbtRecords >= 1, "build input %u: numSbtRecords must be >= 1", i);
+        n += count_tris(t);
+        sbt += t.numSbtRecords;
+    }
+    B2_REQUIRE(ctx, n < (1ull << 30), "too many triangles (%llu)", (unsigned long long)n);
+    B2_REQUIRE(ctx, sbt <= TRI_SBT_MASK, "too many SBT records");
+    p.ntris = (uint32_t)n;
+    p.num_inputs = num_inputs;
+    p.total_sbt = (uint32_t)sbt;
+    p.max_nodes = (uint32_t)(2 * n / 3 + 16);
+    p.rs_blocks = std::max(1u, div_up(n, RS_TILE));
+    p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 22) ? 16 : 21);
+    const size_t N = std::max<size_t>(n, 1);
+    const size_t W = N / 4 + 2;  // widest possible level (every wide node roots >= 4 triangles)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p.off_inputs = take(sizeof(DevInput) * std::max(1u, num_inputs));
+    p.off_flags = take(4 * std::max<size_t>(sbt, 1));
+    p.off_bounds = take(64);
+    p.off_level = take(sizeof(LevelInfo));
+    p.off_last = take(16);
+    p.off_tri_tmp = take(48 * N);
+    p.off_keys0 = take(8 * N);
+    p.off_keys1 = take(8 * N);
+    p.off_vals0 = take(4 * N);
+    p.off_vals1 = take(4 * N);
+    p.off_box_lo = take(16 * 2 * N);
+    p.off_box_hi = take(16 * 2 * N);
+    p.off_parent = take(4 * 2 * N);
+    p.off_range = take(8 * N);
+    p.off_arrive = take(4 * N);
+    p.off_dest = take(4 * N);
+    p.off_hist = take(4 * 256 * (size_t)p.rs_blocks);
+    const size_t scan_elems = std::max(scan_temp_elems<uint32_t>(256 * (size_t)p.rs_blocks), scan_temp_elems<unsigned long long>(W));
+    p.off_scan_tmp = take(8 * scan_elems);
+    p.off_work0 = take(4 * W);
+    p.off_work1 = take(4 * W);
+    p.off_child_tmp = take(4 * 8 * W);
+    p.off_counts = take(8 * W);
+    p.temp_bytes = off;
+    p.out_bytes = align_up(HEADER_BYTES + (size_t)p.max_nodes * NODE8_BYTES + (size_t)n * TRI_BYTES, 128);
+    return 0;
+}
+
+int accel_compute_memory_usage(b200rt_context ctx, const b200rt_accel_build_options* options, const b200rt_build_input* inputs,
+                               unsigned num_inputs, b200rt_accel_buffer_sizes* sizes)
+{
+    B2_REQUIRE(ctx, options && inputs && sizes && num_inputs >= 1, "null argument");
+    B2_REQUIRE(ctx, options->operation == B200RT_BUILD_OPERATION_BUILD, "only OPERATION_BUILD is supported (static scenes)");
+    if (inputs[0].type == B200RT_BUILD_INPUT_TYPE_INSTANCES) {
+        B2_REQUIRE(ctx, num_inputs == 1, "an instance build takes exactly one build input");
+        sizes->outputSizeInBytes = align_up(HEADER_BYTES + (size_t)inputs[0].instanceArray.numInstances * INSTREC_BYTES, 128);
+        sizes->tempSizeInBytes = 128;
+        sizes->tempUpdateSizeInBytes = 0;
+        return 0;
+    }
+    BuildPlan p;
+    int rc = make_plan(ctx, inputs, num_inputs, p);
+    if (rc) return rc;
+    sizes->outputSizeInBytes = p.out_bytes;
+    sizes->tempSizeInBytes = p.temp_bytes;
+    sizes->tempUpdateSizeInBytes = 0;
+    return 0;
+}
+
+int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_options* options, const b200rt_build_input* inputs,
+                unsigned num_inputs, b200rt_deviceptr temp, size_t temp_bytes, b200rt_deviceptr out, size_t out_bytes,
+                b200rt_traversable* handle, const b200rt_accel_emit_desc* emitted, unsigned num_emitted)
+{
+    B2_REQUIRE(ctx, options && inputs && handle && num_inputs >= 1, "null argument");
+    B2_REQUIRE(ctx, options->operation == B200RT_BUILD_OPERATION_BUILD, "only OPERATION_BUILD is supported (static scenes)");
+    B2_REQUIRE(ctx, out && (out % B200RT_ACCEL_BUFFER_BYTE_ALIGNMENT) == 0, "outputBuffer must be 128-byte aligned");
+    DeviceGuard guard(ctx->device);
+    uint64_t exact_bytes = 0;
+
+    if (inputs[0].type == B200RT_BUILD_INPUT_TYPE_INSTANCES) {
+        B2_REQUIRE(ctx, num_inputs == 1, "an instance build takes exactly one build input");
+        const auto& ia = inputs[0].instanceArray;
+        const size_t need = align_up(HEADER_BYTES + (size_t)ia.numInstances * INSTREC_BYTES, 128);
+        B2_REQUIRE(ctx, out_bytes >= need, "outputBuffer too small (%zu < %zu)", out_bytes, need);
+        B2_REQUIRE(ctx, ia.instances || ia.numInstances == 0, "null instances");
+        build_ias_kernel<<<1, 128, 0, s>>>((const char*)ia.instances, ia.numInstances, ia.instanceStride ? ia.instanceStride : 80u,
+                                           (AccelHeader*)out, (InstanceRecord*)(out + HEADER_BYTES));
+        B2_LAUNCH_CHECK(ctx);
+        exact_bytes = HEADER_BYTES + (uint64_t)ia.numInstances * INSTREC_BYTES;
+    } else {
+        BuildPlan p;
+        int rc = make_plan(ctx, inputs, num_inputs, p);
+        if (rc) return rc;
+        B2_REQUIRE(ctx, out_bytes >= p.out_bytes, "outputBuffer too small (%zu < %zu)", out_bytes, p.out_bytes);
+        B2_REQUIRE(ctx, temp_bytes >= p.temp_bytes && temp, "tempBuffer too small (%zu < %zu)", temp_bytes, p.temp_bytes);
+        char* T = (char*)temp;
+        const uint32_t N = p.ntris;
+        // ---- upload input descriptors + geometry flags (pageable -> staged synchronously by the runtime)
+        std::vector<DevInput> dev(num_inputs);
+        std::vector<uint32_t> gflags(std::max(1u, p.total_sbt), 0u);
+        uint32_t tri_start = 0, sbt_base = 0;
+        for (unsigned i = 0; i < num_inputs; ++i) {
+            const auto& t = inputs[i].triangleArray;
+            DevInput& d = dev[i];
+            memset(&d, 0, sizeof(d));
+            B2_REQUIRE(ctx, t.vertexBuffers && t.vertexBuffers[0], "build input %u: null vertex buffer", i);
+            d.verts = (const char*)t.vertexBuffers[0];
+            d.vstride = t.vertexStrideInBytes ? t.vertexStrideInBytes : 12u;
+            const bool indexed = t.indexFormat != B200RT_INDICES_FORMAT_NONE && t.indexBuffer;
+            d.indices = indexed ? (const char*)t.indexBuffer : nullptr;
+            d.iformat = !indexed ? 0u : (t.indexFormat == B200RT_INDICES_FORMAT_UNSIGNED_SHORT3 ? 2u : 4u);
+            d.istride = t.indexStrideInBytes ? t.indexStrideInBytes : 3u * d.iformat;
+            d.xform = (t.transformFormat == B200RT_TRANSFORM_FORMAT_MATRIX_FLOAT12) ? (const float*)t.preTransform : nullptr;
+            d.sbt_index = (const char*)t.sbtIndexOffsetBuffer;
+            d.sbt_size = t.sbtIndexOffsetSizeInBytes ? t.sbtIndexOffsetSizeInBytes : 4u;
+            d.sbt_stride = t.sbtIndexOffsetStrideInBytes ? t.sbtIndexOffsetStrideInBytes : d.sbt_size;
+            d.prim_offset = t.primitiveIndexOffset;
+            d.sbt_base = sbt_base;
+            d.num_sbt = t.numSbtRecords;
+            d.tri_start = tri_start;
+            d.ntris = count_tris(t);
+            d.flags_off = sbt_base;
+            for (unsigned k = 0; k < t.numSbtRecords; ++k) gflags[sbt_base + k] = t.flags ? t.flags[k] : 0u;
+            tri_start += d.ntris;
+            sbt_base += t.numSbtRecords;
+        }
+        B2_CUDA(ctx, cudaMemcpyAsync(T + p.off_inputs, dev.data(), sizeof(DevInput) * num_inputs, cudaMemcpyHostToDevice, s));
+        B2_CUDA(ctx, cudaMemcpyAsync(T + p.off_flags, gflags.data(), 4 * gflags.size(), cudaMemcpyHostToDevice, s));
+
+        uint32_t* d_bounds = (uint32_t*)(T + p.off_bounds);
+        float4* tri_tmp = (float4*)(T + p.off_tri_tmp);
+        uint64_t* keys[2] = {(uint64_t*)(T + p.off_keys0), (uint64_t*)(T + p.off_keys1)};
+        uint32_t* vals[2] = {(uint32_t*)(T + p.off_vals0), (uint32_t*)(T + p.off_vals1)};
+        float4* box_lo = (float4*)(T + p.off_box_lo);
+        float4* box_hi = (float4*)(T + p.off_box_hi);
+        int* parent = (int*)(T + p.off_parent);
+        int2* range = (int2*)(T + p.off_range);
+        uint32_t* arrive = (uint32_t*)(T + p.off_arrive);
+        uint32_t* dest = (uint32_t*)(T + p.off_dest);
+        uint32_t* hist = (uint32_t*)(T + p.off_hist);
+        void* scan_tmp = (void*)(T + p.off_scan_tmp);
+        uint32_t* work[2] = {(uint32_t*)(T + p.off_work0), (uint32_t*)(T + p.off_work1)};
+        int* child_tmp = (int*)(T + p.off_child_tmp);
+        unsigned long long* counts = (unsigned long long*)(T + p.off_counts);
+        unsigned long long* last = (unsigned long long*)(T + p.off_last);
+        LevelInfo* d_level = (LevelInfo*)(T + p.off_level);
+
+        AccelHeader hv;
+        memset(&hv, 0, sizeof(hv));
+        hv.magic = ACCEL_MAGIC;
+        hv.kind = ACCEL_KIND_GAS;
+        hv.num_tris = N;
+        hv.nodes_off = HEADER_BYTES;
+        hv.max_nodes = p.max_nodes;
+        uint4* nodes_out = (uint4*)(out + HEADER_BYTES);
+
+        init_bounds_kernel<<<1, 32, 0, s>>>(d_bounds);
+        B2_LAUNCH_CHECK(ctx);
+        uint32_t total_nodes = 0, depth = 0;
+        if (N > 0) {
+            gather_tris_kernel<<<div_up(N, 256), 256, 0, s>>>((const DevInput*)(T + p.off_inputs), (int)num_inputs, N,
+                                                              (const uint32_t*)(T + p.off_flags), tri_tmp, d_bounds);
+            B2_LAUNCH_CHECK(ctx);
+            morton_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, N, d_bounds, p.morton_bits, keys[0], vals[0]);
+            B2_LAUNCH_CHECK(ctx);
+            int cur = 0;
+            const int passes = (3 * p.morton_bits + 7) / 8;
+            for (int pass = 0; pass < passes && N > 1; ++pass) {
+                rs_hist_kernel<<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], N, pass * 8, hist, p.rs_blocks);
+                B2_LAUNCH_CHECK(ctx);
+                rc = exclusive_scan<uint32_t>(ctx, hist, 256 * (size_t)p.rs_blocks, (uint32_t*)scan_tmp, s);
+                if (rc) return rc;
+                rs_scatter_kernel<<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], N, pass * 8, hist,
+                                                                     p.rs_blocks);
+                B2_LAUNCH_CHECK(ctx);
+                cur ^= 1;
+            }
+            leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
+            B2_LAUNCH_CHECK(ctx);
+            if (N > 1) {
+                karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
+                B2_LAUNCH_CHECK(ctx);
+                B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
+                refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive);
+                B2_LAUNCH_CHECK(ctx);
+            }
+            // ---- collapse, level by level
+            B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
+            set_root_work_kernel<<<1, 1, 0, s>>>(work[0], 0u);  // internal node 0, or leaf id 0 when N == 1
+            B2_LAUNCH_CHECK(ctx);
+            uint32_t nwork = 1, level_start = 0, tri_cursor = 0;
+            int wcur = 0;
+            LevelInfo* h_level = (LevelInfo*)ctx->pinned;
+            while (nwork > 0) {
+                collapse_plan_kernel<<<div_up(nwork, 128), 128, 0, s>>>(nwork, work[wcur], (int)N, box_lo, box_hi, range, child_tmp, counts);
+                B2_LAUNCH_CHECK(ctx);
+                save_last_kernel<<<1, 1, 0, s>>>(nwork, counts, last);
+                B2_LAUNCH_CHECK(ctx);
+                rc = exclusive_scan<unsigned long long>(ctx, counts, nwork, (unsigned long long*)scan_tmp, s);
+                if (rc) return rc;
+                collapse_totals_kernel<<<1, 1, 0, s>>>(nwork, counts, last, d_level);
+                B2_LAUNCH_CHECK(ctx);
+                const uint32_t next_level_start = level_start + nwork;
+                collapse_emit_kernel<<<div_up(nwork, 128), 128, 0, s>>>(nwork, level_start, next_level_start, tri_cursor, p.max_nodes, (int)N,
+                                                                         box_lo, box_hi, range, child_tmp, counts, work[wcur ^ 1], dest,
+                                                                         nodes_out, d_level);
+                B2_LAUNCH_CHECK(ctx);
+                B2_CUDA(ctx, cudaMemcpyAsync(h_level, d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, s));
+                B2_CUDA(ctx, cudaStreamSynchronize(s));
+                if (h_level->error || next_level_start + (uint64_t)h_level->next_nodes > p.max_nodes)
+                    return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: node capacity exceeded (internal error)");
+                total_nodes = next_level_start;
+                level_start = next_level_start;
+                tri_cursor += h_level->level_tris;
+                nwork = h_level->next_nodes;
+                wcur ^= 1;
+                ++depth;
+                B2_REQUIRE(ctx, depth < 64, "accel build: tree too deep");
+            }
+            if (tri_cursor != N) return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: triangle count mismatch (%u != %u)", tri_cursor, N);
+            // triangles go right after the node capacity region; compaction later closes the gap
+            hv.tris_off = HEADER_BYTES + (uint64_t)p.max_nodes * NODE8_BYTES;
+            scatter_tris_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], dest, N, (float4*)(out + hv.tris_off));
+            B2_LAUNCH_CHECK(ctx);
+        } else {
+            hv.tris_off = HEADER_BYTES;
+        }
+        hv.num_nodes = total_nodes;
+        hv.depth = depth;
+        hv.total_bytes = HEADER_BYTES + (uint64_t)total_nodes * NODE8_BYTES + (uint64_t)N * TRI_BYTES;
+        exact_bytes = hv.total_bytes;
+        write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds);
+        B2_LAUNCH_CHECK(ctx);
+        log_msg(ctx, 4, "accel", "GAS: %u triangles, %u nodes, depth %u, %llu bytes", N, total_nodes, depth, (unsigned long long)exact_bytes);
+    }
+    for (unsigned i = 0; i < num_emitted; ++i) {
+        B2_REQUIRE(ctx, emitted && emitted[i].type == B200RT_PROPERTY_TYPE_COMPACTED_SIZE, "only COMPACTED_SIZE can be emitted");
+        const size_t v = align_up(exact_bytes, 128);
+        B2_CUDA(ctx, cudaMemcpyAsync((void*)emitted[i].result, &v, sizeof(size_t), cudaMemcpyHostToDevice, s));
+    }
+    *handle = out;
+    return 0;
+}
+
+__global__ void patch_header_kernel(AccelHeader* h, uint64_t tris_off, uint32_t max_nodes)
+{
+    h->tris_off = tris_off;
+    h->max_nodes = max_nodes;
+}
+
+int accel_compact(b200rt_context ctx, cudaStream_t s, b200rt_traversable input, b200rt_deviceptr out, size_t out_bytes,
+                  b200rt_traversable* handle)
+{
+    B2_REQUIRE(ctx, input && out && handle, "null argument");
+    B2_REQUIRE(ctx, (out % B200RT_ACCEL_BUFFER_BYTE_ALIGNMENT) == 0, "outputBuffer must be 128-byte aligned");
+    DeviceGuard guard(ctx->device);
+    AccelHeader h;
+    B2_CUDA(ctx, cudaMemcpyAsync(&h, (const void*)input, sizeof(h), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(ctx, cudaStreamSynchronize(s));
+    B2_REQUIRE(ctx, h.magic == ACCEL_MAGIC, "not a b200rt traversable");
+    B2_REQUIRE(ctx, out_bytes >= h.total_bytes, "outputBuffer too small (%zu < %llu)", out_bytes, (unsigned long long)h.total_bytes);
+    if (h.kind == ACCEL_KIND_IAS) {
+        B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, h.total_bytes, cudaMemcpyDeviceToDevice, s));
+    } else {
+        const size_t node_bytes = (size_t)h.num_nodes * NODE8_BYTES;
+        B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, HEADER_BYTES + node_bytes, cudaMemcpyDeviceToDevice, s));
+        B2_CUDA(ctx, cudaMemcpyAsync((void*)(out + HEADER_BYTES + node_bytes), (const void*)(input + h.tris_off),
+                                     (size_t)h.num_tris * TRI_BYTES, cudaMemcpyDeviceToDevice, s));
+        patch_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, HEADER_BYTES + node_bytes, h.num_nodes);
+        B2_LAUNCH_CHECK(ctx);
+    }
+    *handle = out;
+    return 0;
+}
+
+int accel_get_info(b200rt_context ctx, b200rt_traversable handle, b200rt_accel_info* info)
+{
+    B2_REQUIRE(ctx, handle && info, "null argument");
+    DeviceGuard guard(ctx->device);
+    AccelHeader h;
+    B2_CUDA(ctx, cudaMemcpy(&h, (const void*)handle, sizeof(h), cudaMemcpyDeviceToHost));
+    B2_REQUIRE(ctx, h.magic == ACCEL_MAGIC, "not a b200rt traversable");
+    info->kind = h.kind;
+    info->num_triangles = h.num_tris;
+    info->num_nodes = h.num_nodes;
+    info->num_instances = h.num_instances;
+    info->total_bytes = h.total_bytes;
+    memcpy(info->bounds, h.bounds, sizeof(h.bounds));
+    info->depth = h.depth;
+    info->reserved = 0;
+    return 0;
+}
+
+}  // namespace b200rt

@@ -1,0 +1,82 @@
+// common.h — context object, error plumbing and launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/b200rt.h"
+
+namespace b200rt {
+
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace b200rt
+
+struct b200rt_context_t {
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    b200rt_log_cb log_cb = nullptr;
+    void* log_data = nullptr;
+    int log_level = 0;
+    std::string last_error;
+    // wavefront workspace (lane state, queues, counters); grown on demand, owned by the context
+    b200rt::Workspace ws;
+    void* pinned = nullptr;   // small pinned host block for counter read-back
+    cudaEvent_t ev = nullptr;
+    std::mutex mu;
+    uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
+};
+
+namespace b200rt {
+
+int set_error(b200rt_context ctx, int code, const char* fmt, ...);
+void log_msg(b200rt_context ctx, int level, const char* tag, const char* fmt, ...);
+int ensure_workspace(b200rt_context ctx, size_t bytes, cudaStream_t stream);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define B2_CUDA(ctx, expr)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return b200rt::set_error(ctx, B200RT_ERROR_CUDA_ERROR, "%s failed: %s (%s:%d)", #expr,          \
+                                     cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+    } while (0)
+
+#define B2_LAUNCH_CHECK(ctx)                                                                                \
+    do {                                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                                \
+        if (_e != cudaSuccess)                                                                              \
+            return b200rt::set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "kernel launch failed: %s (%s:%d)",  \
+                                     cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+        (ctx)->launches++;                                                                                  \
+    } while (0)
+
+#define B2_REQUIRE(ctx, cond, ...)                                                                          \
+    do {                                                                                                    \
+        if (!(cond)) return b200rt::set_error(ctx, B200RT_ERROR_INVALID_VALUE, __VA_ARGS__);                \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline unsigned int div_up(size_t n, size_t d) { return (unsigned int)((n + d - 1) / d); }
+
+}  // namespace b200rt

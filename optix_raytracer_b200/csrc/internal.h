@@ -1,0 +1,28 @@
+// internal.h — functions implemented in the .cu files and exposed through the C ABI in api.cu
+#pragma once
+#include "common.h"
+
+namespace b200rt {
+// bvh_build.cu
+int accel_compute_memory_usage(b200rt_context, const b200rt_accel_build_options*, const b200rt_build_input*, unsigned,
+                               b200rt_accel_buffer_sizes*);
+int accel_build(b200rt_context, cudaStream_t, const b200rt_accel_build_options*, const b200rt_build_input*, unsigned, b200rt_deviceptr,
+                size_t, b200rt_deviceptr, size_t, b200rt_traversable*, const b200rt_accel_emit_desc*, unsigned);
+int accel_compact(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, size_t, b200rt_traversable*);
+int accel_get_info(b200rt_context, b200rt_traversable, b200rt_accel_info*);
+// raycast.cu
+int launch_raycast(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, const b200rt_shader_binding_table*, unsigned, unsigned,
+                   b200rt_deviceptr ext_hits);
+int create_rays_ortho(b200rt_context, cudaStream_t, b200rt_deviceptr, int, int, const float*, const float*, float);
+int translate_rays(b200rt_context, cudaStream_t, b200rt_deviceptr, int, const float*);
+int shade_hits(b200rt_context, cudaStream_t, b200rt_deviceptr, int, b200rt_deviceptr);
+int trace_closest(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, unsigned, b200rt_deviceptr);
+int trace_any(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, unsigned, b200rt_deviceptr);
+int trace_stats(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, uint64_t*, uint64_t*);
+// pathtracer.cu
+int launch_pathtracer(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, const b200rt_shader_binding_table*, unsigned, unsigned,
+                      const b200rt_pt_options*, int multigpu);
+int fill_samples(b200rt_context, cudaStream_t, int, int, int, int, b200rt_deviceptr, int);
+int deinterleave(b200rt_context, cudaStream_t, b200rt_deviceptr, int, int, int, int, b200rt_deviceptr, b200rt_deviceptr);
+int generate_synthetic_mesh(b200rt_context, cudaStream_t, uint64_t, uint32_t, b200rt_deviceptr, b200rt_deviceptr, float*);
+}  // namespace b200rt

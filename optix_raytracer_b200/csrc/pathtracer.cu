@@ -1,0 +1,672 @@
+// pathtracer.cu — wavefront restatement of the Cornell path tracers.
+//
+// Replaces optixLaunch + the device programs of
+//   SDK/optixPathTracer/optixPathTracer.cu:249-413   (mode 0: Russian roulette)
+//   SDK/optixMultiGPU/optixMultiGPU.cu:214-385       (mode 1: depth cap 3, sticky emitted/radiance)
+// with persistent stage kernels over SoA lane state:
+//
+//   INIT    one lane per launch index (pixel, or sample index in mode 1): pixel seed tea<4>, first
+//           camera ray, lane id appended to the active queue
+//   loop:   TRACE  per active lane: resolve the pending shadow ray of the previous bounce (any-hit,
+//                  adds radiance*attenuation into the running pixel sum), then closest hit of the
+//                  extension ray -> (t, prim, sbt)
+//           SHADE  per active lane: miss / closest-hit program, NEE sample -> pending shadow ray,
+//                  Russian roulette or depth cap, next bounce ray or *path regeneration* (the lane
+//                  starts its next sample), finished lanes write accum + sRGB frame; survivors are
+//                  appended to the other queue (warp-aggregated atomics)
+//
+// A lane runs its samples_per_launch samples back to back, so the fp32 summation order of the
+// reference's raygen loop (result += emitted; result += radiance*attenuation, sample after
+// sample) and its RNG stream order (2 jitter draws from the pixel seed; per bounce: 2 bounce, 2
+// light, 1 roulette draw from the path seed) are preserved exactly; with the arithmetic contract of
+// rt_math.cuh the accumulated radiance is bit-identical to the scalar oracle.
+#include "accel.h"
+#include "internal.h"
+#include "traverse.cuh"
+
+namespace b200rt {
+
+struct ParallelogramLight { float3 corner, v1, v2, normal, emission; };
+
+struct PTParams {  // SDK/optixPathTracer/optixPathTracer.h:91-107
+    unsigned int subframe_index;
+    float4* accum_buffer;
+    uchar4* frame_buffer;
+    unsigned int width, height, samples_per_launch;
+    float3 eye, U, V, W;
+    ParallelogramLight light;
+    uint64_t handle;
+};
+static_assert(sizeof(PTParams) == 152 && offsetof(PTParams, eye) == 36 && offsetof(PTParams, light) == 84 && offsetof(PTParams, handle) == 144,
+              "optixPathTracer Params layout");
+
+struct MGParams {  // SDK/optixMultiGPU/optixMultiGPU.h:46-64
+    unsigned int subframe_index;
+    int2* sample_index_buffer;
+    float4* sample_accum_buffer;
+    uchar4* result_buffer;
+    unsigned int width, height, samples_per_launch, device_idx;
+    float3 eye, U, V, W;
+    ParallelogramLight light;
+    uint64_t handle;
+};
+static_assert(sizeof(MGParams) == 168 && offsetof(MGParams, eye) == 48 && offsetof(MGParams, light) == 96 && offsetof(MGParams, handle) == 160,
+              "optixMultiGPU Params layout");
+
+struct HitGroupData { float3 emission_color; float3 diffuse_color; const float4* vertices; };  // optixPathTracer.h:121-126
+
+// unified view of the two Params structs, built on the device at the top of every stage kernel
+struct Frame {
+    unsigned int subframe, width, height, spl, device_idx;
+    float3 eye, U, V, W;
+    ParallelogramLight light;
+    const AccelHeader* handle;
+    float4* accum;
+    uchar4* frame;
+    const int2* sample_index;
+};
+template <int MODE>
+__device__ __forceinline__ Frame load_frame(const void* p)
+{
+    Frame f;
+    if (MODE == 0) {
+        const PTParams* q = (const PTParams*)p;
+        f.subframe = q->subframe_index; f.width = q->width; f.height = q->height; f.spl = q->samples_per_launch; f.device_idx = 0;
+        f.eye = q->eye; f.U = q->U; f.V = q->V; f.W = q->W; f.light = q->light;
+        f.handle = (const AccelHeader*)q->handle; f.accum = q->accum_buffer; f.frame = q->frame_buffer; f.sample_index = nullptr;
+    } else {
+        const MGParams* q = (const MGParams*)p;
+        f.subframe = q->subframe_index; f.width = q->width; f.height = q->height; f.spl = q->samples_per_launch; f.device_idx = q->device_idx;
+        f.eye = q->eye; f.U = q->U; f.V = q->V; f.W = q->W; f.light = q->light;
+        f.handle = (const AccelHeader*)q->handle; f.accum = q->sample_accum_buffer; f.frame = q->result_buffer; f.sample_index = q->sample_index_buffer;
+    }
+    return f;
+}
+
+// lane flag word (ray_d.w)
+constexpr uint32_t LF_DEPTH_MASK = 0xffu;
+constexpr uint32_t LF_SAMPLES_SHIFT = 8, LF_SAMPLES_MASK = 0xfffffu;
+constexpr uint32_t LF_SHADOW = 1u << 28;      // a shadow ray is pending
+constexpr uint32_t LF_NO_EXT = 1u << 29;      // no extension ray: lane only waits for its last shadow ray
+constexpr uint32_t LF_COUNT_EMITTED = 1u << 30;
+
+struct Counters {
+    unsigned int qcount[2];
+    unsigned int pad[2];
+    unsigned long long radiance_segments, shadow_segments;
+};
+
+struct Lanes {
+    float4* ray_o;   // origin, w = path seed
+    float4* ray_d;   // direction, w = flag word
+    float4* att;     // attenuation, w = pixel seed
+    float4* res;     // running pixel sum, w = hit t (-1 = miss)
+    float4* shd_o;   // pending shadow ray origin, w = tmax
+    float4* shd_d;   // pending shadow ray direction, w = light weight
+    float4* pend;    // attenuation the pending radiance is multiplied with (pre-roulette)
+    float4* rad;     // mode 1: sticky radiance (xyz)
+    float4* emi;     // mode 1: sticky emitted (xyz)
+    uint2* hitp;     // prim, sbt
+    unsigned int* queue[2];
+    Counters* counters;
+};
+
+__device__ __forceinline__ void camera_ray(const Frame& f, int px, int py, uint32_t& pixel_seed, float3& org, float3& dir)
+{
+    // optixPathTracer.cu:267-274
+    const float jx = rnd(pixel_seed), jy = rnd(pixel_seed);
+    const float dx = fm(2.0f, fdiv((float)px + jx, (float)f.width), -1.0f);
+    const float dy = fm(2.0f, fdiv((float)py + jy, (float)f.height), -1.0f);
+    dir = normalize(f3(fm(dy, f.V.x, dx * f.U.x) + f.W.x, fm(dy, f.V.y, dx * f.U.y) + f.W.y, fm(dy, f.V.z, dx * f.U.z) + f.W.z));
+    org = f.eye;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool lane_pixel(const Frame& f, uint32_t lane, int& px, int& py)
+{
+    if (MODE == 0) {
+        px = (int)(lane % f.width);
+        py = (int)(lane / f.width);
+        return true;
+    }
+    const int2 p = f.sample_index[lane];
+    px = p.x; py = p.y;
+    return !(px > (int)f.width - 1 || py > (int)f.height - 1);  // optixMultiGPU.cu:221-223
+}
+
+__device__ __forceinline__ void queue_push(unsigned int* queue, unsigned int* count, bool active, uint32_t lane)
+{
+    const uint32_t mask = __ballot_sync(__activemask(), active);
+    if (!active) return;
+    const uint32_t lane_id = threadIdx.x & 31;
+    const uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane_id == leader) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    queue[base + __popc(mask & ((1u << lane_id) - 1u))] = lane;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ params, Lanes L, uint32_t nlanes)
+{
+    const Frame f = load_frame<MODE>(params);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nlanes; base += gridDim.x * blockDim.x) {
+        const uint32_t lane = base + threadIdx.x;
+        bool active = false;
+        if (lane < nlanes) {
+            int px, py;
+            if (lane_pixel<MODE>(f, lane, px, py) && f.spl > 0) {
+                uint32_t pixel_seed = tea4((uint32_t)(py * (int)f.width + px), f.subframe);
+                float3 org, dir;
+                camera_ray(f, px, py, pixel_seed, org, dir);
+                const uint32_t flags = ((f.spl - 1u) & LF_SAMPLES_MASK) << LF_SAMPLES_SHIFT | LF_COUNT_EMITTED;
+                L.ray_o[lane] = make_float4(org.x, org.y, org.z, __uint_as_float(pixel_seed));
+                L.ray_d[lane] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags));
+                L.att[lane] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel_seed));
+                L.res[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
+                if (MODE == 1) {
+                    L.rad[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    L.emi[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                active = true;
+            }
+        }
+        queue_push(L.queue[0], &L.counters->qcount[0], active, lane);
+    }
+}
+
+// ---- TRACE ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
+{
+    const Frame f = load_frame<MODE>(params);
+    const uint32_t n = L.counters->qcount[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->qcount[cur ^ 1] = 0;  // SHADE of this iteration appends there
+    const unsigned int* __restrict__ queue = L.queue[cur];
+    uint32_t nrad = 0, nshd = 0;
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
+        const uint32_t lane = queue[qi];
+        const float4 rd = L.ray_d[lane];
+        const uint32_t flags = __float_as_uint(rd.w);
+        float4 res = L.res[lane];
+        if (flags & LF_SHADOW) {
+            const float4 so = L.shd_o[lane], sd = L.shd_d[lane], pa = L.pend[lane];
+            RayHit sh;
+            ++nshd;
+            const bool occluded = trace_handle<true, false>(f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, so.w,
+                                                            B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT, sh, nullptr);
+            const float weight = occluded ? 0.0f : sd.w;
+            if (MODE == 0) {
+                // prd.radiance = light.emission * weight; result += prd.radiance * prd.attenuation
+                res.x = fm(f.light.emission.x * weight, pa.x, res.x);
+                res.y = fm(f.light.emission.y * weight, pa.y, res.y);
+                res.z = fm(f.light.emission.z * weight, pa.z, res.z);
+            } else {
+                // prd->radiance += light.emission * weight (sticky); result += prd.radiance * prd.attenuation
+                float4 rad = L.rad[lane];
+                rad.x = fm(f.light.emission.x, weight, rad.x);
+                rad.y = fm(f.light.emission.y, weight, rad.y);
+                rad.z = fm(f.light.emission.z, weight, rad.z);
+                res.x = fm(rad.x, pa.x, res.x);
+                res.y = fm(rad.y, pa.y, res.y);
+                res.z = fm(rad.z, pa.z, res.z);
+                // LF_COUNT_EMITTED marks a freshly regenerated camera ray: the shadow ray just resolved belonged
+                // to the previous sample's last bounce, and the new sample starts with prd.radiance = 0
+                L.rad[lane] = (flags & LF_COUNT_EMITTED) ? make_float4(0.f, 0.f, 0.f, 0.f) : rad;
+            }
+        }
+        if (!(flags & LF_NO_EXT)) {
+            const float4 ro = L.ray_o[lane];
+            RayHit hit;
+            ++nrad;
+            const bool found = trace_handle<false, false>(f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 1e16f, 0u, hit, nullptr);
+            res.w = found ? hit.t : -1.0f;
+            if (found) L.hitp[lane] = make_uint2(hit.prim, hit.sbt);
+        }
+        L.res[lane] = res;
+    }
+    // segment counters: one atomic pair per warp
+    for (int off = 16; off; off >>= 1) {
+        nrad += __shfl_xor_sync(0xffffffffu, nrad, off);
+        nshd += __shfl_xor_sync(0xffffffffu, nshd, off);
+    }
+    if ((threadIdx.x & 31) == 0 && (nrad | nshd)) {
+        atomicAdd(&L.counters->radiance_segments, (unsigned long long)nrad);
+        atomicAdd(&L.counters->shadow_segments, (unsigned long long)nshd);
+    }
+}
+
+// ---- SHADE ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 device_color(unsigned int idx)  // optixMultiGPU.cu:199-206
+{
+    return f3(idx == 0 ? 0.05f : 0.0f, idx == 1 ? 0.05f : 0.0f, idx == 2 ? 0.05f : 0.0f);
+}
+
+template <int MODE>
+__device__ __forceinline__ void finalize_lane(const Frame& f, uint32_t lane, int px, int py, float3 result)
+{
+    // optixPathTracer.cu:308-319 / optixMultiGPU.cu:281-292
+    const float spl = (float)f.spl;
+    float3 c = f3(fdiv(result.x, spl), fdiv(result.y, spl), fdiv(result.z, spl));
+    const uint32_t image_index = (uint32_t)py * f.width + (uint32_t)px;
+    const uint32_t accum_index = MODE == 0 ? image_index : lane;
+    if (f.subframe > 0) {
+        const float a = fdiv(1.0f, (float)(f.subframe + 1u));
+        const float4 prev = f.accum[accum_index];
+        c = f3(fm(a, c.x - prev.x, prev.x), fm(a, c.y - prev.y, prev.y), fm(a, c.z - prev.z, prev.z));
+    }
+    f.accum[accum_index] = make_float4(c.x, c.y, c.z, 1.0f);
+    if (f.frame) f.frame[image_index] = make_color(MODE == 0 ? c : c + device_color(f.device_idx));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ params, Lanes L, int cur, const char* __restrict__ hg_base,
+                                                        uint32_t hg_stride, uint32_t hg_count, const char* __restrict__ miss_base)
+{
+    const Frame f = load_frame<MODE>(params);
+    const uint32_t n = L.counters->qcount[cur];
+    const unsigned int* __restrict__ queue = L.queue[cur];
+    unsigned int* next_queue = L.queue[cur ^ 1];
+    unsigned int* next_count = &L.counters->qcount[cur ^ 1];
+    const float3 bg = MODE == 0 ? xyz(*(const float4*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))
+                                : f3(((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[0],
+                                     ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[1],
+                                     ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[2]);
+    constexpr uint32_t RAY_TYPES = MODE == 0 ? 1u : 2u;  // SBT stride of the radiance trace call
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t qi = base + threadIdx.x;
+        bool keep = false;
+        uint32_t lane = 0;
+        if (qi < n) {
+            lane = queue[qi];
+            float4 rd = L.ray_d[lane];
+            uint32_t flags = __float_as_uint(rd.w);
+            float4 resv = L.res[lane];
+            float3 result = f3(resv.x, resv.y, resv.z);
+            int px, py;
+            lane_pixel<MODE>(f, lane, px, py);
+            if (flags & LF_NO_EXT) {
+                // the last shadow ray of the lane has been resolved by TRACE: write the pixel
+                finalize_lane<MODE>(f, lane, px, py, result);
+            } else {
+                const float4 ro = L.ray_o[lane];
+                float4 attv = L.att[lane];
+                float3 att = f3(attv.x, attv.y, attv.z);
+                uint32_t seed = __float_as_uint(ro.w);
+                uint32_t pixel_seed = __float_as_uint(attv.w);
+                const float3 org = f3(ro.x, ro.y, ro.z), dir = f3(rd.x, rd.y, rd.z);
+                uint32_t depth = flags & LF_DEPTH_MASK;
+                uint32_t samples_left = (flags >> LF_SAMPLES_SHIFT) & LF_SAMPLES_MASK;
+                bool count_emitted = (flags & LF_COUNT_EMITTED) != 0;
+                bool has_shadow = false;
+                bool done;
+                float3 nrg = org, ndir = dir;
+                if (resv.w < 0.0f) {
+                    // __miss__radiance: radiance = bg, done.  Mode 0 clears emitted; mode 1 leaves the sticky values.
+                    if (MODE == 0) {
+                        result = f3(fm(bg.x, att.x, result.x), fm(bg.y, att.y, result.y), fm(bg.z, att.z, result.z));
+                    } else {
+                        const float4 em = L.emi[lane];
+                        result = result + f3(em.x, em.y, em.z);
+                        L.rad[lane] = make_float4(bg.x, bg.y, bg.z, 0.f);
+                        result = f3(fm(bg.x, att.x, result.x), fm(bg.y, att.y, result.y), fm(bg.z, att.z, result.z));
+                    }
+                    done = true;
+                } else {
+                    // __closesthit__radiance (optixPathTracer.cu:338-413 / optixMultiGPU.cu:312-385)
+                    const uint2 hp = L.hitp[lane];
+                    uint32_t rec_idx = (hp.y & TRI_SBT_MASK) * RAY_TYPES;
+                    if (rec_idx >= hg_count) rec_idx = hg_count - 1;
+                    const HitGroupData* rt = (const HitGroupData*)(hg_base + (size_t)rec_idx * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE);
+                    const float4* vb = rt->vertices + 3 * (size_t)hp.x;
+                    const float3 v0 = xyz(__ldg(vb)), v1 = xyz(__ldg(vb + 1)), v2 = xyz(__ldg(vb + 2));
+                    const float3 N0 = normalize(cross(v1 - v0, v2 - v0));
+                    const float3 N = N0 * copysignf(1.0f, dot(neg(dir), N0));  // faceforward(N0, -dir, N0)
+                    const float t = resv.w;
+                    const float3 P = f3(fm(t, dir.x, org.x), fm(t, dir.y, org.y), fm(t, dir.z, org.z));
+                    const bool emit_now = MODE == 0 ? (depth == 0) : count_emitted;
+                    const float3 emitted = emit_now ? rt->emission_color : f3(0.f, 0.f, 0.f);
+                    const float z1 = rnd(seed), z2 = rnd(seed);
+                    float s, c;
+                    det_sincos(6.2831855f * z2, s, c);
+                    const float r = fsqrt(z1);
+                    float3 w_in = f3(r * c, r * s, 0.0f);
+                    w_in.z = fsqrt(fmaxf(0.0f, fm(-w_in.y, w_in.y, fm(-w_in.x, w_in.x, 1.0f))));
+                    // Onb (optixPathTracer.cu:47-78)
+                    float3 bn;
+                    if (fabsf(N.x) > fabsf(N.z)) bn = f3(-N.y, N.x, 0.0f);
+                    else bn = f3(0.0f, -N.z, N.y);
+                    bn = normalize(bn);
+                    const float3 tg = cross(bn, N);
+                    ndir = f3(fm(w_in.z, N.x, fm(w_in.y, bn.x, w_in.x * tg.x)), fm(w_in.z, N.y, fm(w_in.y, bn.y, w_in.x * tg.y)),
+                              fm(w_in.z, N.z, fm(w_in.y, bn.z, w_in.x * tg.z)));
+                    nrg = P;
+                    att = att * rt->diffuse_color;
+                    count_emitted = false;
+                    const float l1 = rnd(seed), l2 = rnd(seed);
+                    const ParallelogramLight& lt = f.light;
+                    const float3 lp = f3(fm(lt.v2.x, l2, fm(lt.v1.x, l1, lt.corner.x)), fm(lt.v2.y, l2, fm(lt.v1.y, l1, lt.corner.y)),
+                                         fm(lt.v2.z, l2, fm(lt.v1.z, l1, lt.corner.z)));
+                    const float3 Ld = lp - P;
+                    const float Ldist = length(Ld);
+                    const float3 Lv = normalize(Ld);
+                    const float nDl = dot(N, Lv);
+                    const float LnDl = -dot(lt.normal, Lv);
+                    result = result + emitted;
+                    if (MODE == 1) L.emi[lane] = make_float4(emitted.x, emitted.y, emitted.z, 0.f);
+                    if (nDl > 0.0f && LnDl > 0.0f) {
+                        const float A = length(cross(lt.v1, lt.v2));
+                        const float weight = fdiv((nDl * LnDl) * A, (3.14159265358979323846f * Ldist) * Ldist);
+                        L.shd_o[lane] = make_float4(P.x, P.y, P.z, Ldist - 0.01f);
+                        L.shd_d[lane] = make_float4(Lv.x, Lv.y, Lv.z, weight);
+                        L.pend[lane] = make_float4(att.x, att.y, att.z, 0.f);
+                        has_shadow = true;
+                    } else if (MODE == 1) {
+                        // weight 0: radiance unchanged, but result += radiance * attenuation still happens
+                        const float4 rad = L.rad[lane];
+                        result = f3(fm(rad.x, att.x, result.x), fm(rad.y, att.y, result.y), fm(rad.z, att.z, result.z));
+                    }
+                    done = false;
+                }
+                // raygen loop tail (optixPathTracer.cu:294-303 / optixMultiGPU.cu:271-277)
+                bool path_ends;
+                if (MODE == 0) {
+                    const float p = dot(att, f3(0.30f, 0.59f, 0.11f));
+                    path_ends = done || rnd(seed) > p;
+                    if (!path_ends) att = f3(fdiv(att.x, p), fdiv(att.y, p), fdiv(att.z, p));
+                } else {
+                    path_ends = done || depth >= 3u;
+                }
+                uint32_t nflags;
+                bool lane_done = false;
+                if (!path_ends) {
+                    depth = min(depth + 1u, 255u);
+                    nflags = depth | (samples_left << LF_SAMPLES_SHIFT) | (has_shadow ? LF_SHADOW : 0u);
+                } else if (samples_left > 0) {
+                    // path regeneration: next sample of this launch index
+                    camera_ray(f, px, py, pixel_seed, nrg, ndir);
+                    seed = pixel_seed;
+                    att = f3(1.f, 1.f, 1.f);
+                    nflags = ((samples_left - 1u) << LF_SAMPLES_SHIFT) | LF_COUNT_EMITTED | (has_shadow ? LF_SHADOW : 0u);
+                    if (MODE == 1) {
+                        // prd.emitted / prd.radiance are re-initialised per sample (optixMultiGPU.cu:244-250) — but a pending
+                        // shadow ray of the finished path still needs the old radiance: defer the reset through a marker
+                        if (!has_shadow) { L.rad[lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                        L.emi[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                } else if (has_shadow) {
+                    nflags = LF_SHADOW | LF_NO_EXT;
+                } else {
+                    nflags = 0;
+                    lane_done = true;
+                }
+                if (lane_done) {
+                    finalize_lane<MODE>(f, lane, px, py, result);
+                } else {
+                    keep = true;
+                    L.ray_o[lane] = make_float4(nrg.x, nrg.y, nrg.z, __uint_as_float(seed));
+                    L.ray_d[lane] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(nflags));
+                    L.att[lane] = make_float4(att.x, att.y, att.z, __uint_as_float(pixel_seed));
+                    L.res[lane] = make_float4(result.x, result.y, result.z, -1.0f);
+                }
+            }
+        }
+        queue_push(next_queue, next_count, keep, lane);
+    }
+}
+
+// ---- fillSamples / de-interleave -------------------------------------------------------------------
+__device__ __forceinline__ int2 wd_sample_pixel(int width, int num_gpus, int gpu_idx, int sample_idx)
+{
+    // StaticWorkDistribution::getSamplePixel (SDK/sutil/WorkDistribution.h:60-81), integer arithmetic
+    const int strip_w = 8 * num_gpus;
+    const int cols = (width + strip_w - 1) / strip_w;
+    const int tile = sample_idx >> 5, in_tile = sample_idx & 31;
+    const int row = tile / cols, col = tile - row * cols;
+    const int rot = (gpu_idx + row % num_gpus) % num_gpus;
+    return make_int2(col * strip_w + rot * 8 + (in_tile & 7), row * 4 + (in_tile >> 3));
+}
+
+__global__ void __launch_bounds__(256) fill_samples_kernel(int gpu_idx, int num_gpus, int width, int2* __restrict__ out, int num_samples)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_samples) out[i] = wd_sample_pixel(width, num_gpus, gpu_idx, i);
+}
+
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float4* __restrict__ gathered, int num_gpus, int num_samples, int width,
+                                                            int height, float4* __restrict__ accum, uchar4* __restrict__ frame)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)num_gpus * num_samples) return;
+    const int gpu = (int)(i / num_samples), s = (int)(i - (long long)gpu * num_samples);
+    const int2 p = wd_sample_pixel(width, num_gpus, gpu, s);
+    if (p.x >= width || p.y >= height) return;
+    const float4 v = gathered[i];
+    const size_t idx = (size_t)p.y * width + p.x;
+    if (accum) accum[idx] = v;
+    if (frame) frame[idx] = make_color(f3(v.x, v.y, v.z));
+}
+
+// ---- synthetic tessellated scene (BASELINE.json configs[4]) -----------------------------------------
+// Cornell-sized room (5 tessellated walls, open front), a 3x3x3 grid of displaced lat-long spheres and the
+// Cornell light quad; vertex positions are closed-form functions of integer grid coordinates so shared
+// vertices are bit-identical (watertight).  Materials: 0 white, 1 green, 2 red, 3 light (the Cornell table).
+struct SynthLayout {
+    uint64_t total, blob_tris_each, wall_tris_each, light_tris;
+    uint32_t rows, cols, grid;
+};
+__host__ __device__ inline SynthLayout synth_layout(uint64_t total)
+{
+    SynthLayout s;
+    s.total = total;
+    const uint64_t t = total > 64 ? total - 2 : 0;  // keep >= 2 for the light
+    double per_blob = (double)t * 0.9 / 27.0 / 4.0;
+    uint32_t rows = (uint32_t)floor(sqrt(per_blob > 0 ? per_blob : 0));
+    if (rows < 2) rows = t >= 27 * 16 ? 2 : 0;
+    s.rows = rows;
+    s.cols = 2 * rows;
+    s.blob_tris_each = 2ull * rows * s.cols;
+    const uint64_t used = 27 * s.blob_tris_each;
+    uint32_t grid = (uint32_t)floor(sqrt((double)(t > used ? t - used : 0) / 10.0));
+    s.grid = grid;
+    s.wall_tris_each = 2ull * grid * grid;
+    s.light_tris = total - used - 5 * s.wall_tris_each;
+    return s;
+}
+
+__device__ __forceinline__ float3 blob_vertex(int b, uint32_t i, uint32_t j, uint32_t rows, uint32_t cols, uint32_t seed)
+{
+    const int bx = b % 3, by = (b / 3) % 3, bz = b / 9;
+    const float3 ctr = f3(139.0f + 139.0f * bx, 110.0f + 160.0f * by, 140.0f + 140.0f * bz);
+    const float rad = 48.0f;
+    if (i == 0) return f3(ctr.x, ctr.y + rad, ctr.z);
+    if (i == rows) return f3(ctr.x, ctr.y - rad, ctr.z);
+    j = j % cols;
+    const float theta = 3.14159265358979f * (float)i / (float)rows;
+    const float phi = 6.28318530717959f * (float)j / (float)cols;
+    const float st = sinf(theta), ct = cosf(theta), sp = sinf(phi), cp = cosf(phi);
+    const float ph = 0.37f * (float)((seed + 7u * (uint32_t)b) % 17u);
+    const float disp = 1.0f + st * (0.14f * sinf(5.0f * theta + ph) * sinf(4.0f * phi + ph) + 0.04f * sinf(23.0f * theta) * sinf(17.0f * phi));
+    const float rr = rad * disp;
+    return f3(ctr.x + rr * st * cp, ctr.y + rr * ct, ctr.z + rr * st * sp);
+}
+
+__device__ __forceinline__ float3 wall_vertex(int wall, uint32_t i, uint32_t j, uint32_t grid)
+{
+    const float X = 556.0f, Y = 548.8f, Z = 559.2f;
+    const float u = (float)i / (float)grid, v = (float)j / (float)grid;
+    switch (wall) {
+        case 0: return f3(X * u, 0.0f, Z * v);   // floor
+        case 1: return f3(X * u, Y, Z * v);      // ceiling
+        case 2: return f3(X * u, Y * v, Z);      // back wall
+        case 3: return f3(0.0f, Y * u, Z * v);   // right wall (green)
+        default: return f3(X, Y * u, Z * v);     // left wall (red)
+    }
+}
+
+__global__ void __launch_bounds__(256) synth_mesh_kernel(SynthLayout s, uint32_t seed, float4* __restrict__ verts, uint32_t* __restrict__ mats)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= s.total) return;
+    float3 a, b, c;
+    uint32_t mat = 0;
+    const uint64_t blob_total = 27 * s.blob_tris_each;
+    const uint64_t wall_total = 5 * s.wall_tris_each;
+    if (t < blob_total) {
+        const int bi = (int)(t / s.blob_tris_each);
+        const uint64_t r = t - (uint64_t)bi * s.blob_tris_each;
+        const uint64_t quad = r >> 1;
+        const uint32_t i = (uint32_t)(quad / s.cols), j = (uint32_t)(quad % s.cols);
+        const float3 p00 = blob_vertex(bi, i, j, s.rows, s.cols, seed), p01 = blob_vertex(bi, i, j + 1, s.rows, s.cols, seed);
+        const float3 p10 = blob_vertex(bi, i + 1, j, s.rows, s.cols, seed), p11 = blob_vertex(bi, i + 1, j + 1, s.rows, s.cols, seed);
+        if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+        mat = (bi % 5 == 1) ? 1u : ((bi % 5 == 3) ? 2u : 0u);
+    } else if (t < blob_total + wall_total) {
+        const uint64_t r0 = t - blob_total;
+        const int w = (int)(r0 / s.wall_tris_each);
+        const uint64_t r = r0 - (uint64_t)w * s.wall_tris_each;
+        const uint64_t quad = r >> 1;
+        const uint32_t i = (uint32_t)(quad / s.grid), j = (uint32_t)(quad % s.grid);
+        const float3 p00 = wall_vertex(w, i, j, s.grid), p01 = wall_vertex(w, i, j + 1, s.grid);
+        const float3 p10 = wall_vertex(w, i + 1, j, s.grid), p11 = wall_vertex(w, i + 1, j + 1, s.grid);
+        if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+        mat = w == 3 ? 1u : (w == 4 ? 2u : 0u);
+    } else {
+        // light quad (343..213, 548.6, 227..332) as a strip of K quads along x
+        const uint64_t r = t - blob_total - wall_total;
+        const uint64_t K = s.light_tris / 2;
+        mat = 3u;
+        if (K == 0 || (r >> 1) >= K) {
+            a = b = c = f3(343.0f, 548.6f, 227.0f);  // odd leftover: zero-area triangle (never hit)
+        } else {
+            const uint64_t q = r >> 1;
+            const float x0 = 343.0f - 130.0f * (float)q / (float)K, x1 = (q + 1 == K) ? 213.0f : 343.0f - 130.0f * (float)(q + 1) / (float)K;
+            const float3 p00 = f3(x0, 548.6f, 227.0f), p01 = f3(x0, 548.6f, 332.0f), p10 = f3(x1, 548.6f, 227.0f), p11 = f3(x1, 548.6f, 332.0f);
+            if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+        }
+    }
+    verts[3 * t + 0] = make_float4(a.x, a.y, a.z, 0.f);
+    verts[3 * t + 1] = make_float4(b.x, b.y, b.z, 0.f);
+    verts[3 * t + 2] = make_float4(c.x, c.y, c.z, 0.f);
+    mats[t] = mat;
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+static unsigned persistent_grid(b200rt_context ctx, uint64_t n, int block, int ctas_per_sm)
+{
+    const uint64_t need = (n + block - 1) / block;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)ctx->sm_count * ctas_per_sm));
+}
+
+template <int MODE>
+static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, uint32_t nlanes,
+                          const b200rt_pt_options* opt)
+{
+    // workspace layout
+    const size_t L = nlanes;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_cnt = take(sizeof(Counters));
+    const size_t o_ro = take(16 * L), o_rd = take(16 * L), o_att = take(16 * L), o_res = take(16 * L), o_so = take(16 * L), o_sd = take(16 * L),
+                 o_pend = take(16 * L);
+    const size_t o_rad = MODE == 1 ? take(16 * L) : 0, o_emi = MODE == 1 ? take(16 * L) : 0;
+    const size_t o_hit = take(8 * L), o_q0 = take(4 * L), o_q1 = take(4 * L);
+    int rc = ensure_workspace(ctx, off, s);
+    if (rc) return rc;
+    char* W = (char*)ctx->ws.ptr;
+    Lanes ln;
+    ln.counters = (Counters*)(W + o_cnt);
+    ln.ray_o = (float4*)(W + o_ro); ln.ray_d = (float4*)(W + o_rd); ln.att = (float4*)(W + o_att); ln.res = (float4*)(W + o_res);
+    ln.shd_o = (float4*)(W + o_so); ln.shd_d = (float4*)(W + o_sd); ln.pend = (float4*)(W + o_pend);
+    ln.rad = MODE == 1 ? (float4*)(W + o_rad) : nullptr;
+    ln.emi = MODE == 1 ? (float4*)(W + o_emi) : nullptr;
+    ln.hitp = (uint2*)(W + o_hit);
+    ln.queue[0] = (unsigned int*)(W + o_q0);
+    ln.queue[1] = (unsigned int*)(W + o_q1);
+
+    const uint64_t launches0 = ctx->launches;
+    B2_CUDA(ctx, cudaMemsetAsync(ln.counters, 0, sizeof(Counters), s));
+    const unsigned grid = persistent_grid(ctx, nlanes, 256, 8);
+    const void* params = (const void*)d_params;
+    pt_init_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, nlanes);
+    B2_LAUNCH_CHECK(ctx);
+    Counters* h_cnt = (Counters*)((char*)ctx->pinned + 256);
+    int cur = 0;
+    uint32_t iterations = 0;
+    const int CHECK_EVERY = 8;
+    for (;;) {
+        for (int k = 0; k < CHECK_EVERY; ++k) {
+            pt_trace_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur);
+            B2_LAUNCH_CHECK(ctx);
+            pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,
+                                                       sbt->hitgroupRecordCount, (const char*)sbt->missRecordBase);
+            B2_LAUNCH_CHECK(ctx);
+            cur ^= 1;
+            ++iterations;
+        }
+        B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, ln.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        if (h_cnt->qcount[cur] == 0) break;
+        if (iterations > 100000) return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "path tracer did not terminate");
+    }
+    if (opt && opt->collect_stats && opt->stats) {
+        opt->stats->radiance_segments = h_cnt->radiance_segments;
+        opt->stats->shadow_segments = h_cnt->shadow_segments;
+        opt->stats->iterations = iterations;
+        opt->stats->kernel_launches = (uint32_t)(ctx->launches - launches0);
+    }
+    return 0;
+}
+
+int launch_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, unsigned width,
+                      unsigned height, const b200rt_pt_options* opt, int multigpu)
+{
+    B2_REQUIRE(ctx, d_params && sbt, "null argument");
+    B2_REQUIRE(ctx, sbt->hitgroupRecordBase && sbt->hitgroupRecordCount > 0 && sbt->hitgroupRecordStrideInBytes >= 64, "hit-group records required");
+    B2_REQUIRE(ctx, sbt->missRecordBase && sbt->missRecordCount > 0, "miss record required");
+    const uint64_t nl = (uint64_t)width * height;
+    B2_REQUIRE(ctx, nl < (1ull << 31), "launch too large");
+    if (nl == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    return multigpu ? run_pathtracer<1>(ctx, s, d_params, sbt, (uint32_t)nl, opt) : run_pathtracer<0>(ctx, s, d_params, sbt, (uint32_t)nl, opt);
+}
+
+int fill_samples(b200rt_context ctx, cudaStream_t s, int gpu_idx, int num_gpus, int width, int height, b200rt_deviceptr out, int num_samples)
+{
+    (void)height;
+    B2_REQUIRE(ctx, out && num_gpus > 0 && gpu_idx >= 0 && gpu_idx < num_gpus && width > 0 && num_samples >= 0, "bad argument");
+    DeviceGuard guard(ctx->device);
+    if (num_samples == 0) return 0;
+    fill_samples_kernel<<<div_up(num_samples, 256), 256, 0, s>>>(gpu_idx, num_gpus, width, (int2*)out, num_samples);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int deinterleave(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr gathered, int num_gpus, int num_samples, int width, int height,
+                 b200rt_deviceptr accum, b200rt_deviceptr frame)
+{
+    B2_REQUIRE(ctx, gathered && num_gpus > 0 && num_samples >= 0 && width > 0 && height > 0, "bad argument");
+    DeviceGuard guard(ctx->device);
+    const long long n = (long long)num_gpus * num_samples;
+    if (n == 0) return 0;
+    deinterleave_kernel<<<div_up(n, 256), 256, 0, s>>>((const float4*)gathered, num_gpus, num_samples, width, height, (float4*)accum, (uchar4*)frame);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int generate_synthetic_mesh(b200rt_context ctx, cudaStream_t s, uint64_t num_triangles, uint32_t seed, b200rt_deviceptr verts, b200rt_deviceptr mats,
+                            float* bounds_out)
+{
+    B2_REQUIRE(ctx, verts && mats && num_triangles >= 2 && num_triangles < (1ull << 30), "bad argument");
+    DeviceGuard guard(ctx->device);
+    const SynthLayout lay = synth_layout(num_triangles);
+    synth_mesh_kernel<<<div_up(num_triangles, 256), 256, 0, s>>>(lay, seed, (float4*)verts, (uint32_t*)mats);
+    B2_LAUNCH_CHECK(ctx);
+    if (bounds_out) {
+        bounds_out[0] = 0.f; bounds_out[1] = 0.f; bounds_out[2] = 0.f;
+        bounds_out[3] = 556.0f; bounds_out[4] = 548.8f; bounds_out[5] = 559.2f;
+    }
+    return 0;
+}
+
+}  // namespace b200rt

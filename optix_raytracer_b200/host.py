@@ -1,0 +1,544 @@
+"""Host-side mirror of the reference samples' launch plumbing, on top of the C ABI (include/b200rt.h).
+
+This is the Python test/bench harness equivalent of what the reference's C++ `main()`s do around
+`optixAccelBuild` / `optixLaunch` (SDK/optixPathTracer/optixPathTracer.cpp:424-511,576-898,
+SDK/optixRaycasting/optixRaycasting.cpp:94-349, SDK/optixMultiGPU/optixMultiGPU.cpp:479-594): it owns
+device buffers (torch tensors — plumbing only), fills the reference's Params / SBT record layouts
+byte for byte and calls the library.  All ray tracing happens in libb200rt.so.
+"""
+import ctypes as C
+import json
+import math
+import pathlib
+import struct
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+DATA_DIR = pathlib.Path(__file__).resolve().parent / "data"
+
+
+class B200RTError(RuntimeError):
+    pass
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Context:
+    """b200rt_context (replaces OptixDeviceContext; SDK/optixPathTracer/optixPathTracer.cpp:555-573)."""
+
+    def __init__(self, device=0, log_level=0):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise B200RTError("no CUDA device: b200rt has no CPU path")
+        self.device = device
+        self.torch_device = torch.device("cuda", device)
+        self._messages = []
+
+        def _cb(level, tag, msg, _):
+            self._messages.append((level, tag.decode(), msg.decode()))
+            if log_level >= 4:
+                print(f"[{level:2d}][{tag.decode():>12s}]: {msg.decode()}")
+
+        self._cb = L.LOG_CB(_cb)
+        h = C.c_void_p()
+        rc = self.lib.b200rt_context_create(device, self._cb, None, log_level, C.byref(h))
+        if rc:
+            raise B200RTError(f"b200rt_context_create: {self.lib.b200rt_error_name(rc).decode()}")
+        self.h = h
+
+    def check(self, rc, what=""):
+        if rc:
+            raise B200RTError(f"{what}: {self.lib.b200rt_error_name(rc).decode()} "
+                              f"({self.lib.b200rt_last_error_message(self.h).decode()})")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rt_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.b200rt_context_kernel_launches(self.h))
+
+    def to_device(self, arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.torch_device)
+
+    def empty_bytes(self, n, align=128):
+        # torch's caching allocator returns >= 512-byte aligned blocks
+        t = torch.empty(max(int(n), 1), dtype=torch.uint8, device=self.torch_device)
+        assert t.data_ptr() % align == 0
+        return t
+
+    # ---- acceleration structures ---------------------------------------------------------------
+    def build_accel(self, build_inputs, compact=True, keep=()):
+        """optixAccelComputeMemoryUsage + optixAccelBuild (+ optixAccelCompact), the sequence of
+        SDK/optixPathTracer/optixPathTracer.cpp:627-684.  Returns Accel."""
+        n = len(build_inputs)
+        arr = (L.BuildInput * n)(*build_inputs)
+        opts = L.AccelBuildOptions(L.BUILD_FLAG_ALLOW_COMPACTION if compact else 0, L.BUILD_OPERATION_BUILD)
+        sizes = L.AccelBufferSizes()
+        self.check(self.lib.b200rt_accel_compute_memory_usage(self.h, C.byref(opts), arr, n, C.byref(sizes)), "compute_memory_usage")
+        temp = self.empty_bytes(sizes.tempSizeInBytes)
+        out = self.empty_bytes(sizes.outputSizeInBytes)
+        csize = torch.zeros(1, dtype=torch.int64, device=self.torch_device)
+        emit = L.AccelEmitDesc(csize.data_ptr(), L.PROPERTY_TYPE_COMPACTED_SIZE)
+        handle = C.c_uint64()
+        self.check(self.lib.b200rt_accel_build(self.h, self.stream, C.byref(opts), arr, n, temp.data_ptr(), sizes.tempSizeInBytes,
+                                               out.data_ptr(), sizes.outputSizeInBytes, C.byref(handle), C.byref(emit), 1), "accel_build")
+        acc = Accel(self, out, handle.value, keep)
+        acc.uncompacted_bytes = int(sizes.outputSizeInBytes)
+        acc.temp_bytes = int(sizes.tempSizeInBytes)
+        if compact:
+            compacted = int(csize.item())
+            if compacted < sizes.outputSizeInBytes:
+                out2 = self.empty_bytes(compacted)
+                h2 = C.c_uint64()
+                self.check(self.lib.b200rt_accel_compact(self.h, self.stream, handle.value, out2.data_ptr(), compacted, C.byref(h2)),
+                           "accel_compact")
+                torch.cuda.synchronize(self.torch_device)
+                acc = Accel(self, out2, h2.value, keep)
+                acc.uncompacted_bytes = int(sizes.outputSizeInBytes)
+                acc.temp_bytes = int(sizes.tempSizeInBytes)
+        del temp
+        return acc
+
+    def triangle_input(self, vertices, indices=None, sbt_index=None, num_sbt=1, flags=None, vertex_stride=None, pre_transform=None,
+                       prim_offset=0):
+        """Make one OptixBuildInput-compatible triangle input from device tensors.
+        vertices: float32 tensor (any shape, contiguous); stride defaults to 12 ((n,3)) or 16 ((n,4))."""
+        bi = L.BuildInput()
+        bi.type = L.BUILD_INPUT_TYPE_TRIANGLES
+        ta = bi.triangleArray
+        if vertex_stride is None:
+            vertex_stride = vertices.shape[-1] * 4
+        nverts = vertices.numel() * 4 // vertex_stride
+        vb = (C.c_uint64 * 1)(vertices.data_ptr())
+        ta.vertexBuffers = vb
+        ta.numVertices = nverts
+        ta.vertexFormat = L.VERTEX_FORMAT_FLOAT3
+        ta.vertexStrideInBytes = vertex_stride
+        keep = [vertices, vb]
+        if indices is not None:
+            ta.indexBuffer = indices.data_ptr()
+            ta.numIndexTriplets = indices.numel() // 3
+            if indices.dtype == torch.int16 or indices.dtype == torch.uint16:
+                ta.indexFormat = L.INDICES_FORMAT_UNSIGNED_SHORT3
+                ta.indexStrideInBytes = 6
+            else:
+                ta.indexFormat = L.INDICES_FORMAT_UNSIGNED_INT3
+                ta.indexStrideInBytes = 12
+            keep.append(indices)
+        fl = (C.c_uint32 * num_sbt)(*(flags if flags is not None else [L.GEOMETRY_FLAG_DISABLE_ANYHIT] * num_sbt))
+        ta.flags = fl
+        ta.numSbtRecords = num_sbt
+        keep.append(fl)
+        if sbt_index is not None:
+            ta.sbtIndexOffsetBuffer = sbt_index.data_ptr()
+            ta.sbtIndexOffsetSizeInBytes = sbt_index.element_size()
+            ta.sbtIndexOffsetStrideInBytes = sbt_index.element_size()
+            keep.append(sbt_index)
+        if pre_transform is not None:
+            ta.preTransform = pre_transform.data_ptr()
+            ta.transformFormat = L.TRANSFORM_FORMAT_MATRIX_FLOAT12
+            keep.append(pre_transform)
+        ta.primitiveIndexOffset = prim_offset
+        bi._keep = keep
+        return bi
+
+    def instance_input(self, instances):
+        """instances: list of (transform12, sbt_offset, Accel).  SDK/sutil/Scene.cpp:1134-1212."""
+        n = len(instances)
+        arr = (L.Instance * n)()
+        keep = []
+        for i, (xf, sbt_off, acc) in enumerate(instances):
+            arr[i].transform = (C.c_float * 12)(*[float(x) for x in np.asarray(xf, np.float32).reshape(12)])
+            arr[i].instanceId = i
+            arr[i].sbtOffset = sbt_off
+            arr[i].visibilityMask = 1
+            arr[i].flags = 0
+            arr[i].traversableHandle = acc.handle
+            keep.append(acc)
+        dev = self.to_device(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+        bi = L.BuildInput()
+        bi.type = L.BUILD_INPUT_TYPE_INSTANCES
+        bi.instanceArray.instances = dev.data_ptr()
+        bi.instanceArray.numInstances = n
+        bi.instanceArray.instanceStride = 0
+        bi._keep = keep + [dev]
+        return bi
+
+    # ---- queries ---------------------------------------------------------------------------------
+    def trace_closest(self, accel, rays, ray_flags=0):
+        n = rays.shape[0]
+        ext = torch.empty((n, 5), dtype=torch.int32, device=self.torch_device)
+        self.check(self.lib.b200rt_trace_closest(self.h, self.stream, accel.handle, rays.data_ptr(), n, ray_flags, ext.data_ptr()), "trace_closest")
+        return ext
+
+    def trace_any(self, accel, rays, ray_flags=L.RAY_FLAG_TERMINATE_ON_FIRST_HIT):
+        n = rays.shape[0]
+        occ = torch.empty(n, dtype=torch.int32, device=self.torch_device)
+        self.check(self.lib.b200rt_trace_any(self.h, self.stream, accel.handle, rays.data_ptr(), n, ray_flags, occ.data_ptr()), "trace_any")
+        return occ
+
+    def trace_stats(self, accel, rays):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.b200rt_trace_stats(self.h, self.stream, accel.handle, rays.data_ptr(), rays.shape[0], C.byref(a), C.byref(b)), "trace_stats")
+        return a.value, b.value
+
+
+class Accel:
+    def __init__(self, ctx, buf, handle, keep=()):
+        self.ctx, self.buf, self.handle, self.keep = ctx, buf, handle, list(keep)
+
+    def info(self):
+        inf = L.AccelInfo()
+        self.ctx.check(self.ctx.lib.b200rt_accel_get_info(self.ctx.h, self.handle, C.byref(inf)), "accel_get_info")
+        return inf
+
+
+def ext_hits_to_numpy(ext):
+    a = ext.cpu().numpy()
+    return {"t": a[:, 0].view(np.float32).copy(), "prim": a[:, 1].astype(np.uint32), "inst": a[:, 2].astype(np.uint32),
+            "b1": a[:, 3].view(np.float32).copy(), "b2": a[:, 4].view(np.float32).copy()}
+
+
+# ---- host sutil mirrors -----------------------------------------------------------------------------
+def camera_uvw(eye, lookat, up, fov_y, aspect):
+    lib = L.load()
+    U, V, W = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+    lib.b200rt_camera_uvw(_f3(eye), _f3(lookat), _f3(up), fov_y, aspect, U, V, W)
+    return np.array(U, np.float32), np.array(V, np.float32), np.array(W, np.float32)
+
+
+def wd_num_samples(w, h, ngpu):
+    return L.load().b200rt_wd_num_samples(w, h, ngpu)
+
+
+def wd_sample_pixel(w, h, ngpu, gpu, sample):
+    xy = (C.c_int32 * 2)()
+    L.load().b200rt_wd_sample_pixel(w, h, ngpu, gpu, sample, xy)
+    return xy[0], xy[1]
+
+
+# ---- reference launch structs -------------------------------------------------------------------------
+class ParallelogramLight(C.Structure):
+    _fields_ = [("corner", C.c_float * 3), ("v1", C.c_float * 3), ("v2", C.c_float * 3), ("normal", C.c_float * 3),
+                ("emission", C.c_float * 3)]
+
+
+class PTParams(C.Structure):  # SDK/optixPathTracer/optixPathTracer.h:91-107 (152 bytes)
+    _fields_ = [("subframe_index", C.c_uint32), ("accum_buffer", C.c_uint64), ("frame_buffer", C.c_uint64), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("samples_per_launch", C.c_uint32), ("eye", C.c_float * 3), ("U", C.c_float * 3),
+                ("V", C.c_float * 3), ("W", C.c_float * 3), ("light", ParallelogramLight), ("handle", C.c_uint64)]
+
+
+class MGParams(C.Structure):  # SDK/optixMultiGPU/optixMultiGPU.h:46-64 (168 bytes)
+    _fields_ = [("subframe_index", C.c_uint32), ("sample_index_buffer", C.c_uint64), ("sample_accum_buffer", C.c_uint64),
+                ("result_buffer", C.c_uint64), ("width", C.c_uint32), ("height", C.c_uint32), ("samples_per_launch", C.c_uint32),
+                ("device_idx", C.c_uint32), ("eye", C.c_float * 3), ("U", C.c_float * 3), ("V", C.c_float * 3), ("W", C.c_float * 3),
+                ("light", ParallelogramLight), ("handle", C.c_uint64)]
+
+
+class RaycastParams(C.Structure):  # SDK/optixRaycasting/optixRaycasting.h:41-46 (24 bytes)
+    _fields_ = [("handle", C.c_uint64), ("rays", C.c_uint64), ("hits", C.c_uint64)]
+
+
+assert C.sizeof(PTParams) == 152 and C.sizeof(MGParams) == 168 and C.sizeof(RaycastParams) == 24
+
+
+def load_cornell():
+    d = json.loads((DATA_DIR / "cornell.json").read_text())
+    d["vertices"] = np.array(d["vertices"], np.float32)
+    d["mat_indices"] = np.array(d["mat_indices"], np.uint32)
+    d["emission_colors"] = np.array(d["emission_colors"], np.float32)
+    d["diffuse_colors"] = np.array(d["diffuse_colors"], np.float32)
+    return d
+
+
+def light_normal(v1, v2):
+    """normalize(cross(v1, v2)) as the reference's host vec_math computes it (optixPathTracer.cpp:439)."""
+    v1, v2 = np.asarray(v1, np.float32), np.asarray(v2, np.float32)
+    c = np.array([v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]], np.float32)
+    d = np.float32(c[0] * c[0]) + np.float32(c[1] * c[1]) + np.float32(c[2] * c[2])
+    return (c * (np.float32(1.0) / np.sqrt(d, dtype=np.float32))).astype(np.float32)
+
+
+class PathTracer:
+    """Mirror of optixPathTracer's state + launchSubframe (optixPathTracer.cpp:424-511,576-898), and of
+    optixMultiGPU's per-device state when multigpu=(gpu_idx, num_gpus) is given (optixMultiGPU.cpp:479-594).
+
+    vertices: (ntri*3, 4) float32 (the reference's Vertex{x,y,z,pad}); mat_indices: (ntri,) uint32."""
+
+    def __init__(self, ctx, width, height, samples_per_launch=16, scene=None, vertices=None, mat_indices=None, multigpu=None,
+                 compact=True):
+        self.ctx = ctx
+        sc = scene or load_cornell()
+        self.scene = sc
+        self.width, self.height, self.spl = width, height, samples_per_launch
+        dev = ctx.torch_device
+        if vertices is None:
+            v4 = np.zeros((sc["vertices"].shape[0], 4), np.float32)
+            v4[:, :3] = sc["vertices"]
+            vertices = ctx.to_device(v4)
+            mat_indices = ctx.to_device(sc["mat_indices"])
+        self.d_vertices, self.d_mat = vertices, mat_indices
+        nmat = len(sc["emission_colors"])
+        # buildMeshAccel (optixPathTracer.cpp:576-684): stride-16 float3 vertices, per-primitive u32 SBT index
+        bi = ctx.triangle_input(vertices, sbt_index=mat_indices, num_sbt=nmat, vertex_stride=16)
+        self.accel = ctx.build_accel([bi], compact=compact)
+        # createSBT (optixPathTracer.cpp:829-898 / optixMultiGPU.cpp:960-1018)
+        self.multigpu = multigpu
+        ray_types = 2 if multigpu else 1
+        rec = np.zeros((nmat * ray_types, 64), np.uint8)
+        for i in range(nmat):
+            data = struct.pack("<3f3fQ", *sc["emission_colors"][i], *sc["diffuse_colors"][i], vertices.data_ptr())
+            rec[i * ray_types, 32:64] = np.frombuffer(data, np.uint8)
+        self.d_hitgroup = ctx.to_device(rec)
+        miss = np.zeros((ray_types, 48), np.uint8)  # MissData{bg_color = 0}
+        self.d_miss = ctx.to_device(miss)
+        self.d_raygen = ctx.to_device(np.zeros(32, np.uint8))
+        self.sbt = L.ShaderBindingTable()
+        self.sbt.raygenRecord = self.d_raygen.data_ptr()
+        self.sbt.missRecordBase = self.d_miss.data_ptr()
+        self.sbt.missRecordStrideInBytes = 48
+        self.sbt.missRecordCount = ray_types
+        self.sbt.hitgroupRecordBase = self.d_hitgroup.data_ptr()
+        self.sbt.hitgroupRecordStrideInBytes = 64
+        self.sbt.hitgroupRecordCount = nmat * ray_types
+        # initLaunchParams + handleCameraUpdate (optixPathTracer.cpp:424-470)
+        cam, lt = sc["camera"], sc["light"]
+        U, V, W = camera_uvw(cam["eye"], cam["lookat"], cam["up"], cam["fov_y"], width / float(height))
+        light = ParallelogramLight(_f3(lt["corner"]), _f3(lt["v1"]), _f3(lt["v2"]), _f3(light_normal(lt["v1"], lt["v2"])), _f3(lt["emission"]))
+        self.frame = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
+        if multigpu:
+            gpu_idx, num_gpus = multigpu
+            self.num_samples = wd_num_samples(width, height, num_gpus)
+            self.sample_index = torch.zeros((self.num_samples, 2), dtype=torch.int32, device=dev)
+            ctx.check(ctx.lib.b200rt_fill_samples(ctx.h, ctx.stream, gpu_idx, num_gpus, width, height, self.sample_index.data_ptr(),
+                                                  self.num_samples), "fill_samples")
+            self.accum = torch.zeros((self.num_samples, 4), dtype=torch.float32, device=dev)
+            self.params = MGParams(0, self.sample_index.data_ptr(), self.accum.data_ptr(), self.frame.data_ptr(), width, height,
+                                   samples_per_launch, 3, _f3(cam["eye"]), _f3(U), _f3(V), _f3(W), light, self.accel.handle)
+        else:
+            self.accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+            self.params = PTParams(0, self.accum.data_ptr(), self.frame.data_ptr(), width, height, samples_per_launch, _f3(cam["eye"]),
+                                   _f3(U), _f3(V), _f3(W), light, self.accel.handle)
+        nbytes = C.sizeof(self.params)
+        self.h_params = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.d_params = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.stats = L.PTStats()
+
+    def launch_subframe(self, subframe_index=None, collect_stats=False):
+        """launchSubframe (optixPathTracer.cpp:488-511): copy Params to the device, launch; asynchronous."""
+        if subframe_index is not None:
+            self.params.subframe_index = subframe_index
+        self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
+        self.d_params.copy_(self.h_params, non_blocking=True)
+        opts = L.PTOptions(0, 1 if collect_stats else 0, C.pointer(self.stats))
+        ctx = self.ctx
+        if self.multigpu:
+            ctx.check(ctx.lib.b200rt_launch_multigpu(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.num_samples,
+                                                     C.byref(opts)), "launch_multigpu")
+        else:
+            ctx.check(ctx.lib.b200rt_launch_pathtracer(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.width, self.height,
+                                                       C.byref(opts)), "launch_pathtracer")
+        return self.stats if collect_stats else None
+
+
+# ---- glTF (the subset sutil::Scene loads: SDK/sutil/Scene.cpp:84-210,267-550) ---------------------------
+_GLTF_COMP = {5121: (np.uint8, 1), 5123: (np.uint16, 2), 5125: (np.uint32, 4), 5126: (np.float32, 4)}
+_GLTF_NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
+
+
+def _mat_from_node(node):
+    f = np.float32
+    m = np.eye(4, dtype=f)
+    if "matrix" in node:
+        m = np.array(node["matrix"], f).reshape(4, 4).T.copy()  # column-major in the file
+    t = np.eye(4, dtype=f)
+    if "translation" in node:
+        t[:3, 3] = np.array(node["translation"], f)
+    r = np.eye(4, dtype=f)
+    if "rotation" in node:
+        x, y, z, w = [f(v) for v in node["rotation"]]
+        # sutil::Quaternion::rotationMatrix (SDK/sutil/Quaternion.h:239-267)
+        qw, qx, qy, qz = w, x, y, z
+        r[:3, :3] = np.array([[1 - 2 * qy * qy - 2 * qz * qz, 2 * qx * qy - 2 * qz * qw, 2 * qx * qz + 2 * qy * qw],
+                              [2 * qx * qy + 2 * qz * qw, 1 - 2 * qx * qx - 2 * qz * qz, 2 * qy * qz - 2 * qx * qw],
+                              [2 * qx * qz - 2 * qy * qw, 2 * qy * qz + 2 * qx * qw, 1 - 2 * qx * qx - 2 * qy * qy]], f)
+    s = np.eye(4, dtype=f)
+    if "scale" in node:
+        s[0, 0], s[1, 1], s[2, 2] = [f(v) for v in node["scale"]]
+    return (m @ t @ r @ s).astype(f)
+
+
+def load_gltf(path):
+    """Returns dict(meshes=[{primitives:[{positions, normals, indices, stride info...}], aabb}], instances=[{transform(4x4), mesh, world_aabb}])."""
+    path = pathlib.Path(path)
+    g = json.loads(path.read_text())
+    buffers = [np.fromfile(path.parent / b["uri"], dtype=np.uint8) for b in g["buffers"]]
+
+    def accessor(idx):
+        a = g["accessors"][idx]
+        bv = g["bufferViews"][a["bufferView"]]
+        dt, sz = _GLTF_COMP[a["componentType"]]
+        nc = _GLTF_NCOMP[a["type"]]
+        off = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+        stride = bv.get("byteStride", 0) or sz * nc
+        raw = buffers[bv["buffer"]]
+        out = np.zeros((a["count"], nc), dt)
+        for i in range(nc):
+            out[:, i] = np.ndarray((a["count"],), dt, raw.data, off + i * sz, (stride,))
+        return out, a
+
+    meshes = []
+    for m in g["meshes"]:
+        prims = []
+        lo = np.full(3, np.inf, np.float32)
+        hi = np.full(3, -np.inf, np.float32)
+        for p in m["primitives"]:
+            if p.get("mode", 4) != 4:
+                continue
+            pos, pa = accessor(p["attributes"]["POSITION"])
+            if "min" in pa and "max" in pa:
+                lo = np.minimum(lo, np.array(pa["min"], np.float32))
+                hi = np.maximum(hi, np.array(pa["max"], np.float32))
+            nrm = accessor(p["attributes"]["NORMAL"])[0] if "NORMAL" in p["attributes"] else None
+            idx = accessor(p["indices"])[0].reshape(-1) if "indices" in p else None
+            prims.append({"positions": pos.astype(np.float32), "normals": None if nrm is None else nrm.astype(np.float32),
+                          "indices": idx, "material": p.get("material", -1)})
+        meshes.append({"primitives": prims, "aabb": (lo, hi)})
+    instances = []
+
+    def walk(ni, parent):
+        node = g["nodes"][ni]
+        xf = (parent @ _mat_from_node(node)).astype(np.float32)
+        if "camera" not in node and "mesh" in node:
+            lo, hi = meshes[node["mesh"]]["aabb"]
+            corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float32)
+            wc = (corners @ xf.T)[:, :3].astype(np.float32)
+            instances.append({"transform": xf, "mesh": node["mesh"], "world_aabb": (wc.min(0), wc.max(0))})
+        for c in node.get("children", []):
+            walk(c, xf)
+
+    scene = g["scenes"][g.get("scene", 0)]
+    for ni in scene["nodes"]:
+        walk(ni, np.eye(4, dtype=np.float32))
+    return {"meshes": meshes, "instances": instances}
+
+
+class Raycaster:
+    """Mirror of optixRaycasting's state (optixRaycasting.cpp:94-349) for a loaded glTF scene: one GAS per mesh
+    (one build input per primitive group), an IAS over the mesh instances, whitted::HitGroupData SBT records."""
+
+    def __init__(self, ctx, scene, compact=True):
+        self.ctx = ctx
+        self.scene = scene
+        dev = ctx.torch_device
+        self.mesh_accels, self.keep = [], []
+        records = []
+        self.mesh_sbt_base = []
+        for m in scene["meshes"]:
+            inputs = []
+            self.mesh_sbt_base.append(len(records))
+            for p in m["primitives"]:
+                d_pos = ctx.to_device(p["positions"])
+                d_nrm = ctx.to_device(p["normals"]) if p["normals"] is not None else None
+                idx = p["indices"]
+                d_idx = None
+                if idx is not None:
+                    d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
+                inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, vertex_stride=12))
+                self.keep += [d_pos, d_nrm, d_idx]
+                # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, TriangleMesh @8}; BufferView = {ptr, count, u16 stride, u16 elmt}
+                rec = bytearray(32 + 352)
+                def bview(t, elmt, stride):
+                    return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride, elmt)
+                isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
+                rec[32 + 8:32 + 24] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
+                rec[32 + 24:32 + 40] = bview(d_pos, 12, 12)
+                rec[32 + 40:32 + 56] = bview(d_nrm, 12, 12)
+                records.append(bytes(rec))
+            self.mesh_accels.append(ctx.build_accel(inputs, compact=compact))
+        self.d_hitgroup = ctx.to_device(np.frombuffer(b"".join(records), np.uint8).copy())
+        inst = []
+        for i in scene["instances"]:
+            inst.append((i["transform"][:3, :].reshape(12), self.mesh_sbt_base[i["mesh"]], self.mesh_accels[i["mesh"]]))
+        self.ias = ctx.build_accel([ctx.instance_input(inst)], compact=False)
+        self.sbt = L.ShaderBindingTable()
+        self.d_miss = ctx.to_device(np.zeros(32, np.uint8))
+        self.sbt.raygenRecord = self.d_miss.data_ptr()
+        self.sbt.missRecordBase = self.d_miss.data_ptr()
+        self.sbt.missRecordStrideInBytes = 32
+        self.sbt.missRecordCount = 1
+        self.sbt.hitgroupRecordBase = self.d_hitgroup.data_ptr()
+        self.sbt.hitgroupRecordStrideInBytes = 32 + 352
+        self.sbt.hitgroupRecordCount = len(records)
+        lo = np.min([i["world_aabb"][0] for i in scene["instances"]], axis=0).astype(np.float32)
+        hi = np.max([i["world_aabb"][1] for i in scene["instances"]], axis=0).astype(np.float32)
+        self.bbmin, self.bbmax = lo, hi
+
+    def buffer_rays(self, width):
+        """bufferRays (optixRaycasting.cpp:255-286)."""
+        ctx, dev = self.ctx, self.ctx.torch_device
+        span = (self.bbmax - self.bbmin).astype(np.float32)
+        self.width = width
+        self.height = int(np.float32(width) * span[1] / span[0])
+        n = self.width * self.height
+        self.rays = torch.empty((n, 8), dtype=torch.float32, device=dev)
+        ctx.check(ctx.lib.b200rt_create_rays_ortho(ctx.h, ctx.stream, self.rays.data_ptr(), self.width, self.height, _f3(self.bbmin),
+                                                   _f3(self.bbmax), 0.05), "create_rays_ortho")
+        self.rays_translated = self.rays.clone()
+        off = (span * np.array([0.2, 0, 0], np.float32)).astype(np.float32)
+        ctx.check(ctx.lib.b200rt_translate_rays(ctx.h, ctx.stream, self.rays_translated.data_ptr(), n, _f3(off)), "translate_rays")
+        self.hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.hits_translated = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.ext = torch.empty((n, 5), dtype=torch.int32, device=dev)
+        self.ext_translated = torch.empty((n, 5), dtype=torch.int32, device=dev)
+        self.translate_offset = off
+        p1 = RaycastParams(self.ias.handle, self.rays.data_ptr(), self.hits.data_ptr())
+        p2 = RaycastParams(self.ias.handle, self.rays_translated.data_ptr(), self.hits_translated.data_ptr())
+        self.d_params = ctx.to_device(np.frombuffer(bytes(p1), np.uint8).copy())
+        self.d_params_translated = ctx.to_device(np.frombuffer(bytes(p2), np.uint8).copy())
+        return n
+
+    def launch(self, want_ext=True):
+        """launch (optixRaycasting.cpp:289-317): both batches (the reference uses two streams; same stream here)."""
+        ctx = self.ctx
+        ctx.check(ctx.lib.b200rt_launch_raycast(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.width, self.height,
+                                                self.ext.data_ptr() if want_ext else 0), "launch_raycast")
+        ctx.check(ctx.lib.b200rt_launch_raycast(ctx.h, ctx.stream, self.d_params_translated.data_ptr(), C.byref(self.sbt), self.width,
+                                                self.height, self.ext_translated.data_ptr() if want_ext else 0), "launch_raycast")
+
+    def shade(self, hits):
+        ctx = self.ctx
+        n = hits.shape[0]
+        img = torch.empty((n, 3), dtype=torch.float32, device=ctx.torch_device)
+        ctx.check(ctx.lib.b200rt_shade_hits(ctx.h, ctx.stream, img.data_ptr(), n, hits.data_ptr()), "shade_hits")
+        return img
+
+
+def synthetic_mesh(ctx, num_triangles, seed=0):
+    """Procedural tessellated scene of BASELINE.json configs[4] generated on the device."""
+    dev = ctx.torch_device
+    verts = torch.empty((num_triangles * 3, 4), dtype=torch.float32, device=dev)
+    mats = torch.empty(num_triangles, dtype=torch.int32, device=dev)
+    b = (C.c_float * 6)()
+    ctx.check(ctx.lib.b200rt_generate_synthetic_mesh(ctx.h, ctx.stream, num_triangles, seed, verts.data_ptr(), mats.data_ptr(), b), "synthetic_mesh")
+    return verts, mats

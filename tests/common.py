@@ -1,0 +1,131 @@
+"""Shared helpers for the parity tests (scene fixtures, oracle scene construction)."""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
+
+
+def duck_scene():
+    """The reference's Duck.gltf as a host.load_gltf-shaped dict (from tests/golden/duck_mesh.npz)."""
+    z = np.load(GOLDEN / "duck_mesh.npz")
+    prim = {"positions": z["positions"], "normals": z["normals"], "indices": z["indices"], "material": 0}
+    mesh = {"primitives": [prim], "aabb": (z["aabb_lo"], z["aabb_hi"])}
+    inst = {"transform": z["transform"], "mesh": 0, "world_aabb": (z["world_lo"], z["world_hi"])}
+    return {"meshes": [mesh], "instances": [inst]}
+
+
+def deindex(prim):
+    """(ntri,3,3) object-space triangles and per-triangle vertex normals of one primitive group."""
+    idx = prim["indices"].astype(np.int64).reshape(-1, 3)
+    tris = prim["positions"][idx]
+    nrm = None if prim["normals"] is None else prim["normals"][idx]
+    return tris.astype(np.float32), None if nrm is None else nrm.astype(np.float32)
+
+
+def oracle_pt_params(orc, params, mode, nmat=4):
+    """orc.PTParams from a host.PTParams / host.MGParams."""
+    p = orc.PTParams()
+    p.subframe_index, p.width, p.height = params.subframe_index, params.width, params.height
+    p.samples_per_launch, p.nmat, p.mode = params.samples_per_launch, nmat, mode
+    for k in ("eye", "U", "V", "W"):
+        setattr(p, k, getattr(params, k))
+    for k in ("corner", "v1", "v2", "normal", "emission"):
+        setattr(p, "light_" + k, getattr(params.light, k))
+    p.bg = (C.c_float * 3)(0.0, 0.0, 0.0)
+    return p
+
+
+def random_rays(rng, n, lo, hi, tmin=0.0, tmax=1e16):
+    """Rays with origins in a padded box and directions towards random points of the box (plus axis-aligned
+    and degenerate-component directions, which exercise the clamped-direction box tests)."""
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    ext = hi - lo
+    o = (lo - 0.3 * ext + rng.random((n, 3), dtype=np.float32) * 1.6 * ext).astype(np.float32)
+    tgt = (lo + rng.random((n, 3), dtype=np.float32) * ext).astype(np.float32)
+    d = tgt - o
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    k = n // 8
+    axes = np.eye(3, dtype=np.float32)
+    d[:k] = axes[rng.integers(0, 3, k)] * rng.choice(np.array([-1.0, 1.0], np.float32), (k, 1))
+    zero_one = rng.integers(0, 3, k)
+    d[k:2 * k][np.arange(k), zero_one] = 0.0
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = o
+    rays[:, 3] = tmin
+    rays[:, 4:7] = d.astype(np.float32)
+    rays[:, 7] = tmax
+    return rays
+
+
+def decode_gas(blob):
+    """Decode a GAS blob (optix_raytracer_b200/csrc/accel.h) downloaded from the device into numpy views."""
+    hdr = np.frombuffer(blob[:128].tobytes(), dtype=np.uint32)
+    assert hdr[0] == 0x54523242 and hdr[1] == 1, "not a GAS blob"
+    num_tris, num_nodes = int(hdr[2]), int(hdr[3])
+    nodes_off, tris_off, total = [int(x) for x in np.frombuffer(blob[16:40].tobytes(), dtype=np.uint64)]
+    bounds = np.frombuffer(blob[40:64].tobytes(), dtype=np.float32)
+    nodes = np.frombuffer(blob[nodes_off:nodes_off + 80 * num_nodes].tobytes(), dtype=np.uint8).reshape(num_nodes, 80)
+    tris = np.frombuffer(blob[tris_off:tris_off + 48 * num_tris].tobytes(), dtype=np.float32).reshape(num_tris, 3, 4)
+    return {"num_tris": num_tris, "num_nodes": num_nodes, "nodes": nodes, "tris": tris, "bounds": bounds, "total_bytes": total,
+            "depth": int(hdr[18])}
+
+
+def validate_gas(gas, pad_check=True):
+    """Structural invariants of the 8-wide BVH: every triangle referenced exactly once, every child box
+    (decoded exactly as the traversal does: P + q * 2^e) contains all triangles below it, inner children are
+    stored in slot order.  Returns (max_depth, leaf_count)."""
+    nodes, tris = gas["nodes"], gas["tris"]
+    n = gas["num_tris"]
+    if n == 0:
+        return 0, 0
+    seen = np.zeros(n, np.int32)
+    ordinals = tris[:, 2, 3].view(np.uint32)
+    assert np.array_equal(np.sort(ordinals), np.arange(n, dtype=np.uint32)), "triangle ordinals are not a permutation"
+    node_seen = np.zeros(gas["num_nodes"], np.int32)
+    max_depth, leaves = 0, 0
+    stack = [(0, None, None, 1)]
+    while stack:
+        ni, blo, bhi, depth = stack.pop()
+        node_seen[ni] += 1
+        max_depth = max(max_depth, depth)
+        raw = nodes[ni]
+        P = raw[0:12].view(np.float32).astype(np.float64)
+        e = raw[12:15].astype(np.int64)
+        imask = int(raw[15])
+        child_base, tri_base = [int(x) for x in raw[16:24].view(np.uint32)]
+        meta = raw[24:32]
+        q = raw[32:80].reshape(6, 8).astype(np.float64)  # qlo x,y,z ; qhi x,y,z
+        scale = np.ldexp(1.0, e - 127)
+        for s in range(8):
+            m = int(meta[s])
+            if m == 0:
+                continue
+            lo = P + q[0:3, s] * scale
+            hi = P + q[3:6, s] * scale
+            assert np.all(lo <= hi)
+            if blo is not None and pad_check:
+                pass  # child boxes need not nest exactly inside the (separately quantised) parent box
+            if (m >> 5) == 1 and (m & 0x1f) >= 24:
+                assert (m & 0x1f) == 24 + s, "inner meta must encode its slot"
+                assert imask >> s & 1
+                ci = child_base + bin(imask & ((1 << s) - 1)).count("1")
+                stack.append((ci, lo, hi, depth + 1))
+                # all triangles below ci must be inside (lo,hi): checked when they are reached via box chain
+                _check_subtree_box = (lo, hi)
+                stack[-1] = (ci, lo, hi, depth + 1)
+            else:
+                assert not (imask >> s & 1)
+                cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
+                off = m & 0x1f
+                leaves += 1
+                for t in range(tri_base + off, tri_base + off + cnt):
+                    seen[t] += 1
+                    v = tris[t, :, :3].astype(np.float64)
+                    assert np.all(v >= lo - 0) and np.all(v <= hi + 0), f"triangle {t} outside its leaf box"
+                    if blo is not None:
+                        assert np.all(v >= blo) and np.all(v <= bhi), f"triangle {t} outside its parent's child box"
+    assert np.all(seen == 1), f"{(seen != 1).sum()} triangles not referenced exactly once"
+    assert np.all(node_seen == 1), f"{(node_seen != 1).sum()} nodes not referenced exactly once"
+    return max_depth, leaves
