@@ -216,10 +216,19 @@ typedef struct b200rt_pt_stats {
     uint64_t shadow_segments;    /* occlusion rays traced */
     uint32_t iterations;         /* wavefront iterations (trace+shade pairs) */
     uint32_t kernel_launches;    /* kernels launched by this call */
+    uint64_t nodes_fetched;      /* B200RT_PT_STATS_TRAVERSAL: 8-wide nodes fetched by the trace stage */
+    uint64_t tris_tested;        /* B200RT_PT_STATS_TRAVERSAL: triangle records tested by the trace stage */
+    float trace_ms;              /* B200RT_PT_STATS_TIMING: sum of CUDA-event durations of the trace kernels */
+    float shade_ms;              /* B200RT_PT_STATS_TIMING: same for the shade kernels */
+    uint32_t trace_launches;     /* launches that had at least one active lane */
+    uint32_t reserved;
 } b200rt_pt_stats;
+#define B200RT_PT_STATS_SEGMENTS 1u   /* fill segment / iteration / launch counts */
+#define B200RT_PT_STATS_TIMING 2u     /* bracket every stage kernel with CUDA events on `stream` (profiling pass) */
+#define B200RT_PT_STATS_TRAVERSAL 4u  /* run the instrumented trace kernel that counts nodes / triangles (not for timing) */
 typedef struct b200rt_pt_options {
     uint32_t reserved0;
-    uint32_t collect_stats;      /* 1: fill *stats (synchronises the stream at the end of the launch) */
+    uint32_t collect_stats;      /* bit mask of B200RT_PT_STATS_*; non-zero fills *stats */
     b200rt_pt_stats* stats;      /* host pointer or NULL */
 } b200rt_pt_options;
 int b200rt_launch_pathtracer(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,

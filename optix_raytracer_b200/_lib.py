@@ -25,6 +25,7 @@ RAY_FLAG_TERMINATE_ON_FIRST_HIT = 1 << 2
 RAY_FLAG_CULL_BACK_FACING_TRIANGLES = 1 << 4
 RAY_FLAG_CULL_FRONT_FACING_TRIANGLES = 1 << 5
 SBT_RECORD_HEADER_SIZE = 32
+PT_STATS_SEGMENTS, PT_STATS_TIMING, PT_STATS_TRAVERSAL = 1, 2, 4
 
 
 class TriangleArray(C.Structure):
@@ -82,7 +83,9 @@ class AccelInfo(C.Structure):
 
 
 class PTStats(C.Structure):
-    _fields_ = [("radiance_segments", u64), ("shadow_segments", u64), ("iterations", u32), ("kernel_launches", u32)]
+    _fields_ = [("radiance_segments", u64), ("shadow_segments", u64), ("iterations", u32), ("kernel_launches", u32),
+                ("nodes_fetched", u64), ("tris_tested", u64), ("trace_ms", f32), ("shade_ms", f32), ("trace_launches", u32),
+                ("reserved", u32)]
 
 
 class PTOptions(C.Structure):

@@ -147,6 +147,7 @@ int b200rt_context_destroy(b200rt_context ctx)
         if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         if (ctx->ev) cudaEventDestroy(ctx->ev);
+        for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
     }
     delete ctx;
     return 0;

@@ -6,6 +6,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/b200rt.h"
 
@@ -31,6 +32,7 @@ struct b200rt_context_t {
     void* pinned = nullptr;   // small pinned host block for counter read-back
     cudaEvent_t ev = nullptr;
     std::mutex mu;
+    std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 

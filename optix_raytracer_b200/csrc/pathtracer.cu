@@ -20,6 +20,8 @@
 // sample) and its RNG stream order (2 jitter draws from the pixel seed; per bounce: 2 bounce, 2
 // light, 1 roulette draw from the path seed) are preserved exactly; with the arithmetic contract of
 // rt_math.cuh the accumulated radiance is bit-identical to the scalar oracle.
+#include <string.h>
+
 #include "accel.h"
 #include "internal.h"
 #include "traverse.cuh"
@@ -94,6 +96,7 @@ struct Counters {
     unsigned int qcount[2];
     unsigned int pad[2];
     unsigned long long radiance_segments, shadow_segments;
+    unsigned long long nodes_fetched, tris_tested;
 };
 
 struct Lanes {
@@ -176,9 +179,10 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
 }
 
 // ---- TRACE ---------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
 {
+    TravStats st{0, 0};
     const Frame f = load_frame<MODE>(params);
     const uint32_t n = L.counters->qcount[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->qcount[cur ^ 1] = 0;  // SHADE of this iteration appends there
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ 
             const float4 so = L.shd_o[lane], sd = L.shd_d[lane], pa = L.pend[lane];
             RayHit sh;
             ++nshd;
-            const bool occluded = trace_handle<true, false>(f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, so.w,
-                                                            B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT, sh, nullptr);
+            const bool occluded = trace_handle<true, STATS>(f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, so.w,
+                                                            B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT, sh, &st);
             const float weight = occluded ? 0.0f : sd.w;
             if (MODE == 0) {
                 // prd.radiance = light.emission * weight; result += prd.radiance * prd.attenuation
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ 
             const float4 ro = L.ray_o[lane];
             RayHit hit;
             ++nrad;
-            const bool found = trace_handle<false, false>(f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 1e16f, 0u, hit, nullptr);
+            const bool found = trace_handle<false, STATS>(f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 1e16f, 0u, hit, &st);
             res.w = found ? hit.t : -1.0f;
             if (found) L.hitp[lane] = make_uint2(hit.prim, hit.sbt);
         }
@@ -233,6 +237,16 @@ __global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ 
     if ((threadIdx.x & 31) == 0 && (nrad | nshd)) {
         atomicAdd(&L.counters->radiance_segments, (unsigned long long)nrad);
         atomicAdd(&L.counters->shadow_segments, (unsigned long long)nshd);
+    }
+    if (STATS) {
+        for (int off = 16; off; off >>= 1) {
+            st.nodes += __shfl_xor_sync(0xffffffffu, st.nodes, off);
+            st.tris += __shfl_xor_sync(0xffffffffu, st.tris, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&L.counters->nodes_fetched, (unsigned long long)st.nodes);
+            atomicAdd(&L.counters->tris_tested, (unsigned long long)st.tris);
+        }
     }
 }
 
@@ -474,27 +488,35 @@ __host__ __device__ inline SynthLayout synth_layout(uint64_t total)
     return s;
 }
 
+// All arithmetic below is in the contract's named operations (fm / fdiv / det_sincos), so the oracle's
+// restatement (oracle.cpp: synth_*) produces bit-identical vertices.
 __device__ __forceinline__ float3 blob_vertex(int b, uint32_t i, uint32_t j, uint32_t rows, uint32_t cols, uint32_t seed)
 {
     const int bx = b % 3, by = (b / 3) % 3, bz = b / 9;
-    const float3 ctr = f3(139.0f + 139.0f * bx, 110.0f + 160.0f * by, 140.0f + 140.0f * bz);
+    const float3 ctr = f3(139.0f + 139.0f * (float)bx, 110.0f + 160.0f * (float)by, 140.0f + 140.0f * (float)bz);
     const float rad = 48.0f;
     if (i == 0) return f3(ctr.x, ctr.y + rad, ctr.z);
     if (i == rows) return f3(ctr.x, ctr.y - rad, ctr.z);
     j = j % cols;
-    const float theta = 3.14159265358979f * (float)i / (float)rows;
-    const float phi = 6.28318530717959f * (float)j / (float)cols;
-    const float st = sinf(theta), ct = cosf(theta), sp = sinf(phi), cp = cosf(phi);
+    const float theta = fdiv(3.14159265358979f * (float)i, (float)rows);
+    const float phi = fdiv(6.28318530717959f * (float)j, (float)cols);
+    float st, ct, sp, cp, s1, s2, s3, s4, unused;
+    det_sincos(theta, st, ct);
+    det_sincos(phi, sp, cp);
     const float ph = 0.37f * (float)((seed + 7u * (uint32_t)b) % 17u);
-    const float disp = 1.0f + st * (0.14f * sinf(5.0f * theta + ph) * sinf(4.0f * phi + ph) + 0.04f * sinf(23.0f * theta) * sinf(17.0f * phi));
+    det_sincos(fm(5.0f, theta, ph), s1, unused);
+    det_sincos(fm(4.0f, phi, ph), s2, unused);
+    det_sincos(23.0f * theta, s3, unused);
+    det_sincos(17.0f * phi, s4, unused);
+    const float disp = fm(st, fm(0.14f * s1, s2, (0.04f * s3) * s4), 1.0f);
     const float rr = rad * disp;
-    return f3(ctr.x + rr * st * cp, ctr.y + rr * ct, ctr.z + rr * st * sp);
+    return f3(fm(rr * st, cp, ctr.x), fm(rr, ct, ctr.y), fm(rr * st, sp, ctr.z));
 }
 
 __device__ __forceinline__ float3 wall_vertex(int wall, uint32_t i, uint32_t j, uint32_t grid)
 {
     const float X = 556.0f, Y = 548.8f, Z = 559.2f;
-    const float u = (float)i / (float)grid, v = (float)j / (float)grid;
+    const float u = fdiv((float)i, (float)grid), v = fdiv((float)j, (float)grid);
     switch (wall) {
         case 0: return f3(X * u, 0.0f, Z * v);   // floor
         case 1: return f3(X * u, Y, Z * v);      // ceiling
@@ -540,7 +562,8 @@ __global__ void __launch_bounds__(256) synth_mesh_kernel(SynthLayout s, uint32_t
             a = b = c = f3(343.0f, 548.6f, 227.0f);  // odd leftover: zero-area triangle (never hit)
         } else {
             const uint64_t q = r >> 1;
-            const float x0 = 343.0f - 130.0f * (float)q / (float)K, x1 = (q + 1 == K) ? 213.0f : 343.0f - 130.0f * (float)(q + 1) / (float)K;
+            const float x0 = fm(-130.0f, fdiv((float)q, (float)K), 343.0f);
+            const float x1 = (q + 1 == K) ? 213.0f : fm(-130.0f, fdiv((float)(q + 1), (float)K), 343.0f);
             const float3 p00 = f3(x0, 548.6f, 227.0f), p01 = f3(x0, 548.6f, 332.0f), p10 = f3(x1, 548.6f, 227.0f), p11 = f3(x1, 548.6f, 332.0f);
             if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
         }
@@ -591,16 +614,31 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     pt_init_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, nlanes);
     B2_LAUNCH_CHECK(ctx);
     Counters* h_cnt = (Counters*)((char*)ctx->pinned + 256);
+    const uint32_t want = (opt && opt->stats) ? opt->collect_stats : 0u;
+    const bool timing = (want & B200RT_PT_STATS_TIMING) != 0, travstats = (want & B200RT_PT_STATS_TRAVERSAL) != 0;
+    size_t nev = 0;
+    auto next_event = [&]() -> cudaEvent_t {
+        if (nev == ctx->timing_events.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            ctx->timing_events.push_back(e);
+        }
+        return ctx->timing_events[nev++];
+    };
     int cur = 0;
     uint32_t iterations = 0;
     const int CHECK_EVERY = 8;
     for (;;) {
         for (int k = 0; k < CHECK_EVERY; ++k) {
-            pt_trace_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur);
+            if (timing) cudaEventRecord(next_event(), s);
+            if (travstats) pt_trace_kernel<MODE, true><<<grid, 256, 0, s>>>(params, ln, cur);
+            else pt_trace_kernel<MODE, false><<<grid, 256, 0, s>>>(params, ln, cur);
             B2_LAUNCH_CHECK(ctx);
+            if (timing) cudaEventRecord(next_event(), s);
             pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,
                                                        sbt->hitgroupRecordCount, (const char*)sbt->missRecordBase);
             B2_LAUNCH_CHECK(ctx);
+            if (timing) cudaEventRecord(next_event(), s);
             cur ^= 1;
             ++iterations;
         }
@@ -609,11 +647,25 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
         if (h_cnt->qcount[cur] == 0) break;
         if (iterations > 100000) return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "path tracer did not terminate");
     }
-    if (opt && opt->collect_stats && opt->stats) {
-        opt->stats->radiance_segments = h_cnt->radiance_segments;
-        opt->stats->shadow_segments = h_cnt->shadow_segments;
-        opt->stats->iterations = iterations;
-        opt->stats->kernel_launches = (uint32_t)(ctx->launches - launches0);
+    if (want) {
+        b200rt_pt_stats* st = opt->stats;
+        memset(st, 0, sizeof(*st));
+        st->radiance_segments = h_cnt->radiance_segments;
+        st->shadow_segments = h_cnt->shadow_segments;
+        st->iterations = iterations;
+        st->kernel_launches = (uint32_t)(ctx->launches - launches0);
+        st->nodes_fetched = h_cnt->nodes_fetched;
+        st->tris_tested = h_cnt->tris_tested;
+        if (timing) {
+            for (size_t i = 0; i + 2 < nev; i += 3) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, ctx->timing_events[i], ctx->timing_events[i + 1]);
+                cudaEventElapsedTime(&b, ctx->timing_events[i + 1], ctx->timing_events[i + 2]);
+                st->trace_ms += a;
+                st->shade_ms += b;
+            }
+            st->trace_launches = iterations;
+        }
     }
     return 0;
 }

@@ -350,7 +350,7 @@ class PathTracer:
             self.params.subframe_index = subframe_index
         self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
         self.d_params.copy_(self.h_params, non_blocking=True)
-        opts = L.PTOptions(0, 1 if collect_stats else 0, C.pointer(self.stats))
+        opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))  # bit mask of L.PT_STATS_*
         ctx = self.ctx
         if self.multigpu:
             ctx.check(ctx.lib.b200rt_launch_multigpu(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.num_samples,

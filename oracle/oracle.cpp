@@ -172,6 +172,17 @@ static inline bool tri_hit(const RayPrep& r, const Tri& tr, float tmin, float tm
 // over all triangles, the answer does not depend on this structure; tests cross-check it against
 // brute force.
 // ------------------------------------------------------------------------------------------
+template <class F>
+static void parallel_rows(int rows, int threads, F fn)
+{
+    if (threads <= 1) { for (int y = 0; y < rows; ++y) fn(y, 0); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t] { for (int y; (y = next.fetch_add(1)) < rows;) fn(y, t); });
+    for (auto& th : pool) th.join();
+}
+
 struct BNode { f3 lo, hi; int left, right, first, count; };
 
 struct Geometry {
@@ -183,7 +194,7 @@ struct Geometry {
     uint64_t node_visits = 0, tri_tests = 0;  // single-thread instrumentation only
 };
 
-static void build_bvh(Geometry& g)
+static void build_bvh(Geometry& g, int threads = 1)
 {
     const size_t n = g.tris.size();
     g.nodes.clear();
@@ -192,20 +203,20 @@ static void build_bvh(Geometry& g)
     g.brute = n <= 64;  // default: tiny scenes are traced brute force (the exact definition)
     if (n == 0) return;
     std::vector<f3> cen(n), lo(n), hi(n);
-    for (size_t i = 0; i < n; ++i) {
-        const Tri& t = g.tris[i];
-        lo[i] = mk(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)), fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
-        hi[i] = mk(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)), fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
-        cen[i] = (lo[i] + hi[i]) * 0.5f;
-    }
-    g.nodes.reserve(2 * n / 3 + 16);
+    parallel_rows((int)((n + 65535) / 65536), threads, [&](int row, int) {
+        const size_t b = (size_t)row * 65536, e = std::min(n, b + 65536);
+        for (size_t i = b; i < e; ++i) {
+            const Tri& t = g.tris[i];
+            lo[i] = mk(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)), fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
+            hi[i] = mk(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)), fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
+            cen[i] = (lo[i] + hi[i]) * 0.5f;
+        }
+    });
+    g.nodes.assign(2 * n + 2, BNode{});
+    std::atomic<int> next_node{1};
     struct Job { int node, first, count; };
-    std::vector<Job> stack;
-    g.nodes.push_back({});
-    stack.push_back({0, 0, (int)n});
-    while (!stack.empty()) {
-        Job j = stack.back();
-        stack.pop_back();
+    // processes one job; returns the two child jobs (count 0 => leaf)
+    auto split = [&](Job j, Job& a, Job& b) -> bool {
         f3 blo = mk(INFINITY, INFINITY, INFINITY), bhi = mk(-INFINITY, -INFINITY, -INFINITY);
         f3 clo = blo, chi = bhi;
         for (int i = j.first; i < j.first + j.count; ++i) {
@@ -225,24 +236,48 @@ static void build_bvh(Geometry& g)
         nd.first = j.first;
         nd.count = j.count;
         nd.left = nd.right = -1;
-        if (j.count <= 4) continue;
+        if (j.count <= 4) return false;
         f3 ce = chi - clo;
         int axis = ce.x >= ce.y ? (ce.x >= ce.z ? 0 : 2) : (ce.y >= ce.z ? 1 : 2);
         int mid = j.first + j.count / 2;
         std::nth_element(g.order.begin() + j.first, g.order.begin() + mid, g.order.begin() + j.first + j.count,
-                         [&](uint32_t a, uint32_t b) {
-                             float ca = get(cen[a], axis), cb = get(cen[b], axis);
-                             return ca < cb || (ca == cb && a < b);
+                         [&](uint32_t x, uint32_t y) {
+                             float cx = get(cen[x], axis), cy = get(cen[y], axis);
+                             return cx < cy || (cx == cy && x < y);
                          });
-        int l = (int)g.nodes.size();
-        g.nodes.push_back({});
-        g.nodes.push_back({});
-        g.nodes[j.node].left = l;
-        g.nodes[j.node].right = l + 1;
-        g.nodes[j.node].count = 0;
-        stack.push_back({l, j.first, mid - j.first});
-        stack.push_back({l + 1, mid, j.first + j.count - mid});
+        int l = next_node.fetch_add(2);
+        nd.left = l;
+        nd.right = l + 1;
+        nd.count = 0;
+        a = {l, j.first, mid - j.first};
+        b = {l + 1, mid, j.first + j.count - mid};
+        return true;
+    };
+    auto run_serial = [&](Job root) {
+        std::vector<Job> stack{root};
+        while (!stack.empty()) {
+            Job j = stack.back();
+            stack.pop_back();
+            Job a, b;
+            if (split(j, a, b)) { stack.push_back(a); stack.push_back(b); }
+        }
+    };
+    // top levels serially until there are enough independent subtrees, then one thread per subtree
+    std::vector<Job> frontier{{0, 0, (int)n}};
+    while (threads > 1 && frontier.size() < (size_t)threads * 4) {
+        std::vector<Job> next;
+        bool any = false;
+        for (Job j : frontier) {
+            Job a, b;
+            if (j.count > 4096 && split(j, a, b)) { next.push_back(a); next.push_back(b); any = true; }
+            else next.push_back(j);
+        }
+        frontier.swap(next);
+        if (!any) break;
     }
+    // every job left in the frontier is still unprocessed (split() replaces a job by its two children)
+    parallel_rows((int)frontier.size(), threads, [&](int k, int) { run_serial(frontier[k]); });
+    g.nodes.resize((size_t)next_node.load());
 }
 
 struct HitRec { float t; uint32_t prim; float b1, b2; float det; };
@@ -524,17 +559,6 @@ static f3 pt_pixel(Scene& sc, const PTParams& P, int px, int py, int mode, uint6
     return mk(result.x / spl, result.y / spl, result.z / spl);
 }
 
-template <class F>
-static void parallel_rows(int rows, int threads, F fn)
-{
-    if (threads <= 1) { for (int y = 0; y < rows; ++y) fn(y, 0); return; }
-    std::atomic<int> next{0};
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&, t] { for (int y; (y = next.fetch_add(1)) < rows;) fn(y, t); });
-    for (auto& th : pool) th.join();
-}
-
 }  // namespace
 
 // ============================================================================================
@@ -604,7 +628,7 @@ void* orc_scene_create(const float* verts, int64_t ntri, const uint32_t* sbt)
         g.tris[(size_t)i] = {mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8])};
     }
     if (sbt) g.sbt.assign(sbt, sbt + ntri);
-    build_bvh(g);
+    build_bvh(g, (int)std::max(1u, std::thread::hardware_concurrency()));
     return s;
 }
 // add one instance of geometry 0 with a row-major 3x4 object->world transform
@@ -776,3 +800,110 @@ uint64_t orc_pathtrace(void* scene, const orc_pt_params* p, const float* emissio
 }
 
 }  // extern "C"
+
+// ---- synthetic tessellated scene (BASELINE.json configs[4]) ------------------------------------------
+// Independent restatement of the product's procedural mesh (optix_raytracer_b200/csrc/pathtracer.cu,
+// synth_*): same closed-form vertex functions in the contract's named operations, so the vertices are
+// bit-identical to the GPU generator (checked by tests/test_gpu_parity.py).  The reference has no such
+// asset; SURVEY.md §8(d) C5 defines it as a procedural stand-in.
+namespace {
+struct SynthLayout { uint64_t total, blob_each, wall_each, light; uint32_t rows, cols, grid; };
+static SynthLayout synth_layout(uint64_t total)
+{
+    SynthLayout s;
+    s.total = total;
+    const uint64_t t = total > 64 ? total - 2 : 0;
+    double per_blob = (double)t * 0.9 / 27.0 / 4.0;
+    uint32_t rows = (uint32_t)floor(sqrt(per_blob > 0 ? per_blob : 0));
+    if (rows < 2) rows = t >= 27 * 16 ? 2 : 0;
+    s.rows = rows;
+    s.cols = 2 * rows;
+    s.blob_each = 2ull * rows * s.cols;
+    const uint64_t used = 27 * s.blob_each;
+    s.grid = (uint32_t)floor(sqrt((double)(t > used ? t - used : 0) / 10.0));
+    s.wall_each = 2ull * s.grid * s.grid;
+    s.light = total - used - 5 * s.wall_each;
+    return s;
+}
+static f3 synth_blob_vertex(int b, uint32_t i, uint32_t j, uint32_t rows, uint32_t cols, uint32_t seed)
+{
+    const int bx = b % 3, by = (b / 3) % 3, bz = b / 9;
+    const f3 ctr = mk(139.0f + 139.0f * (float)bx, 110.0f + 160.0f * (float)by, 140.0f + 140.0f * (float)bz);
+    const float rad = 48.0f;
+    if (i == 0) return mk(ctr.x, ctr.y + rad, ctr.z);
+    if (i == rows) return mk(ctr.x, ctr.y - rad, ctr.z);
+    j = j % cols;
+    const float theta = (3.14159265358979f * (float)i) / (float)rows;
+    const float phi = (6.28318530717959f * (float)j) / (float)cols;
+    float st, ct, sp, cp, s1, s2, s3, s4, unused;
+    det_sincos(theta, st, ct);
+    det_sincos(phi, sp, cp);
+    const float ph = 0.37f * (float)((seed + 7u * (uint32_t)b) % 17u);
+    det_sincos(fm(5.0f, theta, ph), s1, unused);
+    det_sincos(fm(4.0f, phi, ph), s2, unused);
+    det_sincos(23.0f * theta, s3, unused);
+    det_sincos(17.0f * phi, s4, unused);
+    const float disp = fm(st, fm(0.14f * s1, s2, (0.04f * s3) * s4), 1.0f);
+    const float rr = rad * disp;
+    return mk(fm(rr * st, cp, ctr.x), fm(rr, ct, ctr.y), fm(rr * st, sp, ctr.z));
+}
+static f3 synth_wall_vertex(int wall, uint32_t i, uint32_t j, uint32_t grid)
+{
+    const float X = 556.0f, Y = 548.8f, Z = 559.2f;
+    const float u = (float)i / (float)grid, v = (float)j / (float)grid;
+    switch (wall) {
+        case 0: return mk(X * u, 0.0f, Z * v);
+        case 1: return mk(X * u, Y, Z * v);
+        case 2: return mk(X * u, Y * v, Z);
+        case 3: return mk(0.0f, Y * u, Z * v);
+        default: return mk(X, Y * u, Z * v);
+    }
+}
+}  // namespace
+
+extern "C" void orc_synth_mesh(uint64_t total, uint32_t seed, float* verts /* total*9 */, uint32_t* mats, int threads)
+{
+    const SynthLayout s = synth_layout(total);
+    const uint64_t blob_total = 27 * s.blob_each, wall_total = 5 * s.wall_each;
+    const uint64_t chunk = 1 << 16;
+    parallel_rows((int)((total + chunk - 1) / chunk), threads, [&](int row, int) {
+        const uint64_t b0 = (uint64_t)row * chunk, e0 = std::min<uint64_t>(total, b0 + chunk);
+        for (uint64_t t = b0; t < e0; ++t) {
+            f3 a, b, c;
+            uint32_t mat = 0;
+            if (t < blob_total) {
+                const int bi = (int)(t / s.blob_each);
+                const uint64_t r = t - (uint64_t)bi * s.blob_each, quad = r >> 1;
+                const uint32_t i = (uint32_t)(quad / s.cols), j = (uint32_t)(quad % s.cols);
+                const f3 p00 = synth_blob_vertex(bi, i, j, s.rows, s.cols, seed), p01 = synth_blob_vertex(bi, i, j + 1, s.rows, s.cols, seed);
+                const f3 p10 = synth_blob_vertex(bi, i + 1, j, s.rows, s.cols, seed), p11 = synth_blob_vertex(bi, i + 1, j + 1, s.rows, s.cols, seed);
+                if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+                mat = (bi % 5 == 1) ? 1u : ((bi % 5 == 3) ? 2u : 0u);
+            } else if (t < blob_total + wall_total) {
+                const uint64_t r0 = t - blob_total;
+                const int w = (int)(r0 / s.wall_each);
+                const uint64_t r = r0 - (uint64_t)w * s.wall_each, quad = r >> 1;
+                const uint32_t i = (uint32_t)(quad / s.grid), j = (uint32_t)(quad % s.grid);
+                const f3 p00 = synth_wall_vertex(w, i, j, s.grid), p01 = synth_wall_vertex(w, i, j + 1, s.grid);
+                const f3 p10 = synth_wall_vertex(w, i + 1, j, s.grid), p11 = synth_wall_vertex(w, i + 1, j + 1, s.grid);
+                if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+                mat = w == 3 ? 1u : (w == 4 ? 2u : 0u);
+            } else {
+                const uint64_t r = t - blob_total - wall_total, K = s.light / 2;
+                mat = 3u;
+                if (K == 0 || (r >> 1) >= K) {
+                    a = b = c = mk(343.0f, 548.6f, 227.0f);
+                } else {
+                    const uint64_t q = r >> 1;
+                    const float x0 = fm(-130.0f, (float)q / (float)K, 343.0f);
+                    const float x1 = (q + 1 == K) ? 213.0f : fm(-130.0f, (float)(q + 1) / (float)K, 343.0f);
+                    const f3 p00 = mk(x0, 548.6f, 227.0f), p01 = mk(x0, 548.6f, 332.0f), p10 = mk(x1, 548.6f, 227.0f), p11 = mk(x1, 548.6f, 332.0f);
+                    if (r & 1) { a = p00; b = p11; c = p01; } else { a = p00; b = p10; c = p11; }
+                }
+            }
+            float* o = verts + 9 * t;
+            o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = c.x; o[7] = c.y; o[8] = c.z;
+            mats[t] = mat;
+        }
+    });
+}

@@ -46,6 +46,7 @@ def lib():
         L.orc_raycast_translate.argtypes = [vp, i64, vp]
         L.orc_raycast_hits.argtypes = [vp, vp, i64, vp, vp, vp, i32]
         L.orc_raycast_shade.argtypes = [vp, i64, vp]
+        L.orc_synth_mesh.argtypes = [C.c_uint64, u32, vp, vp, i32]
         L.orc_pathtrace.restype = C.c_uint64
         L.orc_pathtrace.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
         _LIB = L
@@ -193,3 +194,11 @@ def invert34(m):
     out = np.zeros(12, np.float32)
     lib().orc_invert34(_p(_f32(m).reshape(12)), _p(out))
     return out
+
+
+def synth_mesh(total, seed=0, threads=None):
+    """(total,3,3) float32 triangles and (total,) uint32 material indices of the synthetic scene."""
+    verts = np.zeros((total, 9), np.float32)
+    mats = np.zeros(total, np.uint32)
+    lib().orc_synth_mesh(total, seed, _p(verts), _p(mats), threads or ncores())
+    return verts.reshape(total, 3, 3), mats

@@ -133,3 +133,51 @@ def test_triangle_soup_bvh_vs_oracle(ctx, orc):
     got = host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays)))
     ref = scene.trace(rays)
     _assert_hits_equal(got, ref, "soup")
+
+
+def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc):
+    """The procedural scene of BASELINE.json configs[4]: device generator == oracle restatement bit for bit,
+    the built BVH satisfies the structural invariants, and path tracing it (optixMultiGPU programs) is bit-exact."""
+    from optix_raytracer_b200 import host
+    T = 200_000
+    verts, mats = host.synthetic_mesh(ctx, T, 0)
+    torch.cuda.synchronize()
+    tris, omats = orc.synth_mesh(T, 0)
+    got = verts.cpu().numpy().reshape(T, 3, 4)
+    assert np.array_equal(got[:, :, :3].view(np.uint32), tris.view(np.uint32))
+    assert np.array_equal(mats.cpu().numpy().astype(np.uint32), omats)
+    w, h, spl = 64, 48, 2
+    pt = host.PathTracer(ctx, w, h, spl, vertices=verts, mat_indices=mats, multigpu=(0, 1), compact=True)
+    gas = common.decode_gas(pt.accel.buf.cpu().numpy())
+    assert gas["num_tris"] == T
+    depth, leaves = common.validate_gas(gas)
+    assert depth <= 40
+    st = pt.launch_subframe(0, collect_stats=1)
+    torch.cuda.synchronize()
+    scene = orc.Scene(tris, omats)
+    p = common.oracle_pt_params(orc, pt.params, 1)
+    sc = pt.scene
+    ref_accum, ref_frame, segs = scene.pathtrace(p, sc["emission_colors"], sc["diffuse_colors"])
+    assert st.radiance_segments + st.shadow_segments == segs
+    img = np.zeros((h, w, 4), np.float32)
+    idx = pt.sample_index.cpu().numpy()
+    ok = (idx[:, 0] < w) & (idx[:, 1] < h)
+    img[idx[ok, 1], idx[ok, 0]] = pt.accum.cpu().numpy()[ok]
+    assert np.array_equal(img.view(np.uint32), ref_accum.view(np.uint32))
+
+
+def test_bvh_invariants_and_compaction(ctx):
+    from optix_raytracer_b200 import host
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 5, 33, 1000):
+        tris = (rng.random((n, 3, 3), dtype=np.float32) * 4).astype(np.float32)
+        verts = ctx.to_device(tris.reshape(-1, 3))
+        a = ctx.build_accel([ctx.triangle_input(verts, vertex_stride=12)], compact=False)
+        b = ctx.build_accel([ctx.triangle_input(verts, vertex_stride=12)], compact=True)
+        torch.cuda.synchronize()
+        ga, gb = common.decode_gas(a.buf.cpu().numpy()), common.decode_gas(b.buf.cpu().numpy())
+        common.validate_gas(ga)
+        common.validate_gas(gb)
+        assert np.array_equal(ga["nodes"], gb["nodes"]) and np.array_equal(ga["tris"].view(np.uint32), gb["tris"].view(np.uint32))
+        assert b.buf.numel() <= a.buf.numel()
+        assert gb["total_bytes"] == 128 + 80 * gb["num_nodes"] + 48 * n
