@@ -136,6 +136,7 @@ static inline RayPrep prep_ray(f3 o, f3 d)
 // Watertight ray/triangle test (Woop, Benthin, Wald 2013) in the contract's op order.
 // Returns true and (t, b1, b2) if tmin < t < tmax;  b1/b2 weight vertices 1/2 (OptiX convention,
 // SDK/cuda/LocalGeometry.h:94).  `det_sign` gets sign of the determinant (for face culling).
+template <bool INCLUSIVE = false>
 static inline bool tri_hit(const RayPrep& r, const Tri& tr, float tmin, float tmax, float& t, float& b1, float& b2,
                            float* det_out = nullptr)
 {
@@ -158,7 +159,7 @@ static inline bool tri_hit(const RayPrep& r, const Tri& tr, float tmin, float tm
     const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
     const float T = fm(W, Cz, fm(V, Bz, U * Az));
     const float tt = T / det;
-    if (!(tt > tmin && tt < tmax)) return false;
+    if (!(tt > tmin && (INCLUSIVE ? tt <= tmax : tt < tmax))) return false;
     t = tt;
     b1 = V / det;
     b2 = W / det;
@@ -309,7 +310,7 @@ static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32
         float t, b1, b2, det;
         if (STATS) g.tri_tests++;
         // strict t < best.t, or equal t with a lower ordinal (order independence)
-        if (tri_hit(rp, g.tris[p], tmin, std::nextafterf(best.t, INFINITY), t, b1, b2, &det)) {
+        if (tri_hit<true>(rp, g.tris[p], tmin, best.t, t, b1, b2, &det)) {
             if (cull_flags) {
                 // OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1<<4): det<0 is back facing for
                 // counter-clockwise front faces seen along the ray in this formulation.
