@@ -532,7 +532,6 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
     // slot assignment: greedy, each child takes the free slot whose octant sign vector best matches
     // its centroid offset (slot bit 4/2/1 set = child on the +x/+y/+z side)
     const float3 ctr = f3(0.5f * (Lo.x + Hi.x), 0.5f * (Lo.y + Hi.y), 0.5f * (Lo.z + Hi.z));
-    int slot_of[8];
     int child_in_slot[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
@@ -546,10 +545,8 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
             const float c = ((s & 4) ? ox : -ox) + ((s & 2) ? oy : -oy) + ((s & 1) ? oz : -oz);
             if (c > bc) { bc = c; bs = s; }
         }
-        slot_of[k] = bs;
         child_in_slot[bs] = k;
     }
-    (void)slot_of;
     uint32_t imask = 0;
     uint32_t meta[8], qlo[3][8], qhi[3][8];
     uint32_t int_k = 0, tri_off = 0;

@@ -33,6 +33,7 @@ struct b200rt_context_t {
     cudaEvent_t ev = nullptr;
     std::mutex mu;
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING
+    unsigned int counter_slot = 0;  // rotating fetch-counter slot for persistent ray launches
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 

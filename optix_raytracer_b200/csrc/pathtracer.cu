@@ -22,9 +22,11 @@
 // rt_math.cuh the accumulated radiance is bit-identical to the scalar oracle.
 #include <string.h>
 
+#include <algorithm>
+
 #include "accel.h"
 #include "internal.h"
-#include "traverse.cuh"
+#include "trav_dyn.cuh"
 
 namespace b200rt {
 
@@ -94,7 +96,8 @@ constexpr uint32_t LF_COUNT_EMITTED = 1u << 30;
 
 struct Counters {
     unsigned int qcount[2];
-    unsigned int pad[2];
+    unsigned int fetch;      // work-item cursor of the persistent trace kernel (zeroed by INIT / SHADE)
+    unsigned int pad;
     unsigned long long radiance_segments, shadow_segments;
     unsigned long long nodes_fetched, tris_tested;
 };
@@ -179,57 +182,91 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
 }
 
 // ---- TRACE ---------------------------------------------------------------------------------------
-template <int MODE, bool STATS>
-__global__ void __launch_bounds__(256) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
-{
-    TravStats st{0, 0};
-    const Frame f = load_frame<MODE>(params);
-    const uint32_t n = L.counters->qcount[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->qcount[cur ^ 1] = 0;  // SHADE of this iteration appends there
-    const unsigned int* __restrict__ queue = L.queue[cur];
+// Work items of one iteration: two per active lane — item 2q = pending shadow ray of queue entry q (any-hit),
+// item 2q+1 = its extension ray (closest hit).  Lanes without that ray are skipped at fetch time.
+template <int MODE>
+struct PTWork {
+    const Frame& f;
+    const Lanes& L;
+    const unsigned int* __restrict__ queue;
+    uint32_t lane;
+    float weight;
     uint32_t nrad = 0, nshd = 0;
-    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n; qi += gridDim.x * blockDim.x) {
-        const uint32_t lane = queue[qi];
+    __device__ PTWork(const Frame& f_, const Lanes& L_, const unsigned int* q) : f(f_), L(L_), queue(q), lane(0), weight(0.f) {}
+
+    __device__ __forceinline__ bool fetch(uint32_t item, Trav& s)
+    {
+        lane = queue[item >> 1];
         const float4 rd = L.ray_d[lane];
         const uint32_t flags = __float_as_uint(rd.w);
-        float4 res = L.res[lane];
-        if (flags & LF_SHADOW) {
-            const float4 so = L.shd_o[lane], sd = L.shd_d[lane], pa = L.pend[lane];
-            RayHit sh;
+        if (item & 1u) {
+            if (flags & LF_NO_EXT) return false;
+            const float4 ro = L.ray_o[lane];
+            s.best.t = 1e16f;
+            if (!trav_begin_handle(s, f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 0u, 0u, 0u)) { commit(s, false); return false; }
+            ++nrad;
+        } else {
+            if (!(flags & LF_SHADOW)) return false;
+            const float4 so = L.shd_o[lane], sd = L.shd_d[lane];
+            weight = sd.w;
+            s.best.t = so.w;
             ++nshd;
-            const bool occluded = trace_handle<true, STATS>(f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, so.w,
-                                                            B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT, sh, &st);
-            const float weight = occluded ? 0.0f : sd.w;
+            if (!trav_begin_handle(s, f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, TP_ANY, 0u, 0u)) { commit(s, false); return false; }
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool next_instance(Trav& s)
+    {
+        if (f.handle->kind == ACCEL_KIND_GAS) return false;
+        float3 o, d;
+        if (s.pack & TP_ANY) { const float4 so = L.shd_o[lane], sd = L.shd_d[lane]; o = f3(so.x, so.y, so.z); d = f3(sd.x, sd.y, sd.z); }
+        else { const float4 ro = L.ray_o[lane], rd = L.ray_d[lane]; o = f3(ro.x, ro.y, ro.z); d = f3(rd.x, rd.y, rd.z); }
+        return trav_begin_handle(s, f.handle, o, d, 0.01f, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u);
+    }
+    __device__ __forceinline__ void commit(const Trav& s, bool found)
+    {
+        float* res = (float*)&L.res[lane];
+        if (s.pack & TP_ANY) {
+            // the shadow item owns res.xyz (and rad in mode 1); the extension item owns res.w and hitp
+            const float4 pa = L.pend[lane];
+            const float w = found ? 0.0f : weight;
             if (MODE == 0) {
                 // prd.radiance = light.emission * weight; result += prd.radiance * prd.attenuation
-                res.x = fm(f.light.emission.x * weight, pa.x, res.x);
-                res.y = fm(f.light.emission.y * weight, pa.y, res.y);
-                res.z = fm(f.light.emission.z * weight, pa.z, res.z);
+                res[0] = fm(f.light.emission.x * w, pa.x, res[0]);
+                res[1] = fm(f.light.emission.y * w, pa.y, res[1]);
+                res[2] = fm(f.light.emission.z * w, pa.z, res[2]);
             } else {
                 // prd->radiance += light.emission * weight (sticky); result += prd.radiance * prd.attenuation
                 float4 rad = L.rad[lane];
-                rad.x = fm(f.light.emission.x, weight, rad.x);
-                rad.y = fm(f.light.emission.y, weight, rad.y);
-                rad.z = fm(f.light.emission.z, weight, rad.z);
-                res.x = fm(rad.x, pa.x, res.x);
-                res.y = fm(rad.y, pa.y, res.y);
-                res.z = fm(rad.z, pa.z, res.z);
+                rad.x = fm(f.light.emission.x, w, rad.x);
+                rad.y = fm(f.light.emission.y, w, rad.y);
+                rad.z = fm(f.light.emission.z, w, rad.z);
+                res[0] = fm(rad.x, pa.x, res[0]);
+                res[1] = fm(rad.y, pa.y, res[1]);
+                res[2] = fm(rad.z, pa.z, res[2]);
                 // LF_COUNT_EMITTED marks a freshly regenerated camera ray: the shadow ray just resolved belonged
                 // to the previous sample's last bounce, and the new sample starts with prd.radiance = 0
+                const uint32_t flags = __float_as_uint(L.ray_d[lane].w);
                 L.rad[lane] = (flags & LF_COUNT_EMITTED) ? make_float4(0.f, 0.f, 0.f, 0.f) : rad;
             }
+        } else {
+            res[3] = found ? s.best.t : -1.0f;
+            if (found) L.hitp[lane] = make_uint2(s.best.prim, s.best.sbt);
         }
-        if (!(flags & LF_NO_EXT)) {
-            const float4 ro = L.ray_o[lane];
-            RayHit hit;
-            ++nrad;
-            const bool found = trace_handle<false, STATS>(f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 1e16f, 0u, hit, &st);
-            res.w = found ? hit.t : -1.0f;
-            if (found) L.hitp[lane] = make_uint2(hit.prim, hit.sbt);
-        }
-        L.res[lane] = res;
     }
+};
+
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(128) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
+{
+    const Frame f = load_frame<MODE>(params);
+    const uint32_t n = L.counters->qcount[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->qcount[cur ^ 1] = 0;  // SHADE of this iteration appends there
+    TravStats st{0, 0};
+    PTWork<MODE> work(f, L, L.queue[cur]);
+    trace_persistent(work, 2u * n, &L.counters->fetch, STATS ? &st : nullptr);
     // segment counters: one atomic pair per warp
+    uint32_t nrad = work.nrad, nshd = work.nshd;
     for (int off = 16; off; off >>= 1) {
         nrad += __shfl_xor_sync(0xffffffffu, nrad, off);
         nshd += __shfl_xor_sync(0xffffffffu, nshd, off);
@@ -282,6 +319,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
     const unsigned int* __restrict__ queue = L.queue[cur];
     unsigned int* next_queue = L.queue[cur ^ 1];
     unsigned int* next_count = &L.counters->qcount[cur ^ 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->fetch = 0;  // the next TRACE starts its item cursor at 0
     const float3 bg = MODE == 0 ? xyz(*(const float4*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))
                                 : f3(((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[0],
                                      ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[1],
@@ -587,7 +625,7 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
 {
     // workspace layout
     const size_t L = nlanes;
-    size_t off = 0;
+    size_t off = 16384;  // the first 16 KiB of the workspace hold the fetch counters / stats of the ray-buffer launches (raycast.cu)
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_cnt = take(sizeof(Counters));
     const size_t o_ro = take(16 * L), o_rd = take(16 * L), o_att = take(16 * L), o_res = take(16 * L), o_so = take(16 * L), o_sd = take(16 * L),
@@ -614,6 +652,13 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     pt_init_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, nlanes);
     B2_LAUNCH_CHECK(ctx);
     Counters* h_cnt = (Counters*)((char*)ctx->pinned + 256);
+    // persistent trace kernel: as many CTAs as fit on the device (occupancy query), never more than the work needs
+    int occ = 0, occ_stats = 0;
+    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_trace_kernel<MODE, false>, 128, 0));
+    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, pt_trace_kernel<MODE, true>, 128, 0));
+    const unsigned work_cap = (unsigned)std::max<uint64_t>(1, (2ull * nlanes + 127) / 128);
+    const unsigned trace_grid = std::min(work_cap, (unsigned)(std::max(occ, 1) * ctx->sm_count));
+    const unsigned trace_grid_stats = std::min(work_cap, (unsigned)(std::max(occ_stats, 1) * ctx->sm_count));
     const uint32_t want = (opt && opt->stats) ? opt->collect_stats : 0u;
     const bool timing = (want & B200RT_PT_STATS_TIMING) != 0, travstats = (want & B200RT_PT_STATS_TRAVERSAL) != 0;
     size_t nev = 0;
@@ -631,8 +676,8 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     for (;;) {
         for (int k = 0; k < CHECK_EVERY; ++k) {
             if (timing) cudaEventRecord(next_event(), s);
-            if (travstats) pt_trace_kernel<MODE, true><<<grid, 256, 0, s>>>(params, ln, cur);
-            else pt_trace_kernel<MODE, false><<<grid, 256, 0, s>>>(params, ln, cur);
+            if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, 128, 0, s>>>(params, ln, cur);
+            else pt_trace_kernel<MODE, false><<<trace_grid, 128, 0, s>>>(params, ln, cur);
             B2_LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(next_event(), s);
             pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,

@@ -6,14 +6,16 @@
 // SDK/cuda/LocalGeometry.h:59-176 (shading normal), SDK/optixRaycasting/optixRaycasting.cpp:289-317 (launch).
 // Rays are 32-byte AoS records and hits 16-byte records exactly as in the reference, so a warp reads
 // 1 KiB and writes 512 B contiguous per request; each ray record is fetched as two 16-byte loads.
+#include <algorithm>
+#include <mutex>
+
 #include "accel.h"
 #include "internal.h"
-#include "traverse.cuh"
+#include "trav_dyn.cuh"
 
 namespace b200rt {
 
 struct RayRec { float ox, oy, oz, tmin, dx, dy, dz, tmax; };  // optixRaycastingKernels.h:35-41
-struct RaycastParams { uint64_t handle; const RayRec* rays; float4* hits; };  // optixRaycasting.h:41-46
 
 // ---- createRaysOrthoKernel (optixRaycastingKernels.cu:42-55): origin = (x0 + ix*dx, y0 + iy*dy, z) ----
 __global__ void __launch_bounds__(512) create_rays_ortho_kernel(float4* __restrict__ rays, int width, int height, float x0, float y0,
@@ -50,72 +52,82 @@ __global__ void __launch_bounds__(512) shade_hits_kernel(float* __restrict__ ima
     image[3 * (size_t)idx + 2] = c.z;
 }
 
-// ---- generic queries ------------------------------------------------------------------------------
-template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(256) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint64_t n,
-                                                          uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
-                                                          unsigned long long* __restrict__ stats)
-{
-    TravStats st{0, 0};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-        RayHit hit;
-        const bool found = trace_handle<ANY, STATS>(handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, ray_flags, hit, &st);
-        if (ANY) occluded[i] = found ? 1u : 0u;
-        else {
-            ExtHit e;
-            if (found) { e.t = hit.t; e.prim = hit.prim; e.inst = hit.inst; e.b1 = hit.b1; e.b2 = hit.b2; }
-            else { e.t = -1.0f; e.prim = 0xffffffffu; e.inst = 0xffffffffu; e.b1 = 0.f; e.b2 = 0.f; }
-            ext[i] = e;
-        }
-    }
-    if (STATS) {
-        atomicAdd(&stats[0], (unsigned long long)st.nodes);
-        atomicAdd(&stats[1], (unsigned long long)st.tris);
-    }
-}
-
-// ---- the optixRaycasting launch: raygen + closest-hit + miss fused per ray -------------------------
+// ---- ray-buffer queries on the persistent traversal driver (trav_dyn.cuh) -----------------------------
 struct BufView { uint64_t data; uint32_t count; uint16_t byte_stride; uint16_t elmt; };  // SDK/cuda/BufferView.h:32-38
 
-__global__ void __launch_bounds__(256) raycast_launch_kernel(const RaycastParams* __restrict__ params, const char* __restrict__ hg_base,
-                                                              uint32_t hg_stride, uint32_t hg_count, uint64_t n, ExtHit* __restrict__ ext)
+__device__ __forceinline__ ExtHit make_ext(const Trav& s, bool found)
 {
-    const RaycastParams P = *params;
-    const AccelHeader* handle = (const AccelHeader*)P.handle;
-    const float4* rays = (const float4*)P.rays;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-        RayHit hit;
-        const bool found = trace_handle<false, false>(handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, b.w, 0u, hit, nullptr);
+    ExtHit e;
+    if (found) { e.t = s.best.t; e.prim = s.best.prim; e.inst = s.best.inst; e.b1 = s.best.b1; e.b2 = s.best.b2; }
+    else { e.t = -1.0f; e.prim = 0xffffffffu; e.inst = 0xffffffffu; e.b1 = 0.f; e.b2 = 0.f; }
+    return e;
+}
+
+// KIND 0: closest hit -> ExtHit; 1: any hit -> u32 flag; 2: the optixRaycasting programs -> Hit (+ optional ExtHit)
+template <int KIND>
+struct RayWork {
+    const AccelHeader* handle;
+    const float4* rays;
+    uint32_t ray_flags;
+    ExtHit* ext;
+    uint32_t* occluded;
+    float4* hits;
+    const char* hg_base;
+    uint32_t hg_stride, hg_count;
+    uint64_t item;
+
+    __device__ __forceinline__ bool fetch(uint32_t i, Trav& s)
+    {
+        item = i;
+        const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
+        s.best.t = b.w;
+        if (!trav_begin_handle(s, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, ray_flags & 0x30u, 0u)) {
+            commit(s, false);
+            return false;
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool next_instance(Trav& s)
+    {
+        if (handle->kind == ACCEL_KIND_GAS) return false;
+        const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
+        return trav_begin_handle(s, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY), ray_flags & 0x30u,
+                                 s.inst + 1u);
+    }
+    __device__ __forceinline__ void commit(const Trav& s, bool found)
+    {
+        if (KIND == 1) { occluded[item] = found ? 1u : 0u; return; }
+        if (KIND == 0) { ext[item] = make_ext(s, found); return; }
+        // KIND 2: __miss__buffer_miss / __closesthit__buffer_hit (optixRaycasting.cu:65-86)
         float4 out;
         if (!found) {
-            out = make_float4(-1.0f, 1.0f, 0.0f, 0.0f);  // __miss__buffer_miss
+            out = make_float4(-1.0f, 1.0f, 0.0f, 0.0f);
         } else {
-            // __closesthit__buffer_hit: SBT record = instance.sbtOffset + GAS-local index (ray type 0, stride 1)
-            uint32_t sbt = hit.sbt & TRI_SBT_MASK;
+            // SBT record = instance.sbtOffset + GAS-local index (ray type 0, stride 1)
+            uint32_t sbt = s.best.sbt & TRI_SBT_MASK;
             const InstanceRecord* ir = nullptr;
             if (handle->kind == ACCEL_KIND_IAS) {
-                ir = (const InstanceRecord*)((const char*)handle + handle->inst_off) + hit.inst;
+                ir = (const InstanceRecord*)((const char*)handle + handle->inst_off) + s.best.inst;
                 sbt += ir->sbt_offset;
             }
             if (sbt >= hg_count) sbt = hg_count - 1;
             const char* rec = hg_base + (size_t)sbt * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE;
             // whitted::HitGroupData -> GeometryData{type@0, TriangleMesh@8{indices, positions, normals, ...}}
             const BufView vi = *(const BufView*)(rec + 8), vp = *(const BufView*)(rec + 24), vn = *(const BufView*)(rec + 40);
+            const uint32_t prim = s.best.prim;
             uint32_t i0, i1, i2;
-            if (vi.elmt == 4) { const uint32_t* ip = (const uint32_t*)vi.data + 3 * (size_t)hit.prim; i0 = ip[0]; i1 = ip[1]; i2 = ip[2]; }
-            else if (vi.elmt == 2) { const uint16_t* ip = (const uint16_t*)vi.data + 3 * (size_t)hit.prim; i0 = ip[0]; i1 = ip[1]; i2 = ip[2]; }
-            else { i0 = 3 * hit.prim; i1 = i0 + 1; i2 = i0 + 2; }
+            if (vi.elmt == 4) { const uint32_t* ip = (const uint32_t*)vi.data + 3 * (size_t)prim; i0 = ip[0]; i1 = ip[1]; i2 = ip[2]; }
+            else if (vi.elmt == 2) { const uint16_t* ip = (const uint16_t*)vi.data + 3 * (size_t)prim; i0 = ip[0]; i1 = ip[1]; i2 = ip[2]; }
+            else { i0 = 3 * prim; i1 = i0 + 1; i2 = i0 + 2; }
             float3 N;
             if (vn.data) {
                 const uint32_t st = vn.byte_stride ? vn.byte_stride : 12u;
                 const float* n0 = (const float*)(vn.data + (size_t)i0 * st);
                 const float* n1 = (const float*)(vn.data + (size_t)i1 * st);
                 const float* n2 = (const float*)(vn.data + (size_t)i2 * st);
-                const float b0 = (1.0f - hit.b1) - hit.b2;
-                N = f3(fm(hit.b2, n2[0], fm(hit.b1, n1[0], b0 * n0[0])), fm(hit.b2, n2[1], fm(hit.b1, n1[1], b0 * n0[1])),
-                       fm(hit.b2, n2[2], fm(hit.b1, n1[2], b0 * n0[2])));
+                const float b1 = s.best.b1, b2 = s.best.b2;
+                const float b0 = (1.0f - b1) - b2;
+                N = f3(fm(b2, n2[0], fm(b1, n1[0], b0 * n0[0])), fm(b2, n2[1], fm(b1, n1[1], b0 * n0[1])), fm(b2, n2[2], fm(b1, n1[2], b0 * n0[2])));
             } else {
                 const uint32_t st = vp.byte_stride ? vp.byte_stride : 12u;
                 const float* p0 = (const float*)(vp.data + (size_t)i0 * st);
@@ -127,23 +139,60 @@ __global__ void __launch_bounds__(256) raycast_launch_kernel(const RaycastParams
             if (ir) N = xform_normal(ir->inv, N);
             N = normalize(N);
             // `const unsigned int t = optixGetRayTmax();` — the reference truncates t to an integer
-            out = make_float4((float)(unsigned int)hit.t, N.x, N.y, N.z);
+            out = make_float4((float)(unsigned int)s.best.t, N.x, N.y, N.z);
         }
-        P.hits[i] = out;
-        if (ext) {
-            ExtHit e;
-            if (found) { e.t = hit.t; e.prim = hit.prim; e.inst = hit.inst; e.b1 = hit.b1; e.b2 = hit.b2; }
-            else { e.t = -1.0f; e.prim = 0xffffffffu; e.inst = 0xffffffffu; e.b1 = 0.f; e.b2 = 0.f; }
-            ext[i] = e;
+        hits[item] = out;
+        if (ext) ext[item] = make_ext(s, found);
+    }
+};
+
+struct RaycastParamsDev { uint64_t handle; const float4* rays; float4* hits; };  // optixRaycasting.h:41-46
+
+template <int KIND, bool STATS>
+__global__ void __launch_bounds__(128) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
+                                                          uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
+                                                          const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
+                                                          uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,
+                                                          unsigned long long* __restrict__ stats)
+{
+    RayWork<KIND> w;
+    w.handle = handle; w.rays = rays; w.hits = nullptr;
+    if (KIND == 2) { const RaycastParamsDev P = *rc_params; w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits; }
+    w.ray_flags = ray_flags; w.ext = ext; w.occluded = occluded;
+    w.hg_base = hg_base; w.hg_stride = hg_stride; w.hg_count = hg_count; w.item = 0;
+    TravStats st{0, 0};
+    trace_persistent(w, n, counter, STATS ? &st : nullptr);
+    if (STATS) {
+        for (int off = 16; off; off >>= 1) {
+            st.nodes += __shfl_xor_sync(0xffffffffu, st.nodes, off);
+            st.tris += __shfl_xor_sync(0xffffffffu, st.tris, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[0], (unsigned long long)st.nodes);
+            atomicAdd(&stats[1], (unsigned long long)st.tris);
         }
     }
 }
 
-static unsigned grid_for(b200rt_context ctx, uint64_t n, int block, int ctas_per_sm)
+// a zeroed fetch counter for one persistent launch: slots rotate so launches on different streams do not share one
+static int next_counter(b200rt_context ctx, cudaStream_t s, unsigned int** out)
 {
-    const uint64_t need = (n + block - 1) / block;
-    const uint64_t cap = (uint64_t)ctx->sm_count * ctas_per_sm;
-    return (unsigned)std::max<uint64_t>(1, std::min(need, cap));
+    int rc = ensure_workspace(ctx, 1 << 20, s);
+    if (rc) return rc;
+    unsigned int* base = (unsigned int*)((char*)ctx->ws.ptr + 4096);
+    unsigned int* c = base + (ctx->counter_slot++ % 512u) * 4u;
+    B2_CUDA(ctx, cudaMemsetAsync(c, 0, sizeof(unsigned int), s));
+    *out = c;
+    return 0;
+}
+
+template <int KIND, bool STATS>
+static unsigned persistent_grid_rays(b200rt_context ctx, uint64_t n)
+{
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_rays_kernel<KIND, STATS>, 128, 0);
+    const uint64_t cap = (uint64_t)std::max(occ, 1) * ctx->sm_count;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(cap, (n + 127) / 128));
 }
 
 int create_rays_ortho(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr rays, int width, int height, const float* bbmin,
@@ -187,11 +236,16 @@ int shade_hits(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr image, int c
 int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n, unsigned ray_flags,
                   b200rt_deviceptr ext)
 {
-    B2_REQUIRE(ctx, handle && (n == 0 || (rays && ext)), "null argument");
+    B2_REQUIRE(ctx, handle && (n == 0 || (rays && ext)) && n < (1ull << 32), "bad argument");
     DeviceGuard guard(ctx->device);
     if (n == 0) return 0;
-    trace_rays_kernel<false, false><<<grid_for(ctx, n, 256, 8), 256, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, n, ray_flags,
-                                                                             (ExtHit*)ext, nullptr, nullptr);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    unsigned int* counter = nullptr;
+    int rc = next_counter(ctx, s, &counter);
+    if (rc) return rc;
+    trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+                                                                                       ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0,
+                                                                                       counter, nullptr);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -199,11 +253,16 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
 int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n, unsigned ray_flags,
               b200rt_deviceptr occ)
 {
-    B2_REQUIRE(ctx, handle && (n == 0 || (rays && occ)), "null argument");
+    B2_REQUIRE(ctx, handle && (n == 0 || (rays && occ)) && n < (1ull << 32), "bad argument");
     DeviceGuard guard(ctx->device);
     if (n == 0) return 0;
-    trace_rays_kernel<true, false><<<grid_for(ctx, n, 256, 8), 256, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, n, ray_flags,
-                                                                            nullptr, (uint32_t*)occ, nullptr);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    unsigned int* counter = nullptr;
+    int rc = next_counter(ctx, s, &counter);
+    if (rc) return rc;
+    trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+                                                                                       ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0,
+                                                                                       counter, nullptr);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -211,17 +270,18 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
 int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n, uint64_t* nodes,
                 uint64_t* tris)
 {
-    B2_REQUIRE(ctx, handle && rays && nodes && tris, "null argument");
+    B2_REQUIRE(ctx, handle && rays && nodes && tris && n < (1ull << 32), "bad argument");
     DeviceGuard guard(ctx->device);
-    int rc = ensure_workspace(ctx, 1 << 20, s);
+    unsigned int* counter = nullptr;
+    int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
     unsigned long long* d_stats = (unsigned long long*)ctx->ws.ptr;
     ExtHit* scratch = nullptr;
     B2_CUDA(ctx, cudaMalloc(&scratch, sizeof(ExtHit) * std::max<uint64_t>(n, 1)));
     B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
     if (n) {
-        trace_rays_kernel<false, true><<<grid_for(ctx, n, 256, 8), 256, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, n, 0u,
-                                                                                scratch, nullptr, d_stats);
+        trace_rays_kernel<0, true><<<persistent_grid_rays<0, true>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+                                                                                         0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats);
         ctx->launches++;
     }
     unsigned long long h[2] = {0, 0};
@@ -242,9 +302,17 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                "hit-group records (whitted::HitGroupData) are required");
     DeviceGuard guard(ctx->device);
     const uint64_t n = (uint64_t)width * height;
+    B2_REQUIRE(ctx, n < (1ull << 32), "launch too large");
     if (n == 0) return 0;
-    raycast_launch_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, s>>>((const RaycastParams*)d_params, (const char*)sbt->hitgroupRecordBase,
-                                                                   sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, n, (ExtHit*)ext);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    unsigned int* counter = nullptr;
+    int rc = next_counter(ctx, s, &counter);
+    if (rc) return rc;
+    trace_rays_kernel<2, false><<<persistent_grid_rays<2, false>(ctx, n), 128, 0, s>>>(nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr,
+                                                                                       (const RaycastParamsDev*)d_params,
+                                                                                       (const char*)sbt->hitgroupRecordBase,
+                                                                                       sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount,
+                                                                                       counter, nullptr);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

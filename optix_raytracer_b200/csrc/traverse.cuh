@@ -74,9 +74,11 @@ __device__ __forceinline__ bool tri_test(const TriRay& r, const float4 q0, const
     const float Ax = fm(-r.Sx, Akz, sel3(A, r.kx)), Ay = fm(-r.Sy, Akz, sel3(A, r.ky));
     const float Bx = fm(-r.Sx, Bkz, sel3(B, r.kx)), By = fm(-r.Sy, Bkz, sel3(B, r.ky));
     const float Cx = fm(-r.Sx, Ckz, sel3(C, r.kx)), Cy = fm(-r.Sy, Ckz, sel3(C, r.ky));
-    float U = fm(Cx, By, -(Cy * Bx));
-    float V = fm(Ax, Cy, -(Ay * Cx));
-    float W = fm(Bx, Ay, -(By * Ax));
+    // edge functions: two rounded products and one subtraction (NOT fused) — this is what makes the value for a
+    // shared edge exactly antisymmetric between the two triangles, i.e. watertight (Woop et al. 2013, sec. 3); the library is built with -fmad=false
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
         U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
         V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));

@@ -145,9 +145,11 @@ static inline bool tri_hit(const RayPrep& r, const Tri& tr, float tmin, float tm
     const float Ax = fm(-r.Sx, Akz, get(A, r.kx)), Ay = fm(-r.Sy, Akz, get(A, r.ky));
     const float Bx = fm(-r.Sx, Bkz, get(B, r.kx)), By = fm(-r.Sy, Bkz, get(B, r.ky));
     const float Cx = fm(-r.Sx, Ckz, get(C, r.kx)), Cy = fm(-r.Sy, Ckz, get(C, r.ky));
-    float U = fm(Cx, By, -(Cy * Bx));
-    float V = fm(Ax, Cy, -(Ay * Cx));
-    float W = fm(Bx, Ay, -(By * Ax));
+    // edge functions: two rounded products and one subtraction (NOT fused) — this is what makes the value for a
+    // shared edge exactly antisymmetric between the two triangles, i.e. watertight (Woop et al. 2013, sec. 3)
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
     if (U == 0.0f || V == 0.0f || W == 0.0f) {
         U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
         V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
