@@ -761,6 +761,12 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
     B2_REQUIRE(ctx, options && inputs && handle && num_inputs >= 1, "null argument");
     B2_REQUIRE(ctx, options->operation == B200RT_BUILD_OPERATION_BUILD, "only OPERATION_BUILD is supported (static scenes)");
     B2_REQUIRE(ctx, out && (out % B200RT_ACCEL_BUFFER_BYTE_ALIGNMENT) == 0, "outputBuffer must be 128-byte aligned");
+    for (unsigned i = 0; i < num_emitted; ++i) {
+        B2_REQUIRE(ctx, emitted && emitted[i].type == B200RT_PROPERTY_TYPE_COMPACTED_SIZE, "only COMPACTED_SIZE can be emitted");
+        // same rule (and same error code) as optixAccelBuild: "Querying compacted size, but build flag ALLOW_COMPACTION is not set"
+        B2_REQUIRE(ctx, options->buildFlags & B200RT_BUILD_FLAG_ALLOW_COMPACTION, "emittedProperties[%u]: compacted size queried without BUILD_FLAG_ALLOW_COMPACTION", i);
+        B2_REQUIRE(ctx, emitted[i].result, "emittedProperties[%u].result is null", i);
+    }
     DeviceGuard guard(ctx->device);
     uint64_t exact_bytes = 0;
 
@@ -921,7 +927,6 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         log_msg(ctx, 4, "accel", "GAS: %u triangles, %u nodes, depth %u, %llu bytes", N, total_nodes, depth, (unsigned long long)exact_bytes);
     }
     for (unsigned i = 0; i < num_emitted; ++i) {
-        B2_REQUIRE(ctx, emitted && emitted[i].type == B200RT_PROPERTY_TYPE_COMPACTED_SIZE, "only COMPACTED_SIZE can be emitted");
         const size_t v = align_up(exact_bytes, 128);
         B2_CUDA(ctx, cudaMemcpyAsync((void*)emitted[i].result, &v, sizeof(size_t), cudaMemcpyHostToDevice, s));
     }

@@ -26,7 +26,7 @@
 
 #include "accel.h"
 #include "internal.h"
-#include "trav_dyn.cuh"
+#include "trav_coop.cuh"
 
 namespace b200rt {
 
@@ -95,7 +95,9 @@ constexpr uint32_t LF_NO_EXT = 1u << 29;      // no extension ray: lane only wai
 constexpr uint32_t LF_COUNT_EMITTED = 1u << 30;
 
 struct Counters {
-    unsigned int qcount[2];
+    unsigned int qcount[2];  // active lanes (SHADE's work list), double buffered like the two below
+    unsigned int n_ext[2];   // lanes with an extension ray to trace (dense list ext_list)
+    unsigned int n_shd[2];   // lanes with a pending shadow ray (dense list shd_list)
     unsigned int fetch;      // work-item cursor of the persistent trace kernel (zeroed by INIT / SHADE)
     unsigned int pad;
     unsigned long long radiance_segments, shadow_segments;
@@ -114,6 +116,8 @@ struct Lanes {
     float4* emi;     // mode 1: sticky emitted (xyz)
     uint2* hitp;     // prim, sbt
     unsigned int* queue[2];
+    unsigned int* ext_list;  // TRACE work items: item i < n_ext is the extension ray of lane ext_list[i],
+    unsigned int* shd_list;  //                   item n_ext + j the shadow ray of lane shd_list[j]
     Counters* counters;
 };
 
@@ -178,50 +182,47 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
             }
         }
         queue_push(L.queue[0], &L.counters->qcount[0], active, lane);
+        queue_push(L.ext_list, &L.counters->n_ext[0], active, lane);
     }
 }
 
 // ---- TRACE ---------------------------------------------------------------------------------------
-// Work items of one iteration: two per active lane — item 2q = pending shadow ray of queue entry q (any-hit),
-// item 2q+1 = its extension ray (closest hit).  Lanes without that ray are skipped at fetch time.
+// Work items of one iteration come from the two dense lists SHADE (or INIT) wrote: extension rays (closest hit) first,
+// then pending shadow rays (any-hit).  Every item is a ray, so a refill never comes back empty-handed.
+// The launches take a GAS handle (the reference pipelines are built with OPTIX_TRAVERSABLE_GRAPH_FLAG_ALLOW_SINGLE_GAS,
+// optixPathTracer.cpp:702 / optixMultiGPU.cpp:794); an IAS handle is traversed instance by instance all the same.
 template <int MODE>
 struct PTWork {
     const Frame& f;
     const Lanes& L;
-    const unsigned int* __restrict__ queue;
+    uint32_t n_ext;
     uint32_t lane;
     float weight;
-    uint32_t nrad = 0, nshd = 0;
-    __device__ PTWork(const Frame& f_, const Lanes& L_, const unsigned int* q) : f(f_), L(L_), queue(q), lane(0), weight(0.f) {}
+    __device__ PTWork(const Frame& f_, const Lanes& L_, uint32_t n_ext_) : f(f_), L(L_), n_ext(n_ext_), lane(0), weight(0.f) {}
 
-    __device__ __forceinline__ bool fetch(uint32_t item, Trav& s)
+    __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        lane = queue[item >> 1];
-        const float4 rd = L.ray_d[lane];
-        const uint32_t flags = __float_as_uint(rd.w);
-        if (item & 1u) {
-            if (flags & LF_NO_EXT) return false;
-            const float4 ro = L.ray_o[lane];
+        if (item < n_ext) {
+            lane = L.ext_list[item];
+            const float4 ro = L.ray_o[lane], rd = L.ray_d[lane];
             s.best.t = 1e16f;
-            if (!trav_begin_handle(s, f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 0u, 0u, 0u)) { commit(s, false); return false; }
-            ++nrad;
+            if (!trav_begin_handle(s, my_ray, f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 0u, 0u, 0u)) { commit(s, false); return false; }
         } else {
-            if (!(flags & LF_SHADOW)) return false;
+            lane = L.shd_list[item - n_ext];
             const float4 so = L.shd_o[lane], sd = L.shd_d[lane];
             weight = sd.w;
             s.best.t = so.w;
-            ++nshd;
-            if (!trav_begin_handle(s, f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, TP_ANY, 0u, 0u)) { commit(s, false); return false; }
+            if (!trav_begin_handle(s, my_ray, f.handle, f3(so.x, so.y, so.z), f3(sd.x, sd.y, sd.z), 0.01f, TP_ANY, 0u, 0u)) { commit(s, false); return false; }
         }
         return true;
     }
-    __device__ __forceinline__ bool next_instance(Trav& s)
+    __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
         if (f.handle->kind == ACCEL_KIND_GAS) return false;
         float3 o, d;
         if (s.pack & TP_ANY) { const float4 so = L.shd_o[lane], sd = L.shd_d[lane]; o = f3(so.x, so.y, so.z); d = f3(sd.x, sd.y, sd.z); }
         else { const float4 ro = L.ray_o[lane], rd = L.ray_d[lane]; o = f3(ro.x, ro.y, ro.z); d = f3(rd.x, rd.y, rd.z); }
-        return trav_begin_handle(s, f.handle, o, d, 0.01f, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u);
+        return trav_begin_handle(s, my_ray, f.handle, o, d, 0.01f, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
     {
@@ -257,24 +258,21 @@ struct PTWork {
 };
 
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(128) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
+__global__ void __launch_bounds__(COOP_BLOCK, 8) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
 {
     const Frame f = load_frame<MODE>(params);
-    const uint32_t n = L.counters->qcount[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->qcount[cur ^ 1] = 0;  // SHADE of this iteration appends there
+    const uint32_t n_ext = L.counters->n_ext[cur], n_shd = L.counters->n_shd[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // SHADE of this iteration appends to the other buffers
+        L.counters->qcount[cur ^ 1] = 0;
+        L.counters->n_ext[cur ^ 1] = 0;
+        L.counters->n_shd[cur ^ 1] = 0;
+        atomicAdd(&L.counters->radiance_segments, (unsigned long long)n_ext);
+        atomicAdd(&L.counters->shadow_segments, (unsigned long long)n_shd);
+    }
     TravStats st{0, 0};
-    PTWork<MODE> work(f, L, L.queue[cur]);
-    trace_persistent(work, 2u * n, &L.counters->fetch, STATS ? &st : nullptr);
-    // segment counters: one atomic pair per warp
-    uint32_t nrad = work.nrad, nshd = work.nshd;
-    for (int off = 16; off; off >>= 1) {
-        nrad += __shfl_xor_sync(0xffffffffu, nrad, off);
-        nshd += __shfl_xor_sync(0xffffffffu, nshd, off);
-    }
-    if ((threadIdx.x & 31) == 0 && (nrad | nshd)) {
-        atomicAdd(&L.counters->radiance_segments, (unsigned long long)nrad);
-        atomicAdd(&L.counters->shadow_segments, (unsigned long long)nshd);
-    }
+    PTWork<MODE> work(f, L, n_ext);
+    trace_persistent(work, n_ext + n_shd, &L.counters->fetch, STATS ? &st : nullptr);
     if (STATS) {
         for (int off = 16; off; off >>= 1) {
             st.nodes += __shfl_xor_sync(0xffffffffu, st.nodes, off);
@@ -319,6 +317,8 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
     const unsigned int* __restrict__ queue = L.queue[cur];
     unsigned int* next_queue = L.queue[cur ^ 1];
     unsigned int* next_count = &L.counters->qcount[cur ^ 1];
+    unsigned int* next_ext = &L.counters->n_ext[cur ^ 1];
+    unsigned int* next_shd = &L.counters->n_shd[cur ^ 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) L.counters->fetch = 0;  // the next TRACE starts its item cursor at 0
     const float3 bg = MODE == 0 ? xyz(*(const float4*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))
                                 : f3(((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[0],
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
     constexpr uint32_t RAY_TYPES = MODE == 0 ? 1u : 2u;  // SBT stride of the radiance trace call
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t qi = base + threadIdx.x;
-        bool keep = false;
+        bool keep = false, want_ext = false, want_shd = false;
         uint32_t lane = 0;
         if (qi < n) {
             lane = queue[qi];
@@ -456,6 +456,8 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
                     finalize_lane<MODE>(f, lane, px, py, result);
                 } else {
                     keep = true;
+                    want_ext = (nflags & LF_NO_EXT) == 0u;
+                    want_shd = (nflags & LF_SHADOW) != 0u;
                     L.ray_o[lane] = make_float4(nrg.x, nrg.y, nrg.z, __uint_as_float(seed));
                     L.ray_d[lane] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(nflags));
                     L.att[lane] = make_float4(att.x, att.y, att.z, __uint_as_float(pixel_seed));
@@ -464,6 +466,8 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
             }
         }
         queue_push(next_queue, next_count, keep, lane);
+        queue_push(L.ext_list, next_ext, want_ext, lane);
+        queue_push(L.shd_list, next_shd, want_shd, lane);
     }
 }
 
@@ -631,7 +635,7 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     const size_t o_ro = take(16 * L), o_rd = take(16 * L), o_att = take(16 * L), o_res = take(16 * L), o_so = take(16 * L), o_sd = take(16 * L),
                  o_pend = take(16 * L);
     const size_t o_rad = MODE == 1 ? take(16 * L) : 0, o_emi = MODE == 1 ? take(16 * L) : 0;
-    const size_t o_hit = take(8 * L), o_q0 = take(4 * L), o_q1 = take(4 * L);
+    const size_t o_hit = take(8 * L), o_q0 = take(4 * L), o_q1 = take(4 * L), o_ext = take(4 * L), o_shd = take(4 * L);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
@@ -644,6 +648,8 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     ln.hitp = (uint2*)(W + o_hit);
     ln.queue[0] = (unsigned int*)(W + o_q0);
     ln.queue[1] = (unsigned int*)(W + o_q1);
+    ln.ext_list = (unsigned int*)(W + o_ext);
+    ln.shd_list = (unsigned int*)(W + o_shd);
 
     const uint64_t launches0 = ctx->launches;
     B2_CUDA(ctx, cudaMemsetAsync(ln.counters, 0, sizeof(Counters), s));
@@ -654,9 +660,9 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     Counters* h_cnt = (Counters*)((char*)ctx->pinned + 256);
     // persistent trace kernel: as many CTAs as fit on the device (occupancy query), never more than the work needs
     int occ = 0, occ_stats = 0;
-    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_trace_kernel<MODE, false>, 128, 0));
-    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, pt_trace_kernel<MODE, true>, 128, 0));
-    const unsigned work_cap = (unsigned)std::max<uint64_t>(1, (2ull * nlanes + 127) / 128);
+    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_trace_kernel<MODE, false>, COOP_BLOCK, 0));
+    B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, pt_trace_kernel<MODE, true>, COOP_BLOCK, 0));
+    const unsigned work_cap = (unsigned)std::max<uint64_t>(1, (2ull * nlanes + COOP_BLOCK - 1) / COOP_BLOCK);
     const unsigned trace_grid = std::min(work_cap, (unsigned)(std::max(occ, 1) * ctx->sm_count));
     const unsigned trace_grid_stats = std::min(work_cap, (unsigned)(std::max(occ_stats, 1) * ctx->sm_count));
     const uint32_t want = (opt && opt->stats) ? opt->collect_stats : 0u;
@@ -676,8 +682,8 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     for (;;) {
         for (int k = 0; k < CHECK_EVERY; ++k) {
             if (timing) cudaEventRecord(next_event(), s);
-            if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, 128, 0, s>>>(params, ln, cur);
-            else pt_trace_kernel<MODE, false><<<trace_grid, 128, 0, s>>>(params, ln, cur);
+            if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, COOP_BLOCK, 0, s>>>(params, ln, cur);
+            else pt_trace_kernel<MODE, false><<<trace_grid, COOP_BLOCK, 0, s>>>(params, ln, cur);
             B2_LAUNCH_CHECK(ctx);
             if (timing) cudaEventRecord(next_event(), s);
             pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,

@@ -11,7 +11,7 @@
 
 #include "accel.h"
 #include "internal.h"
-#include "trav_dyn.cuh"
+#include "trav_coop.cuh"
 
 namespace b200rt {
 
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(512) shade_hits_kernel(float* __restrict__ ima
     image[3 * (size_t)idx + 2] = c.z;
 }
 
-// ---- ray-buffer queries on the persistent traversal driver (trav_dyn.cuh) -----------------------------
+// ---- ray-buffer queries on the persistent traversal driver (trav_coop.cuh) -----------------------------
 struct BufView { uint64_t data; uint32_t count; uint16_t byte_stride; uint16_t elmt; };  // SDK/cuda/BufferView.h:32-38
 
 __device__ __forceinline__ ExtHit make_ext(const Trav& s, bool found)
@@ -76,22 +76,22 @@ struct RayWork {
     uint32_t hg_stride, hg_count;
     uint64_t item;
 
-    __device__ __forceinline__ bool fetch(uint32_t i, Trav& s)
+    __device__ __forceinline__ bool fetch(uint32_t i, Trav& s, float* my_ray)
     {
         item = i;
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
-        if (!trav_begin_handle(s, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, ray_flags & 0x30u, 0u)) {
+        if (!trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, ray_flags & 0x30u, 0u)) {
             commit(s, false);
             return false;
         }
         return true;
     }
-    __device__ __forceinline__ bool next_instance(Trav& s)
+    __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
         if (handle->kind == ACCEL_KIND_GAS) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
-        return trav_begin_handle(s, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY), ray_flags & 0x30u,
+        return trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY), ray_flags & 0x30u,
                                  s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
@@ -149,7 +149,7 @@ struct RayWork {
 struct RaycastParamsDev { uint64_t handle; const float4* rays; float4* hits; };  // optixRaycasting.h:41-46
 
 template <int KIND, bool STATS>
-__global__ void __launch_bounds__(128) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(COOP_BLOCK, 8) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
                                                           uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
                                                           const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
                                                           uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,
@@ -190,9 +190,9 @@ template <int KIND, bool STATS>
 static unsigned persistent_grid_rays(b200rt_context ctx, uint64_t n)
 {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_rays_kernel<KIND, STATS>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_rays_kernel<KIND, STATS>, COOP_BLOCK, 0);
     const uint64_t cap = (uint64_t)std::max(occ, 1) * ctx->sm_count;
-    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(cap, (n + 127) / 128));
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(cap, (n + COOP_BLOCK - 1) / COOP_BLOCK));
 }
 
 int create_rays_ortho(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr rays, int width, int height, const float* bbmin,
@@ -243,7 +243,7 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+    trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
                                                                                        ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0,
                                                                                        counter, nullptr);
     B2_LAUNCH_CHECK(ctx);
@@ -260,7 +260,7 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+    trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
                                                                                        ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0,
                                                                                        counter, nullptr);
     B2_LAUNCH_CHECK(ctx);
@@ -280,7 +280,7 @@ int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b
     B2_CUDA(ctx, cudaMalloc(&scratch, sizeof(ExtHit) * std::max<uint64_t>(n, 1)));
     B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
     if (n) {
-        trace_rays_kernel<0, true><<<persistent_grid_rays<0, true>(ctx, n), 128, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
+        trace_rays_kernel<0, true><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
                                                                                          0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats);
         ctx->launches++;
     }
@@ -308,7 +308,7 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<2, false><<<persistent_grid_rays<2, false>(ctx, n), 128, 0, s>>>(nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr,
+    trace_rays_kernel<2, false><<<persistent_grid_rays<2, false>(ctx, n), COOP_BLOCK, 0, s>>>(nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr,
                                                                                        (const RaycastParamsDev*)d_params,
                                                                                        (const char*)sbt->hitgroupRecordBase,
                                                                                        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount,

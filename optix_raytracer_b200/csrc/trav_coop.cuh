@@ -1,0 +1,344 @@
+// trav_coop.cuh — persistent-warp traversal driver: dynamic ray fetch, batched commits, and a
+// WARP-COOPERATIVE triangle phase.
+//
+// The per-ray traversal of traverse.cuh is re-expressed as a state machine (`Trav`).  One warp keeps its 32
+// lanes busy: a lane whose ray terminates fetches the next work item from a global cursor (Aila/Laine 2009
+// persistent threads; Ylitie/Karras/Laine 2017 dynamic fetch).  What is new relative to that literature is
+// the triangle phase.  ncu on the first two versions (profiles/r01_trace_before.md) showed the node test
+// running at 23.6 of 32 lanes but the per-lane triangle loop at 3.5 lanes — with only ~3 triangles per ray
+// among ~15 nodes, a lane rarely has company when it reaches a leaf — so ~1/3 of all warp instructions were
+// triangle tests at 11 % SIMD efficiency.  Here a lane that reaches a leaf *parks* its triangle group and keeps
+// descending; when the warp has collected enough (ray, triangle) units they are spread over all 32 lanes
+// through shared memory, tested, and min-reduced back to the owning lane:
+//
+//   * node step     : pop the best pending child of the current node group, fetch its 80-byte node, test the 8
+//                     quantised child boxes -> new node group (+ a triangle group that is parked)
+//   * triangle round: prefix-sum the parked triangle counts, owners publish (triangle index, owner lane) units,
+//                     every lane tests one unit against its owner's ray constants (kept in shared memory since
+//                     fetch), owners take the lexicographic minimum (t, ordinal) of their units
+//   * refill        : when fewer than REFILL_THRESHOLD lanes are active, finished lanes commit their results
+//                     together and fetch new items with one warp-aggregated atomicAdd
+//
+// Semantics are exactly those of traverse.cuh (same tri_test arithmetic, same conservative box test, closest =
+// min (t, instance, ordinal)); the hit rule is independent of visit order, so results are bit-identical.
+#pragma once
+#include "traverse.cuh"
+
+namespace b200rt {
+
+constexpr uint32_t NODE_BITS = 0xff000000u;
+constexpr int REFILL_THRESHOLD = 24;   // refill when fewer lanes than this hold a ray
+constexpr int TRI_TRIGGER = 24;        // run a triangle round once this many (ray, triangle) units are parked
+constexpr int COOP_BLOCK = 128;        // CTA size of every kernel built on trace_persistent
+constexpr int COOP_WARPS = COOP_BLOCK / 32;
+constexpr int RAY_S_STRIDE = 9;        // odd stride: lanes reading different owners hit different banks
+
+// pack word layout
+constexpr uint32_t TP_ANY = 1u << 16;        // any-hit (terminate on first hit)
+constexpr uint32_t TP_FOUND = 1u << 17;      // a hit was accepted in the GAS currently being traversed (tie-break scope)
+constexpr uint32_t TP_FOUND_ANY = 1u << 18;  // a hit was accepted in any instance so far
+
+struct Trav {
+    const uint4* nodes;
+    const float4* tris;
+    float ox, oy, oz;       // origin in the space of the GAS being traversed
+    float idx, idy, idz;    // reciprocal (clamped) direction for the box tests
+    float tmin;
+    uint32_t pack;          // kx | ky<<2 | kz<<4 | octinv<<8 | negx<<11 | negy<<12 | negz<<13 | TP_*
+    uint32_t inst;          // index of the instance being traversed (0 for a bare GAS)
+    uint2 ngroup, tgroup;   // current node group; parked triangle group (base, 24-bit mask)
+    int sp;
+    RayHit best;
+};
+
+struct CoopShared {
+    float ray[COOP_WARPS][32 * RAY_S_STRIDE];  // per lane: ox, oy, oz, Sx, Sy, Sz, pack, tmin, cull
+    uint32_t unit_tri[COOP_WARPS][32];
+    uint32_t unit_owner[COOP_WARPS][32];
+    float res_t[COOP_WARPS][32];
+    uint32_t res_ord[COOP_WARPS][32];
+};
+
+// Prepare the per-ray constants for a GAS (object-space origin/direction).  best.t must hold tmax.
+__device__ __forceinline__ void trav_begin(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ gas, float3 o, float3 d, float tmin,
+                                           uint32_t keep_flags, uint32_t cull)
+{
+    const char* base = (const char*)gas;
+    s.nodes = (const uint4*)(base + gas->nodes_off);
+    s.tris = (const float4*)(base + gas->tris_off);
+    const TriRay tr = make_tri_ray(o, d);
+    s.ox = o.x; s.oy = o.y; s.oz = o.z;
+    const float bx = fabsf(d.x) < DIR_EPS ? copysignf(DIR_EPS, d.x) : d.x;
+    const float by = fabsf(d.y) < DIR_EPS ? copysignf(DIR_EPS, d.y) : d.y;
+    const float bz = fabsf(d.z) < DIR_EPS ? copysignf(DIR_EPS, d.z) : d.z;
+    s.idx = fdiv(1.0f, bx); s.idy = fdiv(1.0f, by); s.idz = fdiv(1.0f, bz);
+    const uint32_t nx = bx < 0.0f, ny = by < 0.0f, nz = bz < 0.0f;
+    const uint32_t oct = (nx << 2) | (ny << 1) | nz;
+    s.pack = (uint32_t)tr.kx | ((uint32_t)tr.ky << 2) | ((uint32_t)tr.kz << 4) | ((7u - oct) << 8) | (nx << 11) | (ny << 12) | (nz << 13) | keep_flags;
+    s.tmin = tmin;
+    s.ngroup = gas->num_tris ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
+    s.tgroup = make_uint2(0u, 0u);
+    s.sp = 0;
+    // ray constants of the triangle test, read by whichever lane tests this ray's triangles
+    my_ray[0] = o.x; my_ray[1] = o.y; my_ray[2] = o.z;
+    my_ray[3] = tr.Sx; my_ray[4] = tr.Sy; my_ray[5] = tr.Sz;
+    my_ray[6] = __uint_as_float(s.pack & 0x3fu);
+    my_ray[7] = tmin;
+    my_ray[8] = __uint_as_float(cull);
+}
+
+// Set up traversal of `h` (GAS, or the first usable instance >= first_inst of an IAS) for the world-space ray.
+// keep = TP_* bits to carry over.  Returns false when there is nothing (more) to traverse.
+__device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ h, float3 o, float3 d,
+                                                  float tmin, uint32_t keep, uint32_t cull, uint32_t first_inst)
+{
+    if (h->kind == ACCEL_KIND_GAS) {
+        if (first_inst > 0u) return false;
+        s.inst = 0u;
+        trav_begin(s, my_ray, h, o, d, tmin, keep, cull);
+        return true;
+    }
+    const InstanceRecord* recs = (const InstanceRecord*)((const char*)h + h->inst_off);
+    const uint32_t n = h->num_instances;
+    for (uint32_t k = first_inst; k < n; ++k) {
+        const InstanceRecord* ir = recs + k;
+        if (!(ir->mask & 1u)) continue;
+        s.inst = k;
+        const uint32_t c = (ir->flags & 1u) ? 0u : cull;  // OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING
+        trav_begin(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c);
+        return true;
+    }
+    return false;
+}
+
+// One node visit; returns the triangle group of the visited node (mask 0 = none).
+__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st)
+{
+    const uint32_t hits_imask = s.ngroup.y;
+    const uint32_t bit = 31u - __clz(hits_imask);
+    const uint32_t child_base = s.ngroup.x;
+    s.ngroup.y &= ~(1u << bit);
+    if (s.ngroup.y & NODE_BITS) {
+        if (s.sp < TRAV_STACK) stack[s.sp++] = s.ngroup;
+    }
+    const uint32_t octinv = (s.pack >> 8) & 7u;
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
+    const uint4* np = s.nodes + (size_t)(child_base + rel) * 5u;
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    if (st) st->nodes++;
+    const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+    const uint32_t e_imask = n0.w;
+    const float aix = __uint_as_float((e_imask & 0xffu) << 23) * s.idx;
+    const float aiy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * s.idy;
+    const float aiz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * s.idz;
+    const float aox = (px - s.ox) * s.idx, aoy = (py - s.oy) * s.idy, aoz = (pz - s.oz) * s.idz;
+    const float tfar = s.best.t, tmin = s.tmin;
+    const bool negx = (s.pack >> 11) & 1u, negy = (s.pack >> 12) & 1u, negz = (s.pack >> 13) & 1u;
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = byte_mask_from_bit4(is_inner4);
+        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t xn = negx ? qhix : qlox, xf = negx ? qlox : qhix;
+        const uint32_t yn = negy ? qhiy : qloy, yf = negy ? qloy : qhiy;
+        const uint32_t zn = negz ? qhiz : qloz, zf = negz ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tnx = fm(byte_f(xn, j), aix, aox), tfx = fm(byte_f(xf, j), aix, aox);
+            const float tny = fm(byte_f(yn, j), aiy, aoy), tfy = fm(byte_f(yf, j), aiy, aoy);
+            const float tnz = fm(byte_f(zn, j), aiz, aoz), tfz = fm(byte_f(zf, j), aiz, aoz);
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
+            if (cmin <= cmax * BOX_SLACK) {
+                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+                const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= cb << bi;
+            }
+        }
+    }
+    s.ngroup = make_uint2(n1.x, (hitmask & NODE_BITS) | (e_imask >> 24));
+    return make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// Arithmetic of tri_test (traverse.cuh) for one (ray, triangle) unit, without the acceptance bookkeeping: returns
+// true when tmin < t <= tfar and the face-cull flags let the triangle through; the owner decides ties.
+__device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const float4 q0, const float4 q1, const float4 q2, float tfar, float& t_out,
+                                         float& b1, float& b2)
+{
+    TriRay tr;
+    tr.o = f3(r[0], r[1], r[2]);
+    tr.Sx = r[3]; tr.Sy = r[4]; tr.Sz = r[5];
+    const uint32_t k = __float_as_uint(r[6]);
+    tr.kx = (int)(k & 3u); tr.ky = (int)((k >> 2) & 3u); tr.kz = (int)((k >> 4) & 3u);
+    RayHit tmp;
+    tmp.t = tfar;
+    // found = true with the largest ordinal makes tri_test's tie rule accept every tmin < t <= tfar; the owner re-applies the real
+    // rule (strictly smaller t, or equal t and a lower ordinal than its current best within this GAS)
+    tmp.ord = 0xffffffffu;
+    bool found = true;
+    const bool hit = tri_test<false>(tr, q0, q1, q2, r[7], tmp, found, __float_as_uint(r[8]));
+    t_out = tmp.t; b1 = tmp.b1; b2 = tmp.b2;
+    return hit;
+}
+
+// Work concept:
+//   __device__ bool  fetch(uint32_t item, Trav& s, float* my_ray)  load item, set s.best.t = tmax, call trav_begin_handle; false = nothing to trace
+//   __device__ bool  next_instance(Trav& s, float* my_ray)         IAS: set up the next instance (true) or report none left (false)
+//   __device__ void  commit(const Trav& s, bool found)             store the result of the finished item
+template <class Work>
+__device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, unsigned int* __restrict__ fetch_counter, TravStats* st)
+{
+    __shared__ CoopShared sh;
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    float* my_ray = &sh.ray[wid][lane * RAY_S_STRIDE];
+    uint2 stack[TRAV_STACK];
+    Trav s;
+    s.tgroup = make_uint2(0u, 0u);
+    s.ngroup = make_uint2(0u, 0u);
+    s.pack = 0u;
+    s.best.t = 0.f;
+    bool has = false, fin = false, exhausted = false;
+    for (;;) {
+        // ---- commit finished rays together, then every lane without a ray takes the next work item
+        if (fin) { work.commit(s, (s.pack & TP_FOUND_ANY) != 0u); fin = false; }
+        unsigned need = __ballot_sync(FULL, !has && !exhausted);
+        while (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(fetch_counter, (unsigned)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!has && !exhausted) {
+                const uint32_t item = base + __popc(need & lt);
+                if (item >= n_items) exhausted = true;
+                else has = work.fetch(item, s, my_ray);
+            }
+            need = __ballot_sync(FULL, !has && !exhausted);
+        }
+        __syncwarp();
+        unsigned act = __ballot_sync(FULL, has);
+        if (act == 0) break;
+        const bool can_refill = !__any_sync(FULL, exhausted);
+        // ---- traverse until the warp drains below the refill threshold
+        for (;;) {
+            bool blocked = false;  // this lane can only continue after a triangle round
+            if (has) {
+                if (s.ngroup.y & NODE_BITS) {
+                    const uint2 nt = trav_node_step(s, stack, st);
+                    if (nt.y) {
+                        if (s.tgroup.y == 0u) s.tgroup = nt;
+                        else if (s.sp < TRAV_STACK) stack[s.sp++] = nt;  // second parked group: goes on the stack (no NODE_BITS marks it)
+                        else {
+                            // stack full (pathological depth): test the group right here, one lane
+                            uint2 g = nt;
+                            while (g.y) {
+                                const uint32_t ti = 31u - __clz(g.y);
+                                g.y &= ~(1u << ti);
+                                const float4* tp = s.tris + (size_t)(g.x + ti) * 3u;
+                                const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                                if (st) st->tris++;
+                                float t, b1, b2;
+                                if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
+                                    const uint32_t ord = __float_as_uint(q2.w);
+                                    if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
+                                        s.best.t = t; s.best.b1 = b1; s.best.b2 = b2; s.best.ord = ord;
+                                        s.best.prim = __float_as_uint(q0.w); s.best.sbt = __float_as_uint(q1.w); s.best.inst = s.inst;
+                                        s.pack |= TP_FOUND | TP_FOUND_ANY;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else if (s.sp > 0) {
+                    const uint2 e = stack[s.sp - 1];
+                    if (e.y & NODE_BITS) { s.ngroup = e; --s.sp; }
+                    else if (s.tgroup.y == 0u) { s.tgroup = e; --s.sp; }
+                    else blocked = true;  // both triangle slots taken
+                } else if (s.tgroup.y != 0u) {
+                    blocked = true;       // only the parked triangles are left
+                } else {
+                    // this GAS is done
+                    if (!((s.pack & TP_ANY) && (s.pack & TP_FOUND_ANY)) && work.next_instance(s, my_ray)) { /* next instance set up */ }
+                    else { has = false; fin = true; }
+                }
+            }
+            // ---- triangle round?
+            const uint32_t cnt = has ? (uint32_t)__popc(s.tgroup.y) : 0u;
+            const uint32_t total = __reduce_add_sync(FULL, cnt);
+            act = __ballot_sync(FULL, has);
+            const unsigned blk = __ballot_sync(FULL, blocked);
+            if (total >= (uint32_t)TRI_TRIGGER || (total != 0u && __popc(blk) * 2 >= __popc(act))) {
+                // exclusive prefix sum of the unit counts
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                    if ((int)lane >= d) incl += v;
+                }
+                const uint32_t first = incl - cnt;
+                uint32_t pos = first, rem = has ? s.tgroup.y : 0u;
+                for (uint32_t base = 0; base < total; base += 32u) {
+                    while (rem != 0u && pos < base + 32u) {
+                        const uint32_t ti = 31u - __clz(rem);
+                        rem &= ~(1u << ti);
+                        sh.unit_tri[wid][pos - base] = s.tgroup.x + ti;
+                        sh.unit_owner[wid][pos - base] = lane;
+                        ++pos;
+                    }
+                    __syncwarp();
+                    const bool valid = base + lane < total;
+                    const uint32_t owner = valid ? sh.unit_owner[wid][lane] : lane;
+                    const float tfar = __shfl_sync(FULL, s.best.t, owner);
+                    const uint64_t tris_base = __shfl_sync(FULL, (unsigned long long)(uintptr_t)s.tris, owner);
+                    float ut = 0.f, ub1 = 0.f, ub2 = 0.f;
+                    uint32_t uord = 0xffffffffu, uprim = 0u, usbt = 0u;
+                    bool uhit = false;
+                    if (valid) {
+                        const float4* tp = (const float4*)(uintptr_t)tris_base + (size_t)sh.unit_tri[wid][lane] * 3u;
+                        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                        if (st) st->tris++;
+                        uhit = tri_unit(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
+                        uord = __float_as_uint(q2.w); uprim = __float_as_uint(q0.w); usbt = __float_as_uint(q1.w);
+                    }
+                    sh.res_t[wid][lane] = uhit ? ut : __int_as_float(0x7f800000);
+                    sh.res_ord[wid][lane] = uord;
+                    __syncwarp();
+                    // owners: lexicographic minimum (t, ordinal) over their units of this chunk, same acceptance rule as tri_test
+                    int win = -1;
+                    if (cnt) {
+                        const uint32_t lo = first > base ? first : base;
+                        const uint32_t hi = (first + cnt) < (base + 32u) ? (first + cnt) : (base + 32u);
+                        for (uint32_t p = lo; p < hi; ++p) {
+                            const float t = sh.res_t[wid][p - base];
+                            const uint32_t ord = sh.res_ord[wid][p - base];
+                            if (t < s.best.t || (t == s.best.t && (s.pack & TP_FOUND) && ord < s.best.ord)) {
+                                s.best.t = t; s.best.ord = ord; win = (int)(p - base);
+                                s.pack |= TP_FOUND | TP_FOUND_ANY;
+                            }
+                        }
+                    }
+                    const int src = win >= 0 ? win : (int)lane;
+                    const float wb1 = __shfl_sync(FULL, ub1, src), wb2 = __shfl_sync(FULL, ub2, src);
+                    const uint32_t wprim = __shfl_sync(FULL, uprim, src), wsbt = __shfl_sync(FULL, usbt, src);
+                    if (win >= 0) { s.best.b1 = wb1; s.best.b2 = wb2; s.best.prim = wprim; s.best.sbt = wsbt; s.best.inst = s.inst; }
+                    __syncwarp();
+                }
+                if (has) {
+                    s.tgroup.y = 0u;
+                    if ((s.pack & TP_ANY) && (s.pack & TP_FOUND)) { s.ngroup.y = 0u; s.sp = 0; }  // any-hit: done
+                }
+            }
+            if (act == 0u || (can_refill && __popc(act) < REFILL_THRESHOLD)) break;
+        }
+    }
+}
+
+}  // namespace b200rt

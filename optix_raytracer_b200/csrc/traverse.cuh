@@ -114,7 +114,10 @@ __device__ __forceinline__ bool tri_test(const TriRay& r, const float4 q0, const
 
 // bytes with bit 4 set -> 0xff, others -> 0x00 (x has at most bit 4 of each byte set)
 __device__ __forceinline__ uint32_t byte_mask_from_bit4(uint32_t x) { return (x >> 4) * 0xffu; }
-__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xffu); }
+// byte j of w as a float, exactly: PRMT builds the bit pattern of 2^23 + q (0x4B0000qq) on the ALU pipe and one FADD removes the
+// 2^23 on the FMA pipe.  The plain (float)((w >> 8j) & 0xff) compiles to I2F on the quarter-rate XU pipe, which ncu showed as the
+// busiest pipe of the node test (profiles/r01_trace_before.md: xu 42 %, fma 16 %).  48 conversions per node visit.
+__device__ __forceinline__ float byte_f(uint32_t w, int j) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (uint32_t)j)) - 8388608.0f; }
 
 // Trace one ray through one GAS.  `best.t` carries tmax in and the closest t out.
 template <bool ANY, bool STATS>

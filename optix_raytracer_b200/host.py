@@ -86,6 +86,17 @@ class Context:
         return t
 
     # ---- acceleration structures ---------------------------------------------------------------
+    # the three acceleration-structure calls of the boundary; oracle/optix_ref/backend.py overrides them with OptiX's
+    def _accel_memory_usage(self, opts, arr, n, sizes):
+        self.check(self.lib.b200rt_accel_compute_memory_usage(self.h, C.byref(opts), arr, n, C.byref(sizes)), "compute_memory_usage")
+
+    def _accel_build(self, opts, arr, n, temp, temp_bytes, out, out_bytes, handle, emit):
+        self.check(self.lib.b200rt_accel_build(self.h, self.stream, C.byref(opts), arr, n, temp, temp_bytes, out, out_bytes, C.byref(handle),
+                                               C.byref(emit) if emit is not None else None, 1 if emit is not None else 0), "accel_build")
+
+    def _accel_compact(self, handle, out, out_bytes, new_handle):
+        self.check(self.lib.b200rt_accel_compact(self.h, self.stream, handle, out, out_bytes, C.byref(new_handle)), "accel_compact")
+
     def build_accel(self, build_inputs, compact=True, keep=()):
         """optixAccelComputeMemoryUsage + optixAccelBuild (+ optixAccelCompact), the sequence of
         SDK/optixPathTracer/optixPathTracer.cpp:627-684.  Returns Accel."""
@@ -93,14 +104,14 @@ class Context:
         arr = (L.BuildInput * n)(*build_inputs)
         opts = L.AccelBuildOptions(L.BUILD_FLAG_ALLOW_COMPACTION if compact else 0, L.BUILD_OPERATION_BUILD)
         sizes = L.AccelBufferSizes()
-        self.check(self.lib.b200rt_accel_compute_memory_usage(self.h, C.byref(opts), arr, n, C.byref(sizes)), "compute_memory_usage")
+        self._accel_memory_usage(opts, arr, n, sizes)
         temp = self.empty_bytes(sizes.tempSizeInBytes)
         out = self.empty_bytes(sizes.outputSizeInBytes)
         csize = torch.zeros(1, dtype=torch.int64, device=self.torch_device)
-        emit = L.AccelEmitDesc(csize.data_ptr(), L.PROPERTY_TYPE_COMPACTED_SIZE)
+        # the compacted size may only be queried when the build allows compaction (OptiX rejects it otherwise)
+        emit = L.AccelEmitDesc(csize.data_ptr(), L.PROPERTY_TYPE_COMPACTED_SIZE) if compact else None
         handle = C.c_uint64()
-        self.check(self.lib.b200rt_accel_build(self.h, self.stream, C.byref(opts), arr, n, temp.data_ptr(), sizes.tempSizeInBytes,
-                                               out.data_ptr(), sizes.outputSizeInBytes, C.byref(handle), C.byref(emit), 1), "accel_build")
+        self._accel_build(opts, arr, n, temp.data_ptr(), sizes.tempSizeInBytes, out.data_ptr(), sizes.outputSizeInBytes, handle, emit)
         acc = Accel(self, out, handle.value, keep)
         acc.uncompacted_bytes = int(sizes.outputSizeInBytes)
         acc.temp_bytes = int(sizes.tempSizeInBytes)
@@ -109,14 +120,32 @@ class Context:
             if compacted < sizes.outputSizeInBytes:
                 out2 = self.empty_bytes(compacted)
                 h2 = C.c_uint64()
-                self.check(self.lib.b200rt_accel_compact(self.h, self.stream, handle.value, out2.data_ptr(), compacted, C.byref(h2)),
-                           "accel_compact")
+                self._accel_compact(handle.value, out2.data_ptr(), compacted, h2)
                 torch.cuda.synchronize(self.torch_device)
                 acc = Accel(self, out2, h2.value, keep)
                 acc.uncompacted_bytes = int(sizes.outputSizeInBytes)
                 acc.temp_bytes = int(sizes.tempSizeInBytes)
         del temp
         return acc
+
+    # ---- launches (the optixLaunch replacements) and SBT headers --------------------------------------
+    def prepare_programs(self, kind):
+        """kind: 'pathtracer' | 'multigpu' | 'raycast'.  Nothing to do here: the device programs are compiled into
+        libb200rt.so.  (The OptiX backend creates module / program groups / pipeline at this point.)"""
+        return None
+
+    def sbt_header(self, programs, kind, index):
+        """The 32-byte SBT record header optixSbtRecordPackHeader would write; b200rt ignores it (zeros)."""
+        return bytes(32)
+
+    def launch_pathtracer(self, programs, d_params, params_size, sbt, width, height, opts):
+        self.check(self.lib.b200rt_launch_pathtracer(self.h, self.stream, d_params, C.byref(sbt), width, height, C.byref(opts)), "launch_pathtracer")
+
+    def launch_multigpu(self, programs, d_params, params_size, sbt, num_samples, opts):
+        self.check(self.lib.b200rt_launch_multigpu(self.h, self.stream, d_params, C.byref(sbt), num_samples, C.byref(opts)), "launch_multigpu")
+
+    def launch_raycast(self, programs, d_params, sbt, width, height, ext):
+        self.check(self.lib.b200rt_launch_raycast(self.h, self.stream, d_params, C.byref(sbt), width, height, ext), "launch_raycast")
 
     def triangle_input(self, vertices, indices=None, sbt_index=None, num_sbt=1, flags=None, vertex_stride=None, pre_transform=None,
                        prim_offset=0):
@@ -305,14 +334,22 @@ class PathTracer:
         # createSBT (optixPathTracer.cpp:829-898 / optixMultiGPU.cpp:960-1018)
         self.multigpu = multigpu
         ray_types = 2 if multigpu else 1
+        self.programs = ctx.prepare_programs("multigpu" if multigpu else "pathtracer")
         rec = np.zeros((nmat * ray_types, 64), np.uint8)
         for i in range(nmat):
             data = struct.pack("<3f3fQ", *sc["emission_colors"][i], *sc["diffuse_colors"][i], vertices.data_ptr())
+            rec[i * ray_types, 0:32] = np.frombuffer(ctx.sbt_header(self.programs, 2, 0), np.uint8)
             rec[i * ray_types, 32:64] = np.frombuffer(data, np.uint8)
+            if ray_types == 2:  # zeroed occlusion record (optixMultiGPU.cpp:1000-1006)
+                rec[i * ray_types + 1, 0:32] = np.frombuffer(ctx.sbt_header(self.programs, 2, 1), np.uint8)
         self.d_hitgroup = ctx.to_device(rec)
         miss = np.zeros((ray_types, 48), np.uint8)  # MissData{bg_color = 0}
+        for r in range(ray_types):
+            miss[r, 0:32] = np.frombuffer(ctx.sbt_header(self.programs, 1, r), np.uint8)
         self.d_miss = ctx.to_device(miss)
-        self.d_raygen = ctx.to_device(np.zeros(32, np.uint8))
+        rg = np.zeros(32, np.uint8)
+        rg[:] = np.frombuffer(ctx.sbt_header(self.programs, 0, 0), np.uint8)
+        self.d_raygen = ctx.to_device(rg)
         self.sbt = L.ShaderBindingTable()
         self.sbt.raygenRecord = self.d_raygen.data_ptr()
         self.sbt.missRecordBase = self.d_miss.data_ptr()
@@ -353,11 +390,9 @@ class PathTracer:
         opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))  # bit mask of L.PT_STATS_*
         ctx = self.ctx
         if self.multigpu:
-            ctx.check(ctx.lib.b200rt_launch_multigpu(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.num_samples,
-                                                     C.byref(opts)), "launch_multigpu")
+            ctx.launch_multigpu(self.programs, self.d_params.data_ptr(), C.sizeof(self.params), self.sbt, self.num_samples, opts)
         else:
-            ctx.check(ctx.lib.b200rt_launch_pathtracer(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.width, self.height,
-                                                       C.byref(opts)), "launch_pathtracer")
+            ctx.launch_pathtracer(self.programs, self.d_params.data_ptr(), C.sizeof(self.params), self.sbt, self.width, self.height, opts)
         return self.stats if collect_stats else None
 
 
@@ -452,6 +487,7 @@ class Raycaster:
         self.scene = scene
         dev = ctx.torch_device
         self.mesh_accels, self.keep = [], []
+        self.programs = ctx.prepare_programs("raycast")
         records = []
         self.mesh_sbt_base = []
         for m in scene["meshes"]:
@@ -468,6 +504,7 @@ class Raycaster:
                 self.keep += [d_pos, d_nrm, d_idx]
                 # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, TriangleMesh @8}; BufferView = {ptr, count, u16 stride, u16 elmt}
                 rec = bytearray(32 + 352)
+                rec[0:32] = ctx.sbt_header(self.programs, 2, 0)
                 def bview(t, elmt, stride):
                     return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride, elmt)
                 isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
@@ -482,8 +519,9 @@ class Raycaster:
             inst.append((i["transform"][:3, :].reshape(12), self.mesh_sbt_base[i["mesh"]], self.mesh_accels[i["mesh"]]))
         self.ias = ctx.build_accel([ctx.instance_input(inst)], compact=False)
         self.sbt = L.ShaderBindingTable()
-        self.d_miss = ctx.to_device(np.zeros(32, np.uint8))
-        self.sbt.raygenRecord = self.d_miss.data_ptr()
+        self.d_miss = ctx.to_device(np.frombuffer(ctx.sbt_header(self.programs, 1, 0), np.uint8).copy())
+        self.d_raygen = ctx.to_device(np.frombuffer(ctx.sbt_header(self.programs, 0, 0), np.uint8).copy())
+        self.sbt.raygenRecord = self.d_raygen.data_ptr()
         self.sbt.missRecordBase = self.d_miss.data_ptr()
         self.sbt.missRecordStrideInBytes = 32
         self.sbt.missRecordCount = 1
@@ -496,7 +534,9 @@ class Raycaster:
 
     def buffer_rays(self, width):
         """bufferRays (optixRaycasting.cpp:255-286)."""
-        ctx, dev = self.ctx, self.ctx.torch_device
+        # the ray-generation / translate / shade helpers are plain CUDA kernels in the reference too (optixRaycastingKernels.cu);
+        # a context of another back end (oracle/optix_ref) borrows b200rt's through its `helper` attribute
+        ctx, dev = getattr(self.ctx, "helper", self.ctx), self.ctx.torch_device
         span = (self.bbmax - self.bbmin).astype(np.float32)
         self.width = width
         self.height = int(np.float32(width) * span[1] / span[0])
@@ -512,6 +552,7 @@ class Raycaster:
         self.ext = torch.empty((n, 5), dtype=torch.int32, device=dev)
         self.ext_translated = torch.empty((n, 5), dtype=torch.int32, device=dev)
         self.translate_offset = off
+        ctx = self.ctx
         p1 = RaycastParams(self.ias.handle, self.rays.data_ptr(), self.hits.data_ptr())
         p2 = RaycastParams(self.ias.handle, self.rays_translated.data_ptr(), self.hits_translated.data_ptr())
         self.d_params = ctx.to_device(np.frombuffer(bytes(p1), np.uint8).copy())
@@ -521,13 +562,12 @@ class Raycaster:
     def launch(self, want_ext=True):
         """launch (optixRaycasting.cpp:289-317): both batches (the reference uses two streams; same stream here)."""
         ctx = self.ctx
-        ctx.check(ctx.lib.b200rt_launch_raycast(ctx.h, ctx.stream, self.d_params.data_ptr(), C.byref(self.sbt), self.width, self.height,
-                                                self.ext.data_ptr() if want_ext else 0), "launch_raycast")
-        ctx.check(ctx.lib.b200rt_launch_raycast(ctx.h, ctx.stream, self.d_params_translated.data_ptr(), C.byref(self.sbt), self.width,
-                                                self.height, self.ext_translated.data_ptr() if want_ext else 0), "launch_raycast")
+        ctx.launch_raycast(self.programs, self.d_params.data_ptr(), self.sbt, self.width, self.height, self.ext.data_ptr() if want_ext else 0)
+        ctx.launch_raycast(self.programs, self.d_params_translated.data_ptr(), self.sbt, self.width, self.height,
+                           self.ext_translated.data_ptr() if want_ext else 0)
 
     def shade(self, hits):
-        ctx = self.ctx
+        ctx = getattr(self.ctx, "helper", self.ctx)
         n = hits.shape[0]
         img = torch.empty((n, 3), dtype=torch.float32, device=ctx.torch_device)
         ctx.check(ctx.lib.b200rt_shade_hits(ctx.h, ctx.stream, img.data_ptr(), n, hits.data_ptr()), "shade_hits")
