@@ -4,7 +4,10 @@ import ctypes as C
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libb200rt.so"
+import os
+
+# B200RT_LIB_PATH: development override used for A/B runs of kernel variants (tools/ab_variants.sh); the product path is the default
+LIB_PATH = pathlib.Path(os.environ.get("B200RT_LIB_PATH", _HERE / "libb200rt.so"))
 
 u32, i32, u64, f32, vp, sz = C.c_uint32, C.c_int32, C.c_uint64, C.c_float, C.c_void_p, C.c_size_t
 

@@ -112,8 +112,10 @@ struct RayWork {
             }
             if (sbt >= hg_count) sbt = hg_count - 1;
             const char* rec = hg_base + (size_t)sbt * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE;
-            // whitted::HitGroupData -> GeometryData{type@0, TriangleMesh@8{indices, positions, normals, ...}}
-            const BufView vi = *(const BufView*)(rec + 8), vp = *(const BufView*)(rec + 24), vn = *(const BufView*)(rec + 40);
+            // whitted::HitGroupData -> GeometryData{type @0, union @16 (16-byte aligned): TriangleMesh{indices @16, positions @32,
+            // normals @48, texcoords[2] @64/@80, colors @96}} — offsets measured on the reference headers (oracle/ref_shim.cpp,
+            // tests/golden/kat.json "hitgroup_layout")
+            const BufView vi = *(const BufView*)(rec + 16), vp = *(const BufView*)(rec + 32), vn = *(const BufView*)(rec + 48);
             const uint32_t prim = s.best.prim;
             uint32_t i0, i1, i2;
             if (vi.elmt == 4) { const uint32_t* ip = (const uint32_t*)vi.data + 3 * (size_t)prim; i0 = ip[0]; i1 = ip[1]; i2 = ip[2]; }

@@ -26,6 +26,9 @@
 
 namespace b200rt {
 
+#ifndef B200RT_LOOKTHROUGH
+#define B200RT_LOOKTHROUGH 0
+#endif
 constexpr uint32_t NODE_BITS = 0xff000000u;
 constexpr int REFILL_THRESHOLD = 24;   // refill when fewer lanes than this hold a ray
 constexpr int TRI_TRIGGER = 24;        // run a triangle round once this many (ray, triangle) units are parked
@@ -150,16 +153,23 @@ __device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ sta
         const uint32_t yn = negy ? qhiy : qloy, yf = negy ? qloy : qhiy;
         const uint32_t zn = negz ? qhiz : qloz, zf = negz ? qloz : qhiz;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float tnx = fm(byte_f(xn, j), aix, aox), tfx = fm(byte_f(xf, j), aix, aox);
-            const float tny = fm(byte_f(yn, j), aiy, aoy), tfy = fm(byte_f(yf, j), aiy, aoy);
-            const float tnz = fm(byte_f(zn, j), aiz, aoz), tfz = fm(byte_f(zf, j), aiz, aoz);
-            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
-            if (cmin <= cmax * BOX_SLACK) {
-                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
-                const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= cb << bi;
+        for (int jp = 0; jp < 2; ++jp) {
+            const BytePair pxn = jp ? byte_pair23(xn) : byte_pair01(xn), pxf = jp ? byte_pair23(xf) : byte_pair01(xf);
+            const BytePair pyn = jp ? byte_pair23(yn) : byte_pair01(yn), pyf = jp ? byte_pair23(yf) : byte_pair01(yf);
+            const BytePair pzn = jp ? byte_pair23(zn) : byte_pair01(zn), pzf = jp ? byte_pair23(zf) : byte_pair01(zf);
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+                const int j = 2 * jp + jh;
+                const float tnx = fm(jh ? pair_hi(pxn) : pair_lo(pxn), aix, aox), tfx = fm(jh ? pair_hi(pxf) : pair_lo(pxf), aix, aox);
+                const float tny = fm(jh ? pair_hi(pyn) : pair_lo(pyn), aiy, aoy), tfy = fm(jh ? pair_hi(pyf) : pair_lo(pyf), aiy, aoy);
+                const float tnz = fm(jh ? pair_hi(pzn) : pair_lo(pzn), aiz, aoz), tfz = fm(jh ? pair_hi(pzf) : pair_lo(pzf), aiz, aoz);
+                const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+                const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
+                if (cmin <= cmax * BOX_SLACK) {
+                    const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+                    const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+                    hitmask |= cb << bi;
+                }
             }
         }
     }
@@ -229,47 +239,61 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
         const bool can_refill = !__any_sync(FULL, exhausted);
         // ---- traverse until the warp drains below the refill threshold
         for (;;) {
+            // ---- phase A (divergent, short): lanes whose node group is used up take the next one off the stack, finish, or block.
+            // Kept apart from the node step by __syncwarp(): the node step below must run ONCE per iteration with every lane that
+            // has node work in it (without the barrier the compiler threads the "popped a node group" path straight into its own
+            // copy of the node step and the warp executes that expensive block twice with complementary halves).
             bool blocked = false;  // this lane can only continue after a triangle round
-            if (has) {
-                if (s.ngroup.y & NODE_BITS) {
-                    const uint2 nt = trav_node_step(s, stack, st);
-                    if (nt.y) {
-                        if (s.tgroup.y == 0u) s.tgroup = nt;
-                        else if (s.sp < TRAV_STACK) stack[s.sp++] = nt;  // second parked group: goes on the stack (no NODE_BITS marks it)
-                        else {
-                            // stack full (pathological depth): test the group right here, one lane
-                            uint2 g = nt;
-                            while (g.y) {
-                                const uint32_t ti = 31u - __clz(g.y);
-                                g.y &= ~(1u << ti);
-                                const float4* tp = s.tris + (size_t)(g.x + ti) * 3u;
-                                const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                                if (st) st->tris++;
-                                float t, b1, b2;
-                                if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
-                                    const uint32_t ord = __float_as_uint(q2.w);
-                                    if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
-                                        s.best.t = t; s.best.b1 = b1; s.best.b2 = b2; s.best.ord = ord;
-                                        s.best.prim = __float_as_uint(q0.w); s.best.sbt = __float_as_uint(q1.w); s.best.inst = s.inst;
-                                        s.pack |= TP_FOUND | TP_FOUND_ANY;
-                                    }
+            if (has && !(s.ngroup.y & NODE_BITS)) {
+                // triangle groups met on the way down the stack are parked, or — slot taken — skipped over when a node group sits
+                // right below them (B200RT_LOOKTHROUGH)
+                while (s.sp > 0) {
+                    const uint2 e = stack[s.sp - 1];
+                    if (e.y & NODE_BITS) { s.ngroup = e; --s.sp; break; }
+                    if (s.tgroup.y == 0u) { s.tgroup = e; --s.sp; continue; }
+                    if (B200RT_LOOKTHROUGH && s.sp >= 2) {
+                        const uint2 below = stack[s.sp - 2];
+                        if (below.y & NODE_BITS) { s.ngroup = below; stack[s.sp - 2] = e; --s.sp; break; }
+                    }
+                    blocked = true;  // both triangle slots taken and no node group within reach
+                    break;
+                }
+                if (!(s.ngroup.y & NODE_BITS) && !blocked) {
+                    if (s.tgroup.y != 0u) blocked = true;  // only the parked triangles are left
+                    else if (!((s.pack & TP_ANY) && (s.pack & TP_FOUND_ANY)) && work.next_instance(s, my_ray)) { /* next instance set up */ }
+                    else { has = false; fin = true; }
+                }
+            }
+            __syncwarp();
+            // ---- phase B: one node visit for every lane that has node work
+            if (has && (s.ngroup.y & NODE_BITS)) {
+                const uint2 nt = trav_node_step(s, stack, st);
+                if (nt.y) {
+                    if (s.tgroup.y == 0u) s.tgroup = nt;
+                    else if (s.sp < TRAV_STACK) stack[s.sp++] = nt;  // second parked group: goes on the stack (no NODE_BITS marks it)
+                    else {
+                        // stack full (pathological depth): test the group right here, one lane
+                        uint2 g = nt;
+                        while (g.y) {
+                            const uint32_t ti = 31u - __clz(g.y);
+                            g.y &= ~(1u << ti);
+                            const float4* tp = s.tris + (size_t)(g.x + ti) * 3u;
+                            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                            if (st) st->tris++;
+                            float t, b1, b2;
+                            if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
+                                const uint32_t ord = __float_as_uint(q2.w);
+                                if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
+                                    s.best.t = t; s.best.b1 = b1; s.best.b2 = b2; s.best.ord = ord;
+                                    s.best.prim = __float_as_uint(q0.w); s.best.sbt = __float_as_uint(q1.w); s.best.inst = s.inst;
+                                    s.pack |= TP_FOUND | TP_FOUND_ANY;
                                 }
                             }
                         }
                     }
-                } else if (s.sp > 0) {
-                    const uint2 e = stack[s.sp - 1];
-                    if (e.y & NODE_BITS) { s.ngroup = e; --s.sp; }
-                    else if (s.tgroup.y == 0u) { s.tgroup = e; --s.sp; }
-                    else blocked = true;  // both triangle slots taken
-                } else if (s.tgroup.y != 0u) {
-                    blocked = true;       // only the parked triangles are left
-                } else {
-                    // this GAS is done
-                    if (!((s.pack & TP_ANY) && (s.pack & TP_FOUND_ANY)) && work.next_instance(s, my_ray)) { /* next instance set up */ }
-                    else { has = false; fin = true; }
                 }
             }
+            __syncwarp();
             // ---- triangle round?
             const uint32_t cnt = has ? (uint32_t)__popc(s.tgroup.y) : 0u;
             const uint32_t total = __reduce_add_sync(FULL, cnt);

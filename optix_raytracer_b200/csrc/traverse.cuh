@@ -114,10 +114,43 @@ __device__ __forceinline__ bool tri_test(const TriRay& r, const float4 q0, const
 
 // bytes with bit 4 set -> 0xff, others -> 0x00 (x has at most bit 4 of each byte set)
 __device__ __forceinline__ uint32_t byte_mask_from_bit4(uint32_t x) { return (x >> 4) * 0xffu; }
-// byte j of w as a float, exactly: PRMT builds the bit pattern of 2^23 + q (0x4B0000qq) on the ALU pipe and one FADD removes the
-// 2^23 on the FMA pipe.  The plain (float)((w >> 8j) & 0xff) compiles to I2F on the quarter-rate XU pipe, which ncu showed as the
-// busiest pipe of the node test (profiles/r01_trace_before.md: xu 42 %, fma 16 %).  48 conversions per node visit.
-__device__ __forceinline__ float byte_f(uint32_t w, int j) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (uint32_t)j)) - 8388608.0f; }
+// Bytes of w as floats, exactly and without the quarter-rate I2F (XU pipe) that (float)((w >> 8j) & 0xff) compiles to — ncu
+// showed XU as the busiest pipe of the node test (profiles/r01_trace_v1.md: xu 42 %, fma 16 %), then, after a PRMT + FADD
+// version, the ALU pipe (64 %).  One PRMT (ALU pipe) builds two fp16 bit patterns 0x64qq = 1024 + q at once, and sm_100's
+// mixed-precision add (PTX add.rn.f32.f16 -> SASS FHADD with a .H0/.H1 operand select, FMA pipe) subtracts the 1024 in fp32:
+// 24 ALU + 48 FMA-pipe instructions per node visit for its 48 plane bytes, every value exact.
+struct BytePair { uint32_t h; };  // half2 bit pattern {1024 + b_lo, 1024 + b_hi}
+__device__ __forceinline__ BytePair byte_pair01(uint32_t w) { return BytePair{__byte_perm(w, 0x64646464u, 0x4140u)}; }
+__device__ __forceinline__ BytePair byte_pair23(uint32_t w) { return BytePair{__byte_perm(w, 0x64646464u, 0x4342u)}; }
+#ifndef B200RT_DECODE_FADD
+#define B200RT_DECODE_FADD 0
+#endif
+__device__ __forceinline__ float pair_lo(BytePair p)
+{
+#if B200RT_DECODE_FADD
+    return __uint_as_float(0x4B000000u | (p.h & 0xffu)) - 8388608.0f;
+#else
+    float f;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(f) : "h"((unsigned short)(p.h & 0xffffu)), "f"(-1024.0f));
+    return f;
+#endif
+}
+__device__ __forceinline__ float pair_hi(BytePair p)
+{
+#if B200RT_DECODE_FADD
+    return __uint_as_float(0x4B000000u | ((p.h >> 16) & 0xffu)) - 8388608.0f;
+#else
+    float f;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(f) : "h"((unsigned short)(p.h >> 16)), "f"(-1024.0f));
+    return f;
+#endif
+}
+// single byte (compile-time j) through the same path; used by the one-ray-per-thread reference traversal below
+__device__ __forceinline__ float byte_f(uint32_t w, int j)
+{
+    const BytePair p = (j < 2) ? byte_pair01(w) : byte_pair23(w);
+    return (j & 1) ? pair_hi(p) : pair_lo(p);
+}
 
 // Trace one ray through one GAS.  `best.t` carries tmax in and the closest t out.
 template <bool ANY, bool STATS>

@@ -367,8 +367,9 @@ class PathTracer:
             gpu_idx, num_gpus = multigpu
             self.num_samples = wd_num_samples(width, height, num_gpus)
             self.sample_index = torch.zeros((self.num_samples, 2), dtype=torch.int32, device=dev)
-            ctx.check(ctx.lib.b200rt_fill_samples(ctx.h, ctx.stream, gpu_idx, num_gpus, width, height, self.sample_index.data_ptr(),
-                                                  self.num_samples), "fill_samples")
+            hc = getattr(ctx, "helper", ctx)  # fillSamplesCUDA is a plain CUDA kernel in the reference too (optixMultiGPU_kernels.cu)
+            hc.check(hc.lib.b200rt_fill_samples(hc.h, hc.stream, gpu_idx, num_gpus, width, height, self.sample_index.data_ptr(),
+                                                self.num_samples), "fill_samples")
             self.accum = torch.zeros((self.num_samples, 4), dtype=torch.float32, device=dev)
             self.params = MGParams(0, self.sample_index.data_ptr(), self.accum.data_ptr(), self.frame.data_ptr(), width, height,
                                    samples_per_launch, 3, _f3(cam["eye"]), _f3(U), _f3(V), _f3(W), light, self.accel.handle)
@@ -478,6 +479,10 @@ def load_gltf(path):
     return {"meshes": meshes, "instances": instances}
 
 
+# byte offsets inside whitted::HitGroupData (SDK/cuda/whitted.h:44-48, SDK/cuda/GeometryData.h:73-80,248-262)
+HG_OFF_INDICES, HG_OFF_POSITIONS, HG_OFF_NORMALS, HG_OFF_MATERIAL, HG_SIZE = 16, 32, 48, 112, 352
+
+
 class Raycaster:
     """Mirror of optixRaycasting's state (optixRaycasting.cpp:94-349) for a loaded glTF scene: one GAS per mesh
     (one build input per primitive group), an IAS over the mesh instances, whitted::HitGroupData SBT records."""
@@ -502,15 +507,20 @@ class Raycaster:
                     d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
                 inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, vertex_stride=12))
                 self.keep += [d_pos, d_nrm, d_idx]
-                # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, TriangleMesh @8}; BufferView = {ptr, count, u16 stride, u16 elmt}
+                # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, 16-byte aligned union @16 holding TriangleMesh{indices,
+                # positions, normals, texcoords[2], colors}}; BufferView = {ptr, count, u16 stride, u16 elmt}.  Offsets pinned against the
+                # reference headers: tests/golden/kat.json "hitgroup_layout" (tests/test_oracle_kat.py)
                 rec = bytearray(32 + 352)
                 rec[0:32] = ctx.sbt_header(self.programs, 2, 0)
                 def bview(t, elmt, stride):
                     return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride, elmt)
                 isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
-                rec[32 + 8:32 + 24] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
-                rec[32 + 24:32 + 40] = bview(d_pos, 12, 12)
-                rec[32 + 40:32 + 56] = bview(d_nrm, 12, 12)
+                o = 32 + HG_OFF_INDICES
+                rec[o:o + 16] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
+                o = 32 + HG_OFF_POSITIONS
+                rec[o:o + 16] = bview(d_pos, 12, 12)
+                o = 32 + HG_OFF_NORMALS
+                rec[o:o + 16] = bview(d_nrm, 12, 12)
                 records.append(bytes(rec))
             self.mesh_accels.append(ctx.build_accel(inputs, compact=compact))
         self.d_hitgroup = ctx.to_device(np.frombuffer(b"".join(records), np.uint8).copy())

@@ -62,3 +62,76 @@ void ref_light_normal(const float* v1, const float* v2, float* n)
 }
 
 }  // extern "C"
+
+// ---- struct layouts of the launch ABI, measured on the reference's own headers ------------------------------------
+// (SDK/cuda/whitted.h:44-48, SDK/cuda/GeometryData.h:73-80,248-262, SDK/cuda/BufferView.h:32-38, SDK/optixPathTracer/optixPathTracer.h,
+//  SDK/optixMultiGPU/optixMultiGPU.h, SDK/optixRaycasting/optixRaycasting.h + optixRaycastingKernels.h)
+#include <optix_types.h>
+#include <cuda/whitted.h>
+#include <cstring>
+namespace pt {
+#include <optixPathTracer/optixPathTracer.h>
+}
+namespace mg {
+#include <optixMultiGPU/optixMultiGPU.h>
+}
+namespace rc {
+#include <optixRaycasting/optixRaycastingKernels.h>
+#include <optixRaycasting/optixRaycasting.h>
+}
+
+extern "C" {
+
+// out[0..] = sizeof(whitted::HitGroupData), sizeof(GeometryData), sizeof(MaterialData), then the byte offsets inside HitGroupData of
+// TriangleMesh::indices / positions / normals / texcoords[0] / texcoords[1] / colors (found by writing sentinels through
+// GeometryData::setTriangleMesh and scanning), then sizeof(BufferView<float3>), offsetof data/count/byte_stride/elmt_byte_size,
+// then offset of material_data inside HitGroupData.
+int ref_hitgroup_layout(int* out)
+{
+    whitted::HitGroupData hg;  // default-constructed: geometry_data.type == UNKNOWN_TYPE, which setTriangleMesh asserts
+    GeometryData::TriangleMesh tm = {};
+    tm.indices.data = 0x1111111111111111ull;
+    tm.positions.data = 0x2222222222222222ull;
+    tm.normals.data = 0x3333333333333333ull;
+    tm.texcoords[0].data = 0x4444444444444444ull;
+    tm.texcoords[1].data = 0x5555555555555555ull;
+    tm.colors.data = 0x6666666666666666ull;
+    hg.geometry_data.setTriangleMesh(tm);
+    int n = 0;
+    out[n++] = (int)sizeof(whitted::HitGroupData);
+    out[n++] = (int)sizeof(GeometryData);
+    out[n++] = (int)sizeof(MaterialData);
+    const unsigned char* p = (const unsigned char*)&hg;
+    for (unsigned long long s = 1; s <= 6; ++s) {
+        const unsigned long long pat = s * 0x1111111111111111ull;
+        int found = -1;
+        for (size_t o = 0; o + 8 <= sizeof hg; ++o)
+            if (!memcmp(p + o, &pat, 8)) { found = (int)o; break; }
+        out[n++] = found;
+    }
+    out[n++] = (int)sizeof(BufferView<float3>);
+    out[n++] = (int)offsetof(BufferView<float3>, data);
+    out[n++] = (int)offsetof(BufferView<float3>, count);
+    out[n++] = (int)offsetof(BufferView<float3>, byte_stride);
+    out[n++] = (int)offsetof(BufferView<float3>, elmt_byte_size);
+    out[n++] = (int)offsetof(whitted::HitGroupData, material_data);
+    out[n++] = (int)hg.geometry_data.type;  // TRIANGLE_MESH
+    return n;
+}
+
+// sizes / offsets of the Params structs and SBT payloads the launches consume
+int ref_params_layout(int* out)
+{
+    int n = 0;
+    out[n++] = (int)sizeof(pt::Params); out[n++] = (int)offsetof(pt::Params, eye); out[n++] = (int)offsetof(pt::Params, light); out[n++] = (int)offsetof(pt::Params, handle);
+    out[n++] = (int)sizeof(pt::HitGroupData); out[n++] = (int)offsetof(pt::HitGroupData, diffuse_color); out[n++] = (int)offsetof(pt::HitGroupData, vertices);
+    out[n++] = (int)sizeof(pt::MissData);
+    out[n++] = (int)sizeof(mg::Params); out[n++] = (int)offsetof(mg::Params, eye); out[n++] = (int)offsetof(mg::Params, light); out[n++] = (int)offsetof(mg::Params, handle);
+    out[n++] = (int)offsetof(mg::Params, sample_index_buffer); out[n++] = (int)offsetof(mg::Params, device_idx);
+    out[n++] = (int)sizeof(rc::Params); out[n++] = (int)sizeof(rc::Ray); out[n++] = (int)sizeof(rc::Hit);
+    out[n++] = (int)sizeof(OptixBuildInput); out[n++] = (int)sizeof(OptixInstance); out[n++] = (int)sizeof(OptixShaderBindingTable);
+    out[n++] = (int)sizeof(OptixAccelBuildOptions); out[n++] = (int)sizeof(OptixBuildInputTriangleArray);
+    return n;
+}
+
+}  // extern "C"

@@ -98,3 +98,34 @@ def test_cornell_fixture_is_consistent():
     # the emissive triangles are the ceiling light at y = 548.6
     light = sc["vertices"].reshape(32, 3, 3)[sc["mat_indices"] == 3]
     assert np.all(light[:, :, 1] == np.float32(548.6))
+
+
+def test_launch_struct_layouts_match_the_reference_headers():
+    """Sizes / offsets measured on the reference's own headers (oracle/ref_shim.cpp -> tests/golden/kat.json) against the
+    ctypes mirrors the host uses and the offsets csrc/raycast.cu reads whitted::HitGroupData with."""
+    import ctypes as C
+    import json
+    import pathlib
+    import re
+    import struct as pystruct  # noqa: F401
+    torch = pytest.importorskip("torch")  # host.py owns device memory through torch
+    from optix_raytracer_b200 import host, _lib as L
+    kat = json.loads((pathlib.Path(__file__).parent / "golden" / "kat.json").read_text())
+    pl, hl = kat["params_layout"], kat["hitgroup_layout"]
+    assert C.sizeof(host.PTParams) == pl["pt_Params"] and host.PTParams.eye.offset == pl["pt_Params_eye"]
+    assert host.PTParams.light.offset == pl["pt_Params_light"] and host.PTParams.handle.offset == pl["pt_Params_handle"]
+    assert C.sizeof(host.MGParams) == pl["mg_Params"] and host.MGParams.eye.offset == pl["mg_Params_eye"]
+    assert host.MGParams.light.offset == pl["mg_Params_light"] and host.MGParams.handle.offset == pl["mg_Params_handle"]
+    assert host.MGParams.sample_index_buffer.offset == pl["mg_Params_sample_index_buffer"] and host.MGParams.device_idx.offset == pl["mg_Params_device_idx"]
+    assert C.sizeof(host.RaycastParams) == pl["rc_Params"] and pl["rc_Ray"] == 32 and pl["rc_Hit"] == 16
+    assert (pl["pt_HitGroupData"], pl["pt_HitGroupData_diffuse_color"], pl["pt_HitGroupData_vertices"], pl["pt_MissData"]) == (32, 12, 24, 16)
+    assert C.sizeof(L.BuildInput) == pl["OptixBuildInput"] and C.sizeof(L.Instance) == pl["OptixInstance"]
+    assert C.sizeof(L.ShaderBindingTable) == pl["OptixShaderBindingTable"] and C.sizeof(L.AccelBuildOptions) == pl["OptixAccelBuildOptions"]
+    assert C.sizeof(L.TriangleArray) == pl["OptixBuildInputTriangleArray"]
+    # whitted::HitGroupData: the union of GeometryData is 16-byte aligned, so TriangleMesh starts at 16 (not 8)
+    assert (host.HG_OFF_INDICES, host.HG_OFF_POSITIONS, host.HG_OFF_NORMALS, host.HG_OFF_MATERIAL, host.HG_SIZE) == \
+        (hl["off_indices"], hl["off_positions"], hl["off_normals"], hl["off_material_data"], hl["sizeof_HitGroupData"])
+    assert (hl["sizeof_BufferView"], hl["bv_off_data"], hl["bv_off_count"], hl["bv_off_byte_stride"], hl["bv_off_elmt_byte_size"]) == (16, 0, 8, 12, 14)
+    src = (pathlib.Path(__file__).resolve().parents[1] / "optix_raytracer_b200" / "csrc" / "raycast.cu").read_text()
+    m = re.search(r"vi = \*\(const BufView\*\)\(rec \+ (\d+)\), vp = \*\(const BufView\*\)\(rec \+ (\d+)\), vn = \*\(const BufView\*\)\(rec \+ (\d+)\)", src)
+    assert m and tuple(int(x) for x in m.groups()) == (hl["off_indices"], hl["off_positions"], hl["off_normals"])

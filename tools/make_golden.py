@@ -70,6 +70,21 @@ def main():
     f3 = ctypes.c_float * 3
     ref.ref_light_normal(f3(0.0, 0.0, 105.0), f3(-130.0, 0.0, 0.0), n)
     out["cornell_light_normal_bits"] = [fbits(x) for x in n]
+    # --- struct layouts of the launch ABI measured on the reference headers (oracle/ref_shim.cpp)
+    o = (ctypes.c_int * 32)()
+    k = ref.ref_hitgroup_layout(o)
+    names = ["sizeof_HitGroupData", "sizeof_GeometryData", "sizeof_MaterialData", "off_indices", "off_positions", "off_normals", "off_texcoords0",
+             "off_texcoords1", "off_colors", "sizeof_BufferView", "bv_off_data", "bv_off_count", "bv_off_byte_stride", "bv_off_elmt_byte_size",
+             "off_material_data", "TRIANGLE_MESH"]
+    assert k == len(names)
+    out["hitgroup_layout"] = dict(zip(names, list(o[:k])))
+    k = ref.ref_params_layout(o)
+    names = ["pt_Params", "pt_Params_eye", "pt_Params_light", "pt_Params_handle", "pt_HitGroupData", "pt_HitGroupData_diffuse_color",
+             "pt_HitGroupData_vertices", "pt_MissData", "mg_Params", "mg_Params_eye", "mg_Params_light", "mg_Params_handle",
+             "mg_Params_sample_index_buffer", "mg_Params_device_idx", "rc_Params", "rc_Ray", "rc_Hit", "OptixBuildInput", "OptixInstance",
+             "OptixShaderBindingTable", "OptixAccelBuildOptions", "OptixBuildInputTriangleArray"]
+    assert k == len(names)
+    out["params_layout"] = dict(zip(names, list(o[:k])))
     p = ROOT / "tests" / "golden" / "kat.json"
     p.write_text(json.dumps(out) + "\n")
     print("wrote", p, p.stat().st_size, "bytes")

@@ -104,6 +104,11 @@ def main():
     occ_o = octx.trace_any(opt.accel, d2).cpu().numpy().astype(bool)
     rep["occlusion_cornell"] = {"rays": n, "disagree": int((occ_b != occ_o).sum()), "occluded_b200rt": int(occ_b.sum())}
 
+    def checkpoint():
+        pathlib.Path(a.out).parent.mkdir(parents=True, exist_ok=True)
+        pathlib.Path(a.out).write_text(json.dumps(rep, indent=1))
+    checkpoint()
+
     # ---- 2. Duck: optixRaycasting (the reference's own programs) ------------------------------------------
     sc = common.duck_scene()
     brc, orc_ = host.Raycaster(bctx, sc), host.Raycaster(octx, sc)
@@ -130,6 +135,8 @@ def main():
     tb = cuda_ms(lambda: brc.launch(want_ext=False))
     to = cuda_ms(lambda: orc_.launch(want_ext=False))
     rep["raycast_duck"]["ms_two_batches"] = {"b200rt": tb, "optix": to, "Mrays_s_b200rt": 2 * nray / tb / 1e3, "Mrays_s_optix": 2 * nray / to / 1e3}
+
+    checkpoint()
 
     # ---- 3. Cornell image: optixPathTracer, accumulated over subframes --------------------------------------
     segs = 0
@@ -170,6 +177,8 @@ def main():
     s3 = st.radiance_segments + st.shadow_segments
     rep["timing_cornell_768x768x16"] = {"segments": int(s3), "ms_b200rt": tb, "ms_optix": to, "Mrays_s_b200rt": s3 / tb / 1e3, "Mrays_s_optix": s3 / to / 1e3,
                                         "speedup": to / tb}
+
+    checkpoint()
 
     # ---- 4. synthetic mesh (BASELINE.json configs[4]): build + launch timing, optixMultiGPU programs ---------
     if not a.skip_synth:
