@@ -255,6 +255,24 @@ int b200rt_deinterleave(b200rt_context ctx, b200rt_stream stream, b200rt_devicep
                         int num_samples, int width, int height, b200rt_deviceptr accum_float4,
                         b200rt_deviceptr frame_uchar4);
 
+/* imgui_test ("playground") launch: optixLaunch(pipeline, stream, d_param, sizeof(Params)=128, &sbt, buf_width, buf_height, 1)
+ * (reference SDK/imgui_test/tracer_window.cpp:96-105) + the programs of SDK/imgui_test/optixTriangle.cu:103-268.
+ * d_params: device copy of the sample's Params (SDK/imgui_test/optixTriangle.h:42-108) — its camera / lights / materials / normals /
+ * mat_indices / film / image pointers are device pointers to the sample's own objects (Camera 92 B, LightVariant 44 B,
+ * DiffuseMaterial 12 B).  No SBT is needed: the sample's single hit group reads everything from Params.  Params::dt must already
+ * hold the frame's value (frame_step()).  Reads the 128-byte Params back once (synchronises `stream`), then runs asynchronously.
+ * options->stats (optional): radiance_segments = primary rays, iterations = samples, kernel_launches. */
+int b200rt_launch_playground(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params, unsigned int width,
+                             unsigned int height, const b200rt_pt_options* options);
+
+/* Procedural stand-in for the model behind the reference's cover.png (not in the reference repo): 5 x 5
+ * displaced lat-long blobs of 4*rows^2 triangles each over the sample's own 800-triangle floor (triangle_gas.cpp:147-166), as the
+ * unindexed float3 vertex / per-vertex normal arrays and int material indices TriangleGAS keeps.  vertices_float3 == 0: only
+ * *num_triangles is written (size query). */
+int b200rt_generate_playground_scene(b200rt_context ctx, b200rt_stream stream, uint32_t rows, uint32_t seed,
+                                     b200rt_deviceptr vertices_float3, b200rt_deviceptr normals_float3,
+                                     b200rt_deviceptr mat_indices_i32, uint64_t* num_triangles);
+
 /* ---------------------------------------------------------------------------------------------
  * optixRaycasting.  b200rt_launch_raycast replaces
  *   optixLaunch(pipeline, stream, d_params, sizeof(Params)=24, &sbt, width, height, 1)
@@ -295,6 +313,10 @@ int b200rt_trace_stats(b200rt_context ctx, b200rt_stream stream, b200rt_traversa
 /* sutil::Camera::UVWFrame (reference SDK/sutil/Camera.cpp:34-46) */
 void b200rt_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fov_y_deg,
                        float aspect, float U[3], float V[3], float W[3]);
+/* imgui_test Camera (reference SDK/imgui_test/camera.h:19-117) set up as main.cpp:236-243 does — setters then compute_uvw();
+ * writes the 92-byte object Params::camera points to. */
+void b200rt_playground_camera(const float eye[3], const float up[3], const float lookat[3], float aperture, float fd,
+                              float fov_deg, int ortho, void* camera92);
 /* StaticWorkDistribution (reference SDK/sutil/WorkDistribution.h:50-81) */
 int b200rt_wd_num_samples(int width, int height, int num_gpus);
 void b200rt_wd_sample_pixel(int width, int height, int num_gpus, int gpu_idx, int sample_idx, int xy[2]);

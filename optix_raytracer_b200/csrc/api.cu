@@ -270,6 +270,21 @@ int b200rt_generate_synthetic_mesh(b200rt_context ctx, b200rt_stream stream, uin
     return generate_synthetic_mesh(ctx, (cudaStream_t)stream, num_triangles, seed, vertices_float4, mat_indices_u32, bounds_out);
 }
 
+int b200rt_launch_playground(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params, unsigned int width, unsigned int height,
+                             const b200rt_pt_options* options)
+{
+    CTX_CHECK(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return launch_playground(ctx, (cudaStream_t)stream, d_params, width, height, options);
+}
+
+int b200rt_generate_playground_scene(b200rt_context ctx, b200rt_stream stream, uint32_t rows, uint32_t seed, b200rt_deviceptr vertices_float3,
+                                     b200rt_deviceptr normals_float3, b200rt_deviceptr mat_indices_i32, uint64_t* num_triangles)
+{
+    CTX_CHECK(ctx);
+    return generate_playground_scene(ctx, (cudaStream_t)stream, rows, seed, vertices_float3, normals_float3, mat_indices_i32, num_triangles);
+}
+
 // ---- host-side sutil mirrors -------------------------------------------------------------------
 // sutil::Camera::UVWFrame (reference SDK/sutil/Camera.cpp:34-46), host arithmetic without contraction
 void b200rt_camera_uvw(const float eye[3], const float lookat[3], const float up[3], float fov_y_deg, float aspect, float U[3], float V[3],
@@ -291,6 +306,36 @@ void b200rt_camera_uvw(const float eye[3], const float lookat[3], const float up
     U[0] = u.x; U[1] = u.y; U[2] = u.z;
     V[0] = v.x; V[1] = v.y; V[2] = v.z;
     W[0] = w.x; W[1] = w.y; W[2] = w.z;
+}
+
+// imgui_test Camera as main.cpp:236-243 sets it up: set_eye / set_up / set_lookat / set_aperture / set_fd (relative to |lookat - eye|) /
+// set_fov / set_ortho, then compute_uvw (reference SDK/imgui_test/camera.h:19-117).  Writes the 92-byte object the device programs read.
+void b200rt_playground_camera(const float eye[3], const float up[3], const float lookat[3], float aperture, float fd, float fov_deg, int ortho,
+                              void* camera92)
+{
+    struct v3 { float x, y, z; };
+    auto dot = [](v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+    auto cross = [](v3 a, v3 b) { return v3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    auto scale = [](v3 a, float s) { return v3{a.x * s, a.y * s, a.z * s}; };
+    auto norm = [&](v3 a) { return scale(a, 1.0f / sqrtf(dot(a, a))); };
+    const v3 e{eye[0], eye[1], eye[2]}, l{lookat[0], lookat[1], lookat[2]}, upv{up[0], up[1], up[2]};
+    const v3 le{l.x - e.x, l.y - e.y, l.z - e.z};
+    const float m_fd = fd / sqrtf(dot(le, le));
+    v3 w = scale(le, m_fd);
+    const float wlen = sqrtf(dot(w, w));
+    v3 u = norm(cross(w, upv));
+    v3 v = norm(cross(u, w));
+    const float vlen = wlen * tanf(0.5f * fov_deg * 3.14159265358979323846f / 180.0f);
+    v = scale(v, vlen);
+    u = scale(u, vlen);
+    struct Cam { float eye[3], lookat[3], up[3]; unsigned char ortho, pad[3]; float fov, fd, aperture, speed; float u[3], v[3], w[3]; } c;
+    static_assert(sizeof(Cam) == 92, "imgui_test Camera");
+    memset(&c, 0, sizeof c);
+    c.eye[0] = e.x; c.eye[1] = e.y; c.eye[2] = e.z; c.lookat[0] = l.x; c.lookat[1] = l.y; c.lookat[2] = l.z;
+    c.up[0] = upv.x; c.up[1] = upv.y; c.up[2] = upv.z;
+    c.ortho = ortho ? 1 : 0; c.fov = fov_deg; c.fd = m_fd; c.aperture = aperture; c.speed = 0.01f;
+    c.u[0] = u.x; c.u[1] = u.y; c.u[2] = u.z; c.v[0] = v.x; c.v[1] = v.y; c.v[2] = v.z; c.w[0] = w.x; c.w[1] = w.y; c.w[2] = w.z;
+    memcpy(camera92, &c, sizeof c);
 }
 
 // StaticWorkDistribution (reference SDK/sutil/WorkDistribution.h:50-81): 8x4 tiles, strips of 8*N columns

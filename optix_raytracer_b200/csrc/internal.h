@@ -19,6 +19,11 @@ int shade_hits(b200rt_context, cudaStream_t, b200rt_deviceptr, int, b200rt_devic
 int trace_closest(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, unsigned, b200rt_deviceptr);
 int trace_any(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, unsigned, b200rt_deviceptr);
 int trace_stats(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, uint64_t*, uint64_t*);
+int trace_buffer(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev, unsigned n_mult,
+                 int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period = 0);
+// playground.cu
+int launch_playground(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, unsigned, unsigned, const b200rt_pt_options*);
+int generate_playground_scene(b200rt_context, cudaStream_t, uint32_t rows, uint32_t seed, b200rt_deviceptr, b200rt_deviceptr, b200rt_deviceptr, uint64_t*);
 // pathtracer.cu
 int launch_pathtracer(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, const b200rt_shader_binding_table*, unsigned, unsigned,
                       const b200rt_pt_options*, int multigpu);

@@ -74,14 +74,20 @@ struct RayWork {
     float4* hits;
     const char* hg_base;
     uint32_t hg_stride, hg_count;
+    uint32_t flag_period;  // > 0: every flag_period-th ray (the last of each group) ignores the CULL_*_ANYHIT ray flags (playground.cu)
     uint64_t item;
 
+    __device__ __forceinline__ uint32_t cull_flags(uint32_t i) const
+    {
+        const uint32_t f = ray_flags & 0xf0u;
+        return (flag_period && (i % flag_period) == flag_period - 1u) ? (f & 0x30u) : f;
+    }
     __device__ __forceinline__ bool fetch(uint32_t i, Trav& s, float* my_ray)
     {
         item = i;
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
-        if (!trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, ray_flags & 0x30u, 0u)) {
+        if (!trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
             commit(s, false);
             return false;
         }
@@ -91,8 +97,8 @@ struct RayWork {
     {
         if (handle->kind == ACCEL_KIND_GAS) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
-        return trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY), ray_flags & 0x30u,
-                                 s.inst + 1u);
+        return trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
+                                 cull_flags((uint32_t)item), s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
     {
@@ -155,9 +161,12 @@ __global__ void __launch_bounds__(COOP_BLOCK, 8) trace_rays_kernel(const AccelHe
                                                           uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
                                                           const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
                                                           uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,
-                                                          unsigned long long* __restrict__ stats)
+                                                          unsigned long long* __restrict__ stats, const unsigned int* __restrict__ n_dev,
+                                                          uint32_t n_mult, uint32_t flag_period)
 {
+    if (n_dev) n = min(n, *n_dev * n_mult);  // ray count produced on the device by an earlier stage (playground.cu)
     RayWork<KIND> w;
+    w.flag_period = flag_period;
     w.handle = handle; w.rays = rays; w.hits = nullptr;
     if (KIND == 2) { const RaycastParamsDev P = *rc_params; w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits; }
     w.ray_flags = ray_flags; w.ext = ext; w.occluded = occluded;
@@ -247,7 +256,7 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
     if (rc) return rc;
     trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
                                                                                        ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0,
-                                                                                       counter, nullptr);
+                                                                                       counter, nullptr, nullptr, 1u, 0u);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -264,7 +273,7 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
     if (rc) return rc;
     trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
                                                                                        ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0,
-                                                                                       counter, nullptr);
+                                                                                       counter, nullptr, nullptr, 1u, 0u);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -283,7 +292,7 @@ int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b
     B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
     if (n) {
         trace_rays_kernel<0, true><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
-                                                                                         0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats);
+                                                                                         0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u);
         ctx->launches++;
     }
     unsigned long long h[2] = {0, 0};
@@ -300,7 +309,7 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                    unsigned height, b200rt_deviceptr ext)
 {
     B2_REQUIRE(ctx, d_params && sbt, "null argument");
-    B2_REQUIRE(ctx, sbt->hitgroupRecordBase && sbt->hitgroupRecordCount > 0 && sbt->hitgroupRecordStrideInBytes >= 32 + 56,
+    B2_REQUIRE(ctx, sbt->hitgroupRecordBase && sbt->hitgroupRecordCount > 0 && sbt->hitgroupRecordStrideInBytes >= 32 + 64,
                "hit-group records (whitted::HitGroupData) are required");
     DeviceGuard guard(ctx->device);
     const uint64_t n = (uint64_t)width * height;
@@ -314,7 +323,29 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                                                                                        (const RaycastParamsDev*)d_params,
                                                                                        (const char*)sbt->hitgroupRecordBase,
                                                                                        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount,
-                                                                                       counter, nullptr);
+                                                                                       counter, nullptr, nullptr, 1u, 0u);
+    B2_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Internal ray-buffer query used by the multi-stage launches (playground.cu): kind 0 = closest hit -> ExtHit records, 1 = any hit ->
+// u32 flags.  The ray count may live on the device (n_dev * n_mult, capped by n_max).  Caller holds ctx->mu.
+int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev,
+                 unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period)
+{
+    B2_REQUIRE(ctx, handle && rays && out && n_max < (1ull << 32), "bad argument");
+    if (n_max == 0) return 0;
+    unsigned int* counter = nullptr;
+    int rc = next_counter(ctx, s, &counter);
+    if (rc) return rc;
+    if (kind == 0)
+        trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, nullptr, nullptr, nullptr, 0, 0, counter, nullptr,
+            n_dev, n_mult, flag_period);
+    else
+        trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, nullptr, 0, 0, counter, nullptr,
+            n_dev, n_mult, flag_period);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -30,8 +30,14 @@ namespace b200rt {
 #define B200RT_LOOKTHROUGH 0
 #endif
 constexpr uint32_t NODE_BITS = 0xff000000u;
-constexpr int REFILL_THRESHOLD = 24;   // refill when fewer lanes than this hold a ray
-constexpr int TRI_TRIGGER = 24;        // run a triangle round once this many (ray, triangle) units are parked
+#ifndef B200RT_REFILL_THRESHOLD
+#define B200RT_REFILL_THRESHOLD 24
+#endif
+#ifndef B200RT_TRI_TRIGGER
+#define B200RT_TRI_TRIGGER 24
+#endif
+constexpr int REFILL_THRESHOLD = B200RT_REFILL_THRESHOLD;   // refill when fewer lanes than this hold a ray
+constexpr int TRI_TRIGGER = B200RT_TRI_TRIGGER;             // run a triangle round once this many (ray, triangle) units are parked
 constexpr int COOP_BLOCK = 128;        // CTA size of every kernel built on trace_persistent
 constexpr int COOP_WARPS = COOP_BLOCK / 32;
 constexpr int RAY_S_STRIDE = 9;        // odd stride: lanes reading different owners hit different banks

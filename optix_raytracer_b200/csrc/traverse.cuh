@@ -97,6 +97,9 @@ __device__ __forceinline__ bool tri_test(const TriRay& r, const float4 q0, const
             if ((cull & 16u) && det < 0.0f) return false;
             if ((cull & 32u) && det > 0.0f) return false;
         }
+        // OPTIX_RAY_FLAG_CULL_DISABLED_ANYHIT (1<<6) / CULL_ENFORCED_ANYHIT (1<<7) against OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT (1<<0)
+        if ((cull & 64u) && (gflags & 1u)) return false;
+        if ((cull & 128u) && !(gflags & 1u)) return false;
     }
     const uint32_t ord = __float_as_uint(q2.w);
     if (t == best.t && !(found && ord < best.ord)) return false;
@@ -270,7 +273,7 @@ __device__ __forceinline__ bool trace_handle(const AccelHeader* __restrict__ h, 
 {
     hit.t = tmax;
     hit.inst = 0;
-    const uint32_t cull = ray_flags & 0x30u;
+    const uint32_t cull = ray_flags & 0xf0u;
     if (h->kind == ACCEL_KIND_GAS) {
         // initial acceptance must be strict (t < tmax): run with found=false semantics
         return trace_gas<ANY, STATS>(h, o, d, tmin, hit, cull, st);

@@ -144,6 +144,9 @@ class Context:
     def launch_multigpu(self, programs, d_params, params_size, sbt, num_samples, opts):
         self.check(self.lib.b200rt_launch_multigpu(self.h, self.stream, d_params, C.byref(sbt), num_samples, C.byref(opts)), "launch_multigpu")
 
+    def launch_playground(self, programs, d_params, params_size, sbt, width, height, opts):
+        self.check(self.lib.b200rt_launch_playground(self.h, self.stream, d_params, width, height, C.byref(opts)), "launch_playground")
+
     def launch_raycast(self, programs, d_params, sbt, width, height, ext):
         self.check(self.lib.b200rt_launch_raycast(self.h, self.stream, d_params, C.byref(sbt), width, height, ext), "launch_raycast")
 
@@ -592,3 +595,120 @@ def synthetic_mesh(ctx, num_triangles, seed=0):
     b = (C.c_float * 6)()
     ctx.check(ctx.lib.b200rt_generate_synthetic_mesh(ctx.h, ctx.stream, num_triangles, seed, verts.data_ptr(), mats.data_ptr(), b), "synthetic_mesh")
     return verts, mats
+
+
+# ---- imgui_test ("playground"): SDK/imgui_test/main.cpp:236-279, tracer_window.cpp:64-128 -----------------------------------------
+class PGParams(C.Structure):  # SDK/imgui_test/optixTriangle.h:42-108 (128 bytes; offsets pinned in tests/golden/kat.json "playground_layout")
+    _fields_ = [("image_width", C.c_uint32), ("image_height", C.c_uint32), ("samples_per_frame", C.c_uint32), ("camera", C.c_uint64),
+                ("dt", C.c_uint32), ("dirty", C.c_uint8), ("image", C.c_uint64), ("film", C.c_uint64), ("tfactor", C.c_float), ("handle", C.c_uint64),
+                ("normals", C.c_uint64), ("vertices", C.c_uint64), ("mat_indices", C.c_uint64), ("nmat_indices", C.c_int32), ("lights", C.c_uint64),
+                ("nlights", C.c_int32), ("materials", C.c_uint64), ("nmaterials", C.c_int32)]
+
+
+assert C.sizeof(PGParams) == 128 and PGParams.lights.offset == 96 and PGParams.dirty.offset == 28
+
+
+def playground_light(kind, a, lumi, scalar=0.0):
+    """44 raw bytes of LightVariant (light.h:42-50): kind 0 PointLight(position, lumi), 1 DirectionalLight(direction, lumi, jitter),
+    2 VolumetricLight(position, radius, lumi); each light ends with float3 m_dark = 0."""
+    a, lumi = [float(x) for x in a], [float(x) for x in lumi]
+    if kind == 0:
+        return struct.pack("<10fi", *a, *lumi, 0.0, 0.0, 0.0, 0.0, 0)
+    if kind == 1:
+        return struct.pack("<10fi", *a, *lumi, float(scalar), 0.0, 0.0, 0.0, 1)
+    return struct.pack("<10fi", *a, float(scalar), *lumi, 0.0, 0.0, 0.0, 2)
+
+
+def playground_default_lights():
+    """main.cpp:245-249"""
+    return (playground_light(2, (0.0, 2.0, 0.0), (0.1, 0.08, 0.08), 0.1) + playground_light(2, (2.0, 2.0, 0.0), (0.1, 0.08, 0.08), 0.1)
+            + playground_light(2, (2.0, 2.0, 2.0), (0.1, 0.08, 0.08), 0.1) + playground_light(1, (-1.0, 1.0, -1.0), (0.1, 0.1, 0.1), 0.05))
+
+
+def playground_default_materials():
+    """main.cpp:251-261: 28 DiffuseMaterial colours"""
+    m = [(0.5, 0.5, 0.5)]
+    for i in range(5):
+        for j in range(5):
+            m.append((np.float32(i) / np.float32(5.0), np.float32(j) / np.float32(5.0), 0.2))
+    m += [(0.5, 0.5, 0.5), (0.5, 0.5, 0.5)]
+    return np.array(m, np.float32)
+
+
+def playground_camera(eye=(0.0, 1.0, -10.0), up=(0.0, 0.0000073, 1.0), lookat=(0.0, 0.1, 0.0), aperture=0.0, fd=1.0, fov=45.0, ortho=False):
+    """92 raw bytes of the Camera main.cpp:236-243 sets up (defaults = the reference's values)."""
+    buf = (C.c_uint8 * 92)()
+    L.load().b200rt_playground_camera(_f3(eye), _f3(up), _f3(lookat), aperture, fd, fov, int(bool(ortho)), buf)
+    return bytes(buf)
+
+
+class Playground:
+    """Mirror of imgui_test's state (main.cpp:64-279, triangle_gas.cpp:170-241) and of TracerWindow::run's per-frame work
+    (tracer_window.cpp:88-105) without the window.  Geometry: the procedural stand-in (rows -> 25 blobs of 4*rows^2 triangles + floor),
+    or caller-supplied (T*3,3) vertices / normals and (T,) int32 material indices (device tensors)."""
+
+    def __init__(self, ctx, width, height, spf=5, rows=132, seed=0, camera=None, lights=None, materials=None, vertices=None, normals=None,
+                 mat_indices=None):
+        self.ctx = ctx
+        hc = getattr(ctx, "helper", ctx)
+        dev = ctx.torch_device
+        self.width, self.height, self.spf = width, height, spf
+        if vertices is None:
+            n = C.c_uint64()
+            hc.check(hc.lib.b200rt_generate_playground_scene(hc.h, hc.stream, rows, seed, 0, 0, 0, C.byref(n)), "playground_scene(size)")
+            T = int(n.value)
+            vertices = torch.empty((T * 3, 3), dtype=torch.float32, device=dev)
+            normals = torch.empty((T * 3, 3), dtype=torch.float32, device=dev)
+            mat_indices = torch.empty(T, dtype=torch.int32, device=dev)
+            hc.check(hc.lib.b200rt_generate_playground_scene(hc.h, hc.stream, rows, seed, vertices.data_ptr(), normals.data_ptr(),
+                                                             mat_indices.data_ptr(), C.byref(n)), "playground_scene")
+        self.vertices, self.normals, self.mat_indices = vertices, normals, mat_indices
+        self.num_triangles = mat_indices.numel()
+        # TriangleGAS (triangle_gas.cpp:176-234): unindexed float3 vertices, OPTIX_GEOMETRY_FLAG_NONE, BUILD_FLAG_NONE, no compaction
+        bi = ctx.triangle_input(vertices, num_sbt=1, flags=[0], vertex_stride=12)
+        self.accel = ctx.build_accel([bi], compact=False)
+        self.programs = ctx.prepare_programs("playground")
+        self.camera_bytes = camera or playground_camera()
+        self.lights_bytes = lights if lights is not None else playground_default_lights()
+        self.materials = materials if materials is not None else playground_default_materials()
+        self.d_camera = ctx.to_device(np.frombuffer(self.camera_bytes, np.uint8).copy())
+        self.d_lights = ctx.to_device(np.frombuffer(self.lights_bytes, np.uint8).copy())
+        self.d_materials = ctx.to_device(self.materials)
+        self.film = torch.zeros((height, width, 3), dtype=torch.float32, device=dev)
+        self.image = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
+        # SBT (main.cpp:190-227): raygen, miss {bg .3,.1,.2 — never read by __miss__ms}, one empty hit-group record
+        rec = np.zeros((3, 48), np.uint8)
+        for k in range(3):
+            rec[k, 0:32] = np.frombuffer(ctx.sbt_header(self.programs, k, 0), np.uint8)
+        rec[1, 32:44] = np.frombuffer(struct.pack("<3f", 0.3, 0.1, 0.2), np.uint8)
+        self.d_sbt = ctx.to_device(rec)
+        self.sbt = L.ShaderBindingTable()
+        self.sbt.raygenRecord = self.d_sbt.data_ptr()
+        self.sbt.missRecordBase = self.d_sbt.data_ptr() + 48
+        self.sbt.missRecordStrideInBytes, self.sbt.missRecordCount = 48, 1
+        self.sbt.hitgroupRecordBase = self.d_sbt.data_ptr() + 96
+        self.sbt.hitgroupRecordStrideInBytes, self.sbt.hitgroupRecordCount = 48, 1
+        self.params = PGParams()
+        p = self.params
+        p.image_width, p.image_height, p.samples_per_frame = width, height, spf
+        p.camera, p.dt, p.dirty = self.d_camera.data_ptr(), 0, 1
+        p.image, p.film, p.tfactor, p.handle = self.image.data_ptr(), self.film.data_ptr(), 0.5, self.accel.handle
+        p.normals, p.vertices, p.mat_indices, p.nmat_indices = normals.data_ptr(), vertices.data_ptr(), mat_indices.data_ptr(), self.num_triangles
+        p.lights, p.nlights = self.d_lights.data_ptr(), len(self.lights_bytes) // 44
+        p.materials, p.nmaterials = self.d_materials.data_ptr(), self.materials.shape[0]
+        self.h_params = torch.empty(128, dtype=torch.uint8).pin_memory()
+        self.d_params = torch.empty(128, dtype=torch.uint8, device=dev)
+        self.stats = L.PTStats()
+
+    def launch_frame(self, dirty=False, collect_stats=False):
+        """One iteration of TracerWindow::run's loop (tracer_window.cpp:88-105): dirty resets dt, frame_step(), Params upload, launch."""
+        p = self.params
+        p.dirty = 1 if dirty else 0
+        if dirty:
+            p.dt = 0
+        p.dt += p.samples_per_frame
+        self.h_params.numpy()[:] = np.frombuffer(bytes(p), np.uint8)
+        self.d_params.copy_(self.h_params, non_blocking=True)
+        opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))
+        self.ctx.launch_playground(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height, opts)
+        return self.stats if collect_stats else None

@@ -40,6 +40,8 @@ PROGRAMS = {
                  GRAPH_SINGLE_GAS, 2, 1),                                        # optixMultiGPU.cpp:786-950
     "raycast": ("optixRaycasting.ptx", "__raygen__from_buffer", "__miss__buffer_miss", "__closesthit__buffer_hit", "__anyhit__texture_mask", 4,
                 None, GRAPH_SINGLE_LEVEL_INSTANCING, 1, 2),                      # optixRaycasting.cpp:94-196
+    "playground": ("optixTriangle.ptx", "__raygen__rg", "__miss__ms", "__closesthit__ch", "-", 3, None, GRAPH_SINGLE_GAS, 2, 1),  # imgui_test/main.cpp:71-188
+    # (the sample links with maxTraceDepth 1 although its closest-hit program traverses again; 2 here only enlarges the stack)
     "query_gas": ("query_programs.ptx", "__raygen__query", "__miss__query", "__closesthit__query", "-", 5, None, GRAPH_SINGLE_GAS, 1, 1),
     "query_ias": ("query_programs.ptx", "__raygen__query", "__miss__query", "__closesthit__query", "-", 5, None, GRAPH_SINGLE_LEVEL_INSTANCING, 1, 2),
 }
@@ -146,6 +148,9 @@ class OptixContext(host.Context):
 
     def launch_multigpu(self, programs, d_params, params_size, sbt, num_samples, opts):
         self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, params_size, C.byref(sbt), num_samples, 1, 1), "optixLaunch")
+
+    def launch_playground(self, programs, d_params, params_size, sbt, width, height, opts):
+        self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, params_size, C.byref(sbt), width, height, 1), "optixLaunch")
 
     def launch_raycast(self, programs, d_params, sbt, width, height, ext):
         self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, 24, C.byref(sbt), width, height, 1), "optixLaunch")

@@ -191,6 +191,7 @@ struct BNode { f3 lo, hi; int left, right, first, count; };
 struct Geometry {
     std::vector<Tri> tris;            // object space, ordinal = index
     std::vector<uint32_t> sbt;        // per-triangle SBT offset (material), may be empty
+    uint32_t gflags = 1u;             // OptixGeometryFlags of the build input (default DISABLE_ANYHIT, as the samples set it)
     std::vector<BNode> nodes;
     std::vector<uint32_t> order;      // leaf triangle ordinals
     bool brute = true;
@@ -316,8 +317,13 @@ static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32
             if (cull_flags) {
                 // OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1<<4): det<0 is back facing for
                 // counter-clockwise front faces seen along the ray in this formulation.
-                if ((cull_flags & 16u) && det < 0.0f) return;
-                if ((cull_flags & 32u) && det > 0.0f) return;
+                if (!(g.gflags & 4u)) {  // OPTIX_GEOMETRY_FLAG_DISABLE_TRIANGLE_FACE_CULLING
+                    if ((cull_flags & 16u) && det < 0.0f) return;
+                    if ((cull_flags & 32u) && det > 0.0f) return;
+                }
+                // OPTIX_RAY_FLAG_CULL_DISABLED_ANYHIT (1<<6) / CULL_ENFORCED_ANYHIT (1<<7) vs OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT (1<<0)
+                if ((cull_flags & 64u) && (g.gflags & 1u)) return;
+                if ((cull_flags & 128u) && !(g.gflags & 1u)) return;
             }
             if (t < best.t || (t == best.t && found && p < best.prim)) {
                 best = {t, p, b1, b2, det};
@@ -650,6 +656,7 @@ void orc_scene_set_brute(void* scene, int brute)
     for (auto& g : s->geoms) g.brute = brute != 0 || g.nodes.empty();
 }
 void orc_scene_destroy(void* scene) { delete (Scene*)scene; }
+void orc_scene_set_geometry_flags(void* scene, uint32_t gflags) { for (auto& g : ((Scene*)scene)->geoms) g.gflags = gflags; }
 void orc_invert34(const float* m, float* inv) { invert34(m, inv); }
 
 // rays: n * 8 floats {ox,oy,oz,tmin,dx,dy,dz,tmax} (the reference Ray struct,
@@ -669,12 +676,12 @@ void orc_trace(void* scene, const float* rays, int64_t n, uint32_t* out, int any
             uint32_t* o = out + 5 * i;
             f3 org = mk(r[0], r[1], r[2]), dir = mk(r[4], r[5], r[6]);
             if (any_hit) {
-                SceneHit h = stats ? trace_scene<true, true>(*s, org, dir, r[3], r[7], ray_flags & 0x30u)
-                                   : trace_scene<true, false>(*s, org, dir, r[3], r[7], ray_flags & 0x30u);
+                SceneHit h = stats ? trace_scene<true, true>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u)
+                                   : trace_scene<true, false>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u);
                 o[0] = h.hit ? 1u : 0u; o[1] = o[2] = o[3] = o[4] = 0;
             } else {
-                SceneHit h = stats ? trace_scene<false, true>(*s, org, dir, r[3], r[7], ray_flags & 0x30u)
-                                   : trace_scene<false, false>(*s, org, dir, r[3], r[7], ray_flags & 0x30u);
+                SceneHit h = stats ? trace_scene<false, true>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u)
+                                   : trace_scene<false, false>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u);
                 float t = h.hit ? h.t : -1.0f;
                 memcpy(o, &t, 4);
                 o[1] = h.prim; o[2] = h.inst;
@@ -910,3 +917,203 @@ extern "C" void orc_synth_mesh(uint64_t total, uint32_t seed, float* verts /* to
         }
     });
 }
+
+// ------------------------------------------------------------------------------------------
+// imgui_test ("playground") — SDK/imgui_test/optixTriangle.cu:103-268, camera.h:127-144, light.h:19-40,
+// volumetric_light.h:22-27, directional_light.h:19-24, point_light.h, diffuse.h:8-12.  Scalar restatement in
+// the arithmetic contract (same op order as optix_raytracer_b200/csrc/playground.cu).
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PGCam { float eye[3], lookat[3], up[3]; uint8_t ortho; uint8_t pad[3]; float fov, fd, aperture, speed; float u[3], v[3], w[3]; };
+static_assert(sizeof(PGCam) == 92, "imgui_test Camera");
+struct PGLightO { float a[3], b[3], c[4]; int32_t tag; };
+static_assert(sizeof(PGLightO) == 44, "imgui_test LightVariant");
+
+static inline f3 pg_wi(const PGLightO& l, f3 p, uint32_t& seed)
+{
+    if (l.tag == 0) return mk(l.a[0] - p.x, l.a[1] - p.y, l.a[2] - p.z);
+    if (l.tag == 1) {
+        const float j = l.c[0];
+        const float r0 = rnd(seed), r1 = rnd(seed), r2 = rnd(seed);
+        return mk(fm(j, r0, l.a[0]), fm(j, r1, l.a[1]), fm(j, r2, l.a[2]));
+    }
+    const float r = l.b[0];
+    const float r0 = rnd(seed), r1 = rnd(seed), r2 = rnd(seed);
+    return mk(fm(r, r0, l.a[0]) - p.x, fm(r, r1, l.a[1]) - p.y, fm(r, r2, l.a[2]) - p.z);
+}
+static inline f3 pg_lumi(const PGLightO& l) { return l.tag == 2 ? mk(l.b[1], l.b[2], l.c[0]) : mk(l.b[0], l.b[1], l.b[2]); }
+}  // namespace
+
+extern "C" {
+
+// film: width*height*3 floats (read when !dirty, written); image: width*height*4 bytes or NULL.  normals: ntri*9 floats,
+// mat_indices: ntri ints, materials: nmat*3 floats.  Rows [y0,y1).  Returns rays traced (primary + probes).
+uint64_t orc_playground(void* scene, const void* camera92, const void* lights44, int nlights, const float* materials, const float* normals,
+                        const int32_t* mat_indices, int width, int height, uint32_t spf, uint32_t dt, int dirty, float* film, uint8_t* image,
+                        int y0, int y1, int threads)
+{
+    Scene* s = (Scene*)scene;
+    PGCam cam;
+    memcpy(&cam, camera92, sizeof cam);
+    const PGLightO* L = (const PGLightO*)lights44;
+    const f3 cu = ld3(cam.u), cv = ld3(cam.v), cw = ld3(cam.w), eye = ld3(cam.eye);
+    const int T = std::max(1, threads);
+    std::vector<uint64_t> nrays((size_t)T, 0);
+    parallel_rows(y1 - y0, T, [&](int row, int tid) {
+        const int iy = y0 + row;
+        for (int ix = 0; ix < width; ++ix) {
+            uint32_t seed = tea4((uint32_t)ix + (uint32_t)width * (uint32_t)iy, dt);
+            f3 result = mk(0.f, 0.f, 0.f);
+            for (uint32_t smp = 0; smp < spf; ++smp) {
+                float dx = fm(2.0f, (float)ix / (float)width, -1.0f), dy = fm(2.0f, (float)iy / (float)height, -1.0f);
+                f3 org, dir;
+                if (cam.ortho) {
+                    dir = normalize(mk(fm(dy, cv.x, dx * cu.x) + cw.x, fm(dy, cv.y, dx * cu.y) + cw.y, fm(dy, cv.z, dx * cu.z) + cw.z));
+                    org = mk(fm(dy, cv.x, fm(dx, cu.x, eye.x)), fm(dy, cv.y, fm(dx, cu.y, eye.y)), fm(dy, cv.z, fm(dx, cu.z, eye.z)));
+                } else {
+                    const float lx = (rnd(seed) - 0.5f) * cam.aperture, ly = (rnd(seed) - 0.5f) * cam.aperture;
+                    dx = dx - lx; dy = dy - ly;
+                    dir = normalize(mk(fm(dy, cv.x, dx * cu.x) + cw.x, fm(dy, cv.y, dx * cu.y) + cw.y, fm(dy, cv.z, dx * cu.z) + cw.z));
+                    org = mk(fm(ly, cv.x, fm(lx, cu.x, eye.x)), fm(ly, cv.y, fm(lx, cu.y, eye.y)), fm(ly, cv.z, fm(lx, cu.z, eye.z)));
+                }
+                ++nrays[(size_t)tid];
+                const SceneHit h = trace_scene<false>(*s, org, dir, 0.0f, 1e16f, 0u);
+                if (!h.hit) {
+                    result = result + mk(fm(dir.x, 0.5f, 0.5f), fm(dir.y, 0.5f, 0.5f), fm(dir.z, 0.5f, 0.5f));
+                    continue;
+                }
+                const float* N = normals + 9 * (size_t)h.prim;
+                const float b0 = (1.0f - h.b1) - h.b2;
+                const f3 n = mk(fm(b0, N[0], fm(h.b2, N[6], h.b1 * N[3])), fm(b0, N[1], fm(h.b2, N[7], h.b1 * N[4])), fm(b0, N[2], fm(h.b2, N[8], h.b1 * N[5])));
+                const f3 P = mk(fm(n.x, 0.0001f, fm(h.t, dir.x, org.x)), fm(n.y, 0.0001f, fm(h.t, dir.y, org.y)), fm(n.z, 0.0001f, fm(h.t, dir.z, org.z)));
+                uint32_t cs = tea4((uint32_t)ix + (uint32_t)width * (uint32_t)iy, dt);
+                const int m = mat_indices[h.prim];
+                const f3 color = ld3(materials + 3 * m);
+                f3 r = mk(0.f, 0.f, 0.f);
+                for (int li = 0; li < nlights; ++li) {
+                    const f3 wi = pg_wi(L[li], P, cs);
+                    const float nd = dot(n, wi);
+                    ++nrays[(size_t)tid];
+                    // TERMINATE_ON_FIRST_HIT | CULL_DISABLED_ANYHIT (1<<6)
+                    const bool occ = trace_scene<true>(*s, P, wi, 0.01f, 1.0f, 64u).hit;
+                    const f3 lumi = pg_lumi(L[li]);
+                    const f3 term = mk((color.x * lumi.x) * nd, (color.y * lumi.y) * nd, (color.z * lumi.z) * nd);
+                    r = r + ((occ || nd < 0.0f) ? mk(0.f, 0.f, 0.f) : term);
+                }
+                const Onb onb(n);
+                const float u1 = rnd(cs), u2 = rnd(cs);
+                float sn, csn;
+                det_sincos(6.2831855f * u2, sn, csn);
+                const float rr = sqrtf(u1);
+                f3 w_in = mk(rr * csn, rr * sn, 0.0f);
+                w_in.z = sqrtf(fmaxf(0.0f, fm(-w_in.y, w_in.y, fm(-w_in.x, w_in.x, 1.0f))));
+                const f3 out = onb.inverse_transform(w_in);
+                ++nrays[(size_t)tid];
+                const bool bh = trace_scene<true>(*s, P, out, 0.01f, 1e16f, 0u).hit;
+                const f3 amb = mk(0.01f, 0.01f, 0.01f);
+                r = r + (bh ? amb : amb * color);
+                result = result + r;
+            }
+            const size_t idx = (size_t)iy * width + ix;
+            f3 f = result;
+            if (!dirty) f = mk(film[3 * idx] + f.x, film[3 * idx + 1] + f.y, film[3 * idx + 2] + f.z);
+            film[3 * idx] = f.x; film[3 * idx + 1] = f.y; film[3 * idx + 2] = f.z;
+            if (image) make_color(mk(f.x / (float)dt, f.y / (float)dt, f.z / (float)dt), image + 4 * idx);
+        }
+    });
+    uint64_t tot = 0;
+    for (auto v : nrays) tot += v;
+    return tot;
+}
+
+// Camera::compute_ray / LightVariant::wi in the contract's arithmetic, exposed so the tests can hold them against the reference's own
+// host evaluation of the same functions (tests/golden/kat.json "playground_cameras" / "playground_lights")
+void orc_playground_ray(const void* camera92, uint32_t ix, uint32_t iy, uint32_t width, uint32_t height, uint32_t* seed, float* org3, float* dir3)
+{
+    PGCam cam;
+    memcpy(&cam, camera92, sizeof cam);
+    const f3 cu = ld3(cam.u), cv = ld3(cam.v), cw = ld3(cam.w), eye = ld3(cam.eye);
+    float dx = fm(2.0f, (float)ix / (float)width, -1.0f), dy = fm(2.0f, (float)iy / (float)height, -1.0f);
+    f3 org, dir;
+    if (cam.ortho) {
+        dir = normalize(mk(fm(dy, cv.x, dx * cu.x) + cw.x, fm(dy, cv.y, dx * cu.y) + cw.y, fm(dy, cv.z, dx * cu.z) + cw.z));
+        org = mk(fm(dy, cv.x, fm(dx, cu.x, eye.x)), fm(dy, cv.y, fm(dx, cu.y, eye.y)), fm(dy, cv.z, fm(dx, cu.z, eye.z)));
+    } else {
+        const float lx = (rnd(*seed) - 0.5f) * cam.aperture, ly = (rnd(*seed) - 0.5f) * cam.aperture;
+        dx = dx - lx; dy = dy - ly;
+        dir = normalize(mk(fm(dy, cv.x, dx * cu.x) + cw.x, fm(dy, cv.y, dx * cu.y) + cw.y, fm(dy, cv.z, dx * cu.z) + cw.z));
+        org = mk(fm(ly, cv.x, fm(lx, cu.x, eye.x)), fm(ly, cv.y, fm(lx, cu.y, eye.y)), fm(ly, cv.z, fm(lx, cu.z, eye.z)));
+    }
+    org3[0] = org.x; org3[1] = org.y; org3[2] = org.z; dir3[0] = dir.x; dir3[1] = dir.y; dir3[2] = dir.z;
+}
+void orc_playground_light(const void* light44, const float* p, uint32_t* seed, float* wi3, float* lumi3)
+{
+    PGLightO l;
+    memcpy(&l, light44, sizeof l);
+    const f3 w = pg_wi(l, ld3(p), *seed), m = pg_lumi(l);
+    wi3[0] = w.x; wi3[1] = w.y; wi3[2] = w.z; lumi3[0] = m.x; lumi3[1] = m.y; lumi3[2] = m.z;
+}
+
+// stand-in scene of optix_raytracer_b200/csrc/playground.cu (pg_scene_kernel), same arithmetic
+uint64_t orc_playground_scene(uint32_t rows, uint32_t seed, float* verts, float* normals, int32_t* mats, int threads)
+{
+    const uint32_t cols = 2 * rows;
+    const uint64_t blob_each = 2ull * rows * cols, total = 25ull * blob_each + 800ull;
+    if (!verts) return total;
+    auto blob_vertex = [&](int b, uint32_t i, uint32_t j, f3& nrm) {
+        const int gx = b % 5, gy = b / 5;
+        const f3 ctr = mk(0.25f * (float)(gx - 2), 0.1f, 0.25f * (float)(gy - 2));
+        const float rad = 0.08f;
+        if (i == 0) { nrm = mk(0.f, 1.f, 0.f); return mk(ctr.x, ctr.y + rad, ctr.z); }
+        if (i == rows) { nrm = mk(0.f, -1.f, 0.f); return mk(ctr.x, ctr.y - rad, ctr.z); }
+        j = j % cols;
+        const float theta = (3.14159265358979f * (float)i) / (float)rows;
+        const float phi = (6.28318530717959f * (float)j) / (float)cols;
+        float st, ct, sp, cp, s1, s2, unused;
+        det_sincos(theta, st, ct);
+        det_sincos(phi, sp, cp);
+        const float ph = 0.37f * (float)((seed + 7u * (uint32_t)b) % 17u);
+        det_sincos(fm(3.0f, theta, ph), s1, unused);
+        det_sincos(fm(4.0f, phi, ph), s2, unused);
+        const float disp = fm(st, (0.15f * s1) * s2, 1.0f);
+        const float rr = rad * disp;
+        const f3 d = mk((rr * st) * cp, rr * ct, (rr * st) * sp);
+        nrm = normalize(d);
+        return mk(d.x + ctr.x, d.y + ctr.y, d.z + ctr.z);
+    };
+    const int chunk = 8192;
+    parallel_rows((int)((total + chunk - 1) / chunk), std::max(1, threads), [&](int row, int) {
+        const uint64_t b0 = (uint64_t)row * chunk, e0 = std::min<uint64_t>(total, b0 + chunk);
+        for (uint64_t t = b0; t < e0; ++t) {
+            f3 a, b, c, na, nb, nc;
+            int mat;
+            if (t < 25 * blob_each) {
+                const int bi = (int)(t / blob_each);
+                const uint64_t r = t - (uint64_t)bi * blob_each, quad = r >> 1;
+                const uint32_t i = (uint32_t)(quad / cols), j = (uint32_t)(quad % cols);
+                f3 n00, n01, n10, n11;
+                const f3 p00 = blob_vertex(bi, i, j, n00), p01 = blob_vertex(bi, i, j + 1, n01);
+                const f3 p10 = blob_vertex(bi, i + 1, j, n10), p11 = blob_vertex(bi, i + 1, j + 1, n11);
+                if (r & 1) { a = p00; b = p11; c = p01; na = n00; nb = n11; nc = n01; }
+                else { a = p00; b = p10; c = p11; na = n00; nb = n10; nc = n11; }
+                mat = bi;
+            } else {
+                const uint32_t r = (uint32_t)(t - 25 * blob_each);
+                const int cell = (int)(r >> 1), i = cell / 20 - 10, j = cell % 20 - 10;
+                const float x0 = (float)i * 0.1f, x1 = (float)(i + 1) * 0.1f, z0 = (float)j * 0.1f, z1 = (float)(j + 1) * 0.1f;
+                if (r & 1) { a = mk(x1, 0.f, z0); b = mk(x0, 0.f, z1); c = mk(x1, 0.f, z1); }
+                else { a = mk(x0, 0.f, z0); b = mk(x0, 0.f, z1); c = mk(x1, 0.f, z0); }
+                na = nb = nc = mk(0.f, 1.f, 0.f);
+                mat = 26;
+            }
+            float* v = verts + 9 * t;
+            float* n = normals + 9 * t;
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = b.x; v[4] = b.y; v[5] = b.z; v[6] = c.x; v[7] = c.y; v[8] = c.z;
+            n[0] = na.x; n[1] = na.y; n[2] = na.z; n[3] = nb.x; n[4] = nb.y; n[5] = nb.z; n[6] = nc.x; n[7] = nc.y; n[8] = nc.z;
+            mats[t] = mat;
+        }
+    });
+    return total;
+}
+
+}  // extern "C"

@@ -47,6 +47,11 @@ def lib():
         L.orc_raycast_hits.argtypes = [vp, vp, i64, vp, vp, vp, i32]
         L.orc_raycast_shade.argtypes = [vp, i64, vp]
         L.orc_synth_mesh.argtypes = [C.c_uint64, u32, vp, vp, i32]
+        L.orc_scene_set_geometry_flags.argtypes = [vp, u32]
+        L.orc_playground.restype = C.c_uint64
+        L.orc_playground.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, i32, u32, u32, i32, vp, vp, i32, i32, i32]
+        L.orc_playground_scene.restype = C.c_uint64
+        L.orc_playground_scene.argtypes = [u32, u32, vp, vp, vp, i32]
         L.orc_pathtrace.restype = C.c_uint64
         L.orc_pathtrace.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
         _LIB = L
@@ -151,6 +156,28 @@ class Scene:
         lib().orc_raycast_hits(self.h, _p(rays), n, _p(nn), _p(hits), _p(ext), threads or ncores())
         return hits, ext
 
+    def set_geometry_flags(self, gflags):
+        """OptixGeometryFlags of the build input (default 1 = DISABLE_ANYHIT; imgui_test builds with 0)."""
+        lib().orc_scene_set_geometry_flags(self.h, int(gflags))
+
+    def playground(self, camera92, lights44, materials, normals, mat_indices, width, height, spf, dt, dirty, film=None, rows=None, threads=None,
+                   want_image=True):
+        """imgui_test frame (oracle.cpp: orc_playground).  camera92 / lights44: raw bytes of the reference's Camera / LightVariant[] objects.
+        Returns (film (h,w,3) f32, image (h,w,4) u8 or None, rays traced)."""
+        cam = np.frombuffer(bytes(camera92), np.uint8).copy()
+        lights = np.frombuffer(bytes(lights44), np.uint8).copy()
+        nl = lights.size // 44
+        mats = _f32(materials).reshape(-1)
+        nrm = _f32(normals).reshape(-1)
+        mi = np.ascontiguousarray(mat_indices, dtype=np.int32)
+        if film is None:
+            film = np.zeros((height, width, 3), np.float32)
+        image = np.zeros((height, width, 4), np.uint8) if want_image else None
+        y0, y1 = rows or (0, height)
+        n = lib().orc_playground(self.h, _p(cam), _p(lights), nl, _p(mats), _p(nrm), _p(mi), width, height, spf, dt, int(bool(dirty)), _p(film), _p(image),
+                                 y0, y1, threads or ncores())
+        return film, image, int(n)
+
     def pathtrace(self, params, emission, diffuse, accum=None, region=None, threads=None, want_frame=True):
         """params: PTParams.  Returns (accum (h,w,4) f32, frame (h,w,4) u8, segments)."""
         w, h = params.width, params.height
@@ -202,3 +229,13 @@ def synth_mesh(total, seed=0, threads=None):
     mats = np.zeros(total, np.uint32)
     lib().orc_synth_mesh(total, seed, _p(verts), _p(mats), threads or ncores())
     return verts.reshape(total, 3, 3), mats
+
+
+def playground_scene(rows, seed=0, threads=None):
+    """Stand-in scene of imgui_test (playground.cu: pg_scene_kernel): (T,3,3) vertices, (T,3,3) normals, (T,) int32 materials."""
+    total = int(lib().orc_playground_scene(rows, seed, None, None, None, 1))
+    verts = np.zeros((total, 9), np.float32)
+    nrm = np.zeros((total, 9), np.float32)
+    mats = np.zeros(total, np.int32)
+    lib().orc_playground_scene(rows, seed, _p(verts), _p(nrm), _p(mats), threads or ncores())
+    return verts.reshape(total, 3, 3), nrm.reshape(total, 3, 3), mats

@@ -119,3 +119,24 @@ def test_synthetic_mesh_hits_match_optix(ctxs):
     if diff.any():
         rel = np.abs(got["t"][diff] - ref["t"][diff]) / np.abs(ref["t"][diff])
         assert rel.max() < 1e-6
+
+
+@pytest.mark.parametrize("aperture", [0.0, 0.05])
+def test_playground_matches_the_reference_program_on_optix(ctxs, aperture):
+    """imgui_test's own optixTriangle.cu programs on OptiX vs the wavefront restatement, same Params / Camera / LightVariant bytes."""
+    from optix_raytracer_b200 import host
+    bctx, octx = ctxs
+    cam = host.playground_camera(eye=(0.3, 0.6, -1.2), up=(0.0, 1.0, 0.000073), lookat=(0.0, 0.1, 0.0), fov=50.0, aperture=aperture)
+    b = host.Playground(bctx, 256, 192, spf=4, rows=24, camera=cam)
+    o = host.Playground(octx, 256, 192, spf=4, rows=24, camera=cam)
+    for dirty in (True, False):
+        b.launch_frame(dirty=dirty)
+        o.launch_frame(dirty=dirty)
+    torch.cuda.synchronize()
+    fb, fo = b.film.cpu().numpy().astype(np.float64), o.film.cpu().numpy().astype(np.float64)
+    assert fo.mean() > 0.1
+    assert abs(fb.mean() - fo.mean()) / fo.mean() < 1e-3
+    ib, io = b.image.cpu().numpy()[..., :3].astype(np.float64), o.image.cpu().numpy()[..., :3].astype(np.float64)
+    mse = np.mean((ib - io) ** 2)
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+    assert psnr > 45.0, f"PSNR {psnr:.1f} dB"

@@ -181,3 +181,31 @@ def test_bvh_invariants_and_compaction(ctx):
         assert np.array_equal(ga["nodes"], gb["nodes"]) and np.array_equal(ga["tris"].view(np.uint32), gb["tris"].view(np.uint32))
         assert b.buf.numel() <= a.buf.numel()
         assert gb["total_bytes"] == 128 + 80 * gb["num_nodes"] + 48 * n
+
+
+@pytest.mark.parametrize("aperture,ortho", [(0.0, False), (0.05, False), (0.0, True)])
+def test_playground_bit_exact(ctx, orc, aperture, ortho):
+    """imgui_test (BASELINE.json configs[3]): scene generator == oracle restatement, film bit-exact over two frames (dirty, then
+    accumulating), image within 1 LSB."""
+    from optix_raytracer_b200 import host
+    w, h, spf, rows = 64, 48, 3, 10
+    cam = host.playground_camera(eye=(0.3, 0.6, -1.2), up=(0.0, 1.0, 0.000073), lookat=(0.0, 0.1, 0.0), fov=50.0, aperture=aperture, ortho=ortho)
+    pg = host.Playground(ctx, w, h, spf=spf, rows=rows, camera=cam)
+    verts, nrm, mats = orc.playground_scene(rows)
+    torch.cuda.synchronize()
+    assert np.array_equal(pg.vertices.cpu().numpy().reshape(-1, 3, 3).view(np.uint32), verts.view(np.uint32))
+    assert np.array_equal(pg.normals.cpu().numpy().reshape(-1, 3, 3).view(np.uint32), nrm.view(np.uint32))
+    assert np.array_equal(pg.mat_indices.cpu().numpy(), mats)
+    scene = orc.Scene(verts)
+    scene.set_geometry_flags(0)
+    film = None
+    for frame, dirty in enumerate((True, False)):
+        pg.launch_frame(dirty=dirty)
+        torch.cuda.synchronize()
+        dt = pg.params.dt
+        assert dt == spf * (frame + 1)
+        film, image, nrays = scene.playground(cam, pg.lights_bytes, pg.materials, nrm, mats, w, h, spf, dt, dirty, film=film)
+        got = pg.film.cpu().numpy()
+        assert (got > 0).mean() > 0.9
+        assert np.array_equal(got.view(np.uint32), film.view(np.uint32)), f"frame {frame}: film differs"
+        assert np.abs(pg.image.cpu().numpy().astype(np.int32) - image.astype(np.int32)).max() <= 1

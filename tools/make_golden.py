@@ -85,6 +85,40 @@ def main():
              "OptixShaderBindingTable", "OptixAccelBuildOptions", "OptixBuildInputTriangleArray"]
     assert k == len(names)
     out["params_layout"] = dict(zip(names, list(o[:k])))
+    # --- imgui_test: layouts, and the host objects main.cpp:236-252 builds, as raw bytes written by the reference's own classes
+    k = ref.ref_playground_layout(o)
+    names = ["Params", "image_width", "image_height", "samples_per_frame", "camera", "dt", "dirty", "image", "film", "tfactor", "handle", "normals",
+             "vertices", "mat_indices", "nmat_indices", "lights", "nlights", "materials", "nmaterials", "sizeof_Camera", "sizeof_LightVariant",
+             "sizeof_DiffuseMaterial"]
+    assert k == len(names)
+    out["playground_layout"] = dict(zip(names, list(o[:k])))
+    f3 = ctypes.c_float * 3
+    cams = []
+    for eye, up, lookat, aperture, fd, fov, ortho in [((0.0, 1.0, -10.0), (0.0, 0.0000073, 1.0), (0.0, 0.1, 0.0), 0.0, 1.0, 45.0, 0),
+                                                       ((0.0, 1.0, -10.0), (0.0, 0.0000073, 1.0), (0.0, 0.1, 0.0), 0.05, 1.0, 45.0, 0),
+                                                       ((0.3, 0.6, -1.2), (0.0, 1.0, 0.000073), (0.0, 0.1, 0.0), 0.02, 1.0, 50.0, 0),
+                                                       ((0.3, 0.6, -1.2), (0.0, 1.0, 0.000073), (0.0, 0.1, 0.0), 0.0, 1.0, 50.0, 1)]:
+        buf = (ctypes.c_uint8 * 92)()
+        ref.ref_pg_camera(f3(*eye), f3(*up), f3(*lookat), ctypes.c_float(aperture), ctypes.c_float(fd), ctypes.c_float(fov), ortho, buf)
+        rays = []
+        for ix, iy, w, h, seed in [(0, 0, 64, 48, 1), (63, 47, 64, 48, 12345), (17, 30, 64, 48, 0xdeadbeef), (960, 540, 1920, 1080, 7)]:
+            st = ctypes.c_uint(seed)
+            og, dr = f3(), f3()
+            ref.ref_pg_compute_ray(buf, ix, iy, w, h, ctypes.byref(st), og, dr)
+            rays.append({"ix": ix, "iy": iy, "w": w, "h": h, "seed": seed, "seed_after": st.value, "org_bits": [fbits(x) for x in og], "dir_bits": [fbits(x) for x in dr]})
+        cams.append({"eye": eye, "up": up, "lookat": lookat, "aperture": aperture, "fd": fd, "fov": fov, "ortho": ortho, "bytes": bytes(buf).hex(), "rays": rays})
+    out["playground_cameras"] = cams
+    lights = []
+    for kind, a, lumi, scalar in [(2, (0.0, 2.0, 0.0), (0.1, 0.08, 0.08), 0.1), (2, (2.0, 2.0, 0.0), (0.1, 0.08, 0.08), 0.1), (2, (2.0, 2.0, 2.0), (0.1, 0.08, 0.08), 0.1),
+                                  (1, (-1.0, 1.0, -1.0), (0.1, 0.1, 0.1), 0.05), (0, (0.5, 1.5, -0.5), (0.2, 0.3, 0.4), 0.0)]:
+        buf = (ctypes.c_uint8 * 44)()
+        ref.ref_pg_light(kind, f3(*a), f3(*lumi), ctypes.c_float(scalar), buf)
+        st = ctypes.c_uint(4242)
+        wi, lm = f3(), f3()
+        ref.ref_pg_light_eval(buf, f3(0.1, 0.05, -0.2), ctypes.byref(st), wi, lm)
+        lights.append({"kind": kind, "a": a, "lumi": lumi, "scalar": scalar, "bytes": bytes(buf).hex(), "p": [0.1, 0.05, -0.2], "seed": 4242,
+                       "seed_after": st.value, "wi_bits": [fbits(x) for x in wi], "lumi_bits": [fbits(x) for x in lm]})
+    out["playground_lights"] = lights
     p = ROOT / "tests" / "golden" / "kat.json"
     p.write_text(json.dumps(out) + "\n")
     print("wrote", p, p.stat().st_size, "bytes")
