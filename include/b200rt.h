@@ -255,6 +255,25 @@ int b200rt_deinterleave(b200rt_context ctx, b200rt_stream stream, b200rt_devicep
                         int num_samples, int width, int height, b200rt_deviceptr accum_float4,
                         b200rt_deviceptr frame_uchar4);
 
+/* optixMeshViewer launch: optixLaunch(scene.pipeline(), 0, d_params, sizeof(whitted::LaunchParams)=128, scene.sbt(), width, height, 1)
+ * (reference SDK/optixMeshViewer/optixMeshViewer.cpp:283-308) + the programs of SDK/cuda/whitted.cu:44-98,139-289 and
+ * getLocalGeometry / sampleTexture (SDK/cuda/LocalGeometry.h:59-176, SDK/cuda/LocalShading.h:37-53).
+ * d_params: device copy of whitted::LaunchParams (SDK/cuda/whitted.h:59-77); its `lights` BufferView points to Light records
+ * (SDK/cuda/Light.h:31-71).  SBT: as sutil::Scene::createSBT builds it (SDK/sutil/Scene.cpp:1405-1433) — per primitive group a
+ * radiance and an occlusion record, each carrying whitted::HitGroupData {GeometryData, MaterialData}; MaterialData textures are
+ * cudaTextureObject_t handles and are sampled with tex2D like the reference does.
+ * Scope: OPAQUE materials; a launch that hits a MASK / BLEND material returns B200RT_ERROR_NOT_SUPPORTED (the any-hit programs
+ * whitted.cu:100-137 are not built yet).  Synchronises `stream` (Params read-back, support check). */
+int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
+                          const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height);
+
+/* sutil::Scene::addImage + addSampler (reference SDK/sutil/Scene.cpp:576-652): 8-bit RGBA image (as tinygltf decodes every glTF
+ * image, SDK/support/tinygltf/tiny_gltf.h:2368) -> CUDA array + texture object (normalised coordinates, normalised-float reads).
+ * address_s / address_t: cudaTextureAddressMode (0 wrap, 1 clamp, 2 mirror); linear_filter: 0 point, 1 linear. */
+int b200rt_texture_create(b200rt_context ctx, int width, int height, const void* rgba8, int address_s, int address_t,
+                          int linear_filter, uint64_t* texture_object, uint64_t* cuda_array);
+int b200rt_texture_destroy(b200rt_context ctx, uint64_t texture_object, uint64_t cuda_array);
+
 /* imgui_test ("playground") launch: optixLaunch(pipeline, stream, d_param, sizeof(Params)=128, &sbt, buf_width, buf_height, 1)
  * (reference SDK/imgui_test/tracer_window.cpp:96-105) + the programs of SDK/imgui_test/optixTriangle.cu:103-268.
  * d_params: device copy of the sample's Params (SDK/imgui_test/optixTriangle.h:42-108) — its camera / lights / materials / normals /

@@ -129,6 +129,9 @@ SYMBOLS = {
     "b200rt_camera_uvw": (None, [C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), f32, f32, C.POINTER(f32), C.POINTER(f32),
                                  C.POINTER(f32)]),
     "b200rt_playground_camera": (None, [C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), f32, f32, f32, i32, vp]),
+    "b200rt_launch_whitted": (i32, [vp, vp, u64, C.POINTER(ShaderBindingTable), u32, u32]),
+    "b200rt_texture_create": (i32, [vp, i32, i32, vp, i32, i32, i32, C.POINTER(u64), C.POINTER(u64)]),
+    "b200rt_texture_destroy": (i32, [vp, u64, u64]),
     "b200rt_launch_playground": (i32, [vp, vp, u64, u32, u32, C.POINTER(PTOptions)]),
     "b200rt_generate_playground_scene": (i32, [vp, vp, u32, u32, u64, u64, u64, C.POINTER(u64)]),
     "b200rt_wd_num_samples": (i32, [i32, i32, i32]),

@@ -270,6 +270,27 @@ int b200rt_generate_synthetic_mesh(b200rt_context ctx, b200rt_stream stream, uin
     return generate_synthetic_mesh(ctx, (cudaStream_t)stream, num_triangles, seed, vertices_float4, mat_indices_u32, bounds_out);
 }
 
+int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt,
+                          unsigned int width, unsigned int height)
+{
+    CTX_CHECK(ctx);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    return launch_whitted(ctx, (cudaStream_t)stream, d_params, sbt, width, height);
+}
+
+int b200rt_texture_create(b200rt_context ctx, int width, int height, const void* rgba8, int address_s, int address_t, int linear_filter,
+                          uint64_t* texture_object, uint64_t* cuda_array)
+{
+    CTX_CHECK(ctx);
+    return texture_create(ctx, width, height, rgba8, address_s, address_t, linear_filter, texture_object, cuda_array);
+}
+
+int b200rt_texture_destroy(b200rt_context ctx, uint64_t texture_object, uint64_t cuda_array)
+{
+    CTX_CHECK(ctx);
+    return texture_destroy(ctx, texture_object, cuda_array);
+}
+
 int b200rt_launch_playground(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params, unsigned int width, unsigned int height,
                              const b200rt_pt_options* options)
 {

@@ -103,7 +103,11 @@ struct RayWork {
     __device__ __forceinline__ void commit(const Trav& s, bool found)
     {
         if (KIND == 1) { occluded[item] = found ? 1u : 0u; return; }
-        if (KIND == 0) { ext[item] = make_ext(s, found); return; }
+        if (KIND == 0) {
+            ext[item] = make_ext(s, found);
+            if (occluded) occluded[item] = found ? (s.best.sbt & TRI_SBT_MASK) : 0u;  // optional: GAS-local SBT index of the hit (whitted.cu)
+            return;
+        }
         // KIND 2: __miss__buffer_miss / __closesthit__buffer_hit (optixRaycasting.cu:65-86)
         float4 out;
         if (!found) {
@@ -331,7 +335,7 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
 // Internal ray-buffer query used by the multi-stage launches (playground.cu): kind 0 = closest hit -> ExtHit records, 1 = any hit ->
 // u32 flags.  The ray count may live on the device (n_dev * n_mult, capped by n_max).  Caller holds ctx->mu.
 int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev,
-                 unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period)
+                 unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period, b200rt_deviceptr sbt_out)
 {
     B2_REQUIRE(ctx, handle && rays && out && n_max < (1ull << 32), "bad argument");
     if (n_max == 0) return 0;
@@ -340,8 +344,8 @@ int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, 
     if (rc) return rc;
     if (kind == 0)
         trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
-            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, nullptr, nullptr, nullptr, 0, 0, counter, nullptr,
-            n_dev, n_mult, flag_period);
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, nullptr, 0, 0, counter,
+            nullptr, n_dev, n_mult, flag_period);
     else
         trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, nullptr, 0, 0, counter, nullptr,

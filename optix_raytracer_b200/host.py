@@ -144,6 +144,9 @@ class Context:
     def launch_multigpu(self, programs, d_params, params_size, sbt, num_samples, opts):
         self.check(self.lib.b200rt_launch_multigpu(self.h, self.stream, d_params, C.byref(sbt), num_samples, C.byref(opts)), "launch_multigpu")
 
+    def launch_whitted(self, programs, d_params, params_size, sbt, width, height):
+        self.check(self.lib.b200rt_launch_whitted(self.h, self.stream, d_params, C.byref(sbt), width, height), "launch_whitted")
+
     def launch_playground(self, programs, d_params, params_size, sbt, width, height, opts):
         self.check(self.lib.b200rt_launch_playground(self.h, self.stream, d_params, width, height, C.byref(opts)), "launch_playground")
 
@@ -460,14 +463,24 @@ def load_gltf(path):
                 hi = np.maximum(hi, np.array(pa["max"], np.float32))
             nrm = accessor(p["attributes"]["NORMAL"])[0] if "NORMAL" in p["attributes"] else None
             idx = accessor(p["indices"])[0].reshape(-1) if "indices" in p else None
+            uv0 = accessor(p["attributes"]["TEXCOORD_0"])[0].astype(np.float32) if "TEXCOORD_0" in p["attributes"] else None
+            uv1 = accessor(p["attributes"]["TEXCOORD_1"])[0].astype(np.float32) if "TEXCOORD_1" in p["attributes"] else None
             prims.append({"positions": pos.astype(np.float32), "normals": None if nrm is None else nrm.astype(np.float32),
-                          "indices": idx, "material": p.get("material", -1)})
+                          "indices": idx, "material": p.get("material", -1), "texcoords": [uv0, uv1]})
         meshes.append({"primitives": prims, "aabb": (lo, hi)})
     instances = []
+    cameras = []
 
     def walk(ni, parent):
         node = g["nodes"][ni]
         xf = (parent @ _mat_from_node(node)).astype(np.float32)
+        if "camera" in node:
+            # processGLTFNode (Scene.cpp:166-192): eye = M (0,0,0,1), up = M (0,1,0,0), fovY in degrees
+            cam = g["cameras"][node["camera"]]
+            if cam.get("type") == "perspective":
+                yfov = np.float32(cam["perspective"]["yfov"]) * np.float32(180.0) / np.float32(math.pi)
+                cameras.append({"eye": (xf @ np.array([0, 0, 0, 1], np.float32))[:3], "up": (xf @ np.array([0, 1, 0, 0], np.float32))[:3],
+                                "fov_y": float(yfov)})
         if "camera" not in node and "mesh" in node:
             lo, hi = meshes[node["mesh"]]["aabb"]
             corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float32)
@@ -479,7 +492,41 @@ def load_gltf(path):
     scene = g["scenes"][g.get("scene", 0)]
     for ni in scene["nodes"]:
         walk(ni, np.eye(4, dtype=np.float32))
-    return {"meshes": meshes, "instances": instances}
+    return {"meshes": meshes, "instances": instances, "cameras": cameras, "materials": _gltf_materials(g), "images": _gltf_images(g, path.parent),
+            "textures": g.get("textures", []), "samplers": g.get("samplers", [])}
+
+
+def _gltf_materials(g):
+    """The MaterialData fields sutil::loadScene fills (Scene.cpp:350-443); defaults as MaterialData() (MaterialData.h:44-52: metallic = roughness = 1)."""
+    out = []
+    for m in g.get("materials", []):
+        pbr = m.get("pbrMetallicRoughness", {})
+
+        def tex(info):
+            if not info:
+                return None
+            xf = info.get("extensions", {}).get("KHR_texture_transform", {})
+            return {"index": info["index"], "texcoord": xf.get("texCoord", info.get("texCoord", 0)), "offset": xf.get("offset", [0.0, 0.0]),
+                    "rotation": xf.get("rotation", 0.0), "scale": xf.get("scale", [1.0, 1.0])}
+        out.append({"base_color": pbr.get("baseColorFactor", [1.0, 1.0, 1.0, 1.0]), "metallic": pbr.get("metallicFactor", 1.0),
+                    "roughness": pbr.get("roughnessFactor", 1.0), "base_color_tex": tex(pbr.get("baseColorTexture")),
+                    "metallic_roughness_tex": tex(pbr.get("metallicRoughnessTexture")), "normal_tex": tex(m.get("normalTexture")),
+                    "emissive_tex": tex(m.get("emissiveTexture")), "emissive_factor": m.get("emissiveFactor", [0.0, 0.0, 0.0]),
+                    "alpha_mode": {"OPAQUE": 0, "MASK": 1, "BLEND": 2}[m.get("alphaMode", "OPAQUE")], "alpha_cutoff": m.get("alphaCutoff", 0.5),
+                    "double_sided": bool(m.get("doubleSided", False))})
+    return out
+
+
+def _gltf_images(g, base):
+    """8-bit RGBA pixels of every glTF image, 4 channels always as tinygltf/stb decode them (tiny_gltf.h:2368)."""
+    out = []
+    for im in g.get("images", []):
+        try:
+            from PIL import Image
+            out.append(np.ascontiguousarray(np.array(Image.open(base / im["uri"]).convert("RGBA"), np.uint8)))
+        except Exception:  # image library or file missing: the material falls back to its factors
+            out.append(None)
+    return out
 
 
 # byte offsets inside whitted::HitGroupData (SDK/cuda/whitted.h:44-48, SDK/cuda/GeometryData.h:73-80,248-262)
@@ -712,3 +759,153 @@ class Playground:
         opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))
         self.ctx.launch_playground(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height, opts)
         return self.stats if collect_stats else None
+
+
+# ---- optixMeshViewer: SDK/optixMeshViewer/optixMeshViewer.cpp:190-308 + sutil::Scene::finalize (Scene.cpp:673-689,817-1212,1405-1433) -----
+class WLaunchParams(C.Structure):  # whitted::LaunchParams (SDK/cuda/whitted.h:59-77), 128 bytes
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("subframe_index", C.c_uint32), ("accum_buffer", C.c_uint64),
+                ("frame_buffer", C.c_uint64), ("max_depth", C.c_int32), ("scene_epsilon", C.c_float), ("eye", C.c_float * 3), ("U", C.c_float * 3),
+                ("V", C.c_float * 3), ("W", C.c_float * 3), ("lights_data", C.c_uint64), ("lights_count", C.c_uint32), ("lights_stride", C.c_uint16),
+                ("lights_elmt", C.c_uint16), ("miss_color", C.c_float * 3), ("handle", C.c_uint64)]
+
+
+assert C.sizeof(WLaunchParams) == 128 and WLaunchParams.lights_data.offset == 88 and WLaunchParams.handle.offset == 120
+
+
+def pack_texture(t, tex_objects):
+    """MaterialData::Texture (40 B): texcoord, cudaTextureObject_t, offset, rotation (sin, cos), scale (Scene.cpp:214-265)."""
+    if t is None or tex_objects.get(t["index"]) is None:
+        return struct.pack("<iiQ6f", 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+    rot = np.float32(t["rotation"])
+    return struct.pack("<iiQ6f", int(t["texcoord"]), 0, tex_objects[t["index"]], float(t["offset"][0]), float(t["offset"][1]),
+                       float(np.sin(rot, dtype=np.float32)), float(np.cos(rot, dtype=np.float32)), float(t["scale"][0]), float(t["scale"][1]))
+
+
+def pack_material(m, tex_objects):
+    """MaterialData (240 B, SDK/cuda/MaterialData.h:34-140; offsets pinned in tests/golden/kat.json "whitted_layout")."""
+    b = bytearray(240)
+    if m is None:
+        m = {"base_color": [1, 1, 1, 1], "metallic": 1.0, "roughness": 1.0, "base_color_tex": None, "metallic_roughness_tex": None,
+             "normal_tex": None, "emissive_tex": None, "emissive_factor": [0, 0, 0], "alpha_mode": 0, "alpha_cutoff": 0.0, "double_sided": False}
+    b[8:48] = pack_texture(m["normal_tex"], tex_objects)
+    b[48:56] = struct.pack("<if", m["alpha_mode"], float(m["alpha_cutoff"]) if m["alpha_mode"] == 1 else 0.0)
+    b[56:68] = struct.pack("<3f", *[float(x) for x in m["emissive_factor"]])
+    b[72:112] = pack_texture(m["emissive_tex"], tex_objects)
+    b[112] = 1 if m["double_sided"] else 0
+    b[128:152] = struct.pack("<6f", *[float(x) for x in m["base_color"]], float(m["metallic"]), float(m["roughness"]))
+    b[152:192] = pack_texture(m["base_color_tex"], tex_objects)
+    b[192:232] = pack_texture(m["metallic_roughness_tex"], tex_objects)
+    return bytes(b)
+
+
+class MeshViewer:
+    """Mirror of optixMeshViewer's state for a scene dict as load_gltf returns it (textures optional: `images` entries may be None)."""
+
+    def __init__(self, ctx, scene, width, height):
+        self.ctx, self.scene, self.width, self.height = ctx, scene, width, height
+        hc = getattr(ctx, "helper", ctx)
+        dev = ctx.torch_device
+        self.programs = ctx.prepare_programs("whitted")
+        # Scene::addImage / addSampler (Scene.cpp:576-652): one texture object per glTF texture (sampler wrap modes; linear unless NEAREST)
+        self.tex_objects, self._tex_handles = {}, []
+        wrap = {10497: 0, 33071: 1, 33648: 2}
+        for ti, t in enumerate(scene.get("textures", [])):
+            img = scene["images"][t["source"]] if t.get("source") is not None else None
+            if img is None:
+                self.tex_objects[ti] = None
+                continue
+            smp = scene["samplers"][t["sampler"]] if t.get("sampler") is not None and scene.get("samplers") else {}
+            linear = 0 if smp.get("magFilter") == 9728 else 1
+            tex, arr = C.c_uint64(), C.c_uint64()
+            hc.check(hc.lib.b200rt_texture_create(hc.h, img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p), wrap.get(smp.get("wrapS", 10497), 0),
+                                                  wrap.get(smp.get("wrapT", 10497), 0), linear, C.byref(tex), C.byref(arr)), "texture_create")
+            self.tex_objects[ti] = tex.value
+            self._tex_handles.append((hc, tex.value, arr.value))
+        materials = scene.get("materials", [])
+        self.keep, self.mesh_accels, mesh_records = [], [], []
+        for m in scene["meshes"]:
+            inputs, recs = [], []
+            for p in m["primitives"]:
+                d_pos = ctx.to_device(p["positions"])
+                d_nrm = ctx.to_device(p["normals"]) if p.get("normals") is not None else None
+                idx = p["indices"]
+                d_idx = None
+                if idx is not None:
+                    d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
+                uvs = p.get("texcoords") or [None, None]
+                d_uv = [ctx.to_device(u) if u is not None else None for u in uvs]
+                mat = materials[p["material"]] if p.get("material", -1) >= 0 and p["material"] < len(materials) else None
+                # geometry flags by material (Scene.cpp:904-966): OPAQUE -> DISABLE_ANYHIT, MASK -> NONE, BLEND -> REQUIRE_SINGLE_ANYHIT_CALL;
+                # doubleSided adds DISABLE_TRIANGLE_FACE_CULLING
+                am = 0 if mat is None else mat["alpha_mode"]
+                gf = {0: 1, 1: 0, 2: 2}[am] | (4 if (mat is not None and mat["double_sided"]) else 0)
+                inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, flags=[gf], vertex_stride=12))
+                self.keep += [d_pos, d_nrm, d_idx] + d_uv
+                geo = bytearray(112)
+
+                def bview(t, elmt, stride):
+                    return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride if t is not None else 0,
+                                       elmt if t is not None else 0)
+                isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
+                geo[HG_OFF_INDICES:HG_OFF_INDICES + 16] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
+                geo[HG_OFF_POSITIONS:HG_OFF_POSITIONS + 16] = bview(d_pos, 12, 12)
+                geo[HG_OFF_NORMALS:HG_OFF_NORMALS + 16] = bview(d_nrm, 12, 12)
+                geo[64:80] = bview(d_uv[0], 8, 8)
+                geo[80:96] = bview(d_uv[1], 8, 8)
+                recs.append(bytes(geo) + pack_material(mat, self.tex_objects))
+            self.mesh_accels.append(ctx.build_accel(inputs, compact=True))
+            mesh_records.append(recs)
+        # createSBT (Scene.cpp:1405-1433): per INSTANCE, per primitive group: radiance record + occlusion record (same data)
+        records, inst = [], []
+        for i in scene["instances"]:
+            inst.append((i["transform"][:3, :].reshape(12), len(records), self.mesh_accels[i["mesh"]]))
+            for data in mesh_records[i["mesh"]]:
+                records.append(ctx.sbt_header(self.programs, 2, 0) + data)
+                records.append(ctx.sbt_header(self.programs, 2, 1) + data)
+        self.d_hitgroup = ctx.to_device(np.frombuffer(b"".join(records), np.uint8).copy())
+        self.ias = ctx.build_accel([ctx.instance_input(inst)], compact=False)
+        miss = np.zeros((2, 32), np.uint8)
+        for r in range(2):
+            miss[r] = np.frombuffer(ctx.sbt_header(self.programs, 1, r), np.uint8)
+        self.d_miss = ctx.to_device(miss)
+        self.d_raygen = ctx.to_device(np.frombuffer(ctx.sbt_header(self.programs, 0, 0), np.uint8).copy())
+        self.sbt = L.ShaderBindingTable()
+        self.sbt.raygenRecord = self.d_raygen.data_ptr()
+        self.sbt.missRecordBase, self.sbt.missRecordStrideInBytes, self.sbt.missRecordCount = self.d_miss.data_ptr(), 32, 2
+        self.sbt.hitgroupRecordBase, self.sbt.hitgroupRecordStrideInBytes, self.sbt.hitgroupRecordCount = self.d_hitgroup.data_ptr(), 32 + 352, len(records)
+        # scene AABB, camera (Scene.cpp:683-688,777-791), lights (optixMeshViewer.cpp:199-212)
+        lo = np.min([i["world_aabb"][0] for i in scene["instances"]], axis=0).astype(np.float32)
+        hi = np.max([i["world_aabb"][1] for i in scene["instances"]], axis=0).astype(np.float32)
+        center = ((lo + hi) * np.float32(0.5)).astype(np.float32)
+        ext = (hi - lo).astype(np.float32)
+        max_ext = ext[int(np.argmax(ext))]
+        if scene.get("cameras"):
+            cam = scene["cameras"][0]
+            eye, up, fov = cam["eye"], cam["up"], cam["fov_y"]
+        else:
+            eye, up, fov = (center + np.array([0.0, 0.0, 1.5 * max_ext], np.float32)).astype(np.float32), np.array([0, 1, 0], np.float32), 45.0
+        self.eye = np.asarray(eye, np.float32)
+        U, V, W = camera_uvw(self.eye, center, up, fov, np.float32(width) / np.float32(height))
+        lights = b"".join([
+            struct.pack("<i3ff3fi", 0, 1.0, 1.0, 0.8, 5.0, *[float(x) for x in (center + max_ext)], 2),
+            struct.pack("<i3ff3fi", 0, 0.8, 0.8, 1.0, 3.0, *[float(x) for x in (center + np.array([-max_ext, np.float32(0.5) * max_ext, np.float32(-0.5) * max_ext], np.float32))], 2)])
+        self.d_lights = ctx.to_device(np.frombuffer(lights, np.uint8).copy())
+        self.accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+        self.frame = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
+        self.params = WLaunchParams(width, height, 0, self.accum.data_ptr(), self.frame.data_ptr(), 0, 0.0, _f3(self.eye), _f3(U), _f3(V), _f3(W),
+                                    self.d_lights.data_ptr(), 2, 0, 0, _f3([0.1, 0.1, 0.1]), self.ias.handle)
+        self.h_params = torch.empty(128, dtype=torch.uint8).pin_memory()
+        self.d_params = torch.empty(128, dtype=torch.uint8, device=dev)
+
+    def launch_subframe(self, subframe_index=None):
+        """launchSubframe (optixMeshViewer.cpp:283-308)."""
+        if subframe_index is not None:
+            self.params.subframe_index = subframe_index
+        self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
+        self.d_params.copy_(self.h_params, non_blocking=True)
+        self.ctx.launch_whitted(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height)
+
+    def close(self):
+        for hc, tex, arr in self._tex_handles:
+            hc.lib.b200rt_texture_destroy(hc.h, tex, arr)
+        self._tex_handles = []

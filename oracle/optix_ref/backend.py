@@ -40,6 +40,8 @@ PROGRAMS = {
                  GRAPH_SINGLE_GAS, 2, 1),                                        # optixMultiGPU.cpp:786-950
     "raycast": ("optixRaycasting.ptx", "__raygen__from_buffer", "__miss__buffer_miss", "__closesthit__buffer_hit", "__anyhit__texture_mask", 4,
                 None, GRAPH_SINGLE_LEVEL_INSTANCING, 1, 2),                      # optixRaycasting.cpp:94-196
+    "whitted": ("whitted.ptx", "__raygen__pinhole", "__miss__constant_radiance,__miss__occlusion", "__closesthit__radiance,-",
+                "__anyhit__radiance,__anyhit__occlusion", 4, None, GRAPH_SINGLE_LEVEL_INSTANCING, 8, 2),  # Scene.cpp:1215-1403
     "playground": ("optixTriangle.ptx", "__raygen__rg", "__miss__ms", "__closesthit__ch", "-", 3, None, GRAPH_SINGLE_GAS, 2, 1),  # imgui_test/main.cpp:71-188
     # (the sample links with maxTraceDepth 1 although its closest-hit program traverses again; 2 here only enlarges the stack)
     "query_gas": ("query_programs.ptx", "__raygen__query", "__miss__query", "__closesthit__query", "-", 5, None, GRAPH_SINGLE_GAS, 1, 1),
@@ -148,6 +150,9 @@ class OptixContext(host.Context):
 
     def launch_multigpu(self, programs, d_params, params_size, sbt, num_samples, opts):
         self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, params_size, C.byref(sbt), num_samples, 1, 1), "optixLaunch")
+
+    def launch_whitted(self, programs, d_params, params_size, sbt, width, height):
+        self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, params_size, C.byref(sbt), width, height, 1), "optixLaunch")
 
     def launch_playground(self, programs, d_params, params_size, sbt, width, height, opts):
         self.ocheck(self.olib.oref_launch(programs, self.stream, d_params, params_size, C.byref(sbt), width, height, 1), "optixLaunch")

@@ -1117,3 +1117,119 @@ uint64_t orc_playground_scene(uint32_t rows, uint32_t seed, float* verts, float*
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// optixMeshViewer — SDK/cuda/whitted.cu:44-98,139-289 + getLocalGeometry (SDK/cuda/LocalGeometry.h:59-163) for OPAQUE,
+// UNTEXTURED materials (texture fetches are hardware tex2D in the reference and in the product; they are compared on the GPU
+// against the reference programs running on OptiX, tests/test_gpu_optix_parity.py).  Same op order as csrc/whitted.cu.
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+struct orc_whitted_params {
+    uint32_t width, height, subframe_index;
+    float eye[3], U[3], V[3], W[3];
+    float miss_color[3];
+    float base_color[4];
+    float metallic, roughness;
+    float emissive[3];
+    int32_t nlights;
+};
+
+// normals: ntri*9 floats or NULL (geometric normal); lights: nlights x 36-byte Light records; accum: width*height*4 floats
+// (read when subframe_index > 0, written); frame: width*height*4 bytes or NULL.  Returns rays traced.
+uint64_t orc_whitted(void* scene, const orc_whitted_params* p, const float* normals, const void* lights36, float* accum, uint8_t* frame, int y0,
+                     int y1, int threads)
+{
+    Scene* s = (Scene*)scene;
+    struct LightRec { int32_t type; float color[3]; float intensity; float position[3]; int32_t falloff; };
+    static_assert(sizeof(LightRec) == 36, "Light");
+    const LightRec* L = (const LightRec*)lights36;
+    const f3 eye = ld3(p->eye), U = ld3(p->U), V = ld3(p->V), W = ld3(p->W);
+    const int T = std::max(1, threads);
+    std::vector<uint64_t> nrays((size_t)T, 0);
+    const float PI = 3.14159265358979323846f;
+    parallel_rows(y1 - y0, T, [&](int row, int tid) {
+        const uint32_t iy = (uint32_t)(y0 + row);
+        for (uint32_t ix = 0; ix < p->width; ++ix) {
+            uint32_t seed = tea4(iy * p->width + ix, p->subframe_index);
+            float jx = 0.5f, jy = 0.5f;
+            if (p->subframe_index != 0) { jx = rnd(seed); jy = rnd(seed); }
+            const float dx = fm(2.0f, ((float)ix + jx) / (float)p->width, -1.0f), dy = fm(2.0f, ((float)iy + jy) / (float)p->height, -1.0f);
+            const f3 dir = normalize(mk(fm(dy, V.x, dx * U.x) + W.x, fm(dy, V.y, dx * U.y) + W.y, fm(dy, V.z, dx * U.z) + W.z));
+            ++nrays[(size_t)tid];
+            const SceneHit h = trace_scene<false>(*s, eye, dir, 0.0f, 1e16f, 16u /* CULL_BACK_FACING_TRIANGLES */);
+            f3 result;
+            if (!h.hit) {
+                result = ld3(p->miss_color);
+            } else {
+                const Instance* in = s->insts.empty() ? nullptr : &s->insts[h.inst];
+                const Geometry& g = s->geoms[in ? in->geom : 0];
+                const Tri& tr = g.tris[h.prim];
+                const float b1 = h.b1, b2 = h.b2, b0 = (1.0f - b1) - b2;
+                auto bary = [&](f3 a, f3 b, f3 c) { return mk(fm(b2, c.x, fm(b1, b.x, b0 * a.x)), fm(b2, c.y, fm(b1, b.y, b0 * a.y)), fm(b2, c.z, fm(b1, b.z, b0 * a.z))); };
+                f3 P = bary(tr.v0, tr.v1, tr.v2);
+                if (in) P = xform_point(in->m, P);
+                f3 Ng = cross(tr.v1 - tr.v0, tr.v2 - tr.v0);
+                if (in) Ng = xform_normal(in->inv, Ng);
+                Ng = normalize(Ng);
+                f3 N = Ng;
+                if (normals) {
+                    const float* nn = normals + 9 * (size_t)h.prim;
+                    N = bary(ld3(nn), ld3(nn + 3), ld3(nn + 6));
+                    if (in) N = xform_normal(in->inv, N);
+                    N = normalize(N);
+                }
+                const float bc[4] = {p->base_color[0] * 1.0f, p->base_color[1] * 1.0f, p->base_color[2] * 1.0f, p->base_color[3] * 1.0f};
+                const float metallic = p->metallic, roughness = p->roughness;
+                const float F0 = 0.04f, km = 1.0f - metallic;
+                const f3 diff_color = mk((bc[0] * (1.0f - F0)) * km, (bc[1] * (1.0f - F0)) * km, (bc[2] * (1.0f - F0)) * km);
+                const f3 spec_color = mk(fm(metallic, bc[0] - F0, F0), fm(metallic, bc[1] - F0, F0), fm(metallic, bc[2] - F0, F0));
+                const float alpha = roughness * roughness;
+                result = mk(fm(p->emissive[0], 1.0f, 0.0f), fm(p->emissive[1], 1.0f, 0.0f), fm(p->emissive[2], 1.0f, 0.0f));
+                if (dot(N, dir) > 0.0f) N = neg(N);
+                const f3 Vv = neg(normalize(dir));
+                for (int li = 0; li < p->nlights; ++li) {
+                    const LightRec& l = L[li];
+                    if (l.type == 0) {
+                        const f3 Lv = mk(l.position[0] - P.x, l.position[1] - P.y, l.position[2] - P.z);
+                        const float L_dist = length(Lv);
+                        const f3 Ld = mk(Lv.x / L_dist, Lv.y / L_dist, Lv.z / L_dist);
+                        const f3 H = normalize(Ld + Vv);
+                        const float N_dot_L = dot(N, Ld), N_dot_V = dot(N, Vv), N_dot_H = dot(N, H), V_dot_H = dot(Vv, H);
+                        if (N_dot_L > 0.0f && N_dot_V > 0.0f) {
+                            const float x1 = 1.0f - V_dot_H, x2 = x1 * x1, x5 = (x2 * x2) * x1;
+                            const f3 F = mk(fm(1.0f - spec_color.x, x5, spec_color.x), fm(1.0f - spec_color.y, x5, spec_color.y), fm(1.0f - spec_color.z, x5, spec_color.z));
+                            const float a2 = alpha * alpha;
+                            const float ggx0 = N_dot_L * sqrtf(fm(N_dot_V * N_dot_V, 1.0f - a2, a2));
+                            const float ggx1 = N_dot_V * sqrtf(fm(N_dot_L * N_dot_L, 1.0f - a2, a2));
+                            const float G_vis = ((2.0f * N_dot_L) * N_dot_V) / (ggx0 + ggx1);
+                            const float xx = fm(N_dot_H * N_dot_H, a2 - 1.0f, 1.0f);
+                            const float D = a2 / ((PI * xx) * xx);
+                            const f3 diff = mk(((1.0f - F.x) * diff_color.x) / PI, ((1.0f - F.y) * diff_color.y) / PI, ((1.0f - F.z) * diff_color.z) / PI);
+                            const f3 spec = mk((F.x * G_vis) * D, (F.y * G_vis) * D, (F.z * G_vis) * D);
+                            const float sx = (l.color[0] * l.intensity) * N_dot_L, sy = (l.color[1] * l.intensity) * N_dot_L, sz = (l.color[2] * l.intensity) * N_dot_L;
+                            const f3 term = mk(sx * (diff.x + spec.x), sy * (diff.y + spec.y), sz * (diff.z + spec.z));
+                            ++nrays[(size_t)tid];
+                            if (!trace_scene<true>(*s, P, Ld, 0.001f, L_dist - 0.001f, 0u).hit) result = result + term;
+                        }
+                    } else if (l.type == 1) {
+                        result = result + mk(l.color[0] * bc[0], l.color[1] * bc[1], l.color[2] * bc[2]);
+                    }
+                }
+            }
+            const size_t idx = (size_t)iy * p->width + ix;
+            if (p->subframe_index > 0) {
+                const float a = 1.0f / (float)(p->subframe_index + 1);
+                const f3 prev = ld3(accum + 4 * idx);
+                result = mk(fm(a, result.x - prev.x, prev.x), fm(a, result.y - prev.y, prev.y), fm(a, result.z - prev.z, prev.z));
+            }
+            accum[4 * idx] = result.x; accum[4 * idx + 1] = result.y; accum[4 * idx + 2] = result.z; accum[4 * idx + 3] = 1.0f;
+            if (frame) make_color(result, frame + 4 * idx);
+        }
+    });
+    uint64_t tot = 0;
+    for (auto v : nrays) tot += v;
+    return tot;
+}
+
+}  // extern "C"

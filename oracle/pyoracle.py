@@ -52,6 +52,8 @@ def lib():
         L.orc_playground.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, i32, u32, u32, i32, vp, vp, i32, i32, i32]
         L.orc_playground_scene.restype = C.c_uint64
         L.orc_playground_scene.argtypes = [u32, u32, vp, vp, vp, i32]
+        L.orc_whitted.restype = C.c_uint64
+        L.orc_whitted.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32]
         L.orc_pathtrace.restype = C.c_uint64
         L.orc_pathtrace.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
         _LIB = L
@@ -68,6 +70,12 @@ def _f32(a):
 
 def ncores():
     return len(os.sched_getaffinity(0))
+
+
+class WhittedParams(C.Structure):  # oracle.cpp: orc_whitted_params
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("subframe_index", C.c_uint32), ("eye", C.c_float * 3), ("U", C.c_float * 3),
+                ("V", C.c_float * 3), ("W", C.c_float * 3), ("miss_color", C.c_float * 3), ("base_color", C.c_float * 4), ("metallic", C.c_float),
+                ("roughness", C.c_float), ("emissive", C.c_float * 3), ("nlights", C.c_int32)]
 
 
 class PTParams(C.Structure):
@@ -177,6 +185,19 @@ class Scene:
         n = lib().orc_playground(self.h, _p(cam), _p(lights), nl, _p(mats), _p(nrm), _p(mi), width, height, spf, dt, int(bool(dirty)), _p(film), _p(image),
                                  y0, y1, threads or ncores())
         return film, image, int(n)
+
+    def whitted(self, params, lights36, normals=None, accum=None, rows=None, threads=None):
+        """optixMeshViewer frame for an untextured OPAQUE material (oracle.cpp: orc_whitted).  Returns (accum (h,w,4), frame (h,w,4) u8, rays)."""
+        w, h = params.width, params.height
+        if accum is None:
+            accum = np.zeros((h, w, 4), np.float32)
+        frame = np.zeros((h, w, 4), np.uint8)
+        lights = np.frombuffer(bytes(lights36), np.uint8).copy()
+        params.nlights = lights.size // 36
+        nn = None if normals is None else _f32(normals).reshape(-1)
+        y0, y1 = rows or (0, h)
+        n = lib().orc_whitted(self.h, C.byref(params), _p(nn), _p(lights), _p(accum), _p(frame), y0, y1, threads or ncores())
+        return accum, frame, int(n)
 
     def pathtrace(self, params, emission, diffuse, accum=None, region=None, threads=None, want_frame=True):
         """params: PTParams.  Returns (accum (h,w,4) f32, frame (h,w,4) u8, segments)."""

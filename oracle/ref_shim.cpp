@@ -134,4 +134,29 @@ int ref_params_layout(int* out)
     return n;
 }
 
+
+// MaterialData / Texture / Light / whitted::LaunchParams (SDK/cuda/MaterialData.h:34-140, SDK/cuda/Light.h:31-71, SDK/cuda/whitted.h:59-77)
+int ref_whitted_layout(int* out)
+{
+    int n = 0;
+    out[n++] = (int)sizeof(MaterialData); out[n++] = (int)offsetof(MaterialData, type); out[n++] = (int)offsetof(MaterialData, normal_tex);
+    out[n++] = (int)offsetof(MaterialData, alpha_mode); out[n++] = (int)offsetof(MaterialData, alpha_cutoff);
+    out[n++] = (int)offsetof(MaterialData, emissive_factor); out[n++] = (int)offsetof(MaterialData, emissive_tex);
+    out[n++] = (int)offsetof(MaterialData, doubleSided); out[n++] = (int)offsetof(MaterialData, pbr);
+    out[n++] = (int)offsetof(MaterialData::Pbr, base_color); out[n++] = (int)offsetof(MaterialData::Pbr, metallic);
+    out[n++] = (int)offsetof(MaterialData::Pbr, roughness); out[n++] = (int)offsetof(MaterialData::Pbr, base_color_tex);
+    out[n++] = (int)offsetof(MaterialData::Pbr, metallic_roughness_tex);
+    out[n++] = (int)sizeof(MaterialData::Texture); out[n++] = (int)offsetof(MaterialData::Texture, texcoord); out[n++] = (int)offsetof(MaterialData::Texture, tex);
+    out[n++] = (int)offsetof(MaterialData::Texture, texcoord_offset); out[n++] = (int)offsetof(MaterialData::Texture, texcoord_rotation);
+    out[n++] = (int)offsetof(MaterialData::Texture, texcoord_scale);
+    out[n++] = (int)sizeof(Light); out[n++] = (int)offsetof(Light, type); out[n++] = (int)offsetof(Light, point);
+    out[n++] = (int)offsetof(Light::Point, color); out[n++] = (int)offsetof(Light::Point, intensity); out[n++] = (int)offsetof(Light::Point, position);
+    out[n++] = (int)offsetof(Light::Point, falloff);
+    out[n++] = (int)sizeof(whitted::LaunchParams); out[n++] = (int)offsetof(whitted::LaunchParams, subframe_index);
+    out[n++] = (int)offsetof(whitted::LaunchParams, accum_buffer); out[n++] = (int)offsetof(whitted::LaunchParams, frame_buffer);
+    out[n++] = (int)offsetof(whitted::LaunchParams, eye); out[n++] = (int)offsetof(whitted::LaunchParams, U); out[n++] = (int)offsetof(whitted::LaunchParams, lights);
+    out[n++] = (int)offsetof(whitted::LaunchParams, miss_color); out[n++] = (int)offsetof(whitted::LaunchParams, handle);
+    return n;
+}
+
 }  // extern "C"

@@ -7,13 +7,20 @@ import numpy as np
 GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 
 
-def duck_scene():
-    """The reference's Duck.gltf as a host.load_gltf-shaped dict (from tests/golden/duck_mesh.npz)."""
+def duck_scene(textured=True):
+    """The reference's Duck.gltf as a host.load_gltf-shaped dict (from tests/golden/duck_mesh.npz): geometry, instance, camera, the
+    material (metallic 0, roughness 1, base-colour texture) and a 128x128 stand-in of its texture."""
     z = np.load(GOLDEN / "duck_mesh.npz")
-    prim = {"positions": z["positions"], "normals": z["normals"], "indices": z["indices"], "material": 0}
+    prim = {"positions": z["positions"], "normals": z["normals"], "indices": z["indices"], "material": 0, "texcoords": [z["texcoords0"], None]}
     mesh = {"primitives": [prim], "aabb": (z["aabb_lo"], z["aabb_hi"])}
     inst = {"transform": z["transform"], "mesh": 0, "world_aabb": (z["world_lo"], z["world_hi"])}
-    return {"meshes": [mesh], "instances": [inst]}
+    tex = {"index": 0, "texcoord": 0, "offset": [0.0, 0.0], "rotation": 0.0, "scale": [1.0, 1.0]}
+    mat = {"base_color": [1.0, 1.0, 1.0, 1.0], "metallic": 0.0, "roughness": 1.0, "base_color_tex": tex if textured else None,
+           "metallic_roughness_tex": None, "normal_tex": None, "emissive_tex": None, "emissive_factor": [0.0, 0.0, 0.0], "alpha_mode": 0,
+           "alpha_cutoff": 0.5, "double_sided": False}
+    return {"meshes": [mesh], "instances": [inst], "cameras": [{"eye": z["cam_eye"], "up": z["cam_up"], "fov_y": float(z["cam_fov_y"])}],
+            "materials": [mat], "images": [np.ascontiguousarray(z["texture_rgba8"])], "textures": [{"sampler": 0, "source": 0}],
+            "samplers": [{"magFilter": 9729, "minFilter": 9986, "wrapS": 10497, "wrapT": 10497}]}
 
 
 def deindex(prim):

@@ -129,3 +129,34 @@ def test_launch_struct_layouts_match_the_reference_headers():
     src = (pathlib.Path(__file__).resolve().parents[1] / "optix_raytracer_b200" / "csrc" / "raycast.cu").read_text()
     m = re.search(r"vi = \*\(const BufView\*\)\(rec \+ (\d+)\), vp = \*\(const BufView\*\)\(rec \+ (\d+)\), vn = \*\(const BufView\*\)\(rec \+ (\d+)\)", src)
     assert m and tuple(int(x) for x in m.groups()) == (hl["off_indices"], hl["off_positions"], hl["off_normals"])
+
+
+def test_whitted_struct_layouts_match_the_reference_headers():
+    """MaterialData / Texture / Light / whitted::LaunchParams offsets measured on the reference headers against host.pack_material,
+    host.WLaunchParams and the struct views csrc/whitted.cu static_asserts."""
+    import struct as st
+    torch = pytest.importorskip("torch")
+    from optix_raytracer_b200 import host
+    wl = KAT["whitted_layout"]
+    assert (wl["MaterialData"], wl["Texture"], wl["Light"], wl["LaunchParams"]) == (240, 40, 36, 128)
+    tex = {"index": 0, "texcoord": 1, "offset": [0.25, 0.5], "rotation": 0.0, "scale": [2.0, 3.0]}
+    m = {"base_color": [0.1, 0.2, 0.3, 0.4], "metallic": 0.6, "roughness": 0.7, "base_color_tex": tex, "metallic_roughness_tex": None, "normal_tex": tex,
+         "emissive_tex": None, "emissive_factor": [0.01, 0.02, 0.03], "alpha_mode": 1, "alpha_cutoff": 0.5, "double_sided": True}
+    b = host.pack_material(m, {0: 0xABCDEF})
+    assert len(b) == 240
+    pbr = wl["pbr"]
+    assert st.unpack_from("<4f", b, pbr + wl["pbr_base_color"]) == pytest.approx((0.1, 0.2, 0.3, 0.4))
+    assert st.unpack_from("<f", b, pbr + wl["pbr_metallic"])[0] == pytest.approx(0.6) and st.unpack_from("<f", b, pbr + wl["pbr_roughness"])[0] == pytest.approx(0.7)
+    assert st.unpack_from("<i", b, wl["alpha_mode"])[0] == 1 and st.unpack_from("<f", b, wl["alpha_cutoff"])[0] == 0.5
+    assert st.unpack_from("<3f", b, wl["emissive_factor"]) == pytest.approx((0.01, 0.02, 0.03)) and b[wl["doubleSided"]] == 1
+    for off in (wl["normal_tex"], pbr + wl["pbr_base_color_tex"]):
+        assert st.unpack_from("<i", b, off + wl["tex_texcoord"])[0] == 1 and st.unpack_from("<Q", b, off + wl["tex_tex"])[0] == 0xABCDEF
+        assert st.unpack_from("<2f", b, off + wl["tex_offset"]) == (0.25, 0.5) and st.unpack_from("<2f", b, off + wl["tex_scale"]) == (2.0, 3.0)
+        assert st.unpack_from("<2f", b, off + wl["tex_rotation"]) == (0.0, 1.0)  # (sin, cos)
+    assert st.unpack_from("<Q", b, wl["emissive_tex"] + wl["tex_tex"])[0] == 0 and st.unpack_from("<Q", b, pbr + wl["pbr_metallic_roughness_tex"] + wl["tex_tex"])[0] == 0
+    P = host.WLaunchParams
+    assert (P.subframe_index.offset, P.accum_buffer.offset, P.frame_buffer.offset, P.eye.offset, P.U.offset, P.lights_data.offset, P.miss_color.offset,
+            P.handle.offset) == (wl["lp_subframe_index"], wl["lp_accum_buffer"], wl["lp_frame_buffer"], wl["lp_eye"], wl["lp_U"], wl["lp_lights"],
+                                 wl["lp_miss_color"], wl["lp_handle"])
+    assert (wl["light_type"], wl["light_point"] + wl["point_color"], wl["light_point"] + wl["point_intensity"], wl["light_point"] + wl["point_position"],
+            wl["light_point"] + wl["point_falloff"]) == (0, 4, 16, 20, 32)

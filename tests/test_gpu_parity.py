@@ -209,3 +209,36 @@ def test_playground_bit_exact(ctx, orc, aperture, ortho):
         assert (got > 0).mean() > 0.9
         assert np.array_equal(got.view(np.uint32), film.view(np.uint32)), f"frame {frame}: film differs"
         assert np.abs(pg.image.cpu().numpy().astype(np.int32) - image.astype(np.int32)).max() <= 1
+
+
+def test_whitted_untextured_bit_exact(ctx, orc):
+    """optixMeshViewer (BASELINE.json configs[2]) on the Duck with its texture removed: accum bit-exact against the oracle over
+    two subframes (pixel-centre ray, then jittered + running mean), frame within 1 LSB.  Textured shading is compared on the
+    GPU against the reference programs on OptiX (tests/test_gpu_optix_parity.py)."""
+    from optix_raytracer_b200 import host
+    sc = common.duck_scene(textured=False)
+    w, h = 160, 120
+    mv = host.MeshViewer(ctx, sc, w, h)
+    prim = sc["meshes"][0]["primitives"][0]
+    tris, nrm = common.deindex(prim)
+    scene = orc.Scene(tris, None, instances=[sc["instances"][0]["transform"][:3, :].reshape(12)])
+    p = orc.WhittedParams()
+    p.width, p.height = w, h
+    for k in ("eye", "U", "V", "W", "miss_color"):
+        setattr(p, k, getattr(mv.params, k))
+    m = sc["materials"][0]
+    p.base_color = (C.c_float * 4)(*m["base_color"])
+    p.metallic, p.roughness = m["metallic"], m["roughness"]
+    p.emissive = (C.c_float * 3)(*m["emissive_factor"])
+    lights = mv.d_lights.cpu().numpy().tobytes()
+    accum = None
+    for sub in range(2):
+        mv.launch_subframe(sub)
+        torch.cuda.synchronize()
+        p.subframe_index = sub
+        accum, frame, nrays = scene.whitted(p, lights, normals=nrm, accum=accum)
+        got = mv.accum.cpu().numpy()
+        assert nrays > w * h and (got[..., :3] != np.float32(0.1)).any(axis=-1).mean() > 0.03  # the duck covers part of the image
+        assert np.array_equal(got.view(np.uint32), accum.view(np.uint32)), f"subframe {sub}: accum differs"
+        assert np.abs(mv.frame.cpu().numpy().astype(np.int32) - frame.astype(np.int32)).max() <= 1
+    mv.close()

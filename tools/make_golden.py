@@ -71,7 +71,7 @@ def main():
     ref.ref_light_normal(f3(0.0, 0.0, 105.0), f3(-130.0, 0.0, 0.0), n)
     out["cornell_light_normal_bits"] = [fbits(x) for x in n]
     # --- struct layouts of the launch ABI measured on the reference headers (oracle/ref_shim.cpp)
-    o = (ctypes.c_int * 32)()
+    o = (ctypes.c_int * 64)()
     k = ref.ref_hitgroup_layout(o)
     names = ["sizeof_HitGroupData", "sizeof_GeometryData", "sizeof_MaterialData", "off_indices", "off_positions", "off_normals", "off_texcoords0",
              "off_texcoords1", "off_colors", "sizeof_BufferView", "bv_off_data", "bv_off_count", "bv_off_byte_stride", "bv_off_elmt_byte_size",
@@ -119,6 +119,13 @@ def main():
         lights.append({"kind": kind, "a": a, "lumi": lumi, "scalar": scalar, "bytes": bytes(buf).hex(), "p": [0.1, 0.05, -0.2], "seed": 4242,
                        "seed_after": st.value, "wi_bits": [fbits(x) for x in wi], "lumi_bits": [fbits(x) for x in lm]})
     out["playground_lights"] = lights
+    k = ref.ref_whitted_layout(o)
+    names = ["MaterialData", "type", "normal_tex", "alpha_mode", "alpha_cutoff", "emissive_factor", "emissive_tex", "doubleSided", "pbr", "pbr_base_color",
+             "pbr_metallic", "pbr_roughness", "pbr_base_color_tex", "pbr_metallic_roughness_tex", "Texture", "tex_texcoord", "tex_tex", "tex_offset",
+             "tex_rotation", "tex_scale", "Light", "light_type", "light_point", "point_color", "point_intensity", "point_position", "point_falloff",
+             "LaunchParams", "lp_subframe_index", "lp_accum_buffer", "lp_frame_buffer", "lp_eye", "lp_U", "lp_lights", "lp_miss_color", "lp_handle"]
+    assert k == len(names)
+    out["whitted_layout"] = dict(zip(names, list(o[:k])))
     p = ROOT / "tests" / "golden" / "kat.json"
     p.write_text(json.dumps(out) + "\n")
     print("wrote", p, p.stat().st_size, "bytes")
