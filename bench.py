@@ -305,7 +305,8 @@ def run_b200rt(a, rank, world, local_rank):
     # algorithmic bytes of the trace stage: queue entry 4 + ray_d 16 + res 32 (RW) per active lane-iteration;
     # + ray_o 16 + hit 8 per radiance ray; + shd_o/shd_d/pend 48 per shadow ray; 80 B per node and 48 B per triangle fetched
     lane_iters = rad  # every lane-iteration with an extension ray; the few shadow-only visits are counted via shd
-    algo_bytes = lane_iters * (4 + 16 + 32 + 16 + 8) + shd * 48 + nodes * 80 + tris * 48
+    node_bytes = int(info.reserved) or 80  # 80: 8-bit boxes (large scenes), 224: fp32 boxes (cache-resident scenes)
+    algo_bytes = lane_iters * (4 + 16 + 32 + 16 + 8) + shd * 48 + nodes * node_bytes + tris * 48
     achieved = algo_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "pt_trace_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
@@ -318,7 +319,7 @@ def run_b200rt(a, rank, world, local_rank):
         out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
-               "config": {"workload": workload_name(a), "triangles": int(info.num_triangles), "bvh8_nodes": int(info.num_nodes),
+               "config": {"workload": workload_name(a), "triangles": int(info.num_triangles), "bvh8_nodes": int(info.num_nodes), "bvh8_node_bytes": int(info.reserved) or 80,
                           "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl,
                           "parallelism": f"image split x{world} (StaticWorkDistribution 8x4 tiles), scene replicated" + (", ncclAllGather" if world > 1 else ""),
                           "l2": ("inputs larger than L2: accel %.2f GB vs L2 %.0f MB" % (scene_bytes / 1e9, l2_bytes / 1e6)) if flush is None

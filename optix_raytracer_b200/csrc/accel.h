@@ -6,6 +6,12 @@
 //   GAS:  [AccelHeader 128 B][Node8 x num_nodes (80 B each)][TriRecord x num_tris (48 B each)]
 //   IAS:  [AccelHeader 128 B][InstanceRecord x num_instances (128 B each)]
 //
+// Two node encodings share the topology fields (child base, triangle base, 8 meta bytes, inner mask, octant-ordered slots):
+//   Node8  (80 B)  child boxes quantised to 8 bits — for scenes whose BVH does not fit the caches: every node visit moves 80 B,
+//                  at the price of decoding 48 bytes per visit;
+//   Node8F (224 B) child boxes as fp32 offsets from the node origin, plane-major ([lo x][lo y][lo z][hi x][hi y][hi z], 8 floats
+//                  each) — for cache-resident scenes, where the traversal is issue-bound and the decode is the larger half of a
+//                  node visit (profiles/r01_trace_v3.md).  The builder picks by triangle count (bvh_build.cu: choose_node_bytes).
 // Node8 is an 8-wide BVH node with child boxes quantised to 8 bits on a per-node power-of-two grid
 // (compressed wide BVH, Ylitie/Karras/Laine 2017), fetched as 5 x 16-byte loads.  TriRecord is
 // three float4: the xyz are the object-space vertices exactly as supplied (the watertight test runs
@@ -18,7 +24,7 @@ namespace b200rt {
 
 constexpr uint32_t ACCEL_MAGIC = 0x54523242u;  // "B2RT"
 constexpr uint32_t ACCEL_KIND_GAS = 1, ACCEL_KIND_IAS = 2;
-constexpr uint32_t NODE8_BYTES = 80, TRI_BYTES = 48, INSTREC_BYTES = 128, HEADER_BYTES = 128;
+constexpr uint32_t NODE8_BYTES = 80, NODE8F_BYTES = 224, TRI_BYTES = 48, INSTREC_BYTES = 128, HEADER_BYTES = 128;
 
 struct AccelHeader {
     uint32_t magic;
@@ -34,7 +40,8 @@ struct AccelHeader {
     uint64_t inst_off;
     uint32_t max_nodes;      // node capacity of this (uncompacted) blob
     uint32_t error;          // builder overflow flag
-    uint32_t pad[10];
+    uint32_t node_bytes;     // 80: Node8 (8-bit quantised child boxes); 224: Node8F (fp32 child boxes), see below
+    uint32_t pad[9];
 };
 static_assert(sizeof(AccelHeader) == HEADER_BYTES, "header must be 128 bytes");
 

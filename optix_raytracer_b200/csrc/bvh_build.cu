@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
                                                              const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
                                                              const int2* __restrict__ range, const int* __restrict__ child_tmp,
                                                              const unsigned long long* __restrict__ excl, uint32_t* __restrict__ next_work,
-                                                             uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out, LevelInfo* info)
+                                                             uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out, LevelInfo* info, uint32_t node_bytes)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwork) return;
@@ -549,18 +549,26 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
     }
     uint32_t imask = 0;
     uint32_t meta[8], qlo[3][8], qhi[3][8];
+    float flo[3][8], fhi[3][8];  // Node8F: offsets from P, rounded outwards
     uint32_t int_k = 0, tri_off = 0;
     for (int s = 0; s < 8; ++s) {
         const int k = child_in_slot[s];
         meta[s] = 0;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; }
+        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; flo[a][s] = 0.0f; fhi[a][s] = 0.0f; }
         if (k < 0) continue;
         const int id = ids[k];
         const float lo3[3] = {clo[k].x - pad, clo[k].y - pad, clo[k].z - pad};
         const float hi3[3] = {chi[k].x + pad, chi[k].y + pad, chi[k].z + pad};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
+            if (node_bytes == NODE8F_BYTES) {
+                // plane = P + off in exact arithmetic (the traversal evaluates (P + off - o) / d as fma(off, 1/d, (P - o) * (1/d)) and
+                // never forms P + off in floating point): rounding the differences outwards keeps the padded box enclosed
+                flo[a][s] = __fsub_rd(lo3[a], Pa[a]);
+                fhi[a][s] = __fsub_ru(hi3[a], Pa[a]);
+                continue;
+            }
             int ql = (int)floorf((lo3[a] - Pa[a]) / scale[a]);
             ql = min(max(ql, 0), 255);
             while (ql > 0 && fm((float)ql, scale[a], Pa[a]) > lo3[a]) --ql;
@@ -586,6 +594,19 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
         }
     }
     auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    if (node_bytes == NODE8F_BYTES) {
+        uint4* out = nodes_out + (size_t)node_index * (NODE8F_BYTES / 16);
+        out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), imask);
+        out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            out[2 + 2 * a] = make_uint4(__float_as_uint(flo[a][0]), __float_as_uint(flo[a][1]), __float_as_uint(flo[a][2]), __float_as_uint(flo[a][3]));
+            out[3 + 2 * a] = make_uint4(__float_as_uint(flo[a][4]), __float_as_uint(flo[a][5]), __float_as_uint(flo[a][6]), __float_as_uint(flo[a][7]));
+            out[8 + 2 * a] = make_uint4(__float_as_uint(fhi[a][0]), __float_as_uint(fhi[a][1]), __float_as_uint(fhi[a][2]), __float_as_uint(fhi[a][3]));
+            out[9 + 2 * a] = make_uint4(__float_as_uint(fhi[a][4]), __float_as_uint(fhi[a][5]), __float_as_uint(fhi[a][6]), __float_as_uint(fhi[a][7]));
+        }
+        return;
+    }
     uint4* out = nodes_out + (size_t)node_index * 5;
     out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
     out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
@@ -673,11 +694,23 @@ struct BuildPlan {
     size_t off_inputs, off_flags, off_bounds, off_level, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box_lo, off_box_hi,
         off_parent, off_range, off_arrive, off_dest, off_hist, off_scan_tmp, off_work0, off_work1, off_child_tmp, off_counts, off_last;
     size_t temp_bytes = 0, out_bytes = 0;
+    uint32_t node_bytes = NODE8_BYTES;
 };
 
 static uint32_t count_tris(const b200rt_build_input_triangle_array& t)
 {
     return t.indexFormat != B200RT_INDICES_FORMAT_NONE && t.indexBuffer ? t.numIndexTriplets : t.numVertices / 3;
+}
+
+// Node encoding by scene size: fp32 child boxes while nodes + triangles stay within about half of the 126 MB L2 (the traversal
+// is then issue-bound and skipping the 8-bit decode roughly halves a node visit), 8-bit boxes beyond (HBM-bound: 80 B per visit).
+// B200RT_NODE_FORMAT=q8|f32 overrides (A/B measurements, tests of both encodings).
+static uint32_t choose_node_bytes(uint64_t ntris)
+{
+    const char* e = getenv("B200RT_NODE_FORMAT");
+    if (e && !strcmp(e, "q8")) return NODE8_BYTES;
+    if (e && !strcmp(e, "f32")) return NODE8F_BYTES;
+    return ntris <= 600000ull ? NODE8F_BYTES : NODE8_BYTES;
 }
 
 static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsigned num_inputs, BuildPlan& p)
@@ -729,7 +762,8 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.off_child_tmp = take(4 * 8 * W);
     p.off_counts = take(8 * W);
     p.temp_bytes = off;
-    p.out_bytes = align_up(HEADER_BYTES + (size_t)p.max_nodes * NODE8_BYTES + (size_t)n * TRI_BYTES, 128);
+    p.node_bytes = choose_node_bytes(n);
+    p.out_bytes = align_up(HEADER_BYTES + (size_t)p.max_nodes * p.node_bytes + (size_t)n * TRI_BYTES, 128);
     return 0;
 }
 
@@ -896,7 +930,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 const uint32_t next_level_start = level_start + nwork;
                 collapse_emit_kernel<<<div_up(nwork, 128), 128, 0, s>>>(nwork, level_start, next_level_start, tri_cursor, p.max_nodes, (int)N,
                                                                          box_lo, box_hi, range, child_tmp, counts, work[wcur ^ 1], dest,
-                                                                         nodes_out, d_level);
+                                                                         nodes_out, d_level, p.node_bytes);
                 B2_LAUNCH_CHECK(ctx);
                 B2_CUDA(ctx, cudaMemcpyAsync(h_level, d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, s));
                 B2_CUDA(ctx, cudaStreamSynchronize(s));
@@ -912,7 +946,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             }
             if (tri_cursor != N) return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: triangle count mismatch (%u != %u)", tri_cursor, N);
             // triangles go right after the node capacity region; compaction later closes the gap
-            hv.tris_off = HEADER_BYTES + (uint64_t)p.max_nodes * NODE8_BYTES;
+            hv.tris_off = HEADER_BYTES + (uint64_t)p.max_nodes * p.node_bytes;
             scatter_tris_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], dest, N, (float4*)(out + hv.tris_off));
             B2_LAUNCH_CHECK(ctx);
         } else {
@@ -920,7 +954,8 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         }
         hv.num_nodes = total_nodes;
         hv.depth = depth;
-        hv.total_bytes = HEADER_BYTES + (uint64_t)total_nodes * NODE8_BYTES + (uint64_t)N * TRI_BYTES;
+        hv.node_bytes = p.node_bytes;
+        hv.total_bytes = HEADER_BYTES + (uint64_t)total_nodes * p.node_bytes + (uint64_t)N * TRI_BYTES;
         exact_bytes = hv.total_bytes;
         write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds);
         B2_LAUNCH_CHECK(ctx);
@@ -954,7 +989,7 @@ int accel_compact(b200rt_context ctx, cudaStream_t s, b200rt_traversable input, 
     if (h.kind == ACCEL_KIND_IAS) {
         B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, h.total_bytes, cudaMemcpyDeviceToDevice, s));
     } else {
-        const size_t node_bytes = (size_t)h.num_nodes * NODE8_BYTES;
+        const size_t node_bytes = (size_t)h.num_nodes * (h.node_bytes ? h.node_bytes : NODE8_BYTES);
         B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, HEADER_BYTES + node_bytes, cudaMemcpyDeviceToDevice, s));
         B2_CUDA(ctx, cudaMemcpyAsync((void*)(out + HEADER_BYTES + node_bytes), (const void*)(input + h.tris_off),
                                      (size_t)h.num_tris * TRI_BYTES, cudaMemcpyDeviceToDevice, s));
@@ -979,7 +1014,7 @@ int accel_get_info(b200rt_context ctx, b200rt_traversable handle, b200rt_accel_i
     info->total_bytes = h.total_bytes;
     memcpy(info->bounds, h.bounds, sizeof(h.bounds));
     info->depth = h.depth;
-    info->reserved = 0;
+    info->reserved = h.kind == ACCEL_KIND_GAS ? (h.node_bytes ? h.node_bytes : NODE8_BYTES) : 0;  // bytes per wide node (80 or 224)
     return 0;
 }
 

@@ -46,6 +46,7 @@ constexpr int RAY_S_STRIDE = 9;        // odd stride: lanes reading different ow
 constexpr uint32_t TP_ANY = 1u << 16;        // any-hit (terminate on first hit)
 constexpr uint32_t TP_FOUND = 1u << 17;      // a hit was accepted in the GAS currently being traversed (tie-break scope)
 constexpr uint32_t TP_FOUND_ANY = 1u << 18;  // a hit was accepted in any instance so far
+constexpr uint32_t TP_F32 = 1u << 19;        // the GAS being traversed has Node8F nodes (fp32 child boxes, 224 B)
 
 struct Trav {
     const uint4* nodes;
@@ -83,7 +84,8 @@ __device__ __forceinline__ void trav_begin(Trav& s, float* __restrict__ my_ray, 
     s.idx = fdiv(1.0f, bx); s.idy = fdiv(1.0f, by); s.idz = fdiv(1.0f, bz);
     const uint32_t nx = bx < 0.0f, ny = by < 0.0f, nz = bz < 0.0f;
     const uint32_t oct = (nx << 2) | (ny << 1) | nz;
-    s.pack = (uint32_t)tr.kx | ((uint32_t)tr.ky << 2) | ((uint32_t)tr.kz << 4) | ((7u - oct) << 8) | (nx << 11) | (ny << 12) | (nz << 13) | keep_flags;
+    s.pack = (uint32_t)tr.kx | ((uint32_t)tr.ky << 2) | ((uint32_t)tr.kz << 4) | ((7u - oct) << 8) | (nx << 11) | (ny << 12) | (nz << 13) | keep_flags |
+             (gas->node_bytes == NODE8F_BYTES ? TP_F32 : 0u);
     s.tmin = tmin;
     s.ngroup = gas->num_tris ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
     s.tgroup = make_uint2(0u, 0u);
@@ -121,7 +123,7 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
 }
 
 // One node visit; returns the triangle group of the visited node (mask 0 = none).
-__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st)
+__device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ stack, TravStats* st)
 {
     const uint32_t hits_imask = s.ngroup.y;
     const uint32_t bit = 31u - __clz(hits_imask);
@@ -181,6 +183,69 @@ __device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ sta
     }
     s.ngroup = make_uint2(n1.x, (hitmask & NODE_BITS) | (e_imask >> 24));
     return make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// Node8F visit: the child planes are fp32 offsets from the node origin, stored plane-major; the near / far plane arrays are picked
+// by ADDRESS from the ray's direction signs, so there is neither a decode nor a select per plane — 6 FFMA + 4 FMNMX per child.
+__device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__ stack, TravStats* st)
+{
+    const uint32_t hits_imask = s.ngroup.y;
+    const uint32_t bit = 31u - __clz(hits_imask);
+    const uint32_t child_base = s.ngroup.x;
+    s.ngroup.y &= ~(1u << bit);
+    if (s.ngroup.y & NODE_BITS) {
+        if (s.sp < TRAV_STACK) stack[s.sp++] = s.ngroup;
+    }
+    const uint32_t octinv = (s.pack >> 8) & 7u;
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
+    const uint4* np = s.nodes + (size_t)(child_base + rel) * (NODE8F_BYTES / 16u);
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1);
+    if (st) st->nodes++;
+    const float aox = (__uint_as_float(n0.x) - s.ox) * s.idx, aoy = (__uint_as_float(n0.y) - s.oy) * s.idy, aoz = (__uint_as_float(n0.z) - s.oz) * s.idz;
+    const float tfar = s.best.t, tmin = s.tmin;
+    // plane arrays (uint4 units): lo x/y/z at 2/4/6, hi x/y/z at 8/10/12
+    const float4* xn = (const float4*)(np + (((s.pack >> 11) & 1u) ? 8u : 2u));
+    const float4* xf = (const float4*)(np + (((s.pack >> 11) & 1u) ? 2u : 8u));
+    const float4* yn = (const float4*)(np + (((s.pack >> 12) & 1u) ? 10u : 4u));
+    const float4* yf = (const float4*)(np + (((s.pack >> 12) & 1u) ? 4u : 10u));
+    const float4* zn = (const float4*)(np + (((s.pack >> 13) & 1u) ? 12u : 6u));
+    const float4* zf = (const float4*)(np + (((s.pack >> 13) & 1u) ? 6u : 12u));
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = byte_mask_from_bit4(is_inner4);
+        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const float4 vxn = __ldg(xn + half), vxf = __ldg(xf + half), vyn = __ldg(yn + half), vyf = __ldg(yf + half), vzn = __ldg(zn + half),
+                     vzf = __ldg(zf + half);
+        const float axn[4] = {vxn.x, vxn.y, vxn.z, vxn.w}, axf[4] = {vxf.x, vxf.y, vxf.z, vxf.w};
+        const float ayn[4] = {vyn.x, vyn.y, vyn.z, vyn.w}, ayf[4] = {vyf.x, vyf.y, vyf.z, vyf.w};
+        const float azn[4] = {vzn.x, vzn.y, vzn.z, vzn.w}, azf[4] = {vzf.x, vzf.y, vzf.z, vzf.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tnx = fm(axn[j], s.idx, aox), tfx = fm(axf[j], s.idx, aox);
+            const float tny = fm(ayn[j], s.idy, aoy), tfy = fm(ayf[j], s.idy, aoy);
+            const float tnz = fm(azn[j], s.idz, aoz), tfz = fm(azf[j], s.idz, aoz);
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
+            if (cmin <= cmax * BOX_SLACK) {
+                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+                const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= cb << bi;
+            }
+        }
+    }
+    s.ngroup = make_uint2(n1.x, (hitmask & NODE_BITS) | (n0.w & 0xffu));
+    return make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st)
+{
+    return (s.pack & TP_F32) ? trav_node_step_f32(s, stack, st) : trav_node_step_q8(s, stack, st);
 }
 
 // Arithmetic of tri_test (traverse.cuh) for one (ray, triangle) unit, without the acceptance bookkeeping: returns

@@ -73,10 +73,11 @@ def decode_gas(blob):
     num_tris, num_nodes = int(hdr[2]), int(hdr[3])
     nodes_off, tris_off, total = [int(x) for x in np.frombuffer(blob[16:40].tobytes(), dtype=np.uint64)]
     bounds = np.frombuffer(blob[40:64].tobytes(), dtype=np.float32)
-    nodes = np.frombuffer(blob[nodes_off:nodes_off + 80 * num_nodes].tobytes(), dtype=np.uint8).reshape(num_nodes, 80)
+    node_bytes = int(hdr[22]) or 80   # AccelHeader::node_bytes: 80 = Node8 (8-bit boxes), 224 = Node8F (fp32 boxes)
+    nodes = np.frombuffer(blob[nodes_off:nodes_off + node_bytes * num_nodes].tobytes(), dtype=np.uint8).reshape(num_nodes, node_bytes)
     tris = np.frombuffer(blob[tris_off:tris_off + 48 * num_tris].tobytes(), dtype=np.float32).reshape(num_tris, 3, 4)
     return {"num_tris": num_tris, "num_nodes": num_nodes, "nodes": nodes, "tris": tris, "bounds": bounds, "total_bytes": total,
-            "depth": int(hdr[18])}
+            "depth": int(hdr[17]), "node_bytes": node_bytes}
 
 
 def validate_gas(gas, pad_check=True):
@@ -99,12 +100,19 @@ def validate_gas(gas, pad_check=True):
         max_depth = max(max_depth, depth)
         raw = nodes[ni]
         P = raw[0:12].view(np.float32).astype(np.float64)
-        e = raw[12:15].astype(np.int64)
-        imask = int(raw[15])
         child_base, tri_base = [int(x) for x in raw[16:24].view(np.uint32)]
         meta = raw[24:32]
-        q = raw[32:80].reshape(6, 8).astype(np.float64)  # qlo x,y,z ; qhi x,y,z
-        scale = np.ldexp(1.0, e - 127)
+        if gas.get("node_bytes", 80) == 224:
+            # Node8F: [P, imask][child_base, tri_base, meta][lo x|y|z: 8 floats each][hi x|y|z: 8 floats each], offsets from P
+            imask = int(raw[12])
+            planes = raw[32:224].view(np.float32).astype(np.float64).reshape(6, 8)
+            q = planes
+            scale = np.ones(3)
+        else:
+            e = raw[12:15].astype(np.int64)
+            imask = int(raw[15])
+            q = raw[32:80].reshape(6, 8).astype(np.float64)  # qlo x,y,z ; qhi x,y,z
+            scale = np.ldexp(1.0, e - 127)
         for s in range(8):
             m = int(meta[s])
             if m == 0:

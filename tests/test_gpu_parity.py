@@ -37,8 +37,10 @@ def _assert_hits_equal(got, ref, what):
         assert bad.size == 0, f"{what}: {bad.size} rays differ in {k}; first {bad[:5]}: got {got[k][hit][bad[:5]] if k!='t' else got[k][bad[:5]]} ref {ref[k][hit][bad[:5]] if k!='t' else ref[k][bad[:5]]}"
 
 
-def test_cornell_random_rays_closest_and_any(ctx, orc):
+@pytest.mark.parametrize("node_format", ["q8", "f32"])
+def test_cornell_random_rays_closest_and_any(ctx, orc, node_format, monkeypatch):
     from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
     pt = host.PathTracer(ctx, 32, 32, 1)
     sc = pt.scene
     scene = orc.Scene(sc["vertices"].reshape(-1, 3, 3), sc["mat_indices"])
@@ -115,9 +117,11 @@ def test_duck_raycast_bit_exact(ctx, orc):
         assert np.array_equal(img.view(np.uint32), orc.raycast_shade(ref_hits).view(np.uint32))
 
 
-def test_triangle_soup_bvh_vs_oracle(ctx, orc):
-    """A random soup big enough for a multi-level wide BVH, including degenerate and duplicate triangles."""
+@pytest.mark.parametrize("node_format", ["q8", "f32"])
+def test_triangle_soup_bvh_vs_oracle(ctx, orc, node_format, monkeypatch):
+    """A random soup big enough for a multi-level wide BVH, including degenerate and duplicate triangles; both node encodings."""
     from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
     rng = np.random.default_rng(7)
     n = 30_000
     c = rng.random((n, 1, 3), dtype=np.float32) * 10
@@ -135,10 +139,12 @@ def test_triangle_soup_bvh_vs_oracle(ctx, orc):
     _assert_hits_equal(got, ref, "soup")
 
 
-def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc):
+@pytest.mark.parametrize("node_format", ["q8", "f32"])
+def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc, node_format, monkeypatch):
     """The procedural scene of BASELINE.json configs[4]: device generator == oracle restatement bit for bit,
     the built BVH satisfies the structural invariants, and path tracing it (optixMultiGPU programs) is bit-exact."""
     from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
     T = 200_000
     verts, mats = host.synthetic_mesh(ctx, T, 0)
     torch.cuda.synchronize()
@@ -166,8 +172,11 @@ def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc):
     assert np.array_equal(img.view(np.uint32), ref_accum.view(np.uint32))
 
 
-def test_bvh_invariants_and_compaction(ctx):
+@pytest.mark.parametrize("node_format", ["q8", "f32"])
+def test_bvh_invariants_and_compaction(ctx, node_format, monkeypatch):
+    """Both node encodings (accel.h): Node8 with 8-bit boxes and Node8F with fp32 boxes (forced through B200RT_NODE_FORMAT)."""
     from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
     rng = np.random.default_rng(3)
     for n in (1, 2, 3, 4, 5, 33, 1000):
         tris = (rng.random((n, 3, 3), dtype=np.float32) * 4).astype(np.float32)
@@ -180,7 +189,7 @@ def test_bvh_invariants_and_compaction(ctx):
         common.validate_gas(gb)
         assert np.array_equal(ga["nodes"], gb["nodes"]) and np.array_equal(ga["tris"].view(np.uint32), gb["tris"].view(np.uint32))
         assert b.buf.numel() <= a.buf.numel()
-        assert gb["total_bytes"] == 128 + 80 * gb["num_nodes"] + 48 * n
+        assert gb["total_bytes"] == 128 + gb["node_bytes"] * gb["num_nodes"] + 48 * n
 
 
 @pytest.mark.parametrize("aperture,ortho", [(0.0, False), (0.05, False), (0.0, True)])

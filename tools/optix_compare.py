@@ -180,6 +180,49 @@ def main():
 
     checkpoint()
 
+    # ---- 3b. optixMeshViewer (whitted.cu) on the textured Duck, 1920x1080 ------------------------------------------------------
+    sc = common.duck_scene()
+    bmv, omv = host.MeshViewer(bctx, sc, 1920, 1080), host.MeshViewer(octx, sc, 1920, 1080)
+    for sub in range(4):
+        bmv.launch_subframe(sub); omv.launch_subframe(sub)
+    torch.cuda.synchronize()
+    ab, ao = bmv.accum.cpu().numpy()[..., :3].astype(np.float64), omv.accum.cpu().numpy()[..., :3].astype(np.float64)
+    fb, fo = bmv.frame.cpu().numpy()[..., :3].astype(np.float64), omv.frame.cpu().numpy()[..., :3].astype(np.float64)
+    mse8 = np.mean((fb - fo) ** 2)
+    tb = cuda_ms(lambda: bmv.launch_subframe(5))
+    to = cuda_ms(lambda: omv.launch_subframe(5))
+    rep["whitted_duck_1920x1080"] = {"subframes_compared": 4, "rel_mean_diff": float(abs(ab.mean() - ao.mean()) / ao.mean()),
+                                     "rmse_accum": float(np.sqrt(np.mean((ab - ao) ** 2))), "psnr_u8_db": float(10 * np.log10(255.0 ** 2 / max(mse8, 1e-12))),
+                                     "ms_per_subframe_b200rt": tb, "ms_per_subframe_optix": to, "speedup": to / tb,
+                                     "Msamples_s_b200rt": 1920 * 1080 / tb / 1e3, "Msamples_s_optix": 1920 * 1080 / to / 1e3}
+    bmv.close(); omv.close()
+    del bmv, omv
+    checkpoint()
+
+    # ---- 3c. imgui_test (optixTriangle.cu), 1920x1080, stand-in scene of 1.74 M triangles, two cameras x two apertures ------------
+    pgr = {}
+    for name, cam_kw in (("reference_camera", {}), ("close_camera", {"eye": (0.5, 0.7, -1.4), "up": (0.0, 1.0, 0.000073), "lookat": (0.0, 0.1, 0.0), "fov": 50.0})):
+        for ap in (0.0, 0.05):
+            cam = host.playground_camera(aperture=ap, **cam_kw)
+            bp = host.Playground(bctx, 1920, 1080, spf=8, rows=132, camera=cam)
+            op = host.Playground(octx, 1920, 1080, spf=8, rows=132, camera=cam)
+            bp.launch_frame(dirty=True); op.launch_frame(dirty=True)
+            torch.cuda.synchronize()
+            fb, fo = bp.film.cpu().numpy().astype(np.float64), op.film.cpu().numpy().astype(np.float64)
+            ib, io = bp.image.cpu().numpy()[..., :3].astype(np.float64), op.image.cpu().numpy()[..., :3].astype(np.float64)
+            mse8 = np.mean((ib - io) ** 2)
+            tb = cuda_ms(lambda: bp.launch_frame(dirty=True), reps=3, warm=1)
+            to = cuda_ms(lambda: op.launch_frame(dirty=True), reps=3, warm=1)
+            hit_frac = float((np.abs(fo / 8 - np.clip(fo / 8, 0, 1)) < 1).mean())
+            pgr[f"{name}_aperture_{ap}"] = {"triangles": bp.num_triangles, "spf": 8, "rel_mean_diff": float(abs(fb.mean() - fo.mean()) / fo.mean()),
+                                            "psnr_u8_db": float(10 * np.log10(255.0 ** 2 / max(mse8, 1e-12))), "ms_per_frame_b200rt": tb,
+                                            "ms_per_frame_optix": to, "speedup": to / tb, "Msamples_s_b200rt": 1920 * 1080 * 8 / tb / 1e3,
+                                            "Msamples_s_optix": 1920 * 1080 * 8 / to / 1e3}
+            del bp, op
+            torch.cuda.empty_cache()
+    rep["playground_1920x1080"] = pgr
+    checkpoint()
+
     # ---- 4. synthetic mesh (BASELINE.json configs[4]): build + launch timing, optixMultiGPU programs ---------
     if not a.skip_synth:
         del bpt, opt, bpt2, b1, b2, o1
