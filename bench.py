@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spl", type=int, default=16)
+    ap.add_argument("--sample-groups", type=int, default=4, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -113,6 +114,7 @@ def oracle_scene_and_params(a):
     p = orc.PTParams()
     p.subframe_index, p.width, p.height, p.samples_per_launch, p.nmat = 0, a.width, a.height, a.spl, 4
     p.mode = 1 if a.workload == "synthetic" else 0
+    p.groups = a.sample_groups
     f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
     p.eye, p.U, p.V, p.W = f3(cam["eye"]), f3(U), f3(V), f3(W)
     p.light_corner, p.light_v1, p.light_v2 = f3(lt["corner"]), f3(lt["v1"]), f3(lt["v2"])
@@ -198,6 +200,7 @@ def run_b200rt(a, rank, world, local_rank):
     e0, e1 = ev(), ev()
     e0.record()
     pt = host.PathTracer(ctx, a.width, a.height, a.spl, vertices=verts, mat_indices=mats, multigpu=multigpu)
+    pt.sample_groups = a.sample_groups
     e1.record()
     torch.cuda.synchronize()
     build_ms = e0.elapsed_time(e1)
@@ -320,7 +323,7 @@ def run_b200rt(a, rank, world, local_rank):
                "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_name(a), "triangles": int(info.num_triangles), "bvh8_nodes": int(info.num_nodes), "bvh8_node_bytes": int(info.reserved) or 80,
-                          "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl,
+                          "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl, "sample_groups": a.sample_groups,
                           "parallelism": f"image split x{world} (StaticWorkDistribution 8x4 tiles), scene replicated" + (", ncclAllGather" if world > 1 else ""),
                           "l2": ("inputs larger than L2: accel %.2f GB vs L2 %.0f MB" % (scene_bytes / 1e9, l2_bytes / 1e6)) if flush is None
                                 else "L2 flushed between timed steps (1.5x L2 fill)",

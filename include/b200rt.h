@@ -227,7 +227,10 @@ typedef struct b200rt_pt_stats {
 #define B200RT_PT_STATS_TIMING 2u     /* bracket every stage kernel with CUDA events on `stream` (profiling pass) */
 #define B200RT_PT_STATS_TRAVERSAL 4u  /* run the instrumented trace kernel that counts nodes / triangles (not for timing) */
 typedef struct b200rt_pt_options {
-    uint32_t reserved0;
+    uint32_t sample_groups;      /* 0 / 1: one lane per launch index runs its samples_per_launch samples back to back — the reference's
+                                  * flat fp32 summation order.  G > 1: G lanes per launch index run samples [g*spl/G, (g+1)*spl/G) in parallel
+                                  * (same RNG streams) and the pixel value is ((s_0 + s_1) + ...) + s_{G-1} of their sums: G x fewer, G x
+                                  * wider wavefront iterations; differs from G = 1 only in that summation order (~1 ulp). */
     uint32_t collect_stats;      /* bit mask of B200RT_PT_STATS_*; non-zero fills *stats */
     b200rt_pt_stats* stats;      /* host pointer or NULL */
 } b200rt_pt_options;
@@ -262,8 +265,10 @@ int b200rt_deinterleave(b200rt_context ctx, b200rt_stream stream, b200rt_devicep
  * (SDK/cuda/Light.h:31-71).  SBT: as sutil::Scene::createSBT builds it (SDK/sutil/Scene.cpp:1405-1433) — per primitive group a
  * radiance and an occlusion record, each carrying whitted::HitGroupData {GeometryData, MaterialData}; MaterialData textures are
  * cudaTextureObject_t handles and are sampled with tex2D like the reference does.
- * Scope: OPAQUE materials; a launch that hits a MASK / BLEND material returns B200RT_ERROR_NOT_SUPPORTED (the any-hit programs
- * whitted.cu:100-137 are not built yet).  Synchronises `stream` (Params read-back, support check). */
+ * Scope: OPAQUE materials (the any-hit programs whitted.cu:100-137 are not built yet).  Errors found by the kernels — a MASK /
+ * BLEND material was hit (rendered as opaque), or LaunchParams grew more lights than the launch's workspace was sized for — are
+ * asynchronous like CUDA's: the NEXT launch on the context returns B200RT_ERROR_NOT_SUPPORTED / B200RT_ERROR_INVALID_OPERATION.
+ * The first launch with a given d_params reads it back once (synchronises `stream`); later launches are fully asynchronous. */
 int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
                           const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height);
 

@@ -131,6 +131,7 @@ int b200rt_context_create(int cuda_device, b200rt_log_cb cb, void* cbdata, int l
         delete ctx;
         return B200RT_ERROR_CUDA_ERROR;
     }
+    memset(ctx->pinned, 0, 4096);  // counter read-back area + the asynchronous launch-error flags the kernels write (whitted.cu)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     log_msg(ctx, 4, "context", "device %d: %s, %d SMs, L2 %zu MiB", cuda_device, prop.name, ctx->sm_count, ctx->l2_bytes >> 20);

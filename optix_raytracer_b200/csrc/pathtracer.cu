@@ -62,6 +62,7 @@ struct HitGroupData { float3 emission_color; float3 diffuse_color; const float4*
 // unified view of the two Params structs, built on the device at the top of every stage kernel
 struct Frame {
     unsigned int subframe, width, height, spl, device_idx;
+    unsigned int groups, nlaunch;  // sample groups per launch index (1 = the reference's flat summation order) and launch indices
     float3 eye, U, V, W;
     ParallelogramLight light;
     const AccelHeader* handle;
@@ -70,9 +71,10 @@ struct Frame {
     const int2* sample_index;
 };
 template <int MODE>
-__device__ __forceinline__ Frame load_frame(const void* p)
+__device__ __forceinline__ Frame load_frame(const void* p, uint32_t groups, uint32_t nlaunch)
 {
     Frame f;
+    f.groups = groups; f.nlaunch = nlaunch;
     if (MODE == 0) {
         const PTParams* q = (const PTParams*)p;
         f.subframe = q->subframe_index; f.width = q->width; f.height = q->height; f.spl = q->samples_per_launch; f.device_idx = 0;
@@ -116,6 +118,8 @@ struct Lanes {
     float4* emi;     // mode 1: sticky emitted (xyz)
     uint2* hitp;     // prim, sbt
     unsigned int* queue[2];
+    float4* partial;         // groups > 1: per-lane sum of the lane's samples, combined in group order by pt_resolve_kernel
+    uint32_t groups, nlaunch;
     unsigned int* ext_list;  // TRACE work items: item i < n_ext is the extension ray of lane ext_list[i],
     unsigned int* shd_list;  //                   item n_ext + j the shadow ray of lane shd_list[j]
     Counters* counters;
@@ -131,15 +135,17 @@ __device__ __forceinline__ void camera_ray(const Frame& f, int px, int py, uint3
     org = f.eye;
 }
 
+// Lanes are group-major: lane = group * nlaunch + launch index, so neighbouring lanes are neighbouring pixels.
 template <int MODE>
 __device__ __forceinline__ bool lane_pixel(const Frame& f, uint32_t lane, int& px, int& py)
 {
+    const uint32_t idx = f.groups > 1 ? lane % f.nlaunch : lane;
     if (MODE == 0) {
-        px = (int)(lane % f.width);
-        py = (int)(lane / f.width);
+        px = (int)(idx % f.width);
+        py = (int)(idx / f.width);
         return true;
     }
-    const int2 p = f.sample_index[lane];
+    const int2 p = f.sample_index[idx];
     px = p.x; py = p.y;
     return !(px > (int)f.width - 1 || py > (int)f.height - 1);  // optixMultiGPU.cu:221-223
 }
@@ -159,17 +165,22 @@ __device__ __forceinline__ void queue_push(unsigned int* queue, unsigned int* co
 template <int MODE>
 __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ params, Lanes L, uint32_t nlanes)
 {
-    const Frame f = load_frame<MODE>(params);
+    const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
     for (uint32_t base = blockIdx.x * blockDim.x; base < nlanes; base += gridDim.x * blockDim.x) {
         const uint32_t lane = base + threadIdx.x;
         bool active = false;
         if (lane < nlanes) {
             int px, py;
-            if (lane_pixel<MODE>(f, lane, px, py) && f.spl > 0) {
+            // samples [s0, s1) of the launch index belong to this lane's group
+            const uint32_t g = f.groups > 1 ? lane / f.nlaunch : 0u;
+            const uint32_t s0 = (uint32_t)(((uint64_t)g * f.spl) / f.groups), s1 = (uint32_t)(((uint64_t)(g + 1u) * f.spl) / f.groups);
+            if (f.groups > 1) L.partial[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane_pixel<MODE>(f, lane, px, py) && s1 > s0) {
                 uint32_t pixel_seed = tea4((uint32_t)(py * (int)f.width + px), f.subframe);
+                for (uint32_t k = 0; k < 2u * s0; ++k) lcg(pixel_seed);  // every earlier sample drew its two jitter numbers from the pixel seed
                 float3 org, dir;
                 camera_ray(f, px, py, pixel_seed, org, dir);
-                const uint32_t flags = ((f.spl - 1u) & LF_SAMPLES_MASK) << LF_SAMPLES_SHIFT | LF_COUNT_EMITTED;
+                const uint32_t flags = (((s1 - s0) - 1u) & LF_SAMPLES_MASK) << LF_SAMPLES_SHIFT | LF_COUNT_EMITTED;
                 L.ray_o[lane] = make_float4(org.x, org.y, org.z, __uint_as_float(pixel_seed));
                 L.ray_d[lane] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags));
                 L.att[lane] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel_seed));
@@ -260,7 +271,7 @@ struct PTWork {
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(COOP_BLOCK, 8) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
 {
-    const Frame f = load_frame<MODE>(params);
+    const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
     const uint32_t n_ext = L.counters->n_ext[cur], n_shd = L.counters->n_shd[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // SHADE of this iteration appends to the other buffers
@@ -292,13 +303,13 @@ __device__ __forceinline__ float3 device_color(unsigned int idx)  // optixMultiG
 }
 
 template <int MODE>
-__device__ __forceinline__ void finalize_lane(const Frame& f, uint32_t lane, int px, int py, float3 result)
+__device__ __forceinline__ void finalize_index(const Frame& f, uint32_t idx, int px, int py, float3 result)
 {
     // optixPathTracer.cu:308-319 / optixMultiGPU.cu:281-292
     const float spl = (float)f.spl;
     float3 c = f3(fdiv(result.x, spl), fdiv(result.y, spl), fdiv(result.z, spl));
     const uint32_t image_index = (uint32_t)py * f.width + (uint32_t)px;
-    const uint32_t accum_index = MODE == 0 ? image_index : lane;
+    const uint32_t accum_index = MODE == 0 ? image_index : idx;
     if (f.subframe > 0) {
         const float a = fdiv(1.0f, (float)(f.subframe + 1u));
         const float4 prev = f.accum[accum_index];
@@ -309,10 +320,35 @@ __device__ __forceinline__ void finalize_lane(const Frame& f, uint32_t lane, int
 }
 
 template <int MODE>
+__device__ __forceinline__ void finalize_lane(const Frame& f, const Lanes& L, uint32_t lane, int px, int py, float3 result)
+{
+    if (f.groups > 1) L.partial[lane] = make_float4(result.x, result.y, result.z, 0.f);
+    else finalize_index<MODE>(f, lane, px, py, result);
+}
+
+// groups > 1: the pixel value is ((g0 + g1) + g2) + ... of the per-group sums, then the reference's tail
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_resolve_kernel(const void* __restrict__ params, Lanes L)
+{
+    const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= f.nlaunch) return;
+    int px, py;
+    if (!lane_pixel<MODE>(f, idx, px, py) || f.spl == 0) return;
+    const float4 p0 = L.partial[idx];
+    float3 r = f3(p0.x, p0.y, p0.z);
+    for (uint32_t g = 1; g < f.groups; ++g) {
+        const float4 p = L.partial[(size_t)g * f.nlaunch + idx];
+        r = f3(r.x + p.x, r.y + p.y, r.z + p.z);
+    }
+    finalize_index<MODE>(f, idx, px, py, r);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ params, Lanes L, int cur, const char* __restrict__ hg_base,
                                                         uint32_t hg_stride, uint32_t hg_count, const char* __restrict__ miss_base)
 {
-    const Frame f = load_frame<MODE>(params);
+    const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
     const uint32_t n = L.counters->qcount[cur];
     const unsigned int* __restrict__ queue = L.queue[cur];
     unsigned int* next_queue = L.queue[cur ^ 1];
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
             lane_pixel<MODE>(f, lane, px, py);
             if (flags & LF_NO_EXT) {
                 // the last shadow ray of the lane has been resolved by TRACE: write the pixel
-                finalize_lane<MODE>(f, lane, px, py, result);
+                finalize_lane<MODE>(f, L, lane, px, py, result);
             } else {
                 const float4 ro = L.ray_o[lane];
                 float4 attv = L.att[lane];
@@ -453,7 +489,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
                     lane_done = true;
                 }
                 if (lane_done) {
-                    finalize_lane<MODE>(f, lane, px, py, result);
+                    finalize_lane<MODE>(f, L, lane, px, py, result);
                 } else {
                     keep = true;
                     want_ext = (nflags & LF_NO_EXT) == 0u;
@@ -624,9 +660,14 @@ static unsigned persistent_grid(b200rt_context ctx, uint64_t n, int block, int c
 }
 
 template <int MODE>
-static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, uint32_t nlanes,
+static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, uint32_t nlaunch,
                           const b200rt_pt_options* opt)
 {
+    // sample groups: every launch index is served by `groups` lanes that each run a contiguous share of its samples (0 / 1 = one
+    // lane per launch index, the reference's flat summation order)
+    const uint32_t groups = (opt && opt->sample_groups > 1) ? opt->sample_groups : 1u;
+    B2_REQUIRE(ctx, (uint64_t)nlaunch * groups < (1ull << 31), "launch too large (%u launch indices x %u sample groups)", nlaunch, groups);
+    const uint32_t nlanes = nlaunch * groups;
     // workspace layout
     const size_t L = nlanes;
     size_t off = 16384;  // the first 16 KiB of the workspace hold the fetch counters / stats of the ray-buffer launches (raycast.cu)
@@ -636,6 +677,7 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
                  o_pend = take(16 * L);
     const size_t o_rad = MODE == 1 ? take(16 * L) : 0, o_emi = MODE == 1 ? take(16 * L) : 0;
     const size_t o_hit = take(8 * L), o_q0 = take(4 * L), o_q1 = take(4 * L), o_ext = take(4 * L), o_shd = take(4 * L);
+    const size_t o_part = groups > 1 ? take(16 * L) : 0;
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
@@ -650,6 +692,9 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     ln.queue[1] = (unsigned int*)(W + o_q1);
     ln.ext_list = (unsigned int*)(W + o_ext);
     ln.shd_list = (unsigned int*)(W + o_shd);
+    ln.partial = groups > 1 ? (float4*)(W + o_part) : nullptr;
+    ln.groups = groups;
+    ln.nlaunch = nlaunch;
 
     const uint64_t launches0 = ctx->launches;
     B2_CUDA(ctx, cudaMemsetAsync(ln.counters, 0, sizeof(Counters), s));
@@ -697,6 +742,10 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
         B2_CUDA(ctx, cudaStreamSynchronize(s));
         if (h_cnt->qcount[cur] == 0) break;
         if (iterations > 100000) return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "path tracer did not terminate");
+    }
+    if (groups > 1) {
+        pt_resolve_kernel<MODE><<<div_up(nlaunch, 256), 256, 0, s>>>(params, ln);
+        B2_LAUNCH_CHECK(ctx);
     }
     if (want) {
         b200rt_pt_stats* st = opt->stats;

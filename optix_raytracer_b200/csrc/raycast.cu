@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(COOP_BLOCK, 8) trace_rays_kernel(const AccelHe
                                                           uint32_t n_mult, uint32_t flag_period)
 {
     if (n_dev) n = min(n, *n_dev * n_mult);  // ray count produced on the device by an earlier stage (playground.cu)
+    if (KIND != 2 && hg_base) handle = (const AccelHeader*)*(const uint64_t*)hg_base;  // traversable handle read from device memory (whitted.cu)
     RayWork<KIND> w;
     w.flag_period = flag_period;
     w.handle = handle; w.rays = rays; w.hits = nullptr;
@@ -335,21 +336,22 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
 // Internal ray-buffer query used by the multi-stage launches (playground.cu): kind 0 = closest hit -> ExtHit records, 1 = any hit ->
 // u32 flags.  The ray count may live on the device (n_dev * n_mult, capped by n_max).  Caller holds ctx->mu.
 int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev,
-                 unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period, b200rt_deviceptr sbt_out)
+                 unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period, b200rt_deviceptr sbt_out,
+                 b200rt_deviceptr handle_dev)
 {
-    B2_REQUIRE(ctx, handle && rays && out && n_max < (1ull << 32), "bad argument");
+    B2_REQUIRE(ctx, (handle || handle_dev) && rays && out && n_max < (1ull << 32), "bad argument");
     if (n_max == 0) return 0;
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
     if (kind == 0)
         trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
-            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, nullptr, 0, 0, counter,
-            nullptr, n_dev, n_mult, flag_period);
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, (const char*)handle_dev, 0, 0,
+            counter, nullptr, n_dev, n_mult, flag_period);
     else
         trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
-            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, nullptr, 0, 0, counter, nullptr,
-            n_dev, n_mult, flag_period);
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, (const char*)handle_dev, 0, 0, counter,
+            nullptr, n_dev, n_mult, flag_period);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

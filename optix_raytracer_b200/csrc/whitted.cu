@@ -68,7 +68,10 @@ static_assert(sizeof(WParams) == 128 && offsetof(WParams, accum_buffer) == 16 &&
 
 constexpr uint32_t W_RAY_TYPES = 2;  // whitted::RAY_TYPE_COUNT
 constexpr uint32_t W_MAX_TRACE_DEPTH = 8;
-struct WCounters { unsigned int nhit; unsigned int unsupported; unsigned int pad[2]; };
+struct WCounters { unsigned int nhit; unsigned int pad[3]; };
+// asynchronous launch errors, written by the kernels into the context's pinned host block and reported by the NEXT launch
+// (like CUDA's own asynchronous errors): [0] a MASK / BLEND material was hit, [1] more lights than the workspace was sized for
+struct WAsyncFlags { unsigned int unsupported_material; unsigned int too_many_lights; };
 
 // ---- RAYGEN (whitted.cu:44-80) -----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) w_raygen_kernel(const WParams* __restrict__ params, uint32_t width, uint32_t height, float4* __restrict__ rays,
@@ -178,12 +181,13 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const WParams* __restrict_
                                                        const ExtHit* __restrict__ hits, const uint32_t* __restrict__ hit_sbt,
                                                        const char* __restrict__ hg_base, uint32_t hg_stride, uint32_t hg_count, float4* __restrict__ base,
                                                        int* __restrict__ slot, float4* __restrict__ probes, float4* __restrict__ terms,
-                                                       WCounters* __restrict__ counters)
+                                                       WCounters* __restrict__ counters, uint32_t nl_cap, WAsyncFlags* __restrict__ async_flags)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t npix = width * height;
     const WParams P = *params;
-    const uint32_t nl = P.lights.count;
+    if (i == 0 && P.lights.count > nl_cap) async_flags->too_many_lights = P.lights.count;
+    const uint32_t nl = min(P.lights.count, nl_cap);
     bool is_hit = false;
     ExtHit h;
     if (i < npix) {
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const WParams* __restrict_
     const char* rec = hg_base + (size_t)rec_idx * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE;
     const WGeom g = w_local_geometry(rec, h.prim, h.b1, h.b2, ir);
     const WMaterial& m = *(const WMaterial*)(rec + 112);
-    if (m.alpha_mode != 0) counters->unsupported = 1;  // MASK / BLEND need the any-hit programs (not built yet): flagged, rendered opaque
+    if (m.alpha_mode != 0) async_flags->unsupported_material = 1;  // MASK / BLEND need the any-hit programs (not built yet): flagged, rendered opaque
 
     // material (whitted.cu:157-186)
     float4 bc = make_float4(m.base_color[0] * g.color.x, m.base_color[1] * g.color.y, m.base_color[2] * g.color.z, m.base_color[3] * g.color.w);
@@ -295,12 +299,12 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const WParams* __restrict_
 // ---- RESOLVE: rest of __closesthit__radiance + tail of __raygen__pinhole (whitted.cu:84-97) -----------------------------------------
 __global__ void __launch_bounds__(256) w_resolve_kernel(const WParams* __restrict__ params, uint32_t width, uint32_t height, const float4* __restrict__ base,
                                                          const int* __restrict__ slot, const float4* __restrict__ terms,
-                                                         const uint32_t* __restrict__ occluded)
+                                                         const uint32_t* __restrict__ occluded, uint32_t nl_cap)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= width * height) return;
     const WParams P = *params;
-    const uint32_t nl = P.lights.count;
+    const uint32_t nl = min(P.lights.count, nl_cap);
     const float4 b = base[i];
     float3 result = f3(b.x, b.y, b.z);
     const int k = slot[i];
@@ -330,13 +334,31 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     B2_REQUIRE(ctx, npix64 < (1ull << 28), "launch too large");
     if (npix64 == 0) return 0;
     DeviceGuard guard(ctx->device);
-    WParams hp;
-    B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, (const void*)d_params, sizeof(WParams), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(ctx, cudaStreamSynchronize(s));
-    memcpy(&hp, ctx->pinned, sizeof(WParams));
-    B2_REQUIRE(ctx, hp.handle && hp.accum_buffer, "LaunchParams has null pointers");
-    B2_REQUIRE(ctx, hp.lights.count <= 64 && (hp.lights.count == 0 || hp.lights.data), "bad light list");
-    const uint32_t npix = (uint32_t)npix64, nl = hp.lights.count, nlp = std::max(nl, 1u);
+    // errors of earlier launches on this context surface here (no synchronisation on the steady-state path)
+    WAsyncFlags* flags = (WAsyncFlags*)((char*)ctx->pinned + 1024);
+    if (flags->unsupported_material) {
+        flags->unsupported_material = 0;
+        return set_error(ctx, B200RT_ERROR_NOT_SUPPORTED,
+                         "an earlier whitted launch hit a MASK / BLEND material: the any-hit programs of whitted.cu are not built yet (it was rendered as opaque)");
+    }
+    if (flags->too_many_lights) {
+        ctx->w_params = 0;  // re-read the light count below
+        flags->too_many_lights = 0;
+        return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "an earlier whitted launch found more lights than its workspace was sized for (frame incomplete); relaunch");
+    }
+    // The workspace is sized by the light count.  It is read back (one stream synchronisation) on the first launch with a given
+    // d_params; later launches with the same d_params reuse it and the kernels check the live value on the device.
+    if (ctx->w_params != d_params) {
+        WParams hp;
+        B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, (const void*)d_params, sizeof(WParams), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(&hp, ctx->pinned, sizeof(WParams));
+        B2_REQUIRE(ctx, hp.handle && hp.accum_buffer, "LaunchParams has null pointers");
+        B2_REQUIRE(ctx, hp.lights.count <= 64 && (hp.lights.count == 0 || hp.lights.data), "bad light list");
+        ctx->w_params = d_params;
+        ctx->w_lights = hp.lights.count;
+    }
+    const uint32_t npix = (uint32_t)npix64, nl = ctx->w_lights, nlp = std::max(nl, 1u);
     size_t off = 16384;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_cnt = take(sizeof(WCounters)), o_rays = take(32ull * npix), o_hits = take(sizeof(ExtHit) * (size_t)npix), o_sbt = take(4ull * npix),
@@ -355,29 +377,22 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     float4* terms = (float4*)(W + o_terms);
     uint32_t* occ = (uint32_t*)(W + o_occ);
     const WParams* dp = (const WParams*)d_params;
-    B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(WCounters), s));
+    const b200rt_deviceptr handle_dev = d_params + offsetof(WParams, handle);  // the kernels read the live handle
     w_raygen_kernel<<<div_up(npix, 256), 256, 0, s>>>(dp, width, height, rays, cnt);
     B2_LAUNCH_CHECK(ctx);
     // radiance rays cull back faces (whitted_cuda.h:110); DISABLE_TRIANGLE_FACE_CULLING geometry (doubleSided) is exempt in the triangle test
-    rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, npix, nullptr, 1, 0, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, (b200rt_deviceptr)hits, 0,
-                      (b200rt_deviceptr)hsbt);
+    rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)rays, npix, nullptr, 1, 0, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES, (b200rt_deviceptr)hits, 0,
+                      (b200rt_deviceptr)hsbt, handle_dev);
     if (rc) return rc;
     w_shade_kernel<<<div_up(npix, 128), 128, 0, s>>>(dp, width, height, rays, hits, hsbt, (const char*)sbt->hitgroupRecordBase,
-                                                     sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, base, slot, probes, terms, cnt);
+                                                     sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, base, slot, probes, terms, cnt, nl, flags);
     B2_LAUNCH_CHECK(ctx);
     if (nl) {
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)probes, (uint64_t)npix * nl, &cnt->nhit, nl, 1, 0u, (b200rt_deviceptr)occ);
+        rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)probes, (uint64_t)npix * nl, &cnt->nhit, nl, 1, 0u, (b200rt_deviceptr)occ, 0, 0, handle_dev);
         if (rc) return rc;
     }
-    w_resolve_kernel<<<div_up(npix, 256), 256, 0, s>>>(dp, width, height, base, slot, terms, occ);
+    w_resolve_kernel<<<div_up(npix, 256), 256, 0, s>>>(dp, width, height, base, slot, terms, occ, nl);
     B2_LAUNCH_CHECK(ctx);
-    // MASK / BLEND materials: report instead of silently rendering them opaque
-    WCounters hc;
-    B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, cnt, sizeof(WCounters), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(ctx, cudaStreamSynchronize(s));
-    memcpy(&hc, ctx->pinned, sizeof hc);
-    if (hc.unsupported)
-        return set_error(ctx, B200RT_ERROR_NOT_SUPPORTED, "a MASK / BLEND material was hit: the any-hit programs of whitted.cu are not built yet (rendered as opaque)");
     return 0;
 }
 

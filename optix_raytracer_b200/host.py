@@ -387,14 +387,17 @@ class PathTracer:
         self.h_params = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         self.d_params = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.stats = L.PTStats()
+        self.sample_groups = 1
 
-    def launch_subframe(self, subframe_index=None, collect_stats=False):
-        """launchSubframe (optixPathTracer.cpp:488-511): copy Params to the device, launch; asynchronous."""
+    def launch_subframe(self, subframe_index=None, collect_stats=False, sample_groups=None):
+        """launchSubframe (optixPathTracer.cpp:488-511): copy Params to the device, launch; asynchronous.
+        sample_groups: b200rt_pt_options.sample_groups (None = the instance default self.sample_groups)."""
         if subframe_index is not None:
             self.params.subframe_index = subframe_index
         self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
         self.d_params.copy_(self.h_params, non_blocking=True)
-        opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))  # bit mask of L.PT_STATS_*
+        groups = self.sample_groups if sample_groups is None else sample_groups
+        opts = L.PTOptions(int(groups), int(collect_stats), C.pointer(self.stats))  # collect_stats: bit mask of L.PT_STATS_*
         ctx = self.ctx
         if self.multigpu:
             ctx.launch_multigpu(self.programs, self.d_params.data_ptr(), C.sizeof(self.params), self.sbt, self.num_samples, opts)

@@ -456,6 +456,7 @@ struct PTParams {
     float light_corner[3], light_v1[3], light_v2[3], light_normal[3], light_emission[3];
     float bg[3];
     int32_t nmat;
+    int32_t groups;         // sample groups (b200rt_pt_options.sample_groups): 0 / 1 = the reference's flat summation order
     const float* emission;  // nmat*3
     const float* diffuse;   // nmat*3
 };
@@ -488,10 +489,18 @@ static f3 pt_pixel(Scene& sc, const PTParams& P, int px, int py, int mode, uint6
     const f3 lc = ld3(P.light_corner), lv1 = ld3(P.light_v1), lv2 = ld3(P.light_v2), ln = ld3(P.light_normal),
              le = ld3(P.light_emission);
     uint32_t seed = tea4((uint32_t)(py * w + px), P.subframe_index);
-    f3 result = mk(0, 0, 0);
+    f3 result = mk(0, 0, 0), total = mk(0, 0, 0);
     uint64_t nseg = 0;
     Geometry& g0 = sc.geoms[0];
+    // sample groups: group g sums samples [g*spl/G, (g+1)*spl/G) from zero; the pixel is ((s_0 + s_1) + ...) + s_{G-1}
+    const int G = P.groups > 1 ? P.groups : 1;
+    int group = 0;
     for (int i = 0; i < P.spl; ++i) {
+        while (group + 1 < G && i >= (int)(((int64_t)(group + 1) * P.spl) / G)) {
+            total = group == 0 ? result : total + result;
+            result = mk(0, 0, 0);
+            ++group;
+        }
         const float jx = rnd(seed), jy = rnd(seed);
         const float dx = fm(2.0f, ((float)px + jx) / (float)w, -1.0f);
         const float dy = fm(2.0f, ((float)py + jy) / (float)h, -1.0f);
@@ -564,6 +573,12 @@ static f3 pt_pixel(Scene& sc, const PTParams& P, int px, int py, int mode, uint6
         }
     }
     if (segs) *segs += nseg;
+    // close the open group and add the (empty, zero) groups that follow it
+    for (; group < G; ++group) {
+        total = group == 0 ? result : total + result;
+        result = mk(0, 0, 0);
+    }
+    result = total;
     const float spl = (float)P.spl;
     return mk(result.x / spl, result.y / spl, result.z / spl);
 }
@@ -773,6 +788,7 @@ struct orc_pt_params {
     float bg[3];
     int32_t nmat;
     int32_t mode;  // 0 = optixPathTracer (Russian roulette), 1 = optixMultiGPU (depth cap 3)
+    int32_t groups;  // sample groups, 0 / 1 = reference summation order
 };
 // Renders rows [y0,y1) x columns [x0,x1).  accum: width*height*4 floats, read for the running mean
 // when subframe_index > 0 and written (optixPathTracer.cu:310-319); frame: width*height*4 bytes.
@@ -786,7 +802,7 @@ uint64_t orc_pathtrace(void* scene, const orc_pt_params* p, const float* emissio
     memcpy(P.eye, p->eye, 12); memcpy(P.U, p->U, 12); memcpy(P.V, p->V, 12); memcpy(P.W, p->W, 12);
     memcpy(P.light_corner, p->light_corner, 12); memcpy(P.light_v1, p->light_v1, 12); memcpy(P.light_v2, p->light_v2, 12);
     memcpy(P.light_normal, p->light_normal, 12); memcpy(P.light_emission, p->light_emission, 12); memcpy(P.bg, p->bg, 12);
-    P.nmat = p->nmat; P.emission = emission; P.diffuse = diffuse;
+    P.nmat = p->nmat; P.groups = p->groups; P.emission = emission; P.diffuse = diffuse;
     const int T = std::max(1, threads);
     std::vector<uint64_t> segs((size_t)T, 0);
     parallel_rows(y1 - y0, T, [&](int row, int tid) {

@@ -84,7 +84,7 @@ class PTParams(C.Structure):
                 ("eye", C.c_float * 3), ("U", C.c_float * 3), ("V", C.c_float * 3), ("W", C.c_float * 3),
                 ("light_corner", C.c_float * 3), ("light_v1", C.c_float * 3), ("light_v2", C.c_float * 3),
                 ("light_normal", C.c_float * 3), ("light_emission", C.c_float * 3), ("bg", C.c_float * 3),
-                ("nmat", C.c_int32), ("mode", C.c_int32)]
+                ("nmat", C.c_int32), ("mode", C.c_int32), ("groups", C.c_int32)]
 
 
 def tea4(v0, v1):

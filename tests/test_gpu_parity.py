@@ -60,11 +60,14 @@ def test_cornell_random_rays_closest_and_any(ctx, orc, node_format, monkeypatch)
     assert 0.1 < occ.mean() < 0.9
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_cornell_pathtracer_bit_exact(ctx, orc, mode):
+@pytest.mark.parametrize("mode,groups", [(0, 1), (1, 1), (0, 3), (1, 4), (0, 8)])
+def test_cornell_pathtracer_bit_exact(ctx, orc, mode, groups):
+    """groups = b200rt_pt_options.sample_groups: 1 is the reference's flat summation order; 3 (uneven split of 4 samples), 4 and 8
+    (more groups than samples: empty groups) run the samples of a pixel in parallel lanes and must match the oracle's grouped sum."""
     from optix_raytracer_b200 import host
     w, h, spl = 96, 80, 4
     pt = host.PathTracer(ctx, w, h, spl, multigpu=(0, 1) if mode else None)
+    pt.sample_groups = groups
     sc = pt.scene
     scene = orc.Scene(sc["vertices"].reshape(-1, 3, 3), sc["mat_indices"])
     ref_accum = None
@@ -72,6 +75,7 @@ def test_cornell_pathtracer_bit_exact(ctx, orc, mode):
         st = pt.launch_subframe(sub, collect_stats=True)
         torch.cuda.synchronize()
         p = common.oracle_pt_params(orc, pt.params, mode)
+        p.groups = groups
         ref_accum, ref_frame, segs = scene.pathtrace(p, sc["emission_colors"], sc["diffuse_colors"], accum=ref_accum)
         assert st.radiance_segments + st.shadow_segments == segs
         accum = pt.accum.cpu().numpy()
@@ -251,3 +255,20 @@ def test_whitted_untextured_bit_exact(ctx, orc):
         assert np.array_equal(got.view(np.uint32), accum.view(np.uint32)), f"subframe {sub}: accum differs"
         assert np.abs(mv.frame.cpu().numpy().astype(np.int32) - frame.astype(np.int32)).max() <= 1
     mv.close()
+
+
+def test_whitted_reports_unsupported_alpha_modes(ctx):
+    """MASK / BLEND materials need the any-hit programs (not built yet): the launch that meets one renders it opaque and the
+    next launch on the context fails with NOT_SUPPORTED (asynchronous error, like CUDA's) — never a silent wrong picture."""
+    from optix_raytracer_b200 import host
+    sc = common.duck_scene(textured=False)
+    sc["materials"][0]["alpha_mode"] = 1
+    mv = host.MeshViewer(ctx, sc, 64, 48)
+    mv.launch_subframe(0)
+    torch.cuda.synchronize()
+    with pytest.raises(host.B200RTError, match="NOT_SUPPORTED|7800|UNSUPPORTED"):
+        mv.launch_subframe(1)
+    # the flag is consumed: an opaque scene renders again on the same context
+    ok = host.MeshViewer(ctx, common.duck_scene(textured=False), 64, 48)
+    ok.launch_subframe(0)
+    torch.cuda.synchronize()
