@@ -904,8 +904,10 @@ class MeshViewer:
         """launchSubframe (optixMeshViewer.cpp:283-308)."""
         if subframe_index is not None:
             self.params.subframe_index = subframe_index
-        self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
-        self.d_params.copy_(self.h_params, non_blocking=True)
+        # pageable source, like the reference's cudaMemcpyAsync(d_params, &params, ...) (optixMeshViewer.cpp:289-293): the runtime stages it
+        # before returning, so the host may change `params` for the next subframe while this launch is still queued (whitted launches do
+        # not synchronise the stream)
+        self.d_params.copy_(torch.from_numpy(np.frombuffer(bytes(self.params), np.uint8).copy()))
         self.ctx.launch_whitted(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height)
 
     def close(self):
