@@ -14,6 +14,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--spl", type=int, default=4)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--cornell", action="store_true")
+ap.add_argument("--sample-groups", type=int, default=4)
 a = ap.parse_args()
 ctx = host.Context(0)
 if a.cornell:
@@ -21,6 +22,7 @@ if a.cornell:
 else:
     verts, mats = host.synthetic_mesh(ctx, a.triangles, 0)
     pt = host.PathTracer(ctx, a.width, a.height, a.spl, vertices=verts, mat_indices=mats, multigpu=(0, 1))
+pt.sample_groups = a.sample_groups
 torch.cuda.synchronize()
 for i in range(a.steps):
     t = time.perf_counter()
