@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spl", type=int, default=16)
-    ap.add_argument("--sample-groups", type=int, default=4, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
+    ap.add_argument("--sample-groups", type=int, default=None, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -311,8 +311,21 @@ def run_b200rt(a, rank, world, local_rank):
     node_bytes = int(info.reserved) or 80  # 80: 8-bit boxes (large scenes), 224: fp32 boxes (cache-resident scenes)
     algo_bytes = lane_iters * (4 + 16 + 32 + 16 + 8) + shd * 48 + nodes * node_bytes + tris * 48
     achieved = algo_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+    # measured DRAM bytes of the same launches (one ncu capture of this command, profiles/*_trace_dram.json), per launch like
+    # `achieved`; null when no capture of this workload is committed
+    traffic, traffic_src = None, None
+    for f in sorted((ROOT / "profiles").glob("*_trace_dram.json"), reverse=True):
+        try:
+            cap = json.loads(f.read_text())
+        except Exception:
+            continue
+        c = cap.get("config", {})
+        if (c.get("workload"), c.get("triangles"), c.get("width"), c.get("height"), c.get("spl")) == (a.workload, a.triangles, a.width, a.height, a.spl) and world == 1:
+            traffic = (cap["dram_read_bytes_per_step"] + cap["dram_write_bytes_per_step"]) / max(iters, 1)
+            traffic_src = f"profiles/{f.name} (ncu dram__bytes_read.sum + dram__bytes_write.sum of the trace launches of one step, captured with sample_groups {c.get('sample_groups')})"
+            break
     roofline = {"bound": "hbm", "kernel": "pt_trace_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes / max(iters, 1), "launches_per_step": iters,
                 "avg_launch_ms": trace_ms / max(iters, 1), "trace_share_of_step": trace_ms / max(trace_ms + shade_ms, 1e-9),
                 "nodes_per_segment": nodes / max(rad + shd, 1), "tris_per_segment": tris / max(rad + shd, 1)}
@@ -341,6 +354,8 @@ def main():
     a = parse()
     if a.width is None:
         a.width, a.height = (3840, 2160) if a.workload == "synthetic" else (768, 768)
+    if a.sample_groups is None:
+        a.sample_groups = 8 if a.workload == "synthetic" else 4   # measured best on one B200 (gpurun_out/sg_*.json); any value gives the same image on any N
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -269,7 +269,7 @@ struct PTWork {
 };
 
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(COOP_BLOCK, 8) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
+__global__ void __launch_bounds__(COOP_BLOCK, COOP_MIN_CTAS) pt_trace_kernel(const void* __restrict__ params, Lanes L, int cur)
 {
     const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
     const uint32_t n_ext = L.counters->n_ext[cur], n_shd = L.counters->n_shd[cur];

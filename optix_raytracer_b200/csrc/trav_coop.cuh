@@ -40,6 +40,10 @@ constexpr int REFILL_THRESHOLD = B200RT_REFILL_THRESHOLD;   // refill when fewer
 constexpr int TRI_TRIGGER = B200RT_TRI_TRIGGER;             // run a triangle round once this many (ray, triangle) units are parked
 constexpr int COOP_BLOCK = 128;        // CTA size of every kernel built on trace_persistent
 constexpr int COOP_WARPS = COOP_BLOCK / 32;
+#ifndef B200RT_COOP_MIN_CTAS
+#define B200RT_COOP_MIN_CTAS 8
+#endif
+constexpr int COOP_MIN_CTAS = B200RT_COOP_MIN_CTAS;  // resident CTAs per SM the path-tracing trace kernel is compiled for (8 -> 64 registers)
 constexpr int RAY_S_STRIDE = 9;        // odd stride: lanes reading different owners hit different banks
 
 // pack word layout
@@ -47,6 +51,28 @@ constexpr uint32_t TP_ANY = 1u << 16;        // any-hit (terminate on first hit)
 constexpr uint32_t TP_FOUND = 1u << 17;      // a hit was accepted in the GAS currently being traversed (tie-break scope)
 constexpr uint32_t TP_FOUND_ANY = 1u << 18;  // a hit was accepted in any instance so far
 constexpr uint32_t TP_F32 = 1u << 19;        // the GAS being traversed has Node8F nodes (fp32 child boxes, 224 B)
+constexpr uint32_t TP_H64 = 0x64000000u;     // top byte = high byte of the fp16 patterns 0x64qq = 1024 + q the 8-bit decode builds with one PRMT
+
+// 8-bit plane decode of the Node8 visit.  ncu's source page (profiles/r01_trace_kernel.md) showed ~50 of the 352 instructions of a
+// node visit to be constant traffic: PRMT takes only one immediate, so with the constant 0x64646464 as an operand every PRMT needed
+// its selector moved into a register, and every FHADD its -1024.  Here the 0x64 byte comes from the ray's live `pack` word (so the
+// selector is the immediate) and the 1024 bias is folded into the plane offset once per axis (aox - 1024 aix), so the conversion
+// is FHADD with RZ.  Both are exact except for the one extra rounding of the folded offset: <= 2^-24 |aox| + 2^-14 of a grid cell,
+// far inside the build-time padding (2^-16 of the node extent) and the slab slack.
+__device__ __forceinline__ uint32_t q8_pair01(uint32_t w, uint32_t pack) { return __byte_perm(w, pack, 0x7170u); }  // {1024 + b0, 1024 + b1} as half2 bits
+__device__ __forceinline__ uint32_t q8_pair23(uint32_t w, uint32_t pack) { return __byte_perm(w, pack, 0x7372u); }  // {1024 + b2, 1024 + b3}
+__device__ __forceinline__ float q8_lo(uint32_t h)
+{
+    float f;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(f) : "h"((unsigned short)(h & 0xffffu)), "f"(0.0f));
+    return f;
+}
+__device__ __forceinline__ float q8_hi(uint32_t h)
+{
+    float f;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(f) : "h"((unsigned short)(h >> 16)), "f"(0.0f));
+    return f;
+}
 
 struct Trav {
     const uint4* nodes;
@@ -54,7 +80,7 @@ struct Trav {
     float ox, oy, oz;       // origin in the space of the GAS being traversed
     float idx, idy, idz;    // reciprocal (clamped) direction for the box tests
     float tmin;
-    uint32_t pack;          // kx | ky<<2 | kz<<4 | octinv<<8 | negx<<11 | negy<<12 | negz<<13 | TP_*
+    uint32_t pack;          // kx | ky<<2 | kz<<4 | octinv<<8 | negx<<11 | negy<<12 | negz<<13 | TP_* | 0x64 << 24 (fp16 exponent byte, see q8_pair*)
     uint32_t inst;          // index of the instance being traversed (0 for a bare GAS)
     uint2 ngroup, tgroup;   // current node group; parked triangle group (base, 24-bit mask)
     int sp;
@@ -84,7 +110,7 @@ __device__ __forceinline__ void trav_begin(Trav& s, float* __restrict__ my_ray, 
     s.idx = fdiv(1.0f, bx); s.idy = fdiv(1.0f, by); s.idz = fdiv(1.0f, bz);
     const uint32_t nx = bx < 0.0f, ny = by < 0.0f, nz = bz < 0.0f;
     const uint32_t oct = (nx << 2) | (ny << 1) | nz;
-    s.pack = (uint32_t)tr.kx | ((uint32_t)tr.ky << 2) | ((uint32_t)tr.kz << 4) | ((7u - oct) << 8) | (nx << 11) | (ny << 12) | (nz << 13) | keep_flags |
+    s.pack = (uint32_t)tr.kx | ((uint32_t)tr.ky << 2) | ((uint32_t)tr.kz << 4) | ((7u - oct) << 8) | (nx << 11) | (ny << 12) | (nz << 13) | keep_flags | TP_H64 |
              (gas->node_bytes == NODE8F_BYTES ? TP_F32 : 0u);
     s.tmin = tmin;
     s.ngroup = gas->num_tris ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
@@ -143,9 +169,11 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
     const float aix = __uint_as_float((e_imask & 0xffu) << 23) * s.idx;
     const float aiy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * s.idy;
     const float aiz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * s.idz;
-    const float aox = (px - s.ox) * s.idx, aoy = (py - s.oy) * s.idy, aoz = (pz - s.oz) * s.idz;
+    // plane t = (1024 + q) * ai + (ao - 1024 ai): the fp16 patterns carry the 1024 bias, the offset takes it back out
+    const float aox = fm(-1024.0f, aix, (px - s.ox) * s.idx), aoy = fm(-1024.0f, aiy, (py - s.oy) * s.idy), aoz = fm(-1024.0f, aiz, (pz - s.oz) * s.idz);
     const float tfar = s.best.t, tmin = s.tmin;
-    const bool negx = (s.pack >> 11) & 1u, negy = (s.pack >> 12) & 1u, negz = (s.pack >> 13) & 1u;
+    const uint32_t pack = s.pack;
+    const bool negx = (pack >> 11) & 1u, negy = (pack >> 12) & 1u, negz = (pack >> 13) & 1u;
     const uint32_t octinv4 = octinv * 0x01010101u;
     uint32_t hitmask = 0;
 #pragma unroll
@@ -162,15 +190,15 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
         const uint32_t zn = negz ? qhiz : qloz, zf = negz ? qloz : qhiz;
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp) {
-            const BytePair pxn = jp ? byte_pair23(xn) : byte_pair01(xn), pxf = jp ? byte_pair23(xf) : byte_pair01(xf);
-            const BytePair pyn = jp ? byte_pair23(yn) : byte_pair01(yn), pyf = jp ? byte_pair23(yf) : byte_pair01(yf);
-            const BytePair pzn = jp ? byte_pair23(zn) : byte_pair01(zn), pzf = jp ? byte_pair23(zf) : byte_pair01(zf);
+            const uint32_t pxn = jp ? q8_pair23(xn, pack) : q8_pair01(xn, pack), pxf = jp ? q8_pair23(xf, pack) : q8_pair01(xf, pack);
+            const uint32_t pyn = jp ? q8_pair23(yn, pack) : q8_pair01(yn, pack), pyf = jp ? q8_pair23(yf, pack) : q8_pair01(yf, pack);
+            const uint32_t pzn = jp ? q8_pair23(zn, pack) : q8_pair01(zn, pack), pzf = jp ? q8_pair23(zf, pack) : q8_pair01(zf, pack);
 #pragma unroll
             for (int jh = 0; jh < 2; ++jh) {
                 const int j = 2 * jp + jh;
-                const float tnx = fm(jh ? pair_hi(pxn) : pair_lo(pxn), aix, aox), tfx = fm(jh ? pair_hi(pxf) : pair_lo(pxf), aix, aox);
-                const float tny = fm(jh ? pair_hi(pyn) : pair_lo(pyn), aiy, aoy), tfy = fm(jh ? pair_hi(pyf) : pair_lo(pyf), aiy, aoy);
-                const float tnz = fm(jh ? pair_hi(pzn) : pair_lo(pzn), aiz, aoz), tfz = fm(jh ? pair_hi(pzf) : pair_lo(pzf), aiz, aoz);
+                const float tnx = fm(jh ? q8_hi(pxn) : q8_lo(pxn), aix, aox), tfx = fm(jh ? q8_hi(pxf) : q8_lo(pxf), aix, aox);
+                const float tny = fm(jh ? q8_hi(pyn) : q8_lo(pyn), aiy, aoy), tfy = fm(jh ? q8_hi(pyf) : q8_lo(pyf), aiy, aoy);
+                const float tnz = fm(jh ? q8_hi(pzn) : q8_lo(pzn), aiz, aoz), tfz = fm(jh ? q8_hi(pzf) : q8_lo(pzf), aiz, aoz);
                 const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
                 if (cmin <= cmax * BOX_SLACK) {
