@@ -41,7 +41,8 @@ struct AccelHeader {
     uint32_t max_nodes;      // node capacity of this (uncompacted) blob
     uint32_t error;          // builder overflow flag
     uint32_t node_bytes;     // 80: Node8 (8-bit quantised child boxes); 224: Node8F (fp32 child boxes), see below
-    uint32_t pad[9];
+    uint32_t anyhit;         // 1: some triangle (GAS) / some instanced GAS (IAS) leaves any-hit enabled (geometry flags without DISABLE_ANYHIT)
+    uint32_t pad[8];
 };
 static_assert(sizeof(AccelHeader) == HEADER_BYTES, "header must be 128 bytes");
 

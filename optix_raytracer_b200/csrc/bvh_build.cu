@@ -658,9 +658,11 @@ __global__ void build_ias_kernel(const char* __restrict__ instances, uint32_t n,
     if (threadIdx.x == 0) {
         // bounds: serial pass (n is small on this path)
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        uint32_t anyhit = 0;
         for (uint32_t k = 0; k < n; ++k) {
             const AccelHeader* g = (const AccelHeader*)recs[k].gas;
             if (!g || g->magic != ACCEL_MAGIC || !g->num_tris) continue;
+            anyhit |= g->anyhit;
             for (int c = 0; c < 8; ++c) {
                 const float3 p = f3(g->bounds[(c & 1) ? 3 : 0], g->bounds[(c & 2) ? 4 : 1], g->bounds[(c & 4) ? 5 : 2]);
                 const float3 w = xform_point(recs[k].m, p);
@@ -675,6 +677,7 @@ __global__ void build_ias_kernel(const char* __restrict__ instances, uint32_t n,
         v.num_instances = n;
         v.inst_off = HEADER_BYTES;
         v.total_bytes = HEADER_BYTES + (uint64_t)n * INSTREC_BYTES;
+        v.anyhit = anyhit;
         for (int a = 0; a < 3; ++a) { v.bounds[a] = lo[a]; v.bounds[3 + a] = hi[a]; }
         *h = v;
     }
@@ -825,6 +828,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         // ---- upload input descriptors + geometry flags (pageable -> staged synchronously by the runtime)
         std::vector<DevInput> dev(num_inputs);
         std::vector<uint32_t> gflags(std::max(1u, p.total_sbt), 0u);
+        uint32_t any_anyhit = 0;
         uint32_t tri_start = 0, sbt_base = 0;
         for (unsigned i = 0; i < num_inputs; ++i) {
             const auto& t = inputs[i].triangleArray;
@@ -847,7 +851,10 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             d.tri_start = tri_start;
             d.ntris = count_tris(t);
             d.flags_off = sbt_base;
-            for (unsigned k = 0; k < t.numSbtRecords; ++k) gflags[sbt_base + k] = t.flags ? t.flags[k] : 0u;
+            for (unsigned k = 0; k < t.numSbtRecords; ++k) {
+                gflags[sbt_base + k] = t.flags ? t.flags[k] : 0u;
+                if (!(gflags[sbt_base + k] & 1u)) any_anyhit = 1u;  // OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT not set
+            }
             tri_start += d.ntris;
             sbt_base += t.numSbtRecords;
         }
@@ -955,6 +962,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         hv.num_nodes = total_nodes;
         hv.depth = depth;
         hv.node_bytes = p.node_bytes;
+        hv.anyhit = any_anyhit;
         hv.total_bytes = HEADER_BYTES + (uint64_t)total_nodes * p.node_bytes + (uint64_t)N * TRI_BYTES;
         exact_bytes = hv.total_bytes;
         write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds);

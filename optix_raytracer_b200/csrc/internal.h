@@ -21,7 +21,7 @@ int trace_any(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr
 int trace_stats(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, uint64_t, uint64_t*, uint64_t*);
 int trace_buffer(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev, unsigned n_mult,
                  int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period = 0, b200rt_deviceptr sbt_out = 0,
-                 b200rt_deviceptr handle_dev = 0);
+                 b200rt_deviceptr handle_dev = 0, const b200rt_shader_binding_table* anyhit_sbt = nullptr);
 // whitted.cu
 int launch_whitted(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, const b200rt_shader_binding_table*, unsigned, unsigned);
 int texture_create(b200rt_context, int, int, const void*, int, int, int, uint64_t*, uint64_t*);

@@ -12,6 +12,7 @@
 #include "accel.h"
 #include "internal.h"
 #include "trav_coop.cuh"
+#include "anyhit.cuh"
 
 namespace b200rt {
 
@@ -63,9 +64,13 @@ __device__ __forceinline__ ExtHit make_ext(const Trav& s, bool found)
     return e;
 }
 
-// KIND 0: closest hit -> ExtHit; 1: any hit -> u32 flag; 2: the optixRaycasting programs -> Hit (+ optional ExtHit)
-template <int KIND>
+// KIND 0: closest hit -> ExtHit; 1: any hit -> u32 flag (AH: fp32 attenuation, whitted_cuda.h:127-159); 2: the optixRaycasting
+// programs -> Hit (+ optional ExtHit).  AH: the launch has any-hit programs (anyhit.cuh) and the scene may hold geometry that runs them.
+template <int KIND, bool AH>
 struct RayWork {
+    static constexpr bool ANYHIT = AH;
+    AnyHitCfg ah;
+    double att;  // AH, KIND 1: pending occlusion attenuation of this lane's ray
     const AccelHeader* handle;
     const float4* rays;
     uint32_t ray_flags;
@@ -82,9 +87,18 @@ struct RayWork {
         const uint32_t f = ray_flags & 0xf0u;
         return (flag_period && (i % flag_period) == flag_period - 1u) ? (f & 0x30u) : f;
     }
+    __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
+    {
+        uint32_t inst_sbt = 0;
+        if (handle->kind == ACCEL_KIND_IAS) inst_sbt = ((const InstanceRecord*)((const char*)handle + handle->inst_off) + inst)->sbt_offset;
+        return run_anyhit(ah, prim, sbt, inst_sbt, (pack & TP_ANY) != 0u, b1, b2, factor);
+    }
+    __device__ __forceinline__ void attenuate(float factor) { att *= (double)factor; }
+    __device__ __forceinline__ bool anyhit_enabled() const { return ah.mode != AH_NONE && handle->anyhit != 0u; }
     __device__ __forceinline__ bool fetch(uint32_t i, Trav& s, float* my_ray)
     {
         item = i;
+        if (AH) att = 1.0;
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
         if (!trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
@@ -102,7 +116,12 @@ struct RayWork {
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
     {
-        if (KIND == 1) { occluded[item] = found ? 1u : 0u; return; }
+        if (KIND == 1) {
+            // AH: the committed attenuation (0 = occluded: the miss program never ran); otherwise a flag
+            if (AH) ((float*)occluded)[item] = found ? 0.0f : (float)att;
+            else occluded[item] = found ? 1u : 0u;
+            return;
+        }
         if (KIND == 0) {
             ext[item] = make_ext(s, found);
             if (occluded) occluded[item] = found ? (s.best.sbt & TRI_SBT_MASK) : 0u;  // optional: GAS-local SBT index of the hit (whitted.cu)
@@ -160,17 +179,19 @@ struct RayWork {
 
 struct RaycastParamsDev { uint64_t handle; const float4* rays; float4* hits; };  // optixRaycasting.h:41-46
 
-template <int KIND, bool STATS>
+template <int KIND, bool STATS, bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, 8) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
                                                           uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
                                                           const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
                                                           uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,
                                                           unsigned long long* __restrict__ stats, const unsigned int* __restrict__ n_dev,
-                                                          uint32_t n_mult, uint32_t flag_period)
+                                                          uint32_t n_mult, uint32_t flag_period, AnyHitCfg ah)
 {
     if (n_dev) n = min(n, *n_dev * n_mult);  // ray count produced on the device by an earlier stage (playground.cu)
     if (KIND != 2 && hg_base) handle = (const AccelHeader*)*(const uint64_t*)hg_base;  // traversable handle read from device memory (whitted.cu)
-    RayWork<KIND> w;
+    RayWork<KIND, AH> w;
+    w.ah = ah;
+    w.att = 1.0;
     w.flag_period = flag_period;
     w.handle = handle; w.rays = rays; w.hits = nullptr;
     if (KIND == 2) { const RaycastParamsDev P = *rc_params; w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits; }
@@ -202,11 +223,11 @@ static int next_counter(b200rt_context ctx, cudaStream_t s, unsigned int** out)
     return 0;
 }
 
-template <int KIND, bool STATS>
+template <int KIND, bool STATS, bool AH = false>
 static unsigned persistent_grid_rays(b200rt_context ctx, uint64_t n)
 {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_rays_kernel<KIND, STATS>, COOP_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_rays_kernel<KIND, STATS, AH>, COOP_BLOCK, 0);
     const uint64_t cap = (uint64_t)std::max(occ, 1) * ctx->sm_count;
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(cap, (n + COOP_BLOCK - 1) / COOP_BLOCK));
 }
@@ -259,9 +280,9 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
-                                                                                       ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0,
-                                                                                       counter, nullptr, nullptr, 1u, 0u);
+    trace_rays_kernel<0, false, false><<<persistent_grid_rays<0, false>(ctx, n), COOP_BLOCK, 0, s>>>(
+        (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0, counter, nullptr, nullptr, 1u, 0u,
+        AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -276,9 +297,9 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
-                                                                                       ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0,
-                                                                                       counter, nullptr, nullptr, 1u, 0u);
+    trace_rays_kernel<1, false, false><<<persistent_grid_rays<1, false>(ctx, n), COOP_BLOCK, 0, s>>>(
+        (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0, counter, nullptr, nullptr, 1u, 0u,
+        AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -296,8 +317,8 @@ int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b
     B2_CUDA(ctx, cudaMalloc(&scratch, sizeof(ExtHit) * std::max<uint64_t>(n, 1)));
     B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
     if (n) {
-        trace_rays_kernel<0, true><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>((const AccelHeader*)handle, (const float4*)rays, (uint32_t)n,
-                                                                                         0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u);
+        trace_rays_kernel<0, true, false><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>(
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, 0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
         ctx->launches++;
     }
     unsigned long long h[2] = {0, 0};
@@ -324,11 +345,13 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    trace_rays_kernel<2, false><<<persistent_grid_rays<2, false>(ctx, n), COOP_BLOCK, 0, s>>>(nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr,
-                                                                                       (const RaycastParamsDev*)d_params,
-                                                                                       (const char*)sbt->hitgroupRecordBase,
-                                                                                       sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount,
-                                                                                       counter, nullptr, nullptr, 1u, 0u);
+    // __anyhit__texture_mask (optixRaycasting.cu:89-102) needs the material and the texture coordinates of whitted::HitGroupData; a
+    // record too short to hold them (geometry only) runs without any-hit programs
+    const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
+    const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, full_records ? AH_TEXTURE_MASK : AH_NONE};
+    trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
+        nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
+        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -337,21 +360,33 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
 // u32 flags.  The ray count may live on the device (n_dev * n_mult, capped by n_max).  Caller holds ctx->mu.
 int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b200rt_deviceptr rays, uint64_t n_max, const unsigned int* n_dev,
                  unsigned n_mult, int kind, unsigned ray_flags, b200rt_deviceptr out, unsigned flag_period, b200rt_deviceptr sbt_out,
-                 b200rt_deviceptr handle_dev)
+                 b200rt_deviceptr handle_dev, const b200rt_shader_binding_table* ah_sbt)
 {
     B2_REQUIRE(ctx, (handle || handle_dev) && rays && out && n_max < (1ull << 32), "bad argument");
     if (n_max == 0) return 0;
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    if (kind == 0)
-        trace_rays_kernel<0, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+    const AnyHitCfg noah{nullptr, 0u, 0u, AH_NONE};
+    if (ah_sbt) {
+        // the whitted programs (two ray types): kind 0 = radiance rays -> ExtHit, kind 1 = occlusion rays -> fp32 attenuation
+        const AnyHitCfg ah{(const char*)ah_sbt->hitgroupRecordBase, ah_sbt->hitgroupRecordStrideInBytes, ah_sbt->hitgroupRecordCount, AH_WHITTED};
+        if (kind == 0)
+            trace_rays_kernel<0, false, true><<<persistent_grid_rays<0, false, true>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+                (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, (const char*)handle_dev, 0, 0,
+                counter, nullptr, n_dev, n_mult, flag_period, ah);
+        else
+            trace_rays_kernel<1, false, true><<<persistent_grid_rays<1, false, true>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+                (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, (const char*)handle_dev, 0, 0, counter,
+                nullptr, n_dev, n_mult, flag_period, ah);
+    } else if (kind == 0)
+        trace_rays_kernel<0, false, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, (const char*)handle_dev, 0, 0,
-            counter, nullptr, n_dev, n_mult, flag_period);
+            counter, nullptr, n_dev, n_mult, flag_period, noah);
     else
-        trace_rays_kernel<1, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
+        trace_rays_kernel<1, false, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, (const char*)handle_dev, 0, 0, counter,
-            nullptr, n_dev, n_mult, flag_period);
+            nullptr, n_dev, n_mult, flag_period, noah);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

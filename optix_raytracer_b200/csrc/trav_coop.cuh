@@ -94,6 +94,10 @@ struct CoopShared {
     float res_t[COOP_WARPS][32];
     uint32_t res_ord[COOP_WARPS][32];
 };
+template <bool ANYHIT> struct CoopSharedAnyHit {};
+template <> struct CoopSharedAnyHit<true> {
+    float res_fac[COOP_WARPS][32];  // factor the unit's any-hit program returned for the owner's pending attenuation
+};
 
 // Prepare the per-ray constants for a GAS (object-space origin/direction).  best.t must hold tmax.
 __device__ __forceinline__ void trav_begin(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ gas, float3 o, float3 d, float tmin,
@@ -301,10 +305,19 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 //   __device__ bool  fetch(uint32_t item, Trav& s, float* my_ray)  load item, set s.best.t = tmax, call trav_begin_handle; false = nothing to trace
 //   __device__ bool  next_instance(Trav& s, float* my_ray)         IAS: set up the next instance (true) or report none left (false)
 //   __device__ void  commit(const Trav& s, bool found)             store the result of the finished item
+//   static constexpr bool ANYHIT                                   any-hit programs exist: a candidate hit on a triangle whose geometry
+//                                                                  flags lack DISABLE_ANYHIT is put to
+//   __device__ bool  anyhit(prim, sbt, inst, pack, b1, b2, factor) (called by whichever lane tested the triangle: it may only use state
+//                                                                  shared by all lanes plus its arguments; false = ignore the hit), and
+//   __device__ void  attenuate(float factor)                       is called on the OWNING lane for every factor != 1
+//   __device__ bool  anyhit_enabled()                              uniform over the launch: false skips all of it at run time
 template <class Work>
 __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, unsigned int* __restrict__ fetch_counter, TravStats* st)
 {
     __shared__ CoopShared sh;
+    __shared__ CoopSharedAnyHit<Work::ANYHIT> sha;
+    bool ah_on = false;  // uniform: the launch has any-hit programs AND the traversable holds geometry that runs them
+    if constexpr (Work::ANYHIT) ah_on = work.anyhit_enabled();
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
@@ -380,7 +393,15 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                             const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                             if (st) st->tris++;
                             float t, b1, b2;
-                            if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
+                            bool uh = tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2);
+                            if constexpr (Work::ANYHIT) {
+                                if (ah_on && uh && !((__float_as_uint(q1.w) >> TRI_FLAG_SHIFT) & 1u)) {
+                                    float fac;
+                                    uh = work.anyhit(__float_as_uint(q0.w), __float_as_uint(q1.w) & TRI_SBT_MASK, s.inst, s.pack, b1, b2, fac);
+                                    if (fac != 1.0f) work.attenuate(fac);
+                                }
+                            }
+                            if (uh) {
                                 const uint32_t ord = __float_as_uint(q2.w);
                                 if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
                                     s.best.t = t; s.best.b1 = b1; s.best.b2 = b2; s.best.ord = ord;
@@ -424,12 +445,25 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                     float ut = 0.f, ub1 = 0.f, ub2 = 0.f;
                     uint32_t uord = 0xffffffffu, uprim = 0u, usbt = 0u;
                     bool uhit = false;
+                    uint32_t opack = 0u, oinst = 0u;
+                    if constexpr (Work::ANYHIT) {
+                        if (ah_on) { opack = __shfl_sync(FULL, s.pack, owner); oinst = __shfl_sync(FULL, s.inst, owner); }
+                    }
                     if (valid) {
                         const float4* tp = (const float4*)(uintptr_t)tris_base + (size_t)sh.unit_tri[wid][lane] * 3u;
                         const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                         if (st) st->tris++;
                         uhit = tri_unit(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
                         uord = __float_as_uint(q2.w); uprim = __float_as_uint(q0.w); usbt = __float_as_uint(q1.w);
+                    }
+                    if constexpr (Work::ANYHIT) {
+                        // the any-hit program of the candidate runs on the lane that tested it; its verdict (and the occlusion factor)
+                        // goes back to the owner with the unit's result
+                        if (ah_on) {
+                            float fac = 1.0f;
+                            if (uhit && !((usbt >> TRI_FLAG_SHIFT) & 1u)) uhit = work.anyhit(uprim, usbt & TRI_SBT_MASK, oinst, opack, ub1, ub2, fac);
+                            sha.res_fac[wid][lane] = fac;
+                        }
                     }
                     sh.res_t[wid][lane] = uhit ? ut : __int_as_float(0x7f800000);
                     sh.res_ord[wid][lane] = uord;
@@ -442,6 +476,12 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                         for (uint32_t p = lo; p < hi; ++p) {
                             const float t = sh.res_t[wid][p - base];
                             const uint32_t ord = sh.res_ord[wid][p - base];
+                            if constexpr (Work::ANYHIT) {
+                                if (ah_on) {
+                                    const float fac = sha.res_fac[wid][p - base];
+                                    if (fac != 1.0f) work.attenuate(fac);
+                                }
+                            }
                             if (t < s.best.t || (t == s.best.t && (s.pack & TP_FOUND) && ord < s.best.ord)) {
                                 s.best.t = t; s.best.ord = ord; win = (int)(p - base);
                                 s.pack |= TP_FOUND | TP_FOUND_ANY;

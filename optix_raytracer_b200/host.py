@@ -536,6 +536,69 @@ def _gltf_images(g, base):
 HG_OFF_INDICES, HG_OFF_POSITIONS, HG_OFF_NORMALS, HG_OFF_MATERIAL, HG_SIZE = 16, 32, 48, 112, 352
 
 
+def create_scene_textures(ctx, scene):
+    """Scene::addImage / addSampler (Scene.cpp:576-652): one texture object per glTF texture (sampler wrap modes; linear unless NEAREST).
+    Returns ({texture index: cudaTextureObject_t or None}, [(context, texture, array)] to destroy)."""
+    hc = getattr(ctx, "helper", ctx)
+    tex_objects, handles = {}, []
+    wrap = {10497: 0, 33071: 1, 33648: 2}
+    for ti, t in enumerate(scene.get("textures", [])):
+        img = scene["images"][t["source"]] if t.get("source") is not None else None
+        if img is None:
+            tex_objects[ti] = None
+            continue
+        smp = scene["samplers"][t["sampler"]] if t.get("sampler") is not None and scene.get("samplers") else {}
+        linear = 0 if smp.get("magFilter") == 9728 else 1
+        tex, arr = C.c_uint64(), C.c_uint64()
+        hc.check(hc.lib.b200rt_texture_create(hc.h, img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p), wrap.get(smp.get("wrapS", 10497), 0),
+                                              wrap.get(smp.get("wrapT", 10497), 0), linear, C.byref(tex), C.byref(arr)), "texture_create")
+        tex_objects[ti] = tex.value
+        handles.append((hc, tex.value, arr.value))
+    return tex_objects, handles
+
+
+def build_scene_meshes(ctx, scene, tex_objects):
+    """Scene::buildMeshAccels (Scene.cpp:817-1132) + the whitted::HitGroupData payload of every primitive group: one GAS per mesh, one build
+    input per primitive group with the geometry flags of its material (Scene.cpp:904-966: OPAQUE -> DISABLE_ANYHIT, MASK -> NONE, BLEND ->
+    REQUIRE_SINGLE_ANYHIT_CALL; doubleSided adds DISABLE_TRIANGLE_FACE_CULLING).  Returns (accels, per-mesh record payloads, device buffers)."""
+    materials = scene.get("materials", [])
+    keep, mesh_accels, mesh_records = [], [], []
+    for m in scene["meshes"]:
+        inputs, recs = [], []
+        for p in m["primitives"]:
+            d_pos = ctx.to_device(p["positions"])
+            d_nrm = ctx.to_device(p["normals"]) if p.get("normals") is not None else None
+            idx = p["indices"]
+            d_idx = None
+            if idx is not None:
+                d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
+            uvs = p.get("texcoords") or [None, None]
+            d_uv = [ctx.to_device(u) if u is not None else None for u in uvs]
+            mat = materials[p["material"]] if p.get("material", -1) >= 0 and p["material"] < len(materials) else None
+            am = 0 if mat is None else mat["alpha_mode"]
+            gf = {0: 1, 1: 0, 2: 2}[am] | (4 if (mat is not None and mat["double_sided"]) else 0)
+            inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, flags=[gf], vertex_stride=12))
+            keep += [d_pos, d_nrm, d_idx] + d_uv
+            # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, 16-byte aligned union @16 holding TriangleMesh{indices, positions,
+            # normals, texcoords[2], colors}}; BufferView = {ptr, count, u16 stride, u16 elmt}.  Offsets pinned against the reference
+            # headers: tests/golden/kat.json "hitgroup_layout" (tests/test_oracle_kat.py)
+            geo = bytearray(112)
+
+            def bview(t, elmt, stride):
+                return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride if t is not None else 0,
+                                   elmt if t is not None else 0)
+            isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
+            geo[HG_OFF_INDICES:HG_OFF_INDICES + 16] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
+            geo[HG_OFF_POSITIONS:HG_OFF_POSITIONS + 16] = bview(d_pos, 12, 12)
+            geo[HG_OFF_NORMALS:HG_OFF_NORMALS + 16] = bview(d_nrm, 12, 12)
+            geo[64:80] = bview(d_uv[0], 8, 8)
+            geo[80:96] = bview(d_uv[1], 8, 8)
+            recs.append(bytes(geo) + pack_material(mat, tex_objects))
+        mesh_accels.append(ctx.build_accel(inputs, compact=True))
+        mesh_records.append(recs)
+    return mesh_accels, mesh_records, keep
+
+
 class Raycaster:
     """Mirror of optixRaycasting's state (optixRaycasting.cpp:94-349) for a loaded glTF scene: one GAS per mesh
     (one build input per primitive group), an IAS over the mesh instances, whitted::HitGroupData SBT records."""
@@ -544,38 +607,15 @@ class Raycaster:
         self.ctx = ctx
         self.scene = scene
         dev = ctx.torch_device
-        self.mesh_accels, self.keep = [], []
         self.programs = ctx.prepare_programs("raycast")
-        records = []
-        self.mesh_sbt_base = []
-        for m in scene["meshes"]:
-            inputs = []
+        # createSBT (optixRaycasting.cpp:219-237): one record per primitive group holding the mesh views and the scene's MaterialData —
+        # __anyhit__texture_mask reads alpha_mode / alpha_cutoff / base_color_tex from it
+        self.tex_objects, self._tex_handles = create_scene_textures(ctx, scene)
+        self.mesh_accels, mesh_records, self.keep = build_scene_meshes(ctx, scene, self.tex_objects)
+        records, self.mesh_sbt_base = [], []
+        for recs in mesh_records:
             self.mesh_sbt_base.append(len(records))
-            for p in m["primitives"]:
-                d_pos = ctx.to_device(p["positions"])
-                d_nrm = ctx.to_device(p["normals"]) if p["normals"] is not None else None
-                idx = p["indices"]
-                d_idx = None
-                if idx is not None:
-                    d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
-                inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, vertex_stride=12))
-                self.keep += [d_pos, d_nrm, d_idx]
-                # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, 16-byte aligned union @16 holding TriangleMesh{indices,
-                # positions, normals, texcoords[2], colors}}; BufferView = {ptr, count, u16 stride, u16 elmt}.  Offsets pinned against the
-                # reference headers: tests/golden/kat.json "hitgroup_layout" (tests/test_oracle_kat.py)
-                rec = bytearray(32 + 352)
-                rec[0:32] = ctx.sbt_header(self.programs, 2, 0)
-                def bview(t, elmt, stride):
-                    return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride, elmt)
-                isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
-                o = 32 + HG_OFF_INDICES
-                rec[o:o + 16] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
-                o = 32 + HG_OFF_POSITIONS
-                rec[o:o + 16] = bview(d_pos, 12, 12)
-                o = 32 + HG_OFF_NORMALS
-                rec[o:o + 16] = bview(d_nrm, 12, 12)
-                records.append(bytes(rec))
-            self.mesh_accels.append(ctx.build_accel(inputs, compact=compact))
+            records += [ctx.sbt_header(self.programs, 2, 0) + data for data in recs]
         self.d_hitgroup = ctx.to_device(np.frombuffer(b"".join(records), np.uint8).copy())
         inst = []
         for i in scene["instances"]:
@@ -628,6 +668,11 @@ class Raycaster:
         ctx.launch_raycast(self.programs, self.d_params.data_ptr(), self.sbt, self.width, self.height, self.ext.data_ptr() if want_ext else 0)
         ctx.launch_raycast(self.programs, self.d_params_translated.data_ptr(), self.sbt, self.width, self.height,
                            self.ext_translated.data_ptr() if want_ext else 0)
+
+    def close(self):
+        for hc, tex, arr in self._tex_handles:
+            hc.lib.b200rt_texture_destroy(hc.h, tex, arr)
+        self._tex_handles = []
 
     def shade(self, hits):
         ctx = getattr(self.ctx, "helper", self.ctx)
@@ -806,58 +851,10 @@ class MeshViewer:
 
     def __init__(self, ctx, scene, width, height):
         self.ctx, self.scene, self.width, self.height = ctx, scene, width, height
-        hc = getattr(ctx, "helper", ctx)
         dev = ctx.torch_device
         self.programs = ctx.prepare_programs("whitted")
-        # Scene::addImage / addSampler (Scene.cpp:576-652): one texture object per glTF texture (sampler wrap modes; linear unless NEAREST)
-        self.tex_objects, self._tex_handles = {}, []
-        wrap = {10497: 0, 33071: 1, 33648: 2}
-        for ti, t in enumerate(scene.get("textures", [])):
-            img = scene["images"][t["source"]] if t.get("source") is not None else None
-            if img is None:
-                self.tex_objects[ti] = None
-                continue
-            smp = scene["samplers"][t["sampler"]] if t.get("sampler") is not None and scene.get("samplers") else {}
-            linear = 0 if smp.get("magFilter") == 9728 else 1
-            tex, arr = C.c_uint64(), C.c_uint64()
-            hc.check(hc.lib.b200rt_texture_create(hc.h, img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p), wrap.get(smp.get("wrapS", 10497), 0),
-                                                  wrap.get(smp.get("wrapT", 10497), 0), linear, C.byref(tex), C.byref(arr)), "texture_create")
-            self.tex_objects[ti] = tex.value
-            self._tex_handles.append((hc, tex.value, arr.value))
-        materials = scene.get("materials", [])
-        self.keep, self.mesh_accels, mesh_records = [], [], []
-        for m in scene["meshes"]:
-            inputs, recs = [], []
-            for p in m["primitives"]:
-                d_pos = ctx.to_device(p["positions"])
-                d_nrm = ctx.to_device(p["normals"]) if p.get("normals") is not None else None
-                idx = p["indices"]
-                d_idx = None
-                if idx is not None:
-                    d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
-                uvs = p.get("texcoords") or [None, None]
-                d_uv = [ctx.to_device(u) if u is not None else None for u in uvs]
-                mat = materials[p["material"]] if p.get("material", -1) >= 0 and p["material"] < len(materials) else None
-                # geometry flags by material (Scene.cpp:904-966): OPAQUE -> DISABLE_ANYHIT, MASK -> NONE, BLEND -> REQUIRE_SINGLE_ANYHIT_CALL;
-                # doubleSided adds DISABLE_TRIANGLE_FACE_CULLING
-                am = 0 if mat is None else mat["alpha_mode"]
-                gf = {0: 1, 1: 0, 2: 2}[am] | (4 if (mat is not None and mat["double_sided"]) else 0)
-                inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, flags=[gf], vertex_stride=12))
-                self.keep += [d_pos, d_nrm, d_idx] + d_uv
-                geo = bytearray(112)
-
-                def bview(t, elmt, stride):
-                    return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride if t is not None else 0,
-                                       elmt if t is not None else 0)
-                isz = 0 if idx is None else (2 if idx.dtype == np.uint16 else 4)
-                geo[HG_OFF_INDICES:HG_OFF_INDICES + 16] = struct.pack("<QIHH", d_idx.data_ptr() if d_idx is not None else 0, 0 if idx is None else idx.shape[0], isz, isz)
-                geo[HG_OFF_POSITIONS:HG_OFF_POSITIONS + 16] = bview(d_pos, 12, 12)
-                geo[HG_OFF_NORMALS:HG_OFF_NORMALS + 16] = bview(d_nrm, 12, 12)
-                geo[64:80] = bview(d_uv[0], 8, 8)
-                geo[80:96] = bview(d_uv[1], 8, 8)
-                recs.append(bytes(geo) + pack_material(mat, self.tex_objects))
-            self.mesh_accels.append(ctx.build_accel(inputs, compact=True))
-            mesh_records.append(recs)
+        self.tex_objects, self._tex_handles = create_scene_textures(ctx, scene)
+        self.mesh_accels, mesh_records, self.keep = build_scene_meshes(ctx, scene, self.tex_objects)
         # createSBT (Scene.cpp:1405-1433): per INSTANCE, per primitive group: radiance record + occlusion record (same data)
         records, inst = [], []
         for i in scene["instances"]:

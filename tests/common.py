@@ -23,6 +23,23 @@ def duck_scene(textured=True):
             "samplers": [{"magFilter": 9729, "minFilter": 9986, "wrapS": 10497, "wrapT": 10497}]}
 
 
+def duck_alpha_scene(alpha_mode, cutoff=0.5):
+    """duck_scene() with the base-colour texture's alpha channel turned into a pattern of holes (0), solid (255) and smooth ramps in between
+    — the role DuckHole.gltf's DuckHole.png plays in the reference (alphaMode MASK, alphaCutoff 0.5) — and the material's alpha mode set
+    (1 = MASK, 2 = BLEND)."""
+    sc = duck_scene()
+    img = sc["images"][0].copy()
+    h, w = img.shape[:2]
+    yy, xx = np.mgrid[0:h, 0:w]
+    ramp = (128 + 127 * np.sin(xx / 9.0) * np.cos(yy / 7.0)).astype(np.int64)
+    holes = ((xx // 16 + yy // 16) % 3 == 0)
+    solid = ((xx // 16 + yy // 16) % 3 == 1)
+    img[..., 3] = np.where(holes, 0, np.where(solid, 255, ramp)).astype(np.uint8)
+    sc["images"][0] = np.ascontiguousarray(img)
+    sc["materials"][0].update({"alpha_mode": alpha_mode, "alpha_cutoff": cutoff})
+    return sc
+
+
 def deindex(prim):
     """(ntri,3,3) object-space triangles and per-triangle vertex normals of one primitive group."""
     idx = prim["indices"].astype(np.int64).reshape(-1, 3)

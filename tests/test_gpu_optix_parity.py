@@ -83,6 +83,33 @@ def test_duck_raycasting_matches_the_reference_programs_on_optix(ctxs):
     assert (_ulps(got["t"][hit], ref["t"][hit]) <= 8).all()
 
 
+def test_alpha_mask_raycasting_matches_the_reference_anyhit_on_optix(ctxs):
+    """optixRaycasting's default input is DuckHole.gltf (alphaMode MASK): __anyhit__texture_mask (optixRaycasting.cu:89-102) discards
+    hits whose base-colour alpha is below the cutoff, so rays pass through the holes and hit what lies behind."""
+    from optix_raytracer_b200 import host
+    bctx, octx = ctxs
+    sc = common.duck_alpha_scene(1)
+    b, o = host.Raycaster(bctx, sc), host.Raycaster(octx, sc)
+    opaque = host.Raycaster(bctx, common.duck_scene())
+    for r in (b, o, opaque):
+        r.buffer_rays(640)
+    b.launch()
+    o.launch(want_ext=False)
+    opaque.launch()
+    torch.cuda.synchronize()
+    hb, ho, hq = b.hits.cpu().numpy(), o.hits.cpu().numpy(), opaque.hits.cpu().numpy()
+    changed = (hq[:, 0] != ho[:, 0]).mean()
+    assert changed > 0.02, f"the mask changes only {changed:.4f} of the rays: the test would not see a missing any-hit program"
+    # texels right at the cutoff may fall either way (hardware bilinear filtering at 8-bit weights is identical, but t and the
+    # barycentrics differ by ulps between the two triangle tests): a handful of rays, never a pattern
+    differ = hb[:, 0].view(np.uint32) != ho[:, 0].view(np.uint32)
+    assert differ.mean() < 2e-4, f"{differ.sum()} of {differ.size} rays disagree with the reference any-hit program"
+    same = ~differ & (ho[:, 0] >= 0)
+    assert np.abs(hb[same, 1:] - ho[same, 1:]).max() <= 1e-5
+    for r in (b, o, opaque):
+        r.close()
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_cornell_image_matches_optix_at_the_same_seeds(ctxs, mode):
     """optixPathTracer (mode 0) / optixMultiGPU (mode 1) device programs on OptiX vs the wavefront restatement."""
