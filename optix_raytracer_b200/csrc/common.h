@@ -35,8 +35,9 @@ struct b200rt_context_t {
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING
     unsigned int counter_slot = 0;  // rotating fetch-counter slot for persistent ray launches
     // whitted launches: light count the workspace was sized for, learnt from the first launch with a given d_params (whitted.cu)
-    uint64_t w_params = 0;
-    unsigned int w_lights = 0;
+    uint64_t w_params = 0, w_sbt = 0;
+    unsigned int w_lights = 0, w_sbt_count = 0;
+    bool w_blend = false;     // the hit-group records hold an ALPHA_MODE_BLEND material (continuation levels are run)
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 

@@ -230,7 +230,7 @@ struct PTWork {
     }
     __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
-        if (f.handle->kind == ACCEL_KIND_GAS) return false;
+        if (f.handle->kind == ACCEL_KIND_GAS || any_ray_done(s)) return false;
         float3 o, d;
         if (s.pack & TP_ANY) { const float4 so = L.shd_o[lane], sd = L.shd_d[lane]; o = f3(so.x, so.y, so.z); d = f3(sd.x, sd.y, sd.z); }
         else { const float4 ro = L.ray_o[lane], rd = L.ray_d[lane]; o = f3(ro.x, ro.y, ro.z); d = f3(rd.x, rd.y, rd.z); }

@@ -109,7 +109,7 @@ struct RayWork {
     }
     __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
-        if (handle->kind == ACCEL_KIND_GAS) return false;
+        if (handle->kind == ACCEL_KIND_GAS || any_ray_done(s)) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
         return trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
                                  cull_flags((uint32_t)item), s.inst + 1u);

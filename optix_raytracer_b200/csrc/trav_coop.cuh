@@ -280,6 +280,9 @@ __device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ sta
     return (s.pack & TP_F32) ? trav_node_step_f32(s, stack, st) : trav_node_step_q8(s, stack, st);
 }
 
+// TERMINATE_ON_FIRST_HIT rays stop at the first accepted hit: no further instance is traversed
+__device__ __forceinline__ bool any_ray_done(const Trav& s) { return (s.pack & TP_ANY) && (s.pack & TP_FOUND_ANY); }
+
 // Arithmetic of tri_test (traverse.cuh) for one (ray, triangle) unit, without the acceptance bookkeeping: returns
 // true when tmin < t <= tfar and the face-cull flags let the triangle through; the owner decides ties.
 __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const float4 q0, const float4 q1, const float4 q2, float tfar, float& t_out,
@@ -303,7 +306,10 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 
 // Work concept:
 //   __device__ bool  fetch(uint32_t item, Trav& s, float* my_ray)  load item, set s.best.t = tmax, call trav_begin_handle; false = nothing to trace
-//   __device__ bool  next_instance(Trav& s, float* my_ray)         IAS: set up the next instance (true) or report none left (false)
+//   __device__ bool  next_instance(Trav& s, float* my_ray)         the traversal set up last has ended: set up the next instance of an IAS — or,
+//                                                                  for items made of several rays (whitted.cu), the item's next ray — and
+//                                                                  return true; false = the item is finished.  An any-hit ray that found
+//                                                                  its hit ends here too (any_ray_done)
 //   __device__ void  commit(const Trav& s, bool found)             store the result of the finished item
 //   static constexpr bool ANYHIT                                   any-hit programs exist: a candidate hit on a triangle whose geometry
 //                                                                  flags lack DISABLE_ANYHIT is put to
@@ -372,7 +378,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                 }
                 if (!(s.ngroup.y & NODE_BITS) && !blocked) {
                     if (s.tgroup.y != 0u) blocked = true;  // only the parked triangles are left
-                    else if (!((s.pack & TP_ANY) && (s.pack & TP_FOUND_ANY)) && work.next_instance(s, my_ray)) { /* next instance set up */ }
+                    else if (work.next_instance(s, my_ray)) { /* next instance (or the item's next ray) set up */ }
                     else { has = false; fin = true; }
                 }
             }

@@ -28,6 +28,7 @@
 #include <cstring>
 #include <limits>
 #include <thread>
+#include <functional>
 #include <vector>
 
 namespace {
@@ -1135,9 +1136,11 @@ uint64_t orc_playground_scene(uint32_t rows, uint32_t seed, float* verts, float*
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
-// optixMeshViewer — SDK/cuda/whitted.cu:44-98,139-289 + getLocalGeometry (SDK/cuda/LocalGeometry.h:59-163) for OPAQUE,
-// UNTEXTURED materials (texture fetches are hardware tex2D in the reference and in the product; they are compared on the GPU
-// against the reference programs running on OptiX, tests/test_gpu_optix_parity.py).  Same op order as csrc/whitted.cu.
+// optixMeshViewer — SDK/cuda/whitted.cu:44-98,139-289 + getLocalGeometry (SDK/cuda/LocalGeometry.h:59-163) for UNTEXTURED
+// materials (texture fetches are hardware tex2D in the reference and in the product; they are compared on the GPU against the
+// reference programs running on OptiX, tests/test_gpu_optix_parity.py).  alpha_mode 2 = ALPHA_MODE_BLEND: result * alpha plus the
+// continuation of the ray from the hit times (1 - alpha), depth < 8 (whitted.cu:266-286); without a texture the any-hit programs
+// accept every hit (whitted.cu:100-137).  Same op order as csrc/whitted.cu.
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -1149,6 +1152,7 @@ struct orc_whitted_params {
     float metallic, roughness;
     float emissive[3];
     int32_t nlights;
+    int32_t alpha_mode;  // 0 OPAQUE, 1 MASK, 2 BLEND
 };
 
 // normals: ntri*9 floats or NULL (geometric normal); lights: nlights x 36-byte Light records; accum: width*height*4 floats
@@ -1172,12 +1176,15 @@ uint64_t orc_whitted(void* scene, const orc_whitted_params* p, const float* norm
             if (p->subframe_index != 0) { jx = rnd(seed); jy = rnd(seed); }
             const float dx = fm(2.0f, ((float)ix + jx) / (float)p->width, -1.0f), dy = fm(2.0f, ((float)iy + jy) / (float)p->height, -1.0f);
             const f3 dir = normalize(mk(fm(dy, V.x, dx * U.x) + W.x, fm(dy, V.y, dx * U.y) + W.y, fm(dy, V.z, dx * U.z) + W.z));
+            // traceRadiance + __miss__constant_radiance / __closesthit__radiance; payload_depth is what the caller put in the payload
+            std::function<f3(float, uint32_t)> radiance = [&](float tmin, uint32_t payload_depth) -> f3 {
             ++nrays[(size_t)tid];
-            const SceneHit h = trace_scene<false>(*s, eye, dir, 0.0f, 1e16f, 16u /* CULL_BACK_FACING_TRIANGLES */);
+            const SceneHit h = trace_scene<false>(*s, eye, dir, tmin, 1e16f, 16u /* CULL_BACK_FACING_TRIANGLES */);
             f3 result;
             if (!h.hit) {
                 result = ld3(p->miss_color);
             } else {
+                const uint32_t depth = payload_depth + 1u;
                 const Instance* in = s->insts.empty() ? nullptr : &s->insts[h.inst];
                 const Geometry& g = s->geoms[in ? in->geom : 0];
                 const Tri& tr = g.tris[h.prim];
@@ -1207,6 +1214,7 @@ uint64_t orc_whitted(void* scene, const orc_whitted_params* p, const float* norm
                 for (int li = 0; li < p->nlights; ++li) {
                     const LightRec& l = L[li];
                     if (l.type == 0) {
+                        if (!(depth < 8u)) continue;  // MAX_TRACE_DEPTH
                         const f3 Lv = mk(l.position[0] - P.x, l.position[1] - P.y, l.position[2] - P.z);
                         const float L_dist = length(Lv);
                         const f3 Ld = mk(Lv.x / L_dist, Lv.y / L_dist, Lv.z / L_dist);
@@ -1232,7 +1240,18 @@ uint64_t orc_whitted(void* scene, const orc_whitted_params* p, const float* norm
                         result = result + mk(l.color[0] * bc[0], l.color[1] * bc[1], l.color[2] * bc[2]);
                     }
                 }
+                if (p->alpha_mode == 2) {
+                    result = mk(result.x * bc[3], result.y * bc[3], result.z * bc[3]);
+                    if (depth < 8u) {
+                        const f3 deeper = radiance(h.t, depth);  // tmin = optixGetRayTmax()
+                        const float w = 1.0f - bc[3];
+                        result = mk(fm(deeper.x, w, result.x), fm(deeper.y, w, result.y), fm(deeper.z, w, result.z));
+                    }
+                }
             }
+            return result;
+            };
+            f3 result = radiance(0.0f, 0u);
             const size_t idx = (size_t)iy * p->width + ix;
             if (p->subframe_index > 0) {
                 const float a = 1.0f / (float)(p->subframe_index + 1);

@@ -75,7 +75,7 @@ def ncores():
 class WhittedParams(C.Structure):  # oracle.cpp: orc_whitted_params
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("subframe_index", C.c_uint32), ("eye", C.c_float * 3), ("U", C.c_float * 3),
                 ("V", C.c_float * 3), ("W", C.c_float * 3), ("miss_color", C.c_float * 3), ("base_color", C.c_float * 4), ("metallic", C.c_float),
-                ("roughness", C.c_float), ("emissive", C.c_float * 3), ("nlights", C.c_int32)]
+                ("roughness", C.c_float), ("emissive", C.c_float * 3), ("nlights", C.c_int32), ("alpha_mode", C.c_int32)]
 
 
 class PTParams(C.Structure):
@@ -123,12 +123,14 @@ def make_color(rgb):
 class Scene:
     """Triangle soup (ntri,3,3) float32 in object space + optional per-triangle SBT offsets and instances."""
 
-    def __init__(self, tris, sbt=None, instances=()):
+    def __init__(self, tris, sbt=None, instances=(), geom_flags=None):
         self.tris = _f32(tris).reshape(-1, 9)
         self.sbt = None if sbt is None else np.ascontiguousarray(sbt, dtype=np.uint32)
         self.h = lib().orc_scene_create(_p(self.tris), self.tris.shape[0], _p(self.sbt))
         for m in instances:
             lib().orc_scene_add_instance(self.h, _p(_f32(m).reshape(12)))
+        if geom_flags is not None:  # OptixGeometryFlags of the build input (4 = DISABLE_TRIANGLE_FACE_CULLING)
+            lib().orc_scene_set_geometry_flags(self.h, int(geom_flags))
 
     def set_brute(self, brute):
         lib().orc_scene_set_brute(self.h, int(bool(brute)))
@@ -187,7 +189,7 @@ class Scene:
         return film, image, int(n)
 
     def whitted(self, params, lights36, normals=None, accum=None, rows=None, threads=None):
-        """optixMeshViewer frame for an untextured OPAQUE material (oracle.cpp: orc_whitted).  Returns (accum (h,w,4), frame (h,w,4) u8, rays)."""
+        """optixMeshViewer frame for an untextured material (params.alpha_mode 2 = BLEND) (oracle.cpp: orc_whitted).  Returns (accum (h,w,4), frame (h,w,4) u8, rays)."""
         w, h = params.width, params.height
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)

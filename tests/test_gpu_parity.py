@@ -224,17 +224,23 @@ def test_playground_bit_exact(ctx, orc, aperture, ortho):
         assert np.abs(pg.image.cpu().numpy().astype(np.int32) - image.astype(np.int32)).max() <= 1
 
 
-def test_whitted_untextured_bit_exact(ctx, orc):
+@pytest.mark.parametrize("alpha_mode,double_sided", [(0, False), (2, False), (2, True)])
+def test_whitted_untextured_bit_exact(ctx, orc, alpha_mode, double_sided):
     """optixMeshViewer (BASELINE.json configs[2]) on the Duck with its texture removed: accum bit-exact against the oracle over
-    two subframes (pixel-centre ray, then jittered + running mean), frame within 1 LSB.  Textured shading is compared on the
-    GPU against the reference programs on OptiX (tests/test_gpu_optix_parity.py)."""
+    two subframes (pixel-centre ray, then jittered + running mean), frame within 1 LSB.  alpha_mode 2 = ALPHA_MODE_BLEND with
+    base-colour alpha 0.6: every hit continues behind itself (whitted.cu:266-286); doubleSided lifts the back-face culling of the
+    radiance rays, so the chain gets a second level inside the duck.  Textured shading is compared on the GPU against the
+    reference programs on OptiX (tests/test_gpu_optix_parity.py)."""
     from optix_raytracer_b200 import host
     sc = common.duck_scene(textured=False)
+    if alpha_mode:
+        sc["materials"][0].update({"alpha_mode": alpha_mode, "double_sided": double_sided, "base_color": [1.0, 0.9, 0.8, 0.6]})
     w, h = 160, 120
     mv = host.MeshViewer(ctx, sc, w, h)
     prim = sc["meshes"][0]["primitives"][0]
     tris, nrm = common.deindex(prim)
-    scene = orc.Scene(tris, None, instances=[sc["instances"][0]["transform"][:3, :].reshape(12)])
+    scene = orc.Scene(tris, None, instances=[sc["instances"][0]["transform"][:3, :].reshape(12)],
+                      geom_flags=4 if double_sided else 0)
     p = orc.WhittedParams()
     p.width, p.height = w, h
     for k in ("eye", "U", "V", "W", "miss_color"):
@@ -243,8 +249,10 @@ def test_whitted_untextured_bit_exact(ctx, orc):
     p.base_color = (C.c_float * 4)(*m["base_color"])
     p.metallic, p.roughness = m["metallic"], m["roughness"]
     p.emissive = (C.c_float * 3)(*m["emissive_factor"])
+    p.alpha_mode = alpha_mode
     lights = mv.d_lights.cpu().numpy().tobytes()
     accum = None
+    opaque_rays = None
     for sub in range(2):
         mv.launch_subframe(sub)
         torch.cuda.synchronize()
@@ -257,18 +265,3 @@ def test_whitted_untextured_bit_exact(ctx, orc):
     mv.close()
 
 
-def test_whitted_reports_unsupported_alpha_modes(ctx):
-    """MASK / BLEND materials need the any-hit programs (not built yet): the launch that meets one renders it opaque and the
-    next launch on the context fails with NOT_SUPPORTED (asynchronous error, like CUDA's) — never a silent wrong picture."""
-    from optix_raytracer_b200 import host
-    sc = common.duck_scene(textured=False)
-    sc["materials"][0]["alpha_mode"] = 1
-    mv = host.MeshViewer(ctx, sc, 64, 48)
-    mv.launch_subframe(0)
-    torch.cuda.synchronize()
-    with pytest.raises(host.B200RTError, match="NOT_SUPPORTED|7800|UNSUPPORTED"):
-        mv.launch_subframe(1)
-    # the flag is consumed: an opaque scene renders again on the same context
-    ok = host.MeshViewer(ctx, common.duck_scene(textured=False), 64, 48)
-    ok.launch_subframe(0)
-    torch.cuda.synchronize()
