@@ -58,7 +58,7 @@ __device__ __forceinline__ float ah_base_alpha(const char* __restrict__ rec, uin
 
 // Returns true when the hit stands, false for optixIgnoreIntersection().  `factor` multiplies the occlusion ray's pending
 // attenuation (1 = unchanged).  `sbt_local` is the triangle's GAS-local SBT index, `inst_sbt` the instance's sbtOffset (0 for a GAS).
-static __device__ __noinline__ bool run_anyhit(AnyHitCfg c, uint32_t prim, uint32_t sbt_local, uint32_t inst_sbt, bool occlusion, float b1, float b2, float& factor)
+static __device__ __forceinline__ bool run_anyhit(AnyHitCfg c, uint32_t prim, uint32_t sbt_local, uint32_t inst_sbt, bool occlusion, float b1, float b2, float& factor)
 {
     factor = 1.0f;
     const uint32_t ray_types = c.mode == AH_WHITTED ? 2u : 1u;

@@ -37,7 +37,12 @@ struct b200rt_context_t {
     // whitted launches: light count the workspace was sized for, learnt from the first launch with a given d_params (whitted.cu)
     uint64_t w_params = 0, w_sbt = 0;
     unsigned int w_lights = 0, w_sbt_count = 0;
+    bool w_anyhit = false;    // the scene holds geometry that runs the any-hit programs (AccelHeader::anyhit of LaunchParams.handle)
     bool w_blend = false;     // the hit-group records hold an ALPHA_MODE_BLEND material (continuation levels are run)
+    // optixRaycasting launches: does the traversable of this d_params hold any-hit geometry?  (read once per d_params, forgotten at
+    // the next accel build)
+    uint64_t rc_params = 0;
+    bool rc_anyhit = false;
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 

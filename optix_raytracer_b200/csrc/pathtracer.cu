@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
 // optixPathTracer.cpp:702 / optixMultiGPU.cpp:794); an IAS handle is traversed instance by instance all the same.
 template <int MODE>
 struct PTWork {
+    static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = false;  // the Cornell programs have no any-hit (optixPathTracer.cpp:748-767)
     const Frame& f;
     const Lanes& L;

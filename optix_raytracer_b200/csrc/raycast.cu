@@ -68,6 +68,7 @@ __device__ __forceinline__ ExtHit make_ext(const Trav& s, bool found)
 // programs -> Hit (+ optional ExtHit).  AH: the launch has any-hit programs (anyhit.cuh) and the scene may hold geometry that runs them.
 template <int KIND, bool AH>
 struct RayWork {
+    static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
     AnyHitCfg ah;
     double att;  // AH, KIND 1: pending occlusion attenuation of this lane's ray
@@ -345,13 +346,32 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
-    // __anyhit__texture_mask (optixRaycasting.cu:89-102) needs the material and the texture coordinates of whitted::HitGroupData; a
-    // record too short to hold them (geometry only) runs without any-hit programs
+    // __anyhit__texture_mask (optixRaycasting.cu:89-102) needs the material and the texture coordinates of whitted::HitGroupData (a
+    // record too short to hold them runs without any-hit programs) and only ever runs on geometry that leaves any-hit enabled: whether
+    // the traversable has any is read from its header once per d_params (one synchronisation; forgotten at the next accel build)
     const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
-    const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, full_records ? AH_TEXTURE_MASK : AH_NONE};
-    trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
-        nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah);
+    if (full_records && ctx->rc_params != d_params) {
+        RaycastParamsDev hp;
+        B2_CUDA(ctx, cudaMemcpyAsync(&hp, (const void*)d_params, sizeof(hp), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        B2_REQUIRE(ctx, hp.handle, "Params.handle is null");
+        AccelHeader ah;
+        B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "Params.handle is not a b200rt traversable");
+        ctx->rc_params = d_params;
+        ctx->rc_anyhit = ah.anyhit != 0;
+    }
+    if (full_records && ctx->rc_anyhit) {
+        const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, AH_TEXTURE_MASK};
+        trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
+            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
+            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah);
+    } else {
+        trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
+            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
+            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
+    }
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

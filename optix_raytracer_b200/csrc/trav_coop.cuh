@@ -311,6 +311,9 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 //                                                                  return true; false = the item is finished.  An any-hit ray that found
 //                                                                  its hit ends here too (any_ray_done)
 //   __device__ void  commit(const Trav& s, bool found)             store the result of the finished item
+//   static constexpr bool CONTINUES                                true: instead of commit, the finished lanes call
+//   __device__ bool  commit_continue(Trav& s, float* my_ray, found) together; it may start another ray of the same item (true) — the place
+//                                                                  for work that should run with many lanes at once (shading, whitted.cu)
 //   static constexpr bool ANYHIT                                   any-hit programs exist: a candidate hit on a triangle whose geometry
 //                                                                  flags lack DISABLE_ANYHIT is put to
 //   __device__ bool  anyhit(prim, sbt, inst, pack, b1, b2, factor) (called by whichever lane tested the triangle: it may only use state
@@ -337,7 +340,11 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
     bool has = false, fin = false, exhausted = false;
     for (;;) {
         // ---- commit finished rays together, then every lane without a ray takes the next work item
-        if (fin) { work.commit(s, (s.pack & TP_FOUND_ANY) != 0u); fin = false; }
+        if (fin) {
+            if constexpr (Work::CONTINUES) { if (work.commit_continue(s, my_ray, (s.pack & TP_FOUND_ANY) != 0u)) has = true; }
+            else work.commit(s, (s.pack & TP_FOUND_ANY) != 0u);
+            fin = false;
+        }
         unsigned need = __ballot_sync(FULL, !has && !exhausted);
         while (need) {
             const int leader = __ffs(need) - 1;

@@ -199,6 +199,36 @@ def main():
     del bmv, omv
     checkpoint()
 
+    # ---- 3b'. alpha materials: the any-hit programs (optixRaycasting.cu:89-102, whitted.cu:100-137) and the BLEND continuation ----------
+    alpha = {}
+    sc = common.duck_alpha_scene(1)
+    brc2, orc2 = host.Raycaster(bctx, sc), host.Raycaster(octx, sc)
+    nray2 = brc2.buffer_rays(1040); orc2.buffer_rays(1040)
+    brc2.launch(want_ext=False); orc2.launch(want_ext=False)
+    torch.cuda.synchronize()
+    hb, ho = brc2.hits.cpu().numpy(), orc2.hits.cpu().numpy()
+    tb = cuda_ms(lambda: brc2.launch(want_ext=False)); to = cuda_ms(lambda: orc2.launch(want_ext=False))
+    alpha["raycast_mask"] = {"rays_per_batch": nray2, "Hit.t_differs": int((hb[:, 0].view(np.uint32) != ho[:, 0].view(np.uint32)).sum()),
+                             "hits_optix": int((ho[:, 0] >= 0).sum()), "ms_two_batches_b200rt": tb, "ms_two_batches_optix": to, "speedup": to / tb}
+    brc2.close(); orc2.close()
+    for name, mode, ds in (("whitted_mask", 1, False), ("whitted_blend", 2, False), ("whitted_blend_double_sided", 2, True)):
+        sc = common.duck_alpha_scene(mode)
+        sc["materials"][0]["double_sided"] = ds
+        bmv, omv = host.MeshViewer(bctx, sc, 1920, 1080), host.MeshViewer(octx, sc, 1920, 1080)
+        for sub in range(4):
+            bmv.launch_subframe(sub); omv.launch_subframe(sub)
+        torch.cuda.synchronize()
+        ab, ao = bmv.accum.cpu().numpy()[..., :3].astype(np.float64), omv.accum.cpu().numpy()[..., :3].astype(np.float64)
+        fb, fo = bmv.frame.cpu().numpy()[..., :3].astype(np.float64), omv.frame.cpu().numpy()[..., :3].astype(np.float64)
+        mse8 = np.mean((fb - fo) ** 2)
+        tb = cuda_ms(lambda: bmv.launch_subframe(5)); to = cuda_ms(lambda: omv.launch_subframe(5))
+        alpha[name] = {"rel_mean_diff": float(abs(ab.mean() - ao.mean()) / ao.mean()), "psnr_u8_db": float(10 * np.log10(255.0 ** 2 / max(mse8, 1e-12))),
+                       "ms_per_subframe_b200rt": tb, "ms_per_subframe_optix": to, "speedup": to / tb}
+        bmv.close(); omv.close()
+        del bmv, omv
+    rep["alpha_materials_duck"] = alpha
+    checkpoint()
+
     # ---- 3c. imgui_test (optixTriangle.cu), 1920x1080, stand-in scene of 1.74 M triangles, two cameras x two apertures ------------
     pgr = {}
     for name, cam_kw in (("reference_camera", {}), ("close_camera", {"eye": (0.5, 0.7, -1.4), "up": (0.0, 1.0, 0.000073), "lookat": (0.0, 0.1, 0.0), "fov": 50.0})):
