@@ -102,7 +102,8 @@ struct RayWork {
         if (AH) att = 1.0;
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
-        if (!trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
+        // rays of a buffer come from anywhere: those that pass the scene (or an instance) by are dropped at its bounds
+        if (!trav_begin_handle<true>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
             commit(s, false);
             return false;
         }
@@ -112,7 +113,7 @@ struct RayWork {
     {
         if (handle->kind == ACCEL_KIND_GAS || any_ray_done(s)) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
-        return trav_begin_handle(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
+        return trav_begin_handle<true>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
                                  cull_flags((uint32_t)item), s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
@@ -180,8 +181,11 @@ struct RayWork {
 
 struct RaycastParamsDev { uint64_t handle; const float4* rays; float4* hits; };  // optixRaycasting.h:41-46
 
+#ifndef B200RT_RAY_MIN_CTAS
+#define B200RT_RAY_MIN_CTAS 8
+#endif
 template <int KIND, bool STATS, bool AH>
-__global__ void __launch_bounds__(COOP_BLOCK, 8) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
                                                           uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
                                                           const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
                                                           uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,

@@ -17,13 +17,15 @@
 //                                        (anyhit.cuh, run inside traversal)
 //   ALPHA_MODE_BLEND continuation (266-286)  result = result * alpha + trace(same ray, tmin = t, depth + 1) * (1 - alpha), depth < 8
 //
-// ONE launch per subframe (one sample per pixel and launch, as the reference): a persistent traversal kernel (trav_coop.cuh) whose work
-// item is a pixel.  The lane that fetched it generates the camera ray, and when the ray ends it either writes the pixel (miss) or shades
-// the hit and goes on with the item's shadow probes and, for ALPHA_MODE_BLEND, with the continuation ray of the next level; the levels
-// are folded back to front exactly as the recursion of the reference returns (struct WWork below).  Shading runs where the finished
-// lanes of a warp meet (commit_continue), so it is executed by several lanes at once.  Nothing but the per-lane scratch of the lights
-// (a few MB, L2 resident) goes through memory between the stages; measured against the five-stage wavefront pipeline this replaced:
-// profiles/r01_optix_compare.json.
+// Three launches per subframe for a scene without BLEND materials (one sample per pixel and launch, as the reference):
+//   PRIMARY  persistent traversal (trav_coop.cuh) whose fetch generates the camera ray and whose commit writes the pixel of a miss
+//            straight away (the reference's miss program + raygen tail) or a 48-byte hit slot
+//   SHADE    one thread per hit slot: getLocalGeometry, the material, the per-light BRDF factors and shadow probes
+//   SHADOW   persistent traversal, one item per hit slot: its probes one after the other (TERMINATE_ON_FIRST_HIT, attenuation through
+//            the any-hit program), the terms summed in light order, the pixel accumulated and written in the commit
+// BLEND materials add levels: SHADE puts the continuation of a BLEND hit on a list, the host reads the count (the only
+// synchronisation, and only for scenes that have such materials) and runs PRIMARY / SHADE / SHADOW for the list; COMBINE then folds
+// each pixel's chain of levels back to front exactly as the recursion of the reference returns.
 #include <string.h>
 
 #include <algorithm>
@@ -162,29 +164,55 @@ constexpr uint32_t W_MAX_TRACE_DEPTH = 8;
 #ifndef B200RT_W_MIN_CTAS
 #define B200RT_W_MIN_CTAS 5
 #endif
-constexpr int W_MIN_CTAS = B200RT_W_MIN_CTAS;  // resident CTAs per SM the launch is compiled for (5 -> 96 registers, no spills; measured best)
+constexpr int W_MIN_CTAS = B200RT_W_MIN_CTAS;  // resident CTAs per SM the two traversal kernels are compiled for (5 -> 96 registers, no spills)
+constexpr uint32_t W_BLEND_SLOT_FACTOR = 4;  // hit-slot capacity per pixel when the scene has BLEND materials (chains of up to 8 levels)
 
-// asynchronous launch errors, written by the kernel into the context's pinned host block and reported by the NEXT launch
-// (like CUDA's own asynchronous errors)
-struct WAsyncFlags { unsigned int reserved; unsigned int too_many_lights; };
-
-// per-light scratch of the lane that shades a hit
-struct WTerm {
-    float4 t0;      // light colour xyz, intensity            (ambient: colour * base colour in xyz)
-    float4 t1;      // (diff + spec) xyz, N.L
-    float4 po, pd;  // shadow probe: origin | tmin, direction | tmax
+// one hit of a radiance ray (level 0: the camera ray; level l: the l-th BLEND continuation of a pixel)
+struct WSlot {
+    uint32_t pixel;
+    int parent;        // slot whose continuation this is (-1 at level 0)
+    float t;
+    uint32_t prim, inst;
+    float b1, b2;
+    uint32_t sbt;      // GAS-local SBT index of the triangle
+    int next;          // set by the next level: slot of the continuation's hit, W_NEXT_MISS, or W_NEXT_NONE (no continuation was traced)
+    uint32_t flags;    // WS_*
+    float one_minus_alpha;
+    uint32_t level;
 };
+static_assert(sizeof(WSlot) == 48, "WSlot");
+constexpr int W_NEXT_NONE = -1, W_NEXT_MISS = -2;
+constexpr uint32_t WS_BLEND = 1u;   // ALPHA_MODE_BLEND: the level's result is scaled by alpha and the continuation added
+constexpr uint32_t WS_CONT = 2u;    // a continuation ray was put on the list
 
-// launch constants, passed by value (constant bank)
+struct WCounters {
+    unsigned int nslots;   // hit slots allocated so far (all levels)
+    unsigned int ncont;    // continuation rays SHADE put on the list for the next level
+    unsigned int nchain;   // level-0 BLEND slots (pixels COMBINE has to fold)
+    unsigned int overflow; // hits dropped because the slot capacity was reached
+};
+// asynchronous launch errors, written by the kernels into the context's pinned host block and reported by the NEXT launch
+// (like CUDA's own asynchronous errors)
+struct WAsyncFlags { unsigned int unexpected_blend; unsigned int too_many_lights; unsigned int slot_overflow; };
+
+// everything the three stages share, passed by value (constant bank)
 struct WK {
     const WParams* params;
-    uint32_t width, height, nl_cap;
+    uint32_t width, height, nl_cap, level, level_start, cap_slots;
     const char* hg_base;
     uint32_t hg_stride, hg_count;
-    WTerm* terms;        // [persistent lane][light]
-    uint32_t* kinds;     // [persistent lane][light]: 0 nothing, 1 point light behind a shadow probe, 2 ambient term
-    float4* levels;      // [persistent lane][W_MAX_TRACE_DEPTH]: BLEND levels waiting for their continuation: result * alpha | 1 - alpha
-    unsigned int* fetch; // work-item cursor
+    uint32_t blend_levels;  // 1: the host runs the BLEND levels (it found such a material); 0: SHADE flags one as an error
+    WCounters* counters;
+    WSlot* slots;
+    float4* base;        // per slot: emission part of the result
+    float4* t0;          // per (slot, light): light colour xyz, intensity
+    float4* t1;          // per (slot, light): (diff + spec) xyz, N.L
+    uint32_t* kinds;     // per (slot, light): 0 nothing, 1 point light behind a shadow probe, 2 ambient term in t0.xyz
+    float4* probes;      // per (slot, light): origin | tmin, direction | tmax
+    float4* result;      // per slot: the level's radiance (already scaled by alpha for BLEND)
+    uint32_t* cont;      // parent slots of the next level's continuation rays
+    uint32_t* chain;     // level-0 BLEND slots
+    unsigned int* fetch; // work-item cursor of the persistent launch
     WAsyncFlags* async_flags;
 };
 
@@ -217,264 +245,339 @@ __device__ __forceinline__ uint32_t w_inst_sbt(const AccelHeader* handle, uint32
     return handle->kind == ACCEL_KIND_IAS ? ((const InstanceRecord*)((const char*)handle + handle->inst_off) + inst)->sbt_offset : 0u;
 }
 
-// __closesthit__radiance up to the shadow rays (whitted.cu:149-262) for the hit in `hit`: fills the lane's per-light scratch and returns
-// the emission part of the result in xyz and base_color.w in w; `blend` = ALPHA_MODE_BLEND.  `depth` = payload depth + 1.
-struct WHit { uint32_t prim, inst, sbt; float b1, b2; };
-static __device__ __noinline__ float4 w_shade_hit(const WK& k, const AccelHeader* handle, float3 dir, WHit hit, uint32_t depth, WTerm* terms,
-                                                   uint32_t* kinds, uint32_t nl, uint32_t* blend_out)
-{
-    const WParams& P = *k.params;
-    const InstanceRecord* ir = nullptr;
-    // SBT index = instance.sbtOffset + GAS-local index * RAY_TYPE_COUNT + RAY_TYPE_RADIANCE (Scene.cpp:1147-1154: sbtOffset advances by
-    // primitive groups * ray types)
-    uint32_t rec_idx = (hit.sbt & TRI_SBT_MASK) * W_RAY_TYPES;
-    if (handle->kind == ACCEL_KIND_IAS) {
-        ir = (const InstanceRecord*)((const char*)handle + handle->inst_off) + hit.inst;
-        rec_idx += ir->sbt_offset;
-    }
-    if (rec_idx >= k.hg_count) rec_idx = k.hg_count - 1;
-    const char* rec = k.hg_base + (size_t)rec_idx * k.hg_stride + B200RT_SBT_RECORD_HEADER_SIZE;
-    const WGeom g = w_local_geometry(rec, hit.prim, hit.b1, hit.b2, ir);
-    const WMaterial& m = *(const WMaterial*)(rec + 112);
-
-    // material (whitted.cu:157-186)
-    float4 bc = make_float4(m.base_color[0] * g.color.x, m.base_color[1] * g.color.y, m.base_color[2] * g.color.z, m.base_color[3] * g.color.w);
-    if (m.base_color_tex.tex) {
-        const float4 t = w_sample(m.base_color_tex, g);
-        bc = make_float4(bc.x * __powf(t.x, 2.2f), bc.y * __powf(t.y, 2.2f), bc.z * __powf(t.z, 2.2f), bc.w * t.w);
-    }
-    float metallic = m.metallic, roughness = m.roughness;
-    if (m.metallic_roughness_tex.tex) {
-        const float4 t = w_sample(m.metallic_roughness_tex, g);
-        roughness *= t.y;
-        metallic *= t.z;
-    }
-    const float F0 = 0.04f;
-    const float km = 1.0f - metallic;
-    const float3 diff_color = f3((bc.x * (1.0f - F0)) * km, (bc.y * (1.0f - F0)) * km, (bc.z * (1.0f - F0)) * km);
-    // lerp(F0, base_color, metallic) = a + t * (b - a)
-    const float3 spec_color = f3(fm(metallic, bc.x - F0, F0), fm(metallic, bc.y - F0, F0), fm(metallic, bc.z - F0, F0));
-    const float alpha = roughness * roughness;
-    float3 result = f3(0.f, 0.f, 0.f);
-    float4 et = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (m.emissive_tex.tex) et = w_sample(m.emissive_tex, g);
-    result = f3(fm(m.emissive_factor[0], et.x, result.x), fm(m.emissive_factor[1], et.y, result.y), fm(m.emissive_factor[2], et.z, result.z));
-    float3 N = g.N;
-    if (m.normal_tex.tex) {
-        const int tc = m.normal_tex.texcoord & 1;
-        const float4 t = w_sample(m.normal_tex, g);
-        const float nx = fm(2.0f, t.x, -1.0f), ny = fm(2.0f, t.y, -1.0f), nz = fm(2.0f, t.z, -1.0f);
-        const float2 rot = m.normal_tex.rotation;
-        const float tx = fm(ny, -rot.x, nx * rot.y), ty = fm(ny, rot.y, nx * rot.x);
-        const float3 du = normalize(g.dpdu[tc]), dv = normalize(g.dpdv[tc]);
-        N = normalize(f3(fm(nz, g.N.x, fm(ty, dv.x, tx * du.x)), fm(nz, g.N.y, fm(ty, dv.y, tx * du.y)), fm(nz, g.N.z, fm(ty, dv.z, tx * du.z))));
-    }
-    if (dot(N, dir) > 0.0f) N = neg(N);
-    // lights (whitted.cu:222-262)
-    const float3 V = neg(normalize(dir));
-    for (uint32_t li = 0; li < nl; ++li) {
-        const WLight L = *(const WLight*)(P.lights.data + (uint64_t)li * (P.lights.byte_stride ? P.lights.byte_stride : 36u));
-        uint32_t kind = 0;
-        WTerm T;
-        T.t0 = T.t1 = T.po = T.pd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (L.type == 0) {
-            if (depth < W_MAX_TRACE_DEPTH) {
-                const float3 Lv = f3(L.position[0] - g.P.x, L.position[1] - g.P.y, L.position[2] - g.P.z);
-                const float L_dist = length(Lv);
-                const float3 Ld = f3(fdiv(Lv.x, L_dist), fdiv(Lv.y, L_dist), fdiv(Lv.z, L_dist));
-                const float3 H = normalize(Ld + V);
-                const float N_dot_L = dot(N, Ld), N_dot_V = dot(N, V), N_dot_H = dot(N, H), V_dot_H = dot(V, H);
-                if (N_dot_L > 0.0f && N_dot_V > 0.0f) {
-                    // schlick / vis / ggxNormal (whitted_cuda.h:48-72); pow(x, 5) as exact products
-                    const float x1 = 1.0f - V_dot_H, x2 = x1 * x1, x5 = (x2 * x2) * x1;
-                    const float3 F = f3(fm(1.0f - spec_color.x, x5, spec_color.x), fm(1.0f - spec_color.y, x5, spec_color.y), fm(1.0f - spec_color.z, x5, spec_color.z));
-                    const float a2 = alpha * alpha;
-                    const float ggx0 = N_dot_L * fsqrt(fm(N_dot_V * N_dot_V, 1.0f - a2, a2));
-                    const float ggx1 = N_dot_V * fsqrt(fm(N_dot_L * N_dot_L, 1.0f - a2, a2));
-                    const float G_vis = fdiv((2.0f * N_dot_L) * N_dot_V, ggx0 + ggx1);
-                    const float xx = fm(N_dot_H * N_dot_H, a2 - 1.0f, 1.0f);
-                    const float D = fdiv(a2, (3.14159265358979323846f * xx) * xx);
-                    const float3 diff = f3(fdiv((1.0f - F.x) * diff_color.x, 3.14159265358979323846f), fdiv((1.0f - F.y) * diff_color.y, 3.14159265358979323846f),
-                                           fdiv((1.0f - F.z) * diff_color.z, 3.14159265358979323846f));
-                    const float3 spec = f3((F.x * G_vis) * D, (F.y * G_vis) * D, (F.z * G_vis) * D);
-                    // result += light.color * attenuation * intensity * N_dot_L * (diff + spec): the factors are kept apart because the
-                    // attenuation (known after the probe) multiplies first
-                    kind = 1;
-                    T.t0 = make_float4(L.color[0], L.color[1], L.color[2], L.intensity);
-                    T.t1 = make_float4(diff.x + spec.x, diff.y + spec.y, diff.z + spec.z, N_dot_L);
-                    T.po = make_float4(g.P.x, g.P.y, g.P.z, 0.001f);
-                    T.pd = make_float4(Ld.x, Ld.y, Ld.z, L_dist - 0.001f);
-                }
-            }
-        } else if (L.type == 1) {
-            kind = 2;
-            T.t0 = make_float4(L.color[0] * bc.x, L.color[1] * bc.y, L.color[2] * bc.z, 0.f);
-        }
-        kinds[li] = kind;
-        if (kind) terms[li] = T;
-    }
-    *blend_out = m.alpha_mode == 2 ? 1u : 0u;
-    return make_float4(result.x, result.y, result.z, bc.w);
-}
-
-// One work item = one pixel, taken through the whole program by the lane that fetched it:
-//   radiance ray (camera ray; level l > 0: the continuation of a BLEND hit, tmin = its t)
-//   -> miss: the level's value is miss_color                                        (__miss__constant_radiance)
-//   -> hit:  shade (in commit_continue, where the finished lanes of the warp run together), then the shadow probes of the lights one
-//            after the other (TERMINATE_ON_FIRST_HIT, attenuation through __anyhit__occlusion), the terms summed in light order;
-//            ALPHA_MODE_BLEND: value * alpha is parked and the continuation ray starts the next level (depth < 8)
-//   -> the parked levels are folded back to front, as the recursion of the reference returns, and the pixel is written.
+// ---- PRIMARY: radiance rays of one level ---------------------------------------------------------------------------------------------
 template <bool AH>
-struct WWork {
+struct WPrimaryWork {
+    static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
-    static constexpr bool CONTINUES = true;
     const WK& k;
     const AccelHeader* handle;
-    WTerm* terms;
-    uint32_t* kinds;
-    float4* levels;
-    uint32_t nl, pixel, level, li;
-    bool probing;     // the ray in flight (or the one that just ended) is a shadow probe, else a radiance ray
-    bool lit;         // every light of the innermost level is in: only the fold and the pixel write are left
-    bool blend;       // the level being lit is ALPHA_MODE_BLEND
-    float t_hit, alpha;
-    float3 result;
-    double att;
-
-    __device__ WWork(const WK& k_, const AccelHeader* h, uint32_t nl_) : k(k_), handle(h), nl(nl_), pixel(0), level(0), li(0), probing(false), lit(false), blend(false),
-                                                                           t_hit(0.f), alpha(1.f), result(f3(0.f, 0.f, 0.f)), att(1.0)
-    {
-        const size_t gl = (size_t)blockIdx.x * COOP_BLOCK + threadIdx.x;
-        terms = k.terms + gl * max(nl_, 1u);
-        kinds = k.kinds + gl * max(nl_, 1u);
-        levels = k.levels + gl * W_MAX_TRACE_DEPTH;
-    }
+    uint32_t pixel;
+    int parent;
+    __device__ WPrimaryWork(const WK& k_, const AccelHeader* h) : k(k_), handle(h), pixel(0), parent(-1) {}
 
     __device__ __forceinline__ bool anyhit_enabled() const { return handle->anyhit != 0u; }
     __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
     {
-        return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), (pack & TP_ANY) != 0u, b1, b2, factor);
+        return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), false, b1, b2, factor);
+    }
+    __device__ __forceinline__ void attenuate(float) {}
+    __device__ __forceinline__ void ray(float3& o, float3& d, float& tmin) const
+    {
+        const WParams& P = *k.params;
+        w_camera_ray(P, k.width, k.height, pixel, o, d);
+        tmin = parent >= 0 ? k.slots[parent].t : 0.0f;  // continuation: tmin = optixGetRayTmax() of the BLEND hit (whitted.cu:279)
+    }
+    __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
+    {
+        if (k.level == 0) { pixel = item; parent = -1; }
+        else { parent = (int)k.cont[item]; pixel = k.slots[parent].pixel; }
+        float3 o, d;
+        float tmin;
+        ray(o, d, tmin);
+        s.best.t = 1e16f;
+        // radiance rays cull back faces (whitted_cuda.h:110); DISABLE_TRIANGLE_FACE_CULLING geometry (doubleSided) is exempt in the triangle test
+        // most camera rays of a model viewer pass the model by: they are dropped at the bounds of the instance (trav_begin<BOUNDS>)
+        if (!trav_begin_handle<true>(s, my_ray, handle, o, d, tmin, 0u, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES & 0xf0u, 0u)) { commit(s, false); return false; }
+        return true;
+    }
+    __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
+    {
+        if (handle->kind == ACCEL_KIND_GAS) return false;
+        float3 o, d;
+        float tmin;
+        ray(o, d, tmin);
+        return trav_begin_handle<true>(s, my_ray, handle, o, d, tmin, s.pack & TP_FOUND_ANY, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES & 0xf0u, s.inst + 1u);
+    }
+    __device__ __forceinline__ void commit(const Trav& s, bool found)
+    {
+        // hits take a slot (one warp-aggregated atomic for the lanes committing together)
+        const uint32_t mask = __ballot_sync(__activemask(), found);
+        if (!found) {
+            // __miss__constant_radiance (whitted.cu:139-142)
+            if (parent < 0) { const WParams& P = *k.params; w_write_pixel(P, pixel, P.miss_color); }
+            else k.slots[parent].next = W_NEXT_MISS;
+            return;
+        }
+        const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&k.counters->nslots, (unsigned)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+        if (slot >= k.cap_slots) {
+            // capacity reached (only possible on BLEND levels): the continuation is dropped like one beyond the depth cap
+            k.counters->overflow = 1u;
+            if (parent >= 0) k.slots[parent].next = W_NEXT_NONE;
+            return;
+        }
+        WSlot w;
+        w.pixel = pixel; w.parent = parent; w.t = s.best.t; w.prim = s.best.prim; w.inst = s.best.inst; w.b1 = s.best.b1; w.b2 = s.best.b2;
+        w.sbt = s.best.sbt & TRI_SBT_MASK; w.next = W_NEXT_NONE; w.flags = 0u; w.one_minus_alpha = 0.f; w.level = k.level;
+        k.slots[slot] = w;
+        if (parent >= 0) k.slots[parent].next = (int)slot;
+    }
+};
+
+// AH: the traversable holds geometry that runs the any-hit programs (the host read AccelHeader::anyhit with the light count)
+template <bool AH>
+__global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const __grid_constant__ WK k, uint32_t n_items)
+{
+    const AccelHeader* handle = (const AccelHeader*)k.params->handle;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && k.level == 0) { k.counters->ncont = 0; k.counters->nchain = 0; k.counters->overflow = 0; }
+    WPrimaryWork<AH> work(k, handle);
+    trace_persistent(work, n_items, k.fetch, nullptr);
+}
+
+// ---- SHADE: __closesthit__radiance up to the shadow rays, one thread per hit slot of the level --------------------------------------
+__global__ void __launch_bounds__(128) w_shade_kernel(const __grid_constant__ WK k)
+{
+    const WParams P = *k.params;
+    const uint32_t end = min(k.counters->nslots, k.cap_slots);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (P.lights.count > k.nl_cap) k.async_flags->too_many_lights = P.lights.count;
+        if (k.counters->overflow) k.async_flags->slot_overflow = 1u;
+    }
+    const uint32_t nl = min(P.lights.count, k.nl_cap);
+    const AccelHeader* handle = (const AccelHeader*)P.handle;
+    for (uint32_t si = k.level_start + blockIdx.x * blockDim.x + threadIdx.x; si < end; si += gridDim.x * blockDim.x) {
+        const WSlot h = k.slots[si];
+        float3 org, dir;
+        w_camera_ray(P, k.width, k.height, h.pixel, org, dir);
+        const InstanceRecord* ir = nullptr;
+        // SBT index = instance.sbtOffset + GAS-local index * RAY_TYPE_COUNT + RAY_TYPE_RADIANCE (Scene.cpp:1147-1154: sbtOffset advances by
+        // primitive groups * ray types)
+        uint32_t rec_idx = h.sbt * W_RAY_TYPES;
+        if (handle->kind == ACCEL_KIND_IAS) {
+            ir = (const InstanceRecord*)((const char*)handle + handle->inst_off) + h.inst;
+            rec_idx += ir->sbt_offset;
+        }
+        if (rec_idx >= k.hg_count) rec_idx = k.hg_count - 1;
+        const char* rec = k.hg_base + (size_t)rec_idx * k.hg_stride + B200RT_SBT_RECORD_HEADER_SIZE;
+        const WGeom g = w_local_geometry(rec, h.prim, h.b1, h.b2, ir);
+        const WMaterial& m = *(const WMaterial*)(rec + 112);
+
+        // material (whitted.cu:157-186)
+        float4 bc = make_float4(m.base_color[0] * g.color.x, m.base_color[1] * g.color.y, m.base_color[2] * g.color.z, m.base_color[3] * g.color.w);
+        if (m.base_color_tex.tex) {
+            const float4 t = w_sample(m.base_color_tex, g);
+            bc = make_float4(bc.x * __powf(t.x, 2.2f), bc.y * __powf(t.y, 2.2f), bc.z * __powf(t.z, 2.2f), bc.w * t.w);
+        }
+        float metallic = m.metallic, roughness = m.roughness;
+        if (m.metallic_roughness_tex.tex) {
+            const float4 t = w_sample(m.metallic_roughness_tex, g);
+            roughness *= t.y;
+            metallic *= t.z;
+        }
+        const float F0 = 0.04f;
+        const float km = 1.0f - metallic;
+        const float3 diff_color = f3((bc.x * (1.0f - F0)) * km, (bc.y * (1.0f - F0)) * km, (bc.z * (1.0f - F0)) * km);
+        // lerp(F0, base_color, metallic) = a + t * (b - a)
+        const float3 spec_color = f3(fm(metallic, bc.x - F0, F0), fm(metallic, bc.y - F0, F0), fm(metallic, bc.z - F0, F0));
+        const float alpha = roughness * roughness;
+        float3 result = f3(0.f, 0.f, 0.f);
+        float4 et = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (m.emissive_tex.tex) et = w_sample(m.emissive_tex, g);
+        result = f3(fm(m.emissive_factor[0], et.x, result.x), fm(m.emissive_factor[1], et.y, result.y), fm(m.emissive_factor[2], et.z, result.z));
+        float3 N = g.N;
+        if (m.normal_tex.tex) {
+            const int tc = m.normal_tex.texcoord & 1;
+            const float4 t = w_sample(m.normal_tex, g);
+            const float nx = fm(2.0f, t.x, -1.0f), ny = fm(2.0f, t.y, -1.0f), nz = fm(2.0f, t.z, -1.0f);
+            const float2 rot = m.normal_tex.rotation;
+            const float tx = fm(ny, -rot.x, nx * rot.y), ty = fm(ny, rot.y, nx * rot.x);
+            const float3 du = normalize(g.dpdu[tc]), dv = normalize(g.dpdv[tc]);
+            N = normalize(f3(fm(nz, g.N.x, fm(ty, dv.x, tx * du.x)), fm(nz, g.N.y, fm(ty, dv.y, tx * du.y)), fm(nz, g.N.z, fm(ty, dv.z, tx * du.z))));
+        }
+        if (dot(N, dir) > 0.0f) N = neg(N);
+        // lights (whitted.cu:222-262): depth = payload depth + 1 = level + 1
+        const uint32_t depth = h.level + 1u;
+        const float3 V = neg(normalize(dir));
+        for (uint32_t li = 0; li < nl; ++li) {
+            const WLight L = *(const WLight*)(P.lights.data + (uint64_t)li * (P.lights.byte_stride ? P.lights.byte_stride : 36u));
+            uint32_t kind = 0;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, po = a0, pd = a0;
+            if (L.type == 0) {
+                if (depth < W_MAX_TRACE_DEPTH) {
+                    const float3 Lv = f3(L.position[0] - g.P.x, L.position[1] - g.P.y, L.position[2] - g.P.z);
+                    const float L_dist = length(Lv);
+                    const float3 Ld = f3(fdiv(Lv.x, L_dist), fdiv(Lv.y, L_dist), fdiv(Lv.z, L_dist));
+                    const float3 H = normalize(Ld + V);
+                    const float N_dot_L = dot(N, Ld), N_dot_V = dot(N, V), N_dot_H = dot(N, H), V_dot_H = dot(V, H);
+                    if (N_dot_L > 0.0f && N_dot_V > 0.0f) {
+                        // schlick / vis / ggxNormal (whitted_cuda.h:48-72); pow(x, 5) as exact products
+                        const float x1 = 1.0f - V_dot_H, x2 = x1 * x1, x5 = (x2 * x2) * x1;
+                        const float3 F = f3(fm(1.0f - spec_color.x, x5, spec_color.x), fm(1.0f - spec_color.y, x5, spec_color.y), fm(1.0f - spec_color.z, x5, spec_color.z));
+                        const float a2 = alpha * alpha;
+                        const float ggx0 = N_dot_L * fsqrt(fm(N_dot_V * N_dot_V, 1.0f - a2, a2));
+                        const float ggx1 = N_dot_V * fsqrt(fm(N_dot_L * N_dot_L, 1.0f - a2, a2));
+                        const float G_vis = fdiv((2.0f * N_dot_L) * N_dot_V, ggx0 + ggx1);
+                        const float xx = fm(N_dot_H * N_dot_H, a2 - 1.0f, 1.0f);
+                        const float D = fdiv(a2, (3.14159265358979323846f * xx) * xx);
+                        const float3 diff = f3(fdiv((1.0f - F.x) * diff_color.x, 3.14159265358979323846f), fdiv((1.0f - F.y) * diff_color.y, 3.14159265358979323846f),
+                                               fdiv((1.0f - F.z) * diff_color.z, 3.14159265358979323846f));
+                        const float3 spec = f3((F.x * G_vis) * D, (F.y * G_vis) * D, (F.z * G_vis) * D);
+                        // result += light.color * attenuation * intensity * N_dot_L * (diff + spec): the factors are kept apart because the
+                        // attenuation (known after the probe) multiplies first
+                        kind = 1;
+                        a0 = make_float4(L.color[0], L.color[1], L.color[2], L.intensity);
+                        a1 = make_float4(diff.x + spec.x, diff.y + spec.y, diff.z + spec.z, N_dot_L);
+                        po = make_float4(g.P.x, g.P.y, g.P.z, 0.001f);
+                        pd = make_float4(Ld.x, Ld.y, Ld.z, L_dist - 0.001f);
+                    }
+                }
+            } else if (L.type == 1) {
+                kind = 2;
+                a0 = make_float4(L.color[0] * bc.x, L.color[1] * bc.y, L.color[2] * bc.z, 0.f);
+            }
+            const size_t s = (size_t)si * nl + li;
+            k.kinds[s] = kind;
+            if (kind) k.t0[s] = a0;
+            if (kind == 1) { k.t1[s] = a1; k.probes[2 * s] = po; k.probes[2 * s + 1] = pd; }
+        }
+        k.base[si] = make_float4(result.x, result.y, result.z, bc.w);
+        // ALPHA_MODE_BLEND (whitted.cu:266-286): result *= alpha; a continuation from the hit while depth < MAX_TRACE_DEPTH
+        if (m.alpha_mode == 2) {
+            uint32_t flags = WS_BLEND;
+            if (!k.blend_levels) k.async_flags->unexpected_blend = 1u;
+            else if (depth < W_MAX_TRACE_DEPTH) {
+                flags |= WS_CONT;
+                k.cont[atomicAdd(&k.counters->ncont, 1u)] = si;
+            }
+            if (h.level == 0 && k.blend_levels) k.chain[atomicAdd(&k.counters->nchain, 1u)] = si;
+            k.slots[si].flags = flags;
+            k.slots[si].one_minus_alpha = 1.0f - bc.w;
+        }
+    }
+}
+
+// ---- SHADOW: the probes of one hit slot, then the rest of __closesthit__radiance and (level 0, no BLEND) the raygen tail -----------------
+template <bool AH>
+struct WShadowWork {
+    static constexpr bool CONTINUES = false;
+    static constexpr bool ANYHIT = AH;
+    const WK& k;
+    const AccelHeader* handle;
+    uint32_t nl, slot, li;
+    float3 result;
+    double att;
+    __device__ WShadowWork(const WK& k_, const AccelHeader* h, uint32_t nl_) : k(k_), handle(h), nl(nl_), slot(0), li(0), result(f3(0.f, 0.f, 0.f)), att(1.0) {}
+
+    __device__ __forceinline__ bool anyhit_enabled() const { return handle->anyhit != 0u; }
+    __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
+    {
+        return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), true, b1, b2, factor);
     }
     __device__ __forceinline__ void attenuate(float f) { att *= (double)f; }
-
-    // radiance rays cull back faces (whitted_cuda.h:110); DISABLE_TRIANGLE_FACE_CULLING geometry (doubleSided) is exempt in the triangle test
-    __device__ __forceinline__ bool begin_radiance(Trav& s, float* my_ray, uint32_t keep, uint32_t first_inst)
-    {
-        float3 o, d;
-        w_camera_ray(*k.params, k.width, k.height, pixel, o, d);
-        if (first_inst == 0u) s.best.t = 1e16f;
-        // level 0: tmin 0; continuation: tmin = optixGetRayTmax() of the BLEND hit (whitted.cu:279)
-        return trav_begin_handle(s, my_ray, handle, o, d, level ? t_hit : 0.0f, keep, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES & 0xf0u, first_inst);
-    }
     // result += light.color * attenuation * intensity * N_dot_L * (diff + spec) (whitted.cu:249-256)
-    __device__ __forceinline__ void add_point(float a)
+    __device__ __forceinline__ void add_point(size_t s, float a)
     {
         if (!(a > 0.0f)) return;
-        const float4 c = terms[li].t0, d = terms[li].t1;
+        const float4 c = k.t0[s], d = k.t1[s];
         result = f3(result.x + (((c.x * a) * c.w) * d.w) * d.x, result.y + (((c.y * a) * c.w) * d.w) * d.y, result.z + (((c.z * a) * c.w) * d.w) * d.z);
     }
     // walk the lights from `li` on: ambient terms are added on the way, the first point light with a probe starts its traversal
     __device__ __forceinline__ bool start_next_probe(Trav& s, float* my_ray)
     {
         for (; li < nl; ++li) {
-            const uint32_t kind = kinds[li];
-            if (kind == 2) { const float4 c = terms[li].t0; result = f3(result.x + c.x, result.y + c.y, result.z + c.z); }
+            const size_t idx = (size_t)slot * nl + li;
+            const uint32_t kind = k.kinds[idx];
+            if (kind == 2) { const float4 c = k.t0[idx]; result = f3(result.x + c.x, result.y + c.y, result.z + c.z); }
             else if (kind == 1) {
-                const float4 po = terms[li].po, pd = terms[li].pd;
+                const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
                 att = 1.0;
                 s.best.t = pd.w;
                 // traceOcclusion (whitted_cuda.h:127-159): TERMINATE_ON_FIRST_HIT | DISABLE_CLOSESTHIT, no face culling
-                if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, TP_ANY, 0u, 0u)) { probing = true; return true; }
-                add_point(1.0f);  // nothing to traverse: the miss program commits the untouched attenuation
+                if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, TP_ANY, 0u, 0u)) return true;
+                add_point(idx, 1.0f);  // nothing to traverse: the miss program commits the untouched attenuation
             }
         }
-        probing = false;
         return false;
     }
-    // every light of the level is in: BLEND parks value * alpha and continues behind the hit; otherwise the level's value is final
-    __device__ __forceinline__ bool finish_level(Trav& s, float* my_ray)
-    {
-        if (blend) {
-            // result *= base_color.w; result += trace(...) * (1 - base_color.w) while depth < MAX_TRACE_DEPTH (whitted.cu:266-286)
-            result = f3(result.x * alpha, result.y * alpha, result.z * alpha);
-            if (level + 1u < W_MAX_TRACE_DEPTH) {
-                levels[level] = make_float4(result.x, result.y, result.z, 1.0f - alpha);
-                ++level;
-                probing = false;
-                if (begin_radiance(s, my_ray, 0u, 0u)) return true;
-                result = k.params->miss_color;  // nothing to traverse: the miss program
-            }
-        }
-        lit = true;
-        return false;
-    }
-
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        pixel = item; level = 0; probing = false; lit = false;
-        if (begin_radiance(s, my_ray, 0u, 0u)) return true;
-        commit_continue(s, my_ray, false);
+        slot = k.level_start + item;
+        li = 0;
+        const float4 b = k.base[slot];
+        result = f3(b.x, b.y, b.z);
+        if (start_next_probe(s, my_ray)) return true;
+        commit(s, false);
         return false;
     }
     __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
-        if (!probing) {
-            // radiance ray: next instance of the IAS; when there is none the lane finishes and meets its warp mates in commit_continue
-            return handle->kind == ACCEL_KIND_IAS && begin_radiance(s, my_ray, s.pack & TP_FOUND_ANY, s.inst + 1u);
-        }
+        const size_t idx = (size_t)slot * nl + li;
         if (!any_ray_done(s) && handle->kind == ACCEL_KIND_IAS) {
-            const float4 po = terms[li].po, pd = terms[li].pd;
+            const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
             if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u)) return true;
         }
         // the probe is finished: occluded -> attenuation never committed (0), else the pending product (whitted_cuda.h:155-158)
-        add_point((s.pack & TP_FOUND_ANY) ? 0.0f : (float)att);
+        add_point(idx, (s.pack & TP_FOUND_ANY) ? 0.0f : (float)att);
         ++li;
-        if (start_next_probe(s, my_ray)) return true;
-        return finish_level(s, my_ray);
+        return start_next_probe(s, my_ray);
     }
-    // called by the lanes of the warp that finished a ray, together
-    __device__ __forceinline__ bool commit_continue(Trav& s, float* my_ray, bool found)
+    __device__ __forceinline__ void commit(const Trav&, bool)
     {
-        if (!lit) {
-            if (found) {
-                // __closesthit__radiance
-                float3 o, d;
-                w_camera_ray(*k.params, k.width, k.height, pixel, o, d);
-                t_hit = s.best.t;
-                uint32_t is_blend = 0;
-                const float4 b = w_shade_hit(k, handle, d, WHit{s.best.prim, s.best.inst, s.best.sbt, s.best.b1, s.best.b2}, level + 1u, terms, kinds, nl, &is_blend);
-                blend = is_blend != 0u;
-                result = f3(b.x, b.y, b.z);
-                alpha = b.w;
-                li = 0;
-                if (start_next_probe(s, my_ray)) return true;
-                if (finish_level(s, my_ray)) return true;
-            } else {
-                result = k.params->miss_color;  // __miss__constant_radiance (whitted.cu:139-142)
-            }
+        const WSlot h = k.slots[slot];
+        if (h.flags & WS_BLEND) {
+            const float alpha = k.base[slot].w;  // base_color.w
+            k.result[slot] = make_float4(result.x * alpha, result.y * alpha, result.z * alpha, h.one_minus_alpha);
+        } else if (h.level == 0) {
+            w_write_pixel(*k.params, h.pixel, result);
+        } else {
+            k.result[slot] = make_float4(result.x, result.y, result.z, 0.f);
         }
-        // the innermost level is in `result`: fold the parked BLEND levels back to front, write the pixel
-        for (uint32_t l = level; l-- > 0u;) {
-            const float4 r = levels[l];
-            result = f3(fm(result.x, r.w, r.x), fm(result.y, r.w, r.y), fm(result.z, r.w, r.z));
-        }
-        w_write_pixel(*k.params, pixel, result);
-        return false;
     }
 };
 
-// AH: the traversable holds geometry that runs the any-hit programs (the host read AccelHeader::anyhit with the light count)
 template <bool AH>
-__global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_launch_kernel(const __grid_constant__ WK k, uint32_t npix)
+__global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const __grid_constant__ WK k)
 {
     const WParams* P = k.params;
     const AccelHeader* handle = (const AccelHeader*)P->handle;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && P->lights.count > k.nl_cap) k.async_flags->too_many_lights = P->lights.count;
-    WWork<AH> work(k, handle, min(P->lights.count, k.nl_cap));
-    trace_persistent(work, npix, k.fetch, nullptr);
+    const uint32_t end = min(k.counters->nslots, k.cap_slots);
+    const uint32_t n_items = end > k.level_start ? end - k.level_start : 0u;
+    WShadowWork<AH> work(k, handle, min(P->lights.count, k.nl_cap));
+    trace_persistent(work, n_items, k.fetch, nullptr);
+}
+
+// ---- COMBINE: fold the levels of a BLEND pixel back to front, as the recursion of __closesthit__radiance returns -----------------------
+__global__ void __launch_bounds__(128) w_combine_kernel(const __grid_constant__ WK k)
+{
+    const WParams P = *k.params;
+    const uint32_t n = k.counters->nchain;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int ids[W_MAX_TRACE_DEPTH];
+        int depth = 0, tail = W_NEXT_NONE;
+        for (int s = (int)k.chain[c]; depth < (int)W_MAX_TRACE_DEPTH;) {
+            ids[depth++] = s;
+            const int nx = k.slots[s].next;
+            if (nx < 0) { tail = nx; break; }
+            s = nx;
+        }
+        // the innermost continuation: the miss colour, or nothing when no ray was traced (depth cap / opaque hit)
+        bool have = tail == W_NEXT_MISS;
+        float3 R = P.miss_color;
+        for (int i = depth - 1; i >= 0; --i) {
+            const float4 r = k.result[ids[i]];
+            const uint32_t flags = k.slots[ids[i]].flags;
+            // result = result * alpha (done in SHADOW); result += payload.result * (1 - alpha) when the continuation was traced
+            if ((flags & WS_BLEND) && (flags & WS_CONT) && have) R = f3(fm(R.x, r.w, r.x), fm(R.y, r.w, r.y), fm(R.z, r.w, r.z));
+            else R = f3(r.x, r.y, r.z);
+            have = true;
+        }
+        w_write_pixel(P, k.slots[ids[0]].pixel, R);
+    }
 }
 
 // ---- host --------------------------------------------------------------------------------------------------------------------------
+static unsigned w_persistent_grid(b200rt_context ctx, const void* kernel, uint64_t n)
+{
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, COOP_BLOCK, 0);
+    const uint64_t cap = (uint64_t)std::max(occ, 1) * ctx->sm_count;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(cap, (n + COOP_BLOCK - 1) / COOP_BLOCK));
+}
+
 int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, unsigned width, unsigned height)
 {
     B2_REQUIRE(ctx, d_params && sbt, "null argument");
@@ -486,17 +589,31 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     DeviceGuard guard(ctx->device);  // the C ABI entry point holds ctx->mu
     // errors of earlier launches on this context surface here (no synchronisation on the steady-state path)
     WAsyncFlags* flags = (WAsyncFlags*)((char*)ctx->pinned + 1024);
+    if (flags->unexpected_blend) {
+        flags->unexpected_blend = 0;
+        ctx->w_params = 0;  // look at the hit-group records again
+        return set_error(ctx, B200RT_ERROR_INVALID_OPERATION,
+                         "an earlier whitted launch met an ALPHA_MODE_BLEND material that was not in the hit-group records when they were first seen "
+                         "(its continuation was not traced); relaunch");
+    }
     if (flags->too_many_lights) {
         ctx->w_params = 0;  // re-read the light count below
         flags->too_many_lights = 0;
         return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "an earlier whitted launch found more lights than its workspace was sized for (frame incomplete); relaunch");
     }
-    // The per-lane scratch is sized by the light count, and the kernel variant is picked by whether the scene holds any-hit geometry.
-    // Both are read back (one stream synchronisation) on the first launch with a given d_params after an accel build; later launches
-    // reuse them and the kernel checks the live light count.
-    if (ctx->w_params != d_params) {
+    if (flags->slot_overflow) {
+        flags->slot_overflow = 0;
+        log_msg(ctx, 2, "whitted", "an earlier launch ran out of hit slots for BLEND continuations (more than %u levels per pixel on average); the deepest were dropped",
+                W_BLEND_SLOT_FACTOR);
+    }
+    // The workspace is sized by the light count and by whether BLEND materials exist.  Both are read back (one stream synchronisation)
+    // on the first launch with a given (d_params, hit-group records); later launches reuse them and the kernels check the live values.
+    if (ctx->w_params != d_params || ctx->w_sbt != sbt->hitgroupRecordBase || ctx->w_sbt_count != sbt->hitgroupRecordCount) {
         WParams hp;
         B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, (const void*)d_params, sizeof(WParams), cudaMemcpyDeviceToHost, s));
+        const size_t rec_bytes = (size_t)sbt->hitgroupRecordCount * sbt->hitgroupRecordStrideInBytes;
+        std::vector<char> recs(rec_bytes);
+        B2_CUDA(ctx, cudaMemcpyAsync(recs.data(), (const void*)sbt->hitgroupRecordBase, rec_bytes, cudaMemcpyDeviceToHost, s));
         B2_CUDA(ctx, cudaStreamSynchronize(s));
         memcpy(&hp, ctx->pinned, sizeof(WParams));
         B2_REQUIRE(ctx, hp.handle && hp.accum_buffer, "LaunchParams has null pointers");
@@ -505,34 +622,70 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
         B2_CUDA(ctx, cudaStreamSynchronize(s));
         B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "LaunchParams.handle is not a b200rt traversable");
-        ctx->w_params = d_params;
-        ctx->w_lights = hp.lights.count;
         ctx->w_anyhit = ah.anyhit != 0;
+        bool blend = false;
+        for (unsigned r = 0; r < sbt->hitgroupRecordCount; ++r)
+            blend |= ((const WMaterial*)(recs.data() + (size_t)r * sbt->hitgroupRecordStrideInBytes + 32 + 112))->alpha_mode == 2;
+        ctx->w_params = d_params;
+        ctx->w_sbt = sbt->hitgroupRecordBase;
+        ctx->w_sbt_count = sbt->hitgroupRecordCount;
+        ctx->w_lights = hp.lights.count;
+        ctx->w_blend = blend;
     }
     const uint32_t npix = (uint32_t)npix64, nl = ctx->w_lights, nlp = std::max(nl, 1u);
-    const bool anyhit = ctx->w_anyhit;
-    int occ = 0;
-    if (anyhit) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, w_launch_kernel<true>, COOP_BLOCK, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, w_launch_kernel<false>, COOP_BLOCK, 0);
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(occ, 1) * ctx->sm_count, div_up(npix, COOP_BLOCK)));
-    const size_t lanes = (size_t)grid * COOP_BLOCK;
+    const bool blend = ctx->w_blend, anyhit = ctx->w_anyhit;
+    const void* k_primary = anyhit ? (const void*)w_primary_kernel<true> : (const void*)w_primary_kernel<false>;
+    const void* k_shadow = anyhit ? (const void*)w_shadow_kernel<true> : (const void*)w_shadow_kernel<false>;
+    const size_t cap = (size_t)npix * (blend ? W_BLEND_SLOT_FACTOR : 1u);
     size_t off = 16384;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_cur = take(256), o_terms = take(sizeof(WTerm) * lanes * nlp), o_kinds = take(4 * lanes * nlp), o_levels = take(16 * lanes * W_MAX_TRACE_DEPTH);
+    const size_t o_cnt = take(256), o_slots = take(sizeof(WSlot) * cap), o_base = take(16 * cap), o_t0 = take(16 * cap * nlp), o_t1 = take(16 * cap * nlp),
+                 o_kinds = take(4 * cap * nlp), o_probes = take(32 * cap * nlp), o_result = take(blend ? 16 * cap : 0), o_cont = take(blend ? 4 * cap : 0),
+                 o_chain = take(blend ? 4 * (size_t)npix : 0);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
     WK k;
     k.params = (const WParams*)d_params;
-    k.width = width; k.height = height; k.nl_cap = nl;
+    k.width = width; k.height = height; k.nl_cap = nl; k.level = 0; k.level_start = 0; k.cap_slots = (uint32_t)cap;
     k.hg_base = (const char*)sbt->hitgroupRecordBase; k.hg_stride = sbt->hitgroupRecordStrideInBytes; k.hg_count = sbt->hitgroupRecordCount;
-    k.terms = (WTerm*)(W + o_terms); k.kinds = (uint32_t*)(W + o_kinds); k.levels = (float4*)(W + o_levels);
-    k.fetch = (unsigned int*)(W + o_cur);
+    k.blend_levels = blend ? 1u : 0u;
+    k.counters = (WCounters*)(W + o_cnt);
+    k.slots = (WSlot*)(W + o_slots); k.base = (float4*)(W + o_base); k.t0 = (float4*)(W + o_t0); k.t1 = (float4*)(W + o_t1);
+    k.kinds = (uint32_t*)(W + o_kinds); k.probes = (float4*)(W + o_probes); k.result = (float4*)(W + o_result); k.cont = (uint32_t*)(W + o_cont);
+    k.chain = (uint32_t*)(W + o_chain);
     k.async_flags = flags;
-    B2_CUDA(ctx, cudaMemsetAsync(k.fetch, 0, sizeof(unsigned int), s));
-    if (anyhit) w_launch_kernel<true><<<grid, COOP_BLOCK, 0, s>>>(k, npix);
-    else w_launch_kernel<false><<<grid, COOP_BLOCK, 0, s>>>(k, npix);
-    B2_LAUNCH_CHECK(ctx);
+    unsigned int* cursors = (unsigned int*)(W + o_cnt + 64);  // two per level
+    B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters + all work-item cursors of the frame
+    WCounters* h_cnt = (WCounters*)((char*)ctx->pinned + 512);
+    uint32_t n_items = npix, level_start = 0;
+    for (uint32_t level = 0; level < W_MAX_TRACE_DEPTH; ++level) {
+        k.level = level;
+        k.level_start = level_start;
+        k.fetch = cursors + 2 * level;
+        if (anyhit) w_primary_kernel<true><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+        else w_primary_kernel<false><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+        B2_LAUNCH_CHECK(ctx);
+        const unsigned shade_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n_items, 128), (uint64_t)ctx->sm_count * 16));
+        w_shade_kernel<<<shade_grid, 128, 0, s>>>(k);
+        B2_LAUNCH_CHECK(ctx);
+        k.fetch = cursors + 2 * level + 1;
+        if (anyhit) w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, n_items), COOP_BLOCK, 0, s>>>(k);
+        else w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, n_items), COOP_BLOCK, 0, s>>>(k);
+        B2_LAUNCH_CHECK(ctx);
+        if (!blend) break;
+        // BLEND scenes: how many continuations did this level start?  (the only host synchronisation of a whitted launch)
+        B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, k.counters, sizeof(WCounters), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        if (h_cnt->ncont == 0 || level + 1 == W_MAX_TRACE_DEPTH) break;
+        n_items = h_cnt->ncont;
+        level_start = std::min<uint32_t>(h_cnt->nslots, (uint32_t)cap);
+        B2_CUDA(ctx, cudaMemsetAsync(&k.counters->ncont, 0, sizeof(unsigned int), s));
+    }
+    if (blend) {
+        w_combine_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 8)), 128, 0, s>>>(k);
+        B2_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

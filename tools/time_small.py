@@ -31,6 +31,11 @@ for name, sc in (("whitted", common.duck_scene()), ("whitted_mask", common.duck_
     mv = host.MeshViewer(ctx, sc, 1920, 1080)
     out[name] = cuda_ms(lambda: mv.launch_subframe(5))
     mv.close()
+for name, kw in (("pg_ref", {}), ("pg_close", {"eye": (0.5, 0.7, -1.4), "up": (0.0, 1.0, 0.000073), "lookat": (0.0, 0.1, 0.0), "fov": 50.0})):
+    cam = host.playground_camera(aperture=0.0, **kw)
+    pg = host.Playground(ctx, 1920, 1080, spf=8, rows=132, camera=cam)
+    out[name] = cuda_ms(lambda: pg.launch_frame(dirty=True), reps=3, warm=1)
+    del pg
 pt = host.PathTracer(ctx, 768, 768, 16)
 pt.sample_groups = 4
 out["cornell_sg4"] = cuda_ms(lambda: pt.launch_subframe(3))
