@@ -190,6 +190,7 @@ struct WCounters {
     unsigned int ncont;    // continuation rays SHADE put on the list for the next level
     unsigned int nchain;   // level-0 BLEND slots (pixels COMBINE has to fold)
     unsigned int overflow; // hits dropped because the slot capacity was reached
+    unsigned int nprimary; // camera rays RAYGEN found heading for the scene bounds (PRIMARY's work items at level 0)
 };
 // asynchronous launch errors, written by the kernels into the context's pinned host block and reported by the NEXT launch
 // (like CUDA's own asynchronous errors)
@@ -210,8 +211,11 @@ struct WK {
     uint32_t* kinds;     // per (slot, light): 0 nothing, 1 point light behind a shadow probe, 2 ambient term in t0.xyz
     float4* probes;      // per (slot, light): origin | tmin, direction | tmax
     float4* result;      // per slot: the level's radiance (already scaled by alpha for BLEND)
+    float* att;          // per (slot, light): committed attenuation of the probe
+    unsigned int* arrived;  // per slot: probe items finished (zeroed by SHADE)
     uint32_t* cont;      // parent slots of the next level's continuation rays
     uint32_t* chain;     // level-0 BLEND slots
+    uint32_t* primary;   // pixels whose camera ray heads for the scene bounds (written by RAYGEN)
     unsigned int* fetch; // work-item cursor of the persistent launch
     WAsyncFlags* async_flags;
 };
@@ -245,6 +249,45 @@ __device__ __forceinline__ uint32_t w_inst_sbt(const AccelHeader* handle, uint32
     return handle->kind == ACCEL_KIND_IAS ? ((const InstanceRecord*)((const char*)handle + handle->inst_off) + inst)->sbt_offset : 0u;
 }
 
+// ---- RAYGEN: one thread per pixel — the camera ray against the bounds of the scene -----------------------------------------------------
+// A model viewer's camera rays mostly pass the model by.  Those pixels are finished right here, by 2 M independent threads (the miss
+// program and the raygen tail: whitted.cu:84-97,139-142); only the rays that reach the (padded, hence conservative: trav_coop.cuh
+// trav_begin<BOUNDS>) scene bounds become work items of the persistent traversal, whose lanes take one item at a time and would
+// otherwise spend their time on the latency of fetch -> set-up -> accum read for rays that hit nothing (measured: 150 us of a 270 us
+// frame, profiles/r01_whitted_launches.md).
+__global__ void __launch_bounds__(256) w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool candidate = false;
+    if (i < npix) {
+        const WParams& P = *k.params;
+        const AccelHeader* h = (const AccelHeader*)P.handle;
+        float3 o, d;
+        w_camera_ray(P, k.width, k.height, i, o, d);
+        const float bx = fabsf(d.x) < DIR_EPS ? copysignf(DIR_EPS, d.x) : d.x;
+        const float by = fabsf(d.y) < DIR_EPS ? copysignf(DIR_EPS, d.y) : d.y;
+        const float bz = fabsf(d.z) < DIR_EPS ? copysignf(DIR_EPS, d.z) : d.z;
+        const float idx = fdiv(1.0f, bx), idy = fdiv(1.0f, by), idz = fdiv(1.0f, bz);
+        const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
+        // an IAS's bounds are the box of its instances' transformed corners: one more rounding than a GAS's, covered by a wider pad
+        const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 6.103515625e-05f;
+        const float ax = ((lx - pad) - o.x) * idx, cx = ((hx + pad) - o.x) * idx;
+        const float ay = ((ly - pad) - o.y) * idy, cy = ((hy + pad) - o.y) * idy;
+        const float az = ((lz - pad) - o.z) * idz, cz = ((hz + pad) - o.z) * idz;
+        const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), 0.0f));
+        const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), 1e16f));
+        candidate = tn <= tf * BOX_SLACK && (h->kind == ACCEL_KIND_IAS ? h->num_instances != 0u : h->num_tris != 0u);
+        if (!candidate) w_write_pixel(P, i, P.miss_color);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
+    if (!mask) return;
+    const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&k.counters->nprimary, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (candidate) k.primary[base + __popc(mask & ((1u << lane) - 1u))] = i;
+}
+
 // ---- PRIMARY: radiance rays of one level ---------------------------------------------------------------------------------------------
 template <bool AH>
 struct WPrimaryWork {
@@ -270,7 +313,7 @@ struct WPrimaryWork {
     }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        if (k.level == 0) { pixel = item; parent = -1; }
+        if (k.level == 0) { pixel = k.primary[item]; parent = -1; }
         else { parent = (int)k.cont[item]; pixel = k.slots[parent].pixel; }
         float3 o, d;
         float tmin;
@@ -323,7 +366,7 @@ template <bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const __grid_constant__ WK k, uint32_t n_items)
 {
     const AccelHeader* handle = (const AccelHeader*)k.params->handle;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && k.level == 0) { k.counters->ncont = 0; k.counters->nchain = 0; k.counters->overflow = 0; }
+    if (k.level == 0) n_items = k.counters->nprimary;  // counted by RAYGEN
     WPrimaryWork<AH> work(k, handle);
     trace_persistent(work, n_items, k.fetch, nullptr);
 }
@@ -435,6 +478,7 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const __grid_constant__ WK
             if (kind == 1) { k.t1[s] = a1; k.probes[2 * s] = po; k.probes[2 * s + 1] = pd; }
         }
         k.base[si] = make_float4(result.x, result.y, result.z, bc.w);
+        k.arrived[si] = 0u;
         // ALPHA_MODE_BLEND (whitted.cu:266-286): result *= alpha; a continuation from the hit while depth < MAX_TRACE_DEPTH
         if (m.alpha_mode == 2) {
             uint32_t flags = WS_BLEND;
@@ -450,17 +494,19 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const __grid_constant__ WK
     }
 }
 
-// ---- SHADOW: the probes of one hit slot, then the rest of __closesthit__radiance and (level 0, no BLEND) the raygen tail -----------------
+// ---- SHADOW: one work item per (hit slot, light) — the probe; the item that completes a slot finishes __closesthit__radiance for it ------
+// The hits of a model viewer are few (tens of thousands), so the probes run one per lane for as much parallelism as there is; the lane
+// that stores a slot's last attenuation sums the slot's terms in LIGHT order (not arrival order: the fp32 sum is the reference's) and,
+// at level 0 without BLEND, runs the raygen tail for the pixel.
 template <bool AH>
 struct WShadowWork {
     static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
     const WK& k;
     const AccelHeader* handle;
-    uint32_t nl, slot, li;
-    float3 result;
+    uint32_t nl, per_slot, slot, li;
     double att;
-    __device__ WShadowWork(const WK& k_, const AccelHeader* h, uint32_t nl_) : k(k_), handle(h), nl(nl_), slot(0), li(0), result(f3(0.f, 0.f, 0.f)), att(1.0) {}
+    __device__ WShadowWork(const WK& k_, const AccelHeader* h, uint32_t nl_) : k(k_), handle(h), nl(nl_), per_slot(max(nl_, 1u)), slot(0), li(0), att(1.0) {}
 
     __device__ __forceinline__ bool anyhit_enabled() const { return handle->anyhit != 0u; }
     __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
@@ -468,58 +514,54 @@ struct WShadowWork {
         return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), true, b1, b2, factor);
     }
     __device__ __forceinline__ void attenuate(float f) { att *= (double)f; }
-    // result += light.color * attenuation * intensity * N_dot_L * (diff + spec) (whitted.cu:249-256)
-    __device__ __forceinline__ void add_point(size_t s, float a)
-    {
-        if (!(a > 0.0f)) return;
-        const float4 c = k.t0[s], d = k.t1[s];
-        result = f3(result.x + (((c.x * a) * c.w) * d.w) * d.x, result.y + (((c.y * a) * c.w) * d.w) * d.y, result.z + (((c.z * a) * c.w) * d.w) * d.z);
-    }
-    // walk the lights from `li` on: ambient terms are added on the way, the first point light with a probe starts its traversal
-    __device__ __forceinline__ bool start_next_probe(Trav& s, float* my_ray)
-    {
-        for (; li < nl; ++li) {
-            const size_t idx = (size_t)slot * nl + li;
-            const uint32_t kind = k.kinds[idx];
-            if (kind == 2) { const float4 c = k.t0[idx]; result = f3(result.x + c.x, result.y + c.y, result.z + c.z); }
-            else if (kind == 1) {
-                const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
-                att = 1.0;
-                s.best.t = pd.w;
-                // traceOcclusion (whitted_cuda.h:127-159): TERMINATE_ON_FIRST_HIT | DISABLE_CLOSESTHIT, no face culling
-                if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, TP_ANY, 0u, 0u)) return true;
-                add_point(idx, 1.0f);  // nothing to traverse: the miss program commits the untouched attenuation
-            }
-        }
-        return false;
-    }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        slot = k.level_start + item;
-        li = 0;
-        const float4 b = k.base[slot];
-        result = f3(b.x, b.y, b.z);
-        if (start_next_probe(s, my_ray)) return true;
+        slot = k.level_start + item / per_slot;
+        li = item % per_slot;
+        att = 1.0;
+        if (li < nl && k.kinds[(size_t)slot * nl + li] == 1u) {
+            const size_t idx = (size_t)slot * nl + li;
+            const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
+            s.best.t = pd.w;
+            // traceOcclusion (whitted_cuda.h:127-159): TERMINATE_ON_FIRST_HIT | DISABLE_CLOSESTHIT, no face culling
+            if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, TP_ANY, 0u, 0u)) return true;
+            // nothing to traverse: the miss program commits the untouched attenuation
+        }
         commit(s, false);
         return false;
     }
     __device__ __forceinline__ bool next_instance(Trav& s, float* my_ray)
     {
+        if (any_ray_done(s) || handle->kind != ACCEL_KIND_IAS) return false;
         const size_t idx = (size_t)slot * nl + li;
-        if (!any_ray_done(s) && handle->kind == ACCEL_KIND_IAS) {
-            const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
-            if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u)) return true;
-        }
-        // the probe is finished: occluded -> attenuation never committed (0), else the pending product (whitted_cuda.h:155-158)
-        add_point(idx, (s.pack & TP_FOUND_ANY) ? 0.0f : (float)att);
-        ++li;
-        return start_next_probe(s, my_ray);
+        const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
+        return trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, s.pack & (TP_ANY | TP_FOUND_ANY), 0u, s.inst + 1u);
     }
-    __device__ __forceinline__ void commit(const Trav&, bool)
+    __device__ __forceinline__ void commit(const Trav&, bool found)
     {
+        // occluded -> the attenuation is never committed (0), else the pending product (whitted_cuda.h:155-158)
+        if (li < nl) k.att[(size_t)slot * nl + li] = found ? 0.0f : (float)att;
+        __threadfence();
+        if (atomicAdd(&k.arrived[slot], 1u) != per_slot - 1u) return;
+        __threadfence();
+        // last item of the slot: result += light.color * attenuation * intensity * N_dot_L * (diff + spec) in light order (whitted.cu:249-256)
+        const float4 b = k.base[slot];
+        float3 result = f3(b.x, b.y, b.z);
+        for (uint32_t l = 0; l < nl; ++l) {
+            const size_t idx = (size_t)slot * nl + l;
+            const uint32_t kind = k.kinds[idx];
+            if (kind == 2) { const float4 c = k.t0[idx]; result = f3(result.x + c.x, result.y + c.y, result.z + c.z); }
+            else if (kind == 1) {
+                const float a = *(volatile const float*)&k.att[idx];
+                if (a > 0.0f) {
+                    const float4 c = k.t0[idx], d = k.t1[idx];
+                    result = f3(result.x + (((c.x * a) * c.w) * d.w) * d.x, result.y + (((c.y * a) * c.w) * d.w) * d.y, result.z + (((c.z * a) * c.w) * d.w) * d.z);
+                }
+            }
+        }
         const WSlot h = k.slots[slot];
         if (h.flags & WS_BLEND) {
-            const float alpha = k.base[slot].w;  // base_color.w
+            const float alpha = b.w;  // base_color.w
             k.result[slot] = make_float4(result.x * alpha, result.y * alpha, result.z * alpha, h.one_minus_alpha);
         } else if (h.level == 0) {
             w_write_pixel(*k.params, h.pixel, result);
@@ -535,8 +577,9 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const 
     const WParams* P = k.params;
     const AccelHeader* handle = (const AccelHeader*)P->handle;
     const uint32_t end = min(k.counters->nslots, k.cap_slots);
-    const uint32_t n_items = end > k.level_start ? end - k.level_start : 0u;
-    WShadowWork<AH> work(k, handle, min(P->lights.count, k.nl_cap));
+    const uint32_t nl = min(P->lights.count, k.nl_cap);
+    const uint32_t n_items = end > k.level_start ? (end - k.level_start) * max(nl, 1u) : 0u;
+    WShadowWork<AH> work(k, handle, nl);
     trace_persistent(work, n_items, k.fetch, nullptr);
 }
 
@@ -641,7 +684,7 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_cnt = take(256), o_slots = take(sizeof(WSlot) * cap), o_base = take(16 * cap), o_t0 = take(16 * cap * nlp), o_t1 = take(16 * cap * nlp),
                  o_kinds = take(4 * cap * nlp), o_probes = take(32 * cap * nlp), o_result = take(blend ? 16 * cap : 0), o_cont = take(blend ? 4 * cap : 0),
-                 o_chain = take(blend ? 4 * (size_t)npix : 0);
+                 o_chain = take(blend ? 4 * (size_t)npix : 0), o_primary = take(4 * (size_t)npix), o_att = take(4 * cap * nlp), o_arr = take(4 * cap);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
@@ -654,11 +697,16 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     k.slots = (WSlot*)(W + o_slots); k.base = (float4*)(W + o_base); k.t0 = (float4*)(W + o_t0); k.t1 = (float4*)(W + o_t1);
     k.kinds = (uint32_t*)(W + o_kinds); k.probes = (float4*)(W + o_probes); k.result = (float4*)(W + o_result); k.cont = (uint32_t*)(W + o_cont);
     k.chain = (uint32_t*)(W + o_chain);
+    k.primary = (uint32_t*)(W + o_primary);
+    k.att = (float*)(W + o_att);
+    k.arrived = (unsigned int*)(W + o_arr);
     k.async_flags = flags;
     unsigned int* cursors = (unsigned int*)(W + o_cnt + 64);  // two per level
     B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters + all work-item cursors of the frame
     WCounters* h_cnt = (WCounters*)((char*)ctx->pinned + 512);
-    uint32_t n_items = npix, level_start = 0;
+    w_raygen_kernel<<<div_up(npix, 256), 256, 0, s>>>(k, npix);
+    B2_LAUNCH_CHECK(ctx);
+    uint32_t n_items = npix, level_start = 0;  // level 0: an upper bound (grid sizing); the kernels read the live counts
     for (uint32_t level = 0; level < W_MAX_TRACE_DEPTH; ++level) {
         k.level = level;
         k.level_start = level_start;
@@ -670,8 +718,8 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         w_shade_kernel<<<shade_grid, 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         k.fetch = cursors + 2 * level + 1;
-        if (anyhit) w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, n_items), COOP_BLOCK, 0, s>>>(k);
-        else w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, n_items), COOP_BLOCK, 0, s>>>(k);
+        if (anyhit) w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
+        else w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         if (!blend) break;
         // BLEND scenes: how many continuations did this level start?  (the only host synchronisation of a whitted launch)
