@@ -265,10 +265,15 @@ int b200rt_deinterleave(b200rt_context ctx, b200rt_stream stream, b200rt_devicep
  * (SDK/cuda/Light.h:31-71).  SBT: as sutil::Scene::createSBT builds it (SDK/sutil/Scene.cpp:1405-1433) — per primitive group a
  * radiance and an occlusion record, each carrying whitted::HitGroupData {GeometryData, MaterialData}; MaterialData textures are
  * cudaTextureObject_t handles and are sampled with tex2D like the reference does.
- * Scope: OPAQUE materials (the any-hit programs whitted.cu:100-137 are not built yet).  Errors found by the kernels — a MASK /
- * BLEND material was hit (rendered as opaque), or LaunchParams grew more lights than the launch's workspace was sized for — are
- * asynchronous like CUDA's: the NEXT launch on the context returns B200RT_ERROR_NOT_SUPPORTED / B200RT_ERROR_INVALID_OPERATION.
- * The first launch with a given d_params reads it back once (synchronises `stream`); later launches are fully asynchronous. */
+ * All three alpha modes: MASK / BLEND geometry (geometry flags without DISABLE_ANYHIT, SDK/sutil/Scene.cpp:904-966) runs
+ * __anyhit__radiance / __anyhit__occlusion (whitted.cu:100-137: alpha cut-outs, pending / committed occlusion attenuation) inside
+ * traversal, and ALPHA_MODE_BLEND hits continue behind themselves up to MAX_TRACE_DEPTH 8 (whitted.cu:266-286).  A scene whose
+ * hit-group records hold a BLEND material costs one host synchronisation per level of continuation; other scenes none.
+ * Errors found by the kernels — LaunchParams grew more lights than the launch's workspace was sized for, a BLEND material
+ * appeared in records that had none when they were first seen — are asynchronous like CUDA's: the NEXT launch on the context
+ * returns B200RT_ERROR_INVALID_OPERATION (and looks at the scene again).
+ * The first launch with a given (d_params, hit-group records) after an accel build reads the light count, the records' alpha modes
+ * and the traversable's any-hit flag back once (synchronises `stream`); later launches are fully asynchronous. */
 int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
                           const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height);
 

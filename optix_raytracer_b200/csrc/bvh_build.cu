@@ -809,7 +809,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
     // what the whitted launch learnt about the scene (light count, BLEND materials) belongs to the scene that was there before:
     // a new scene always comes with a build, and its buffers may well reuse the old addresses
     ctx->w_params = 0;
-    ctx->rc_params = 0;
+    for (auto& v : ctx->rc_params) v = 0;
 
     if (inputs[0].type == B200RT_BUILD_INPUT_TYPE_INSTANCES) {
         B2_REQUIRE(ctx, num_inputs == 1, "an instance build takes exactly one build input");

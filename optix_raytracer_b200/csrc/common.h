@@ -41,8 +41,9 @@ struct b200rt_context_t {
     bool w_blend = false;     // the hit-group records hold an ALPHA_MODE_BLEND material (continuation levels are run)
     // optixRaycasting launches: does the traversable of this d_params hold any-hit geometry?  (read once per d_params, forgotten at
     // the next accel build)
-    uint64_t rc_params = 0;
-    bool rc_anyhit = false;
+    uint64_t rc_params[4] = {0, 0, 0, 0};   // the sample launches two Params blocks alternately (optixRaycasting.cpp:291-313)
+    bool rc_anyhit[4] = {false, false, false, false};
+    unsigned int rc_next = 0;
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 

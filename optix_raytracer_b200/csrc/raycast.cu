@@ -14,6 +14,10 @@
 #include "trav_coop.cuh"
 #include "anyhit.cuh"
 
+#ifndef B200RT_RAY_BOUNDS
+#define B200RT_RAY_BOUNDS 1   // drop the rays of a buffer that pass the scene by at its bounds (trav_coop.cuh: trav_begin<BOUNDS>)
+#endif
+
 namespace b200rt {
 
 struct RayRec { float ox, oy, oz, tmin, dx, dy, dz, tmax; };  // optixRaycastingKernels.h:35-41
@@ -103,7 +107,7 @@ struct RayWork {
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
         // rays of a buffer come from anywhere: those that pass the scene (or an instance) by are dropped at its bounds
-        if (!trav_begin_handle<true>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
+        if (!trav_begin_handle<B200RT_RAY_BOUNDS != 0>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
             commit(s, false);
             return false;
         }
@@ -113,7 +117,7 @@ struct RayWork {
     {
         if (handle->kind == ACCEL_KIND_GAS || any_ray_done(s)) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
-        return trav_begin_handle<true>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
+        return trav_begin_handle<B200RT_RAY_BOUNDS != 0>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
                                  cull_flags((uint32_t)item), s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
@@ -354,19 +358,27 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     // record too short to hold them runs without any-hit programs) and only ever runs on geometry that leaves any-hit enabled: whether
     // the traversable has any is read from its header once per d_params (one synchronisation; forgotten at the next accel build)
     const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
-    if (full_records && ctx->rc_params != d_params) {
-        RaycastParamsDev hp;
-        B2_CUDA(ctx, cudaMemcpyAsync(&hp, (const void*)d_params, sizeof(hp), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(ctx, cudaStreamSynchronize(s));
-        B2_REQUIRE(ctx, hp.handle, "Params.handle is null");
-        AccelHeader ah;
-        B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(ctx, cudaStreamSynchronize(s));
-        B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "Params.handle is not a b200rt traversable");
-        ctx->rc_params = d_params;
-        ctx->rc_anyhit = ah.anyhit != 0;
+    bool anyhit = false;
+    if (full_records) {
+        int slot = -1;
+        for (int i = 0; i < 4; ++i)
+            if (ctx->rc_params[i] == d_params) slot = i;
+        if (slot < 0) {
+            RaycastParamsDev hp;
+            B2_CUDA(ctx, cudaMemcpyAsync(&hp, (const void*)d_params, sizeof(hp), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(ctx, cudaStreamSynchronize(s));
+            B2_REQUIRE(ctx, hp.handle, "Params.handle is null");
+            AccelHeader ah;
+            B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(ctx, cudaStreamSynchronize(s));
+            B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "Params.handle is not a b200rt traversable");
+            slot = (int)(ctx->rc_next++ % 4u);
+            ctx->rc_params[slot] = d_params;
+            ctx->rc_anyhit[slot] = ah.anyhit != 0;
+        }
+        anyhit = ctx->rc_anyhit[slot];
     }
-    if (full_records && ctx->rc_anyhit) {
+    if (anyhit) {
         const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, AH_TEXTURE_MASK};
         trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
             nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
