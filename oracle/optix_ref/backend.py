@@ -11,6 +11,7 @@ on the GPU box only (probed: SURVEY.md section 8c / DESIGN.md section 6); `avail
 can be used in this process.
 """
 import ctypes as C
+import os
 import pathlib
 
 import numpy as np
@@ -22,6 +23,12 @@ from optix_raytracer_b200 import host
 _REF = pathlib.Path(__file__).resolve().parents[1] / "_ref"
 _LIB = None
 _WHY = None
+_SHIM = None
+
+
+def shim_active():
+    """True when this process drives the harness through optix_raytracer_b200/optix_shim/libnvoptix.so.1 (B200RT_OPTIX_SHIM=1)."""
+    return _SHIM is not None
 
 # OptixPayloadSemantics (reference include/optix_types.h:2003-2029)
 _CALLER_R, _CALLER_W, _CALLER_RW = 1 << 0, 2 << 0, 3 << 0
@@ -53,6 +60,12 @@ def _load():
     global _LIB, _WHY
     if _LIB is not None or _WHY is not None:
         return _LIB
+    if os.environ.get("B200RT_OPTIX_SHIM") == "1":
+        # Run the harness — an OptiX host program like the samples — on the product's own optixQueryFunctionTable instead of the driver's:
+        # a library with the soname libnvoptix.so.1 that is already loaded is what optixInit()'s dlopen("libnvoptix.so.1") returns.
+        global _SHIM
+        shim = pathlib.Path(L.__file__).resolve().parent / "optix_shim" / "libnvoptix.so.1"
+        _SHIM = C.CDLL(str(shim), mode=C.RTLD_GLOBAL)
     so = _REF / "liboptixref.so"
     if not so.exists():
         _WHY = f"{so} not built (make -C oracle optix needs /root/reference)"

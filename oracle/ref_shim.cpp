@@ -67,6 +67,7 @@ void ref_light_normal(const float* v1, const float* v2, float* n)
 // (SDK/cuda/whitted.h:44-48, SDK/cuda/GeometryData.h:73-80,248-262, SDK/cuda/BufferView.h:32-38, SDK/optixPathTracer/optixPathTracer.h,
 //  SDK/optixMultiGPU/optixMultiGPU.h, SDK/optixRaycasting/optixRaycasting.h + optixRaycastingKernels.h)
 #include <optix_types.h>
+#include <optix_function_table.h>
 #include <cuda/whitted.h>
 #include <cstring>
 namespace pt {
@@ -157,6 +158,29 @@ int ref_whitted_layout(int* out)
     out[n++] = (int)offsetof(whitted::LaunchParams, eye); out[n++] = (int)offsetof(whitted::LaunchParams, U); out[n++] = (int)offsetof(whitted::LaunchParams, lights);
     out[n++] = (int)offsetof(whitted::LaunchParams, miss_color); out[n++] = (int)offsetof(whitted::LaunchParams, handle);
     return n;
+}
+
+// OptiX host API layouts the function-table shim mirrors (optix_raytracer_b200/csrc/optix_shim.cu: b200rt_optix_shim_layout returns the
+// same list): ABI version, sizeof(OptixFunctionTable), OptixDeviceContextOptions, OptixProgramGroupDesc and the offsets of its entry
+// names, OptixPipelineCompileOptions, OptixStackSizes, program-group kinds, the RTCORE_VERSION property id.
+int ref_optix_api_layout(int* out)
+{
+    int k = 0;
+    out[k++] = OPTIX_ABI_VERSION;
+    out[k++] = (int)sizeof(OptixFunctionTable);
+    out[k++] = (int)sizeof(OptixDeviceContextOptions);
+    out[k++] = (int)sizeof(OptixProgramGroupDesc);
+    out[k++] = (int)(offsetof(OptixProgramGroupDesc, raygen) + offsetof(OptixProgramGroupSingleModule, entryFunctionName));
+    out[k++] = (int)(offsetof(OptixProgramGroupDesc, hitgroup) + offsetof(OptixProgramGroupHitgroup, entryFunctionNameCH));
+    out[k++] = (int)(offsetof(OptixProgramGroupDesc, hitgroup) + offsetof(OptixProgramGroupHitgroup, entryFunctionNameAH));
+    out[k++] = (int)(offsetof(OptixProgramGroupDesc, hitgroup) + offsetof(OptixProgramGroupHitgroup, entryFunctionNameIS));
+    out[k++] = (int)sizeof(OptixPipelineCompileOptions);
+    out[k++] = (int)sizeof(OptixStackSizes);
+    out[k++] = (int)OPTIX_PROGRAM_GROUP_KIND_RAYGEN;
+    out[k++] = (int)OPTIX_PROGRAM_GROUP_KIND_MISS;
+    out[k++] = (int)OPTIX_PROGRAM_GROUP_KIND_HITGROUP;
+    out[k++] = (int)OPTIX_DEVICE_PROPERTY_RTCORE_VERSION;
+    return k;
 }
 
 }  // extern "C"

@@ -160,3 +160,31 @@ def test_whitted_struct_layouts_match_the_reference_headers():
                                  wl["lp_miss_color"], wl["lp_handle"])
     assert (wl["light_type"], wl["light_point"] + wl["point_color"], wl["light_point"] + wl["point_intensity"], wl["light_point"] + wl["point_position"],
             wl["light_point"] + wl["point_falloff"]) == (0, 4, 16, 20, 32)
+
+
+def test_optix_function_table_shim_answers_like_the_reference_expects():
+    """optixQueryFunctionTable of optix_shim/libnvoptix.so.1 (csrc/optix_shim.cu): ABI 87 only, the 384-byte table of the reference's
+    include/optix_function_table.h, every entry callable; the OptiX API structs it mirrors have the layout measured on the reference headers."""
+    import ctypes as C
+    from optix_raytracer_b200 import _lib
+    shim = pathlib.Path(_lib.__file__).resolve().parent / "optix_shim" / "libnvoptix.so.1"
+    assert shim.exists(), "csrc/Makefile builds it next to libb200rt.so"
+    lib = C.CDLL(str(shim))
+    q = lib.optixQueryFunctionTable
+    q.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lay = KAT["optix_api_layout"]
+    n = lay["sizeof_OptixFunctionTable"] // 8
+    table = (C.c_void_p * n)()
+    assert q(lay["OPTIX_ABI_VERSION"] + 1, 0, None, None, table, C.sizeof(table)) == 7801   # OPTIX_ERROR_UNSUPPORTED_ABI_VERSION
+    assert q(lay["OPTIX_ABI_VERSION"], 0, None, None, table, C.sizeof(table) - 8) == 7802   # OPTIX_ERROR_FUNCTION_TABLE_SIZE_MISMATCH
+    assert q(lay["OPTIX_ABI_VERSION"], 0, None, None, table, C.sizeof(table)) == 0
+    assert all(table[i] for i in range(n))
+    # optixGetErrorName / optixGetErrorString are the first two entries
+    name = C.CFUNCTYPE(C.c_char_p, C.c_int)(table[0])
+    assert name(7800) == b"OPTIX_ERROR_NOT_SUPPORTED" and name(0) == b"OPTIX_SUCCESS"
+    # an entry without a restatement (optixDenoiserCreate, entry 40) says so
+    assert C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)(table[40])(None, 0, None, None) == 7800
+    out = (C.c_uint * 32)()
+    k = lib.b200rt_optix_shim_layout(out, 32)
+    assert list(out[:k]) == list(lay.values())
+

@@ -265,3 +265,18 @@ def test_whitted_untextured_bit_exact(ctx, orc, alpha_mode, double_sided):
     mv.close()
 
 
+def test_unmodified_optix_host_calls_run_on_the_function_table_shim():
+    """SURVEY 8(b) layer 2: a library with the soname libnvoptix.so.1 answers optixQueryFunctionTable, so the reference's own call sequence
+    (here: oracle/optix_ref/optix_harness.cpp, built against the reference's optix_stubs.h) runs on b200rt and gives bit-identical
+    results to the native C ABI — Cornell (both program sets), optixRaycasting with an alpha mask, whitted with BLEND, imgui_test."""
+    import os
+    import pathlib
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parents[1]
+    if not (root / "oracle" / "_ref" / "liboptixref.so").exists():
+        pytest.skip("oracle/_ref/liboptixref.so (the OptiX host harness) is built only where /root/reference exists")
+    env = dict(os.environ, B200RT_OPTIX_SHIM="1")
+    r = subprocess.run([sys.executable, str(root / "tests" / "shim_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+

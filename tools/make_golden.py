@@ -126,6 +126,12 @@ def main():
              "LaunchParams", "lp_subframe_index", "lp_accum_buffer", "lp_frame_buffer", "lp_eye", "lp_U", "lp_lights", "lp_miss_color", "lp_handle"]
     assert k == len(names)
     out["whitted_layout"] = dict(zip(names, list(o[:k])))
+    k = ref.ref_optix_api_layout(o)
+    names = ["OPTIX_ABI_VERSION", "sizeof_OptixFunctionTable", "sizeof_OptixDeviceContextOptions", "sizeof_OptixProgramGroupDesc", "off_single_entryFunctionName",
+             "off_hitgroup_entryFunctionNameCH", "off_hitgroup_entryFunctionNameAH", "off_hitgroup_entryFunctionNameIS", "sizeof_OptixPipelineCompileOptions",
+             "sizeof_OptixStackSizes", "KIND_RAYGEN", "KIND_MISS", "KIND_HITGROUP", "PROPERTY_RTCORE_VERSION"]
+    assert k == len(names)
+    out["optix_api_layout"] = dict(zip(names, list(o[:k])))
     p = ROOT / "tests" / "golden" / "kat.json"
     p.write_text(json.dumps(out) + "\n")
     print("wrote", p, p.stat().st_size, "bytes")
