@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spl", type=int, default=16)
     ap.add_argument("--sample-groups", type=int, default=None, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
+    ap.add_argument("--ray-sort", type=int, default=None, help="b200rt_pt_options.ray_sort (default: 1 for the synthetic workload, 0 for cornell)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -201,6 +202,7 @@ def run_b200rt(a, rank, world, local_rank):
     e0.record()
     pt = host.PathTracer(ctx, a.width, a.height, a.spl, vertices=verts, mat_indices=mats, multigpu=multigpu)
     pt.sample_groups = a.sample_groups
+    pt.ray_sort = a.ray_sort
     e1.record()
     torch.cuda.synchronize()
     build_ms = e0.elapsed_time(e1)
@@ -336,7 +338,7 @@ def run_b200rt(a, rank, world, local_rank):
                "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_name(a), "triangles": int(info.num_triangles), "bvh8_nodes": int(info.num_nodes), "bvh8_node_bytes": int(info.reserved) or 80,
-                          "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl, "sample_groups": a.sample_groups,
+                          "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl, "sample_groups": a.sample_groups, "ray_sort": a.ray_sort,
                           "parallelism": f"image split x{world} (StaticWorkDistribution 8x4 tiles), scene replicated" + (", ncclAllGather" if world > 1 else ""),
                           "l2": ("inputs larger than L2: accel %.2f GB vs L2 %.0f MB" % (scene_bytes / 1e9, l2_bytes / 1e6)) if flush is None
                                 else "L2 flushed between timed steps (1.5x L2 fill)",
@@ -354,6 +356,8 @@ def main():
     a = parse()
     if a.width is None:
         a.width, a.height = (3840, 2160) if a.workload == "synthetic" else (768, 768)
+    if a.ray_sort is None:
+        a.ray_sort = 0
     if a.sample_groups is None:
         a.sample_groups = 8 if a.workload == "synthetic" else 4   # measured best on one B200 (gpurun_out/sg_*.json); any value gives the same image on any N
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -233,6 +233,10 @@ typedef struct b200rt_pt_options {
                                   * wider wavefront iterations; differs from G = 1 only in that summation order (~1 ulp). */
     uint32_t collect_stats;      /* bit mask of B200RT_PT_STATS_*; non-zero fills *stats */
     b200rt_pt_stats* stats;      /* host pointer or NULL */
+    uint32_t ray_sort;           /* 1: before every trace stage but the first, order the rays by (origin cell, direction) with a radix sort
+                                  * — for scenes whose BVH lives in HBM, where incoherent bounce rays are bound by node-fetch latency.
+                                  * Costs one host synchronisation per wavefront iteration.  Results are unaffected (a lane owns its state). */
+    uint32_t reserved;
 } b200rt_pt_options;
 int b200rt_launch_pathtracer(b200rt_context ctx, b200rt_stream stream, b200rt_deviceptr d_params,
                              const b200rt_shader_binding_table* sbt, unsigned int width, unsigned int height,

@@ -92,7 +92,7 @@ class PTStats(C.Structure):
 
 
 class PTOptions(C.Structure):
-    _fields_ = [("sample_groups", u32), ("collect_stats", u32), ("stats", C.POINTER(PTStats))]
+    _fields_ = [("sample_groups", u32), ("collect_stats", u32), ("stats", C.POINTER(PTStats)), ("ray_sort", u32), ("reserved", u32)]
 
 
 assert C.sizeof(BuildInput) == 1032 and C.sizeof(TriangleArray) == 240 and C.sizeof(Instance) == 80

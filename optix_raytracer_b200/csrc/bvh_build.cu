@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_IPT = 16, RS_TILE = RS_THREADS * RS_IPT;
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift,
                                                               uint32_t* __restrict__ hist, uint32_t nblocks)
 {
     __shared__ uint32_t h[256];
@@ -275,8 +276,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __r
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                                                 uint64_t* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n,
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                                 K* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n,
                                                                  int shift, const uint32_t* __restrict__ offs, uint32_t nblocks)
 {
     __shared__ uint32_t wcount[RS_WARPS][256];
@@ -284,14 +286,14 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
     __syncthreads();
     const uint32_t wbase = blockIdx.x * RS_TILE + warp * (32 * RS_IPT);
-    uint64_t k[RS_IPT];
+    K k[RS_IPT];
     uint16_t rank[RS_IPT];
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < RS_IPT; ++r) {
         const uint32_t idx = wbase + r * 32 + lane;
         const bool valid = idx < n;
-        k[r] = valid ? kin[idx] : ~0ull;
+        k[r] = valid ? kin[idx] : (K)~(K)0;
         const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
         const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : (256u + lane));
         const uint32_t cnt = valid ? wcount[warp][d] : 0u;
@@ -322,6 +324,29 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
             vout[dst] = vin[idx];
         }
     }
+}
+
+// Stable LSD sort of (32-bit key, 32-bit value) pairs, `passes` digits of 8 bits from bit 0 — the ray reordering of pathtracer.cu.
+// keys / vals are ping-pong buffers; returns the index of the buffer holding the result.  hist: 256 * div_up(n, RS_TILE) words,
+// scan_tmp: radix_sort_scan_words(n) words.
+size_t radix_sort_hist_words(size_t n) { return 256 * (size_t)std::max(1u, div_up(n, RS_TILE)); }
+size_t radix_sort_scan_words(size_t n) { return scan_temp_elems<uint32_t>(radix_sort_hist_words(n)); }
+int radix_sort_pairs32(b200rt_context ctx, cudaStream_t s, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* scan_tmp,
+                       int* result)
+{
+    int cur = 0;
+    const uint32_t blocks = std::max(1u, div_up(n, RS_TILE));
+    for (int pass = 0; pass < passes && n > 1; ++pass) {
+        rs_hist_kernel<uint32_t><<<blocks, RS_THREADS, 0, s>>>(keys[cur], n, pass * 8, hist, blocks);
+        B2_LAUNCH_CHECK(ctx);
+        int rc = exclusive_scan<uint32_t>(ctx, hist, 256 * (size_t)blocks, scan_tmp, s);
+        if (rc) return rc;
+        rs_scatter_kernel<uint32_t><<<blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass * 8, hist, blocks);
+        B2_LAUNCH_CHECK(ctx);
+        cur ^= 1;
+    }
+    *result = cur;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -904,12 +929,12 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             int cur = 0;
             const int passes = (3 * p.morton_bits + 7) / 8;
             for (int pass = 0; pass < passes && N > 1; ++pass) {
-                rs_hist_kernel<<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], N, pass * 8, hist, p.rs_blocks);
+                rs_hist_kernel<uint64_t><<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], N, pass * 8, hist, p.rs_blocks);
                 B2_LAUNCH_CHECK(ctx);
                 rc = exclusive_scan<uint32_t>(ctx, hist, 256 * (size_t)p.rs_blocks, (uint32_t*)scan_tmp, s);
                 if (rc) return rc;
-                rs_scatter_kernel<<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], N, pass * 8, hist,
-                                                                     p.rs_blocks);
+                rs_scatter_kernel<uint64_t><<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], N, pass * 8, hist,
+                                                                               p.rs_blocks);
                 B2_LAUNCH_CHECK(ctx);
                 cur ^= 1;
             }

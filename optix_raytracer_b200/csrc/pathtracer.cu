@@ -122,6 +122,9 @@ struct Lanes {
     uint32_t groups, nlaunch;
     unsigned int* ext_list;  // TRACE work items: item i < n_ext is the extension ray of lane ext_list[i],
     unsigned int* shd_list;  //                   item n_ext + j the shadow ray of lane shd_list[j]
+    unsigned int* key_ext;   // ray_sort: sort key of ext_list[i] / shd_list[j], written with the list entry
+    unsigned int* key_shd;
+    const unsigned int* items;  // ray_sort: this iteration's rays in sorted order, lane | shadow << 31 (nullptr: the two lists as they are)
     Counters* counters;
 };
 
@@ -150,16 +153,67 @@ __device__ __forceinline__ bool lane_pixel(const Frame& f, uint32_t lane, int& p
     return !(px > (int)f.width - 1 || py > (int)f.height - 1);  // optixMultiGPU.cu:221-223
 }
 
-__device__ __forceinline__ void queue_push(unsigned int* queue, unsigned int* count, bool active, uint32_t lane)
+__device__ __forceinline__ uint32_t queue_push(unsigned int* queue, unsigned int* count, bool active, uint32_t lane)
 {
     const uint32_t mask = __ballot_sync(__activemask(), active);
-    if (!active) return;
+    if (!active) return 0xffffffffu;
     const uint32_t lane_id = threadIdx.x & 31;
     const uint32_t leader = __ffs(mask) - 1;
     uint32_t base = 0;
     if (lane_id == leader) base = atomicAdd(count, __popc(mask));
     base = __shfl_sync(mask, base, leader);
-    queue[base + __popc(mask & ((1u << lane_id) - 1u))] = lane;
+    const uint32_t idx = base + __popc(mask & ((1u << lane_id) - 1u));
+    queue[idx] = lane;
+    return idx;
+}
+
+// ---- ray reordering (b200rt_pt_options.ray_sort) ----------------------------------------------------------------------------------
+// Bounce rays of a big scene start all over it and go everywhere: a warp's 24 node fetches are 24 cache misses, and the trace kernel is
+// bound by their latency (profiles/r01_trace_kernel.md: camera rays trace at 5.4 Grays/s, the average ray at 2.4).  Sorting the rays
+// of an iteration by the cell of their origin, then by direction, puts rays that walk the same part of the tree into the same warp.
+// Key: Morton code of the origin on a 2^SORT_OBITS grid over the scene bounds (high bits), direction on 2^SORT_DBITS steps per axis (low).
+#ifndef B200RT_SORT_OBITS
+#define B200RT_SORT_OBITS 6
+#endif
+#ifndef B200RT_SORT_DBITS
+#define B200RT_SORT_DBITS 2
+#endif
+constexpr int SORT_OBITS = B200RT_SORT_OBITS, SORT_DBITS = B200RT_SORT_DBITS;
+constexpr int SORT_PASSES = (3 * (SORT_OBITS + SORT_DBITS) + 7) / 8;
+static_assert(3 * (SORT_OBITS + SORT_DBITS) <= 32, "sort key is 32 bits");
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v)  // ...b2 b1 b0 -> ...b2 0 0 b1 0 0 b0 (up to 10 bits)
+{
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t ray_sort_key(const AccelHeader* __restrict__ h, float3 o, float3 d)
+{
+    const float on = (float)(1 << SORT_OBITS), dn = (float)(1 << SORT_DBITS);
+    const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2];
+    const float ex = fmaxf(h->bounds[3] - lx, 1e-30f), ey = fmaxf(h->bounds[4] - ly, 1e-30f), ez = fmaxf(h->bounds[5] - lz, 1e-30f);
+    const uint32_t qx = (uint32_t)fminf(fmaxf(__fdividef(o.x - lx, ex) * on, 0.0f), on - 1.0f);
+    const uint32_t qy = (uint32_t)fminf(fmaxf(__fdividef(o.y - ly, ey) * on, 0.0f), on - 1.0f);
+    const uint32_t qz = (uint32_t)fminf(fmaxf(__fdividef(o.z - lz, ez) * on, 0.0f), on - 1.0f);
+    const uint32_t dx = (uint32_t)fminf(fmaxf((d.x * 0.5f + 0.5f) * dn, 0.0f), dn - 1.0f);
+    const uint32_t dy = (uint32_t)fminf(fmaxf((d.y * 0.5f + 0.5f) * dn, 0.0f), dn - 1.0f);
+    const uint32_t dz = (uint32_t)fminf(fmaxf((d.z * 0.5f + 0.5f) * dn, 0.0f), dn - 1.0f);
+    const uint32_t okey = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+    const uint32_t dkey = spread3(dx) | (spread3(dy) << 1) | (spread3(dz) << 2);
+    return (okey << (3 * SORT_DBITS)) | dkey;
+}
+
+// (key, lane | shadow << 31) pairs of one iteration's rays, extension rays first
+__global__ void __launch_bounds__(256) pt_build_items_kernel(Lanes L, int cur, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t n_ext = L.counters->n_ext[cur], n_shd = L.counters->n_shd[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ext + n_shd; i += gridDim.x * blockDim.x) {
+        if (i < n_ext) { keys[i] = L.key_ext[i]; vals[i] = L.ext_list[i]; }
+        else { keys[i] = L.key_shd[i - n_ext]; vals[i] = L.shd_list[i - n_ext] | 0x80000000u; }
+    }
 }
 
 template <int MODE>
@@ -215,13 +269,15 @@ struct PTWork {
 
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        if (item < n_ext) {
-            lane = L.ext_list[item];
+        bool ext;
+        if (L.items) { const uint32_t e = L.items[item]; lane = e & 0x7fffffffu; ext = (e >> 31) == 0u; }
+        else if (item < n_ext) { lane = L.ext_list[item]; ext = true; }
+        else { lane = L.shd_list[item - n_ext]; ext = false; }
+        if (ext) {
             const float4 ro = L.ray_o[lane], rd = L.ray_d[lane];
             s.best.t = 1e16f;
             if (!trav_begin_handle(s, my_ray, f.handle, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 0.01f, 0u, 0u, 0u)) { commit(s, false); return false; }
         } else {
-            lane = L.shd_list[item - n_ext];
             const float4 so = L.shd_o[lane], sd = L.shd_d[lane];
             weight = sd.w;
             s.best.t = so.w;
@@ -366,6 +422,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t qi = base + threadIdx.x;
         bool keep = false, want_ext = false, want_shd = false;
+        float3 key_eo = f3(0.f, 0.f, 0.f), key_ed = key_eo, key_so = key_eo, key_sd = key_eo;  // rays pushed this iteration (ray_sort keys)
         uint32_t lane = 0;
         if (qi < n) {
             lane = queue[qi];
@@ -447,6 +504,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
                     if (nDl > 0.0f && LnDl > 0.0f) {
                         const float A = length(cross(lt.v1, lt.v2));
                         const float weight = fdiv((nDl * LnDl) * A, (3.14159265358979323846f * Ldist) * Ldist);
+                        key_so = P; key_sd = Lv;
                         L.shd_o[lane] = make_float4(P.x, P.y, P.z, Ldist - 0.01f);
                         L.shd_d[lane] = make_float4(Lv.x, Lv.y, Lv.z, weight);
                         L.pend[lane] = make_float4(att.x, att.y, att.z, 0.f);
@@ -496,6 +554,7 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
                     keep = true;
                     want_ext = (nflags & LF_NO_EXT) == 0u;
                     want_shd = (nflags & LF_SHADOW) != 0u;
+                    key_eo = nrg; key_ed = ndir;
                     L.ray_o[lane] = make_float4(nrg.x, nrg.y, nrg.z, __uint_as_float(seed));
                     L.ray_d[lane] = make_float4(ndir.x, ndir.y, ndir.z, __uint_as_float(nflags));
                     L.att[lane] = make_float4(att.x, att.y, att.z, __uint_as_float(pixel_seed));
@@ -504,8 +563,12 @@ __global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ 
             }
         }
         queue_push(next_queue, next_count, keep, lane);
-        queue_push(L.ext_list, next_ext, want_ext, lane);
-        queue_push(L.shd_list, next_shd, want_shd, lane);
+        const uint32_t ie = queue_push(L.ext_list, next_ext, want_ext, lane);
+        const uint32_t is = queue_push(L.shd_list, next_shd, want_shd, lane);
+        if (L.key_ext) {
+            if (want_ext) L.key_ext[ie] = ray_sort_key(f.handle, key_eo, key_ed);
+            if (want_shd) L.key_shd[is] = ray_sort_key(f.handle, key_so, key_sd);
+        }
     }
 }
 
@@ -680,6 +743,11 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     const size_t o_rad = MODE == 1 ? take(16 * L) : 0, o_emi = MODE == 1 ? take(16 * L) : 0;
     const size_t o_hit = take(8 * L), o_q0 = take(4 * L), o_q1 = take(4 * L), o_ext = take(4 * L), o_shd = take(4 * L);
     const size_t o_part = groups > 1 ? take(16 * L) : 0;
+    // ray_sort: keys written with the two lists, and the (key, item) ping-pong of the radix sort over both (2 L items at most)
+    const bool sorting = opt && opt->ray_sort == 1u;
+    const size_t o_kext = sorting ? take(4 * L) : 0, o_kshd = sorting ? take(4 * L) : 0, o_sk0 = sorting ? take(8 * L) : 0, o_sk1 = sorting ? take(8 * L) : 0,
+                 o_sv0 = sorting ? take(8 * L) : 0, o_sv1 = sorting ? take(8 * L) : 0, o_hist = sorting ? take(4 * radix_sort_hist_words(2 * L)) : 0,
+                 o_scan = sorting ? take(4 * radix_sort_scan_words(2 * L)) : 0;
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
@@ -697,6 +765,11 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     ln.partial = groups > 1 ? (float4*)(W + o_part) : nullptr;
     ln.groups = groups;
     ln.nlaunch = nlaunch;
+    ln.key_ext = sorting ? (unsigned int*)(W + o_kext) : nullptr;
+    ln.key_shd = sorting ? (unsigned int*)(W + o_kshd) : nullptr;
+    ln.items = nullptr;
+    uint32_t* sort_keys[2] = {(uint32_t*)(W + o_sk0), (uint32_t*)(W + o_sk1)};
+    uint32_t* sort_vals[2] = {(uint32_t*)(W + o_sv0), (uint32_t*)(W + o_sv1)};
 
     const uint64_t launches0 = ctx->launches;
     B2_CUDA(ctx, cudaMemsetAsync(ln.counters, 0, sizeof(Counters), s));
@@ -725,9 +798,22 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     };
     int cur = 0;
     uint32_t iterations = 0;
-    const int CHECK_EVERY = 8;
+    const int CHECK_EVERY = sorting ? 1 : 8;
     for (;;) {
         for (int k = 0; k < CHECK_EVERY; ++k) {
+            ln.items = nullptr;
+            if (sorting && iterations > 0) {
+                // the counts of this iteration's rays are on the host (read below); camera rays (iteration 0) are coherent as they are
+                const uint32_t n_rays = h_cnt->n_ext[cur] + h_cnt->n_shd[cur];
+                if (n_rays >= 65536u) {
+                    pt_build_items_kernel<<<persistent_grid(ctx, n_rays, 256, 8), 256, 0, s>>>(ln, cur, sort_keys[0], sort_vals[0]);
+                    B2_LAUNCH_CHECK(ctx);
+                    int res = 0;
+                    rc = radix_sort_pairs32(ctx, s, sort_keys, sort_vals, n_rays, SORT_PASSES, (uint32_t*)(W + o_hist), (uint32_t*)(W + o_scan), &res);
+                    if (rc) return rc;
+                    ln.items = sort_vals[res];
+                }
+            }
             if (timing) cudaEventRecord(next_event(), s);
             if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, COOP_BLOCK, 0, s>>>(params, ln, cur);
             else pt_trace_kernel<MODE, false><<<trace_grid, COOP_BLOCK, 0, s>>>(params, ln, cur);

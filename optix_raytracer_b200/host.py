@@ -388,6 +388,7 @@ class PathTracer:
         self.d_params = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.stats = L.PTStats()
         self.sample_groups = 1
+        self.ray_sort = 0  # b200rt_pt_options.ray_sort
 
     def launch_subframe(self, subframe_index=None, collect_stats=False, sample_groups=None):
         """launchSubframe (optixPathTracer.cpp:488-511): copy Params to the device, launch; asynchronous.
@@ -397,7 +398,7 @@ class PathTracer:
         self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
         self.d_params.copy_(self.h_params, non_blocking=True)
         groups = self.sample_groups if sample_groups is None else sample_groups
-        opts = L.PTOptions(int(groups), int(collect_stats), C.pointer(self.stats))  # collect_stats: bit mask of L.PT_STATS_*
+        opts = L.PTOptions(int(groups), int(collect_stats), C.pointer(self.stats), int(self.ray_sort), 0)  # collect_stats: bit mask of L.PT_STATS_*
         ctx = self.ctx
         if self.multigpu:
             ctx.launch_multigpu(self.programs, self.d_params.data_ptr(), C.sizeof(self.params), self.sbt, self.num_samples, opts)
@@ -804,7 +805,7 @@ class Playground:
         p.dt += p.samples_per_frame
         self.h_params.numpy()[:] = np.frombuffer(bytes(p), np.uint8)
         self.d_params.copy_(self.h_params, non_blocking=True)
-        opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats))
+        opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats), 0, 0)
         self.ctx.launch_playground(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height, opts)
         return self.stats if collect_stats else None
 

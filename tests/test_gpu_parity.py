@@ -60,14 +60,17 @@ def test_cornell_random_rays_closest_and_any(ctx, orc, node_format, monkeypatch)
     assert 0.1 < occ.mean() < 0.9
 
 
-@pytest.mark.parametrize("mode,groups", [(0, 1), (1, 1), (0, 3), (1, 4), (0, 8)])
-def test_cornell_pathtracer_bit_exact(ctx, orc, mode, groups):
+@pytest.mark.parametrize("mode,groups,ray_sort", [(0, 1, 0), (1, 1, 0), (0, 3, 0), (1, 4, 0), (0, 8, 0), (0, 4, 1), (1, 2, 1)])
+def test_cornell_pathtracer_bit_exact(ctx, orc, mode, groups, ray_sort):
     """groups = b200rt_pt_options.sample_groups: 1 is the reference's flat summation order; 3 (uneven split of 4 samples), 4 and 8
-    (more groups than samples: empty groups) run the samples of a pixel in parallel lanes and must match the oracle's grouped sum."""
+    (more groups than samples: empty groups) run the samples of a pixel in parallel lanes and must match the oracle's grouped sum.
+    ray_sort = b200rt_pt_options.ray_sort: the rays of an iteration are radix-sorted by origin cell and direction before they are
+    traced (image large enough for iterations above the 65536-ray threshold); a lane owns its state, so nothing may change."""
     from optix_raytracer_b200 import host
-    w, h, spl = 96, 80, 4
+    w, h, spl = (320, 240, 4) if ray_sort else (96, 80, 4)
     pt = host.PathTracer(ctx, w, h, spl, multigpu=(0, 1) if mode else None)
     pt.sample_groups = groups
+    pt.ray_sort = ray_sort
     sc = pt.scene
     scene = orc.Scene(sc["vertices"].reshape(-1, 3, 3), sc["mat_indices"])
     ref_accum = None
