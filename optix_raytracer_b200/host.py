@@ -912,3 +912,93 @@ class MeshViewer:
         for hc, tex, arr in self._tex_handles:
             hc.lib.b200rt_texture_destroy(hc.h, tex, arr)
         self._tex_handles = []
+
+# ---- output and model ingest either side of the path ---------------------------------------------------------
+def _to_srgb_u8(f):
+    """toSRGB + the 256-scale quantisation of sutil::saveImage's float branches (SDK/sutil/sutil.cpp:585-618, SDK/cuda/helpers.h:36-48)."""
+    f = np.asarray(f, np.float32)
+    inv = np.float32(1.0 / 2.4)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        srgb = np.where(f < np.float32(0.0031308), np.float32(12.92) * f, np.float32(1.055) * np.power(f, inv, dtype=np.float32) - np.float32(0.055))
+    v = (np.float32(256.0) * srgb.astype(np.float32)).astype(np.int64)
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
+def save_image(path, image, disable_srgb_conversion=False):
+    """sutil::saveImage (SDK/sutil/sutil.cpp:542-709) for .ppm / .png: `image` is a (h, w, 4) uint8 frame (written as is), or a (h, w, 3|4)
+    float32 buffer (sRGB-converted unless disabled, 256-scaled, clamped).  Rows are flipped: the launch index (0, 0) is the bottom-left
+    pixel of the picture.  PPM is the binary P6 the reference writes; PNG keeps the alpha of a uchar4 frame like stbi_write_png(…, 4, …)."""
+    if hasattr(image, "cpu"):
+        image = image.cpu().numpy()
+    a = np.asarray(image)
+    if a.ndim != 3 or a.shape[2] not in (3, 4):
+        raise ValueError("sutil::saveImage(): Unrecognized image buffer pixel format.")
+    path = str(path)
+    if len(path) < 5:
+        raise ValueError("sutil::saveImage(): Failed to determine filename extension")
+    ext = path[-3:].lower()
+    if a.dtype == np.uint8:
+        if a.shape[2] != 4:
+            raise ValueError("sutil::saveImage(): Unrecognized image buffer pixel format.")
+        pix = a
+    elif a.dtype == np.float32:
+        rgb = a[..., :3] if disable_srgb_conversion else None
+        q = np.clip((np.float32(256.0) * rgb).astype(np.int64), 0, 255).astype(np.uint8) if disable_srgb_conversion else _to_srgb_u8(a[..., :3])
+        pix = np.concatenate([q, np.full(q.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+    else:
+        raise ValueError("sutil::saveImage(): Unrecognized image buffer pixel format.")
+    pix = pix[::-1]  # flipped vertically as it is written
+    if ext == "ppm":
+        h, w = pix.shape[:2]
+        with open(path, "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (w, h))
+            f.write(np.ascontiguousarray(pix[..., :3]).tobytes())
+    elif ext == "png":
+        from PIL import Image
+        Image.fromarray(np.ascontiguousarray(pix if a.dtype == np.uint8 else pix[..., :3])).save(path)
+    else:
+        raise ValueError(f"sutil::saveImage(): Invalid extension '{ext}'")
+
+
+def load_obj_like_assimp(path, floor_material=26):
+    """imgui_test's load_assimp (SDK/imgui_test/triangle_gas.cpp:78-168) for a Wavefront OBJ: every face becomes three unindexed vertices
+    (faces with more corners are fanned, as assimp's triangulation of convex polygons does), per-vertex normals where the file has them,
+    material index 0, and the sample's floor — 20 x 20 cells of 0.1 at the lowest y of the model, two triangles each, normal (0, 1, 0),
+    material 26 — appended.  Returns (vertices (3T, 3) f32, normals (3T', 3) f32, mat_indices (T,) i32): what TriangleGAS keeps and
+    host.Playground takes."""
+    v, vn, verts, norms = [], [], [], []
+    with open(path) as f:
+        for line in f:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "v":
+                v.append([float(x) for x in t[1:4]])
+            elif t[0] == "vn":
+                vn.append([float(x) for x in t[1:4]])
+            elif t[0] == "f":
+                corners = []
+                for c in t[1:]:
+                    parts = c.split("/")
+                    vi = int(parts[0])
+                    ni = int(parts[2]) if len(parts) > 2 and parts[2] else None
+                    corners.append((vi - 1 if vi > 0 else len(v) + vi, None if ni is None else (ni - 1 if ni > 0 else len(vn) + ni)))
+                for k in range(1, len(corners) - 1):
+                    for vi, ni in (corners[0], corners[k], corners[k + 1]):
+                        verts.append(v[vi])
+                        if ni is not None:
+                            norms.append(vn[ni])
+    vertices = np.asarray(verts, np.float32).reshape(-1, 3)
+    normals = np.asarray(norms, np.float32).reshape(-1, 3)
+    mats = [0] * (vertices.shape[0] // 3)
+    floor = np.float32(vertices[:, 1].min()) if vertices.size else np.float32(1.0e12)
+    fv = []
+    for i in range(-10, 10):
+        for j in range(-10, 10):
+            x0, x1 = np.float32(i) * np.float32(0.1), np.float32(i + 1) * np.float32(0.1)
+            z0, z1 = np.float32(j) * np.float32(0.1), np.float32(j + 1) * np.float32(0.1)
+            fv += [[x0, floor, z0], [x0, floor, z1], [x1, floor, z0], [x1, floor, z0], [x0, floor, z1], [x1, floor, z1]]
+            mats += [floor_material, floor_material]
+    vertices = np.concatenate([vertices, np.asarray(fv, np.float32)], axis=0)
+    normals = np.concatenate([normals, np.tile(np.asarray([[0.0, 1.0, 0.0]], np.float32), (len(fv), 1))], axis=0)
+    return vertices, normals, np.asarray(mats, np.int32)
