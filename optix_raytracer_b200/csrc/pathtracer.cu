@@ -402,8 +402,11 @@ __global__ void __launch_bounds__(256) pt_resolve_kernel(const void* __restrict_
     finalize_index<MODE>(f, idx, px, py, r);
 }
 
+#ifndef B200RT_SHADE_MIN_CTAS
+#define B200RT_SHADE_MIN_CTAS 2
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256) pt_shade_kernel(const void* __restrict__ params, Lanes L, int cur, const char* __restrict__ hg_base,
+__global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(const void* __restrict__ params, Lanes L, int cur, const char* __restrict__ hg_base,
                                                         uint32_t hg_stride, uint32_t hg_count, const char* __restrict__ miss_base)
 {
     const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
