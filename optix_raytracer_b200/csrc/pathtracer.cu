@@ -20,6 +20,7 @@
 // sample) and its RNG stream order (2 jitter draws from the pixel seed; per bounce: 2 bounce, 2
 // light, 1 roulette draw from the path seed) are preserved exactly; with the arithmetic contract of
 // rt_math.cuh the accumulated radiance is bit-identical to the scalar oracle.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -267,6 +268,7 @@ struct PTWork {
     float weight;
     __device__ PTWork(const Frame& f_, const Lanes& L_, uint32_t n_ext_) : f(f_), L(L_), n_ext(n_ext_), lane(0), weight(0.f) {}
 
+    __device__ __forceinline__ bool stream_triangles() const { return f.handle->kind == ACCEL_KIND_GAS && f.handle->node_bytes == NODE8_BYTES; }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
         bool ext;
@@ -782,6 +784,15 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     B2_LAUNCH_CHECK(ctx);
     Counters* h_cnt = (Counters*)((char*)ctx->pinned + 256);
     // persistent trace kernel: as many CTAs as fit on the device (occupancy query), never more than the work needs
+    {
+        // L1 and shared memory share 256 KB per SM.  The trace kernel needs 8 x 7.7 KB of shared memory; left to itself the driver carved
+        // out 135 KB (ncu: launch__shared_mem_config_size), i.e. took ~70 KB of L1 away from the BVH nodes.
+        static const int carveout = [] { const char* e = getenv("B200RT_TRACE_CARVEOUT"); return e ? atoi(e) : 28; }();
+        if (carveout >= 0) {
+            cudaFuncSetAttribute(pt_trace_kernel<MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+            cudaFuncSetAttribute(pt_trace_kernel<MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        }
+    }
     int occ = 0, occ_stats = 0;
     B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pt_trace_kernel<MODE, false>, COOP_BLOCK, 0));
     B2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stats, pt_trace_kernel<MODE, true>, COOP_BLOCK, 0));

@@ -99,6 +99,7 @@ struct RayWork {
         return run_anyhit(ah, prim, sbt, inst_sbt, (pack & TP_ANY) != 0u, b1, b2, factor);
     }
     __device__ __forceinline__ void attenuate(float factor) { att *= (double)factor; }
+    __device__ __forceinline__ bool stream_triangles() const { return false; }
     __device__ __forceinline__ bool anyhit_enabled() const { return ah.mode != AH_NONE && handle->anyhit != 0u; }
     __device__ __forceinline__ bool fetch(uint32_t i, Trav& s, float* my_ray)
     {

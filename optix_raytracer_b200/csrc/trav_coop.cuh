@@ -29,6 +29,10 @@ namespace b200rt {
 #ifndef B200RT_LOOKTHROUGH
 #define B200RT_LOOKTHROUGH 0
 #endif
+// Triangle records of a scene that lives in HBM are read once per ray and not again soon, while nodes (the upper levels at least) are
+// read again and again: such launches load triangles with the streaming (evict-first) policy so they do not push nodes out of L1 / L2
+// (measured on the 50 M-triangle bench: 2033 -> 2045 Mrays/s).  Cache-resident scenes keep the default policy.
+#define TRI_LOAD(p) (tri_stream ? __ldcs(p) : __ldg(p))
 constexpr uint32_t NODE_BITS = 0xff000000u;
 #ifndef B200RT_REFILL_THRESHOLD
 #define B200RT_REFILL_THRESHOLD 24
@@ -328,6 +332,7 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 //                                                                  return true; false = the item is finished.  An any-hit ray that found
 //                                                                  its hit ends here too (any_ray_done)
 //   __device__ void  commit(const Trav& s, bool found)             store the result of the finished item
+//   __device__ bool  stream_triangles()                            uniform over the launch: true = triangle records are not worth caching
 //   static constexpr bool CONTINUES                                true: instead of commit, the finished lanes call
 //   __device__ bool  commit_continue(Trav& s, float* my_ray, found) together; it may start another ray of the same item (true) — the place
 //                                                                  for work that should run with many lanes at once (shading, whitted.cu)
@@ -342,6 +347,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
 {
     __shared__ CoopShared sh;
     __shared__ CoopSharedAnyHit<Work::ANYHIT> sha;
+    const bool tri_stream = work.stream_triangles();  // uniform over the launch
     bool ah_on = false;  // uniform: the launch has any-hit programs AND the traversable holds geometry that runs them
     if constexpr (Work::ANYHIT) ah_on = work.anyhit_enabled();
     constexpr unsigned FULL = 0xffffffffu;
@@ -481,7 +487,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                     }
                     if (valid) {
                         const float4* tp = (const float4*)(uintptr_t)tris_base + (size_t)sh.unit_tri[wid][lane] * 3u;
-                        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                        const float4 q0 = TRI_LOAD(tp), q1 = TRI_LOAD(tp + 1), q2 = TRI_LOAD(tp + 2);
                         if (st) st->tris++;
                         uhit = tri_unit(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
                         uord = __float_as_uint(q2.w); uprim = __float_as_uint(q0.w); usbt = __float_as_uint(q1.w);

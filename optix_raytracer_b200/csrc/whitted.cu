@@ -305,6 +305,7 @@ struct WPrimaryWork {
         return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), false, b1, b2, factor);
     }
     __device__ __forceinline__ void attenuate(float) {}
+    __device__ __forceinline__ bool stream_triangles() const { return false; }
     __device__ __forceinline__ void ray(float3& o, float3& d, float& tmin) const
     {
         const WParams& P = *k.params;
@@ -514,6 +515,7 @@ struct WShadowWork {
         return run_anyhit(AnyHitCfg{k.hg_base, k.hg_stride, k.hg_count, AH_WHITTED}, prim, sbt, w_inst_sbt(handle, inst), true, b1, b2, factor);
     }
     __device__ __forceinline__ void attenuate(float f) { att *= (double)f; }
+    __device__ __forceinline__ bool stream_triangles() const { return false; }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
         slot = k.level_start + item / per_slot;

@@ -1,2 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "cornell_pathtracer" > /tmp/o.txt 2>&1; echo "rc=$?"; tail -5 /tmp/o.txt | cut -c1-300
-for rs in 0 1; do timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --ray-sort $rs > gpurun_out/rs_$rs.json 2> gpurun_out/rs_$rs.err; done
+for c in -1 28 35 50 100; do
+  echo -n "carveout $c synth: "; B200RT_TRACE_CARVEOUT=$c timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],1), round(d['ms_per_step'],2))"
+  echo -n "carveout $c cornell: "; B200RT_TRACE_CARVEOUT=$c timeout 300 python bench.py --workload cornell --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],1), round(d['ms_per_step'],2))"
+done
