@@ -6,7 +6,7 @@ built by `optixAccelBuild` and the launch is `optixLaunch` of the REFERENCE'S OW
 (oracle/_ref/*.ptx, compiled by oracle/Makefile from /root/reference/SDK/optix*/...cu where they lie) on
 the closed runtime `libnvoptix.so.1`, through the harness oracle/optix_ref/optix_harness.cpp.
 
-Only tests/ and bench.py (--impl optix, an extra measurement arm) import this.  libnvoptix.so.1 is present
+Only tests/ and tools/optix_compare.py (the same-GPU comparison report) import this.  libnvoptix.so.1 is present
 on the GPU box only (probed: SURVEY.md section 8c / DESIGN.md section 6); `available()` says whether it
 can be used in this process.
 """
