@@ -393,6 +393,86 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4b. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) — the quality alternative to the Karras tree: bottom-up
+// agglomeration of the Morton-ordered leaves.  Every cluster looks PLOC_RADIUS positions to either side for the neighbour with which
+// it would form the smallest box; mutual nearest neighbours merge into a new internal node; the cluster array is compacted; repeat
+// until one cluster is left.  Prefix sums place both the survivors and the new nodes, so the tree is deterministic.  Boxes and leaf
+// counts are final when a node is created (no refit pass).  Internal ids are handed out in creation order: the root is the last one.
+// ---------------------------------------------------------------------------------------------
+#ifndef B200RT_PLOC_RADIUS
+#define B200RT_PLOC_RADIUS 16
+#endif
+constexpr int PLOC_RADIUS = B200RT_PLOC_RADIUS, PLOC_THREADS = 256;
+
+__global__ void __launch_bounds__(PLOC_THREADS) ploc_nearest_kernel(const uint32_t* __restrict__ clusters, uint32_t n, const float4* __restrict__ box_lo,
+                                                                     const float4* __restrict__ box_hi, uint32_t* __restrict__ nearest)
+{
+    __shared__ float4 slo[PLOC_THREADS + 2 * PLOC_RADIUS], shi[PLOC_THREADS + 2 * PLOC_RADIUS];
+    const int base = (int)(blockIdx.x * PLOC_THREADS) - PLOC_RADIUS;
+    for (int k = threadIdx.x; k < PLOC_THREADS + 2 * PLOC_RADIUS; k += PLOC_THREADS) {
+        const int g = base + k;
+        if (g >= 0 && g < (int)n) { const uint32_t id = clusters[g]; slo[k] = box_lo[id]; shi[k] = box_hi[id]; }
+    }
+    __syncthreads();
+    const int i = (int)(blockIdx.x * PLOC_THREADS + threadIdx.x);
+    if (i >= (int)n) return;
+    const int me = threadIdx.x + PLOC_RADIUS;
+    const float4 alo = slo[me], ahi = shi[me];
+    float best = INFINITY;
+    int bj = -1;
+    for (int d = -PLOC_RADIUS; d <= PLOC_RADIUS; ++d) {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= (int)n) continue;
+        const float4 blo = slo[me + d], bhi = shi[me + d];
+        const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+        const float a = dx * dy + dy * dz + dz * dx;
+        if (a < best) { best = a; bj = j; }  // ties: the lower position (scan order), so (i, j) and (j, i) agree on equal areas
+    }
+    nearest[i] = (uint32_t)bj;
+}
+
+// flags: high word = this position survives into the next round, low word = it creates a node
+__global__ void __launch_bounds__(256) ploc_flag_kernel(const uint32_t* __restrict__ nearest, uint32_t n, unsigned long long* __restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = nearest[i];
+    const bool mutual = j < n && nearest[j] == i;
+    const bool leader = mutual && i < j;
+    flags[i] = ((unsigned long long)((!mutual || leader) ? 1u : 0u) << 32) | (leader ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256) ploc_merge_kernel(const uint32_t* __restrict__ clusters, const uint32_t* __restrict__ nearest, uint32_t n,
+                                                          const unsigned long long* __restrict__ excl, uint32_t node_base, int ninternal,
+                                                          float4* __restrict__ box_lo, float4* __restrict__ box_hi, int2* __restrict__ range,
+                                                          uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = nearest[i];
+    const bool mutual = j < n && nearest[j] == i;
+    if (mutual && i > j) return;  // absorbed by its partner
+    const unsigned long long e = excl[i];
+    const uint32_t pos = (uint32_t)(e >> 32);
+    if (!mutual) { out[pos] = clusters[i]; return; }
+    const uint32_t id = node_base + (uint32_t)(e & 0xffffffffu);
+    const uint32_t a = clusters[i], b = clusters[j];
+    const float4 alo = box_lo[a], ahi = box_hi[a], blo = box_lo[b], bhi = box_hi[b];
+    const int ca = (int)a < ninternal ? range[a].y : 1, cb = (int)b < ninternal ? range[b].y : 1;
+    box_lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float((int)a));
+    box_hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), __int_as_float((int)b));
+    range[id] = make_int2(-1, ca + cb);  // x: leaves of a PLOC node are not a range of sorted positions (collapse walks small subtrees)
+    out[pos] = id;
+}
+
+__global__ void ploc_init_kernel(uint32_t* clusters, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) clusters[i] = n - 1u + i;  // leaf ids in Morton order
+}
+__global__ void read_root_kernel(const uint32_t* clusters, uint32_t* work) { work[0] = clusters[0]; }
+
+// ---------------------------------------------------------------------------------------------
 // 5. refit
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_boxes_kernel(const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
@@ -614,7 +694,19 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
         } else {
             const uint32_t unary = count == 1 ? 1u : (count == 2 ? 3u : 7u);
             meta[s] = (unary << 5) | tri_off;
-            for (int j = 0; j < count; ++j) dest[first + j] = tri_base + tri_off + (uint32_t)j;
+            if (first >= 0) {
+                for (int j = 0; j < count; ++j) dest[first + j] = tri_base + tri_off + (uint32_t)j;
+            } else {
+                // PLOC subtree of 2 or 3 leaves: its leaves are not consecutive sorted positions, walk it (left to right)
+                int stack2[4] = {id, -1, -1, -1};
+                int sp2 = 1, j = 0;
+                while (sp2 > 0) {
+                    const int nd = stack2[--sp2];
+                    if (nd >= ninternal) { dest[nd - ninternal] = tri_base + tri_off + (uint32_t)j; ++j; continue; }
+                    stack2[sp2++] = __float_as_int(box_hi[nd].w);
+                    stack2[sp2++] = __float_as_int(box_lo[nd].w);
+                }
+            }
             tri_off += (uint32_t)count;
         }
     }
@@ -741,6 +833,21 @@ static uint32_t choose_node_bytes(uint64_t ntris)
     return ntris <= 600000ull ? NODE8F_BYTES : NODE8_BYTES;
 }
 
+// Which binary hierarchy the 8-wide collapse starts from.  PLOC costs a few dozen clustering rounds (each with a host read-back of the
+// cluster count) and pays where Morton order is a poor guide — few, large or unevenly sized triangles: measured (profiles/
+// r01_hierarchy.md) Cornell 7.95 -> 7.29 ms per launch, the imgui_test scene (1.74 M triangles) 20.9 -> 17.0 ms per frame.  On the
+// regularly tessellated 50 M-triangle bench scene the Karras tree over 63-bit Morton codes is already the better one (15.6 vs 16.8
+// node visits per ray) and twice as fast to build, so big inputs keep it.  B200RT_HIERARCHY=ploc|lbvh overrides (A/B runs, tests).
+constexpr uint32_t PLOC_MAX_TRIANGLES = 1u << 23;
+static bool use_ploc(const b200rt_accel_build_options* options, uint32_t ntris)
+{
+    const char* e = getenv("B200RT_HIERARCHY");  // read per build: tests switch it
+    if (e && !strcmp(e, "ploc")) return true;
+    if (e && !strcmp(e, "lbvh")) return false;
+    (void)options;
+    return ntris <= PLOC_MAX_TRIANGLES;
+}
+
 static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsigned num_inputs, BuildPlan& p)
 {
     uint64_t n = 0, sbt = 0;
@@ -783,7 +890,8 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.off_arrive = take(4 * N);
     p.off_dest = take(4 * N);
     p.off_hist = take(4 * 256 * (size_t)p.rs_blocks);
-    const size_t scan_elems = std::max(scan_temp_elems<uint32_t>(256 * (size_t)p.rs_blocks), scan_temp_elems<unsigned long long>(W));
+    const size_t scan_elems = std::max(std::max(scan_temp_elems<uint32_t>(256 * (size_t)p.rs_blocks), scan_temp_elems<unsigned long long>(W)),
+                                       scan_temp_elems<unsigned long long>(N));  // PLOC scans one word per cluster
     p.off_scan_tmp = take(8 * scan_elems);
     p.off_work0 = take(4 * W);
     p.off_work1 = take(4 * W);
@@ -940,17 +1048,57 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             }
             leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
             B2_LAUNCH_CHECK(ctx);
-            if (N > 1) {
-                karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
+            const bool ploc = use_ploc(options, N);
+            if (N > 1 && ploc) {
+                // the sort's key buffers are free now: cluster ping-pong in one, the scan words in the other
+                uint32_t* cl[2] = {(uint32_t*)keys[cur], (uint32_t*)keys[cur] + N};
+                unsigned long long* flags = (unsigned long long*)keys[cur ^ 1];
+                uint32_t* nearest = arrive;
+                unsigned long long* h_tot = (unsigned long long*)((char*)ctx->pinned + 64);
+                ploc_init_kernel<<<div_up(N, 256), 256, 0, s>>>(cl[0], N);
                 B2_LAUNCH_CHECK(ctx);
-                B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
-                refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive);
+                uint32_t n = N, node_base = 0;
+                int cc = 0;
+                for (int round = 0; n > 1; ++round) {
+                    B2_REQUIRE(ctx, round < 4096, "accel build: clustering does not converge (internal error)");
+                    ploc_nearest_kernel<<<div_up(n, PLOC_THREADS), PLOC_THREADS, 0, s>>>(cl[cc], n, box_lo, box_hi, nearest);
+                    B2_LAUNCH_CHECK(ctx);
+                    ploc_flag_kernel<<<div_up(n, 256), 256, 0, s>>>(nearest, n, flags);
+                    B2_LAUNCH_CHECK(ctx);
+                    save_last_kernel<<<1, 1, 0, s>>>(n, flags, last);
+                    B2_LAUNCH_CHECK(ctx);
+                    rc = exclusive_scan<unsigned long long>(ctx, flags, n, (unsigned long long*)scan_tmp, s);
+                    if (rc) return rc;
+                    ploc_merge_kernel<<<div_up(n, 256), 256, 0, s>>>(cl[cc], nearest, n, flags, node_base, (int)N - 1, box_lo, box_hi, range, cl[cc ^ 1]);
+                    B2_LAUNCH_CHECK(ctx);
+                    // totals = exclusive value of the last position + its own flags
+                    B2_CUDA(ctx, cudaMemcpyAsync(h_tot, flags + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+                    B2_CUDA(ctx, cudaMemcpyAsync(h_tot + 1, last, 8, cudaMemcpyDeviceToHost, s));
+                    B2_CUDA(ctx, cudaStreamSynchronize(s));
+                    const unsigned long long tot = h_tot[0] + h_tot[1];
+                    const uint32_t survivors = (uint32_t)(tot >> 32), created = (uint32_t)(tot & 0xffffffffu);
+                    B2_REQUIRE(ctx, created > 0 && survivors == n - created, "accel build: clustering made no progress (internal error)");
+                    node_base += created;
+                    n = survivors;
+                    cc ^= 1;
+                }
+                B2_REQUIRE(ctx, node_base == N - 1, "accel build: clustering node count mismatch (internal error)");
+                B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
+                read_root_kernel<<<1, 1, 0, s>>>(cl[cc], work[0]);
+                B2_LAUNCH_CHECK(ctx);
+            } else {
+                if (N > 1) {
+                    karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
+                    B2_LAUNCH_CHECK(ctx);
+                    B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
+                    refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive);
+                    B2_LAUNCH_CHECK(ctx);
+                }
+                B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
+                set_root_work_kernel<<<1, 1, 0, s>>>(work[0], 0u);  // internal node 0, or leaf id 0 when N == 1
                 B2_LAUNCH_CHECK(ctx);
             }
             // ---- collapse, level by level
-            B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
-            set_root_work_kernel<<<1, 1, 0, s>>>(work[0], 0u);  // internal node 0, or leaf id 0 when N == 1
-            B2_LAUNCH_CHECK(ctx);
             uint32_t nwork = 1, level_start = 0, tri_cursor = 0;
             int wcur = 0;
             LevelInfo* h_level = (LevelInfo*)ctx->pinned;

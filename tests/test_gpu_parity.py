@@ -124,11 +124,13 @@ def test_duck_raycast_bit_exact(ctx, orc):
         assert np.array_equal(img.view(np.uint32), orc.raycast_shade(ref_hits).view(np.uint32))
 
 
-@pytest.mark.parametrize("node_format", ["q8", "f32"])
-def test_triangle_soup_bvh_vs_oracle(ctx, orc, node_format, monkeypatch):
-    """A random soup big enough for a multi-level wide BVH, including degenerate and duplicate triangles; both node encodings."""
+@pytest.mark.parametrize("node_format,hierarchy", [("q8", "lbvh"), ("f32", "lbvh"), ("q8", "ploc"), ("f32", "ploc")])
+def test_triangle_soup_bvh_vs_oracle(ctx, orc, node_format, hierarchy, monkeypatch):
+    """A random soup big enough for a multi-level wide BVH, including degenerate and duplicate triangles; both node encodings and both
+    binary hierarchies the collapse can start from (Karras tree over Morton codes, PLOC clustering: bvh_build.cu)."""
     from optix_raytracer_b200 import host
     monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
+    monkeypatch.setenv("B200RT_HIERARCHY", hierarchy)
     rng = np.random.default_rng(7)
     n = 30_000
     c = rng.random((n, 1, 3), dtype=np.float32) * 10
@@ -179,11 +181,13 @@ def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc, node_forma
     assert np.array_equal(img.view(np.uint32), ref_accum.view(np.uint32))
 
 
-@pytest.mark.parametrize("node_format", ["q8", "f32"])
-def test_bvh_invariants_and_compaction(ctx, node_format, monkeypatch):
-    """Both node encodings (accel.h): Node8 with 8-bit boxes and Node8F with fp32 boxes (forced through B200RT_NODE_FORMAT)."""
+@pytest.mark.parametrize("node_format,hierarchy", [("q8", "lbvh"), ("f32", "lbvh"), ("q8", "ploc"), ("f32", "ploc")])
+def test_bvh_invariants_and_compaction(ctx, node_format, hierarchy, monkeypatch):
+    """Both node encodings (accel.h): Node8 with 8-bit boxes and Node8F with fp32 boxes (forced through B200RT_NODE_FORMAT), from both
+    binary hierarchies (B200RT_HIERARCHY); builds are deterministic (compacted == uncompacted node for node)."""
     from optix_raytracer_b200 import host
     monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
+    monkeypatch.setenv("B200RT_HIERARCHY", hierarchy)
     rng = np.random.default_rng(3)
     for n in (1, 2, 3, 4, 5, 33, 1000):
         tris = (rng.random((n, 3, 3), dtype=np.float32) * 4).astype(np.float32)
