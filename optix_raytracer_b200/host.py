@@ -197,15 +197,16 @@ class Context:
         return bi
 
     def instance_input(self, instances):
-        """instances: list of (transform12, sbt_offset, Accel).  SDK/sutil/Scene.cpp:1134-1212."""
+        """instances: list of (transform12, sbt_offset, Accel[, visibility_mask]).  SDK/sutil/Scene.cpp:1134-1212."""
         n = len(instances)
         arr = (L.Instance * n)()
         keep = []
-        for i, (xf, sbt_off, acc) in enumerate(instances):
+        for i, inst in enumerate(instances):
+            xf, sbt_off, acc = inst[:3]
             arr[i].transform = (C.c_float * 12)(*[float(x) for x in np.asarray(xf, np.float32).reshape(12)])
             arr[i].instanceId = i
             arr[i].sbtOffset = sbt_off
-            arr[i].visibilityMask = 1
+            arr[i].visibilityMask = inst[3] if len(inst) > 3 else 1
             arr[i].flags = 0
             arr[i].traversableHandle = acc.handle
             keep.append(acc)

@@ -148,6 +148,36 @@ def test_triangle_soup_bvh_vs_oracle(ctx, orc, node_format, hierarchy, monkeypat
     _assert_hits_equal(got, ref, "soup")
 
 
+def test_multi_instance_ias_vs_oracle(ctx, orc):
+    """One GAS instanced five times (rotated, scaled, overlapping) plus an instance whose visibility mask is 0: hit records (t, primitive,
+    instance, barycentrics) and occlusion flags are those of the oracle — closest over instances = min (t, instance index, ordinal); the
+    bounds test that drops a ray at an instance it passes by (trav_begin<BOUNDS>) must not change anything."""
+    from optix_raytracer_b200 import host
+    rng = np.random.default_rng(17)
+    n = 3000
+    c = rng.random((n, 1, 3), dtype=np.float32) * 2 - 1
+    tris = (c + (rng.random((n, 3, 3), dtype=np.float32) - 0.5) * 0.15).astype(np.float32)
+    gas = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
+
+    def xf(angle, scale, t):
+        ca, sa = np.cos(angle), np.sin(angle)
+        m = np.array([[ca * scale, 0, sa * scale, t[0]], [0, scale * 0.8, 0, t[1]], [-sa * scale, 0, ca * scale, t[2]]], np.float32)
+        return m.reshape(12)
+    xfs = [xf(0.0, 1.0, (0, 0, 0)), xf(0.7, 0.5, (1.5, 0.2, 0)), xf(-1.1, 1.3, (-1, -0.5, 2)), xf(2.0, 0.9, (0.5, 0.5, 0.5)), xf(0.3, 2.0, (0, 3, 0))]
+    inst = [(m, 0, gas) for m in xfs] + [(xf(0.1, 5.0, (0, 0, 0)), 0, gas, 0)]   # the last one is invisible (mask 0)
+    ias = ctx.build_accel([ctx.instance_input(inst)], compact=False)
+    assert ias.info().num_instances == 6
+    scene = orc.Scene(tris, None, instances=xfs)
+    rays = common.random_rays(rng, 200_000, [-4, -3, -4], [4, 6, 5])
+    got = host.ext_hits_to_numpy(ctx.trace_closest(ias, ctx.to_device(rays)))
+    ref = scene.trace(rays)
+    assert (ref["t"] >= 0).mean() > 0.1 and len(np.unique(ref["inst"][ref["t"] >= 0])) == 5
+    _assert_hits_equal(got, ref, "multi-instance")
+    rays[:, 7] = rng.random(rays.shape[0], dtype=np.float32) * 6
+    occ = ctx.trace_any(ias, ctx.to_device(rays)).cpu().numpy().astype(bool)
+    assert np.array_equal(occ, scene.trace(rays, any_hit=True)["occluded"])
+
+
 @pytest.mark.parametrize("node_format", ["q8", "f32"])
 def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc, node_format, monkeypatch):
     """The procedural scene of BASELINE.json configs[4]: device generator == oracle restatement bit for bit,
