@@ -167,7 +167,8 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
         if (!(ir->mask & 1u)) continue;
         s.inst = k;
         const uint32_t c = (ir->flags & 1u) ? 0u : cull;  // OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING
-        if (trav_begin<BOUNDS>(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c)) return true;
+        // instances are tested at their bounds always: with several of them a ray passes most of them by
+        if (trav_begin<true>(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c)) return true;
     }
     s.pack = keep;  // nothing (more) to traverse: the flags carried so far are what commit sees
     return false;

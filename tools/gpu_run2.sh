@@ -1,1 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "multi_instance" > /tmp/o.txt 2>&1; echo "pytest rc=$?"; tail -15 /tmp/o.txt | cut -c1-400
+timeout 600 python -m pytest tests -x -q -m gpu > /tmp/o.txt 2>&1; echo "pytest rc=$?"; tail -5 /tmp/o.txt | cut -c1-400
+timeout 200 python tools/time_small.py 2>&1 | tail -1
