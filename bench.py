@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--spl", type=int, default=16)
     ap.add_argument("--sample-groups", type=int, default=None, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
     ap.add_argument("--ray-sort", type=int, default=None, help="b200rt_pt_options.ray_sort (default: 1 for the synthetic workload, 0 for cornell)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+                    help="N > 1: how the frame is assembled — p2p: every rank's launch stores its pixels into rank 0's result buffer over NVLink "
+                         "(the reference's single result buffer, optixMultiGPU.cpp:479-508); allgather: per-rank sample buffers all-gathered (NCCL) "
+                         "and de-interleaved on every rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -214,10 +218,30 @@ def run_b200rt(a, rank, world, local_rank):
         flush = torch.empty(int(l2_bytes * 1.5) // 4, dtype=torch.float32, device=dev)
 
     n_local = pt.num_samples if multigpu else a.width * a.height
+    exchange, shared = "none", None
     if world > 1:
-        gathered = torch.empty((world, n_local, 4), dtype=torch.float32, device=dev)
-        full_accum = torch.empty((a.height, a.width, 4), dtype=torch.float32, device=dev)
-        full_frame = torch.empty((a.height, a.width, 4), dtype=torch.uint8, device=dev)
+        exchange = a.exchange
+        if exchange == "p2p":
+            # one result buffer in rank 0's HBM, written by every rank's launch over NVLink; if any rank cannot map it (no peer path), all
+            # ranks fall back to the gather together
+            ok = 1
+            try:
+                shared = host.SharedResultBuffer(ctx, a.height, a.width, rank)
+            except Exception as e:  # noqa: BLE001
+                ok = 0
+                print(f"[rank {rank}] shared result buffer unavailable ({e}); falling back to all-gather", file=sys.stderr)
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                if shared is not None:
+                    shared.close()
+                shared, exchange = None, "allgather"
+            else:
+                pt.params.result_buffer = shared.ptr
+        if exchange == "allgather":
+            gathered = torch.empty((world, n_local, 4), dtype=torch.float32, device=dev)
+            full_accum = torch.empty((a.height, a.width, 4), dtype=torch.float32, device=dev)
+            full_frame = torch.empty((a.height, a.width, 4), dtype=torch.uint8, device=dev)
     h_frame = torch.empty((a.height, a.width, 4), dtype=torch.uint8).pin_memory()
     stats_mask = L.PT_STATS_SEGMENTS
 
@@ -225,11 +249,17 @@ def run_b200rt(a, rank, world, local_rank):
         pt.launch_subframe(sub, collect_stats=mask)
         segs = pt.stats.radiance_segments + pt.stats.shadow_segments
         frame = pt.frame
-        if world > 1:
+        if exchange == "allgather":
             dist.all_gather_into_tensor(gathered.view(-1), pt.accum.view(-1))
             ctx.check(ctx.lib.b200rt_deinterleave(ctx.h, ctx.stream, gathered.data_ptr(), world, n_local, a.width, a.height,
                                                   full_accum.data_ptr(), full_frame.data_ptr()), "deinterleave")
             frame = full_frame
+        elif exchange == "p2p":
+            frame = shared.tensor  # rank 0 only
+            if want_host_frame:
+                # the frame is complete when every rank's launch has finished: one barrier, then rank 0 reads it
+                torch.cuda.synchronize()
+                dist.barrier()
         if want_host_frame and rank == 0:
             h_frame.copy_(frame, non_blocking=True)
         return segs
@@ -261,7 +291,7 @@ def run_b200rt(a, rank, world, local_rank):
         t_ms += s0.elapsed_time(s1)
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
-    launches = ctx.kernel_launches - launches0 + (a.steps if world > 1 else 0)
+    launches = ctx.kernel_launches - launches0 + (a.steps if exchange == "allgather" else 0)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: same steps through the public call with host buffers (Params H2D from pinned memory is part of
@@ -339,7 +369,9 @@ def run_b200rt(a, rank, world, local_rank):
                "data": "synthetic",
                "config": {"workload": workload_name(a), "triangles": int(info.num_triangles), "bvh8_nodes": int(info.num_nodes), "bvh8_node_bytes": int(info.reserved) or 80,
                           "accel_bytes": scene_bytes, "width": a.width, "height": a.height, "samples_per_launch": a.spl, "sample_groups": a.sample_groups, "ray_sort": a.ray_sort,
-                          "parallelism": f"image split x{world} (StaticWorkDistribution 8x4 tiles), scene replicated" + (", ncclAllGather" if world > 1 else ""),
+                          "parallelism": f"image split x{world} (StaticWorkDistribution 8x4 tiles), scene replicated"
+                                         + {"none": "", "allgather": ", ncclAllGather of the sample buffers + de-interleave",
+                                            "p2p": ", one result buffer in rank 0's HBM written by every rank's launch over NVLink (no collective)"}[exchange],
                           "l2": ("inputs larger than L2: accel %.2f GB vs L2 %.0f MB" % (scene_bytes / 1e9, l2_bytes / 1e6)) if flush is None
                                 else "L2 flushed between timed steps (1.5x L2 fill)",
                           "bvh_build_ms": build_ms, "segments_per_step": segs_total / a.steps},

@@ -164,6 +164,19 @@ const char* b200rt_error_name(int code);       /* optixGetErrorName */
 const char* b200rt_last_error_message(b200rt_context ctx); /* detail text of the last failure on this context */
 const char* b200rt_version(void);
 uint64_t b200rt_context_kernel_launches(b200rt_context ctx); /* kernels launched so far through this context */
+/* enablePeerAccess of the reference's optixNVLink (SDK/optixNVLink/optixNVLink.cpp:1617-1635): lets launches of this context store into
+ * memory of `peer_device` — one result buffer for all GPUs (Params::result_buffer of optixMultiGPU pointing into another GPU's HBM, the
+ * pixels travel over NVLink).  B200RT_ERROR_NOT_SUPPORTED when the two GPUs have no peer path. */
+int b200rt_enable_peer_access(b200rt_context ctx, int peer_device);
+/* One result buffer for several processes (one process per GPU): the owner creates it in its HBM (zero-filled) and hands the 64-byte
+ * handle (a cudaIpcMemHandle_t) to the others, which open it with THEIR context: the pointer they get may be used as
+ * Params::result_buffer of their launches, whose stores then go to the owner's memory over NVLink.  The reference's counterpart is the
+ * single result buffer all devices of optixMultiGPU write (zero-copy: SDK/sutil/CUDAOutputBuffer.h:203-216; peer memory:
+ * SDK/optixNVLink/optixNVLink.cpp:1975-1992) — there inside one process. */
+int b200rt_shared_buffer_create(b200rt_context ctx, size_t bytes, b200rt_deviceptr* ptr, unsigned char handle64[64]);
+int b200rt_shared_buffer_open(b200rt_context ctx, const unsigned char handle64[64], b200rt_deviceptr* ptr);
+int b200rt_shared_buffer_close(b200rt_context ctx, b200rt_deviceptr ptr);    /* pointer from _open */
+int b200rt_shared_buffer_destroy(b200rt_context ctx, b200rt_deviceptr ptr);  /* pointer from _create */
 
 /* ---------------------------------------------------------------------------------------------
  * Acceleration structures.  Replace optixAccelComputeMemoryUsage / optixAccelBuild /

@@ -109,6 +109,11 @@ SYMBOLS = {
     "b200rt_last_error_message": (C.c_char_p, [vp]),
     "b200rt_version": (C.c_char_p, []),
     "b200rt_context_kernel_launches": (u64, [vp]),
+    "b200rt_enable_peer_access": (i32, [vp, i32]),
+    "b200rt_shared_buffer_create": (i32, [vp, C.c_size_t, C.POINTER(u64), C.c_char_p]),
+    "b200rt_shared_buffer_open": (i32, [vp, C.c_char_p, C.POINTER(u64)]),
+    "b200rt_shared_buffer_close": (i32, [vp, u64]),
+    "b200rt_shared_buffer_destroy": (i32, [vp, u64]),
     "b200rt_accel_compute_memory_usage": (i32, [vp, C.POINTER(AccelBuildOptions), C.POINTER(BuildInput), u32,
                                                 C.POINTER(AccelBufferSizes)]),
     "b200rt_accel_build": (i32, [vp, vp, C.POINTER(AccelBuildOptions), C.POINTER(BuildInput), u32, u64, sz, u64, sz,

@@ -156,6 +156,66 @@ int b200rt_context_destroy(b200rt_context ctx)
 
 uint64_t b200rt_context_kernel_launches(b200rt_context ctx) { return ctx ? ctx->launches : 0; }
 
+int b200rt_shared_buffer_create(b200rt_context ctx, size_t bytes, b200rt_deviceptr* ptr, unsigned char* handle64)
+{
+    CTX_CHECK(ctx);
+    B2_REQUIRE(ctx, bytes && ptr && handle64, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    DeviceGuard guard(ctx->device);
+    void* p = nullptr;
+    B2_CUDA(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "shared buffer: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *ptr = (b200rt_deviceptr)p;
+    return B200RT_SUCCESS;
+}
+
+int b200rt_shared_buffer_open(b200rt_context ctx, const unsigned char* handle64, b200rt_deviceptr* ptr)
+{
+    CTX_CHECK(ctx);
+    B2_REQUIRE(ctx, handle64 && ptr, "bad argument");
+    DeviceGuard guard(ctx->device);  // opened by the device whose launches will store through it: peer access is set up for this pair
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    B2_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = (b200rt_deviceptr)p;
+    return B200RT_SUCCESS;
+}
+
+int b200rt_shared_buffer_close(b200rt_context ctx, b200rt_deviceptr ptr)
+{
+    CTX_CHECK(ctx);
+    DeviceGuard guard(ctx->device);
+    if (ptr) B2_CUDA(ctx, cudaIpcCloseMemHandle((void*)ptr));
+    return B200RT_SUCCESS;
+}
+
+int b200rt_shared_buffer_destroy(b200rt_context ctx, b200rt_deviceptr ptr)
+{
+    CTX_CHECK(ctx);
+    DeviceGuard guard(ctx->device);
+    if (ptr) B2_CUDA(ctx, cudaFree((void*)ptr));
+    return B200RT_SUCCESS;
+}
+
+int b200rt_enable_peer_access(b200rt_context ctx, int peer_device)
+{
+    CTX_CHECK(ctx);
+    if (peer_device == ctx->device) return B200RT_SUCCESS;
+    DeviceGuard guard(ctx->device);
+    int can = 0;
+    B2_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) return set_error(ctx, B200RT_ERROR_NOT_SUPPORTED, "GPU %d has no peer access to GPU %d", ctx->device, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return B200RT_SUCCESS; }
+    if (e != cudaSuccess) return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    return B200RT_SUCCESS;
+}
+
 int b200rt_accel_compute_memory_usage(b200rt_context ctx, const b200rt_accel_build_options* options, const b200rt_build_input* inputs,
                                       unsigned int num_inputs, b200rt_accel_buffer_sizes* sizes)
 {

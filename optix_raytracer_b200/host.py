@@ -914,6 +914,47 @@ class MeshViewer:
             hc.lib.b200rt_texture_destroy(hc.h, tex, arr)
         self._tex_handles = []
 
+# ---- one result buffer for all GPUs (optixMultiGPU / optixNVLink) ------------------------------------------------------------------------
+u64_t = C.c_uint64
+
+
+class SharedResultBuffer:
+    """The reference's optixMultiGPU lets every device write its pixels into ONE result buffer (zero-copy host memory,
+    SDK/sutil/CUDAOutputBuffer.h:203-216; device memory reached by peer access in optixNVLink.cpp:1975-1992).  With one process per GPU the
+    buffer lives in the owner rank's HBM (b200rt_shared_buffer_create), its 64-byte handle goes to the other ranks through
+    torch.distributed, and they open it with their own context: `ptr` is what each rank puts into Params::result_buffer, and the final
+    stores of its launch travel over NVLink — no gather, 4 bytes per pixel.  `tensor` (owner only) views the buffer as (h, w, 4) uint8.
+    Collective: construct on every rank."""
+
+    def __init__(self, ctx, height, width, rank, owner=0):
+        import torch.distributed as dist
+        self.ctx, self.owner, self.rank, self.shape = ctx, owner, rank, (height, width, 4)
+        ptr, payload, err = u64_t(), [None], None
+        if rank == owner:
+            handle = C.create_string_buffer(64)
+            try:
+                ctx.check(ctx.lib.b200rt_shared_buffer_create(ctx.h, height * width * 4, C.byref(ptr), handle), "shared_buffer_create")
+                payload[0] = handle.raw
+            except B200RTError as e:  # the others are waiting in the broadcast: tell them
+                err = e
+        dist.broadcast_object_list(payload, src=owner)
+        if payload[0] is None:
+            raise err or B200RTError("the owner rank could not create the shared result buffer")
+        if rank != owner:
+            ctx.check(ctx.lib.b200rt_shared_buffer_open(ctx.h, payload[0], C.byref(ptr)), "shared_buffer_open")
+        self.ptr = ptr.value
+        self.tensor = None
+        if rank == owner:
+            self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+            self.tensor = torch.as_tensor(self, device=ctx.torch_device)
+
+    def close(self):
+        if self.ptr:
+            fn = self.ctx.lib.b200rt_shared_buffer_destroy if self.rank == self.owner else self.ctx.lib.b200rt_shared_buffer_close
+            fn(self.ctx.h, self.ptr)
+            self.ptr = 0
+
+
 # ---- output and model ingest either side of the path (SURVEY.md 8(f) rank 4) ---------------------------------------------------------
 def _to_srgb_u8(f):
     """toSRGB + the 256-scale quantisation of sutil::saveImage's float branches (SDK/sutil/sutil.cpp:585-618, SDK/cuda/helpers.h:36-48)."""

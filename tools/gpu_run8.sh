@@ -1,2 +1,3 @@
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 4 --warmup 3 > gpurun_out/scale_n4_g8.json 2> gpurun_out/scale_n4_g8.err
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 4 --steps 1 --warmup 1 > gpurun_out/scale_n4_ref.json 2> gpurun_out/scale_n4_ref.err
+for ex in p2p allgather; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 4 --warmup 3 --exchange $ex > gpurun_out/ex_n2_$ex.json 2> gpurun_out/ex_n2_$ex.err
+done
