@@ -13,14 +13,16 @@
 // LightVariant 44 B, DiffuseMaterial 12 B, float3 vertex / normal arrays, int material indices) byte for byte; layouts are
 // pinned against the reference headers in tests/golden/kat.json ("playground_layout").
 //
-// Stages per sample s of the frame (all pixels at once; samples run one after the other because the reference adds the sample
-// payloads into `result` in order):
+// Stages per BATCH of samples of the frame (lane = sample-in-batch * pixels + pixel: every sample of the batch, all pixels at once — a
+// frame of 8 samples is 5 launches of 16 M lanes instead of 40 of 2 M; the samples are independent except for the order in which the
+// reference adds their payloads into `result`, which ACCUMULATE keeps):
 //   RAYGEN   pixel seed tea<4>(pixel, dt) advanced by the 2 lens draws of every earlier sample -> primary Ray buffer
 //   TRACE    closest hit over the ray buffer (trav_coop.cuh persistent driver, as b200rt_trace_closest)
 //   SHADE    miss -> payload into the frame sum; hit -> normal, P, light directions (consuming the closest-hit seed in the
 //            reference's order), the nlights + 1 probe rays appended to a dense probe buffer
 //   TRACE    any-hit over the probe buffer (hit / no hit is all optixHitObjectIsHit() is asked for, also for the bounce probe)
-//   RESOLVE  per hit pixel: sum of the unoccluded light terms + ambient term -> frame sum
+//   RESOLVE  per hit lane: sum of the unoccluded light terms + ambient term -> the lane's payload
+//   ACCUMULATE  per pixel: frame sum += payloads of the batch in sample order
 // then FINISH writes film and image.  Arithmetic follows the contract of rt_math.cuh (named IEEE operations, fma where nvcc
 // contracts the reference source), so the film is bit-identical to the scalar oracle (oracle/oracle.cpp: playground_*).
 #include <string.h>
@@ -77,32 +79,33 @@ static_assert(sizeof(PGParams) == 128 && offsetof(PGParams, camera) == 16 && off
 struct PGCounters { unsigned int nhit; unsigned int pad[3]; };
 
 // ---- RAYGEN: Camera::compute_ray (camera.h:127-144) --------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t sample,
-                                                         float4* __restrict__ rays, uint32_t* __restrict__ seeds, float4* __restrict__ sum,
-                                                         PGCounters* __restrict__ counters)
+__global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t sample0,
+                                                         uint32_t nlanes, float4* __restrict__ rays, PGCounters* __restrict__ counters)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) counters->nhit = 0;
-    if (i >= width * height) return;
+    const uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane == 0) counters->nhit = 0;
+    if (lane >= nlanes) return;
     const PGParams P = *params;
     const PGCamera cam = *P.camera;
+    const uint32_t npix = width * height;
+    const uint32_t i = lane % npix, sample = sample0 + lane / npix;
     const uint32_t ix = i % width, iy = i / width;
-    uint32_t seed = sample == 0 ? tea4(ix + width * iy, P.dt) : seeds[i];
-    if (sample == 0) sum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t seed = tea4(ix + width * iy, P.dt);
     float dx = fm(2.0f, fdiv((float)ix, (float)width), -1.0f), dy = fm(2.0f, fdiv((float)iy, (float)height), -1.0f);
     float3 org, dir;
     if (cam.ortho) {
         dir = normalize(f3(fm(dy, cam.v.x, dx * cam.u.x) + cam.w.x, fm(dy, cam.v.y, dx * cam.u.y) + cam.w.y, fm(dy, cam.v.z, dx * cam.u.z) + cam.w.z));
         org = f3(fm(dy, cam.v.x, fm(dx, cam.u.x, cam.eye.x)), fm(dy, cam.v.y, fm(dx, cam.u.y, cam.eye.y)), fm(dy, cam.v.z, fm(dx, cam.u.z, cam.eye.z)));
     } else {
+        // the raygen seed runs through the samples of the frame: every earlier sample drew its two lens numbers from it
+        for (uint32_t k = 0; k < 2u * sample; ++k) lcg(seed);
         const float lx = (rnd(seed) - 0.5f) * cam.aperture, ly = (rnd(seed) - 0.5f) * cam.aperture;
         dx = dx - lx; dy = dy - ly;
         dir = normalize(f3(fm(dy, cam.v.x, dx * cam.u.x) + cam.w.x, fm(dy, cam.v.y, dx * cam.u.y) + cam.w.y, fm(dy, cam.v.z, dx * cam.u.z) + cam.w.z));
         org = f3(fm(ly, cam.v.x, fm(lx, cam.u.x, cam.eye.x)), fm(ly, cam.v.y, fm(lx, cam.u.y, cam.eye.y)), fm(ly, cam.v.z, fm(lx, cam.u.z, cam.eye.z)));
     }
-    seeds[i] = seed;
-    rays[2 * (size_t)i] = make_float4(org.x, org.y, org.z, 0.0f);
-    rays[2 * (size_t)i + 1] = make_float4(dir.x, dir.y, dir.z, 1e16f);
+    rays[2 * (size_t)lane] = make_float4(org.x, org.y, org.z, 0.0f);
+    rays[2 * (size_t)lane + 1] = make_float4(dir.x, dir.y, dir.z, 1e16f);
 }
 
 // LightVariant::wi / lumi
@@ -124,28 +127,26 @@ __device__ __forceinline__ float3 pg_light_lumi(const PGLight& l)
 }
 
 // ---- SHADE: __miss__ms and the first half of __closesthit__ch -------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height,
-                                                        const float4* __restrict__ rays, const ExtHit* __restrict__ hits, float4* __restrict__ sum,
+__global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t nlanes,
+                                                        const float4* __restrict__ rays, const ExtHit* __restrict__ hits, float4* __restrict__ payload,
                                                         float4* __restrict__ probes, float* __restrict__ ndw, uint2* __restrict__ hitinfo,
                                                         PGCounters* __restrict__ counters)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane_idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t npix = width * height;
     const PGParams P = *params;
     const int nl = P.nlights;
     bool is_hit = false;
     ExtHit h;
     float4 ro, rd;
-    if (i < npix) {
-        h = hits[i];
-        ro = rays[2 * (size_t)i]; rd = rays[2 * (size_t)i + 1];
+    if (lane_idx < nlanes) {
+        h = hits[lane_idx];
+        ro = rays[2 * (size_t)lane_idx]; rd = rays[2 * (size_t)lane_idx + 1];
         is_hit = h.t >= 0.0f;
-        if (!is_hit) {
-            float4 s = sum[i];
-            s.x += fm(rd.x, 0.5f, 0.5f); s.y += fm(rd.y, 0.5f, 0.5f); s.z += fm(rd.z, 0.5f, 0.5f);
-            sum[i] = s;
-        }
+        // __miss__ms: payload = direction * 0.5 + 0.5
+        if (!is_hit) payload[lane_idx] = make_float4(fm(rd.x, 0.5f, 0.5f), fm(rd.y, 0.5f, 0.5f), fm(rd.z, 0.5f, 0.5f), 0.f);
     }
+    const uint32_t i = lane_idx % npix;
     // dense slot for the probes of this pixel
     const uint32_t mask = __ballot_sync(0xffffffffu, is_hit);
     uint32_t base = 0;
@@ -188,13 +189,13 @@ __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restric
                           fm(w_in.z, n.z, fm(w_in.y, bn.z, w_in.x * tg.z)));
     probes[2 * (pb + nl)] = make_float4(Pp.x, Pp.y, Pp.z, 0.01f);
     probes[2 * (pb + nl) + 1] = make_float4(out.x, out.y, out.z, 1e16f);
-    hitinfo[k] = make_uint2(i, h.prim);
+    hitinfo[k] = make_uint2(lane_idx, h.prim);
 }
 
 // ---- RESOLVE: second half of __closesthit__ch ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_resolve_kernel(const PGParams* __restrict__ params, const uint32_t* __restrict__ occluded,
                                                           const float* __restrict__ ndw, const uint2* __restrict__ hitinfo,
-                                                          float4* __restrict__ sum, const PGCounters* __restrict__ counters)
+                                                          float4* __restrict__ payload, const PGCounters* __restrict__ counters)
 {
     const PGParams P = *params;
     const uint32_t nhit = counters->nhit;
@@ -216,10 +217,22 @@ __global__ void __launch_bounds__(256) pg_resolve_kernel(const PGParams* __restr
         const bool bounce_hit = occluded[pb + nl] != 0u;
         const float3 amb = f3(0.01f, 0.01f, 0.01f);
         result = result + (bounce_hit ? amb : amb * color);
-        float4 s = sum[hi.x];
-        s.x += result.x; s.y += result.y; s.z += result.z;
-        sum[hi.x] = s;
+        payload[hi.x] = make_float4(result.x, result.y, result.z, 0.f);
     }
+}
+
+// ---- ACCUMULATE: result += payload, sample after sample (optixTriangle.cu:121-141) -----------------------------------------------------
+__global__ void __launch_bounds__(256) pg_accumulate_kernel(uint32_t npix, uint32_t nbatch, int first_batch, const float4* __restrict__ payload,
+                                                             float4* __restrict__ sum)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float4 s = first_batch ? make_float4(0.f, 0.f, 0.f, 0.f) : sum[i];
+    for (uint32_t b = 0; b < nbatch; ++b) {
+        const float4 v = payload[(size_t)b * npix + i];
+        s.x += v.x; s.y += v.y; s.z += v.z;
+    }
+    sum[i] = s;
 }
 
 // ---- FINISH: tail of __raygen__rg (optixTriangle.cu:143-149) ------------------------------------------------------------------------
@@ -326,18 +339,23 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     B2_REQUIRE(ctx, hp.nlights >= 0 && hp.nlights <= 64 && (hp.nlights == 0 || hp.lights), "bad light list");
     B2_REQUIRE(ctx, hp.dt > 0, "Params::dt must be > 0 (frame_step() before the launch, tracer_window.cpp:93-94)");
     const uint32_t npix = (uint32_t)npix64, nl = (uint32_t)hp.nlights, np1 = nl + 1;
+    // samples per batch: all of the frame's unless that takes more than ~8 GB of lane buffers (32 + 20 + 16 + 8 + 40 per probe bytes a lane)
+    const size_t lane_bytes = 32 + sizeof(ExtHit) + 16 + 8 + (size_t)np1 * 40;
+    const uint32_t max_batch = (uint32_t)std::max<size_t>(1, std::min<size_t>((8ull << 30) / (lane_bytes * npix), (1ull << 31) / ((size_t)npix * np1)));
+    const uint32_t batch = std::max(1u, std::min(hp.samples_per_frame, max_batch));
+    const size_t L = (size_t)npix * batch;
     size_t off = 16384;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_cnt = take(sizeof(PGCounters)), o_rays = take(32ull * npix), o_hits = take(sizeof(ExtHit) * (size_t)npix), o_seed = take(4ull * npix),
-                 o_sum = take(16ull * npix), o_probe = take(32ull * npix * np1), o_ndw = take(4ull * npix * np1), o_occ = take(4ull * npix * np1),
-                 o_info = take(8ull * npix);
+    const size_t o_cnt = take(sizeof(PGCounters)), o_rays = take(32 * L), o_hits = take(sizeof(ExtHit) * L), o_pay = take(16 * L),
+                 o_sum = take(16ull * npix), o_probe = take(32 * L * np1), o_ndw = take(4 * L * np1), o_occ = take(4 * L * np1),
+                 o_info = take(8 * L);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
     PGCounters* cnt = (PGCounters*)(W + o_cnt);
     float4* rays = (float4*)(W + o_rays);
     ExtHit* hits = (ExtHit*)(W + o_hits);
-    uint32_t* seeds = (uint32_t*)(W + o_seed);
+    float4* payload = (float4*)(W + o_pay);
     float4* sum = (float4*)(W + o_sum);
     float4* probes = (float4*)(W + o_probe);
     float* ndw = (float*)(W + o_ndw);
@@ -347,23 +365,29 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     const unsigned grid = div_up(npix, 256);
     const uint64_t launches0 = ctx->launches;
     uint64_t primary = 0;
-    for (uint32_t smp = 0; smp < hp.samples_per_frame; ++smp) {
-        pg_raygen_kernel<<<grid, 256, 0, s>>>(dp, width, height, smp, rays, seeds, sum, cnt);
+    if (hp.samples_per_frame == 0) B2_CUDA(ctx, cudaMemsetAsync(sum, 0, 16ull * npix, s));
+    for (uint32_t smp = 0; smp < hp.samples_per_frame; smp += batch) {
+        const uint32_t nb = std::min(batch, hp.samples_per_frame - smp);
+        const uint32_t nlanes = npix * nb;
+        const unsigned lgrid = div_up(nlanes, 256);
+        pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cnt);
         B2_LAUNCH_CHECK(ctx);
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, npix, nullptr, 1, 0, 0u, (b200rt_deviceptr)hits);
+        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, nlanes, nullptr, 1, 0, 0u, (b200rt_deviceptr)hits);
         if (rc) return rc;
-        pg_shade_kernel<<<grid, 256, 0, s>>>(dp, width, height, rays, hits, sum, probes, ndw, info, cnt);
+        pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, hits, payload, probes, ndw, info, cnt);
         B2_LAUNCH_CHECK(ctx);
         // shadow probes: TERMINATE_ON_FIRST_HIT | CULL_DISABLED_ANYHIT (optixTriangle.cu:213-223); the bounce probe carries no flags
         // but is only asked hit / no hit, so both kinds go through one any-hit batch; the last ray of every group of nl + 1 (the
         // bounce probe) ignores CULL_DISABLED_ANYHIT.  With the sample's OPTIX_GEOMETRY_FLAG_NONE build input nothing is culled;
         // a DISABLE_ANYHIT geometry is invisible to the light probes, exactly as in OptiX.
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)probes, (uint64_t)npix * np1, &cnt->nhit, np1, 1, 64u /* CULL_DISABLED_ANYHIT */,
+        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)probes, (uint64_t)nlanes * np1, &cnt->nhit, np1, 1, 64u /* CULL_DISABLED_ANYHIT */,
                           (b200rt_deviceptr)occ, np1);
         if (rc) return rc;
-        pg_resolve_kernel<<<std::min<unsigned>(grid, (unsigned)ctx->sm_count * 8u), 256, 0, s>>>(dp, occ, ndw, info, sum, cnt);
+        pg_resolve_kernel<<<std::min<unsigned>(lgrid, (unsigned)ctx->sm_count * 8u), 256, 0, s>>>(dp, occ, ndw, info, payload, cnt);
         B2_LAUNCH_CHECK(ctx);
-        primary += npix;
+        pg_accumulate_kernel<<<grid, 256, 0, s>>>(npix, nb, smp == 0 ? 1 : 0, payload, sum);
+        B2_LAUNCH_CHECK(ctx);
+        primary += nlanes;
     }
     pg_finish_kernel<<<grid, 256, 0, s>>>(dp, width, height, sum);
     B2_LAUNCH_CHECK(ctx);
