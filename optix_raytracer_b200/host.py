@@ -665,11 +665,19 @@ class Raycaster:
         return n
 
     def launch(self, want_ext=True):
-        """launch (optixRaycasting.cpp:289-317): both batches (the reference uses two streams; same stream here)."""
-        ctx = self.ctx
-        ctx.launch_raycast(self.programs, self.d_params.data_ptr(), self.sbt, self.width, self.height, self.ext.data_ptr() if want_ext else 0)
-        ctx.launch_raycast(self.programs, self.d_params_translated.data_ptr(), self.sbt, self.width, self.height,
-                           self.ext_translated.data_ptr() if want_ext else 0)
+        """launch (optixRaycasting.cpp:289-317): the two batches go to two streams, as in the reference, so they may overlap; the
+        caller's stream waits for both."""
+        ctx, dev = self.ctx, self.ctx.torch_device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        batches = ((self.d_params, self.ext), (self.d_params_translated, self.ext_translated))
+        for st, (params, ext) in zip(self._streams, batches):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                ctx.launch_raycast(self.programs, params.data_ptr(), self.sbt, self.width, self.height, ext.data_ptr() if want_ext else 0)
+        for st in self._streams:
+            cur.wait_stream(st)
 
     def close(self):
         for hc, tex, arr in self._tex_handles:
