@@ -32,6 +32,7 @@
 #include "accel.h"
 #include "internal.h"
 #include "rt_math.cuh"
+#include "trav_coop.cuh"
 
 namespace b200rt {
 
@@ -76,15 +77,17 @@ static_assert(sizeof(PGParams) == 128 && offsetof(PGParams, camera) == 16 && off
                   offsetof(PGParams, nlights) == 104 && offsetof(PGParams, materials) == 112 && offsetof(PGParams, nmaterials) == 120,
               "imgui_test Params layout");
 
-struct PGCounters { unsigned int nhit; unsigned int pad[3]; };
+struct PGCounters { unsigned int nhit; unsigned int ncand; unsigned int pad[2]; };
 
 // ---- RAYGEN: Camera::compute_ray (camera.h:127-144) --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t sample0,
-                                                         uint32_t nlanes, float4* __restrict__ rays, PGCounters* __restrict__ counters)
+                                                         uint32_t nlanes, float4* __restrict__ rays, uint32_t* __restrict__ cand,
+                                                         float4* __restrict__ payload, PGCounters* __restrict__ counters)
 {
     const uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane == 0) counters->nhit = 0;
-    if (lane >= nlanes) return;
+    bool candidate = false;
+    float3 org = f3(0.f, 0.f, 0.f), dir = org;
+    if (lane < nlanes) {
     const PGParams P = *params;
     const PGCamera cam = *P.camera;
     const uint32_t npix = width * height;
@@ -92,7 +95,6 @@ __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restri
     const uint32_t ix = i % width, iy = i / width;
     uint32_t seed = tea4(ix + width * iy, P.dt);
     float dx = fm(2.0f, fdiv((float)ix, (float)width), -1.0f), dy = fm(2.0f, fdiv((float)iy, (float)height), -1.0f);
-    float3 org, dir;
     if (cam.ortho) {
         dir = normalize(f3(fm(dy, cam.v.x, dx * cam.u.x) + cam.w.x, fm(dy, cam.v.y, dx * cam.u.y) + cam.w.y, fm(dy, cam.v.z, dx * cam.u.z) + cam.w.z));
         org = f3(fm(dy, cam.v.x, fm(dx, cam.u.x, cam.eye.x)), fm(dy, cam.v.y, fm(dx, cam.u.y, cam.eye.y)), fm(dy, cam.v.z, fm(dx, cam.u.z, cam.eye.z)));
@@ -104,8 +106,22 @@ __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restri
         dir = normalize(f3(fm(dy, cam.v.x, dx * cam.u.x) + cam.w.x, fm(dy, cam.v.y, dx * cam.u.y) + cam.w.y, fm(dy, cam.v.z, dx * cam.u.z) + cam.w.z));
         org = f3(fm(ly, cam.v.x, fm(lx, cam.u.x, cam.eye.x)), fm(ly, cam.v.y, fm(lx, cam.u.y, cam.eye.y)), fm(ly, cam.v.z, fm(lx, cam.u.z, cam.eye.z)));
     }
-    rays[2 * (size_t)lane] = make_float4(org.x, org.y, org.z, 0.0f);
-    rays[2 * (size_t)lane + 1] = make_float4(dir.x, dir.y, dir.z, 1e16f);
+    // a ray that passes the scene bounds by is a miss: __miss__ms on the spot (payload = direction * 0.5 + 0.5); the others are
+    // compacted into the ray buffer of the persistent traversal
+    candidate = ray_reaches_bounds((const AccelHeader*)P.handle, org, dir, 0.0f, 1e16f);
+    if (!candidate) payload[lane] = make_float4(fm(dir.x, 0.5f, 0.5f), fm(dir.y, 0.5f, 0.5f), fm(dir.z, 0.5f, 0.5f), 0.f);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
+    if (!mask) return;
+    const uint32_t l32 = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (l32 == leader) base = atomicAdd(&counters->ncand, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!candidate) return;
+    const uint32_t j = base + __popc(mask & ((1u << l32) - 1u));
+    cand[j] = lane;
+    rays[2 * (size_t)j] = make_float4(org.x, org.y, org.z, 0.0f);
+    rays[2 * (size_t)j + 1] = make_float4(dir.x, dir.y, dir.z, 1e16f);
 }
 
 // LightVariant::wi / lumi
@@ -128,20 +144,23 @@ __device__ __forceinline__ float3 pg_light_lumi(const PGLight& l)
 
 // ---- SHADE: __miss__ms and the first half of __closesthit__ch -------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t nlanes,
-                                                        const float4* __restrict__ rays, const ExtHit* __restrict__ hits, float4* __restrict__ payload,
+                                                        const float4* __restrict__ rays, const uint32_t* __restrict__ cand,
+                                                        const ExtHit* __restrict__ hits, float4* __restrict__ payload,
                                                         float4* __restrict__ probes, float* __restrict__ ndw, uint2* __restrict__ hitinfo,
                                                         PGCounters* __restrict__ counters)
 {
-    const uint32_t lane_idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;   // candidate ray
     const uint32_t npix = width * height;
     const PGParams P = *params;
     const int nl = P.nlights;
     bool is_hit = false;
     ExtHit h;
     float4 ro, rd;
-    if (lane_idx < nlanes) {
-        h = hits[lane_idx];
-        ro = rays[2 * (size_t)lane_idx]; rd = rays[2 * (size_t)lane_idx + 1];
+    uint32_t lane_idx = 0;
+    if (j < min(counters->ncand, nlanes)) {
+        lane_idx = cand[j];
+        h = hits[j];
+        ro = rays[2 * (size_t)j]; rd = rays[2 * (size_t)j + 1];
         is_hit = h.t >= 0.0f;
         // __miss__ms: payload = direction * 0.5 + 0.5
         if (!is_hit) payload[lane_idx] = make_float4(fm(rd.x, 0.5f, 0.5f), fm(rd.y, 0.5f, 0.5f), fm(rd.z, 0.5f, 0.5f), 0.f);
@@ -348,7 +367,7 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_cnt = take(sizeof(PGCounters)), o_rays = take(32 * L), o_hits = take(sizeof(ExtHit) * L), o_pay = take(16 * L),
                  o_sum = take(16ull * npix), o_probe = take(32 * L * np1), o_ndw = take(4 * L * np1), o_occ = take(4 * L * np1),
-                 o_info = take(8 * L);
+                 o_info = take(8 * L), o_cand = take(4 * L);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
     char* W = (char*)ctx->ws.ptr;
@@ -361,6 +380,7 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     float* ndw = (float*)(W + o_ndw);
     uint32_t* occ = (uint32_t*)(W + o_occ);
     uint2* info = (uint2*)(W + o_info);
+    uint32_t* cand = (uint32_t*)(W + o_cand);
     const PGParams* dp = (const PGParams*)d_params;
     const unsigned grid = div_up(npix, 256);
     const uint64_t launches0 = ctx->launches;
@@ -370,11 +390,12 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
         const uint32_t nb = std::min(batch, hp.samples_per_frame - smp);
         const uint32_t nlanes = npix * nb;
         const unsigned lgrid = div_up(nlanes, 256);
-        pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cnt);
+        B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(PGCounters), s));
+        pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cand, payload, cnt);
         B2_LAUNCH_CHECK(ctx);
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, nlanes, nullptr, 1, 0, 0u, (b200rt_deviceptr)hits);
+        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, nlanes, &cnt->ncand, 1, 0, 0u, (b200rt_deviceptr)hits);
         if (rc) return rc;
-        pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, hits, payload, probes, ndw, info, cnt);
+        pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, cand, hits, payload, probes, ndw, info, cnt);
         B2_LAUNCH_CHECK(ctx);
         // shadow probes: TERMINATE_ON_FIRST_HIT | CULL_DISABLED_ANYHIT (optixTriangle.cu:213-223); the bounce probe carries no flags
         // but is only asked hit / no hit, so both kinds go through one any-hit batch; the last ray of every group of nl + 1 (the

@@ -103,6 +103,27 @@ template <> struct CoopSharedAnyHit<true> {
     float res_fac[COOP_WARPS][32];  // factor the unit's any-hit program returned for the owner's pending attenuation
 };
 
+// Does the ray reach the (padded) bounds of the traversable at all?  For ray-generation kernels that finish the rays passing the scene
+// by on the spot (one thread per ray) instead of making them work items of the persistent traversal.  Conservative like every box test
+// here: the pad (2^-14 of the largest extent; an IAS's bounds are the box of its instances' transformed corners, one more rounding than
+// a GAS's) and the slack keep every ray the triangle test could accept.
+__device__ __forceinline__ bool ray_reaches_bounds(const AccelHeader* __restrict__ h, float3 o, float3 d, float tmin, float tmax)
+{
+    if (h->kind == ACCEL_KIND_IAS ? h->num_instances == 0u : h->num_tris == 0u) return false;
+    const float bx = fabsf(d.x) < DIR_EPS ? copysignf(DIR_EPS, d.x) : d.x;
+    const float by = fabsf(d.y) < DIR_EPS ? copysignf(DIR_EPS, d.y) : d.y;
+    const float bz = fabsf(d.z) < DIR_EPS ? copysignf(DIR_EPS, d.z) : d.z;
+    const float idx = fdiv(1.0f, bx), idy = fdiv(1.0f, by), idz = fdiv(1.0f, bz);
+    const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
+    const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 6.103515625e-05f;
+    const float ax = ((lx - pad) - o.x) * idx, cx = ((hx + pad) - o.x) * idx;
+    const float ay = ((ly - pad) - o.y) * idy, cy = ((hy + pad) - o.y) * idy;
+    const float az = ((lz - pad) - o.z) * idz, cz = ((hz + pad) - o.z) * idz;
+    const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
+    const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), tmax));
+    return tn <= tf * BOX_SLACK;
+}
+
 // Prepare the per-ray constants for a GAS (object-space origin/direction).  best.t must hold tmax.
 // BOUNDS: first test the ray against the GAS bounds and return false when it passes them by — for launches where most rays miss the
 // scene (camera rays around a model) this replaces the ray set-up (three more IEEE divisions), the root fetch and a full node visit by

@@ -264,19 +264,7 @@ __global__ void __launch_bounds__(256) w_raygen_kernel(const __grid_constant__ W
         const AccelHeader* h = (const AccelHeader*)P.handle;
         float3 o, d;
         w_camera_ray(P, k.width, k.height, i, o, d);
-        const float bx = fabsf(d.x) < DIR_EPS ? copysignf(DIR_EPS, d.x) : d.x;
-        const float by = fabsf(d.y) < DIR_EPS ? copysignf(DIR_EPS, d.y) : d.y;
-        const float bz = fabsf(d.z) < DIR_EPS ? copysignf(DIR_EPS, d.z) : d.z;
-        const float idx = fdiv(1.0f, bx), idy = fdiv(1.0f, by), idz = fdiv(1.0f, bz);
-        const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
-        // an IAS's bounds are the box of its instances' transformed corners: one more rounding than a GAS's, covered by a wider pad
-        const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 6.103515625e-05f;
-        const float ax = ((lx - pad) - o.x) * idx, cx = ((hx + pad) - o.x) * idx;
-        const float ay = ((ly - pad) - o.y) * idy, cy = ((hy + pad) - o.y) * idy;
-        const float az = ((lz - pad) - o.z) * idz, cz = ((hz + pad) - o.z) * idz;
-        const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), 0.0f));
-        const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), 1e16f));
-        candidate = tn <= tf * BOX_SLACK && (h->kind == ACCEL_KIND_IAS ? h->num_instances != 0u : h->num_tris != 0u);
+        candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
         if (!candidate) w_write_pixel(P, i, P.miss_color);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
