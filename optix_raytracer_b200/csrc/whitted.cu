@@ -17,15 +17,17 @@
 //                                        (anyhit.cuh, run inside traversal)
 //   ALPHA_MODE_BLEND continuation (266-286)  result = result * alpha + trace(same ray, tmin = t, depth + 1) * (1 - alpha), depth < 8
 //
-// Three launches per subframe for a scene without BLEND materials (one sample per pixel and launch, as the reference):
-//   PRIMARY  persistent traversal (trav_coop.cuh) whose fetch generates the camera ray and whose commit writes the pixel of a miss
-//            straight away (the reference's miss program + raygen tail) or a 48-byte hit slot
+// Four launches per subframe for a scene without BLEND materials (one sample per pixel and launch, as the reference):
+//   RAYGEN   one thread per pixel: the camera ray against the padded scene bounds; a ray that passes them by is a miss and its pixel is
+//            written here (miss program + raygen tail); the rest become work items
+//   PRIMARY  persistent traversal (trav_coop.cuh) of those camera rays: miss -> pixel written in the commit, hit -> a 48-byte hit slot
 //   SHADE    one thread per hit slot: getLocalGeometry, the material, the per-light BRDF factors and shadow probes
-//   SHADOW   persistent traversal, one item per hit slot: its probes one after the other (TERMINATE_ON_FIRST_HIT, attenuation through
-//            the any-hit program), the terms summed in light order, the pixel accumulated and written in the commit
+//   SHADOW   persistent traversal, one item per (hit slot, light): the probe (TERMINATE_ON_FIRST_HIT, attenuation through the any-hit
+//            program); the item that completes a slot sums the slot's terms in light order and writes the pixel
 // BLEND materials add levels: SHADE puts the continuation of a BLEND hit on a list, the host reads the count (the only
 // synchronisation, and only for scenes that have such materials) and runs PRIMARY / SHADE / SHADOW for the list; COMBINE then folds
 // each pixel's chain of levels back to front exactly as the recursion of the reference returns.
+// (One persistent launch for the whole program — pixel = work item — was built and measured slower: profiles/r01_whitted_launches.md.)
 #include <string.h>
 
 #include <algorithm>
