@@ -779,7 +779,8 @@ __global__ void build_ias_kernel(const char* __restrict__ instances, uint32_t n,
         for (uint32_t k = 0; k < n; ++k) {
             const AccelHeader* g = (const AccelHeader*)recs[k].gas;
             if (!g || g->magic != ACCEL_MAGIC || !g->num_tris) continue;
-            anyhit |= g->anyhit;
+            // OPTIX_INSTANCE_FLAG_DISABLE_ANYHIT (1<<2) / ENFORCE_ANYHIT (1<<3) override the geometry flags of the instanced GAS
+            anyhit |= (recs[k].flags & 4u) ? 0u : (recs[k].flags & 8u) ? 1u : g->anyhit;
             for (int c = 0; c < 8; ++c) {
                 const float3 p = f3(g->bounds[(c & 1) ? 3 : 0], g->bounds[(c & 2) ? 4 : 1], g->bounds[(c & 4) ? 5 : 2]);
                 const float3 w = xform_point(recs[k].m, p);

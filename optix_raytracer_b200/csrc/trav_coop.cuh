@@ -170,7 +170,8 @@ __device__ __forceinline__ bool trav_begin(Trav& s, float* __restrict__ my_ray, 
 }
 
 // Set up traversal of `h` (GAS, or the first usable instance >= first_inst of an IAS) for the world-space ray.
-// keep = TP_* bits to carry over.  Returns false when there is nothing (more) to traverse.
+// keep = TP_* bits to carry over; cull = the ray's OptixRayFlags (the CULL_* and DISABLE/ENFORCE_ANYHIT bits are used).
+// Returns false when there is nothing (more) to traverse.
 template <bool BOUNDS = false>
 __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ h, float3 o, float3 d,
                                                   float tmin, uint32_t keep, uint32_t cull, uint32_t first_inst)
@@ -178,7 +179,7 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
     if (h->kind == ACCEL_KIND_GAS) {
         if (first_inst > 0u) return false;
         s.inst = 0u;
-        if (!trav_begin<BOUNDS>(s, my_ray, h, o, d, tmin, keep, cull)) { s.pack = keep; return false; }
+        if (!trav_begin<BOUNDS>(s, my_ray, h, o, d, tmin, keep, cull_word(cull, 0u))) { s.pack = keep; return false; }
         return true;
     }
     const InstanceRecord* recs = (const InstanceRecord*)((const char*)h + h->inst_off);
@@ -187,7 +188,7 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
         const InstanceRecord* ir = recs + k;
         if (!(ir->mask & 1u)) continue;
         s.inst = k;
-        const uint32_t c = (ir->flags & 1u) ? 0u : cull;  // OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING
+        const uint32_t c = cull_word(cull, ir->flags);  // the instance's face-culling / facing / any-hit flags
         // instances are tested at their bounds always: with several of them a ray passes most of them by
         if (trav_begin<true>(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c)) return true;
     }
@@ -453,7 +454,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                             float t, b1, b2;
                             bool uh = tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2);
                             if constexpr (Work::ANYHIT) {
-                                if (ah_on && uh && !((__float_as_uint(q1.w) >> TRI_FLAG_SHIFT) & 1u)) {
+                                if (ah_on && uh && !anyhit_off(__float_as_uint(q1.w) >> TRI_FLAG_SHIFT, __float_as_uint(my_ray[8]))) {
                                     float fac;
                                     uh = work.anyhit(__float_as_uint(q0.w), __float_as_uint(q1.w) & TRI_SBT_MASK, s.inst, s.pack, b1, b2, fac);
                                     if (fac != 1.0f) work.attenuate(fac);
@@ -519,7 +520,8 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                         // goes back to the owner with the unit's result
                         if (ah_on) {
                             float fac = 1.0f;
-                            if (uhit && !((usbt >> TRI_FLAG_SHIFT) & 1u)) uhit = work.anyhit(uprim, usbt & TRI_SBT_MASK, oinst, opack, ub1, ub2, fac);
+                            if (uhit && !anyhit_off(usbt >> TRI_FLAG_SHIFT, __float_as_uint(sh.ray[wid][owner * RAY_S_STRIDE + 8])))
+                                uhit = work.anyhit(uprim, usbt & TRI_SBT_MASK, oinst, opack, ub1, ub2, fac);
                             sha.res_fac[wid][lane] = fac;
                         }
                     }

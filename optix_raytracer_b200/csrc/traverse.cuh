@@ -63,6 +63,23 @@ __device__ __forceinline__ TriRay make_tri_ray(float3 o, float3 d)
     return r;
 }
 
+// The cull word a triangle test sees: the ray's CULL_* flags (bits 4-7, reference include/optix_types.h:1819-1839) after the instance
+// flags had their say, plus the any-hit override in bits 0-1 — 1 = any-hit off for every triangle, 2 = any-hit on for every triangle,
+// 0 = the triangle's own OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT decides.  Precedence as documented in include/optix_types.h:1088-1108 and
+// 1794-1806: ray flags over instance flags over geometry flags.  OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING drops the two
+// face-cull bits, OPTIX_INSTANCE_FLAG_FLIP_TRIANGLE_FACING swaps them.  Same function in oracle.cpp (cull_word).
+__host__ __device__ __forceinline__ uint32_t cull_word(uint32_t ray_flags, uint32_t inst_flags)
+{
+    uint32_t c = ray_flags & 0xf0u;
+    if (inst_flags & 1u) c &= ~0x30u;
+    else if (inst_flags & 2u) c = (c & ~0x30u) | ((c & 0x10u) << 1) | ((c & 0x20u) >> 1);
+    uint32_t force = (ray_flags & 1u) ? 1u : (ray_flags & 2u) ? 2u : 0u;
+    if (!force) force = (inst_flags & 4u) ? 1u : (inst_flags & 8u) ? 2u : 0u;
+    return c | force;
+}
+// does the triangle (geometry flags gflags) run any-hit programs under this cull word?
+__device__ __forceinline__ bool anyhit_off(uint32_t gflags, uint32_t cull) { return (cull & 3u) ? (cull & 1u) != 0u : (gflags & 1u) != 0u; }
+
 // Watertight test; identical op sequence to oracle.cpp:tri_hit.  Accepts tmin < t and
 // (t < best.t  or  t == best.t with lower ordinal once something was found).
 template <bool ANY>
@@ -97,9 +114,12 @@ __device__ __forceinline__ bool tri_test(const TriRay& r, const float4 q0, const
             if ((cull & 16u) && det < 0.0f) return false;
             if ((cull & 32u) && det > 0.0f) return false;
         }
-        // OPTIX_RAY_FLAG_CULL_DISABLED_ANYHIT (1<<6) / CULL_ENFORCED_ANYHIT (1<<7) against OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT (1<<0)
-        if ((cull & 64u) && (gflags & 1u)) return false;
-        if ((cull & 128u) && !(gflags & 1u)) return false;
+        // OPTIX_RAY_FLAG_CULL_DISABLED_ANYHIT (1<<6) / CULL_ENFORCED_ANYHIT (1<<7) against the effective any-hit state of the triangle
+        if (cull & 0xc0u) {
+            const bool off = anyhit_off(gflags, cull);
+            if ((cull & 64u) && off) return false;
+            if ((cull & 128u) && !off) return false;
+        }
     }
     const uint32_t ord = __float_as_uint(q2.w);
     if (t == best.t && !(found && ord < best.ord)) return false;
@@ -273,7 +293,7 @@ __device__ __forceinline__ bool trace_handle(const AccelHeader* __restrict__ h, 
 {
     hit.t = tmax;
     hit.inst = 0;
-    const uint32_t cull = ray_flags & 0xf0u;
+    const uint32_t cull = cull_word(ray_flags, 0u);
     if (h->kind == ACCEL_KIND_GAS) {
         // initial acceptance must be strict (t < tmax): run with found=false semantics
         return trace_gas<ANY, STATS>(h, o, d, tmin, hit, cull, st);
@@ -286,8 +306,7 @@ __device__ __forceinline__ bool trace_handle(const AccelHeader* __restrict__ h, 
         if (!(ir->mask & 1u)) continue;
         const float3 oo = xform_point(ir->inv, o), dd = xform_vec(ir->inv, d);
         RayHit cand = hit;
-        uint32_t c = cull;
-        if (ir->flags & 1u) c = 0;  // OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING
+        const uint32_t c = cull_word(ray_flags, ir->flags);
         if (trace_gas<ANY, STATS>((const AccelHeader*)ir->gas, oo, dd, tmin, cand, c, st)) {
             // a later instance only replaces on strictly smaller t (lower instance index wins ties)
             if (!any || cand.t < hit.t) {

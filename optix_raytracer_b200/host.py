@@ -197,7 +197,7 @@ class Context:
         return bi
 
     def instance_input(self, instances):
-        """instances: list of (transform12, sbt_offset, Accel[, visibility_mask]).  SDK/sutil/Scene.cpp:1134-1212."""
+        """instances: list of (transform12, sbt_offset, Accel[, visibility_mask[, OptixInstanceFlags]]).  SDK/sutil/Scene.cpp:1134-1212."""
         n = len(instances)
         arr = (L.Instance * n)()
         keep = []
@@ -207,7 +207,7 @@ class Context:
             arr[i].instanceId = i
             arr[i].sbtOffset = sbt_off
             arr[i].visibilityMask = inst[3] if len(inst) > 3 else 1
-            arr[i].flags = 0
+            arr[i].flags = inst[4] if len(inst) > 4 else 0
             arr[i].traversableHandle = acc.handle
             keep.append(acc)
         dev = self.to_device(np.frombuffer(bytes(arr), dtype=np.uint8).copy())

@@ -193,6 +193,7 @@ struct Geometry {
     std::vector<Tri> tris;            // object space, ordinal = index
     std::vector<uint32_t> sbt;        // per-triangle SBT offset (material), may be empty
     uint32_t gflags = 1u;             // OptixGeometryFlags of the build input (default DISABLE_ANYHIT, as the samples set it)
+    std::vector<uint8_t> tri_gflags;  // optional: OptixGeometryFlags per triangle (= of its SBT record); empty => gflags for all
     std::vector<BNode> nodes;
     std::vector<uint32_t> order;      // leaf triangle ordinals
     bool brute = true;
@@ -304,6 +305,18 @@ static inline bool box_hit(const BNode& n, f3 o, f3 inv, float tmin, float tmax)
     return t0 <= t1;
 }
 
+// The cull word of a triangle test: the ray's CULL_* flags after the instance flags, any-hit override in bits 0-1 (1 = off, 2 = on).
+// Precedence ray > instance > geometry, reference include/optix_types.h:1088-1108, 1794-1839.  Same function as traverse.cuh:cull_word.
+static inline uint32_t cull_word(uint32_t ray_flags, uint32_t inst_flags)
+{
+    uint32_t c = ray_flags & 0xf0u;
+    if (inst_flags & 1u) c &= ~0x30u;                                                                     // DISABLE_TRIANGLE_FACE_CULLING
+    else if (inst_flags & 2u) c = (c & ~0x30u) | ((c & 0x10u) << 1) | ((c & 0x20u) >> 1);                   // FLIP_TRIANGLE_FACING
+    uint32_t force = (ray_flags & 1u) ? 1u : (ray_flags & 2u) ? 2u : 0u;                                  // ray DISABLE / ENFORCE_ANYHIT
+    if (!force) force = (inst_flags & 4u) ? 1u : (inst_flags & 8u) ? 2u : 0u;                             // instance DISABLE / ENFORCE_ANYHIT
+    return c | force;
+}
+
 // closest hit in one geometry, object space.  `best` carries the current closest (t, prim).
 template <bool ANY, bool STATS>
 static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32_t cull_flags)
@@ -316,15 +329,17 @@ static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32
         // strict t < best.t, or equal t with a lower ordinal (order independence)
         if (tri_hit<true>(rp, g.tris[p], tmin, best.t, t, b1, b2, &det)) {
             if (cull_flags) {
+                const uint32_t gf = g.tri_gflags.empty() ? g.gflags : (uint32_t)g.tri_gflags[p];
                 // OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1<<4): det<0 is back facing for
                 // counter-clockwise front faces seen along the ray in this formulation.
-                if (!(g.gflags & 4u)) {  // OPTIX_GEOMETRY_FLAG_DISABLE_TRIANGLE_FACE_CULLING
+                if (!(gf & 4u)) {  // OPTIX_GEOMETRY_FLAG_DISABLE_TRIANGLE_FACE_CULLING
                     if ((cull_flags & 16u) && det < 0.0f) return;
                     if ((cull_flags & 32u) && det > 0.0f) return;
                 }
                 // OPTIX_RAY_FLAG_CULL_DISABLED_ANYHIT (1<<6) / CULL_ENFORCED_ANYHIT (1<<7) vs OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT (1<<0)
-                if ((cull_flags & 64u) && (g.gflags & 1u)) return;
-                if ((cull_flags & 128u) && !(g.gflags & 1u)) return;
+                const bool ah_off = (cull_flags & 3u) ? (cull_flags & 1u) != 0u : (gf & 1u) != 0u;
+                if ((cull_flags & 64u) && ah_off) return;
+                if ((cull_flags & 128u) && !ah_off) return;
             }
             if (t < best.t || (t == best.t && found && p < best.prim)) {
                 best = {t, p, b1, b2, det};
@@ -363,7 +378,7 @@ static bool trace_geom(Geometry& g, f3 o, f3 d, float tmin, HitRec& best, uint32
 // A scene = one geometry, optionally behind one or more instance transforms (IAS of the glTF path,
 // SDK/sutil/Scene.cpp:1134-1212).  Rays are carried into object space with the inverse 3x4 and `t`
 // is shared between spaces (OptiX semantics).
-struct Instance { float m[12]; float inv[12]; int geom; };
+struct Instance { float m[12]; float inv[12]; int geom; uint32_t flags = 0u, mask = 1u; };  // OptixInstance flags / visibilityMask
 
 struct Scene {
     std::vector<Geometry> geoms;
@@ -405,19 +420,20 @@ static inline f3 xform_normal(const float* inv, f3 n)
 struct SceneHit { float t; uint32_t inst, prim; float b1, b2; bool hit; };
 
 template <bool ANY, bool STATS = false>
-static SceneHit trace_scene(Scene& s, f3 o, f3 d, float tmin, float tmax, uint32_t cull_flags = 0)
+static SceneHit trace_scene(Scene& s, f3 o, f3 d, float tmin, float tmax, uint32_t ray_flags = 0)
 {
     SceneHit r{tmax, 0xffffffffu, 0xffffffffu, 0.f, 0.f, false};
     if (s.insts.empty()) {
         HitRec b{tmax, 0, 0, 0, 0};
-        if (trace_geom<ANY, STATS>(s.geoms[0], o, d, tmin, b, cull_flags)) r = {b.t, 0, b.prim, b.b1, b.b2, true};
+        if (trace_geom<ANY, STATS>(s.geoms[0], o, d, tmin, b, cull_word(ray_flags, 0u))) r = {b.t, 0, b.prim, b.b1, b.b2, true};
         return r;
     }
     for (uint32_t k = 0; k < s.insts.size(); ++k) {
         const Instance& in = s.insts[k];
+        if (!(in.mask & 1u)) continue;  // every ray on the path is traced with OptixVisibilityMask(1) or (255): bit 0 decides
         HitRec b{r.t, 0, 0, 0, 0};
         // a later instance only wins with strictly smaller t (lower instance index wins ties)
-        if (trace_geom<ANY, STATS>(s.geoms[in.geom], xform_point(in.inv, o), xform_vec(in.inv, d), tmin, b, cull_flags)) {
+        if (trace_geom<ANY, STATS>(s.geoms[in.geom], xform_point(in.inv, o), xform_vec(in.inv, d), tmin, b, cull_word(ray_flags, in.flags))) {
             if (b.t < r.t) { r = {b.t, k, b.prim, b.b1, b.b2, true}; if (ANY) return r; }
         }
     }
@@ -657,22 +673,31 @@ void* orc_scene_create(const float* verts, int64_t ntri, const uint32_t* sbt)
     return s;
 }
 // add one instance of geometry 0 with a row-major 3x4 object->world transform
-void orc_scene_add_instance(void* scene, const float* m34)
+void orc_scene_add_instance_ex(void* scene, const float* m34, uint32_t flags, uint32_t mask)
 {
     Scene* s = (Scene*)scene;
     Instance in;
     memcpy(in.m, m34, sizeof(in.m));
     invert34(in.m, in.inv);
     in.geom = 0;
+    in.flags = flags;
+    in.mask = mask;
     s->insts.push_back(in);
 }
+void orc_scene_add_instance(void* scene, const float* m34) { orc_scene_add_instance_ex(scene, m34, 0u, 1u); }
 void orc_scene_set_brute(void* scene, int brute)
 {
     Scene* s = (Scene*)scene;
     for (auto& g : s->geoms) g.brute = brute != 0 || g.nodes.empty();
 }
 void orc_scene_destroy(void* scene) { delete (Scene*)scene; }
-void orc_scene_set_geometry_flags(void* scene, uint32_t gflags) { for (auto& g : ((Scene*)scene)->geoms) g.gflags = gflags; }
+void orc_scene_set_geometry_flags(void* scene, uint32_t gflags) { for (auto& g : ((Scene*)scene)->geoms) { g.gflags = gflags; g.tri_gflags.clear(); } }
+// OptixGeometryFlags per triangle (the flags of the SBT record each triangle belongs to), one byte each
+void orc_scene_set_triangle_flags(void* scene, const uint8_t* flags)
+{
+    Geometry& g = ((Scene*)scene)->geoms[0];
+    g.tri_gflags.assign(flags, flags + g.tris.size());
+}
 void orc_invert34(const float* m, float* inv) { invert34(m, inv); }
 
 // rays: n * 8 floats {ox,oy,oz,tmin,dx,dy,dz,tmax} (the reference Ray struct,
@@ -692,12 +717,12 @@ void orc_trace(void* scene, const float* rays, int64_t n, uint32_t* out, int any
             uint32_t* o = out + 5 * i;
             f3 org = mk(r[0], r[1], r[2]), dir = mk(r[4], r[5], r[6]);
             if (any_hit) {
-                SceneHit h = stats ? trace_scene<true, true>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u)
-                                   : trace_scene<true, false>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u);
+                SceneHit h = stats ? trace_scene<true, true>(*s, org, dir, r[3], r[7], ray_flags)
+                                   : trace_scene<true, false>(*s, org, dir, r[3], r[7], ray_flags);
                 o[0] = h.hit ? 1u : 0u; o[1] = o[2] = o[3] = o[4] = 0;
             } else {
-                SceneHit h = stats ? trace_scene<false, true>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u)
-                                   : trace_scene<false, false>(*s, org, dir, r[3], r[7], ray_flags & 0xf0u);
+                SceneHit h = stats ? trace_scene<false, true>(*s, org, dir, r[3], r[7], ray_flags)
+                                   : trace_scene<false, false>(*s, org, dir, r[3], r[7], ray_flags);
                 float t = h.hit ? h.t : -1.0f;
                 memcpy(o, &t, 4);
                 o[1] = h.prim; o[2] = h.inst;

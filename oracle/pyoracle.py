@@ -37,6 +37,8 @@ def lib():
         L.orc_make_color.argtypes = [vp, i32, vp]
         L.orc_scene_create.restype = vp; L.orc_scene_create.argtypes = [vp, i64, vp]
         L.orc_scene_add_instance.argtypes = [vp, vp]
+        L.orc_scene_add_instance_ex.argtypes = [vp, vp, u32, u32]
+        L.orc_scene_set_triangle_flags.argtypes = [vp, vp]
         L.orc_scene_set_brute.argtypes = [vp, i32]
         L.orc_scene_destroy.argtypes = [vp]
         L.orc_invert34.argtypes = [vp, vp]
@@ -121,16 +123,26 @@ def make_color(rgb):
 
 
 class Scene:
-    """Triangle soup (ntri,3,3) float32 in object space + optional per-triangle SBT offsets and instances."""
+    """Triangle soup (ntri,3,3) float32 in object space + optional per-triangle SBT offsets and instances.
+    instances: 3x4 transforms, or (transform, OptixInstanceFlags, visibilityMask) tuples.  geom_flags: OptixGeometryFlags of the build
+    input — one value, or one per triangle (the flags of the SBT record the triangle belongs to)."""
 
     def __init__(self, tris, sbt=None, instances=(), geom_flags=None):
         self.tris = _f32(tris).reshape(-1, 9)
         self.sbt = None if sbt is None else np.ascontiguousarray(sbt, dtype=np.uint32)
         self.h = lib().orc_scene_create(_p(self.tris), self.tris.shape[0], _p(self.sbt))
         for m in instances:
-            lib().orc_scene_add_instance(self.h, _p(_f32(m).reshape(12)))
+            if isinstance(m, tuple):
+                lib().orc_scene_add_instance_ex(self.h, _p(_f32(m[0]).reshape(12)), int(m[1]), int(m[2]) if len(m) > 2 else 1)
+            else:
+                lib().orc_scene_add_instance(self.h, _p(_f32(m).reshape(12)))
         if geom_flags is not None:  # OptixGeometryFlags of the build input (4 = DISABLE_TRIANGLE_FACE_CULLING)
-            lib().orc_scene_set_geometry_flags(self.h, int(geom_flags))
+            if np.ndim(geom_flags) == 0:
+                lib().orc_scene_set_geometry_flags(self.h, int(geom_flags))
+            else:
+                gf = np.ascontiguousarray(geom_flags, dtype=np.uint8)
+                assert gf.shape[0] == self.tris.shape[0]
+                lib().orc_scene_set_triangle_flags(self.h, _p(gf))
 
     def set_brute(self, brute):
         lib().orc_scene_set_brute(self.h, int(bool(brute)))

@@ -235,6 +235,51 @@ def test_multi_instance_ias_vs_oracle(ctx, orc):
     assert np.array_equal(occ, scene.trace(rays, any_hit=True)["occluded"])
 
 
+def test_ray_and_instance_flags_vs_oracle(ctx, orc):
+    """Every ray-flag family against instances that carry every instance-flag family, over geometry whose two SBT records differ in
+    their geometry flags: face culling (with OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING / FLIP_TRIANGLE_FACING and
+    OPTIX_GEOMETRY_FLAG_DISABLE_TRIANGLE_FACE_CULLING), the any-hit state under ray > instance > geometry precedence as seen by
+    CULL_DISABLED_ANYHIT / CULL_ENFORCED_ANYHIT, an invisible instance.  Hit records and occlusion flags equal the oracle's
+    (semantics pinned on hand-made cases in tests/test_oracle_flags.py)."""
+    from optix_raytracer_b200 import host
+    rng = np.random.default_rng(23)
+    n = 2500
+    c = rng.random((n, 1, 3), dtype=np.float32) * 2 - 1
+    tris = (c + (rng.random((n, 3, 3), dtype=np.float32) - 0.5) * 0.25).astype(np.float32)
+    sbt = (rng.random(n) < 0.5).astype(np.uint32)
+    rec_flags = [1, 4]  # record 0: DISABLE_ANYHIT; record 1: any-hit enabled + DISABLE_TRIANGLE_FACE_CULLING
+    gas = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12, sbt_index=ctx.to_device(sbt), num_sbt=2,
+                                              flags=rec_flags)])
+    tri_flags = np.array(rec_flags, np.uint8)[sbt]
+
+    def xf(angle, scale, t):
+        ca, sa = np.cos(angle), np.sin(angle)
+        return np.array([[ca * scale, 0, sa * scale, t[0]], [0, scale, 0, t[1]], [-sa * scale, 0, ca * scale, t[2]]], np.float32).reshape(12)
+    xfs = [xf(0.0, 1.0, (0, 0, 0)), xf(0.9, 0.8, (1.0, 0.3, 0)), xf(-0.6, 1.2, (-1, -0.4, 1)), xf(1.7, 0.9, (0.4, 0.6, 0.2)), xf(0.2, 1.5, (0, 1.5, 0)),
+           xf(2.5, 1.1, (0.5, -1, -0.5)), xf(0.1, 4.0, (0, 0, 0))]
+    iflags = [0, 1, 2, 4, 8, 2 | 8, 0]
+    masks = [1, 1, 1, 1, 1, 255, 0]
+    ias = ctx.build_accel([ctx.instance_input([(m, 0, gas, k, f) for m, f, k in zip(xfs, iflags, masks)])], compact=False)
+    scene_gas = orc.Scene(tris, sbt, geom_flags=tri_flags)
+    scene_ias = orc.Scene(tris, sbt, instances=[(m, f, k) for m, f, k in zip(xfs, iflags, masks)], geom_flags=tri_flags)
+    rays = common.random_rays(rng, 30_000, [-3, -3, -3], [3, 4, 3])
+    rays_any = rays.copy()
+    rays_any[:, 7] = rng.random(rays.shape[0], dtype=np.float32) * 5
+    d_rays, d_rays_any = ctx.to_device(rays), ctx.to_device(rays_any)
+    seen = set()
+    for rf in (0, 16, 32, 48, 64, 128, 1 | 64, 2 | 64, 1 | 128, 2 | 128, 16 | 64, 32 | 128 | 2, 1, 2):
+        for accel, scene, what in ((gas, scene_gas, "gas"), (ias, scene_ias, "ias")):
+            got = host.ext_hits_to_numpy(ctx.trace_closest(accel, d_rays, ray_flags=rf))
+            ref = scene.trace(rays, ray_flags=rf)
+            _assert_hits_equal(got, ref, f"{what} ray_flags {rf:#x}")
+            occ = ctx.trace_any(accel, d_rays_any, ray_flags=rf | 4).cpu().numpy().astype(bool)
+            assert np.array_equal(occ, scene.trace(rays_any, any_hit=True, ray_flags=rf)["occluded"]), f"{what} occlusion, ray_flags {rf:#x}"
+            seen.add((what, rf, int((ref["t"] >= 0).sum())))
+    # the flags do something: the hit counts differ between the settings, and the invisible instance is never reported
+    assert len({c for w, rf, c in seen if w == "ias"}) >= 6
+    assert not np.any(scene_ias.trace(rays)["inst"][scene_ias.trace(rays)["t"] >= 0] == 6)
+
+
 @pytest.mark.parametrize("node_format", ["q8", "f32"])
 def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc, node_format, monkeypatch):
     """The procedural scene of BASELINE.json configs[4]: device generator == oracle restatement bit for bit,
