@@ -616,14 +616,18 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
     // conservative padding: 2^-16 of the largest extent on every side (covers the rounding of the
     // slab arithmetic in traverse.cuh; see DESIGN.md "why box tests never cull a true hit")
     const float maxext = fmaxf(fmaxf(Hi.x - Lo.x, Hi.y - Lo.y), Hi.z - Lo.z);
+    // The pad is applied with directed rounding: far from the origin it is smaller than the spacing of the coordinates (extent 4 at 1e6:
+    // pad 6e-5 against an ulp of 0.0625) and a round-to-nearest `hi + pad` would hand back `hi` — an unpadded box, which the slab test
+    // with clamped zero direction components rejects for a ray lying exactly in one of its face planes.  Rounded outwards, every box
+    // grows by at least one ulp on every side.
     const float pad = fmaxf(maxext * 1.52587890625e-5f, 1e-30f);
-    const float3 P = f3(Lo.x - pad, Lo.y - pad, Lo.z - pad);
+    const float3 P = f3(__fsub_rd(Lo.x, pad), __fsub_rd(Lo.y, pad), __fsub_rd(Lo.z, pad));
     // grid exponent per axis: smallest e with 255 * 2^e >= padded extent
     uint32_t eb[3];
     float scale[3];
-    const float ext3[3] = {(Hi.x + pad) - P.x, (Hi.y + pad) - P.y, (Hi.z + pad) - P.z};
     const float Pa[3] = {P.x, P.y, P.z};
-    const float Ha[3] = {Hi.x + pad, Hi.y + pad, Hi.z + pad};
+    const float Ha[3] = {__fadd_ru(Hi.x, pad), __fadd_ru(Hi.y, pad), __fadd_ru(Hi.z, pad)};
+    const float ext3[3] = {__fsub_ru(Ha[0], P.x), __fsub_ru(Ha[1], P.y), __fsub_ru(Ha[2], P.z)};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const float v = ext3[a] * (1.0000002f / 255.0f);
@@ -663,8 +667,8 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
         for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; flo[a][s] = 0.0f; fhi[a][s] = 0.0f; }
         if (k < 0) continue;
         const int id = ids[k];
-        const float lo3[3] = {clo[k].x - pad, clo[k].y - pad, clo[k].z - pad};
-        const float hi3[3] = {chi[k].x + pad, chi[k].y + pad, chi[k].z + pad};
+        const float lo3[3] = {__fsub_rd(clo[k].x, pad), __fsub_rd(clo[k].y, pad), __fsub_rd(clo[k].z, pad)};
+        const float hi3[3] = {__fadd_ru(chi[k].x, pad), __fadd_ru(chi[k].y, pad), __fadd_ru(chi[k].z, pad)};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             if (node_bytes == NODE8F_BYTES) {

@@ -115,10 +115,11 @@ __device__ __forceinline__ bool ray_reaches_bounds(const AccelHeader* __restrict
     const float bz = fabsf(d.z) < DIR_EPS ? copysignf(DIR_EPS, d.z) : d.z;
     const float idx = fdiv(1.0f, bx), idy = fdiv(1.0f, by), idz = fdiv(1.0f, bz);
     const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
+    // padded with directed rounding: far from the origin the pad is below the spacing of the coordinates and must still move the plane
     const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 6.103515625e-05f;
-    const float ax = ((lx - pad) - o.x) * idx, cx = ((hx + pad) - o.x) * idx;
-    const float ay = ((ly - pad) - o.y) * idy, cy = ((hy + pad) - o.y) * idy;
-    const float az = ((lz - pad) - o.z) * idz, cz = ((hz + pad) - o.z) * idz;
+    const float ax = (__fsub_rd(lx, pad) - o.x) * idx, cx = (__fadd_ru(hx, pad) - o.x) * idx;
+    const float ay = (__fsub_rd(ly, pad) - o.y) * idy, cy = (__fadd_ru(hy, pad) - o.y) * idy;
+    const float az = (__fsub_rd(lz, pad) - o.z) * idz, cz = (__fadd_ru(hz, pad) - o.z) * idz;
     const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
     const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), tmax));
     return tn <= tf * BOX_SLACK;
@@ -140,9 +141,9 @@ __device__ __forceinline__ bool trav_begin(Trav& s, float* __restrict__ my_ray, 
     if (BOUNDS) {
         const float lx = gas->bounds[0], ly = gas->bounds[1], lz = gas->bounds[2], hx = gas->bounds[3], hy = gas->bounds[4], hz = gas->bounds[5];
         const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 1.52587890625e-05f;
-        const float ax = ((lx - pad) - o.x) * s.idx, cx = ((hx + pad) - o.x) * s.idx;
-        const float ay = ((ly - pad) - o.y) * s.idy, cy = ((hy + pad) - o.y) * s.idy;
-        const float az = ((lz - pad) - o.z) * s.idz, cz = ((hz + pad) - o.z) * s.idz;
+        const float ax = (__fsub_rd(lx, pad) - o.x) * s.idx, cx = (__fadd_ru(hx, pad) - o.x) * s.idx;
+        const float ay = (__fsub_rd(ly, pad) - o.y) * s.idy, cy = (__fadd_ru(hy, pad) - o.y) * s.idy;
+        const float az = (__fsub_rd(lz, pad) - o.z) * s.idz, cz = (__fadd_ru(hz, pad) - o.z) * s.idz;
         const float tn = fmaxf(fmaxf(fminf(ax, cx), fminf(ay, cy)), fmaxf(fminf(az, cz), tmin));
         const float tf = fminf(fminf(fmaxf(ax, cx), fmaxf(ay, cy)), fminf(fmaxf(az, cz), s.best.t));
         if (!(tn <= tf * BOX_SLACK)) return false;

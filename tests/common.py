@@ -83,6 +83,52 @@ def random_rays(rng, n, lo, hi, tmin=0.0, tmax=1e16):
     return rays
 
 
+def edge_case_scene(seed=23):
+    """Triangles and rays of test_edge_case_rays_and_geometry_vs_oracle (tests/test_gpu_parity.py): a coplanar grid with shared edges,
+    a fan of slivers, a small grid a million units from the origin; rays at vertices, edge midpoints, along diagonals, in the plane of
+    the grid, with degenerate intervals, plus random ones."""
+    rng = np.random.default_rng(seed)
+    G = 24
+    xs = np.arange(G + 1, dtype=np.float32) * np.float32(0.25)
+    tris = []
+    for i in range(G):          # coplanar grid at z = 1, two triangles per cell, shared edges everywhere
+        for j in range(G):
+            a, b, c, d = (xs[i], xs[j], 1), (xs[i + 1], xs[j], 1), (xs[i + 1], xs[j + 1], 1), (xs[i], xs[j + 1], 1)
+            tris += [[a, b, c], [a, c, d]]
+    fan_c = (3.0, 3.0, 2.0)      # fan of slivers around one vertex
+    for k in range(64):
+        a0, a1 = 2 * np.pi * k / 64, 2 * np.pi * (k + 1) / 64
+        tris.append([fan_c, (3 + 2 * np.cos(a0), 3 + 2 * np.sin(a0), 2.0 + 1e-3 * k), (3 + 2 * np.cos(a1), 3 + 2 * np.sin(a1), 2.0 + 1e-3 * (k + 1))])
+    far = np.float32(1.0e6)      # the same little grid a million units away (coarse float spacing: 0.0625)
+    for i in range(4):
+        for j in range(4):
+            a, b, c, d = (far + i, far + j, far), (far + i + 1, far + j, far), (far + i + 1, far + j + 1, far), (far + i, far + j + 1, far)
+            tris += [[a, b, c], [a, c, d]]
+    tris = np.asarray(tris, np.float32)
+    rays = []
+    for i in range(G + 1):       # straight down at every grid vertex, and at edge midpoints
+        for j in range(G + 1):
+            rays.append([xs[i], xs[j], 5, 0, 0, 0, -1, 100])
+            if i < G:
+                rays.append([(xs[i] + xs[i + 1]) / 2, xs[j], 5, 0, 0, 0, -1, 100])
+            if i < G and j < G:  # along the cell diagonal (the edge shared by the two triangles of a cell), obliquely
+                rays.append([xs[i] + 0.125, xs[j] + 0.125, 5, 0, 0.25, 0.25, -1, 100])
+    for k in range(2000):        # rays lying in the plane z = 1 (parallel to the grid), and axis-parallel ones through the fan
+        y = np.float32(rng.random() * 6)
+        rays.append([-1, y, 1, 0, 1, 0, 0, 100])
+        rays.append([3, 3, -1, 0, 0, 0, 1, 100])
+        rays.append([np.float32(rng.random() * 6), y, 3, 0, 0, 0, -1, np.inf])
+    rays += [[1, 1, 5, 0, 0, 0, -1, 4.0], [1, 1, 5, 4.0, 0, 0, -1, 4.0], [1, 1, 5, 4.5, 0, 0, -1, 4.0], [1, 1, 5, 0, 0, 0, -1, -1.0],
+             [1, 1, 1, 0, 0, 0, -1, 100], [1, 1, 1, 0, 0, 0, 1, 100], [0.3, 0.3, 1, 0, 1, 1, 0, 100]]
+    for i in range(5):           # at the far grid: vertices, edges, interior
+        for j in range(5):
+            rays.append([far + i, far + j, far + 10, 0, 0, 0, -1, 100])
+            rays.append([far + i + 0.5, far + j + 0.25, far + 10, 0, 0, 0, -1, 100])
+    rnd = random_rays(rng, 20000, [-1, -1, 0], [7, 7, 4])
+    rays = np.concatenate([np.asarray(rays, np.float32), rnd]).astype(np.float32)
+    return tris, rays
+
+
 def decode_gas(blob):
     """Decode a GAS blob (optix_raytracer_b200/csrc/accel.h) downloaded from the device into numpy views."""
     hdr = np.frombuffer(blob[:128].tobytes(), dtype=np.uint32)

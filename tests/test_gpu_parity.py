@@ -156,53 +156,40 @@ def test_edge_case_rays_and_geometry_vs_oracle(ctx, orc, hierarchy, monkeypatch)
     fan sharing one vertex.  Hit records and occlusion flags must equal the oracle's bit for bit."""
     from optix_raytracer_b200 import host
     monkeypatch.setenv("B200RT_HIERARCHY", hierarchy)
-    rng = np.random.default_rng(23)
-    G = 24
-    xs = np.arange(G + 1, dtype=np.float32) * np.float32(0.25)
-    tris = []
-    for i in range(G):          # coplanar grid at z = 1, two triangles per cell, shared edges everywhere
-        for j in range(G):
-            a, b, c, d = (xs[i], xs[j], 1), (xs[i + 1], xs[j], 1), (xs[i + 1], xs[j + 1], 1), (xs[i], xs[j + 1], 1)
-            tris += [[a, b, c], [a, c, d]]
-    fan_c = (3.0, 3.0, 2.0)      # fan of slivers around one vertex
-    for k in range(64):
-        a0, a1 = 2 * np.pi * k / 64, 2 * np.pi * (k + 1) / 64
-        tris.append([fan_c, (3 + 2 * np.cos(a0), 3 + 2 * np.sin(a0), 2.0 + 1e-3 * k), (3 + 2 * np.cos(a1), 3 + 2 * np.sin(a1), 2.0 + 1e-3 * (k + 1))])
-    far = np.float32(1.0e6)      # the same little grid a million units away (coarse float spacing: 0.0625)
-    for i in range(4):
-        for j in range(4):
-            a, b, c, d = (far + i, far + j, far), (far + i + 1, far + j, far), (far + i + 1, far + j + 1, far), (far + i, far + j + 1, far)
-            tris += [[a, b, c], [a, c, d]]
-    tris = np.asarray(tris, np.float32)
+    tris, rays = common.edge_case_scene()
     accel = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
     scene = orc.Scene(tris)
-    rays = []
-    for i in range(G + 1):       # straight down at every grid vertex, and at edge midpoints
-        for j in range(G + 1):
-            rays.append([xs[i], xs[j], 5, 0, 0, 0, -1, 100])
-            if i < G:
-                rays.append([(xs[i] + xs[i + 1]) / 2, xs[j], 5, 0, 0, 0, -1, 100])
-            if i < G and j < G:  # along the cell diagonal (the edge shared by the two triangles of a cell), obliquely
-                rays.append([xs[i] + 0.125, xs[j] + 0.125, 5, 0, 0.25, 0.25, -1, 100])
-    for k in range(2000):        # rays lying in the plane z = 1 (parallel to the grid), and axis-parallel ones through the fan
-        y = np.float32(rng.random() * 6)
-        rays.append([-1, y, 1, 0, 1, 0, 0, 100])
-        rays.append([3, 3, -1, 0, 0, 0, 1, 100])
-        rays.append([np.float32(rng.random() * 6), y, 3, 0, 0, 0, -1, np.inf])
-    rays += [[1, 1, 5, 0, 0, 0, -1, 4.0], [1, 1, 5, 4.0, 0, 0, -1, 4.0], [1, 1, 5, 4.5, 0, 0, -1, 4.0], [1, 1, 5, 0, 0, 0, -1, -1.0],
-             [1, 1, 1, 0, 0, 0, -1, 100], [1, 1, 1, 0, 0, 0, 1, 100], [0.3, 0.3, 1, 0, 1, 1, 0, 100]]
-    for i in range(5):           # at the far grid: vertices, edges, interior
-        for j in range(5):
-            rays.append([far + i, far + j, far + 10, 0, 0, 0, -1, 100])
-            rays.append([far + i + 0.5, far + j + 0.25, far + 10, 0, 0, 0, -1, 100])
-    rnd = common.random_rays(rng, 20000, [-1, -1, 0], [7, 7, 4])
-    rays = np.concatenate([np.asarray(rays, np.float32), rnd]).astype(np.float32)
     got = host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays)))
     ref = scene.trace(rays)
     assert (ref["t"] >= 0).sum() > 2000
     _assert_hits_equal(got, ref, "edge cases")
     occ = ctx.trace_any(accel, ctx.to_device(rays)).cpu().numpy().astype(bool)
     assert np.array_equal(occ, scene.trace(rays, any_hit=True)["occluded"])
+
+
+@pytest.mark.parametrize("node_format", ["q8", "f32"])
+def test_scene_far_from_origin_vs_oracle(ctx, orc, node_format, monkeypatch):
+    """A scene that lives only a million units from the origin (coordinate spacing 0.0625, extent 4): the padding of the scene bounds
+    and of every child box is below that spacing and has to be applied with outward rounding, or rays lying exactly in a face plane
+    of a box (grid vertices and edges, zero direction components) are culled.  Both node encodings, straight and IAS-instanced."""
+    from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_NODE_FORMAT", node_format)
+    tris, rays = common.edge_case_scene()
+    tris = tris[1216:]
+    far = rays[np.abs(rays[:, 0]) > 1e5]
+    assert tris.shape[0] == 32 and far.shape[0] == 50
+    rng = np.random.default_rng(3)
+    rnd = common.random_rays(rng, 5000, [1e6, 1e6, 1e6 - 1], [1e6 + 4, 1e6 + 4, 1e6 + 1])
+    rays = np.concatenate([far, rnd]).astype(np.float32)
+    gas = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    ias = ctx.build_accel([ctx.instance_input([(ident, 0, gas)])], compact=False)
+    for accel, scene, what in ((gas, orc.Scene(tris), "gas"), (ias, orc.Scene(tris, None, instances=[ident]), "ias")):
+        ref = scene.trace(rays)
+        assert (ref["t"][:50] >= 0).sum() >= 40 and (ref["t"] >= 0).sum() > 500
+        _assert_hits_equal(host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays))), ref, f"far scene {what}")
+        occ = ctx.trace_any(accel, ctx.to_device(rays)).cpu().numpy().astype(bool)
+        assert np.array_equal(occ, scene.trace(rays, any_hit=True)["occluded"])
 
 
 def test_multi_instance_ias_vs_oracle(ctx, orc):
