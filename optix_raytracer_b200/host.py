@@ -128,6 +128,32 @@ class Context:
         del temp
         return acc
 
+    def time_accel_build(self, build_inputs, reps=2, warm=1):
+        """The "BVH build ms" figure: optixAccelBuild alone (vertices on the device -> traversable ready), CUDA events on the build's
+        stream around the call, temp and output buffers allocated beforehand as the reference does (optixPathTracer.cpp:634-662).
+        Returns the per-build times of the `reps` builds after `warm` untimed ones."""
+        n = len(build_inputs)
+        arr = (L.BuildInput * n)(*build_inputs)
+        opts = L.AccelBuildOptions(L.BUILD_FLAG_ALLOW_COMPACTION, L.BUILD_OPERATION_BUILD)
+        sizes = L.AccelBufferSizes()
+        self._accel_memory_usage(opts, arr, n, sizes)
+        temp = self.empty_bytes(sizes.tempSizeInBytes)
+        out = self.empty_bytes(sizes.outputSizeInBytes)
+        csize = torch.zeros(1, dtype=torch.int64, device=self.torch_device)
+        emit = L.AccelEmitDesc(csize.data_ptr(), L.PROPERTY_TYPE_COMPACTED_SIZE)
+        times = []
+        for k in range(warm + reps):
+            handle = C.c_uint64()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._accel_build(opts, arr, n, temp.data_ptr(), sizes.tempSizeInBytes, out.data_ptr(), sizes.outputSizeInBytes, handle, emit)
+            e1.record()
+            torch.cuda.synchronize(self.torch_device)
+            if k >= warm:
+                times.append(e0.elapsed_time(e1))
+        del temp, out
+        return times
+
     # ---- launches (the optixLaunch replacements) and SBT headers --------------------------------------
     def prepare_programs(self, kind):
         """kind: 'pathtracer' | 'multigpu' | 'raycast'.  Nothing to do here: the device programs are compiled into
@@ -337,6 +363,7 @@ class PathTracer:
         nmat = len(sc["emission_colors"])
         # buildMeshAccel (optixPathTracer.cpp:576-684): stride-16 float3 vertices, per-primitive u32 SBT index
         bi = ctx.triangle_input(vertices, sbt_index=mat_indices, num_sbt=nmat, vertex_stride=16)
+        self.build_input = bi
         self.accel = ctx.build_accel([bi], compact=compact)
         # createSBT (optixPathTracer.cpp:829-898 / optixMultiGPU.cpp:960-1018)
         self.multigpu = multigpu
