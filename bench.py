@@ -244,6 +244,15 @@ def run_b200rt(a, rank, world, local_rank):
             gathered = torch.empty((world, n_local, 4), dtype=torch.float32, device=dev)
             full_accum = torch.empty((a.height, a.width, 4), dtype=torch.float32, device=dev)
             full_frame = torch.empty((a.height, a.width, 4), dtype=torch.uint8, device=dev)
+    islands = None
+    if world > 1 and rank == 0:
+        # optixNVLink's topology report (optixNVLink.cpp:1698-1825): which devices reach each other's memory over NVLink
+        try:
+            from optix_raytracer_b200 import topology
+            islands = topology.format_islands(topology.compute_p2p_islands(topology.find_peers(world)))
+            print(islands, file=sys.stderr)
+        except Exception as e:  # noqa: BLE001
+            islands = f"unavailable ({e})"
     h_frame = torch.empty((a.height, a.width, 4), dtype=torch.uint8).pin_memory()
     stats_mask = L.PT_STATS_SEGMENTS
 
@@ -376,7 +385,7 @@ def run_b200rt(a, rank, world, local_rank):
                                             "p2p": ", one result buffer in rank 0's HBM written by every rank's launch over NVLink (no collective)"}[exchange],
                           "l2": ("inputs larger than L2: accel %.2f GB vs L2 %.0f MB" % (scene_bytes / 1e9, l2_bytes / 1e6)) if flush is None
                                 else "L2 flushed between timed steps (1.5x L2 fill)",
-                          "bvh_build_ms": accel_build_ms, "scene_setup_cold_ms": build_ms, "segments_per_step": segs_total / a.steps},
+                          "bvh_build_ms": accel_build_ms, "scene_setup_cold_ms": build_ms, **({"p2p_islands": islands} if islands else {}), "segments_per_step": segs_total / a.steps},
                "samples_per_sec_per_gpu": a.width * a.height * a.spl * a.steps / (t_ms * 1e-3) / world,
                "wall_ms_per_step": wall_ms / a.steps,
                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(pt.params), "d2h_bytes_per_step": a.width * a.height * 4,

@@ -991,6 +991,9 @@ class SharedResultBuffer:
 
 
 # ---- output and model ingest either side of the path ---------------------------------------------------------
+from .scene_io import load_exr, load_nbt, read_nbt, save_exr, save_nbt  # noqa: E402,F401  (NBT models, EXR output: no GPU involved)
+
+
 def _to_srgb_u8(f):
     """toSRGB + the 256-scale quantisation of sutil::saveImage's float branches (SDK/sutil/sutil.cpp:585-618, SDK/cuda/helpers.h:36-48)."""
     f = np.asarray(f, np.float32)
@@ -1002,7 +1005,7 @@ def _to_srgb_u8(f):
 
 
 def save_image(path, image, disable_srgb_conversion=False):
-    """sutil::saveImage (SDK/sutil/sutil.cpp:542-709) for .ppm / .png: `image` is a (h, w, 4) uint8 frame (written as is), or a (h, w, 3|4)
+    """sutil::saveImage (SDK/sutil/sutil.cpp:542-709) for .ppm / .png / .exr (scene_io.save_exr): `image` is a (h, w, 4) uint8 frame (written as is), or a (h, w, 3|4)
     float32 buffer (sRGB-converted unless disabled, 256-scaled, clamped).  Rows are flipped: the launch index (0, 0) is the bottom-left
     pixel of the picture.  PPM is the binary P6 the reference writes; PNG keeps the alpha of a uchar4 frame like stbi_write_png(…, 4, …)."""
     if hasattr(image, "cpu"):
@@ -1014,6 +1017,14 @@ def save_image(path, image, disable_srgb_conversion=False):
     if len(path) < 5:
         raise ValueError("sutil::saveImage(): Failed to determine filename extension")
     ext = path[-3:].lower()
+    if ext == "exr":
+        # SDK/sutil/sutil.cpp:660-702: float3 / float4 buffers go to tinyexr as they are (linear, fp16, buffer row order)
+        if a.dtype == np.uint8:
+            raise ValueError("sutil::saveImage(): saving of uchar4 images to EXR not implemented yet")
+        if a.dtype != np.float32:
+            raise ValueError("sutil::saveImage: Unrecognized image buffer pixel format.")
+        save_exr(path, a)
+        return
     if a.dtype == np.uint8:
         if a.shape[2] != 4:
             raise ValueError("sutil::saveImage(): Unrecognized image buffer pixel format.")

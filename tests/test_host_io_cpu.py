@@ -37,7 +37,7 @@ def test_save_image_png_round_trip_and_errors(tmp_path):
     host.save_image(tmp_path / "f.png", frame)
     back = np.array(Image.open(tmp_path / "f.png"))
     assert np.array_equal(back, frame[::-1])
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="uchar4 images to EXR"):
         host.save_image(tmp_path / "f.exr", frame)
     with pytest.raises(ValueError):
         host.save_image(tmp_path / "g.ppm", np.zeros((2, 2), np.uint8))
@@ -53,3 +53,65 @@ def test_obj_loader_has_the_layout_and_the_floor_of_load_assimp(tmp_path):
     assert (m[:2] == 0).all() and (m[2:] == 26).all()
     assert np.allclose(v[6:, 1], 0.5) and np.array_equal(n[6:], np.tile(np.array([[0, 1, 0]], np.float32), (2400, 1)))
     assert np.allclose(v[6], [-1.0, 0.5, -1.0]) and np.allclose(v[-1], [1.0, 0.5, 1.0])
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 3), (40, 33, 4), (16, 16, 4)])
+def test_save_image_exr_round_trip(tmp_path, shape):
+    """EXR branch of sutil::saveImage (SDK/sutil/sutil.cpp:660-702): fp16 channels in alphabetical order, ZIP blocks of 16 lines from
+    16 x 16 on, rows in buffer order, values linear."""
+    rng = np.random.default_rng(1)
+    acc = (rng.random(shape, dtype=np.float32) * 4).astype(np.float32)
+    acc[0, 0, :3] = (0.0, 1.0, 65504.0)
+    p = tmp_path / "a.exr"
+    host.save_image(p, acc)
+    raw = p.read_bytes()
+    assert raw[:8] == (20000630).to_bytes(4, "little") + (2).to_bytes(4, "little")
+    names = [b"A", b"B", b"G", b"R"] if shape[2] == 4 else [b"B", b"G", b"R"]
+    pos = [raw.index(b"channels\0chlist\0") + 20]
+    assert raw[pos[0]:pos[0] + 1] == names[0] and b"compression\0compression\0\x01\0\0\0" + bytes([3 if min(shape[:2]) >= 16 else 0]) in raw
+    back = host.load_exr(p)
+    assert sorted(back) == sorted(n.decode() for n in names)
+    for k, c in enumerate("RGBA"[:shape[2]]):
+        assert np.array_equal(back[c], acc[..., k].astype(np.float16).astype(np.float32)), c
+
+
+def test_nbt_model_round_trip_and_layout(tmp_path):
+    """imgui_test's load_nbt (SDK/imgui_test/triangle_gas.cpp:16-76): meshes in file order, little-endian float triplets inside big-endian NBT
+    byte arrays, one material index per vertex; gzip-wrapped or raw."""
+    rng = np.random.default_rng(2)
+    a_v, a_n = rng.random((6, 3), dtype=np.float32), rng.random((6, 3), dtype=np.float32)
+    b_v, b_n = rng.random((3, 3), dtype=np.float32) - 2, rng.random((3, 3), dtype=np.float32)
+    for compress in (True, False):
+        p = tmp_path / f"m{int(compress)}.nbt"
+        host.save_nbt(p, {"blob": (a_v, a_n), "floor": (b_v, b_n)}, compress=compress)
+        assert (p.read_bytes()[:2] == b"\x1f\x8b") == compress
+        v, n, m = host.load_nbt(p)
+        assert np.array_equal(v, np.concatenate([a_v, b_v])) and np.array_equal(n, np.concatenate([a_n, b_n]))
+        assert m.shape == (9,) and m.dtype == np.int32 and not m.any()
+    raw = (tmp_path / "m0.nbt").read_bytes()
+    # root compound, empty name; first child: compound "blob"; its first entry: byte array "vertices" of 72 bytes, big-endian length
+    assert raw[:3] == b"\x0a\x00\x00" and raw[3:10] == b"\x0a\x00\x04blob" and raw[10:25] == b"\x07\x00\x08vertices\x00\x00\x00\x48"
+    assert np.array_equal(np.frombuffer(raw[25:37], "<f4"), a_v[0])
+    with pytest.raises(RuntimeError, match="can't find file"):
+        host.load_nbt(tmp_path / "missing.nbt")
+    bad = tmp_path / "bad.nbt"
+    bad.write_bytes(b"\x01\x00\x00\x05")
+    with pytest.raises(ValueError):
+        host.load_nbt(bad)
+
+
+def test_exr_is_read_by_an_independent_decoder(tmp_path, monkeypatch):
+    """The file save_exr writes, decoded by OpenCV's OpenEXR reader (not by this repo's load_exr)."""
+    import os
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for shape in [(40, 33, 4), (5, 7, 3)]:
+        acc = (rng.random(shape, dtype=np.float32) * 4).astype(np.float32)
+        p = str(tmp_path / "x.exr")
+        host.save_image(p, acc)
+        img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if img is None:
+            pytest.skip("this OpenCV build has no OpenEXR codec")
+        got = img[..., [2, 1, 0, 3]] if shape[2] == 4 else img[..., ::-1]
+        assert np.array_equal(got, acc.astype(np.float16).astype(np.float32))
