@@ -55,11 +55,28 @@ extern "C" {
 #define B200RT_BUILD_OPERATION_BUILD 0x2161
 #define B200RT_PROPERTY_TYPE_COMPACTED_SIZE 0x2181
 #define B200RT_BUILD_FLAG_ALLOW_COMPACTION (1u << 1)
-/* ray flags, reference include/optix_types.h:1794-1840 */
+/* ray flags, reference include/optix_types.h:1794-1840 (same values).  Precedence of the any-hit state of a triangle, as documented
+ * there: ray flags (DISABLE / ENFORCE_ANYHIT) over instance flags over the geometry flag of its SBT record. */
 #define B200RT_RAY_FLAG_NONE 0u
+#define B200RT_RAY_FLAG_DISABLE_ANYHIT (1u << 0)
+#define B200RT_RAY_FLAG_ENFORCE_ANYHIT (1u << 1)
 #define B200RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT (1u << 2)
+#define B200RT_RAY_FLAG_DISABLE_CLOSESTHIT (1u << 3)
 #define B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES (1u << 4)
 #define B200RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES (1u << 5)
+#define B200RT_RAY_FLAG_CULL_DISABLED_ANYHIT (1u << 6)
+#define B200RT_RAY_FLAG_CULL_ENFORCED_ANYHIT (1u << 7)
+/* instance flags (b200rt_instance.flags), reference include/optix_types.h:1088-1115 */
+#define B200RT_INSTANCE_FLAG_NONE 0u
+#define B200RT_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING (1u << 0)
+#define B200RT_INSTANCE_FLAG_FLIP_TRIANGLE_FACING (1u << 1)
+#define B200RT_INSTANCE_FLAG_DISABLE_ANYHIT (1u << 2)
+#define B200RT_INSTANCE_FLAG_ENFORCE_ANYHIT (1u << 3)
+/* geometry flags (b200rt triangle input, one per SBT record), reference include/optix_types.h:311-325 */
+#define B200RT_GEOMETRY_FLAG_NONE 0u
+#define B200RT_GEOMETRY_FLAG_DISABLE_ANYHIT (1u << 0)
+#define B200RT_GEOMETRY_FLAG_REQUIRE_SINGLE_ANYHIT_CALL (1u << 1)
+#define B200RT_GEOMETRY_FLAG_DISABLE_TRIANGLE_FACE_CULLING (1u << 2)
 
 typedef struct b200rt_context_t* b200rt_context;
 typedef uint64_t b200rt_deviceptr;         /* CUdeviceptr */
