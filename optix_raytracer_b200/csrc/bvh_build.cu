@@ -155,13 +155,16 @@ __global__ void init_bounds_kernel(uint32_t* b)
     else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
 }
 
+// One thread per triangle, grid-stride over a persistent grid: the scene bounds are reduced in registers over all the triangles a
+// thread sees, then per warp, then per block, and only then go to the six global words — one atomic per warp and word (1.5 M warps
+// hitting six addresses of one L2 slice for 50 M triangles) used to be most of this kernel's time.  Vertex records of 16 bytes (the
+// samples' float4 / Vertex{x, y, z, pad}) are read with one 128-bit load each.
 __global__ void __launch_bounds__(256) gather_tris_kernel(const DevInput* __restrict__ inputs, int num_inputs, uint32_t ntris,
                                                            const uint32_t* __restrict__ geom_flags, float4* __restrict__ tri_tmp,
                                                            uint32_t* __restrict__ bounds)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (g < ntris) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ntris; g += gridDim.x * blockDim.x) {
         int k = 0;
         while (k + 1 < num_inputs && g >= inputs[k + 1].tri_start) ++k;
         const DevInput in = inputs[k];
@@ -176,10 +179,18 @@ __global__ void __launch_bounds__(256) gather_tris_kernel(const DevInput* __rest
         } else {
             i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2;
         }
-        const float* a = (const float*)(in.verts + (size_t)i0 * in.vstride);
-        const float* b = (const float*)(in.verts + (size_t)i1 * in.vstride);
-        const float* c = (const float*)(in.verts + (size_t)i2 * in.vstride);
-        float3 v0 = f3(a[0], a[1], a[2]), v1 = f3(b[0], b[1], b[2]), v2 = f3(c[0], c[1], c[2]);
+        float3 v0, v1, v2;
+        if ((((uintptr_t)in.verts | (uintptr_t)in.vstride) & 15u) == 0u) {
+            const float4 a = __ldg((const float4*)(in.verts + (size_t)i0 * in.vstride));
+            const float4 b = __ldg((const float4*)(in.verts + (size_t)i1 * in.vstride));
+            const float4 c = __ldg((const float4*)(in.verts + (size_t)i2 * in.vstride));
+            v0 = f3(a.x, a.y, a.z); v1 = f3(b.x, b.y, b.z); v2 = f3(c.x, c.y, c.z);
+        } else {
+            const float* a = (const float*)(in.verts + (size_t)i0 * in.vstride);
+            const float* b = (const float*)(in.verts + (size_t)i1 * in.vstride);
+            const float* c = (const float*)(in.verts + (size_t)i2 * in.vstride);
+            v0 = f3(a[0], a[1], a[2]); v1 = f3(b[0], b[1], b[2]); v2 = f3(c[0], c[1], c[2]);
+        }
         if (in.xform) {
             v0 = xform_point(in.xform, v0);
             v1 = xform_point(in.xform, v1);
@@ -196,10 +207,12 @@ __global__ void __launch_bounds__(256) gather_tris_kernel(const DevInput* __rest
         tri_tmp[3 * (size_t)g + 0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(in.prim_offset + p));
         tri_tmp[3 * (size_t)g + 1] = make_float4(v1.x, v1.y, v1.z, __uint_as_float(sbt));
         tri_tmp[3 * (size_t)g + 2] = make_float4(v2.x, v2.y, v2.z, __uint_as_float(g));
-        lo[0] = fminf(v0.x, fminf(v1.x, v2.x)); hi[0] = fmaxf(v0.x, fmaxf(v1.x, v2.x));
-        lo[1] = fminf(v0.y, fminf(v1.y, v2.y)); hi[1] = fmaxf(v0.y, fmaxf(v1.y, v2.y));
-        lo[2] = fminf(v0.z, fminf(v1.z, v2.z)); hi[2] = fmaxf(v0.z, fmaxf(v1.z, v2.z));
+        lo[0] = fminf(lo[0], fminf(v0.x, fminf(v1.x, v2.x))); hi[0] = fmaxf(hi[0], fmaxf(v0.x, fmaxf(v1.x, v2.x)));
+        lo[1] = fminf(lo[1], fminf(v0.y, fminf(v1.y, v2.y))); hi[1] = fmaxf(hi[1], fmaxf(v0.y, fmaxf(v1.y, v2.y)));
+        lo[2] = fminf(lo[2], fminf(v0.z, fminf(v1.z, v2.z))); hi[2] = fmaxf(hi[2], fmaxf(v0.z, fmaxf(v1.z, v2.z)));
     }
+    __shared__ float sh_lo[3][8], sh_hi[3][8];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         float l = lo[a], h = hi[a];
@@ -208,7 +221,14 @@ __global__ void __launch_bounds__(256) gather_tris_kernel(const DevInput* __rest
             l = fminf(l, __shfl_xor_sync(0xffffffffu, l, off));
             h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, off));
         }
-        if ((threadIdx.x & 31) == 0 && l <= h) {
+        if (lane == 0) { sh_lo[a][wid] = l; sh_hi[a][wid] = h; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = (int)threadIdx.x;
+        float l = sh_lo[a][0], h = sh_hi[a][0];
+        for (int w = 1; w < 8; ++w) { l = fminf(l, sh_lo[a][w]); h = fmaxf(h, sh_hi[a][w]); }
+        if (l <= h) {
             atomicMin(&bounds[a], float_to_ordered(l));
             atomicMax(&bounds[3 + a], float_to_ordered(h));
         }
@@ -873,7 +893,9 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.total_sbt = (uint32_t)sbt;
     p.max_nodes = (uint32_t)(2 * n / 3 + 16);
     p.rs_blocks = std::max(1u, div_up(n, RS_TILE));
-    p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 22) ? 16 : 21);
+    // bits per axis of the Morton key = radix passes of the sort (8 bits each): 30 / 48 / 54 / 63 bits -> 4 / 6 / 7 / 8 passes.  2^18 cells
+    // per axis separate the centroids of 10^8 triangles as well as 2^21 do; the eighth pass is for inputs beyond that.
+    p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 22) ? 16 : (n < (1u << 27) ? 18 : 21));
     const size_t N = std::max<size_t>(n, 1);
     const size_t W = N / 4 + 2;  // widest possible level (every wide node roots >= 4 triangles)
     size_t off = 0;
@@ -1034,7 +1056,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         B2_LAUNCH_CHECK(ctx);
         uint32_t total_nodes = 0, depth = 0;
         if (N > 0) {
-            gather_tris_kernel<<<div_up(N, 256), 256, 0, s>>>((const DevInput*)(T + p.off_inputs), (int)num_inputs, N,
+            gather_tris_kernel<<<persistent_grid(ctx, N, 256, 8), 256, 0, s>>>((const DevInput*)(T + p.off_inputs), (int)num_inputs, N,
                                                               (const uint32_t*)(T + p.off_flags), tri_tmp, d_bounds);
             B2_LAUNCH_CHECK(ctx);
             morton_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, N, d_bounds, p.morton_bits, keys[0], vals[0]);

@@ -49,6 +49,14 @@ struct b200rt_context_t {
 
 namespace b200rt {
 
+// grid of a grid-stride kernel: what the work needs, at most ctas_per_sm resident CTAs on every SM
+inline unsigned persistent_grid(b200rt_context ctx, uint64_t n, int block, int ctas_per_sm)
+{
+    const uint64_t need = (n + block - 1) / block;
+    const uint64_t cap = (uint64_t)ctx->sm_count * ctas_per_sm;
+    return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
 int set_error(b200rt_context ctx, int code, const char* fmt, ...);
 void log_msg(b200rt_context ctx, int level, const char* tag, const char* fmt, ...);
 int ensure_workspace(b200rt_context ctx, size_t bytes, cudaStream_t stream);

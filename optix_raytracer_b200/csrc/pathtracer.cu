@@ -154,18 +154,41 @@ __device__ __forceinline__ bool lane_pixel(const Frame& f, uint32_t lane, int& p
     return !(px > (int)f.width - 1 || py > (int)f.height - 1);  // optixMultiGPU.cu:221-223
 }
 
-__device__ __forceinline__ uint32_t queue_push(unsigned int* queue, unsigned int* count, bool active, uint32_t lane)
+// Append `lane` to up to three queues at once, the slots aggregated over the whole CTA (256 threads): one atomic per CTA and queue instead
+// of one per warp and queue.  With 33-66 M lanes per iteration the per-warp form sends millions of atomics to three words of one L2 slice, which
+// serialises them (B300_MICROARCH.md: ~0.85 cycles per contended atomic): a floor of several milliseconds per launch.  Must be called
+// by every thread of the CTA the same number of times (`iter` = the caller's loop counter; the scratch is double-buffered on its parity).
+template <int NQ>
+__device__ __forceinline__ void queue_push_block(unsigned int* const (&queue)[NQ], unsigned int* const (&count)[NQ], const bool (&active)[NQ],
+                                                 uint32_t lane, uint32_t iter, uint32_t (&idx)[NQ])
 {
-    const uint32_t mask = __ballot_sync(__activemask(), active);
-    if (!active) return 0xffffffffu;
-    const uint32_t lane_id = threadIdx.x & 31;
-    const uint32_t leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane_id == leader) base = atomicAdd(count, __popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    const uint32_t idx = base + __popc(mask & ((1u << lane_id) - 1u));
-    queue[idx] = lane;
-    return idx;
+    __shared__ uint32_t sh_base[2][NQ][8];
+    const uint32_t lane_id = threadIdx.x & 31u, wid = threadIdx.x >> 5, lt = (1u << lane_id) - 1u, par = iter & 1u;
+    uint32_t mask[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        mask[q] = __ballot_sync(0xffffffffu, active[q]);
+        if (lane_id == 0) sh_base[par][q][wid] = (uint32_t)__popc(mask[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        const int q = (int)threadIdx.x;
+        uint32_t pre[8], tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { pre[w] = tot; tot += sh_base[par][q][w]; }
+        unsigned int* c = count[0];
+#pragma unroll
+        for (int j = 1; j < NQ; ++j) c = q == j ? count[j] : c;  // no dynamically indexed pointer array (it would live in local memory)
+        const uint32_t base = tot ? atomicAdd(c, tot) : 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sh_base[par][q][w] = base + pre[w];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        idx[q] = sh_base[par][q][wid] + (uint32_t)__popc(mask[q] & lt);
+        if (active[q]) queue[q][idx[q]] = lane;
+    }
 }
 
 // ---- ray reordering (b200rt_pt_options.ray_sort) ----------------------------------------------------------------------------------
@@ -221,7 +244,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ params, Lanes L, uint32_t nlanes)
 {
     const Frame f = load_frame<MODE>(params, L.groups, L.nlaunch);
-    for (uint32_t base = blockIdx.x * blockDim.x; base < nlanes; base += gridDim.x * blockDim.x) {
+    uint32_t iter = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nlanes; base += gridDim.x * blockDim.x, ++iter) {
         const uint32_t lane = base + threadIdx.x;
         bool active = false;
         if (lane < nlanes) {
@@ -247,8 +271,11 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
                 active = true;
             }
         }
-        queue_push(L.queue[0], &L.counters->qcount[0], active, lane);
-        queue_push(L.ext_list, &L.counters->n_ext[0], active, lane);
+        unsigned int* const qs[2] = {L.queue[0], L.ext_list};
+        unsigned int* const cs[2] = {&L.counters->qcount[0], &L.counters->n_ext[0]};
+        const bool as[2] = {active, active};
+        uint32_t idx[2];
+        queue_push_block<2>(qs, cs, as, lane, iter, idx);
     }
 }
 
@@ -424,7 +451,8 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                                      ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[1],
                                      ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[2]);
     constexpr uint32_t RAY_TYPES = MODE == 0 ? 1u : 2u;  // SBT stride of the radiance trace call
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    uint32_t iter = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x, ++iter) {
         const uint32_t qi = base + threadIdx.x;
         bool keep = false, want_ext = false, want_shd = false;
         float3 key_eo = f3(0.f, 0.f, 0.f), key_ed = key_eo, key_so = key_eo, key_sd = key_eo;  // rays pushed this iteration (ray_sort keys)
@@ -567,9 +595,12 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                 }
             }
         }
-        queue_push(next_queue, next_count, keep, lane);
-        const uint32_t ie = queue_push(L.ext_list, next_ext, want_ext, lane);
-        const uint32_t is = queue_push(L.shd_list, next_shd, want_shd, lane);
+        unsigned int* const qs[3] = {next_queue, L.ext_list, L.shd_list};
+        unsigned int* const cs[3] = {next_count, next_ext, next_shd};
+        const bool as[3] = {keep, want_ext, want_shd};
+        uint32_t idx[3];
+        queue_push_block<3>(qs, cs, as, lane, iter, idx);
+        const uint32_t ie = idx[1], is = idx[2];
         if (L.key_ext) {
             if (want_ext) L.key_ext[ie] = ray_sort_key(f.handle, key_eo, key_ed);
             if (want_shd) L.key_shd[is] = ray_sort_key(f.handle, key_so, key_sd);
@@ -723,12 +754,6 @@ __global__ void __launch_bounds__(256) synth_mesh_kernel(SynthLayout s, uint32_t
 }
 
 // ---- host ------------------------------------------------------------------------------------------
-static unsigned persistent_grid(b200rt_context ctx, uint64_t n, int block, int ctas_per_sm)
-{
-    const uint64_t need = (n + block - 1) / block;
-    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)ctx->sm_count * ctas_per_sm));
-}
-
 template <int MODE>
 static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, uint32_t nlaunch,
                           const b200rt_pt_options* opt)
