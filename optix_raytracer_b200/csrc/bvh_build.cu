@@ -296,12 +296,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// Scatter of one tile.  Ranks come from __match_any_sync within a warp plus per-(warp, digit) counters; the tile is then put in digit
+// order in shared memory and written out by consecutive threads, so that every run of equal digits (16 keys on average for uniformly
+// distributed digits) leaves the SM as whole 32-byte sectors instead of one 8- or 4-byte store per bucket and lane.
+template <typename K>
+constexpr size_t rs_scatter_smem() { return (size_t)RS_TILE * (sizeof(K) + sizeof(uint32_t)); }
+
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                                  K* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n,
                                                                  int shift, const uint32_t* __restrict__ offs, uint32_t nblocks)
 {
+    extern __shared__ __align__(16) unsigned char rs_stage[];
+    K* skeys = (K*)rs_stage;
+    uint32_t* svals = (uint32_t*)(skeys + RS_TILE);
     __shared__ uint32_t wcount[RS_WARPS][256];
+    __shared__ uint32_t dstart[256];  // position of the tile's first key with digit d in the staged tile
+    __shared__ uint32_t gdelta[256];  // global position of that key minus dstart[d] (modulo 2^32)
+    __shared__ uint32_t wsum[RS_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
     __syncthreads();
@@ -324,14 +336,29 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restr
     }
     __syncthreads();
     {
+        // thread d: counts of digit d over the warps -> start of every warp's share; tile totals -> exclusive scan over the digits
         const int d = threadIdx.x;
-        uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const uint32_t c = wcount[w][d];
             wcount[w][d] = run;
             run += c;
         }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) before += w < warp ? wsum[w] : 0u;
+        const uint32_t excl = before + incl - run;
+        dstart[d] = excl;
+        gdelta[d] = offs[(size_t)d * nblocks + blockIdx.x] - excl;
     }
     __syncthreads();
 #pragma unroll
@@ -339,11 +366,28 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restr
         const uint32_t idx = wbase + r * 32 + lane;
         if (idx < n) {
             const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
-            const uint32_t dst = wcount[warp][d] + rank[r];
-            kout[dst] = k[r];
-            vout[dst] = vin[idx];
+            const uint32_t pos = dstart[d] + wcount[warp][d] + rank[r];
+            skeys[pos] = k[r];
+            svals[pos] = vin[idx];
         }
     }
+    __syncthreads();
+    const uint32_t tile_first = blockIdx.x * RS_TILE;
+    const uint32_t tile_n = n - tile_first < (uint32_t)RS_TILE ? n - tile_first : (uint32_t)RS_TILE;
+    for (uint32_t pos = threadIdx.x; pos < tile_n; pos += RS_THREADS) {
+        const K key = skeys[pos];
+        const uint32_t dst = gdelta[(uint32_t)(key >> shift) & 255u] + pos;
+        kout[dst] = key;
+        vout[dst] = svals[pos];
+    }
+}
+
+template <typename K>
+static int rs_scatter_prepare(b200rt_context ctx)
+{
+    // per device function and per device: set on every sort (microseconds), the process may drive several devices
+    B2_CUDA(ctx, cudaFuncSetAttribute(rs_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_scatter_smem<K>()));
+    return 0;
 }
 
 // Stable LSD sort of (32-bit key, 32-bit value) pairs, `passes` digits of 8 bits from bit 0 — the ray reordering of pathtracer.cu.
@@ -356,12 +400,13 @@ int radix_sort_pairs32(b200rt_context ctx, cudaStream_t s, uint32_t* keys[2], ui
 {
     int cur = 0;
     const uint32_t blocks = std::max(1u, div_up(n, RS_TILE));
+    if (int rc = rs_scatter_prepare<uint32_t>(ctx)) return rc;
     for (int pass = 0; pass < passes && n > 1; ++pass) {
         rs_hist_kernel<uint32_t><<<blocks, RS_THREADS, 0, s>>>(keys[cur], n, pass * 8, hist, blocks);
         B2_LAUNCH_CHECK(ctx);
         int rc = exclusive_scan<uint32_t>(ctx, hist, 256 * (size_t)blocks, scan_tmp, s);
         if (rc) return rc;
-        rs_scatter_kernel<uint32_t><<<blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass * 8, hist, blocks);
+        rs_scatter_kernel<uint32_t><<<blocks, RS_THREADS, rs_scatter_smem<uint32_t>(), s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass * 8, hist, blocks);
         B2_LAUNCH_CHECK(ctx);
         cur ^= 1;
     }
@@ -1062,13 +1107,14 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             morton_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, N, d_bounds, p.morton_bits, keys[0], vals[0]);
             B2_LAUNCH_CHECK(ctx);
             int cur = 0;
+            if ((rc = rs_scatter_prepare<uint64_t>(ctx))) return rc;
             const int passes = (3 * p.morton_bits + 7) / 8;
             for (int pass = 0; pass < passes && N > 1; ++pass) {
                 rs_hist_kernel<uint64_t><<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], N, pass * 8, hist, p.rs_blocks);
                 B2_LAUNCH_CHECK(ctx);
                 rc = exclusive_scan<uint32_t>(ctx, hist, 256 * (size_t)p.rs_blocks, (uint32_t*)scan_tmp, s);
                 if (rc) return rc;
-                rs_scatter_kernel<uint64_t><<<p.rs_blocks, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], N, pass * 8, hist,
+                rs_scatter_kernel<uint64_t><<<p.rs_blocks, RS_THREADS, rs_scatter_smem<uint64_t>(), s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], N, pass * 8, hist,
                                                                                p.rs_blocks);
                 B2_LAUNCH_CHECK(ctx);
                 cur ^= 1;
