@@ -431,6 +431,11 @@ __global__ void __launch_bounds__(256) pt_resolve_kernel(const void* __restrict_
     finalize_index<MODE>(f, idx, px, py, r);
 }
 
+#ifndef B200RT_SHADE_PREFETCH
+#define B200RT_SHADE_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 #ifndef B200RT_SHADE_MIN_CTAS
 #define B200RT_SHADE_MIN_CTAS 2
 #endif
@@ -452,13 +457,42 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                                      ((const float*)(miss_base + B200RT_SBT_RECORD_HEADER_SIZE))[2]);
     constexpr uint32_t RAY_TYPES = MODE == 0 ? 1u : 2u;  // SBT stride of the radiance trace call
     uint32_t iter = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x, ++iter) {
+    // SHADE is a chain of dependent gathers (queue -> lane state -> hit -> vertices) run by 16 warps per SM: ncu shows it waiting on
+    // the long scoreboard with 13 % of the issue slots busy.  The queue entry of the NEXT grid-stride iteration is read one iteration
+    // ahead and that lane's state lines are pulled into L2 while the current lane is shaded (B200RT_SHADE_PREFETCH >= 1); with >= 2 the
+    // hit of the next lane is read ahead too and the vertices of its triangle are prefetched.
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nprims = (B200RT_SHADE_PREFETCH >= 2 && f.handle->kind == ACCEL_KIND_GAS) ? f.handle->num_tris : 0u;  // prefetch guard only
+    uint32_t lane_next = 0;
+    if (B200RT_SHADE_PREFETCH) { const uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; if (q0 < n) lane_next = queue[q0]; }
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride, ++iter) {
         const uint32_t qi = base + threadIdx.x;
         bool keep = false, want_ext = false, want_shd = false;
         float3 key_eo = f3(0.f, 0.f, 0.f), key_ed = key_eo, key_so = key_eo, key_sd = key_eo;  // rays pushed this iteration (ray_sort keys)
         uint32_t lane = 0;
+        if (B200RT_SHADE_PREFETCH) {
+            lane = lane_next;
+            const uint32_t nqi = qi + stride;
+            if (nqi < n) {
+                lane_next = queue[nqi];
+                prefetch_l2(&L.ray_d[lane_next]); prefetch_l2(&L.res[lane_next]); prefetch_l2(&L.ray_o[lane_next]); prefetch_l2(&L.att[lane_next]);
+                prefetch_l2(&L.hitp[lane_next]);
+                if (MODE == 1) prefetch_l2(&L.emi[lane_next]);
+                if (B200RT_SHADE_PREFETCH >= 2) {
+                    // the hit of the next lane (valid when its res.w >= 0; a stale or never-written record is clamped into the buffer)
+                    const uint2 hpn = L.hitp[lane_next];
+                    uint32_t rec = (hpn.y & TRI_SBT_MASK) * RAY_TYPES;
+                    if (rec >= hg_count) rec = hg_count - 1;
+                    const HitGroupData* rtn = (const HitGroupData*)(hg_base + (size_t)rec * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE);
+                    if (hpn.x < nprims) {
+                        prefetch_l2(rtn->vertices + 3 * (size_t)hpn.x);
+                        prefetch_l2(rtn->vertices + 3 * (size_t)hpn.x + 2);
+                    }
+                }
+            }
+        }
         if (qi < n) {
-            lane = queue[qi];
+            if (!B200RT_SHADE_PREFETCH) lane = queue[qi];
             float4 rd = L.ray_d[lane];
             uint32_t flags = __float_as_uint(rd.w);
             float4 resv = L.res[lane];
