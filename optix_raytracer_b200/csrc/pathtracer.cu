@@ -287,6 +287,8 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
 template <int MODE>
 struct PTWork {
     static constexpr bool CONTINUES = false;
+    static constexpr bool NODE_POLICY = B200RT_NODE_KEEP_MB > 0;
+    __device__ __forceinline__ uint64_t node_policy() const { return node_policy_for(f.handle); }
     static constexpr bool ANYHIT = false;  // the Cornell programs have no any-hit (optixPathTracer.cpp:748-767)
     const Frame& f;
     const Lanes& L;

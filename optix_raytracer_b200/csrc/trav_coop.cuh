@@ -78,6 +78,37 @@ __device__ __forceinline__ float q8_hi(uint32_t h)
     return f;
 }
 
+// L2 eviction priorities for the node fetches of a scene that lives in HBM (B200RT_NODE_KEEP_MB > 0): nodes are laid out level by
+// level, so the first megabytes of the node array are the upper levels of the tree.  A range policy (createpolicy.range: one 64-bit
+// descriptor, held in uniform registers) gives them evict_last and the deep levels — hundreds of megabytes read once per ray that
+// reaches them — evict_first, so that the deep levels stop pushing the middle of the tree out of L2.
+#ifndef B200RT_NODE_KEEP_MB
+#define B200RT_NODE_KEEP_MB 0
+#endif
+__device__ __forceinline__ uint64_t node_policy_for(const AccelHeader* __restrict__ h)
+{
+    uint64_t pol;
+    if (h->kind == ACCEL_KIND_GAS && h->node_bytes == NODE8_BYTES) {
+        const char* base = (const char*)h + h->nodes_off;
+        asm("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;"
+            : "=l"(pol) : "l"(base), "r"((uint32_t)B200RT_NODE_KEEP_MB << 20), "r"(0xffffff00u));
+    } else {
+        asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    }
+    return pol;
+}
+template <bool POLICY>
+__device__ __forceinline__ uint4 node_load(const uint4* p, uint64_t pol)
+{
+    if constexpr (POLICY) {
+        uint4 v;
+        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+        return v;
+    } else {
+        return __ldg(p);
+    }
+}
+
 struct Trav {
     const uint4* nodes;
     const float4* tris;
@@ -198,7 +229,8 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
 }
 
 // One node visit; returns the triangle group of the visited node (mask 0 = none).
-__device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ stack, TravStats* st)
+template <bool POLICY = false>
+__device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ stack, TravStats* st, uint64_t pol = 0)
 {
     const uint32_t hits_imask = s.ngroup.y;
     const uint32_t bit = 31u - __clz(hits_imask);
@@ -211,7 +243,8 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
     const uint32_t slot = (bit - 24u) ^ octinv;
     const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
     const uint4* np = s.nodes + (size_t)(child_base + rel) * 5u;
-    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const uint4 n0 = node_load<POLICY>(np, pol), n1 = node_load<POLICY>(np + 1, pol), n2 = node_load<POLICY>(np + 2, pol),
+                n3 = node_load<POLICY>(np + 3, pol), n4 = node_load<POLICY>(np + 4, pol);
     if (st) st->nodes++;
     const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
     const uint32_t e_imask = n0.w;
@@ -320,9 +353,10 @@ __device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__
     return make_uint2(n1.y, hitmask & 0x00ffffffu);
 }
 
-__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st)
+template <bool POLICY = false>
+__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st, uint64_t pol = 0)
 {
-    return (s.pack & TP_F32) ? trav_node_step_f32(s, stack, st) : trav_node_step_q8(s, stack, st);
+    return (s.pack & TP_F32) ? trav_node_step_f32(s, stack, st) : trav_node_step_q8<POLICY>(s, stack, st, pol);
 }
 
 // TERMINATE_ON_FIRST_HIT rays stop at the first accepted hit: no further instance is traversed
@@ -366,12 +400,21 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 //                                                                  shared by all lanes plus its arguments; false = ignore the hit), and
 //   __device__ void  attenuate(float factor)                       is called on the OWNING lane for every factor != 1
 //   __device__ bool  anyhit_enabled()                              uniform over the launch: false skips all of it at run time
+//   static constexpr bool NODE_POLICY (optional)                   the launch gives its node fetches an L2 eviction policy:
+//   __device__ uint64_t node_policy()                              uniform over the launch (node_policy_for)
+template <class Work, class = void> struct CoopHasNodePolicy { static constexpr bool value = false; };
+template <class Work> struct CoopHasNodePolicy<Work, decltype((void)Work::NODE_POLICY)> { static constexpr bool value = Work::NODE_POLICY; };
+template <class Work> constexpr bool coop_node_policy() { return CoopHasNodePolicy<Work>::value; }
+
 template <class Work>
 __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, unsigned int* __restrict__ fetch_counter, TravStats* st)
 {
     __shared__ CoopShared sh;
     __shared__ CoopSharedAnyHit<Work::ANYHIT> sha;
     const bool tri_stream = work.stream_triangles();  // uniform over the launch
+    constexpr bool NODE_POLICY = coop_node_policy<Work>();
+    uint64_t node_pol = 0;  // uniform over the launch
+    if constexpr (NODE_POLICY) node_pol = work.node_policy();
     bool ah_on = false;  // uniform: the launch has any-hit programs AND the traversable holds geometry that runs them
     if constexpr (Work::ANYHIT) ah_on = work.anyhit_enabled();
     constexpr unsigned FULL = 0xffffffffu;
@@ -439,7 +482,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
             __syncwarp();
             // ---- phase B: one node visit for every lane that has node work
             if (has && (s.ngroup.y & NODE_BITS)) {
-                const uint2 nt = trav_node_step(s, stack, st);
+                const uint2 nt = trav_node_step<NODE_POLICY>(s, stack, st, node_pol);
                 if (nt.y) {
                     if (s.tgroup.y == 0u) s.tgroup = nt;
                     else if (s.sp < TRAV_STACK) stack[s.sp++] = nt;  // second parked group: goes on the stack (no NODE_BITS marks it)
