@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
     // ahead and that lane's state lines are pulled into L2 while the current lane is shaded (B200RT_SHADE_PREFETCH >= 1); with >= 2 the
     // hit of the next lane is read ahead too and the vertices of its triangle are prefetched.
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t nprims = (B200RT_SHADE_PREFETCH >= 2 && f.handle->kind == ACCEL_KIND_GAS) ? f.handle->num_tris : 0u;  // prefetch guard only
+#if B200RT_SHADE_PREFETCH >= 2
+    const uint32_t nprims = f.handle->kind == ACCEL_KIND_GAS ? f.handle->num_tris : 0u;  // prefetch guard only
+#endif
     uint32_t lane_next = 0;
     if (B200RT_SHADE_PREFETCH) { const uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; if (q0 < n) lane_next = queue[q0]; }
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride, ++iter) {
@@ -480,7 +482,8 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                 prefetch_l2(&L.ray_d[lane_next]); prefetch_l2(&L.res[lane_next]); prefetch_l2(&L.ray_o[lane_next]); prefetch_l2(&L.att[lane_next]);
                 prefetch_l2(&L.hitp[lane_next]);
                 if (MODE == 1) prefetch_l2(&L.emi[lane_next]);
-                if (B200RT_SHADE_PREFETCH >= 2) {
+#if B200RT_SHADE_PREFETCH >= 2
+                {
                     // the hit of the next lane (valid when its res.w >= 0; a stale or never-written record is clamped into the buffer)
                     const uint2 hpn = L.hitp[lane_next];
                     uint32_t rec = (hpn.y & TRI_SBT_MASK) * RAY_TYPES;
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                         prefetch_l2(rtn->vertices + 3 * (size_t)hpn.x + 2);
                     }
                 }
+#endif
             }
         }
         if (qi < n) {

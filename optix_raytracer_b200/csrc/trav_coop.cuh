@@ -29,6 +29,9 @@ namespace b200rt {
 #ifndef B200RT_LOOKTHROUGH
 #define B200RT_LOOKTHROUGH 0
 #endif
+#ifndef B200RT_STACK_TOP
+#define B200RT_STACK_TOP 0   // measured slower at 64 registers (the two extra live registers turn into 190 bytes of spills): see stack_push
+#endif
 // Triangle records of a scene that lives in HBM are read once per ray and not again soon, while nodes (the upper levels at least) are
 // read again and again: such launches load triangles with the streaming (evict-first) policy so they do not push nodes out of L1 / L2
 // (measured on the 50 M-triangle bench: 2033 -> 2045 Mrays/s).  Cache-resident scenes keep the default policy.
@@ -119,8 +122,43 @@ struct Trav {
     uint32_t inst;          // index of the instance being traversed (0 for a bare GAS)
     uint2 ngroup, tgroup;   // current node group; parked triangle group (base, 24-bit mask)
     int sp;
+#if B200RT_STACK_TOP
+    uint2 top;              // the top stack entry (index sp - 1) lives here; stack[0 .. sp-2] are in local memory
+#endif
     RayHit best;
 };
+
+// Traversal stack.  ncu's source page (profiles/r01_trace_kernel.md, v5) charged 10.7 % of the kernel's stall samples to the line that
+// looks at the entry just popped: the pop is a local-memory load (a miss in the node-filled L1 more often than not) whose value the very
+// next instructions need.  With B200RT_STACK_TOP the top entry is kept in registers: a pop hands it over at once and issues the load of
+// the entry below, which has the whole next node visit to arrive; a push stores the old top and keeps the new one.  Measured on the
+// bench: 2083 -> 1931 Mrays/s — under the 64-register cap of 8 CTAs per SM the kernel spills 190 instead of 10 bytes per thread, which
+// costs more than the exposed pop.  Off by default; the helpers keep both forms.
+__device__ __forceinline__ void stack_push(Trav& s, uint2* __restrict__ stack, uint2 e)
+{
+#if B200RT_STACK_TOP
+    if (s.sp > 0) stack[s.sp - 1] = s.top;
+    s.top = e;
+    ++s.sp;
+#else
+    stack[s.sp++] = e;
+#endif
+}
+__device__ __forceinline__ uint2 stack_peek(const Trav& s, const uint2* __restrict__ stack)
+{
+#if B200RT_STACK_TOP
+    return s.top;
+#else
+    return stack[s.sp - 1];
+#endif
+}
+__device__ __forceinline__ void stack_drop(Trav& s, const uint2* __restrict__ stack)  // remove the top entry
+{
+    --s.sp;
+#if B200RT_STACK_TOP
+    if (s.sp > 0) s.top = stack[s.sp - 1];
+#endif
+}
 
 struct CoopShared {
     float ray[COOP_WARPS][32 * RAY_S_STRIDE];  // per lane: ox, oy, oz, Sx, Sy, Sz, pack, tmin, cull
@@ -237,7 +275,7 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
     const uint32_t child_base = s.ngroup.x;
     s.ngroup.y &= ~(1u << bit);
     if (s.ngroup.y & NODE_BITS) {
-        if (s.sp < TRAV_STACK) stack[s.sp++] = s.ngroup;
+        if (s.sp < TRAV_STACK) stack_push(s, stack, s.ngroup);
     }
     const uint32_t octinv = (s.pack >> 8) & 7u;
     const uint32_t slot = (bit - 24u) ^ octinv;
@@ -304,7 +342,7 @@ __device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__
     const uint32_t child_base = s.ngroup.x;
     s.ngroup.y &= ~(1u << bit);
     if (s.ngroup.y & NODE_BITS) {
-        if (s.sp < TRAV_STACK) stack[s.sp++] = s.ngroup;
+        if (s.sp < TRAV_STACK) stack_push(s, stack, s.ngroup);
     }
     const uint32_t octinv = (s.pack >> 8) & 7u;
     const uint32_t slot = (bit - 24u) ^ octinv;
@@ -463,12 +501,20 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                 // triangle groups met on the way down the stack are parked, or — slot taken — skipped over when a node group sits
                 // right below them (B200RT_LOOKTHROUGH)
                 while (s.sp > 0) {
-                    const uint2 e = stack[s.sp - 1];
-                    if (e.y & NODE_BITS) { s.ngroup = e; --s.sp; break; }
-                    if (s.tgroup.y == 0u) { s.tgroup = e; --s.sp; continue; }
+                    const uint2 e = stack_peek(s, stack);
+                    if (e.y & NODE_BITS) { s.ngroup = e; stack_drop(s, stack); break; }
+                    if (s.tgroup.y == 0u) { s.tgroup = e; stack_drop(s, stack); continue; }
                     if (B200RT_LOOKTHROUGH && s.sp >= 2) {
                         const uint2 below = stack[s.sp - 2];
-                        if (below.y & NODE_BITS) { s.ngroup = below; stack[s.sp - 2] = e; --s.sp; break; }
+                        if (below.y & NODE_BITS) {
+                            // take the node group from under the triangle group, which stays on top
+                            s.ngroup = below;
+#if !B200RT_STACK_TOP
+                            stack[s.sp - 2] = e;
+#endif
+                            --s.sp;
+                            break;
+                        }
                     }
                     blocked = true;  // both triangle slots taken and no node group within reach
                     break;
@@ -485,7 +531,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                 const uint2 nt = trav_node_step<NODE_POLICY>(s, stack, st, node_pol);
                 if (nt.y) {
                     if (s.tgroup.y == 0u) s.tgroup = nt;
-                    else if (s.sp < TRAV_STACK) stack[s.sp++] = nt;  // second parked group: goes on the stack (no NODE_BITS marks it)
+                    else if (s.sp < TRAV_STACK) stack_push(s, stack, nt);  // second parked group: goes on the stack (no NODE_BITS marks it)
                     else {
                         // stack full (pathological depth): test the group right here, one lane
                         uint2 g = nt;
