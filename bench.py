@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spl", type=int, default=16)
     ap.add_argument("--sample-groups", type=int, default=None, help="b200rt_pt_options.sample_groups: lanes per launch index (1 = reference summation order)")
-    ap.add_argument("--ray-sort", type=int, default=None, help="b200rt_pt_options.ray_sort (default: 1 for the synthetic workload, 0 for cornell)")
+    ap.add_argument("--ray-sort", type=int, default=None, help="b200rt_pt_options.ray_sort (default 0: measured slower end to end, profiles/r01_trace_kernel.md)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
                     help="N > 1: how the frame is assembled — p2p: every rank's launch stores its pixels into rank 0's result buffer over NVLink "
                          "(the reference's single result buffer, optixMultiGPU.cpp:479-508); allgather: per-rank sample buffers all-gathered (NCCL) "
