@@ -380,6 +380,11 @@ void b200rt_camera_uvw(const float eye[3], const float lookat[3], const float up
  * writes the 92-byte object Params::camera points to. */
 void b200rt_playground_camera(const float eye[3], const float up[3], const float lookat[3], float aperture, float fd,
                               float fov_deg, int ortho, void* camera92);
+/* How OptixRayFlags and OptixInstanceFlags combine for the triangles of one instance (host function, no GPU; reference
+ * include/optix_types.h:1088-1108, 1794-1839): bits 4-7 = the ray's CULL_* flags after DISABLE_TRIANGLE_FACE_CULLING (face bits dropped)
+ * or FLIP_TRIANGLE_FACING (face bits swapped); bits 0-1 = any-hit override, 1 = off for every triangle, 2 = on, 0 = the geometry flag
+ * decides; ray flags take precedence over instance flags.  Exposed so that the CPU oracle and the device code can be compared. */
+unsigned int b200rt_triangle_flag_word(unsigned int ray_flags, unsigned int instance_flags);
 /* StaticWorkDistribution (reference SDK/sutil/WorkDistribution.h:50-81) */
 int b200rt_wd_num_samples(int width, int height, int num_gpus);
 void b200rt_wd_sample_pixel(int width, int height, int num_gpus, int gpu_idx, int sample_idx, int xy[2]);

@@ -139,6 +139,7 @@ SYMBOLS = {
     "b200rt_texture_destroy": (i32, [vp, u64, u64]),
     "b200rt_launch_playground": (i32, [vp, vp, u64, u32, u32, C.POINTER(PTOptions)]),
     "b200rt_generate_playground_scene": (i32, [vp, vp, u32, u32, u64, u64, u64, C.POINTER(u64)]),
+    "b200rt_triangle_flag_word": (u32, [u32, u32]),
     "b200rt_wd_num_samples": (i32, [i32, i32, i32]),
     "b200rt_wd_sample_pixel": (None, [i32, i32, i32, i32, i32, C.POINTER(i32)]),
     "b200rt_generate_synthetic_mesh": (i32, [vp, vp, u64, u32, u64, u64, C.POINTER(f32)]),

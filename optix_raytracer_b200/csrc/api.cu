@@ -420,6 +420,9 @@ void b200rt_playground_camera(const float eye[3], const float up[3], const float
     memcpy(camera92, &c, sizeof c);
 }
 
+// what the triangle tests of an instance see of the ray's flags (accel.h: cull_word)
+unsigned int b200rt_triangle_flag_word(unsigned int ray_flags, unsigned int instance_flags) { return b200rt::cull_word(ray_flags, instance_flags); }
+
 // StaticWorkDistribution (reference SDK/sutil/WorkDistribution.h:50-81): 8x4 tiles, strips of 8*N columns
 int b200rt_wd_num_samples(int width, int height, int num_gpus)
 {

@@ -63,20 +63,7 @@ __device__ __forceinline__ TriRay make_tri_ray(float3 o, float3 d)
     return r;
 }
 
-// The cull word a triangle test sees: the ray's CULL_* flags (bits 4-7, reference include/optix_types.h:1819-1839) after the instance
-// flags had their say, plus the any-hit override in bits 0-1 — 1 = any-hit off for every triangle, 2 = any-hit on for every triangle,
-// 0 = the triangle's own OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT decides.  Precedence as documented in include/optix_types.h:1088-1108 and
-// 1794-1806: ray flags over instance flags over geometry flags.  OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING drops the two
-// face-cull bits, OPTIX_INSTANCE_FLAG_FLIP_TRIANGLE_FACING swaps them.  Same function in oracle.cpp (cull_word).
-__host__ __device__ __forceinline__ uint32_t cull_word(uint32_t ray_flags, uint32_t inst_flags)
-{
-    uint32_t c = ray_flags & 0xf0u;
-    if (inst_flags & 1u) c &= ~0x30u;
-    else if (inst_flags & 2u) c = (c & ~0x30u) | ((c & 0x10u) << 1) | ((c & 0x20u) >> 1);
-    uint32_t force = (ray_flags & 1u) ? 1u : (ray_flags & 2u) ? 2u : 0u;
-    if (!force) force = (inst_flags & 4u) ? 1u : (inst_flags & 8u) ? 2u : 0u;
-    return c | force;
-}
+// cull_word(ray_flags, instance_flags): accel.h.
 // does the triangle (geometry flags gflags) run any-hit programs under this cull word?
 __device__ __forceinline__ bool anyhit_off(uint32_t gflags, uint32_t cull) { return (cull & 3u) ? (cull & 1u) != 0u : (gflags & 1u) != 0u; }
 

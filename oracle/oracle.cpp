@@ -673,6 +673,7 @@ void* orc_scene_create(const float* verts, int64_t ntri, const uint32_t* sbt)
     return s;
 }
 // add one instance of geometry 0 with a row-major 3x4 object->world transform
+uint32_t orc_cull_word(uint32_t ray_flags, uint32_t inst_flags) { return cull_word(ray_flags, inst_flags); }
 void orc_scene_add_instance_ex(void* scene, const float* m34, uint32_t flags, uint32_t mask)
 {
     Scene* s = (Scene*)scene;

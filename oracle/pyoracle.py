@@ -38,6 +38,8 @@ def lib():
         L.orc_scene_create.restype = vp; L.orc_scene_create.argtypes = [vp, i64, vp]
         L.orc_scene_add_instance.argtypes = [vp, vp]
         L.orc_scene_add_instance_ex.argtypes = [vp, vp, u32, u32]
+        L.orc_cull_word.argtypes = [u32, u32]
+        L.orc_cull_word.restype = u32
         L.orc_scene_set_triangle_flags.argtypes = [vp, vp]
         L.orc_scene_set_brute.argtypes = [vp, i32]
         L.orc_scene_destroy.argtypes = [vp]

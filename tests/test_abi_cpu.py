@@ -23,7 +23,7 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     from optix_raytracer_b200 import _lib
     header = (ROOT / "include" / "b200rt.h").read_text()
-    declared = set(re.findall(r"^(?:int|void|uint64_t|const char\*)\s+(b200rt_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|void|uint64_t|unsigned int|const char\*)\s+(b200rt_[a-z0-9_]+)\s*\(", header, re.M))
     assert len(declared) >= 25
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in b200rt.h but not exported by libb200rt.so"

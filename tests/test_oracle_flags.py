@@ -72,3 +72,18 @@ def test_per_triangle_geometry_flags_and_mask():
     r = s.trace(FROM_FRONT)
     assert r["t"][0] == 1.0 and r["inst"][0] == 1
     assert not hit(orc.Scene(TRI, None, instances=[(IDENT, 0, 0)]), FROM_FRONT, 0)
+
+
+def test_flag_word_of_the_library_equals_the_oracles():
+    """accel.h: cull_word (what the device triangle tests see) against oracle.cpp: cull_word, over every combination of the eight ray-flag
+    bits and the four instance-flag bits that concern triangles — a host function of the C ABI, no GPU involved."""
+    from optix_raytracer_b200 import _lib
+    lib, o = _lib.load(), orc.lib()
+    for rf in range(256):
+        for inf in range(16):
+            w = lib.b200rt_triangle_flag_word(rf, inf)
+            assert w == o.orc_cull_word(rf, inf), (rf, inf)
+            assert w & ~0xf3 == 0
+    # documented cases: ray flags win over instance flags; FLIP swaps the face-cull bits; DISABLE_TRIANGLE_FACE_CULLING drops them only
+    assert lib.b200rt_triangle_flag_word(R_ENF_AH | R_CULL_BACK, I_DIS_AH | I_FLIP) == (2 | R_CULL_FRONT)
+    assert lib.b200rt_triangle_flag_word(R_CULL_BACK | R_CULL_DIS_AH, I_NO_CULL | I_ENF_AH) == (2 | R_CULL_DIS_AH)
