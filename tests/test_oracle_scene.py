@@ -145,3 +145,22 @@ def test_synthetic_mesh_is_closed_and_counts_add_up():
         assert np.isfinite(tris).all()
         assert tris.min() >= -1e-3 and tris[..., 0].max() <= 556.001 and tris[..., 2].max() <= 559.201
         assert (mats == 3).sum() >= 2 or total < 64
+
+
+def test_oracle_bvh_equals_brute_force_on_the_edge_case_scene():
+    """The oracle's own median-split BVH must not change a single hit record against its brute-force loop (the exact definition) on the
+    rays traversals usually disagree on: shared edges and vertices, rays in box face planes, degenerate intervals, geometry a million
+    units from the origin (tests/common.py: edge_case_scene; the GPU runs the same set in tests/test_gpu_parity.py)."""
+    tris, rays = common.edge_case_scene()
+    scene = orc.Scene(tris)
+    a = scene.trace(rays)
+    occ_a = scene.trace(rays, any_hit=True)["occluded"]
+    scene.set_brute(True)
+    b = scene.trace(rays)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert np.array_equal(occ_a, scene.trace(rays, any_hit=True)["occluded"])
+    assert (a["t"] >= 0).sum() > 2000
+    # a vertex shared by six triangles of the coplanar grid goes to the lowest ordinal
+    hit = scene.trace(np.array([[1.0, 1.0, 5, 0, 0, 0, -1, 100]], np.float32))
+    assert hit["t"][0] == 4.0 and hit["prim"][0] == min(i for i in range(tris.shape[0]) if (tris[i] == np.array([1, 1, 1], np.float32)).all(axis=1).any())
