@@ -58,6 +58,11 @@ struct InstanceRecord {
 };
 static_assert(sizeof(InstanceRecord) == INSTREC_BYTES, "instance record must be 128 bytes");
 
+// Entries of the per-lane traversal stack (traverse.cuh, trav_coop.cuh).  A visited level leaves at most two entries behind (the rest of
+// its node group and a parked triangle group), so a tree of depth d needs 2 d entries; the builder refuses deeper trees instead of
+// letting a traversal drop children (bvh_build.cu).  The 50 M-triangle bench scene has depth 17.
+constexpr int TRAV_STACK = 40;
+
 // TriRecord w-lane packing
 constexpr uint32_t TRI_SBT_MASK = 0x00ffffffu;   // v1.w low 24 bits: GAS-local SBT index
 constexpr uint32_t TRI_FLAG_SHIFT = 24;          // v1.w high 8 bits: OptixGeometryFlags of its SBT record

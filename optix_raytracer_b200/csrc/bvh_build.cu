@@ -1199,7 +1199,9 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 nwork = h_level->next_nodes;
                 wcur ^= 1;
                 ++depth;
-                B2_REQUIRE(ctx, depth < 64, "accel build: tree too deep");
+                if (2 * depth > (uint32_t)TRAV_STACK)
+                    return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: the hierarchy is %u levels deep, the traversal stack holds %d entries (2 per level)",
+                                     depth, TRAV_STACK);
             }
             if (tri_cursor != N) return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: triangle count mismatch (%u != %u)", tri_cursor, N);
             // triangles go right after the node capacity region; compaction later closes the gap

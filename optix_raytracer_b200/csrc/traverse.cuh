@@ -20,7 +20,7 @@
 
 namespace b200rt {
 
-constexpr int TRAV_STACK = 40;
+// TRAV_STACK (entries of the per-lane traversal stack): accel.h — the builder checks the tree depth against it
 constexpr float BOX_SLACK = 1.0000038f;   // 1 + 2^-18 on the far side of every slab comparison
 constexpr float DIR_EPS = 8.27180613e-25f;  // 2^-80: |d| below this is clamped for the *box* tests only
 
