@@ -110,7 +110,10 @@ def test_exr_is_read_by_an_independent_decoder(tmp_path, monkeypatch):
         acc = (rng.random(shape, dtype=np.float32) * 4).astype(np.float32)
         p = str(tmp_path / "x.exr")
         host.save_image(p, acc)
-        img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        try:
+            img = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        except cv2.error as e:  # codec compiled out or disabled in this process
+            pytest.skip(f"OpenCV cannot decode EXR here: {e}")
         if img is None:
             pytest.skip("this OpenCV build has no OpenEXR codec")
         got = img[..., [2, 1, 0, 3]] if shape[2] == 4 else img[..., ::-1]
