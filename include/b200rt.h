@@ -56,7 +56,11 @@ extern "C" {
 #define B200RT_PROPERTY_TYPE_COMPACTED_SIZE 0x2181
 #define B200RT_BUILD_FLAG_ALLOW_COMPACTION (1u << 1)
 /* ray flags, reference include/optix_types.h:1794-1840 (same values).  Precedence of the any-hit state of a triangle, as documented
- * there: ray flags (DISABLE / ENFORCE_ANYHIT) over instance flags over the geometry flag of its SBT record. */
+ * there: ray flags (DISABLE / ENFORCE_ANYHIT) over instance flags over the geometry flag of its SBT record.  OptiX declares some
+ * combinations mutually exclusive (DISABLE / ENFORCE_ANYHIT with each other and with the CULL_*_ANYHIT flags; the two face-cull flags
+ * with each other); this library gives them the obvious meaning instead of leaving them undefined: DISABLE wins over ENFORCE, the
+ * CULL_*_ANYHIT flags see the any-hit state after the ray's override, and both face-cull flags together cull every triangle that takes
+ * part in face culling. */
 #define B200RT_RAY_FLAG_NONE 0u
 #define B200RT_RAY_FLAG_DISABLE_ANYHIT (1u << 0)
 #define B200RT_RAY_FLAG_ENFORCE_ANYHIT (1u << 1)

@@ -210,3 +210,48 @@ def test_whitted_matches_the_reference_programs_on_optix(ctxs, variant):
     assert psnr > 45.0, f"PSNR {psnr:.1f} dB"
     b.close()
     o.close()
+
+
+def test_face_culling_and_instance_flags_match_optix(ctxs):
+    """OptixRayFlags CULL_BACK / CULL_FRONT_FACING_TRIANGLES, OptixInstanceFlags DISABLE_TRIANGLE_FACE_CULLING / FLIP_TRIANGLE_FACING, the
+    geometry flag DISABLE_TRIANGLE_FACE_CULLING and the visibility mask on the real OptiX runtime against b200rt: same hit / miss, same
+    primitive, same instance.  A wrong facing convention or a wrong flip would change about half of the culled hits.  (The OptiX query
+    programs trace with OPTIX_RAY_FLAG_DISABLE_ANYHIT, which OptiX declares mutually exclusive with the CULL_*_ANYHIT ray flags, and
+    the two face-cull flags exclude each other too: those combinations are not put to OptiX.)"""
+    from optix_raytracer_b200 import host
+    bctx, octx = ctxs
+    rng = np.random.default_rng(29)
+    n = 1500
+    c = rng.random((n, 1, 3), dtype=np.float32) * 2 - 1
+    tris = (c + (rng.random((n, 3, 3), dtype=np.float32) - 0.5) * 0.4).astype(np.float32)
+    sbt = (rng.random(n) < 0.3).astype(np.uint32)
+    rec_flags = [1, 1 | 4]   # both records DISABLE_ANYHIT (the query pipeline has no any-hit program); record 1 is exempt from face culling
+
+    def xf(angle, scale, t):
+        ca, sa = np.cos(angle), np.sin(angle)
+        return np.array([[ca * scale, 0, sa * scale, t[0]], [0, scale, 0, t[1]], [-sa * scale, 0, ca * scale, t[2]]], np.float32).reshape(12)
+    xfs = [xf(0.0, 1.0, (0, 0, 0)), xf(0.9, 0.8, (1.2, 0.3, 0)), xf(-0.6, 1.1, (-1.2, -0.4, 0.8)), xf(0.1, 3.0, (0, 0, 0))]
+    iflags, masks = [0, 1, 2, 0], [1, 1, 1, 0]
+    accels = []
+    for ctx in (bctx, octx):
+        gas = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12, sbt_index=ctx.to_device(sbt), num_sbt=2,
+                                                  flags=rec_flags)])
+        ias = ctx.build_accel([ctx.instance_input([(m, 0, gas, k, f) for m, f, k in zip(xfs, iflags, masks)])], compact=False)
+        accels.append((gas, ias))
+    rays = common.random_rays(rng, 100_000, [-2.5, -2, -2], [2.5, 2, 2])
+    d = bctx.to_device(rays)
+    counts = {}
+    for rf in (0, 16, 32):
+        for which, is_ias in ((0, False), (1, True)):
+            got = host.ext_hits_to_numpy(bctx.trace_closest(accels[0][which], d, ray_flags=rf | 1))
+            ref = host.ext_hits_to_numpy(octx.trace_closest(accels[1][which], d, ray_flags=rf, is_ias=is_ias))
+            hb, ho = got["t"] >= 0, ref["t"] >= 0
+            what = f"ray_flags {rf:#x} {'ias' if is_ias else 'gas'}"
+            # silhouette edges of a triangle soup: a ray within an ulp of an edge may fall either way between two triangle tests
+            assert (hb != ho).mean() < 2e-4, f"{what}: {(hb != ho).sum()} rays disagree on hit / miss"
+            both = hb & ho
+            assert (got["prim"][both] != ref["prim"][both]).mean() < 2e-4, f"{what}: primitive differs from OptiX"
+            assert (got["inst"][both] != ref["inst"][both]).mean() < 2e-4, f"{what}: instance differs from OptiX"
+            counts[(rf, is_ias)] = int(ho.sum())
+    for is_ias in (False, True):
+        assert 0 < counts[(16, is_ias)] < counts[(0, is_ias)] and 0 < counts[(32, is_ias)] < counts[(0, is_ias)]

@@ -2,7 +2,8 @@
 hand-made cases against what the OptiX headers document: face culling and its two instance overrides
 (reference include/optix_types.h:1093-1097, 1819-1825), the any-hit state of a triangle under the precedence
 ray flags > instance flags > geometry flags (include/optix_types.h:1102-1108, 1800-1806) as seen by CULL_DISABLED_ANYHIT /
-CULL_ENFORCED_ANYHIT (:1832-1839), and the visibility mask.  The GPU path is compared with the oracle on random scenes in
+CULL_ENFORCED_ANYHIT (:1832-1839), and the visibility mask.  Combinations OptiX declares mutually exclusive (ray DISABLE / ENFORCE_ANYHIT
+with the CULL_*_ANYHIT flags, both face-cull flags at once) have the meaning include/b200rt.h gives them.  The GPU path is compared with the oracle on random scenes in
 tests/test_gpu_parity.py::test_ray_and_instance_flags_vs_oracle."""
 import numpy as np
 import pytest
