@@ -59,9 +59,10 @@ struct InstanceRecord {
 static_assert(sizeof(InstanceRecord) == INSTREC_BYTES, "instance record must be 128 bytes");
 
 // Entries of the per-lane traversal stack (traverse.cuh, trav_coop.cuh).  A visited level leaves at most two entries behind (the rest of
-// its node group and a parked triangle group), so a tree of depth d needs 2 d entries; the builder refuses deeper trees instead of
-// letting a traversal drop children (bvh_build.cu).  The 50 M-triangle bench scene has depth 17.
-constexpr int TRAV_STACK = 40;
+// its node group and a parked triangle group), so a tree of depth d needs 2 d entries.  The builder keeps every tree within
+// TRAV_STACK / 2 levels whatever the input (bvh_build.cu: collapse_plan_kernel opens the tallest subtrees first where the surface-area
+// order would run out of levels), so no input is refused and no traversal ever drops a child.  The 50 M-triangle bench scene has depth 17.
+constexpr int TRAV_STACK = 64;
 
 // TriRecord w-lane packing
 constexpr uint32_t TRI_SBT_MASK = 0x00ffffffu;   // v1.w low 24 bits: GAS-local SBT index

@@ -145,6 +145,7 @@ int b200rt_context_destroy(b200rt_context ctx)
     {
         DeviceGuard guard(ctx->device);
         cudaDeviceSynchronize();
+        pathtracer_release(ctx);
         if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         if (ctx->ev) cudaEventDestroy(ctx->ev);
@@ -154,7 +155,7 @@ int b200rt_context_destroy(b200rt_context ctx)
     return 0;
 }
 
-uint64_t b200rt_context_kernel_launches(b200rt_context ctx) { return ctx ? ctx->launches : 0; }
+uint64_t b200rt_context_kernel_launches(b200rt_context ctx) { return ctx ? ctx->launches + pathtracer_graph_kernels(ctx) : 0; }
 
 int b200rt_shared_buffer_create(b200rt_context ctx, size_t bytes, b200rt_deviceptr* ptr, unsigned char* handle64)
 {

@@ -22,6 +22,7 @@
 
 #include "accel.h"
 #include "common.h"
+#include "loop_graph.h"
 #include "rt_math.cuh"
 
 namespace b200rt {
@@ -127,6 +128,101 @@ static int exclusive_scan(b200rt_context ctx, T* data, size_t n, T* tmp, cudaStr
     scan_add_kernel<T><<<tiles, SCAN_THREADS, 0, s>>>(data, n, tmp);
     B2_LAUNCH_CHECK(ctx);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan whose length lives on the device (exclusive, in place): the loops of the build (clustering rounds, collapse levels) run as CUDA
+// graphs whose kernels have fixed launch shapes and read their problem size from device memory.  DS_BLOCKS blocks own one contiguous
+// chunk each: (1) chunk totals, (2) one block scans the totals and writes the grand total, (3) every block rescans its chunk.
+// Deterministic (no atomics), so the hierarchy and the node order are the same from run to run.
+// ---------------------------------------------------------------------------------------------
+constexpr int DS_BLOCKS = 592, DS_THREADS = 256;  // 4 blocks per SM on 148 SMs
+
+__device__ __forceinline__ void ds_chunk(uint32_t n, uint32_t& first, uint32_t& last)
+{
+    const uint32_t chunk = ((n + DS_BLOCKS - 1) / DS_BLOCKS + DS_THREADS - 1) / DS_THREADS * DS_THREADS;
+    first = min(n, blockIdx.x * chunk);
+    last = min(n, first + chunk);
+}
+
+template <typename T>
+__device__ __forceinline__ T ds_block_scan(T v, T* wsum, T& total)  // exclusive scan over the block's threads; total = block sum
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const T o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    __syncthreads();  // wsum may still be read by the previous call
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    T before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < DS_THREADS / 32; ++w) { const T x = wsum[w]; before += w < warp ? x : (T)0; tot += x; }
+    total = tot;
+    return before + incl - v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DS_THREADS) dscan_reduce_kernel(const T* __restrict__ data, const uint32_t* __restrict__ n_dev, T* __restrict__ block_sums)
+{
+    __shared__ T wsum[DS_THREADS / 32];
+    uint32_t first, last;
+    ds_chunk(*n_dev, first, last);
+    T sum = 0;
+    for (uint32_t i = first + threadIdx.x; i < last; i += DS_THREADS) sum += data[i];
+    T total;
+    ds_block_scan<T>(sum, wsum, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) dscan_spine_kernel(T* __restrict__ block_sums, T* __restrict__ total_out)
+{
+    __shared__ T wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T v = threadIdx.x < DS_BLOCKS ? block_sums[threadIdx.x] : (T)0;
+    T incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const T o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    T before = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { const T x = wsum[w]; before += w < warp ? x : (T)0; tot += x; }
+    if (threadIdx.x < DS_BLOCKS) block_sums[threadIdx.x] = before + incl - v;
+    if (threadIdx.x == 0) *total_out = tot;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DS_THREADS) dscan_apply_kernel(T* __restrict__ data, const uint32_t* __restrict__ n_dev, const T* __restrict__ block_sums)
+{
+    __shared__ T wsum[DS_THREADS / 32];
+    uint32_t first, last;
+    ds_chunk(*n_dev, first, last);
+    T run = block_sums[blockIdx.x];
+    for (uint32_t base = first; base < last; base += DS_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const T v = i < last ? data[i] : (T)0;
+        T total;
+        const T ex = ds_block_scan<T>(v, wsum, total);
+        if (i < last) data[i] = run + ex;
+        run += total;
+    }
+}
+
+// appends the three kernels to a loop body; block_sums: DS_BLOCKS elements of T; *total_out = sum of data[0 .. *n_dev)
+template <typename T>
+static int dscan_add(LoopGraph& g, T* data, const uint32_t* n_dev, T* block_sums, T* total_out)
+{
+    static_assert(DS_BLOCKS <= 1024, "one block scans the chunk totals");
+    if (int rc = g.add((const void*)dscan_reduce_kernel<T>, DS_BLOCKS, DS_THREADS, 0, (const T*)data, n_dev, block_sums)) return rc;
+    if (int rc = g.add((const void*)dscan_spine_kernel<T>, 1, 1024, 0, block_sums, total_out)) return rc;
+    return g.add((const void*)dscan_apply_kernel<T>, DS_BLOCKS, DS_THREADS, 0, data, n_dev, (const T*)block_sums);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -469,73 +565,114 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 #endif
 constexpr int PLOC_RADIUS = B200RT_PLOC_RADIUS, PLOC_THREADS = 256;
 
-__global__ void __launch_bounds__(PLOC_THREADS) ploc_nearest_kernel(const uint32_t* __restrict__ clusters, uint32_t n, const float4* __restrict__ box_lo,
-                                                                     const float4* __restrict__ box_hi, uint32_t* __restrict__ nearest)
+// The clustering rounds run as a device-side loop (loop_graph.h): every kernel is grid-stride over the live cluster count in PlocState.
+struct PlocState {
+    uint32_t n;           // clusters alive
+    uint32_t node_base;   // internal nodes created so far
+    uint32_t cc;          // which of the two cluster arrays is current
+    uint32_t round;
+    unsigned long long total;  // this round's flag totals: survivors << 32 | nodes created
+    uint32_t error, pad;
+};
+// Rounds from this one on pair the clusters by position (2 i with 2 i + 1) instead of by nearest neighbour: a round adds at most one
+// level to the tree, clustering by neighbour may take arbitrarily many rounds on adversarial input, and the collapse needs a bounded
+// height to keep the wide tree within the traversal stack (collapse_plan_kernel).  Typical inputs finish in about 40 rounds.
+constexpr uint32_t PLOC_POSITIONAL_ROUND = 64;
+
+__global__ void __launch_bounds__(PLOC_THREADS) ploc_nearest_kernel(const uint32_t* __restrict__ cl0, const uint32_t* __restrict__ cl1, const PlocState* __restrict__ st,
+                                                                     const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, uint32_t* __restrict__ nearest)
 {
     __shared__ float4 slo[PLOC_THREADS + 2 * PLOC_RADIUS], shi[PLOC_THREADS + 2 * PLOC_RADIUS];
-    const int base = (int)(blockIdx.x * PLOC_THREADS) - PLOC_RADIUS;
-    for (int k = threadIdx.x; k < PLOC_THREADS + 2 * PLOC_RADIUS; k += PLOC_THREADS) {
-        const int g = base + k;
-        if (g >= 0 && g < (int)n) { const uint32_t id = clusters[g]; slo[k] = box_lo[id]; shi[k] = box_hi[id]; }
+    const uint32_t n = st->n;
+    const uint32_t* __restrict__ clusters = st->cc ? cl1 : cl0;
+    if (st->round >= PLOC_POSITIONAL_ROUND) {
+        for (uint32_t i = blockIdx.x * PLOC_THREADS + threadIdx.x; i < n; i += gridDim.x * PLOC_THREADS) nearest[i] = (i ^ 1u) < n ? (i ^ 1u) : 0xffffffffu;
+        return;
     }
-    __syncthreads();
-    const int i = (int)(blockIdx.x * PLOC_THREADS + threadIdx.x);
-    if (i >= (int)n) return;
-    const int me = threadIdx.x + PLOC_RADIUS;
-    const float4 alo = slo[me], ahi = shi[me];
-    float best = INFINITY;
-    int bj = -1;
-    for (int d = -PLOC_RADIUS; d <= PLOC_RADIUS; ++d) {
-        const int j = i + d;
-        if (d == 0 || j < 0 || j >= (int)n) continue;
-        const float4 blo = slo[me + d], bhi = shi[me + d];
-        const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
-        const float a = dx * dy + dy * dz + dz * dx;
-        if (a < best) { best = a; bj = j; }  // ties: the lower position (scan order), so (i, j) and (j, i) agree on equal areas
+    for (uint32_t tile = blockIdx.x; tile * PLOC_THREADS < n; tile += gridDim.x) {
+        const int base = (int)(tile * PLOC_THREADS) - PLOC_RADIUS;
+        __syncthreads();
+        for (int k = threadIdx.x; k < PLOC_THREADS + 2 * PLOC_RADIUS; k += PLOC_THREADS) {
+            const int g = base + k;
+            if (g >= 0 && g < (int)n) { const uint32_t id = clusters[g]; slo[k] = box_lo[id]; shi[k] = box_hi[id]; }
+        }
+        __syncthreads();
+        const int i = (int)(tile * PLOC_THREADS + threadIdx.x);
+        if (i >= (int)n) continue;
+        const int me = threadIdx.x + PLOC_RADIUS;
+        const float4 alo = slo[me], ahi = shi[me];
+        float best = INFINITY;
+        int bj = -1;
+        for (int d = -PLOC_RADIUS; d <= PLOC_RADIUS; ++d) {
+            const int j = i + d;
+            if (d == 0 || j < 0 || j >= (int)n) continue;
+            const float4 blo = slo[me + d], bhi = shi[me + d];
+            const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a < best) { best = a; bj = j; }  // ties: the lower position (scan order), so (i, j) and (j, i) agree on equal areas
+        }
+        nearest[i] = (uint32_t)bj;
     }
-    nearest[i] = (uint32_t)bj;
 }
 
 // flags: high word = this position survives into the next round, low word = it creates a node
-__global__ void __launch_bounds__(256) ploc_flag_kernel(const uint32_t* __restrict__ nearest, uint32_t n, unsigned long long* __restrict__ flags)
+__global__ void __launch_bounds__(256) ploc_flag_kernel(const uint32_t* __restrict__ nearest, const PlocState* __restrict__ st, unsigned long long* __restrict__ flags)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t j = nearest[i];
-    const bool mutual = j < n && nearest[j] == i;
-    const bool leader = mutual && i < j;
-    flags[i] = ((unsigned long long)((!mutual || leader) ? 1u : 0u) << 32) | (leader ? 1u : 0u);
+    const uint32_t n = st->n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t j = nearest[i];
+        const bool mutual = j < n && nearest[j] == i;
+        const bool leader = mutual && i < j;
+        flags[i] = ((unsigned long long)((!mutual || leader) ? 1u : 0u) << 32) | (leader ? 1u : 0u);
+    }
 }
 
-__global__ void __launch_bounds__(256) ploc_merge_kernel(const uint32_t* __restrict__ clusters, const uint32_t* __restrict__ nearest, uint32_t n,
-                                                          const unsigned long long* __restrict__ excl, uint32_t node_base, int ninternal,
+__global__ void __launch_bounds__(256) ploc_merge_kernel(uint32_t* __restrict__ cl0, uint32_t* __restrict__ cl1, const uint32_t* __restrict__ nearest,
+                                                          const PlocState* __restrict__ st, const unsigned long long* __restrict__ excl, int ninternal,
                                                           float4* __restrict__ box_lo, float4* __restrict__ box_hi, int2* __restrict__ range,
-                                                          uint32_t* __restrict__ out)
+                                                          uint8_t* __restrict__ height)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t j = nearest[i];
-    const bool mutual = j < n && nearest[j] == i;
-    if (mutual && i > j) return;  // absorbed by its partner
-    const unsigned long long e = excl[i];
-    const uint32_t pos = (uint32_t)(e >> 32);
-    if (!mutual) { out[pos] = clusters[i]; return; }
-    const uint32_t id = node_base + (uint32_t)(e & 0xffffffffu);
-    const uint32_t a = clusters[i], b = clusters[j];
-    const float4 alo = box_lo[a], ahi = box_hi[a], blo = box_lo[b], bhi = box_hi[b];
-    const int ca = (int)a < ninternal ? range[a].y : 1, cb = (int)b < ninternal ? range[b].y : 1;
-    box_lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float((int)a));
-    box_hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), __int_as_float((int)b));
-    range[id] = make_int2(-1, ca + cb);  // x: leaves of a PLOC node are not a range of sorted positions (collapse walks small subtrees)
-    out[pos] = id;
+    const uint32_t n = st->n, node_base = st->node_base;
+    const uint32_t* __restrict__ clusters = st->cc ? cl1 : cl0;
+    uint32_t* __restrict__ out = st->cc ? cl0 : cl1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t j = nearest[i];
+        const bool mutual = j < n && nearest[j] == i;
+        if (mutual && i > j) continue;  // absorbed by its partner
+        const unsigned long long e = excl[i];
+        const uint32_t pos = (uint32_t)(e >> 32);
+        if (!mutual) { out[pos] = clusters[i]; continue; }
+        const uint32_t id = node_base + (uint32_t)(e & 0xffffffffu);
+        const uint32_t a = clusters[i], b = clusters[j];
+        const float4 alo = box_lo[a], ahi = box_hi[a], blo = box_lo[b], bhi = box_hi[b];
+        const int ca = (int)a < ninternal ? range[a].y : 1, cb = (int)b < ninternal ? range[b].y : 1;
+        const int ha = (int)a < ninternal ? height[a] : 0, hb = (int)b < ninternal ? height[b] : 0;
+        box_lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float((int)a));
+        box_hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), __int_as_float((int)b));
+        range[id] = make_int2(-1, ca + cb);  // x: leaves of a PLOC node are not a range of sorted positions (collapse walks small subtrees)
+        height[id] = (uint8_t)min(max(ha, hb) + 1, 255);
+        out[pos] = id;
+    }
 }
 
-__global__ void ploc_init_kernel(uint32_t* clusters, uint32_t n)
+__global__ void ploc_advance_kernel(PlocState* st, cudaGraphConditionalHandle cond)
+{
+    const unsigned long long tot = st->total;
+    const uint32_t survivors = (uint32_t)(tot >> 32), created = (uint32_t)(tot & 0xffffffffu);
+    if (created == 0u || survivors != st->n - created) st->error = 1u;  // cannot happen: the pair with the smallest union is mutual
+    st->node_base += created;
+    st->n = survivors;
+    st->cc ^= 1u;
+    st->round += 1u;
+    cudaGraphSetConditional(cond, (st->n > 1u && !st->error && st->round < 4096u) ? 1u : 0u);
+}
+
+__global__ void ploc_init_kernel(uint32_t* clusters, uint32_t n, PlocState* st)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) clusters[i] = n - 1u + i;  // leaf ids in Morton order
+    if (i == 0) { PlocState z = {}; z.n = n; *st = z; }
 }
-__global__ void read_root_kernel(const uint32_t* clusters, uint32_t* work) { work[0] = clusters[0]; }
 
 // ---------------------------------------------------------------------------------------------
 // 5. refit
@@ -552,7 +689,7 @@ __global__ void __launch_bounds__(256) leaf_boxes_kernel(const float4* __restric
 }
 
 __global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float4* box_hi, const int* __restrict__ parent,
-                                                     uint32_t* __restrict__ arrive)
+                                                     uint32_t* __restrict__ arrive, uint8_t* height)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -567,6 +704,12 @@ __global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float
         const float rlx = vlo[r].x, rly = vlo[r].y, rlz = vlo[r].z, rhx = vhi[r].x, rhy = vhi[r].y, rhz = vhi[r].z;
         box_lo[node] = make_float4(fminf(llx, rlx), fminf(lly, rly), fminf(llz, rlz), __int_as_float(l));
         box_hi[node] = make_float4(fmaxf(lhx, rhx), fmaxf(lhy, rhy), fmaxf(lhz, rhz), __int_as_float(r));
+        {
+            // subtree height (edges to the deepest leaf): what the collapse needs to keep the wide tree within the traversal stack
+            const volatile uint8_t* vh = height;
+            const int hl = l < n - 1 ? vh[l] : 0, hr = r < n - 1 ? vh[r] : 0;
+            height[node] = (uint8_t)min(max(hl, hr) + 1, 255);
+        }
         node = parent[node];
     }
 }
@@ -574,11 +717,17 @@ __global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float
 // ---------------------------------------------------------------------------------------------
 // 6. collapse to the 8-wide layout
 // ---------------------------------------------------------------------------------------------
-struct LevelInfo {  // device <-> host per level
-    uint32_t next_nodes;   // internal children produced by this level
-    uint32_t level_tris;   // triangles referenced by this level's leaves
-    uint32_t error;
+// The levels run as a device-side loop (loop_graph.h); every kernel is grid-stride over the level's work list, whose length lives here.
+struct CollapseState {
+    uint32_t nwork;        // wide nodes of the current level
+    uint32_t level_start;  // index of the level's first node
+    uint32_t tri_cursor;   // triangles placed by the levels above
+    uint32_t wcur;         // which of the two work lists holds the current level
+    uint32_t depth;        // levels finished
+    uint32_t total_nodes;
+    uint32_t error;        // 1: node capacity exceeded, 2: triangle count mismatch, 3: clustering failed (internal errors)
     uint32_t pad;
+    unsigned long long total;  // this level's totals: inner children << 32 | triangles in leaf children
 };
 
 __device__ __forceinline__ float box_area(const float4 lo, const float4 hi)
@@ -587,84 +736,116 @@ __device__ __forceinline__ float box_area(const float4 lo, const float4 hi)
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void __launch_bounds__(128) collapse_plan_kernel(uint32_t nwork, const uint32_t* __restrict__ work, int n,
-                                                             const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
-                                                             const int2* __restrict__ range, int* __restrict__ child_tmp,
-                                                             unsigned long long* __restrict__ counts)
+// Wide-tree depth the traversal stack is good for (two entries per level, accel.h) and the levels a binary subtree of height h needs
+// at most when every wide node below opens its tallest children first (7 openings take 3 off the height of a full binary tree, more
+// off anything thinner).  Binary heights are bounded by the key length: 63 Morton bits + 30 index bits for the radix tree,
+// PLOC_POSITIONAL_ROUND + 23 rounds for the clustering, so levels_needed(root) <= MAX_WIDE_DEPTH for every input.
+constexpr int MAX_WIDE_DEPTH = TRAV_STACK / 2;
+__device__ __forceinline__ int levels_needed(int h) { return (h + 2) / 3 + 1; }
+static_assert((93 + 2) / 3 + 1 <= MAX_WIDE_DEPTH, "the traversal stack must hold the deepest tree the builder can make");
+
+__global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState* __restrict__ st, const uint32_t* __restrict__ work0,
+                                                             const uint32_t* __restrict__ work1, int n, const float4* __restrict__ box_lo,
+                                                             const float4* __restrict__ box_hi, const int2* __restrict__ range,
+                                                             const uint8_t* __restrict__ height, int* __restrict__ child_tmp,
+                                                             unsigned long long* __restrict__ counts, int max_depth)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwork) return;
+    const uint32_t nwork = st->nwork;
+    const uint32_t* __restrict__ work = st->wcur ? work1 : work0;
     const int ninternal = n - 1;
-    int ids[8];
-    float area[8];
-    int cnt[8];
-    int m = 0;
-    auto push = [&](int id) {
-        ids[m] = id;
-        if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); }
-        else { cnt[m] = 1; area[m] = -1.0f; }
-        ++m;
-    };
-    const int root = (int)work[i];
-    if (root >= ninternal) push(root);  // single-triangle scene
-    else { push(__float_as_int(box_lo[root].w)); push(__float_as_int(box_hi[root].w)); }
-    // phase 1: open the largest inner subtree with more than 3 triangles; phase 2: split small multi-triangle leaves
-    for (int phase = 0; phase < 2; ++phase) {
-        while (m < 8) {
-            int best = -1;
-            float ba = -1.0f;
-            for (int k = 0; k < m; ++k) {
-                const bool inner = ids[k] < ninternal;
-                const bool ok = phase == 0 ? (inner && cnt[k] > 3) : inner;
-                if (ok && area[k] > ba) { ba = area[k]; best = k; }
+    const int levels_left = max_depth - (int)st->depth;  // levels available from this one down, this one included
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
+        int ids[8];
+        float area[8];
+        int cnt[8];
+        int hgt[8];
+        int m = 0;
+        auto push = [&](int id) {
+            ids[m] = id;
+            if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); hgt[m] = height[id]; }
+            else { cnt[m] = 1; area[m] = -1.0f; hgt[m] = 0; }
+            ++m;
+        };
+        const int root = (int)work[i];
+        int hroot = 0;
+        if (root >= ninternal) push(root);  // single-triangle scene
+        else { hroot = height[root]; push(__float_as_int(box_lo[root].w)); push(__float_as_int(box_hi[root].w)); }
+        // depth guard: a subtree too tall for the levels that are left opens its tallest children first until every child is at least 3
+        // lower than the root (7 openings always suffice); this takes precedence over the surface-area order below
+        if (levels_needed(hroot) > levels_left - 2) {
+            while (m < 8) {
+                int best = -1, bh = hroot - 3;
+                for (int k = 0; k < m; ++k)
+                    if (ids[k] < ninternal && hgt[k] > bh) { bh = hgt[k]; best = k; }
+                if (best < 0) break;
+                const int id = ids[best];
+                const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
+                const int save = m;
+                m = best; push(l);
+                m = save; push(r);
             }
-            if (best < 0) break;
-            const int id = ids[best];
-            const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
-            const int save = m;
-            m = best; push(l);
-            m = save; push(r);
         }
+        // phase 1: open the largest inner subtree with more than 3 triangles; phase 2: split small multi-triangle leaves
+        for (int phase = 0; phase < 2; ++phase) {
+            while (m < 8) {
+                int best = -1;
+                float ba = -1.0f;
+                for (int k = 0; k < m; ++k) {
+                    const bool inner = ids[k] < ninternal;
+                    const bool ok = phase == 0 ? (inner && cnt[k] > 3) : inner;
+                    if (ok && area[k] > ba) { ba = area[k]; best = k; }
+                }
+                if (best < 0) break;
+                const int id = ids[best];
+                const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
+                const int save = m;
+                m = best; push(l);
+                m = save; push(r);
+            }
+        }
+        uint32_t nint = 0, ntri = 0;
+        for (int k = 0; k < 8; ++k) {
+            if (k < m) {
+                child_tmp[(size_t)i * 8 + k] = ids[k];
+                if (ids[k] < ninternal && cnt[k] > 3) ++nint; else ntri += cnt[k];
+            } else child_tmp[(size_t)i * 8 + k] = -1;
+        }
+        counts[i] = ((unsigned long long)nint << 32) | ntri;
     }
-    uint32_t nint = 0, ntri = 0;
-    for (int k = 0; k < 8; ++k) {
-        if (k < m) {
-            child_tmp[(size_t)i * 8 + k] = ids[k];
-            if (ids[k] < ninternal && cnt[k] > 3) ++nint; else ntri += cnt[k];
-        } else child_tmp[(size_t)i * 8 + k] = -1;
-    }
-    counts[i] = ((unsigned long long)nint << 32) | ntri;
 }
 
-__global__ void collapse_totals_kernel(uint32_t nwork, const unsigned long long* __restrict__ excl,
-                                        const unsigned long long* __restrict__ last_count, LevelInfo* info)
+__global__ void collapse_advance_kernel(CollapseState* st, uint32_t max_nodes, cudaGraphConditionalHandle cond)
 {
-    // excl[nwork-1] + original count of the last element (saved before the scan)
-    const unsigned long long tot = excl[nwork - 1] + *last_count;
-    info->next_nodes = (uint32_t)(tot >> 32);
-    info->level_tris = (uint32_t)(tot & 0xffffffffu);
+    const unsigned long long tot = st->total;
+    const uint32_t next_nodes = (uint32_t)(tot >> 32), level_tris = (uint32_t)(tot & 0xffffffffu);
+    const uint32_t next_level_start = st->level_start + st->nwork;
+    st->total_nodes = next_level_start;
+    if ((unsigned long long)next_level_start + next_nodes > max_nodes) st->error = 1u;
+    st->level_start = next_level_start;
+    st->tri_cursor += level_tris;
+    st->nwork = next_nodes;
+    st->wcur ^= 1u;
+    st->depth += 1u;
+    cudaGraphSetConditional(cond, (st->nwork > 0u && !st->error) ? 1u : 0u);
 }
 
-__global__ void save_last_kernel(uint32_t nwork, const unsigned long long* __restrict__ counts, unsigned long long* last)
-{
-    *last = counts[nwork - 1];
-}
-
-__global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint32_t level_start, uint32_t next_level_start,
-                                                             uint32_t tri_cursor, uint32_t max_nodes, int n,
+__global__ void __launch_bounds__(128) collapse_emit_kernel(CollapseState* __restrict__ st, uint32_t max_nodes, int n,
                                                              const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
                                                              const int2* __restrict__ range, const int* __restrict__ child_tmp,
-                                                             const unsigned long long* __restrict__ excl, uint32_t* __restrict__ next_work,
-                                                             uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out, LevelInfo* info, uint32_t node_bytes)
+                                                             const unsigned long long* __restrict__ excl, uint32_t* __restrict__ work0,
+                                                             uint32_t* __restrict__ work1, uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out,
+                                                             uint32_t node_bytes)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwork) return;
+    const uint32_t nwork = st->nwork, level_start = st->level_start, next_level_start = level_start + nwork, tri_cursor = st->tri_cursor;
+    uint32_t* __restrict__ next_work = st->wcur ? work0 : work1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
     const uint32_t node_index = level_start + i;
-    if (node_index >= max_nodes) { info->error = 1; return; }
+    if (node_index >= max_nodes) { st->error = 1u; continue; }
     const int ninternal = n - 1;
     const unsigned long long ex = excl[i];
     const uint32_t child_base = next_level_start + (uint32_t)(ex >> 32);
     const uint32_t tri_base = tri_cursor + (uint32_t)(ex & 0xffffffffu);
+    if (child_base > max_nodes - min(max_nodes, 8u)) { st->error = 1u; continue; }  // its children would not fit: the level check reports it
 
     int ids[8];
     float4 clo[8], chi[8];
@@ -791,7 +972,7 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
             out[8 + 2 * a] = make_uint4(__float_as_uint(fhi[a][0]), __float_as_uint(fhi[a][1]), __float_as_uint(fhi[a][2]), __float_as_uint(fhi[a][3]));
             out[9 + 2 * a] = make_uint4(__float_as_uint(fhi[a][4]), __float_as_uint(fhi[a][5]), __float_as_uint(fhi[a][6]), __float_as_uint(fhi[a][7]));
         }
-        return;
+        continue;
     }
     uint4* out = nodes_out + (size_t)node_index * 5;
     out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
@@ -799,6 +980,7 @@ __global__ void __launch_bounds__(128) collapse_emit_kernel(uint32_t nwork, uint
     out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
     out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     out[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    }
 }
 
 __global__ void __launch_bounds__(256) scatter_tris_kernel(const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals,
@@ -813,13 +995,36 @@ __global__ void __launch_bounds__(256) scatter_tris_kernel(const float4* __restr
     tris_out[3 * d + 2] = tri_tmp[3 * g + 2];
 }
 
-__global__ void write_header_kernel(AccelHeader* h, AccelHeader v, const uint32_t* bounds)
+// The header is completed on the device from the collapse's final state; the compacted size goes to the caller's emit address.
+__global__ void write_header_kernel(AccelHeader* h, AccelHeader v, const uint32_t* bounds, const CollapseState* st, unsigned long long* emit0,
+                                    unsigned long long* emit1)
 {
     for (int a = 0; a < 6; ++a) v.bounds[a] = ordered_to_float(bounds[a]);
+    if (st) {
+        v.num_nodes = st->total_nodes;
+        v.depth = st->depth;
+        v.error = st->error ? st->error : (st->tri_cursor != v.num_tris ? 2u : 0u);
+    }
+    v.total_bytes = HEADER_BYTES + (uint64_t)v.num_nodes * v.node_bytes + (uint64_t)v.num_tris * TRI_BYTES;
     *h = v;
+    const unsigned long long compacted = (v.total_bytes + 127ull) / 128ull * 128ull;
+    if (emit0) *emit0 = compacted;
+    if (emit1) *emit1 = compacted;
 }
 
-__global__ void set_root_work_kernel(uint32_t* work, uint32_t id) { work[0] = id; }
+// first work item of the collapse: the root of the binary hierarchy (radix tree: internal node 0, or leaf 0 of a one-triangle input;
+// clustering: the last cluster standing)
+__global__ void collapse_init_kernel(CollapseState* st, uint32_t* work0, uint32_t root, const uint32_t* cl0, const uint32_t* cl1, const PlocState* ploc)
+{
+    CollapseState z = {};
+    z.nwork = 1u;
+    if (ploc) {
+        root = (ploc->cc ? cl1 : cl0)[0];
+        if (ploc->error || ploc->n != 1u) z.error = 3u;
+    }
+    work0[0] = root;
+    *st = z;
+}
 
 // ---------------------------------------------------------------------------------------------
 // IAS
@@ -881,8 +1086,8 @@ struct BuildPlan {
     uint32_t rs_blocks = 0;
     int morton_bits = 21;
     // temp offsets
-    size_t off_inputs, off_flags, off_bounds, off_level, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box_lo, off_box_hi,
-        off_parent, off_range, off_arrive, off_dest, off_hist, off_scan_tmp, off_work0, off_work1, off_child_tmp, off_counts, off_last;
+    size_t off_inputs, off_flags, off_bounds, off_state, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box_lo, off_box_hi,
+        off_parent, off_range, off_arrive, off_dest, off_hist, off_scan_tmp, off_work0, off_work1, off_child_tmp, off_counts, off_height, off_dsums;
     size_t temp_bytes = 0, out_bytes = 0;
     uint32_t node_bytes = NODE8_BYTES;
 };
@@ -918,6 +1123,15 @@ static bool use_ploc(const b200rt_accel_build_options* options, uint32_t ntris)
     return ntris <= PLOC_MAX_TRIANGLES;
 }
 
+// B200RT_MAX_WIDE_DEPTH=<n> lowers the depth the collapse aims for (tests of the depth guard; it holds whenever the binary hierarchy is
+// at most 3 (n - 1) levels tall).  Never above what the traversal stack is good for.
+static int max_wide_depth()
+{
+    const char* e = getenv("B200RT_MAX_WIDE_DEPTH");
+    const int v = e ? atoi(e) : MAX_WIDE_DEPTH;
+    return std::min(std::max(v, 3), MAX_WIDE_DEPTH);
+}
+
 static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsigned num_inputs, BuildPlan& p)
 {
     uint64_t n = 0, sbt = 0;
@@ -948,8 +1162,8 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.off_inputs = take(sizeof(DevInput) * std::max(1u, num_inputs));
     p.off_flags = take(4 * std::max<size_t>(sbt, 1));
     p.off_bounds = take(64);
-    p.off_level = take(sizeof(LevelInfo));
-    p.off_last = take(16);
+    p.off_state = take(256);      // PlocState at 0, CollapseState at 128
+    p.off_dsums = take(8 * DS_BLOCKS);
     p.off_tri_tmp = take(48 * N);
     p.off_keys0 = take(8 * N);
     p.off_keys1 = take(8 * N);
@@ -961,9 +1175,9 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.off_range = take(8 * N);
     p.off_arrive = take(4 * N);
     p.off_dest = take(4 * N);
+    p.off_height = take(N);
     p.off_hist = take(4 * 256 * (size_t)p.rs_blocks);
-    const size_t scan_elems = std::max(std::max(scan_temp_elems<uint32_t>(256 * (size_t)p.rs_blocks), scan_temp_elems<unsigned long long>(W)),
-                                       scan_temp_elems<unsigned long long>(N));  // PLOC scans one word per cluster
+    const size_t scan_elems = scan_temp_elems<uint32_t>(256 * (size_t)p.rs_blocks);
     p.off_scan_tmp = take(8 * scan_elems);
     p.off_work0 = take(4 * W);
     p.off_work1 = take(4 * W);
@@ -1014,7 +1228,6 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
     // what the whitted launch learnt about the scene (light count, BLEND materials) belongs to the scene that was there before:
     // a new scene always comes with a build, and its buffers may well reuse the old addresses
     ctx->w_params = 0;
-    for (auto& v : ctx->rc_params) v = 0;
 
     if (inputs[0].type == B200RT_BUILD_INPUT_TYPE_INSTANCES) {
         B2_REQUIRE(ctx, num_inputs == 1, "an instance build takes exactly one build input");
@@ -1085,8 +1298,10 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         uint32_t* work[2] = {(uint32_t*)(T + p.off_work0), (uint32_t*)(T + p.off_work1)};
         int* child_tmp = (int*)(T + p.off_child_tmp);
         unsigned long long* counts = (unsigned long long*)(T + p.off_counts);
-        unsigned long long* last = (unsigned long long*)(T + p.off_last);
-        LevelInfo* d_level = (LevelInfo*)(T + p.off_level);
+        uint8_t* height = (uint8_t*)(T + p.off_height);
+        PlocState* d_ploc = (PlocState*)(T + p.off_state);
+        CollapseState* d_cst = (CollapseState*)(T + p.off_state + 128);
+        unsigned long long* dsums = (unsigned long long*)(T + p.off_dsums);
 
         AccelHeader hv;
         memset(&hv, 0, sizeof(hv));
@@ -1099,7 +1314,6 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
 
         init_bounds_kernel<<<1, 32, 0, s>>>(d_bounds);
         B2_LAUNCH_CHECK(ctx);
-        uint32_t total_nodes = 0, depth = 0;
         if (N > 0) {
             gather_tris_kernel<<<persistent_grid(ctx, N, 256, 8), 256, 0, s>>>((const DevInput*)(T + p.off_inputs), (int)num_inputs, N,
                                                               (const uint32_t*)(T + p.off_flags), tri_tmp, d_bounds);
@@ -1121,89 +1335,52 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             }
             leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
             B2_LAUNCH_CHECK(ctx);
-            const bool ploc = use_ploc(options, N);
-            if (N > 1 && ploc) {
+            // No host read-back from here on: optixAccelBuild is asynchronous, so the rounds of the clustering and the levels of
+            // the collapse, whose counts only the device knows, run as device-side loops (CUDA graphs with a conditional WHILE node).
+            const unsigned wide_grid = std::max(1u, std::min(div_up(N, 128), (unsigned)ctx->sm_count * 16u));
+            const bool ploc = use_ploc(options, N) && N > 1;
+            uint32_t* cl[2] = {nullptr, nullptr};
+            if (ploc) {
                 // the sort's key buffers are free now: cluster ping-pong in one, the scan words in the other
-                uint32_t* cl[2] = {(uint32_t*)keys[cur], (uint32_t*)keys[cur] + N};
+                cl[0] = (uint32_t*)keys[cur]; cl[1] = (uint32_t*)keys[cur] + N;
                 unsigned long long* flags = (unsigned long long*)keys[cur ^ 1];
                 uint32_t* nearest = arrive;
-                unsigned long long* h_tot = (unsigned long long*)((char*)ctx->pinned + 64);
-                ploc_init_kernel<<<div_up(N, 256), 256, 0, s>>>(cl[0], N);
+                ploc_init_kernel<<<div_up(N, 256), 256, 0, s>>>(cl[0], N, d_ploc);
                 B2_LAUNCH_CHECK(ctx);
-                uint32_t n = N, node_base = 0;
-                int cc = 0;
-                for (int round = 0; n > 1; ++round) {
-                    B2_REQUIRE(ctx, round < 4096, "accel build: clustering does not converge (internal error)");
-                    ploc_nearest_kernel<<<div_up(n, PLOC_THREADS), PLOC_THREADS, 0, s>>>(cl[cc], n, box_lo, box_hi, nearest);
-                    B2_LAUNCH_CHECK(ctx);
-                    ploc_flag_kernel<<<div_up(n, 256), 256, 0, s>>>(nearest, n, flags);
-                    B2_LAUNCH_CHECK(ctx);
-                    save_last_kernel<<<1, 1, 0, s>>>(n, flags, last);
-                    B2_LAUNCH_CHECK(ctx);
-                    rc = exclusive_scan<unsigned long long>(ctx, flags, n, (unsigned long long*)scan_tmp, s);
-                    if (rc) return rc;
-                    ploc_merge_kernel<<<div_up(n, 256), 256, 0, s>>>(cl[cc], nearest, n, flags, node_base, (int)N - 1, box_lo, box_hi, range, cl[cc ^ 1]);
-                    B2_LAUNCH_CHECK(ctx);
-                    // totals = exclusive value of the last position + its own flags
-                    B2_CUDA(ctx, cudaMemcpyAsync(h_tot, flags + (n - 1), 8, cudaMemcpyDeviceToHost, s));
-                    B2_CUDA(ctx, cudaMemcpyAsync(h_tot + 1, last, 8, cudaMemcpyDeviceToHost, s));
-                    B2_CUDA(ctx, cudaStreamSynchronize(s));
-                    const unsigned long long tot = h_tot[0] + h_tot[1];
-                    const uint32_t survivors = (uint32_t)(tot >> 32), created = (uint32_t)(tot & 0xffffffffu);
-                    B2_REQUIRE(ctx, created > 0 && survivors == n - created, "accel build: clustering made no progress (internal error)");
-                    node_base += created;
-                    n = survivors;
-                    cc ^= 1;
-                }
-                B2_REQUIRE(ctx, node_base == N - 1, "accel build: clustering node count mismatch (internal error)");
-                B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
-                read_root_kernel<<<1, 1, 0, s>>>(cl[cc], work[0]);
+                const unsigned pgrid = std::max(1u, std::min(div_up(N, 256), (unsigned)ctx->sm_count * 8u));
+                LoopGraph g(ctx);
+                if ((rc = g.begin())) return rc;
+                if ((rc = g.add((const void*)ploc_nearest_kernel, pgrid, PLOC_THREADS, 0, (const uint32_t*)cl[0], (const uint32_t*)cl[1], (const PlocState*)d_ploc,
+                                (const float4*)box_lo, (const float4*)box_hi, nearest))) return rc;
+                if ((rc = g.add((const void*)ploc_flag_kernel, pgrid, 256, 0, (const uint32_t*)nearest, (const PlocState*)d_ploc, flags))) return rc;
+                if ((rc = dscan_add<unsigned long long>(g, flags, &d_ploc->n, dsums, &d_ploc->total))) return rc;
+                if ((rc = g.add((const void*)ploc_merge_kernel, pgrid, 256, 0, cl[0], cl[1], (const uint32_t*)nearest, (const PlocState*)d_ploc,
+                                (const unsigned long long*)flags, (int)N - 1, box_lo, box_hi, range, height))) return rc;
+                if ((rc = g.add((const void*)ploc_advance_kernel, 1, 1, 0, d_ploc, g.cond()))) return rc;
+                if ((rc = g.launch(s))) return rc;
+                ctx->launches += 1;
+            } else if (N > 1) {
+                karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
                 B2_LAUNCH_CHECK(ctx);
-            } else {
-                if (N > 1) {
-                    karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
-                    B2_LAUNCH_CHECK(ctx);
-                    B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
-                    refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive);
-                    B2_LAUNCH_CHECK(ctx);
-                }
-                B2_CUDA(ctx, cudaMemsetAsync(d_level, 0, sizeof(LevelInfo), s));
-                set_root_work_kernel<<<1, 1, 0, s>>>(work[0], 0u);  // internal node 0, or leaf id 0 when N == 1
+                B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
+                refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive, height);
                 B2_LAUNCH_CHECK(ctx);
             }
+            collapse_init_kernel<<<1, 1, 0, s>>>(d_cst, work[0], 0u, cl[0], cl[1], ploc ? d_ploc : nullptr);  // radix tree: internal node 0, or leaf 0 when N == 1
+            B2_LAUNCH_CHECK(ctx);
             // ---- collapse, level by level
-            uint32_t nwork = 1, level_start = 0, tri_cursor = 0;
-            int wcur = 0;
-            LevelInfo* h_level = (LevelInfo*)ctx->pinned;
-            while (nwork > 0) {
-                collapse_plan_kernel<<<div_up(nwork, 128), 128, 0, s>>>(nwork, work[wcur], (int)N, box_lo, box_hi, range, child_tmp, counts);
-                B2_LAUNCH_CHECK(ctx);
-                save_last_kernel<<<1, 1, 0, s>>>(nwork, counts, last);
-                B2_LAUNCH_CHECK(ctx);
-                rc = exclusive_scan<unsigned long long>(ctx, counts, nwork, (unsigned long long*)scan_tmp, s);
-                if (rc) return rc;
-                collapse_totals_kernel<<<1, 1, 0, s>>>(nwork, counts, last, d_level);
-                B2_LAUNCH_CHECK(ctx);
-                const uint32_t next_level_start = level_start + nwork;
-                collapse_emit_kernel<<<div_up(nwork, 128), 128, 0, s>>>(nwork, level_start, next_level_start, tri_cursor, p.max_nodes, (int)N,
-                                                                         box_lo, box_hi, range, child_tmp, counts, work[wcur ^ 1], dest,
-                                                                         nodes_out, d_level, p.node_bytes);
-                B2_LAUNCH_CHECK(ctx);
-                B2_CUDA(ctx, cudaMemcpyAsync(h_level, d_level, sizeof(LevelInfo), cudaMemcpyDeviceToHost, s));
-                B2_CUDA(ctx, cudaStreamSynchronize(s));
-                if (h_level->error || next_level_start + (uint64_t)h_level->next_nodes > p.max_nodes)
-                    return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: node capacity exceeded (internal error)");
-                total_nodes = next_level_start;
-                level_start = next_level_start;
-                tri_cursor += h_level->level_tris;
-                nwork = h_level->next_nodes;
-                wcur ^= 1;
-                ++depth;
-                if (2 * depth > (uint32_t)TRAV_STACK)
-                    return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: the hierarchy is %u levels deep, the traversal stack holds %d entries (2 per level)",
-                                     depth, TRAV_STACK);
+            {
+                LoopGraph g(ctx);
+                if ((rc = g.begin())) return rc;
+                if ((rc = g.add((const void*)collapse_plan_kernel, wide_grid, 128, 0, (const CollapseState*)d_cst, (const uint32_t*)work[0], (const uint32_t*)work[1], (int)N,
+                                (const float4*)box_lo, (const float4*)box_hi, (const int2*)range, (const uint8_t*)height, child_tmp, counts, max_wide_depth()))) return rc;
+                if ((rc = dscan_add<unsigned long long>(g, counts, &d_cst->nwork, dsums, &d_cst->total))) return rc;
+                if ((rc = g.add((const void*)collapse_emit_kernel, wide_grid, 128, 0, d_cst, p.max_nodes, (int)N, (const float4*)box_lo, (const float4*)box_hi,
+                                (const int2*)range, (const int*)child_tmp, (const unsigned long long*)counts, work[0], work[1], dest, nodes_out, p.node_bytes))) return rc;
+                if ((rc = g.add((const void*)collapse_advance_kernel, 1, 1, 0, d_cst, p.max_nodes, g.cond()))) return rc;
+                if ((rc = g.launch(s))) return rc;
+                ctx->launches += 1;
             }
-            if (tri_cursor != N) return set_error(ctx, B200RT_ERROR_INVALID_OPERATION, "accel build: triangle count mismatch (%u != %u)", tri_cursor, N);
             // triangles go right after the node capacity region; compaction later closes the gap
             hv.tris_off = HEADER_BYTES + (uint64_t)p.max_nodes * p.node_bytes;
             scatter_tris_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], dest, N, (float4*)(out + hv.tris_off));
@@ -1211,17 +1388,17 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         } else {
             hv.tris_off = HEADER_BYTES;
         }
-        hv.num_nodes = total_nodes;
-        hv.depth = depth;
         hv.node_bytes = p.node_bytes;
         hv.anyhit = any_anyhit;
-        hv.total_bytes = HEADER_BYTES + (uint64_t)total_nodes * p.node_bytes + (uint64_t)N * TRI_BYTES;
-        exact_bytes = hv.total_bytes;
-        write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds);
+        B2_REQUIRE(ctx, num_emitted <= 2, "at most two emitted properties");
+        write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds, N > 0 ? d_cst : nullptr, num_emitted > 0 ? (unsigned long long*)emitted[0].result : nullptr,
+                                            num_emitted > 1 ? (unsigned long long*)emitted[1].result : nullptr);
         B2_LAUNCH_CHECK(ctx);
-        log_msg(ctx, 4, "accel", "GAS: %u triangles, %u nodes, depth %u, %llu bytes", N, total_nodes, depth, (unsigned long long)exact_bytes);
+        log_msg(ctx, 4, "accel", "GAS build enqueued: %u triangles, node capacity %u, %u-byte nodes", N, p.max_nodes, p.node_bytes);
+        *handle = out;
+        return 0;
     }
-    for (unsigned i = 0; i < num_emitted; ++i) {
+    for (unsigned i = 0; i < num_emitted; ++i) {  // instance acceleration structures: the size is known here
         const size_t v = align_up(exact_bytes, 128);
         B2_CUDA(ctx, cudaMemcpyAsync((void*)emitted[i].result, &v, sizeof(size_t), cudaMemcpyHostToDevice, s));
     }
@@ -1229,10 +1406,43 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
     return 0;
 }
 
-__global__ void patch_header_kernel(AccelHeader* h, uint64_t tris_off, uint32_t max_nodes)
+// optixAccelCompact (optixPathTracer.cpp:671-683) is asynchronous like the build: the sizes are in the header, which only the device
+// has, so one grid-stride kernel reads it there, copies the used part of the node array and the triangle records behind it, and
+// writes the patched header.  A blob that is not a b200rt traversable, or an output buffer that is too small, leaves a header with the
+// error field set and no handle contents (error 4 / 5); accel_get_info reports it.
+__global__ void __launch_bounds__(256) compact_kernel(const char* __restrict__ in, char* __restrict__ out, size_t out_bytes)
 {
-    h->tris_off = tris_off;
-    h->max_nodes = max_nodes;
+    const AccelHeader h = *(const AccelHeader*)in;
+    const bool ok = h.magic == ACCEL_MAGIC && out_bytes >= h.total_bytes;
+    if (!ok) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && out_bytes >= HEADER_BYTES) {
+            AccelHeader e = {};
+            e.magic = ACCEL_MAGIC; e.kind = ACCEL_KIND_GAS; e.nodes_off = HEADER_BYTES; e.tris_off = HEADER_BYTES; e.total_bytes = HEADER_BYTES;
+            e.node_bytes = NODE8_BYTES; e.error = h.magic == ACCEL_MAGIC ? 5u : 4u;
+            *(AccelHeader*)out = e;
+        }
+        return;
+    }
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    if (h.kind == ACCEL_KIND_IAS) {
+        const size_t n16 = (size_t)(h.total_bytes / 16);
+        for (size_t i = tid; i < n16; i += nthreads) ((uint4*)out)[i] = __ldg((const uint4*)in + i);
+        return;
+    }
+    const size_t node_bytes = (size_t)h.num_nodes * (h.node_bytes ? h.node_bytes : NODE8_BYTES);
+    const size_t nn16 = node_bytes / 16, nt16 = (size_t)h.num_tris * (TRI_BYTES / 16);
+    const uint4* src_nodes = (const uint4*)(in + HEADER_BYTES);
+    const uint4* src_tris = (const uint4*)(in + h.tris_off);
+    uint4* dst_nodes = (uint4*)(out + HEADER_BYTES);
+    uint4* dst_tris = (uint4*)(out + HEADER_BYTES + node_bytes);
+    for (size_t i = tid; i < nn16; i += nthreads) dst_nodes[i] = __ldcs(src_nodes + i);
+    for (size_t i = tid; i < nt16; i += nthreads) dst_tris[i] = __ldcs(src_tris + i);
+    if (tid == 0) {
+        AccelHeader v = h;
+        v.tris_off = HEADER_BYTES + node_bytes;
+        v.max_nodes = h.num_nodes;
+        *(AccelHeader*)out = v;
+    }
 }
 
 int accel_compact(b200rt_context ctx, cudaStream_t s, b200rt_traversable input, b200rt_deviceptr out, size_t out_bytes,
@@ -1240,22 +1450,10 @@ int accel_compact(b200rt_context ctx, cudaStream_t s, b200rt_traversable input, 
 {
     B2_REQUIRE(ctx, input && out && handle, "null argument");
     B2_REQUIRE(ctx, (out % B200RT_ACCEL_BUFFER_BYTE_ALIGNMENT) == 0, "outputBuffer must be 128-byte aligned");
+    B2_REQUIRE(ctx, out_bytes >= HEADER_BYTES, "outputBuffer too small (%zu bytes)", out_bytes);
     DeviceGuard guard(ctx->device);
-    AccelHeader h;
-    B2_CUDA(ctx, cudaMemcpyAsync(&h, (const void*)input, sizeof(h), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(ctx, cudaStreamSynchronize(s));
-    B2_REQUIRE(ctx, h.magic == ACCEL_MAGIC, "not a b200rt traversable");
-    B2_REQUIRE(ctx, out_bytes >= h.total_bytes, "outputBuffer too small (%zu < %llu)", out_bytes, (unsigned long long)h.total_bytes);
-    if (h.kind == ACCEL_KIND_IAS) {
-        B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, h.total_bytes, cudaMemcpyDeviceToDevice, s));
-    } else {
-        const size_t node_bytes = (size_t)h.num_nodes * (h.node_bytes ? h.node_bytes : NODE8_BYTES);
-        B2_CUDA(ctx, cudaMemcpyAsync((void*)out, (const void*)input, HEADER_BYTES + node_bytes, cudaMemcpyDeviceToDevice, s));
-        B2_CUDA(ctx, cudaMemcpyAsync((void*)(out + HEADER_BYTES + node_bytes), (const void*)(input + h.tris_off),
-                                     (size_t)h.num_tris * TRI_BYTES, cudaMemcpyDeviceToDevice, s));
-        patch_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, HEADER_BYTES + node_bytes, h.num_nodes);
-        B2_LAUNCH_CHECK(ctx);
-    }
+    compact_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, s>>>((const char*)input, (char*)out, out_bytes);
+    B2_LAUNCH_CHECK(ctx);
     *handle = out;
     return 0;
 }
@@ -1267,6 +1465,11 @@ int accel_get_info(b200rt_context ctx, b200rt_traversable handle, b200rt_accel_i
     AccelHeader h;
     B2_CUDA(ctx, cudaMemcpy(&h, (const void*)handle, sizeof(h), cudaMemcpyDeviceToHost));
     B2_REQUIRE(ctx, h.magic == ACCEL_MAGIC, "not a b200rt traversable");
+    // builds and compactions are asynchronous: what went wrong on the device is in the header
+    B2_REQUIRE(ctx, h.error == 0, "the acceleration structure is invalid: %s",
+               h.error == 1 ? "node capacity exceeded during the build (internal error)" : h.error == 2 ? "triangle count mismatch after the build (internal error)" :
+               h.error == 3 ? "clustering failed during the build (internal error)" : h.error == 4 ? "compaction source was not a b200rt traversable" :
+               h.error == 5 ? "compaction output buffer too small" : "unknown error");
     info->kind = h.kind;
     info->num_triangles = h.num_tris;
     info->num_nodes = h.num_nodes;

@@ -16,6 +16,7 @@ struct Workspace {
     void* ptr = nullptr;
     size_t bytes = 0;
 };
+struct PTGraphCache;
 
 }  // namespace b200rt
 
@@ -29,21 +30,24 @@ struct b200rt_context_t {
     std::string last_error;
     // wavefront workspace (lane state, queues, counters); grown on demand, owned by the context
     b200rt::Workspace ws;
-    void* pinned = nullptr;   // small pinned host block for counter read-back
+    void* pinned = nullptr;   // small pinned host block for counter read-back and the asynchronous error flags the kernels write
+    // Launches that keep their state in `ws` are ordered by their stream; a launch on ANOTHER stream first waits for `ev`, recorded at
+    // the end of the last launch that used the workspace (ws_acquire / ws_release): two streams never see the lane state of each other.
     cudaEvent_t ev = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_busy = false;
+    b200rt::PTGraphCache* pt_graphs = nullptr;  // instantiated wavefront-loop graphs of the path-tracer launches (pathtracer.cu)
     std::mutex mu;
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING
     unsigned int counter_slot = 0;  // rotating fetch-counter slot for persistent ray launches
     // whitted launches: light count the workspace was sized for, learnt from the first launch with a given d_params (whitted.cu)
     uint64_t w_params = 0, w_sbt = 0;
     unsigned int w_lights = 0, w_sbt_count = 0;
-    bool w_anyhit = false;    // the scene holds geometry that runs the any-hit programs (AccelHeader::anyhit of LaunchParams.handle)
     bool w_blend = false;     // the hit-group records hold an ALPHA_MODE_BLEND material (continuation levels are run)
-    // optixRaycasting launches: does the traversable of this d_params hold any-hit geometry?  (read once per d_params, forgotten at
-    // the next accel build)
-    uint64_t rc_params[4] = {0, 0, 0, 0};   // the sample launches two Params blocks alternately (optixRaycasting.cpp:291-313)
-    bool rc_anyhit[4] = {false, false, false, false};
-    unsigned int rc_next = 0;
+    // imgui_test launches: samples_per_frame / nlights of the Params block at pg_params, read on the first launch with it (playground.cu)
+    uint64_t pg_params = 0;
+    unsigned int pg_spf = 0;
+    int pg_nlights = 0;
     uint64_t launches = 0;    // kernels launched through this context (bench: gpu_launches)
 };
 
@@ -60,6 +64,17 @@ inline unsigned persistent_grid(b200rt_context ctx, uint64_t n, int block, int c
 int set_error(b200rt_context ctx, int code, const char* fmt, ...);
 void log_msg(b200rt_context ctx, int level, const char* tag, const char* fmt, ...);
 int ensure_workspace(b200rt_context ctx, size_t bytes, cudaStream_t stream);
+// bracket every launch whose kernels read or write ctx->ws (caller holds ctx->mu)
+inline void ws_acquire(b200rt_context ctx, cudaStream_t s)
+{
+    if (ctx->ws_busy && ctx->ws_stream != s) cudaStreamWaitEvent(s, ctx->ev, 0);
+}
+inline void ws_release(b200rt_context ctx, cudaStream_t s)
+{
+    cudaEventRecord(ctx->ev, s);
+    ctx->ws_stream = s;
+    ctx->ws_busy = true;
+}
 
 struct DeviceGuard {
     int prev = -1;

@@ -38,4 +38,6 @@ int launch_pathtracer(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, c
 int fill_samples(b200rt_context, cudaStream_t, int, int, int, int, b200rt_deviceptr, int);
 int deinterleave(b200rt_context, cudaStream_t, b200rt_deviceptr, int, int, int, int, b200rt_deviceptr, b200rt_deviceptr);
 int generate_synthetic_mesh(b200rt_context, cudaStream_t, uint64_t, uint32_t, b200rt_deviceptr, b200rt_deviceptr, float*);
+void pathtracer_release(b200rt_context);  // destroys the context's launch graphs
+uint64_t pathtracer_graph_kernels(b200rt_context);  // kernels run inside launch graphs so far
 }  // namespace b200rt

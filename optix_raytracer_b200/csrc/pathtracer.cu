@@ -102,7 +102,7 @@ struct Counters {
     unsigned int n_ext[2];   // lanes with an extension ray to trace (dense list ext_list)
     unsigned int n_shd[2];   // lanes with a pending shadow ray (dense list shd_list)
     unsigned int fetch;      // work-item cursor of the persistent trace kernel (zeroed by INIT / SHADE)
-    unsigned int pad;
+    unsigned int iterations; // wavefront iterations run so far (written by the loop-condition kernel of the launch graph)
     unsigned long long radiance_segments, shadow_segments;
     unsigned long long nodes_fetched, tris_tested;
 };
@@ -793,6 +793,136 @@ __global__ void __launch_bounds__(256) synth_mesh_kernel(SynthLayout s, uint32_t
     mats[t] = mat;
 }
 
+// ---- the wavefront loop as a CUDA graph ---------------------------------------------------------------------------------------------
+// while (active lanes) { TRACE(0); SHADE(0); TRACE(1); SHADE(1); }  — a conditional WHILE node whose condition the last kernel of the
+// body sets from the queue count on the device.  The body holds two iterations so that every kernel node has a fixed `cur`.  The graph
+// is instantiated once per (mode, Params address, workspace, launch size, SBT) and relaunched for every subframe.
+struct PTAsyncFlags {  // in the context's pinned block: written by the device, read by the host without synchronisation
+    unsigned int runaway;                // the loop hit its iteration cap (reported by the next launch)
+    unsigned int pad;
+    unsigned long long graph_kernels;    // kernels run inside launch graphs so far (b200rt_context_kernel_launches adds them)
+};
+constexpr size_t PT_ASYNC_FLAGS_OFFSET = 2048;  // inside ctx->pinned (4096 bytes; whitted.cu keeps its flags at 1024)
+
+__global__ void pt_loop_cond_kernel(Counters* __restrict__ c, cudaGraphConditionalHandle h, PTAsyncFlags* __restrict__ flags)
+{
+    const unsigned int it = c->iterations + 2u;
+    c->iterations = it;
+    unsigned int more = c->qcount[0] != 0u ? 1u : 0u;  // SHADE(cur = 1) filled queue 0
+    if (more && it > 200000u) { flags->runaway = 1u; more = 0u; }
+    atomicAdd_system(&flags->graph_kernels, 5ull);
+    cudaGraphSetConditional(h, more);
+}
+
+struct PTLoopArgs {
+    int mode;
+    const void* params;
+    Lanes ln;
+    bool travstats;
+    unsigned trace_grid, shade_grid;
+    const char* hg_base;
+    uint32_t hg_stride, hg_count;
+    const char* miss_base;
+};
+struct PTGraphEntry {
+    bool valid = false;
+    PTLoopArgs key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+struct PTGraphCache { PTGraphEntry e[4]; unsigned next = 0; };
+
+static bool same_loop(const PTLoopArgs& a, const PTLoopArgs& b)
+{
+    return a.mode == b.mode && a.params == b.params && !memcmp(&a.ln, &b.ln, sizeof(Lanes)) && a.travstats == b.travstats && a.trace_grid == b.trace_grid &&
+           a.shade_grid == b.shade_grid && a.hg_base == b.hg_base && a.hg_stride == b.hg_stride && a.hg_count == b.hg_count && a.miss_base == b.miss_base;
+}
+
+uint64_t pathtracer_graph_kernels(b200rt_context ctx) { return ((const volatile PTAsyncFlags*)((char*)ctx->pinned + PT_ASYNC_FLAGS_OFFSET))->graph_kernels; }
+
+void pathtracer_release(b200rt_context ctx)
+{
+    if (!ctx->pt_graphs) return;
+    for (PTGraphEntry& e : ctx->pt_graphs->e) {
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+        if (e.graph) cudaGraphDestroy(e.graph);
+    }
+    delete ctx->pt_graphs;
+    ctx->pt_graphs = nullptr;
+}
+
+template <int MODE>
+static int launch_pt_loop_graph(b200rt_context ctx, cudaStream_t s, const PTLoopArgs& la)
+{
+    PTAsyncFlags* flags = (PTAsyncFlags*)((char*)ctx->pinned + PT_ASYNC_FLAGS_OFFSET);
+    if (flags->runaway) {
+        flags->runaway = 0;
+        return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "an earlier path-tracer launch did not terminate (its loop was cut off after 200000 iterations)");
+    }
+    if (!ctx->pt_graphs) ctx->pt_graphs = new PTGraphCache();
+    PTGraphCache& cache = *ctx->pt_graphs;
+    PTGraphEntry* ent = nullptr;
+    for (PTGraphEntry& e : cache.e)
+        if (e.valid && same_loop(e.key, la)) ent = &e;
+    if (!ent) {
+        ent = &cache.e[cache.next++ % 4u];
+        if (ent->exec) { cudaGraphExecDestroy(ent->exec); ent->exec = nullptr; }
+        if (ent->graph) { cudaGraphDestroy(ent->graph); ent->graph = nullptr; }
+        ent->valid = false;
+        // a zeroed Lanes has padding bytes: the key is compared with memcmp, so it is copied whole
+        memcpy(&ent->key, &la, sizeof(PTLoopArgs));
+        B2_CUDA(ctx, cudaGraphCreate(&ent->graph, 0));
+        cudaGraphConditionalHandle cond;
+        B2_CUDA(ctx, cudaGraphConditionalHandleCreate(&cond, ent->graph, 1u, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t loop;
+        B2_CUDA(ctx, cudaGraphAddNode(&loop, ent->graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        cudaGraphNode_t prev = nullptr;
+        Lanes ln = la.ln;
+        const void* params = la.params;
+        const char* hg_base = la.hg_base;
+        uint32_t hg_stride = la.hg_stride, hg_count = la.hg_count;
+        const char* miss_base = la.miss_base;
+        for (int cur = 0; cur < 2; ++cur) {
+            int c = cur;
+            void* targs[3] = {(void*)&params, (void*)&ln, (void*)&c};
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            kp.func = la.travstats ? (void*)pt_trace_kernel<MODE, true> : (void*)pt_trace_kernel<MODE, false>;
+            kp.gridDim = dim3(la.trace_grid); kp.blockDim = dim3(COOP_BLOCK); kp.kernelParams = targs;
+            cudaGraphNode_t nt;
+            B2_CUDA(ctx, cudaGraphAddKernelNode(&nt, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+            void* sargs[7] = {(void*)&params, (void*)&ln, (void*)&c, (void*)&hg_base, (void*)&hg_stride, (void*)&hg_count, (void*)&miss_base};
+            memset(&kp, 0, sizeof(kp));
+            kp.func = (void*)pt_shade_kernel<MODE>;
+            kp.gridDim = dim3(la.shade_grid); kp.blockDim = dim3(256); kp.kernelParams = sargs;
+            cudaGraphNode_t ns;
+            B2_CUDA(ctx, cudaGraphAddKernelNode(&ns, body, &nt, 1, &kp));
+            prev = ns;
+        }
+        {
+            Counters* cnt = ln.counters;
+            void* cargs[3] = {(void*)&cnt, (void*)&cond, (void*)&flags};
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            kp.func = (void*)pt_loop_cond_kernel;
+            kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = cargs;
+            cudaGraphNode_t nc;
+            B2_CUDA(ctx, cudaGraphAddKernelNode(&nc, body, &prev, 1, &kp));
+        }
+        B2_CUDA(ctx, cudaGraphInstantiate(&ent->exec, ent->graph, 0));
+        ent->valid = true;
+        log_msg(ctx, 4, "pathtracer", "wavefront loop graph instantiated (mode %d, %u lanes, trace grid %u)", MODE, ln.nlaunch * ln.groups, la.trace_grid);
+    }
+    B2_CUDA(ctx, cudaGraphLaunch(ent->exec, s));
+    return 0;
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 template <int MODE>
 static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params, const b200rt_shader_binding_table* sbt, uint32_t nlaunch,
@@ -842,6 +972,7 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     uint32_t* sort_vals[2] = {(uint32_t*)(W + o_sv0), (uint32_t*)(W + o_sv1)};
 
     const uint64_t launches0 = ctx->launches;
+    ws_acquire(ctx, s);
     B2_CUDA(ctx, cudaMemsetAsync(ln.counters, 0, sizeof(Counters), s));
     const unsigned grid = persistent_grid(ctx, nlanes, 256, 8);
     const void* params = (const void*)d_params;
@@ -866,61 +997,81 @@ static int run_pathtracer(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d
     const unsigned trace_grid_stats = std::min(work_cap, (unsigned)(std::max(occ_stats, 1) * ctx->sm_count));
     const uint32_t want = (opt && opt->stats) ? opt->collect_stats : 0u;
     const bool timing = (want & B200RT_PT_STATS_TIMING) != 0, travstats = (want & B200RT_PT_STATS_TRAVERSAL) != 0;
-    size_t nev = 0;
-    auto next_event = [&]() -> cudaEvent_t {
-        if (nev == ctx->timing_events.size()) {
-            cudaEvent_t e = nullptr;
-            cudaEventCreate(&e);
-            ctx->timing_events.push_back(e);
-        }
-        return ctx->timing_events[nev++];
-    };
-    int cur = 0;
+    static const bool force_host_loop = [] { const char* e = getenv("B200RT_PT_HOST_LOOP"); return e && atoi(e) != 0; }();
     uint32_t iterations = 0;
-    const int CHECK_EVERY = sorting ? 1 : 8;
-    for (;;) {
-        for (int k = 0; k < CHECK_EVERY; ++k) {
-            ln.items = nullptr;
-            if (sorting && iterations > 0) {
-                // the counts of this iteration's rays are on the host (read below); camera rays (iteration 0) are coherent as they are
-                const uint32_t n_rays = h_cnt->n_ext[cur] + h_cnt->n_shd[cur];
-                if (n_rays >= 65536u) {
-                    pt_build_items_kernel<<<persistent_grid(ctx, n_rays, 256, 8), 256, 0, s>>>(ln, cur, sort_keys[0], sort_vals[0]);
-                    B2_LAUNCH_CHECK(ctx);
-                    int res = 0;
-                    rc = radix_sort_pairs32(ctx, s, sort_keys, sort_vals, n_rays, SORT_PASSES, (uint32_t*)(W + o_hist), (uint32_t*)(W + o_scan), &res);
-                    if (rc) return rc;
-                    ln.items = sort_vals[res];
-                }
+    size_t nev = 0;
+    if (!timing && !sorting && !force_host_loop) {
+        // ---- asynchronous form: the wavefront loop is a CUDA graph with a conditional WHILE node, launched into the caller's stream.
+        // Nothing here waits for the device: optixLaunch is asynchronous by contract (SURVEY 8(b) "Threading"; the reference's one-thread
+        // loop over devices, optixMultiGPU.cpp:562-594, relies on it), and so is this launch unless statistics are asked for.
+        PTLoopArgs la;
+        la.mode = MODE; la.params = params; la.ln = ln; la.travstats = travstats;
+        la.trace_grid = travstats ? trace_grid_stats : trace_grid; la.shade_grid = grid;
+        la.hg_base = (const char*)sbt->hitgroupRecordBase; la.hg_stride = sbt->hitgroupRecordStrideInBytes; la.hg_count = sbt->hitgroupRecordCount;
+        la.miss_base = (const char*)sbt->missRecordBase;
+        rc = launch_pt_loop_graph<MODE>(ctx, s, la);
+        if (rc) return rc;
+    } else {
+        // ---- host-driven form (per-stage CUDA events, ray sorting): the host reads the queue counts, so this form synchronises
+        auto next_event = [&]() -> cudaEvent_t {
+            if (nev == ctx->timing_events.size()) {
+                cudaEvent_t e = nullptr;
+                cudaEventCreate(&e);
+                ctx->timing_events.push_back(e);
             }
-            if (timing) cudaEventRecord(next_event(), s);
-            if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, COOP_BLOCK, 0, s>>>(params, ln, cur);
-            else pt_trace_kernel<MODE, false><<<trace_grid, COOP_BLOCK, 0, s>>>(params, ln, cur);
-            B2_LAUNCH_CHECK(ctx);
-            if (timing) cudaEventRecord(next_event(), s);
-            pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,
-                                                       sbt->hitgroupRecordCount, (const char*)sbt->missRecordBase);
-            B2_LAUNCH_CHECK(ctx);
-            if (timing) cudaEventRecord(next_event(), s);
-            cur ^= 1;
-            ++iterations;
+            return ctx->timing_events[nev++];
+        };
+        int cur = 0;
+        const int CHECK_EVERY = sorting ? 1 : 8;
+        for (;;) {
+            for (int k = 0; k < CHECK_EVERY; ++k) {
+                ln.items = nullptr;
+                if (sorting && iterations > 0) {
+                    // the counts of this iteration's rays are on the host (read below); camera rays (iteration 0) are coherent as they are
+                    const uint32_t n_rays = h_cnt->n_ext[cur] + h_cnt->n_shd[cur];
+                    if (n_rays >= 65536u) {
+                        pt_build_items_kernel<<<persistent_grid(ctx, n_rays, 256, 8), 256, 0, s>>>(ln, cur, sort_keys[0], sort_vals[0]);
+                        B2_LAUNCH_CHECK(ctx);
+                        int res = 0;
+                        rc = radix_sort_pairs32(ctx, s, sort_keys, sort_vals, n_rays, SORT_PASSES, (uint32_t*)(W + o_hist), (uint32_t*)(W + o_scan), &res);
+                        if (rc) return rc;
+                        ln.items = sort_vals[res];
+                    }
+                }
+                if (timing) cudaEventRecord(next_event(), s);
+                if (travstats) pt_trace_kernel<MODE, true><<<trace_grid_stats, COOP_BLOCK, 0, s>>>(params, ln, cur);
+                else pt_trace_kernel<MODE, false><<<trace_grid, COOP_BLOCK, 0, s>>>(params, ln, cur);
+                B2_LAUNCH_CHECK(ctx);
+                if (timing) cudaEventRecord(next_event(), s);
+                pt_shade_kernel<MODE><<<grid, 256, 0, s>>>(params, ln, cur, (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,
+                                                           sbt->hitgroupRecordCount, (const char*)sbt->missRecordBase);
+                B2_LAUNCH_CHECK(ctx);
+                if (timing) cudaEventRecord(next_event(), s);
+                cur ^= 1;
+                ++iterations;
+            }
+            B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, ln.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+            B2_CUDA(ctx, cudaStreamSynchronize(s));
+            if (h_cnt->qcount[cur] == 0) break;
+            if (iterations > 100000) return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "path tracer did not terminate");
         }
-        B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, ln.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(ctx, cudaStreamSynchronize(s));
-        if (h_cnt->qcount[cur] == 0) break;
-        if (iterations > 100000) return set_error(ctx, B200RT_ERROR_LAUNCH_FAILURE, "path tracer did not terminate");
     }
     if (groups > 1) {
         pt_resolve_kernel<MODE><<<div_up(nlaunch, 256), 256, 0, s>>>(params, ln);
         B2_LAUNCH_CHECK(ctx);
     }
+    ws_release(ctx, s);
     if (want) {
+        // statistics are read back: a launch that asks for them returns when it has finished
+        B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, ln.counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        if (iterations == 0) iterations = h_cnt->iterations;
         b200rt_pt_stats* st = opt->stats;
         memset(st, 0, sizeof(*st));
         st->radiance_segments = h_cnt->radiance_segments;
         st->shadow_segments = h_cnt->shadow_segments;
         st->iterations = iterations;
-        st->kernel_launches = (uint32_t)(ctx->launches - launches0);
+        st->kernel_launches = (uint32_t)(ctx->launches - launches0) + (nev == 0 && !sorting && h_cnt->iterations ? 5u * (h_cnt->iterations / 2u) : 0u);
         st->nodes_fetched = h_cnt->nodes_fetched;
         st->tris_tested = h_cnt->tris_tested;
         if (timing) {

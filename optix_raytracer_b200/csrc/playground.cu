@@ -79,14 +79,23 @@ static_assert(sizeof(PGParams) == 128 && offsetof(PGParams, camera) == 16 && off
 
 struct PGCounters { unsigned int nhit; unsigned int ncand; unsigned int pad[2]; };
 
+// What the host needs to shape a launch (samples per frame, light count) is read from Params once per Params address and kept
+// (ctx->pg_*); every launch's RAYGEN compares the live values with them on the device and reports a difference here, in the context's
+// pinned block — the launch after that returns an error and reads Params again.  Kernels take the light count from the HOST's value
+// (buffer strides) and never read more lights than Params holds now, so a stale value cannot run anything out of bounds.
+struct PGAsyncFlags { unsigned int params_changed; };
+constexpr size_t PG_ASYNC_FLAGS_OFFSET = 1536;  // inside ctx->pinned (whitted.cu: 1024, pathtracer.cu: 2048)
+
 // ---- RAYGEN: Camera::compute_ray (camera.h:127-144) --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t sample0,
                                                          uint32_t nlanes, float4* __restrict__ rays, uint32_t* __restrict__ cand,
-                                                         float4* __restrict__ payload, PGCounters* __restrict__ counters)
+                                                         float4* __restrict__ payload, PGCounters* __restrict__ counters, uint32_t host_spf,
+                                                         int host_nl, PGAsyncFlags* __restrict__ flags)
 {
     const uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
     bool candidate = false;
     float3 org = f3(0.f, 0.f, 0.f), dir = org;
+    if (lane == 0 && (params->samples_per_frame != host_spf || params->nlights != host_nl)) flags->params_changed = 1u;
     if (lane < nlanes) {
     const PGParams P = *params;
     const PGCamera cam = *P.camera;
@@ -147,12 +156,12 @@ __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restric
                                                         const float4* __restrict__ rays, const uint32_t* __restrict__ cand,
                                                         const ExtHit* __restrict__ hits, float4* __restrict__ payload,
                                                         float4* __restrict__ probes, float* __restrict__ ndw, uint2* __restrict__ hitinfo,
-                                                        PGCounters* __restrict__ counters)
+                                                        PGCounters* __restrict__ counters, int nl)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;   // candidate ray
     const uint32_t npix = width * height;
     const PGParams P = *params;
-    const int nl = P.nlights;
+    const int nl_live = min(nl, P.nlights);
     bool is_hit = false;
     ExtHit h;
     float4 ro, rd;
@@ -186,7 +195,9 @@ __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restric
     uint32_t seed = tea4(ix + width * iy, P.dt);
     const size_t pb = (size_t)k * (size_t)(nl + 1);
     for (int li = 0; li < nl; ++li) {
-        const PGLight l = P.lights[li];
+        PGLight l;
+        if (li < nl_live) l = P.lights[li];
+        else { l = PGLight{}; l.a[1] = 1.0f; l.tag = 1; }  // Params changed under the launch (reported by RAYGEN): a harmless stand-in
         const float3 wi = pg_light_wi(l, Pp, seed);
         ndw[pb + li] = dot(n, wi);
         probes[2 * (pb + li)] = make_float4(Pp.x, Pp.y, Pp.z, 0.01f);
@@ -214,11 +225,11 @@ __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restric
 // ---- RESOLVE: second half of __closesthit__ch ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_resolve_kernel(const PGParams* __restrict__ params, const uint32_t* __restrict__ occluded,
                                                           const float* __restrict__ ndw, const uint2* __restrict__ hitinfo,
-                                                          float4* __restrict__ payload, const PGCounters* __restrict__ counters)
+                                                          float4* __restrict__ payload, const PGCounters* __restrict__ counters, int nl)
 {
     const PGParams P = *params;
     const uint32_t nhit = counters->nhit;
-    const int nl = P.nlights;
+    const int nl_live = min(nl, P.nlights);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nhit; k += gridDim.x * blockDim.x) {
         const uint2 hi = hitinfo[k];
         int m = P.mat_indices[hi.y];
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(256) pg_resolve_kernel(const PGParams* __restr
         for (int li = 0; li < nl; ++li) {
             const float nd = ndw[pb + li];
             const bool dark = occluded[pb + li] != 0u || nd < 0.0f;
-            const float3 lumi = pg_light_lumi(P.lights[li]);
+            const float3 lumi = li < nl_live ? pg_light_lumi(P.lights[li]) : f3(0.f, 0.f, 0.f);
             // mat.f(...) * lights[li].lumi() * ndotwi
             const float3 term = f3((color.x * lumi.x) * nd, (color.y * lumi.y) * nd, (color.z * lumi.z) * nd);
             result = result + (dark ? f3(0.f, 0.f, 0.f) : term);
@@ -348,15 +359,31 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     B2_REQUIRE(ctx, npix64 < (1ull << 28), "launch too large");
     if (npix64 == 0) return 0;
     DeviceGuard guard(ctx->device);
-    // the launch needs nlights / samples_per_frame / the handle on the host to size its buffers: one 128-byte read-back
-    // (the reference allocates, copies and frees its device Params every frame, tracer_window.cpp:96-105)
-    PGParams hp;
-    B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, (const void*)d_params, sizeof(PGParams), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(ctx, cudaStreamSynchronize(s));
-    memcpy(&hp, ctx->pinned, sizeof(PGParams));
-    B2_REQUIRE(ctx, hp.camera && hp.film && hp.handle && hp.normals && hp.mat_indices && hp.materials, "Params has null pointers");
-    B2_REQUIRE(ctx, hp.nlights >= 0 && hp.nlights <= 64 && (hp.nlights == 0 || hp.lights), "bad light list");
-    B2_REQUIRE(ctx, hp.dt > 0, "Params::dt must be > 0 (frame_step() before the launch, tracer_window.cpp:93-94)");
+    // the launch needs nlights / samples_per_frame on the host to size its buffers and count its batches: one 128-byte read-back on
+    // the first launch with a given Params address (the reference allocates, copies and frees its device Params every frame,
+    // tracer_window.cpp:96-105); later launches are asynchronous and check the live values on the device (PGAsyncFlags)
+    PGAsyncFlags* flags = (PGAsyncFlags*)((char*)ctx->pinned + PG_ASYNC_FLAGS_OFFSET);
+    if (flags->params_changed) {
+        flags->params_changed = 0;
+        ctx->pg_params = 0;
+        return set_error(ctx, B200RT_ERROR_INVALID_OPERATION,
+                         "samples_per_frame or nlights of Params changed since they were first read for this Params address (the last frame was rendered "
+                         "with the old values); relaunch");
+    }
+    if (ctx->pg_params != d_params) {
+        PGParams hp0;
+        B2_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, (const void*)d_params, sizeof(PGParams), cudaMemcpyDeviceToHost, s));
+        B2_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(&hp0, ctx->pinned, sizeof(PGParams));
+        B2_REQUIRE(ctx, hp0.camera && hp0.film && hp0.handle && hp0.normals && hp0.mat_indices && hp0.materials, "Params has null pointers");
+        B2_REQUIRE(ctx, hp0.nlights >= 0 && hp0.nlights <= 64 && (hp0.nlights == 0 || hp0.lights), "bad light list");
+        B2_REQUIRE(ctx, hp0.dt > 0, "Params::dt must be > 0 (frame_step() before the launch, tracer_window.cpp:93-94)");
+        ctx->pg_params = d_params;
+        ctx->pg_spf = hp0.samples_per_frame;
+        ctx->pg_nlights = hp0.nlights;
+    }
+    struct { unsigned int samples_per_frame; int nlights; } hp = {ctx->pg_spf, ctx->pg_nlights};
+    const b200rt_deviceptr handle_dev = d_params + offsetof(PGParams, handle);  // the traversal reads the live handle from Params
     const uint32_t npix = (uint32_t)npix64, nl = (uint32_t)hp.nlights, np1 = nl + 1;
     // samples per batch: all of the frame's unless that takes more than ~8 GB of lane buffers (32 + 20 + 16 + 8 + 40 per probe bytes a lane)
     const size_t lane_bytes = 32 + sizeof(ExtHit) + 16 + 8 + (size_t)np1 * 40;
@@ -370,6 +397,7 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
                  o_info = take(8 * L), o_cand = take(4 * L);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
+    ws_acquire(ctx, s);
     char* W = (char*)ctx->ws.ptr;
     PGCounters* cnt = (PGCounters*)(W + o_cnt);
     float4* rays = (float4*)(W + o_rays);
@@ -391,20 +419,20 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
         const uint32_t nlanes = npix * nb;
         const unsigned lgrid = div_up(nlanes, 256);
         B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(PGCounters), s));
-        pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cand, payload, cnt);
+        pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cand, payload, cnt, hp.samples_per_frame, hp.nlights, flags);
         B2_LAUNCH_CHECK(ctx);
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)rays, nlanes, &cnt->ncand, 1, 0, 0u, (b200rt_deviceptr)hits);
+        rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)rays, nlanes, &cnt->ncand, 1, 0, 0u, (b200rt_deviceptr)hits, 0, 0, handle_dev);
         if (rc) return rc;
-        pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, cand, hits, payload, probes, ndw, info, cnt);
+        pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, cand, hits, payload, probes, ndw, info, cnt, hp.nlights);
         B2_LAUNCH_CHECK(ctx);
         // shadow probes: TERMINATE_ON_FIRST_HIT | CULL_DISABLED_ANYHIT (optixTriangle.cu:213-223); the bounce probe carries no flags
         // but is only asked hit / no hit, so both kinds go through one any-hit batch; the last ray of every group of nl + 1 (the
         // bounce probe) ignores CULL_DISABLED_ANYHIT.  With the sample's OPTIX_GEOMETRY_FLAG_NONE build input nothing is culled;
         // a DISABLE_ANYHIT geometry is invisible to the light probes, exactly as in OptiX.
-        rc = trace_buffer(ctx, s, hp.handle, (b200rt_deviceptr)probes, (uint64_t)nlanes * np1, &cnt->nhit, np1, 1, 64u /* CULL_DISABLED_ANYHIT */,
-                          (b200rt_deviceptr)occ, np1);
+        rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)probes, (uint64_t)nlanes * np1, &cnt->nhit, np1, 1, 64u /* CULL_DISABLED_ANYHIT */,
+                          (b200rt_deviceptr)occ, np1, 0, handle_dev);
         if (rc) return rc;
-        pg_resolve_kernel<<<std::min<unsigned>(lgrid, (unsigned)ctx->sm_count * 8u), 256, 0, s>>>(dp, occ, ndw, info, payload, cnt);
+        pg_resolve_kernel<<<std::min<unsigned>(lgrid, (unsigned)ctx->sm_count * 8u), 256, 0, s>>>(dp, occ, ndw, info, payload, cnt, hp.nlights);
         B2_LAUNCH_CHECK(ctx);
         pg_accumulate_kernel<<<grid, 256, 0, s>>>(npix, nb, smp == 0 ? 1 : 0, payload, sum);
         B2_LAUNCH_CHECK(ctx);
@@ -412,6 +440,7 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
     }
     pg_finish_kernel<<<grid, 256, 0, s>>>(dp, width, height, sum);
     B2_LAUNCH_CHECK(ctx);
+    ws_release(ctx, s);
     if (opt && opt->stats && opt->collect_stats) {
         b200rt_pt_stats* st = opt->stats;
         memset(st, 0, sizeof(*st));

@@ -189,13 +189,19 @@ struct RaycastParamsDev { uint64_t handle; const float4* rays; float4* hits; }; 
 #ifndef B200RT_RAY_MIN_CTAS
 #define B200RT_RAY_MIN_CTAS 8
 #endif
+// AH: this instantiation carries the any-hit machinery (anyhit.cuh).  Launches that HAVE any-hit programs (KIND 2 with records long
+// enough to hold material and texture coordinates; the whitted stages) enqueue BOTH instantiations with DUAL set: each reads
+// AccelHeader::anyhit on the device and returns at once unless the traversable is its kind — scenes without any-hit geometry run the
+// plain kernel at its full speed (a merged kernel measured 8 % slower on the Duck ray buffers: twice the shared memory, more spills), the
+// other launch costs about two microseconds, and no decision rests on what the host remembers of an earlier launch (another handle may
+// have been written into the same Params block).
 template <int KIND, bool STATS, bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_kernel(const AccelHeader* __restrict__ handle, const float4* __restrict__ rays, uint32_t n,
                                                           uint32_t ray_flags, ExtHit* __restrict__ ext, uint32_t* __restrict__ occluded,
                                                           const RaycastParamsDev* __restrict__ rc_params, const char* __restrict__ hg_base,
                                                           uint32_t hg_stride, uint32_t hg_count, unsigned int* __restrict__ counter,
                                                           unsigned long long* __restrict__ stats, const unsigned int* __restrict__ n_dev,
-                                                          uint32_t n_mult, uint32_t flag_period, AnyHitCfg ah)
+                                                          uint32_t n_mult, uint32_t flag_period, AnyHitCfg ah, uint32_t dual)
 {
     if (n_dev) n = min(n, *n_dev * n_mult);  // ray count produced on the device by an earlier stage (playground.cu)
     if (KIND != 2 && hg_base) handle = (const AccelHeader*)*(const uint64_t*)hg_base;  // traversable handle read from device memory (whitted.cu)
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_ke
     w.flag_period = flag_period;
     w.handle = handle; w.rays = rays; w.hits = nullptr;
     if (KIND == 2) { const RaycastParamsDev P = *rc_params; w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits; }
+    if (dual && (w.handle->anyhit != 0u) != AH) return;
     w.ray_flags = ray_flags; w.ext = ext; w.occluded = occluded;
     w.hg_base = hg_base; w.hg_stride = hg_stride; w.hg_count = hg_count; w.item = 0;
     TravStats st{0, 0};
@@ -292,7 +299,7 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
     if (rc) return rc;
     trace_rays_kernel<0, false, false><<<persistent_grid_rays<0, false>(ctx, n), COOP_BLOCK, 0, s>>>(
         (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, ray_flags, (ExtHit*)ext, nullptr, nullptr, nullptr, 0, 0, counter, nullptr, nullptr, 1u, 0u,
-        AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
+        AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, 0u);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -309,7 +316,7 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
     if (rc) return rc;
     trace_rays_kernel<1, false, false><<<persistent_grid_rays<1, false>(ctx, n), COOP_BLOCK, 0, s>>>(
         (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, ray_flags, nullptr, (uint32_t*)occ, nullptr, nullptr, 0, 0, counter, nullptr, nullptr, 1u, 0u,
-        AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
+        AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, 0u);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -328,7 +335,7 @@ int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b
     B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
     if (n) {
         trace_rays_kernel<0, true, false><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>(
-            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, 0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
+            (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, 0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, 0u);
         ctx->launches++;
     }
     unsigned long long h[2] = {0, 0};
@@ -356,38 +363,19 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
     // __anyhit__texture_mask (optixRaycasting.cu:89-102) needs the material and the texture coordinates of whitted::HitGroupData (a
-    // record too short to hold them runs without any-hit programs) and only ever runs on geometry that leaves any-hit enabled: whether
-    // the traversable has any is read from its header once per d_params (one synchronisation; forgotten at the next accel build)
+    // record too short to hold them runs without any-hit programs); whether the traversable holds geometry that runs any-hit programs
+    // at all is decided on the device (trace_rays_kernel), so the launch never waits for anything
     const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
-    bool anyhit = false;
+    const uint32_t dual = full_records ? 1u : 0u;
+    trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
+        nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
+        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
     if (full_records) {
-        int slot = -1;
-        for (int i = 0; i < 4; ++i)
-            if (ctx->rc_params[i] == d_params) slot = i;
-        if (slot < 0) {
-            RaycastParamsDev hp;
-            B2_CUDA(ctx, cudaMemcpyAsync(&hp, (const void*)d_params, sizeof(hp), cudaMemcpyDeviceToHost, s));
-            B2_CUDA(ctx, cudaStreamSynchronize(s));
-            B2_REQUIRE(ctx, hp.handle, "Params.handle is null");
-            AccelHeader ah;
-            B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
-            B2_CUDA(ctx, cudaStreamSynchronize(s));
-            B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "Params.handle is not a b200rt traversable");
-            slot = (int)(ctx->rc_next++ % 4u);
-            ctx->rc_params[slot] = d_params;
-            ctx->rc_anyhit[slot] = ah.anyhit != 0;
-        }
-        anyhit = ctx->rc_anyhit[slot];
-    }
-    if (anyhit) {
+        B2_LAUNCH_CHECK(ctx);
         const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, AH_TEXTURE_MASK};
         trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
             nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah);
-    } else {
-        trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
-            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE});
+            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah, dual);
     }
     B2_LAUNCH_CHECK(ctx);
     return 0;
@@ -411,19 +399,19 @@ int trace_buffer(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, 
         if (kind == 0)
             trace_rays_kernel<0, false, true><<<persistent_grid_rays<0, false, true>(ctx, n_max), COOP_BLOCK, 0, s>>>(
                 (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, (const char*)handle_dev, 0, 0,
-                counter, nullptr, n_dev, n_mult, flag_period, ah);
+                counter, nullptr, n_dev, n_mult, flag_period, ah, 0u);
         else
             trace_rays_kernel<1, false, true><<<persistent_grid_rays<1, false, true>(ctx, n_max), COOP_BLOCK, 0, s>>>(
                 (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, (const char*)handle_dev, 0, 0, counter,
-                nullptr, n_dev, n_mult, flag_period, ah);
+                nullptr, n_dev, n_mult, flag_period, ah, 0u);
     } else if (kind == 0)
         trace_rays_kernel<0, false, false><<<persistent_grid_rays<0, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, (ExtHit*)out, (uint32_t*)sbt_out, nullptr, (const char*)handle_dev, 0, 0,
-            counter, nullptr, n_dev, n_mult, flag_period, noah);
+            counter, nullptr, n_dev, n_mult, flag_period, noah, 0u);
     else
         trace_rays_kernel<1, false, false><<<persistent_grid_rays<1, false>(ctx, n_max), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n_max, ray_flags, nullptr, (uint32_t*)out, nullptr, (const char*)handle_dev, 0, 0, counter,
-            nullptr, n_dev, n_mult, flag_period, noah);
+            nullptr, n_dev, n_mult, flag_period, noah, 0u);
     B2_LAUNCH_CHECK(ctx);
     return 0;
 }

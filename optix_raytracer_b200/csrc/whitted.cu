@@ -352,11 +352,14 @@ struct WPrimaryWork {
     }
 };
 
-// AH: the traversable holds geometry that runs the any-hit programs (the host read AccelHeader::anyhit with the light count)
+// Both instantiations are enqueued; each reads AccelHeader::anyhit on the device and returns at once unless the traversable is its
+// kind (raycast.cu: trace_rays_kernel): opaque scenes pay nothing for the any-hit machinery, and the choice cannot go stale when
+// another handle is written into the same LaunchParams block.
 template <bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const __grid_constant__ WK k, uint32_t n_items)
 {
     const AccelHeader* handle = (const AccelHeader*)k.params->handle;
+    if ((handle->anyhit != 0u) != AH) return;
     if (k.level == 0) n_items = k.counters->nprimary;  // counted by RAYGEN
     WPrimaryWork<AH> work(k, handle);
     trace_persistent(work, n_items, k.fetch, nullptr);
@@ -568,6 +571,7 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const 
 {
     const WParams* P = k.params;
     const AccelHeader* handle = (const AccelHeader*)P->handle;
+    if ((handle->anyhit != 0u) != AH) return;
     const uint32_t end = min(k.counters->nslots, k.cap_slots);
     const uint32_t nl = min(P->lights.count, k.nl_cap);
     const uint32_t n_items = end > k.level_start ? (end - k.level_start) * max(nl, 1u) : 0u;
@@ -657,7 +661,6 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         B2_CUDA(ctx, cudaMemcpyAsync(&ah, (const void*)hp.handle, sizeof(ah), cudaMemcpyDeviceToHost, s));
         B2_CUDA(ctx, cudaStreamSynchronize(s));
         B2_REQUIRE(ctx, ah.magic == ACCEL_MAGIC, "LaunchParams.handle is not a b200rt traversable");
-        ctx->w_anyhit = ah.anyhit != 0;
         bool blend = false;
         for (unsigned r = 0; r < sbt->hitgroupRecordCount; ++r)
             blend |= ((const WMaterial*)(recs.data() + (size_t)r * sbt->hitgroupRecordStrideInBytes + 32 + 112))->alpha_mode == 2;
@@ -668,9 +671,9 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         ctx->w_blend = blend;
     }
     const uint32_t npix = (uint32_t)npix64, nl = ctx->w_lights, nlp = std::max(nl, 1u);
-    const bool blend = ctx->w_blend, anyhit = ctx->w_anyhit;
-    const void* k_primary = anyhit ? (const void*)w_primary_kernel<true> : (const void*)w_primary_kernel<false>;
-    const void* k_shadow = anyhit ? (const void*)w_shadow_kernel<true> : (const void*)w_shadow_kernel<false>;
+    const bool blend = ctx->w_blend;
+    const void* k_primary = (const void*)w_primary_kernel<true>;   // grid sizing: the instantiation with the smaller occupancy
+    const void* k_shadow = (const void*)w_shadow_kernel<true>;
     const size_t cap = (size_t)npix * (blend ? W_BLEND_SLOT_FACTOR : 1u);
     size_t off = 16384;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -679,6 +682,7 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                  o_chain = take(blend ? 4 * (size_t)npix : 0), o_primary = take(4 * (size_t)npix), o_att = take(4 * cap * nlp), o_arr = take(4 * cap);
     int rc = ensure_workspace(ctx, off, s);
     if (rc) return rc;
+    ws_acquire(ctx, s);
     char* W = (char*)ctx->ws.ptr;
     WK k;
     k.params = (const WParams*)d_params;
@@ -703,15 +707,17 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         k.level = level;
         k.level_start = level_start;
         k.fetch = cursors + 2 * level;
-        if (anyhit) w_primary_kernel<true><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
-        else w_primary_kernel<false><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+        w_primary_kernel<false><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+        B2_LAUNCH_CHECK(ctx);
+        w_primary_kernel<true><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
         B2_LAUNCH_CHECK(ctx);
         const unsigned shade_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n_items, 128), (uint64_t)ctx->sm_count * 16));
         w_shade_kernel<<<shade_grid, 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         k.fetch = cursors + 2 * level + 1;
-        if (anyhit) w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
-        else w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
+        w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
+        B2_LAUNCH_CHECK(ctx);
+        w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         if (!blend) break;
         // BLEND scenes: how many continuations did this level start?  (the only host synchronisation of a whitted launch)
@@ -726,6 +732,7 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         w_combine_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 8)), 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
     }
+    ws_release(ctx, s);
     return 0;
 }
 

@@ -341,6 +341,29 @@ def light_normal(v1, v2):
     return (c * (np.float32(1.0) / np.sqrt(d, dtype=np.float32))).astype(np.float32)
 
 
+class ParamsUploader:
+    """Params -> device copy of a launch (optixPathTracer.cpp:491-495: cudaMemcpyAsync on the launch's stream).  The launches are
+    asynchronous, so the host may be several subframes ahead of the device: the pinned staging block of a copy must not be rewritten
+    before that copy has run.  A small ring of pinned blocks, each guarded by an event recorded behind its copy."""
+
+    def __init__(self, nbytes, device, slots=4):
+        self.h = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.ev = [None] * slots
+        self.d = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.k = 0
+
+    def upload(self, struct):
+        k = self.k
+        self.k = (k + 1) % len(self.h)
+        if self.ev[k] is not None:
+            self.ev[k].synchronize()
+        self.h[k].numpy()[:] = np.frombuffer(bytes(struct), np.uint8)
+        self.d.copy_(self.h[k], non_blocking=True)
+        self.ev[k] = torch.cuda.Event()
+        self.ev[k].record(torch.cuda.current_stream(self.d.device))
+        return self.d
+
+
 class PathTracer:
     """Mirror of optixPathTracer's state + launchSubframe (optixPathTracer.cpp:424-511,576-898), and of
     optixMultiGPU's per-device state when multigpu=(gpu_idx, num_gpus) is given (optixMultiGPU.cpp:479-594).
@@ -411,9 +434,8 @@ class PathTracer:
             self.accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
             self.params = PTParams(0, self.accum.data_ptr(), self.frame.data_ptr(), width, height, samples_per_launch, _f3(cam["eye"]),
                                    _f3(U), _f3(V), _f3(W), light, self.accel.handle)
-        nbytes = C.sizeof(self.params)
-        self.h_params = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        self.d_params = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.uploader = ParamsUploader(C.sizeof(self.params), dev)
+        self.d_params = self.uploader.d
         self.stats = L.PTStats()
         self.sample_groups = 1
         self.ray_sort = 0  # b200rt_pt_options.ray_sort
@@ -423,8 +445,7 @@ class PathTracer:
         sample_groups: b200rt_pt_options.sample_groups (None = the instance default self.sample_groups)."""
         if subframe_index is not None:
             self.params.subframe_index = subframe_index
-        self.h_params.numpy()[:] = np.frombuffer(bytes(self.params), np.uint8)
-        self.d_params.copy_(self.h_params, non_blocking=True)
+        self.uploader.upload(self.params)
         groups = self.sample_groups if sample_groups is None else sample_groups
         opts = L.PTOptions(int(groups), int(collect_stats), C.pointer(self.stats), int(self.ray_sort), 0)  # collect_stats: bit mask of L.PT_STATS_*
         ctx = self.ctx
@@ -828,8 +849,8 @@ class Playground:
         p.normals, p.vertices, p.mat_indices, p.nmat_indices = normals.data_ptr(), vertices.data_ptr(), mat_indices.data_ptr(), self.num_triangles
         p.lights, p.nlights = self.d_lights.data_ptr(), len(self.lights_bytes) // 44
         p.materials, p.nmaterials = self.d_materials.data_ptr(), self.materials.shape[0]
-        self.h_params = torch.empty(128, dtype=torch.uint8).pin_memory()
-        self.d_params = torch.empty(128, dtype=torch.uint8, device=dev)
+        self.uploader = ParamsUploader(128, dev)
+        self.d_params = self.uploader.d
         self.stats = L.PTStats()
 
     def launch_frame(self, dirty=False, collect_stats=False):
@@ -839,8 +860,7 @@ class Playground:
         if dirty:
             p.dt = 0
         p.dt += p.samples_per_frame
-        self.h_params.numpy()[:] = np.frombuffer(bytes(p), np.uint8)
-        self.d_params.copy_(self.h_params, non_blocking=True)
+        self.uploader.upload(p)
         opts = L.PTOptions(0, int(collect_stats), C.pointer(self.stats), 0, 0)
         self.ctx.launch_playground(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height, opts)
         return self.stats if collect_stats else None

@@ -285,7 +285,7 @@ def test_synthetic_mesh_generator_matches_oracle_and_traces(ctx, orc, node_forma
     gas = common.decode_gas(pt.accel.buf.cpu().numpy())
     assert gas["num_tris"] == T
     depth, leaves = common.validate_gas(gas)
-    assert depth <= 40
+    assert depth <= 32
     st = pt.launch_subframe(0, collect_stats=1)
     torch.cuda.synchronize()
     scene = orc.Scene(tris, omats)
@@ -406,3 +406,50 @@ def test_unmodified_optix_host_calls_run_on_the_function_table_shim():
     r = subprocess.run([sys.executable, str(root / "tests" / "shim_check.py")], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "SHIM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
+
+
+@pytest.mark.parametrize("hierarchy", ["lbvh", "ploc"])
+def test_builder_takes_any_input_and_keeps_the_tree_within_the_traversal_stack(ctx, orc, hierarchy, monkeypatch):
+    """Inputs that make a tall binary hierarchy: positions in geometric progression (every Morton bit splits off one triangle: a chain),
+    a pile of coincident triangles (identical keys: the index bits decide), and both together.  OptiX builds anything, so does this
+    builder: the collapse opens the tallest subtrees first where the surface-area order would run out of levels (bvh_build.cu), the
+    tree stays within TRAV_STACK / 2 levels and the hits equal the oracle's.  Run once more with the depth target lowered, which forces
+    the guard to act on an ordinary soup."""
+    from optix_raytracer_b200 import host
+    monkeypatch.setenv("B200RT_HIERARCHY", hierarchy)
+    rng = np.random.default_rng(5)
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32) * 0.01
+    chain = np.stack([base * np.float32(2.0 ** -k) + np.float32(100.0 * 2.0 ** -k) for k in range(60)]).astype(np.float32)
+    pile = np.repeat((base + 3.0)[None], 5000, axis=0).astype(np.float32)
+    soup = (rng.random((20_000, 1, 3), dtype=np.float32) * 100 + (rng.random((20_000, 3, 3), dtype=np.float32) - 0.5)).astype(np.float32)
+    tris = np.concatenate([chain, pile, soup]).astype(np.float32)
+    rays = np.concatenate([common.random_rays(rng, 60_000, [0, 0, 0], [100, 100, 100]),
+                           common.random_rays(rng, 20_000, [2.9, 2.9, 2.9], [3.1, 3.1, 3.1]),
+                           common.random_rays(rng, 20_000, [0, 0, 0], [0.5, 0.5, 0.5])]).astype(np.float32)
+    scene = orc.Scene(tris)
+    ref = scene.trace(rays)
+    depths = []
+    for target in (None, "8"):
+        if target:
+            monkeypatch.setenv("B200RT_MAX_WIDE_DEPTH", target)
+        accel = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
+        gas = common.decode_gas(accel.buf.cpu().numpy())
+        depth, _ = common.validate_gas(gas)
+        assert depth == gas["depth"] and depth <= 32
+        depths.append(depth)
+        got = host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays)))
+        _assert_hits_equal(got, ref, f"tall hierarchy ({hierarchy}, depth {depth})")
+    assert depths[1] <= depths[0]
+
+
+def test_a_million_coincident_triangles_build_and_trace(ctx, orc):
+    from optix_raytracer_b200 import host
+    tri = np.array([[[0, 0, 1], [2, 0, 1], [0, 2, 1]]], np.float32)
+    tris = np.repeat(tri, 1_000_000, axis=0)
+    accel = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
+    info = accel.info()
+    assert info.num_triangles == 1_000_000 and info.depth <= 32
+    rays = np.array([[0.5, 0.5, 5, 0, 0, 0, -1, 100], [3, 3, 5, 0, 0, 0, -1, 100], [0.25, 0.25, 0, 0, 0, 0, 1, 100]], np.float32)
+    got = host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays)))
+    # the closest hit among equal t is the lowest ordinal: primitive 0
+    assert got["t"][0] == 4.0 and got["prim"][0] == 0 and got["t"][1] < 0 and got["t"][2] == 1.0 and got["prim"][2] == 0
