@@ -54,6 +54,7 @@ extern "C" {
 #define B200RT_TRANSFORM_FORMAT_MATRIX_FLOAT12 0x21E1
 #define B200RT_BUILD_OPERATION_BUILD 0x2161
 #define B200RT_PROPERTY_TYPE_COMPACTED_SIZE 0x2181
+#define B200RT_PROPERTY_TYPE_AABBS 0x2182
 #define B200RT_BUILD_FLAG_ALLOW_COMPACTION (1u << 1)
 /* ray flags, reference include/optix_types.h:1794-1840 (same values).  Precedence of the any-hit state of a triangle, as documented
  * there: ray flags (DISABLE / ENFORCE_ANYHIT) over instance flags over the geometry flag of its SBT record.  OptiX declares some
@@ -208,6 +209,13 @@ int b200rt_shared_buffer_destroy(b200rt_context ctx, b200rt_deviceptr ptr);  /* 
  * outputBuffer must be 128-byte aligned; the returned handle is valid as long as outputBuffer is,
  * and does not reference tempBuffer or the vertex/index buffers after the build has run on `stream`.
  * The build records the exact size; emitted COMPACTED_SIZE properties are written on `stream`.
+ * Builds and compactions are ASYNCHRONOUS like optixAccelBuild / optixAccelCompact: no call waits for the device (the loops of the
+ * build whose trip counts only the device knows run as CUDA graphs with conditional nodes).  Any input builds (no depth limit is
+ * imposed on the caller: the builder keeps every tree within the traversal stack).  What can only be known when the device has run —
+ * an output buffer too small for the compaction, a source that is no traversable — is left in the header of the result and reported by
+ * b200rt_accel_get_info.
+ * b200rt_accel_emit_property replaces optixAccelEmitProperty (reference include/optix_stubs.h:520): COMPACTED_SIZE (size_t) or AABBS
+ * (one OptixAabb = 6 floats) of a finished structure, written to device memory on `stream`.
  * ------------------------------------------------------------------------------------------- */
 int b200rt_accel_compute_memory_usage(b200rt_context ctx, const b200rt_accel_build_options* options,
                                       const b200rt_build_input* inputs, unsigned int num_inputs,
@@ -218,6 +226,8 @@ int b200rt_accel_build(b200rt_context ctx, b200rt_stream stream, const b200rt_ac
                        b200rt_traversable* handle, const b200rt_accel_emit_desc* emitted, unsigned int num_emitted);
 int b200rt_accel_compact(b200rt_context ctx, b200rt_stream stream, b200rt_traversable input,
                          b200rt_deviceptr output_buffer, size_t output_bytes, b200rt_traversable* handle);
+int b200rt_accel_emit_property(b200rt_context ctx, b200rt_stream stream, b200rt_traversable handle,
+                               const b200rt_accel_emit_desc* emitted, unsigned int num_emitted);
 
 /* Introspection used by tests / bench (no OptiX equivalent): synchronous. */
 typedef struct b200rt_accel_info {

@@ -119,6 +119,7 @@ SYMBOLS = {
     "b200rt_accel_build": (i32, [vp, vp, C.POINTER(AccelBuildOptions), C.POINTER(BuildInput), u32, u64, sz, u64, sz,
                                  C.POINTER(u64), C.POINTER(AccelEmitDesc), u32]),
     "b200rt_accel_compact": (i32, [vp, vp, u64, u64, sz, C.POINTER(u64)]),
+    "b200rt_accel_emit_property": (i32, [vp, vp, u64, vp, u32]),
     "b200rt_accel_get_info": (i32, [vp, u64, C.POINTER(AccelInfo)]),
     "b200rt_launch_pathtracer": (i32, [vp, vp, u64, C.POINTER(ShaderBindingTable), u32, u32, C.POINTER(PTOptions)]),
     "b200rt_launch_multigpu": (i32, [vp, vp, u64, C.POINTER(ShaderBindingTable), u32, C.POINTER(PTOptions)]),

@@ -7,6 +7,7 @@
 
 #include "accel.h"
 #include "internal.h"
+#include "loop_graph.h"
 
 // layouts promised by b200rt.h (reference include/optix_types.h)
 static_assert(sizeof(b200rt_build_input) == 1032, "OptixBuildInput");
@@ -146,6 +147,7 @@ int b200rt_context_destroy(b200rt_context ctx)
         DeviceGuard guard(ctx->device);
         cudaDeviceSynchronize();
         pathtracer_release(ctx);
+        retire_loops(ctx, true);
         if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         if (ctx->ev) cudaEventDestroy(ctx->ev);
@@ -239,6 +241,13 @@ int b200rt_accel_compact(b200rt_context ctx, b200rt_stream stream, b200rt_traver
 {
     CTX_CHECK(ctx);
     return accel_compact(ctx, (cudaStream_t)stream, input, output_buffer, output_bytes, handle);
+}
+
+int b200rt_accel_emit_property(b200rt_context ctx, b200rt_stream stream, b200rt_traversable handle, const b200rt_accel_emit_desc* emitted,
+                               unsigned int num_emitted)
+{
+    CTX_CHECK(ctx);
+    return accel_emit_property(ctx, (cudaStream_t)stream, handle, emitted, num_emitted);
 }
 
 int b200rt_accel_get_info(b200rt_context ctx, b200rt_traversable handle, b200rt_accel_info* info)

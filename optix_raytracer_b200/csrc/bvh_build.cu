@@ -27,6 +27,17 @@
 
 namespace b200rt {
 
+void retire_loops(b200rt_context ctx, bool all)
+{
+    size_t keep = 0;
+    for (LoopGraph* g : ctx->loops) {
+        if (all || g->finished()) delete g;
+        else ctx->loops[keep++] = g;
+    }
+    ctx->loops.resize(keep);
+}
+void park_loop(b200rt_context ctx, LoopGraph* g) { ctx->loops.push_back(g); }
+
 // ---------------------------------------------------------------------------------------------
 // device-side description of one triangle build input
 // ---------------------------------------------------------------------------------------------
@@ -702,15 +713,15 @@ __global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float
         const int l = __float_as_int(vlo[node].w), r = __float_as_int(vhi[node].w);
         const float llx = vlo[l].x, lly = vlo[l].y, llz = vlo[l].z, lhx = vhi[l].x, lhy = vhi[l].y, lhz = vhi[l].z;
         const float rlx = vlo[r].x, rly = vlo[r].y, rlz = vlo[r].z, rhx = vhi[r].x, rhy = vhi[r].y, rhz = vhi[r].z;
+        // subtree height (edges to the deepest leaf): what the collapse needs to keep the wide tree within the traversal stack; read with
+        // the boxes so that the loads are in flight together
+        const volatile uint8_t* vh = height;
+        const int hl = l < n - 1 ? vh[l] : 0, hr = r < n - 1 ? vh[r] : 0;
+        const int next = parent[node];
         box_lo[node] = make_float4(fminf(llx, rlx), fminf(lly, rly), fminf(llz, rlz), __int_as_float(l));
         box_hi[node] = make_float4(fmaxf(lhx, rhx), fmaxf(lhy, rhy), fmaxf(lhz, rhz), __int_as_float(r));
-        {
-            // subtree height (edges to the deepest leaf): what the collapse needs to keep the wide tree within the traversal stack
-            const volatile uint8_t* vh = height;
-            const int hl = l < n - 1 ? vh[l] : 0, hr = r < n - 1 ? vh[r] : 0;
-            height[node] = (uint8_t)min(max(hl, hr) + 1, 255);
-        }
-        node = parent[node];
+        height[node] = (uint8_t)min(max(hl, hr) + 1, 255);
+        node = next;
     }
 }
 
@@ -1224,6 +1235,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         B2_REQUIRE(ctx, emitted[i].result, "emittedProperties[%u].result is null", i);
     }
     DeviceGuard guard(ctx->device);
+    retire_loops(ctx, false);
     uint64_t exact_bytes = 0;
     // what the whitted launch learnt about the scene (light count, BLEND materials) belongs to the scene that was there before:
     // a new scene always comes with a build, and its buffers may well reuse the old addresses
@@ -1314,6 +1326,12 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
 
         init_bounds_kernel<<<1, 32, 0, s>>>(d_bounds);
         B2_LAUNCH_CHECK(ctx);
+        // B200RT_BUILD_TIMING=1: CUDA events between the phases, read (with a synchronisation) and logged at the end of the call
+        static const bool phase_timing = [] { const char* e = getenv("B200RT_BUILD_TIMING"); return e && atoi(e) != 0; }();
+        cudaEvent_t pev[8];
+        int npev = 0;
+        auto mark = [&]() { if (phase_timing && npev < 8) { cudaEventCreate(&pev[npev]); cudaEventRecord(pev[npev], s); ++npev; } };
+        mark();
         if (N > 0) {
             gather_tris_kernel<<<persistent_grid(ctx, N, 256, 8), 256, 0, s>>>((const DevInput*)(T + p.off_inputs), (int)num_inputs, N,
                                                               (const uint32_t*)(T + p.off_flags), tri_tmp, d_bounds);
@@ -1333,6 +1351,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 B2_LAUNCH_CHECK(ctx);
                 cur ^= 1;
             }
+            mark();  // gather + Morton + sort
             leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
             B2_LAUNCH_CHECK(ctx);
             // No host read-back from here on: optixAccelBuild is asynchronous, so the rounds of the clustering and the levels of
@@ -1348,7 +1367,8 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 ploc_init_kernel<<<div_up(N, 256), 256, 0, s>>>(cl[0], N, d_ploc);
                 B2_LAUNCH_CHECK(ctx);
                 const unsigned pgrid = std::max(1u, std::min(div_up(N, 256), (unsigned)ctx->sm_count * 8u));
-                LoopGraph g(ctx);
+                LoopGraph& g = *new LoopGraph(ctx);
+                park_loop(ctx, &g);
                 if ((rc = g.begin())) return rc;
                 if ((rc = g.add((const void*)ploc_nearest_kernel, pgrid, PLOC_THREADS, 0, (const uint32_t*)cl[0], (const uint32_t*)cl[1], (const PlocState*)d_ploc,
                                 (const float4*)box_lo, (const float4*)box_hi, nearest))) return rc;
@@ -1366,11 +1386,13 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive, height);
                 B2_LAUNCH_CHECK(ctx);
             }
+            mark();  // leaf boxes + binary hierarchy
             collapse_init_kernel<<<1, 1, 0, s>>>(d_cst, work[0], 0u, cl[0], cl[1], ploc ? d_ploc : nullptr);  // radix tree: internal node 0, or leaf 0 when N == 1
             B2_LAUNCH_CHECK(ctx);
             // ---- collapse, level by level
             {
-                LoopGraph g(ctx);
+                LoopGraph& g = *new LoopGraph(ctx);
+                park_loop(ctx, &g);
                 if ((rc = g.begin())) return rc;
                 if ((rc = g.add((const void*)collapse_plan_kernel, wide_grid, 128, 0, (const CollapseState*)d_cst, (const uint32_t*)work[0], (const uint32_t*)work[1], (int)N,
                                 (const float4*)box_lo, (const float4*)box_hi, (const int2*)range, (const uint8_t*)height, child_tmp, counts, max_wide_depth()))) return rc;
@@ -1381,6 +1403,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 if ((rc = g.launch(s))) return rc;
                 ctx->launches += 1;
             }
+            mark();  // collapse
             // triangles go right after the node capacity region; compaction later closes the gap
             hv.tris_off = HEADER_BYTES + (uint64_t)p.max_nodes * p.node_bytes;
             scatter_tris_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], dest, N, (float4*)(out + hv.tris_off));
@@ -1394,6 +1417,14 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         write_header_kernel<<<1, 1, 0, s>>>((AccelHeader*)out, hv, d_bounds, N > 0 ? d_cst : nullptr, num_emitted > 0 ? (unsigned long long*)emitted[0].result : nullptr,
                                             num_emitted > 1 ? (unsigned long long*)emitted[1].result : nullptr);
         B2_LAUNCH_CHECK(ctx);
+        mark();
+        if (phase_timing && npev == 5) {
+            cudaEventSynchronize(pev[4]);
+            float t[4];
+            for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], pev[i], pev[i + 1]);
+            fprintf(stderr, "[b200rt build] %u triangles: keys+sort %.3f ms, hierarchy %.3f ms, collapse %.3f ms, triangles+header %.3f ms\n", N, t[0], t[1], t[2], t[3]);
+        }
+        for (int i = 0; i < npev; ++i) cudaEventDestroy(pev[i]);
         log_msg(ctx, 4, "accel", "GAS build enqueued: %u triangles, node capacity %u, %u-byte nodes", N, p.max_nodes, p.node_bytes);
         *handle = out;
         return 0;
@@ -1455,6 +1486,27 @@ int accel_compact(b200rt_context ctx, cudaStream_t s, b200rt_traversable input, 
     compact_kernel<<<(unsigned)ctx->sm_count * 8u, 256, 0, s>>>((const char*)input, (char*)out, out_bytes);
     B2_LAUNCH_CHECK(ctx);
     *handle = out;
+    return 0;
+}
+
+// optixAccelEmitProperty: the compacted size (or the bounds) of a finished acceleration structure, written to device memory by a
+// one-thread kernel that reads the header where it lives
+__global__ void emit_property_kernel(const AccelHeader* h, unsigned type, void* result)
+{
+    if (type == B200RT_PROPERTY_TYPE_COMPACTED_SIZE) *(unsigned long long*)result = (h->total_bytes + 127ull) / 128ull * 128ull;
+    else { float* b = (float*)result; for (int a = 0; a < 6; ++a) b[a] = h->bounds[a]; }  // OPTIX_PROPERTY_TYPE_AABBS: one OptixAabb
+}
+
+int accel_emit_property(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, const b200rt_accel_emit_desc* emitted, unsigned num_emitted)
+{
+    B2_REQUIRE(ctx, handle && (emitted || num_emitted == 0), "null argument");
+    DeviceGuard guard(ctx->device);
+    for (unsigned i = 0; i < num_emitted; ++i) {
+        B2_REQUIRE(ctx, emitted[i].result && (emitted[i].type == B200RT_PROPERTY_TYPE_COMPACTED_SIZE || emitted[i].type == B200RT_PROPERTY_TYPE_AABBS),
+                   "emittedProperties[%u]: COMPACTED_SIZE or AABBS with a result address", i);
+        emit_property_kernel<<<1, 1, 0, s>>>((const AccelHeader*)handle, emitted[i].type, (void*)emitted[i].result);
+        B2_LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

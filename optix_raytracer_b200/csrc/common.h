@@ -17,6 +17,7 @@ struct Workspace {
     size_t bytes = 0;
 };
 struct PTGraphCache;
+class LoopGraph;
 
 }  // namespace b200rt
 
@@ -36,6 +37,7 @@ struct b200rt_context_t {
     cudaEvent_t ev = nullptr;
     cudaStream_t ws_stream = nullptr;
     bool ws_busy = false;
+    std::vector<b200rt::LoopGraph*> loops;      // build loops in flight (loop_graph.h)
     b200rt::PTGraphCache* pt_graphs = nullptr;  // instantiated wavefront-loop graphs of the path-tracer launches (pathtracer.cu)
     std::mutex mu;
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING

@@ -10,6 +10,7 @@ int accel_build(b200rt_context, cudaStream_t, const b200rt_accel_build_options*,
                 size_t, b200rt_deviceptr, size_t, b200rt_traversable*, const b200rt_accel_emit_desc*, unsigned);
 int accel_compact(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_deviceptr, size_t, b200rt_traversable*);
 int accel_get_info(b200rt_context, b200rt_traversable, b200rt_accel_info*);
+int accel_emit_property(b200rt_context, cudaStream_t, b200rt_traversable, const b200rt_accel_emit_desc*, unsigned);
 size_t radix_sort_hist_words(size_t n);
 size_t radix_sort_scan_words(size_t n);
 int radix_sort_pairs32(b200rt_context, cudaStream_t, uint32_t* keys[2], uint32_t* vals[2], uint32_t n, int passes, uint32_t* hist, uint32_t* scan_tmp, int* result);

@@ -13,7 +13,7 @@ public:
     explicit LoopGraph(b200rt_context ctx) : ctx_(ctx) {}
     ~LoopGraph()
     {
-        // graph executions in flight are not terminated by destroying their objects; the resources go when the execution completes
+        if (done_) cudaEventDestroy(done_);
         if (exec_) cudaGraphExecDestroy(exec_);
         if (graph_) cudaGraphDestroy(graph_);
     }
@@ -60,8 +60,12 @@ public:
     {
         B2_CUDA(ctx_, cudaGraphInstantiate(&exec_, graph_, 0));
         B2_CUDA(ctx_, cudaGraphLaunch(exec_, s));
+        B2_CUDA(ctx_, cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+        B2_CUDA(ctx_, cudaEventRecord(done_, s));
         return 0;
     }
+    // has the launched loop finished?  (a loop that was never launched counts as finished)
+    bool finished() const { return !done_ || cudaEventQuery(done_) == cudaSuccess; }
     unsigned kernels_per_round() const { return kernels_; }
 
 private:
@@ -70,7 +74,13 @@ private:
     cudaGraphExec_t exec_ = nullptr;
     cudaGraphConditionalHandle cond_ = 0;
     cudaGraphNode_t prev_ = nullptr;
+    cudaEvent_t done_ = nullptr;
     unsigned kernels_ = 0;
 };
+
+// Loops that may still be running are parked in the context and destroyed once their completion event has fired (destroying an
+// executable graph that is in flight makes the host wait for it): retire_loops() at the start of every build, and at context destruction.
+void retire_loops(b200rt_context ctx, bool all);
+void park_loop(b200rt_context ctx, LoopGraph* g);
 
 }  // namespace b200rt

@@ -70,6 +70,16 @@ struct StackSizes { unsigned v[7]; };  // OptixStackSizes, 28 bytes
 
 enum Which { W_NONE = 0, W_PATHTRACER_FAMILY, W_RAYCAST, W_WHITTED, W_PLAYGROUND };
 
+unsigned env_sample_groups()
+{
+    // 1 by default: a drop-in keeps the reference's arithmetic, i.e. the flat fp32 summation order of a pixel's samples.
+    // B200RT_SAMPLE_GROUPS=<n> opts in to n parallel lanes per pixel whose sums are added in lane order (the per-pixel sum is regrouped,
+    // ~1 ulp; the oracle restates the grouped order too): 1.77x instead of 1.50x OptiX on the Cornell launch.
+    const char* e = getenv("B200RT_SAMPLE_GROUPS");
+    const long v = e ? strtol(e, nullptr, 10) : 1;
+    return v >= 1 && v <= 64 ? (unsigned)v : 1u;
+}
+
 struct ShimContext { b200rt_context ctx = nullptr; LogCb cb = nullptr; void* cbdata = nullptr; int level = 0; };
 struct ShimModule { ShimContext* c; };
 struct ShimProgramGroup { ShimContext* c; unsigned kind; std::string name, name_ah, name_is; };
@@ -180,7 +190,10 @@ int s_program_group_create(ShimContext* c, const ProgramGroupDesc* descs, unsign
     for (unsigned i = 0; i < n; ++i) {
         const ProgramGroupDesc& d = descs[i];
         ShimProgramGroup* g = new (std::nothrow) ShimProgramGroup{c, d.kind, "", "", ""};
-        if (!g) return OPTIX_ERROR_HOST_OUT_OF_MEMORY_;
+        if (!g) {
+            for (unsigned k = 0; k < i; ++k) { delete out[k]; out[k] = nullptr; }
+            return OPTIX_ERROR_HOST_OUT_OF_MEMORY_;
+        }
         if (d.kind == KIND_HITGROUP) {
             if (d.hitgroup.nameCH) g->name = d.hitgroup.nameCH;
             if (d.hitgroup.nameAH) g->name_ah = d.hitgroup.nameAH;
@@ -189,6 +202,7 @@ int s_program_group_create(ShimContext* c, const ProgramGroupDesc* descs, unsign
             if (d.single.name) g->name = d.single.name;
         } else if (d.kind != KIND_CALLABLES) {
             delete g;
+            for (unsigned k = 0; k < i; ++k) { delete out[k]; out[k] = nullptr; }  // nothing of a failed call is left behind
             return OPTIX_ERROR_INVALID_VALUE_;
         }
         out[i] = g;
@@ -209,27 +223,41 @@ int s_pipeline_create(ShimContext* c, const PipelineCompileOptions* /*pco*/, con
                       char* log, size_t* log_size, ShimPipeline** out)
 {
     if (!c || !groups || !out) return OPTIX_ERROR_INVALID_VALUE_;
-    std::string raygen;
-    bool miss_radiance = false, miss_ms = false;
+    std::string raygen, hits;
+    bool miss_radiance = false, miss_ms = false, miss_buffer = false, miss_constant = false;
+    bool ch_radiance = false, ch_buffer = false, ch_ch = false;
     for (unsigned i = 0; i < n; ++i) {
         if (!groups[i]) return OPTIX_ERROR_INVALID_VALUE_;
-        if (groups[i]->kind == KIND_RAYGEN) raygen = groups[i]->name;
-        if (groups[i]->kind == KIND_MISS) { miss_radiance |= groups[i]->name == "__miss__radiance"; miss_ms |= groups[i]->name == "__miss__ms"; }
+        const std::string& nm = groups[i]->name;
+        if (groups[i]->kind == KIND_RAYGEN) raygen = nm;
+        if (groups[i]->kind == KIND_MISS) {
+            miss_radiance |= nm == "__miss__radiance"; miss_ms |= nm == "__miss__ms"; miss_buffer |= nm == "__miss__buffer_miss";
+            miss_constant |= nm == "__miss__constant_radiance";
+        }
+        if (groups[i]->kind == KIND_HITGROUP) {
+            ch_radiance |= nm == "__closesthit__radiance"; ch_buffer |= nm == "__closesthit__buffer_hit"; ch_ch |= nm == "__closesthit__ch";
+            hits += (hits.empty() ? "" : ", ") + (nm.empty() ? std::string("(none)") : nm);
+        }
     }
+    // the whole set of entry points has to be a sample's: a pipeline that reuses a sample's raygen name with other hit programs would
+    // otherwise silently run this library's restatement of the sample
     Which w = W_NONE;
-    if (raygen == "__raygen__from_buffer") w = W_RAYCAST;
-    else if (raygen == "__raygen__pinhole") w = W_WHITTED;
-    else if (raygen == "__raygen__rg" && miss_ms) w = W_PLAYGROUND;
-    else if (raygen == "__raygen__rg" && miss_radiance) w = W_PATHTRACER_FAMILY;
+    if (raygen == "__raygen__from_buffer" && miss_buffer && ch_buffer) w = W_RAYCAST;
+    else if (raygen == "__raygen__pinhole" && miss_constant && ch_radiance) w = W_WHITTED;
+    else if (raygen == "__raygen__rg" && miss_ms && ch_ch) w = W_PLAYGROUND;
+    else if (raygen == "__raygen__rg" && miss_radiance && ch_radiance) w = W_PATHTRACER_FAMILY;
     if (w == W_NONE) {
-        const std::string msg = "b200rt: no restatement of a pipeline with raygen program '" + raygen +
-                                "' (known: optixPathTracer, optixMultiGPU, optixRaycasting, optixMeshViewer/whitted, imgui_test)";
+        const std::string msg = "b200rt: no restatement of a pipeline with raygen program '" + raygen + "' and closest-hit programs {" + hits +
+                                "} (known: optixPathTracer, optixMultiGPU, optixRaycasting, optixMeshViewer/whitted, imgui_test)";
         put_log(log, log_size, msg);
         say(c, 2, "B200RT", msg);
         return OPTIX_ERROR_NOT_SUPPORTED_;
     }
     ShimPipeline* p = new (std::nothrow) ShimPipeline{c, w};
     if (!p) return OPTIX_ERROR_HOST_OUT_OF_MEMORY_;
+    if (w == W_PATHTRACER_FAMILY)
+        say(c, 4, "B200RT", "path-tracer launches of this pipeline run with sample_groups " + std::to_string(env_sample_groups()) +
+                                (env_sample_groups() == 1 ? " (the reference's summation order)" : " (B200RT_SAMPLE_GROUPS: the per-pixel fp32 sum is regrouped)"));
     put_log(log, log_size, "");
     *out = p;
     return OPTIX_SUCCESS_;
@@ -253,6 +281,18 @@ int s_accel_compact(ShimContext* c, void* stream, b200rt_traversable in, b200rt_
     return c ? b200rt_accel_compact(c->ctx, (b200rt_stream)stream, in, out, out_bytes, handle) : OPTIX_ERROR_INVALID_DEVICE_CONTEXT_;
 }
 
+int s_accel_emit_property(ShimContext* c, void* stream, b200rt_traversable handle, const b200rt_accel_emit_desc* emitted)
+{
+    return c ? b200rt_accel_emit_property(c->ctx, (b200rt_stream)stream, handle, emitted, emitted ? 1u : 0u) : OPTIX_ERROR_INVALID_DEVICE_CONTEXT_;
+}
+// optixConvertPointerToTraversableHandle: a traversable handle of this library IS the device address of its blob
+int s_convert_pointer(ShimContext* c, b200rt_deviceptr pointer, unsigned /*OptixTraversableType*/, b200rt_traversable* handle)
+{
+    if (!c || !handle) return OPTIX_ERROR_INVALID_VALUE_;
+    *handle = pointer;
+    return OPTIX_SUCCESS_;
+}
+
 // ---- SBT + launch ---------------------------------------------------------------------------------------------------------------------
 int s_sbt_record_pack_header(ShimProgramGroup* g, void* header)
 {
@@ -267,15 +307,6 @@ int s_sbt_record_pack_header(ShimProgramGroup* g, void* header)
     return OPTIX_SUCCESS_;
 }
 
-unsigned env_sample_groups()
-{
-    // 4 by default: the samples of a pixel run in 4 parallel lanes and their sums are added in lane order — the fp32 sum of a pixel is
-    // regrouped (~1 ulp; the oracle restates the grouped order too), everything else is the reference's; 1.57x instead of 1.34x OptiX on
-    // the Cornell launch.  B200RT_SAMPLE_GROUPS=1 gives the reference's flat summation order.
-    const char* e = getenv("B200RT_SAMPLE_GROUPS");
-    const long v = e ? strtol(e, nullptr, 10) : 4;
-    return v >= 1 && v <= 64 ? (unsigned)v : 4u;
-}
 
 int s_launch(ShimPipeline* p, void* stream, b200rt_deviceptr params, size_t params_size, const b200rt_shader_binding_table* sbt, unsigned w, unsigned h,
              unsigned d)
@@ -342,7 +373,9 @@ extern "C" int optixQueryFunctionTable(int abi_id, unsigned int num_options, con
     t[25] = (void*)&s_accel_build;                // optixAccelBuild
     //  26-28 relocation: not supported
     t[29] = (void*)&s_accel_compact;              // optixAccelCompact
-    //  30 optixAccelEmitProperty, 31 optixConvertPointerToTraversableHandle, 32-37 micromaps: not supported
+    t[30] = (void*)&s_accel_emit_property;        // optixAccelEmitProperty
+    t[31] = (void*)&s_convert_pointer;            // optixConvertPointerToTraversableHandle
+    //  32-37 micromaps: not supported
     t[38] = (void*)&s_sbt_record_pack_header;     // optixSbtRecordPackHeader
     t[39] = (void*)&s_launch;                     // optixLaunch
     //  40-47 denoiser: not supported

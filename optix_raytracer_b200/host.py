@@ -457,50 +457,93 @@ class PathTracer:
 
 
 # ---- glTF (the subset sutil::Scene loads: SDK/sutil/Scene.cpp:84-210,267-550) ---------------------------
-_GLTF_COMP = {5121: (np.uint8, 1), 5123: (np.uint16, 2), 5125: (np.uint32, 4), 5126: (np.float32, 4)}
-_GLTF_NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
+_GLTF_COMP = {5123: (np.uint16, 2), 5125: (np.uint32, 4), 5126: (np.float32, 4)}  # bufferViewFromGLTF: u16, u32, f32 — anything else throws
+_GLTF_NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
+_F = np.float32
 
 
-def _mat_from_node(node):
-    f = np.float32
-    m = np.eye(4, dtype=f)
-    if "matrix" in node:
-        m = np.array(node["matrix"], f).reshape(4, 4).T.copy()  # column-major in the file
+def _mat4_mul(a, b):
+    """sutil::Matrix operator* (SDK/sutil/Matrix.h:339-355): fp32, sum = 0; sum += a[i][k] * b[k][j] for k = 0..3 — spelled out, because
+    a BLAS product adds in another order and the instance transforms are compared bit for bit with sutil's."""
+    a, b = np.asarray(a, _F), np.asarray(b, _F)
+    out = np.zeros((4, 4), _F)
+    for i in range(4):
+        for j in range(4):
+            acc = _F(0.0)
+            for k in range(4):
+                acc = _F(acc + _F(a[i, k] * b[k, j]))
+            out[i, j] = acc
+    return out
+
+
+def _mat4_vec(m, v):
+    """Matrix4x4 * float4 (SDK/sutil/Matrix.h:467-487): ((m0 x + m1 y) + m2 z) + m3 w per row, fp32."""
+    m, v = np.asarray(m, _F), np.asarray(v, _F)
+    return np.array([_F(_F(_F(_F(m[r, 0] * v[0]) + _F(m[r, 1] * v[1])) + _F(m[r, 2] * v[2])) + _F(m[r, 3] * v[3])) for r in range(4)], _F)
+
+
+def _aabb_transform(lo, hi, m):
+    """Aabb::transform(Matrix4x4) (SDK/sutil/Aabb.h:389-409): the eight corners through the matrix, min / max."""
+    pts = [_mat4_vec(m, [x, y, z, 1.0])[:3] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]
+    return np.min(pts, axis=0).astype(_F), np.max(pts, axis=0).astype(_F)
+
+
+def _node_matrices(node):
+    """translation, rotation, scale, matrix of processGLTFNode (SDK/sutil/Scene.cpp:132-163); doubles of the file cast to fp32 first."""
+    f = _F
     t = np.eye(4, dtype=f)
-    if "translation" in node:
+    if node.get("translation"):
         t[:3, 3] = np.array(node["translation"], f)
     r = np.eye(4, dtype=f)
-    if "rotation" in node:
-        x, y, z, w = [f(v) for v in node["rotation"]]
-        # sutil::Quaternion::rotationMatrix (SDK/sutil/Quaternion.h:239-267)
-        qw, qx, qy, qz = w, x, y, z
-        r[:3, :3] = np.array([[1 - 2 * qy * qy - 2 * qz * qz, 2 * qx * qy - 2 * qz * qw, 2 * qx * qz + 2 * qy * qw],
-                              [2 * qx * qy + 2 * qz * qw, 1 - 2 * qx * qx - 2 * qz * qz, 2 * qy * qz - 2 * qx * qw],
-                              [2 * qx * qz - 2 * qy * qw, 2 * qy * qz + 2 * qx * qw, 1 - 2 * qx * qx - 2 * qy * qy]], f)
-    s = np.eye(4, dtype=f)
-    if "scale" in node:
-        s[0, 0], s[1, 1], s[2, 2] = [f(v) for v in node["scale"]]
-    return (m @ t @ r @ s).astype(f)
+    if node.get("rotation"):
+        qx, qy, qz, qw = [f(v) for v in node["rotation"]]
+        two = f(2.0)
+        # sutil::Quaternion::rotationMatrix (SDK/sutil/Quaternion.h:239-267), left to right in fp32
+        r[0, 0] = f(f(f(1.0) - f(f(two * qy) * qy)) - f(f(two * qz) * qz)); r[0, 1] = f(f(f(two * qx) * qy) - f(f(two * qz) * qw)); r[0, 2] = f(f(f(two * qx) * qz) + f(f(two * qy) * qw))
+        r[1, 0] = f(f(f(two * qx) * qy) + f(f(two * qz) * qw)); r[1, 1] = f(f(f(1.0) - f(f(two * qx) * qx)) - f(f(two * qz) * qz)); r[1, 2] = f(f(f(two * qy) * qz) - f(f(two * qx) * qw))
+        r[2, 0] = f(f(f(two * qx) * qz) - f(f(two * qy) * qw)); r[2, 1] = f(f(f(two * qy) * qz) + f(f(two * qx) * qw)); r[2, 2] = f(f(f(1.0) - f(f(two * qx) * qx)) - f(f(two * qy) * qy))
+    sc = np.eye(4, dtype=f)
+    if node.get("scale"):
+        sc[0, 0], sc[1, 1], sc[2, 2] = [f(v) for v in node["scale"]]
+    m = np.eye(4, dtype=f)
+    if node.get("matrix"):
+        m = np.array(node["matrix"], f).reshape(4, 4).T.copy()  # column-major in the file
+    return m, t, r, sc
 
 
 def load_gltf(path):
-    """Returns dict(meshes=[{primitives:[{positions, normals, indices, stride info...}], aabb}], instances=[{transform(4x4), mesh, world_aabb}])."""
+    """sutil::loadScene (SDK/sutil/Scene.cpp:267-550) for a .gltf with external buffers.  Returns a dict:
+      buffers    the glTF buffers, whole (Scene::addBuffer uploads each once; every view points into them)
+      meshes     [{primitives: [{positions, normals, texcoords[2], colors, indices (decoded copies, for CPU-side use),
+                                 views: {name: (buffer, byte offset, count, byte stride, element size)} — what bufferViewFromGLTF
+                                 (Scene.cpp:84-123) makes: nothing is repacked, interleaved attributes stay interleaved —, material}], aabb}]
+      instances  [{transform (4x4 fp32), mesh, world_aabb}] in the order processGLTFNode meets them, starting from every node that is
+                 nobody's child (Scene.cpp:535-549: not from scenes[scene].nodes)
+      cameras, materials, images, textures, samplers."""
     path = pathlib.Path(path)
     g = json.loads(path.read_text())
     buffers = [np.fromfile(path.parent / b["uri"], dtype=np.uint8) for b in g["buffers"]]
 
-    def accessor(idx):
+    def view(idx):
+        """bufferViewFromGLTF: (buffer, offset, count, stride, elmt) — elmt is the COMPONENT size, as in the reference"""
         a = g["accessors"][idx]
         bv = g["bufferViews"][a["bufferView"]]
+        if a["componentType"] not in _GLTF_COMP:
+            raise B200RTError("gltf accessor component type not supported")
         dt, sz = _GLTF_COMP[a["componentType"]]
-        nc = _GLTF_NCOMP[a["type"]]
-        off = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
-        stride = bv.get("byteStride", 0) or sz * nc
-        raw = buffers[bv["buffer"]]
-        out = np.zeros((a["count"], nc), dt)
-        for i in range(nc):
-            out[:, i] = np.ndarray((a["count"],), dt, raw.data, off + i * sz, (stride,))
-        return out, a
+        stride = bv.get("byteStride", 0) or sz * _GLTF_NCOMP.get(a["type"], 1)
+        return (bv["buffer"], bv.get("byteOffset", 0) + a.get("byteOffset", 0), a["count"], stride, sz), dt, a
+
+    def decode(v, dt, ncomp):
+        buf, off, count, stride, sz = v
+        raw = buffers[buf]
+        out = np.zeros((count, ncomp), dt)
+        for i in range(ncomp):
+            # the last element of a view read wider than its accessor (COLOR_0 as Vec4f over a VEC3 accessor) may end past the buffer
+            n_ok = min(count, max(0, (raw.size - off - i * sz - sz) // stride + 1)) if raw.size >= off + i * sz + sz else 0
+            if n_ok:
+                out[:n_ok, i] = np.ndarray((n_ok,), dt, raw.data, off + i * sz, (stride,))
+        return out
 
     meshes = []
     for m in g["meshes"]:
@@ -508,45 +551,66 @@ def load_gltf(path):
         lo = np.full(3, np.inf, np.float32)
         hi = np.full(3, -np.inf, np.float32)
         for p in m["primitives"]:
-            if p.get("mode", 4) != 4:
+            if p.get("mode", 4) != 4:  # TINYGLTF_MODE_TRIANGLES only
                 continue
-            pos, pa = accessor(p["attributes"]["POSITION"])
-            if "min" in pa and "max" in pa:
+            views = {}
+            att = p["attributes"]
+            idx = None
+            if "indices" in p:
+                views["indices"], dt, _ = view(p["indices"])
+                idx = decode(views["indices"], dt, 1).reshape(-1)
+            views["positions"], dt, pa = view(att["POSITION"])
+            pos = decode(views["positions"], dt, 3).astype(np.float32)
+            if pa.get("min") and pa.get("max"):
                 lo = np.minimum(lo, np.array(pa["min"], np.float32))
                 hi = np.maximum(hi, np.array(pa["max"], np.float32))
-            nrm = accessor(p["attributes"]["NORMAL"])[0] if "NORMAL" in p["attributes"] else None
-            idx = accessor(p["indices"])[0].reshape(-1) if "indices" in p else None
-            uv0 = accessor(p["attributes"]["TEXCOORD_0"])[0].astype(np.float32) if "TEXCOORD_0" in p["attributes"] else None
-            uv1 = accessor(p["attributes"]["TEXCOORD_1"])[0].astype(np.float32) if "TEXCOORD_1" in p["attributes"] else None
-            prims.append({"positions": pos.astype(np.float32), "normals": None if nrm is None else nrm.astype(np.float32),
-                          "indices": idx, "material": p.get("material", -1), "texcoords": [uv0, uv1]})
-        meshes.append({"primitives": prims, "aabb": (lo, hi)})
+            nrm = None
+            if "NORMAL" in att:
+                views["normals"], dt, _ = view(att["NORMAL"])
+                nrm = decode(views["normals"], dt, 3).astype(np.float32)
+            uvs = [None, None]
+            for j in range(2):
+                if f"TEXCOORD_{j}" in att:
+                    views[f"texcoords{j}"], dt, _ = view(att[f"TEXCOORD_{j}"])
+                    uvs[j] = decode(views[f"texcoords{j}"], dt, 2).astype(np.float32)
+            col = None
+            if "COLOR_0" in att:
+                # BufferView<Vec4f> whatever the accessor's type (Scene.cpp:520-524): a VEC3 colour is read four floats at a time
+                views["colors"], dt, _ = view(att["COLOR_0"])
+                col = decode(views["colors"], dt, 4).astype(np.float32)
+            prims.append({"positions": pos, "normals": nrm, "indices": idx, "material": p.get("material", -1), "texcoords": uvs, "colors": col,
+                          "views": views})
+        meshes.append({"name": m.get("name", ""), "primitives": prims, "aabb": (lo, hi)})
     instances = []
     cameras = []
 
     def walk(ni, parent):
         node = g["nodes"][ni]
-        xf = (parent @ _mat_from_node(node)).astype(np.float32)
+        m, t, r, sc = _node_matrices(node)
+        xf = _mat4_mul(_mat4_mul(_mat4_mul(_mat4_mul(parent, m), t), r), sc)  # parent * matrix * translation * rotation * scale
         if "camera" in node:
             # processGLTFNode (Scene.cpp:166-192): eye = M (0,0,0,1), up = M (0,1,0,0), fovY in degrees
             cam = g["cameras"][node["camera"]]
-            if cam.get("type") == "perspective":
-                yfov = np.float32(cam["perspective"]["yfov"]) * np.float32(180.0) / np.float32(math.pi)
-                cameras.append({"eye": (xf @ np.array([0, 0, 0, 1], np.float32))[:3], "up": (xf @ np.array([0, 1, 0, 0], np.float32))[:3],
-                                "fov_y": float(yfov)})
-        if "camera" not in node and "mesh" in node:
+            if cam.get("type") != "perspective":
+                return  # the reference returns here: the children of a non-perspective camera node are not visited
+            yfov = np.float32(np.float32(cam["perspective"]["yfov"]) * np.float32(180.0)) / np.float32(math.pi)
+            cameras.append({"eye": _mat4_vec(xf, [0, 0, 0, 1])[:3], "up": _mat4_vec(xf, [0, 1, 0, 0])[:3], "fov_y": float(yfov),
+                            "aspect": float(np.float32(cam["perspective"].get("aspectRatio", 0.0)))})
+        elif "mesh" in node:
             lo, hi = meshes[node["mesh"]]["aabb"]
-            corners = np.array([[x, y, z, 1.0] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])], np.float32)
-            wc = (corners @ xf.T)[:, :3].astype(np.float32)
-            instances.append({"transform": xf, "mesh": node["mesh"], "world_aabb": (wc.min(0), wc.max(0))})
+            instances.append({"transform": xf, "mesh": node["mesh"], "world_aabb": _aabb_transform(lo, hi, xf)})
         for c in node.get("children", []):
             walk(c, xf)
 
-    scene = g["scenes"][g.get("scene", 0)]
-    for ni in scene["nodes"]:
-        walk(ni, np.eye(4, dtype=np.float32))
-    return {"meshes": meshes, "instances": instances, "cameras": cameras, "materials": _gltf_materials(g), "images": _gltf_images(g, path.parent),
-            "textures": g.get("textures", []), "samplers": g.get("samplers", [])}
+    is_root = [True] * len(g.get("nodes", []))
+    for node in g.get("nodes", []):
+        for c in node.get("children", []):
+            is_root[c] = False
+    for ni, root in enumerate(is_root):
+        if root:
+            walk(ni, np.eye(4, dtype=np.float32))
+    return {"buffers": buffers, "meshes": meshes, "instances": instances, "cameras": cameras, "materials": _gltf_materials(g),
+            "images": _gltf_images(g, path.parent), "textures": g.get("textures", []), "samplers": g.get("samplers", [])}
 
 
 def _gltf_materials(g):
@@ -613,9 +677,47 @@ def build_scene_meshes(ctx, scene, tex_objects):
     REQUIRE_SINGLE_ANYHIT_CALL; doubleSided adds DISABLE_TRIANGLE_FACE_CULLING).  Returns (accels, per-mesh record payloads, device buffers)."""
     materials = scene.get("materials", [])
     keep, mesh_accels, mesh_records = [], [], []
+    # Scene::addBuffer (Scene.cpp:562-574): every glTF buffer goes to the device once, whole; all views of a loaded file point into these
+    d_buffers = [ctx.to_device(b) for b in scene.get("buffers", [])]
+    keep += d_buffers
     for m in scene["meshes"]:
         inputs, recs = [], []
         for p in m["primitives"]:
+            mat = materials[p["material"]] if p.get("material", -1) >= 0 and p["material"] < len(materials) else None
+            am = 0 if mat is None else mat["alpha_mode"]
+            gf = {0: 1, 1: 0, 2: 2}[am] | (4 if (mat is not None and mat["double_sided"]) else 0)
+            geo = bytearray(112)
+            views = p.get("views") if d_buffers else None
+            if views:
+                # the reference's own memory layout: BufferView = {buffer base + byte offset, count, byte stride, COMPONENT size} (Scene.cpp:84-123)
+                def bview(name):
+                    if name not in views:
+                        return struct.pack("<QIHH", 0, 0, 0, 0)
+                    buf, off, count, stride, elmt = views[name]
+                    return struct.pack("<QIHH", d_buffers[buf].data_ptr() + off, count, stride, elmt)
+                bi = L.BuildInput()
+                bi.type = L.BUILD_INPUT_TYPE_TRIANGLES
+                ta = bi.triangleArray
+                pbuf, poff, pcount, pstride, _ = views["positions"]
+                vb = (C.c_uint64 * 1)(d_buffers[pbuf].data_ptr() + poff)
+                ta.vertexBuffers, ta.numVertices, ta.vertexFormat, ta.vertexStrideInBytes = vb, pcount, L.VERTEX_FORMAT_FLOAT3, pstride
+                if "indices" in views:
+                    ibuf, ioff, icount, istride, ielmt = views["indices"]
+                    ta.indexBuffer, ta.numIndexTriplets = d_buffers[ibuf].data_ptr() + ioff, icount // 3
+                    ta.indexFormat = L.INDICES_FORMAT_UNSIGNED_SHORT3 if ielmt == 2 else L.INDICES_FORMAT_UNSIGNED_INT3
+                    ta.indexStrideInBytes = istride * 3  # Scene.cpp:930
+                fl = (C.c_uint32 * 1)(gf)
+                ta.flags, ta.numSbtRecords = fl, 1
+                bi._keep = [vb, fl]
+                inputs.append(bi)
+                geo[HG_OFF_INDICES:HG_OFF_INDICES + 16] = bview("indices")
+                geo[HG_OFF_POSITIONS:HG_OFF_POSITIONS + 16] = bview("positions")
+                geo[HG_OFF_NORMALS:HG_OFF_NORMALS + 16] = bview("normals")
+                geo[64:80] = bview("texcoords0")
+                geo[80:96] = bview("texcoords1")
+                geo[96:112] = bview("colors")
+                recs.append(bytes(geo) + pack_material(mat, tex_objects))
+                continue
             d_pos = ctx.to_device(p["positions"])
             d_nrm = ctx.to_device(p["normals"]) if p.get("normals") is not None else None
             idx = p["indices"]
@@ -624,15 +726,11 @@ def build_scene_meshes(ctx, scene, tex_objects):
                 d_idx = ctx.to_device(idx.astype(np.uint16).view(np.int16) if idx.dtype == np.uint16 else idx.astype(np.uint32).view(np.int32))
             uvs = p.get("texcoords") or [None, None]
             d_uv = [ctx.to_device(u) if u is not None else None for u in uvs]
-            mat = materials[p["material"]] if p.get("material", -1) >= 0 and p["material"] < len(materials) else None
-            am = 0 if mat is None else mat["alpha_mode"]
-            gf = {0: 1, 1: 0, 2: 2}[am] | (4 if (mat is not None and mat["double_sided"]) else 0)
             inputs.append(ctx.triangle_input(d_pos, indices=d_idx, num_sbt=1, flags=[gf], vertex_stride=12))
             keep += [d_pos, d_nrm, d_idx] + d_uv
             # whitted::HitGroupData: GeometryData{type=TRIANGLE_MESH(0) @0, 16-byte aligned union @16 holding TriangleMesh{indices, positions,
             # normals, texcoords[2], colors}}; BufferView = {ptr, count, u16 stride, u16 elmt}.  Offsets pinned against the reference
             # headers: tests/golden/kat.json "hitgroup_layout" (tests/test_oracle_kat.py)
-            geo = bytearray(112)
 
             def bview(t, elmt, stride):
                 return struct.pack("<QIHH", t.data_ptr() if t is not None else 0, (t.shape[0] if t is not None else 0), stride if t is not None else 0,

@@ -26,7 +26,14 @@ def ctxs():
     ok, why = ob.available(0)
     if not ok:
         pytest.skip(f"OptiX reference not usable here: {why}")
-    return host.Context(0), ob.OptixContext(0)
+    octx = ob.OptixContext(0)
+    # the libnvoptix.so.1 mapped into this process must be the DRIVER's: with optix_raytracer_b200/optix_shim on LD_LIBRARY_PATH these
+    # tests would compare b200rt with itself
+    mapped = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if "libnvoptix" in ln})
+    assert mapped, "OptiX initialised but no libnvoptix is mapped?"
+    assert not any("optix_shim" in m for m in mapped), f"the OptiX parity tests are running on the shim, not on the driver's OptiX: {mapped}"
+    assert not ob.shim_active()
+    return host.Context(0), octx
 
 
 def _ulps(a, b):

@@ -1,0 +1,189 @@
+"""The reference's own sample programs, UNMODIFIED (baseline/_ref, built headless by baseline/Makefile from the sources where they lie),
+run twice on the GPU box: on the driver's libnvoptix.so.1 and on this library's optixQueryFunctionTable shim
+(optix_raytracer_b200/optix_shim/libnvoptix.so.1 in front on LD_LIBRARY_PATH).  The pictures they write must agree within the image
+tolerance of the matching in-process tests.  This is the literal drop-in check: not a harness of ours calling
+OptiX-shaped functions, but main() of optixPathTracer / optixRaycasting / optixMeshViewer / optixMultiGPU as the reference wrote them
+(SDK/optixPathTracer/optixPathTracer.cpp:929-1095, SDK/optixRaycasting/optixRaycasting.cpp:352-450, SDK/optixMeshViewer/optixMeshViewer.cpp:352-520,
+SDK/optixMultiGPU/optixMultiGPU.cpp:1047-1195).
+Second half: sutil::loadScene (SDK/sutil/Scene.cpp:267-550) against host.load_gltf on the reference's glTF assets."""
+import json
+import os
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+REF = ROOT / "baseline" / "_ref"
+BIN = REF / "bin"
+SHIM_DIR = ROOT / "optix_raytracer_b200" / "optix_shim"
+torch = pytest.importorskip("torch")
+
+
+def _need(*names):
+    missing = [n for n in names if not (BIN / n).exists()]
+    if missing:
+        pytest.skip(f"baseline/_ref/bin/{missing[0]} not built (make -C baseline needs /root/reference)")
+
+
+def _driver_optix_present():
+    import ctypes
+    try:
+        ctypes.CDLL("libnvoptix.so.1")
+        return True
+    except OSError:
+        return False
+
+
+def _run(binary, args, shim, cwd, extra_env=None):
+    env = dict(os.environ)
+    env["OPTIX_SAMPLES_SDK_DIR"] = str(REF / "SDK")
+    env["OPTIX_SAMPLES_SDK_PTX_DIR"] = str(REF / "ptx")
+    paths = [str(BIN)] + ([str(SHIM_DIR)] if shim else []) + [p for p in env.get("LD_LIBRARY_PATH", "").split(":") if p and "optix_shim" not in p]
+    if shim:
+        paths = [str(SHIM_DIR)] + [p for p in paths if p != str(SHIM_DIR)]
+    env["LD_LIBRARY_PATH"] = ":".join(paths)
+    env["LD_DEBUG"] = "libs"
+    env.update(extra_env or {})
+    r = subprocess.run([str(BIN / binary)] + args, cwd=cwd, env=env, capture_output=True, text=True, timeout=600)
+    loaded = [ln.split("calling init:")[1].strip() for ln in r.stderr.splitlines() if "calling init:" in ln and "libnvoptix" in ln]
+    err = "\n".join(ln for ln in r.stderr.splitlines() if not ln.lstrip().split(":")[0].strip().isdigit())
+    assert r.returncode == 0, f"{binary} {' '.join(args)} (shim={shim}) failed ({r.returncode}):\n{r.stdout[-1500:]}\n{err[-3000:]}"
+    # which libnvoptix.so.1 did optixInit's dlopen get?  (the comparison is worthless if both runs used the same one)
+    assert loaded, f"{binary}: no libnvoptix.so.1 was loaded"
+    assert all((str(SHIM_DIR) in p) == shim for p in loaded), f"{binary} (shim={shim}) loaded {loaded}"
+    return r
+
+
+def _read_ppm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P6"
+        dims = f.readline().split()
+        while len(dims) < 2:
+            dims += f.readline().split()
+        w, h = int(dims[0]), int(dims[1])
+        assert int(f.readline()) == 255
+        return np.frombuffer(f.read(w * h * 3), np.uint8).reshape(h, w, 3)
+
+
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.fixture(scope="module")
+def optix():
+    if not _driver_optix_present():
+        pytest.skip("libnvoptix.so.1 (driver) not present on this box")
+
+
+def _both(binary, args_for, tmp_path, outputs, extra_env=None):
+    pics = {}
+    for shim in (False, True):
+        d = tmp_path / ("shim" if shim else "optix")
+        d.mkdir()
+        _run(binary, args_for(d), shim, cwd=str(d), extra_env=extra_env)
+        pics[shim] = [_read_ppm(d / o) for o in outputs]
+    return pics
+
+
+def test_optixPathTracer_binary_on_the_shim(optix, tmp_path):
+    _need("optixPathTracer")
+    pics = _both("optixPathTracer", lambda d: ["--file", str(d / "out.ppm"), "--no-gl-interop", "--dim=512x512", "--launch-samples", "16"], tmp_path, ["out.ppm"])
+    a, b = pics[False][0], pics[True][0]
+    assert a.shape == (512, 512, 3) and a.mean() > 20
+    # same seeds, same programs: OptiX and the shim differ by the fp32 arithmetic of the closed traversal only (the in-process test
+    # test_cornell_image_matches_optix_at_the_same_seeds asserts > 55 dB on the accumulation buffer)
+    assert _psnr(a, b) > 45, _psnr(a, b)
+    assert (np.abs(a.astype(int) - b.astype(int)) <= 1).mean() > 0.99
+
+
+@pytest.mark.parametrize("model", ["Duck/Duck.gltf", "Duck/DuckHole.gltf"])
+def test_optixRaycasting_binary_on_the_shim(optix, tmp_path, model):
+    _need("optixRaycasting")
+    if not (REF / "SDK" / "data" / model).exists():
+        pytest.skip(f"{model} not in baseline/_ref/SDK/data")
+    pics = _both("optixRaycasting", lambda d: ["-f", str(d / "out"), "-m", model, "-w", "800"], tmp_path, ["out.ppm", "out_translated.ppm"])
+    for a, b in zip(pics[False], pics[True]):
+        assert a.shape == b.shape and (a != a[0, 0]).any()
+        # Hit.t is truncated to an integer and shaded by the interpolated normal: identical up to the normal's last bits
+        assert (np.abs(a.astype(int) - b.astype(int)) <= 1).mean() > 0.999
+        assert _psnr(a, b) > 50
+
+
+@pytest.mark.parametrize("model", ["Duck/Duck.gltf", "WaterBottle/WaterBottle.gltf"])
+def test_optixMeshViewer_binary_on_the_shim(optix, tmp_path, model):
+    _need("optixMeshViewer")
+    if not (REF / "SDK" / "data" / model).exists():
+        pytest.skip(f"{model} not in baseline/_ref/SDK/data")
+    pics = _both("optixMeshViewer", lambda d: ["--file", str(d / "out.ppm"), "--no-gl-interop", "--model", model, "--dim=640x480"], tmp_path, ["out.ppm"])
+    a, b = pics[False][0], pics[True][0]
+    assert a.shape == (480, 640, 3) and a.std() > 5
+    assert _psnr(a, b) > 40, _psnr(a, b)
+
+
+def test_optixMultiGPU_binary_on_the_shim(optix, tmp_path):
+    """The reference's one-thread loop over all devices of the box (optixMultiGPU.cpp:562-594): asynchronous launches keep every device busy."""
+    _need("optixMultiGPU")
+    pics = _both("optixMultiGPU", lambda d: ["--file", str(d / "out.ppm"), "--launch-samples", "8"], tmp_path, ["out.ppm"])
+    a, b = pics[False][0], pics[True][0]
+    assert a.mean() > 20 and _psnr(a, b) > 40, _psnr(a, b)
+
+
+# ---- sutil::loadScene vs host.load_gltf -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["Duck/Duck.gltf", "Duck/DuckHole.gltf", "WaterBottle/WaterBottle.gltf"])
+def test_load_gltf_matches_sutil_loadScene(tmp_path, model):
+    _need("scene_dump")
+    from optix_raytracer_b200 import host
+    path = REF / "SDK" / "data" / model
+    if not path.exists():
+        pytest.skip(f"{model} not in baseline/_ref/SDK/data")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = str(BIN) + ":" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([str(BIN / "scene_dump"), str(path)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(r.stdout)
+    got = host.load_gltf(path)
+    assert len(got["meshes"]) == len(ref["meshes"]) and len(got["instances"]) == len(ref["instances"])
+    f32 = lambda v, n: np.asarray(v, np.float32).reshape(-1, n)
+    for gm, rm in zip(got["meshes"], ref["meshes"]):
+        assert len(gm["primitives"]) == len(rm["primitives"])
+        assert np.array_equal(np.concatenate(gm["aabb"]).astype(np.float32), np.asarray(rm["aabb"], np.float32))
+        for gp, rp in zip(gm["primitives"], rm["primitives"]):
+            assert np.array_equal(gp["positions"].view(np.uint32), f32(rp["positions"], 3).view(np.uint32))
+            if rp["normals"]:
+                assert np.array_equal(gp["normals"].view(np.uint32), f32(rp["normals"], 3).view(np.uint32))
+            else:
+                assert gp["normals"] is None
+            for k, key in enumerate(("texcoords0", "texcoords1")):
+                if rp[key]:
+                    assert np.array_equal(gp["texcoords"][k].view(np.uint32), f32(rp[key], 2).view(np.uint32))
+                else:
+                    assert gp["texcoords"][k] is None
+            if rp["colors"]:
+                assert np.array_equal(gp["colors"].view(np.uint32), f32(rp["colors"], 4).view(np.uint32))
+            else:
+                assert gp.get("colors") is None
+            assert np.array_equal(np.asarray(gp["indices"], np.uint32), np.asarray(rp["indices"], np.uint32))
+            assert (0 if gp["indices"] is None else gp["indices"].dtype.itemsize) == rp["index_size"]
+            assert gp["material"] == rp["material"]
+    for gi, ri in zip(got["instances"], ref["instances"]):
+        assert gi["mesh"] == ri["mesh"]
+        assert np.array_equal(gi["transform"].astype(np.float32).view(np.uint32), f32(ri["transform"], 4).view(np.uint32))
+        assert np.array_equal(np.concatenate(gi["world_aabb"]).astype(np.float32).view(np.uint32), np.asarray(ri["world_aabb"], np.float32).view(np.uint32))
+    assert len(got["materials"]) == len(ref["materials"])
+    for gm, rm in zip(got["materials"], ref["materials"]):
+        assert np.array_equal(np.asarray(gm["base_color"], np.float32), np.asarray(rm["base_color"], np.float32))
+        assert np.float32(gm["metallic"]) == np.float32(rm["metallic"]) and np.float32(gm["roughness"]) == np.float32(rm["roughness"])
+        assert gm["alpha_mode"] == rm["alpha_mode"] and bool(gm["double_sided"]) == bool(rm["double_sided"])
+        if rm["alpha_mode"] == 1:
+            assert np.float32(gm["alpha_cutoff"]) == np.float32(rm["alpha_cutoff"])
+        assert np.array_equal(np.asarray(gm["emissive_factor"], np.float32), np.asarray(rm["emissive_factor"], np.float32))
+        for key in ("base_color_tex", "metallic_roughness_tex", "normal_tex", "emissive_tex"):
+            assert (gm[key] is not None) == bool(rm[key]["present"]), key
+            if gm[key] is not None:
+                assert gm[key]["texcoord"] == rm[key]["texcoord"]
+                assert np.allclose(gm[key]["scale"], rm[key]["scale"]) and np.allclose(gm[key]["offset"], rm[key]["offset"])

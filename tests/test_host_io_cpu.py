@@ -118,3 +118,24 @@ def test_exr_is_read_by_an_independent_decoder(tmp_path, monkeypatch):
             pytest.skip("this OpenCV build has no OpenEXR codec")
         got = img[..., [2, 1, 0, 3]] if shape[2] == 4 else img[..., ::-1]
         assert np.array_equal(got, acc.astype(np.float16).astype(np.float32))
+
+
+def test_load_gltf_reads_the_duck_as_the_committed_fixture_has_it():
+    """host.load_gltf on the reference's Duck.gltf (baseline/_ref/SDK/data, where baseline/Makefile put the assets) against the
+    fixture tests/golden/duck_mesh.npz that tools/make_duck_fixture.py made from the same file; the comparison with sutil::loadScene
+    itself runs on the GPU box (tests/test_gpu_reference_samples.py)."""
+    import pathlib
+    import pytest
+    from optix_raytracer_b200 import host
+    from tests import common
+    path = pathlib.Path(__file__).resolve().parents[1] / "baseline" / "_ref" / "SDK" / "data" / "Duck" / "Duck.gltf"
+    if not path.exists():
+        pytest.skip("baseline/_ref/SDK/data/Duck not present (make -C baseline needs /root/reference)")
+    sc, fx = host.load_gltf(path), common.duck_scene()
+    p, q = sc["meshes"][0]["primitives"][0], fx["meshes"][0]["primitives"][0]
+    for k in ("positions", "normals"):
+        assert np.array_equal(p[k].view(np.uint32), q[k].view(np.uint32))
+    assert np.array_equal(p["indices"], q["indices"]) and np.array_equal(p["texcoords"][0], q["texcoords"][0])
+    assert np.allclose(sc["instances"][0]["transform"], fx["instances"][0]["transform"], rtol=0, atol=1e-7)
+    assert p["views"]["positions"][3] == 12 and p["views"]["indices"][4] == 2 and len(sc["buffers"]) == 1
+    assert sc["materials"][0]["base_color_tex"] is not None and p["colors"] is None
