@@ -27,9 +27,10 @@ static std::vector<unsigned char> fetch(const V& v, size_t elmt)
 }
 static void put_floats(const char* key, const std::vector<unsigned char>& b, bool comma = true)
 {
+    // the fp32 BIT PATTERNS (a decimal -0 would come back from a JSON parser as the integer 0)
     printf("\"%s\": [", key);
-    const float* f = (const float*)b.data();
-    for (size_t i = 0; i < b.size() / 4; ++i) printf("%s%.9g", i ? "," : "", f[i]);
+    const unsigned* f = (const unsigned*)b.data();
+    for (size_t i = 0; i < b.size() / 4; ++i) printf("%s%u", i ? "," : "", f[i]);
     printf("]%s", comma ? "," : "");
 }
 static void put_tex(const char* key, const MaterialData::Texture& t, bool comma = true)

@@ -147,6 +147,7 @@ int b200rt_context_destroy(b200rt_context ctx)
         DeviceGuard guard(ctx->device);
         cudaDeviceSynchronize();
         pathtracer_release(ctx);
+        whitted_release(ctx);
         retire_loops(ctx, true);
         if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);

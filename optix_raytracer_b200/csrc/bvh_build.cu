@@ -769,12 +769,11 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
         int ids[8];
         float area[8];
         int cnt[8];
-        int hgt[8];
         int m = 0;
         auto push = [&](int id) {
             ids[m] = id;
-            if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); hgt[m] = height[id]; }
-            else { cnt[m] = 1; area[m] = -1.0f; hgt[m] = 0; }
+            if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); }
+            else { cnt[m] = 1; area[m] = -1.0f; }
             ++m;
         };
         const int root = (int)work[i];
@@ -783,11 +782,15 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
         else { hroot = height[root]; push(__float_as_int(box_lo[root].w)); push(__float_as_int(box_hi[root].w)); }
         // depth guard: a subtree too tall for the levels that are left opens its tallest children first until every child is at least 3
         // lower than the root (7 openings always suffice); this takes precedence over the surface-area order below
+        // (heights are read here only: one load per wide node on the ordinary path)
         if (levels_needed(hroot) > levels_left - 2) {
             while (m < 8) {
                 int best = -1, bh = hroot - 3;
-                for (int k = 0; k < m; ++k)
-                    if (ids[k] < ninternal && hgt[k] > bh) { bh = hgt[k]; best = k; }
+                for (int k = 0; k < m; ++k) {
+                    if (ids[k] >= ninternal) continue;  // a leaf cannot be opened (and hroot - 3 may be negative)
+                    const int hk = (int)height[ids[k]];
+                    if (hk > bh) { bh = hk; best = k; }
+                }
                 if (best < 0) break;
                 const int id = ids[best];
                 const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);

@@ -18,6 +18,7 @@ struct Workspace {
 };
 struct PTGraphCache;
 class LoopGraph;
+struct WLoopCache;
 
 }  // namespace b200rt
 
@@ -38,6 +39,7 @@ struct b200rt_context_t {
     cudaStream_t ws_stream = nullptr;
     bool ws_busy = false;
     std::vector<b200rt::LoopGraph*> loops;      // build loops in flight (loop_graph.h)
+    b200rt::WLoopCache* w_loop = nullptr;       // the BLEND level loop of the whitted launches (whitted.cu)
     b200rt::PTGraphCache* pt_graphs = nullptr;  // instantiated wavefront-loop graphs of the path-tracer launches (pathtracer.cu)
     std::mutex mu;
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING

@@ -28,6 +28,7 @@ int trace_buffer(b200rt_context, cudaStream_t, b200rt_traversable, b200rt_device
                  b200rt_deviceptr handle_dev = 0, const b200rt_shader_binding_table* anyhit_sbt = nullptr);
 // whitted.cu
 int launch_whitted(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, const b200rt_shader_binding_table*, unsigned, unsigned);
+void whitted_release(b200rt_context);  // destroys the context's BLEND level loop
 int texture_create(b200rt_context, int, int, const void*, int, int, int, uint64_t*, uint64_t*);
 int texture_destroy(b200rt_context, uint64_t, uint64_t);
 // playground.cu

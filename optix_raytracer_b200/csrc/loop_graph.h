@@ -56,11 +56,12 @@ public:
         return 0;
     }
 
+    // instantiated on the first launch; a loop whose kernels and arguments stay the same can be launched again and again
     int launch(cudaStream_t s)
     {
-        B2_CUDA(ctx_, cudaGraphInstantiate(&exec_, graph_, 0));
+        if (!exec_) B2_CUDA(ctx_, cudaGraphInstantiate(&exec_, graph_, 0));
         B2_CUDA(ctx_, cudaGraphLaunch(exec_, s));
-        B2_CUDA(ctx_, cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+        if (!done_) B2_CUDA(ctx_, cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
         B2_CUDA(ctx_, cudaEventRecord(done_, s));
         return 0;
     }

@@ -6,6 +6,9 @@
 // SDK/cuda/LocalGeometry.h:59-176 (shading normal), SDK/optixRaycasting/optixRaycasting.cpp:289-317 (launch).
 // Rays are 32-byte AoS records and hits 16-byte records exactly as in the reference, so a warp reads
 // 1 KiB and writes 512 B contiguous per request; each ray record is fetched as two 16-byte loads.
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -74,6 +77,7 @@ template <int KIND, bool AH>
 struct RayWork {
     static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
+    static constexpr bool SMEM_STATE = true;  // commit wants the whole hit record: keep it in the lane's shared slot (trav_coop.cuh)
     AnyHitCfg ah;
     double att;  // AH, KIND 1: pending occlusion attenuation of this lane's ray
     const AccelHeader* handle;
@@ -108,7 +112,7 @@ struct RayWork {
         const float4 a = __ldg(rays + 2 * (size_t)i), b = __ldg(rays + 2 * (size_t)i + 1);
         s.best.t = b.w;
         // rays of a buffer come from anywhere: those that pass the scene (or an instance) by are dropped at its bounds
-        if (!trav_begin_handle<B200RT_RAY_BOUNDS != 0>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
+        if (!trav_begin_handle<B200RT_RAY_BOUNDS != 0, SMEM_STATE>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, KIND == 1 ? TP_ANY : 0u, cull_flags(i), 0u)) {
             commit(s, false);
             return false;
         }
@@ -118,7 +122,7 @@ struct RayWork {
     {
         if (handle->kind == ACCEL_KIND_GAS || any_ray_done(s)) return false;
         const float4 a = __ldg(rays + 2 * item), b = __ldg(rays + 2 * item + 1);
-        return trav_begin_handle<B200RT_RAY_BOUNDS != 0>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
+        return trav_begin_handle<B200RT_RAY_BOUNDS != 0, SMEM_STATE>(s, my_ray, handle, f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), a.w, s.pack & (TP_ANY | TP_FOUND_ANY),
                                  cull_flags((uint32_t)item), s.inst + 1u);
     }
     __device__ __forceinline__ void commit(const Trav& s, bool found)
@@ -226,6 +230,25 @@ __global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_ke
             atomicAdd(&stats[1], (unsigned long long)st.tris);
         }
     }
+}
+
+// optixRaycasting's launch on the one-ray-per-thread driver (trav_coop.cuh: trace_one_per_thread): the sample's ray buffers are coherent
+// (orthographic grid in pixel order, optixRaycastingKernels.cu:42-55).  Scenes with any-hit geometry return at once, like the plain
+// cooperative kernel does, and the any-hit cooperative kernel enqueued behind this one takes them.
+__global__ void __launch_bounds__(128) raycast_simple_kernel(const RaycastParamsDev* __restrict__ rc_params, uint32_t n, ExtHit* __restrict__ ext,
+                                                              const char* __restrict__ hg_base, uint32_t hg_stride, uint32_t hg_count, uint32_t dual)
+{
+    const RaycastParamsDev P = *rc_params;
+    RayWork<2, false> w;
+    w.ah = AnyHitCfg{nullptr, 0u, 0u, AH_NONE};
+    w.att = 1.0;
+    w.flag_period = 0;
+    w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits;
+    if (dual && w.handle->anyhit != 0u) return;
+    w.ray_flags = 0u; w.ext = ext; w.occluded = nullptr;
+    w.hg_base = hg_base; w.hg_stride = hg_stride; w.hg_count = hg_count; w.item = 0;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    trace_one_per_thread(w, i, i < n, nullptr);
 }
 
 // a zeroed fetch counter for one persistent launch: slots rotate so launches on different streams do not share one
@@ -367,9 +390,15 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     // at all is decided on the device (trace_rays_kernel), so the launch never waits for anything
     const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
     const uint32_t dual = full_records ? 1u : 0u;
-    trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
-        nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-        sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
+    // B200RT_RAYCAST_DRIVER=coop puts the launch back on the persistent cooperative driver (A/B runs; buffers of incoherent rays)
+    static const bool coop = [] { const char* e = getenv("B200RT_RAYCAST_DRIVER"); return e && !strcmp(e, "coop"); }();
+    if (coop)
+        trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
+            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
+            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
+    else
+        raycast_simple_kernel<<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, (ExtHit*)ext, (const char*)sbt->hitgroupRecordBase,
+                                                             sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, dual);
     if (full_records) {
         B2_LAUNCH_CHECK(ctx);
         const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, AH_TEXTURE_MASK};

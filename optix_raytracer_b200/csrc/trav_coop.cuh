@@ -54,7 +54,17 @@ constexpr int COOP_WARPS = COOP_BLOCK / 32;
 #define B200RT_COOP_MIN_CTAS 8
 #endif
 constexpr int COOP_MIN_CTAS = B200RT_COOP_MIN_CTAS;  // resident CTAs per SM the path-tracing trace kernel is compiled for (8 -> 64 registers)
-constexpr int RAY_S_STRIDE = 9;        // odd stride: lanes reading different owners hit different banks
+// Lane slot in shared memory (floats): ox, oy, oz, Sx, Sy, Sz, pack, tmin, cull — what the lane that tests one of this ray's triangles
+// needs.  Kernels whose Work sets SMEM_STATE keep more of the lane's state there: the triangle base pointer of the GAS being traversed
+// (read by the triangle rounds only — by other lanes, which otherwise fetch it with two shuffles) and the primitive / SBT / instance /
+// barycentrics of the best hit so far (written when a hit is accepted, read at commit).  That takes registers off kernels whose commit
+// needs the whole hit record: the optixRaycasting kernel spilled 158 bytes at the 64-register cap and spills 16 with it (Duck ray
+// buffers 5666 -> 6389 Mrays/s).  The path-tracing trace kernel only carries prim and sbt and does not spill; for it the larger slot
+// costs occupancy through shared memory (8 CTAs x 10.7 KB no longer fit the 28 % carve-out: 2138 -> 1645 Mrays/s on the bench), so it
+// stays off there.  Keeping the popped stack entry in registers on top of it (B200RT_STACK_TOP) measured slower in both settings.
+constexpr int RAY_S_STRIDE_BASE = 9, RAY_S_STRIDE_SMEM = 17;  // odd strides: lanes reading different owners hit different banks
+constexpr int RS_TRIS = 9, RS_PRIM = 11, RS_SBT = 12, RS_INST = 13, RS_B1 = 14, RS_B2 = 15;
+template <bool SM> constexpr int ray_s_stride() { return SM ? RAY_S_STRIDE_SMEM : RAY_S_STRIDE_BASE; }
 
 // pack word layout
 constexpr uint32_t TP_ANY = 1u << 16;        // any-hit (terminate on first hit)
@@ -117,7 +127,7 @@ __device__ __forceinline__ uint4 node_load(const uint4* p, uint64_t pol)
 
 struct Trav {
     const uint4* nodes;
-    const float4* tris;
+    const float4* tris;     // unused (and dead) in kernels that keep it in the lane's shared slot (SMEM_STATE)
     float ox, oy, oz;       // origin in the space of the GAS being traversed
     float idx, idy, idz;    // reciprocal (clamped) direction for the box tests
     float tmin;
@@ -163,8 +173,40 @@ __device__ __forceinline__ void stack_drop(Trav& s, const uint2* __restrict__ st
 #endif
 }
 
+template <bool SM>
+__device__ __forceinline__ const float4* lane_tris(const Trav& s, const float* __restrict__ slot)
+{
+    if constexpr (SM) return (const float4*)(uintptr_t)(((unsigned long long)__float_as_uint(slot[RS_TRIS + 1]) << 32) | __float_as_uint(slot[RS_TRIS]));
+    else return s.tris;
+}
+template <bool SM>
+__device__ __forceinline__ void set_lane_tris(Trav& s, float* __restrict__ slot, const float4* p)
+{
+    if constexpr (SM) {
+        slot[RS_TRIS] = __uint_as_float((uint32_t)(uintptr_t)p);
+        slot[RS_TRIS + 1] = __uint_as_float((uint32_t)((unsigned long long)(uintptr_t)p >> 32));
+    } else s.tris = p;
+}
+// best-hit fields that only commit reads
+template <bool SM>
+__device__ __forceinline__ void store_hit(Trav& s, float* __restrict__ slot, float b1, float b2, uint32_t prim, uint32_t sbt)
+{
+    if constexpr (SM) {
+        slot[RS_B1] = b1; slot[RS_B2] = b2; slot[RS_PRIM] = __uint_as_float(prim); slot[RS_SBT] = __uint_as_float(sbt); slot[RS_INST] = __uint_as_float(s.inst);
+    } else { s.best.b1 = b1; s.best.b2 = b2; s.best.prim = prim; s.best.sbt = sbt; s.best.inst = s.inst; }
+}
+template <bool SM>
+__device__ __forceinline__ void load_hit(Trav& s, const float* __restrict__ slot)
+{
+    if constexpr (SM) {
+        s.best.b1 = slot[RS_B1]; s.best.b2 = slot[RS_B2]; s.best.prim = __float_as_uint(slot[RS_PRIM]); s.best.sbt = __float_as_uint(slot[RS_SBT]);
+        s.best.inst = __float_as_uint(slot[RS_INST]);
+    }
+}
+
+template <int STRIDE>
 struct CoopShared {
-    float ray[COOP_WARPS][32 * RAY_S_STRIDE];  // per lane: ox, oy, oz, Sx, Sy, Sz, pack, tmin, cull
+    float ray[COOP_WARPS][32 * STRIDE];  // per lane: ox, oy, oz, Sx, Sy, Sz, pack, tmin, cull (+ triangle base, best-hit fields: SMEM_STATE)
     uint32_t unit_tri[COOP_WARPS][32];
     uint32_t unit_owner[COOP_WARPS][32];
     float res_t[COOP_WARPS][32];
@@ -202,7 +244,7 @@ __device__ __forceinline__ bool ray_reaches_bounds(const AccelHeader* __restrict
 // scene (camera rays around a model) this replaces the ray set-up (three more IEEE divisions), the root fetch and a full node visit by
 // some twenty instructions.  The box is padded like every node box of the BVH (2^-16 of the largest extent) and compared with the same
 // slack, so it is exactly as conservative as the traversal it stands in for: the hit rule (traverse.cuh) still decides alone.
-template <bool BOUNDS = false>
+template <bool BOUNDS = false, bool SM = false>
 __device__ __forceinline__ bool trav_begin(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ gas, float3 o, float3 d, float tmin,
                                            uint32_t keep_flags, uint32_t cull)
 {
@@ -222,7 +264,7 @@ __device__ __forceinline__ bool trav_begin(Trav& s, float* __restrict__ my_ray, 
     }
     const char* base = (const char*)gas;
     s.nodes = (const uint4*)(base + gas->nodes_off);
-    s.tris = (const float4*)(base + gas->tris_off);
+    set_lane_tris<SM>(s, my_ray, (const float4*)(base + gas->tris_off));
     const TriRay tr = make_tri_ray(o, d);
     s.ox = o.x; s.oy = o.y; s.oz = o.z;
     const uint32_t nx = bx < 0.0f, ny = by < 0.0f, nz = bz < 0.0f;
@@ -245,14 +287,14 @@ __device__ __forceinline__ bool trav_begin(Trav& s, float* __restrict__ my_ray, 
 // Set up traversal of `h` (GAS, or the first usable instance >= first_inst of an IAS) for the world-space ray.
 // keep = TP_* bits to carry over; cull = the ray's OptixRayFlags (the CULL_* and DISABLE/ENFORCE_ANYHIT bits are used).
 // Returns false when there is nothing (more) to traverse.
-template <bool BOUNDS = false>
+template <bool BOUNDS = false, bool SM = false>
 __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ my_ray, const AccelHeader* __restrict__ h, float3 o, float3 d,
                                                   float tmin, uint32_t keep, uint32_t cull, uint32_t first_inst)
 {
     if (h->kind == ACCEL_KIND_GAS) {
         if (first_inst > 0u) return false;
         s.inst = 0u;
-        if (!trav_begin<BOUNDS>(s, my_ray, h, o, d, tmin, keep, cull_word(cull, 0u))) { s.pack = keep; return false; }
+        if (!trav_begin<BOUNDS, SM>(s, my_ray, h, o, d, tmin, keep, cull_word(cull, 0u))) { s.pack = keep; return false; }
         return true;
     }
     const InstanceRecord* recs = (const InstanceRecord*)((const char*)h + h->inst_off);
@@ -263,7 +305,7 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
         s.inst = k;
         const uint32_t c = cull_word(cull, ir->flags);  // the instance's face-culling / facing / any-hit flags
         // instances are tested at their bounds always: with several of them a ray passes most of them by
-        if (trav_begin<true>(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c)) return true;
+        if (trav_begin<true, SM>(s, my_ray, (const AccelHeader*)ir->gas, xform_point(ir->inv, o), xform_vec(ir->inv, d), tmin, keep, c)) return true;
     }
     s.pack = keep;  // nothing (more) to traverse: the flags carried so far are what commit sees
     return false;
@@ -446,11 +488,18 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
 template <class Work, class = void> struct CoopHasNodePolicy { static constexpr bool value = false; };
 template <class Work> struct CoopHasNodePolicy<Work, decltype((void)Work::NODE_POLICY)> { static constexpr bool value = Work::NODE_POLICY; };
 template <class Work> constexpr bool coop_node_policy() { return CoopHasNodePolicy<Work>::value; }
+//   static constexpr bool SMEM_STATE (optional)                    the lane's shared slot also holds the triangle base and the best hit's
+//                                                                  fields; the Work's trav_begin* calls must pass the same value
+template <class Work, class = void> struct CoopHasSmemState { static constexpr bool value = false; };
+template <class Work> struct CoopHasSmemState<Work, decltype((void)Work::SMEM_STATE)> { static constexpr bool value = Work::SMEM_STATE; };
+template <class Work> constexpr bool coop_smem_state() { return CoopHasSmemState<Work>::value; }
 
 template <class Work>
 __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, unsigned int* __restrict__ fetch_counter, TravStats* st)
 {
-    __shared__ CoopShared sh;
+    constexpr bool SM = coop_smem_state<Work>();
+    constexpr int RAY_S_STRIDE = ray_s_stride<SM>();
+    __shared__ CoopShared<RAY_S_STRIDE> sh;
     __shared__ CoopSharedAnyHit<Work::ANYHIT> sha;
     const bool tri_stream = work.stream_triangles();  // uniform over the launch
     constexpr bool NODE_POLICY = coop_node_policy<Work>();
@@ -480,6 +529,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
     for (;;) {
         // ---- commit finished rays together, then every lane without a ray takes the next work item
         if (fin) {
+            load_hit<SM>(s, my_ray);
             if constexpr (Work::CONTINUES) { if (work.commit_continue(s, my_ray, (s.pack & TP_FOUND_ANY) != 0u)) has = true; }
             else work.commit(s, (s.pack & TP_FOUND_ANY) != 0u);
             fin = false;
@@ -572,7 +622,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                         while (g.y) {
                             const uint32_t ti = 31u - __clz(g.y);
                             g.y &= ~(1u << ti);
-                            const float4* tp = s.tris + (size_t)(g.x + ti) * 3u;
+                            const float4* tp = lane_tris<SM>(s, my_ray) + (size_t)(g.x + ti) * 3u;
                             const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                             if (st) st->tris++;
                             float t, b1, b2;
@@ -587,8 +637,8 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                             if (uh) {
                                 const uint32_t ord = __float_as_uint(q2.w);
                                 if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
-                                    s.best.t = t; s.best.b1 = b1; s.best.b2 = b2; s.best.ord = ord;
-                                    s.best.prim = __float_as_uint(q0.w); s.best.sbt = __float_as_uint(q1.w); s.best.inst = s.inst;
+                                    s.best.t = t; s.best.ord = ord;
+                                    store_hit<SM>(s, my_ray, b1, b2, __float_as_uint(q0.w), __float_as_uint(q1.w));
                                     s.pack |= TP_FOUND | TP_FOUND_ANY;
                                 }
                             }
@@ -624,7 +674,9 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                     const bool valid = base + lane < total;
                     const uint32_t owner = valid ? sh.unit_owner[wid][lane] : lane;
                     const float tfar = __shfl_sync(FULL, s.best.t, owner);
-                    const uint64_t tris_base = __shfl_sync(FULL, (unsigned long long)(uintptr_t)s.tris, owner);
+                    uint64_t tris_base;
+                    if constexpr (SM) tris_base = (uint64_t)(uintptr_t)lane_tris<true>(s, &sh.ray[wid][owner * RAY_S_STRIDE]);
+                    else tris_base = __shfl_sync(FULL, (unsigned long long)(uintptr_t)s.tris, owner);
                     float ut = 0.f, ub1 = 0.f, ub2 = 0.f;
                     uint32_t uord = 0xffffffffu, uprim = 0u, usbt = 0u;
                     bool uhit = false;
@@ -675,7 +727,7 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                     const int src = win >= 0 ? win : (int)lane;
                     const float wb1 = __shfl_sync(FULL, ub1, src), wb2 = __shfl_sync(FULL, ub2, src);
                     const uint32_t wprim = __shfl_sync(FULL, uprim, src), wsbt = __shfl_sync(FULL, usbt, src);
-                    if (win >= 0) { s.best.b1 = wb1; s.best.b2 = wb2; s.best.prim = wprim; s.best.sbt = wsbt; s.best.inst = s.inst; }
+                    if (win >= 0) store_hit<SM>(s, my_ray, wb1, wb2, wprim, wsbt);
                     __syncwarp();
                 }
                 if (has) {
@@ -686,6 +738,57 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
             if (act == 0u || (can_refill && __popc(act) < REFILL_THRESHOLD)) break;
         }
     }
+}
+
+// ---- one ray per thread ---------------------------------------------------------------------------------------------------------------
+// The same traversal state machine without the warp-cooperative machinery: every thread takes ONE work item, visits its nodes and tests
+// the triangles of a leaf group as it meets them.  For COHERENT ray buffers (orthographic / camera rays in pixel order) the lanes of a
+// warp walk the same nodes anyway, so there is nothing for the cooperative rounds to repair, and their bookkeeping (shared-memory unit
+// lists, prefix sums, refills) is pure cost: optixRaycasting's two 1 M-ray ortho batches on the Duck took 0.35 ms on the persistent
+// driver, against OptiX's 0.33 (profiles/r02_small_scenes.md).  Incoherent rays stay on trace_persistent.  Same Work concept (no any-hit
+// programs: ANYHIT launches stay on the cooperative driver), same tri_unit arithmetic, same hit rule: bit-identical results.
+template <class Work>
+__device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, bool valid, TravStats* st)
+{
+    static_assert(!Work::ANYHIT && !Work::CONTINUES, "any-hit / continuing launches use trace_persistent");
+    constexpr bool SM = coop_smem_state<Work>();
+    float my_ray[ray_s_stride<SM>()];   // registers here: every index is a compile-time constant
+    uint2 stack[TRAV_STACK];
+    Trav s;
+    s.tgroup = make_uint2(0u, 0u);
+    s.ngroup = make_uint2(0u, 0u);
+    s.pack = 0u;
+    s.best.t = 0.f;
+    if (!valid || !work.fetch(item, s, my_ray)) return;   // fetch commits a ray that has nothing to traverse
+    for (;;) {
+        if (s.ngroup.y & NODE_BITS) {
+            const uint2 nt = trav_node_step(s, stack, st);
+            uint32_t rem = nt.y;
+            while (rem) {
+                const uint32_t ti = 31u - __clz(rem);
+                rem &= ~(1u << ti);
+                const float4* tp = lane_tris<SM>(s, my_ray) + (size_t)(nt.x + ti) * 3u;
+                const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                if (st) st->tris++;
+                float t, b1, b2;
+                if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
+                    const uint32_t ord = __float_as_uint(q2.w);
+                    if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
+                        s.best.t = t; s.best.ord = ord;
+                        store_hit<SM>(s, my_ray, b1, b2, __float_as_uint(q0.w), __float_as_uint(q1.w));
+                        s.pack |= TP_FOUND | TP_FOUND_ANY;
+                        if (s.pack & TP_ANY) { s.ngroup.y = 0u; s.sp = 0; break; }
+                    }
+                }
+            }
+            continue;
+        }
+        if (s.sp > 0) { s.ngroup = stack_peek(s, stack); stack_drop(s, stack); continue; }   // only node groups are ever pushed here
+        if (work.next_instance(s, my_ray)) continue;
+        break;
+    }
+    load_hit<SM>(s, my_ray);
+    work.commit(s, (s.pack & TP_FOUND_ANY) != 0u);
 }
 
 }  // namespace b200rt

@@ -36,6 +36,7 @@
 #include "internal.h"
 #include "rt_math.cuh"
 #include "trav_coop.cuh"
+#include "loop_graph.h"
 #include "anyhit.cuh"
 
 namespace b200rt {
@@ -193,18 +194,27 @@ struct WCounters {
     unsigned int nchain;   // level-0 BLEND slots (pixels COMBINE has to fold)
     unsigned int overflow; // hits dropped because the slot capacity was reached
     unsigned int nprimary; // camera rays RAYGEN found heading for the scene bounds (PRIMARY's work items at level 0)
+    // BLEND scenes: the levels run as a device-side loop (loop_graph.h); its state
+    unsigned int level;        // level being traced
+    unsigned int level_start;  // first hit slot of the level
+    unsigned int n_items;      // continuation rays of the level (level > 0)
 };
 // asynchronous launch errors, written by the kernels into the context's pinned host block and reported by the NEXT launch
 // (like CUDA's own asynchronous errors)
 struct WAsyncFlags { unsigned int unexpected_blend; unsigned int too_many_lights; unsigned int slot_overflow; };
 
 // everything the three stages share, passed by value (constant bank)
+struct WK;
+__device__ __forceinline__ uint32_t w_level(const WK& k);
+__device__ __forceinline__ uint32_t w_level_start(const WK& k);
+__device__ __forceinline__ unsigned int* w_fetch(const WK& k, uint32_t which);
 struct WK {
     const WParams* params;
     uint32_t width, height, nl_cap, level, level_start, cap_slots;
     const char* hg_base;
     uint32_t hg_stride, hg_count;
-    uint32_t blend_levels;  // 1: the host runs the BLEND levels (it found such a material); 0: SHADE flags one as an error
+    uint32_t blend_levels;  // 1: the BLEND levels are run (the host found such a material; level / level_start / fetch come from the
+                            //    device-side loop state in WCounters); 0: one level, and SHADE flags a BLEND material as an error
     WCounters* counters;
     WSlot* slots;
     float4* base;        // per slot: emission part of the result
@@ -221,6 +231,11 @@ struct WK {
     unsigned int* fetch; // work-item cursor of the persistent launch
     WAsyncFlags* async_flags;
 };
+__device__ __forceinline__ uint32_t w_level(const WK& k) { return k.blend_levels ? k.counters->level : 0u; }
+__device__ __forceinline__ uint32_t w_level_start(const WK& k) { return k.blend_levels ? k.counters->level_start : 0u; }
+// work-item cursor of a persistent launch: two per level (PRIMARY, SHADOW), all zeroed at the start of the frame
+__device__ __forceinline__ unsigned int* w_fetch(const WK& k, uint32_t which) { return k.fetch + 2u * w_level(k) + which; }
+
 
 // __raygen__pinhole's ray for a pixel (whitted.cu:44-80); a continuation regenerates it (optixGetWorldRayOrigin / Direction)
 __device__ __forceinline__ void w_camera_ray(const WParams& P, uint32_t width, uint32_t height, uint32_t pixel, float3& org, float3& dir)
@@ -285,9 +300,10 @@ struct WPrimaryWork {
     static constexpr bool ANYHIT = AH;
     const WK& k;
     const AccelHeader* handle;
+    uint32_t level;
     uint32_t pixel;
     int parent;
-    __device__ WPrimaryWork(const WK& k_, const AccelHeader* h) : k(k_), handle(h), pixel(0), parent(-1) {}
+    __device__ WPrimaryWork(const WK& k_, const AccelHeader* h, uint32_t level_) : k(k_), handle(h), level(level_), pixel(0), parent(-1) {}
 
     __device__ __forceinline__ bool anyhit_enabled() const { return handle->anyhit != 0u; }
     __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
@@ -304,7 +320,7 @@ struct WPrimaryWork {
     }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        if (k.level == 0) { pixel = k.primary[item]; parent = -1; }
+        if (level == 0) { pixel = k.primary[item]; parent = -1; }
         else { parent = (int)k.cont[item]; pixel = k.slots[parent].pixel; }
         float3 o, d;
         float tmin;
@@ -346,7 +362,7 @@ struct WPrimaryWork {
         }
         WSlot w;
         w.pixel = pixel; w.parent = parent; w.t = s.best.t; w.prim = s.best.prim; w.inst = s.best.inst; w.b1 = s.best.b1; w.b2 = s.best.b2;
-        w.sbt = s.best.sbt & TRI_SBT_MASK; w.next = W_NEXT_NONE; w.flags = 0u; w.one_minus_alpha = 0.f; w.level = k.level;
+        w.sbt = s.best.sbt & TRI_SBT_MASK; w.next = W_NEXT_NONE; w.flags = 0u; w.one_minus_alpha = 0.f; w.level = level;
         k.slots[slot] = w;
         if (parent >= 0) k.slots[parent].next = (int)slot;
     }
@@ -360,9 +376,10 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const
 {
     const AccelHeader* handle = (const AccelHeader*)k.params->handle;
     if ((handle->anyhit != 0u) != AH) return;
-    if (k.level == 0) n_items = k.counters->nprimary;  // counted by RAYGEN
-    WPrimaryWork<AH> work(k, handle);
-    trace_persistent(work, n_items, k.fetch, nullptr);
+    const uint32_t level = w_level(k);
+    n_items = level == 0 ? k.counters->nprimary : k.counters->n_items;  // counted by RAYGEN / by the previous level's SHADE
+    WPrimaryWork<AH> work(k, handle, level);
+    trace_persistent(work, n_items, w_fetch(k, 0u), nullptr);
 }
 
 // ---- SHADE: __closesthit__radiance up to the shadow rays, one thread per hit slot of the level --------------------------------------
@@ -376,7 +393,7 @@ __global__ void __launch_bounds__(128) w_shade_kernel(const __grid_constant__ WK
     }
     const uint32_t nl = min(P.lights.count, k.nl_cap);
     const AccelHeader* handle = (const AccelHeader*)P.handle;
-    for (uint32_t si = k.level_start + blockIdx.x * blockDim.x + threadIdx.x; si < end; si += gridDim.x * blockDim.x) {
+    for (uint32_t si = w_level_start(k) + blockIdx.x * blockDim.x + threadIdx.x; si < end; si += gridDim.x * blockDim.x) {
         const WSlot h = k.slots[si];
         float3 org, dir;
         w_camera_ray(P, k.width, k.height, h.pixel, org, dir);
@@ -498,9 +515,10 @@ struct WShadowWork {
     static constexpr bool ANYHIT = AH;
     const WK& k;
     const AccelHeader* handle;
-    uint32_t nl, per_slot, slot, li;
+    uint32_t nl, per_slot, slot, li, level_start;
     double att;
-    __device__ WShadowWork(const WK& k_, const AccelHeader* h, uint32_t nl_) : k(k_), handle(h), nl(nl_), per_slot(max(nl_, 1u)), slot(0), li(0), att(1.0) {}
+    __device__ WShadowWork(const WK& k_, const AccelHeader* h, uint32_t nl_, uint32_t level_start_)
+        : k(k_), handle(h), nl(nl_), per_slot(max(nl_, 1u)), slot(0), li(0), level_start(level_start_), att(1.0) {}
 
     __device__ __forceinline__ bool anyhit_enabled() const { return handle->anyhit != 0u; }
     __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
@@ -511,7 +529,7 @@ struct WShadowWork {
     __device__ __forceinline__ bool stream_triangles() const { return false; }
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
-        slot = k.level_start + item / per_slot;
+        slot = level_start + item / per_slot;
         li = item % per_slot;
         att = 1.0;
         if (li < nl && k.kinds[(size_t)slot * nl + li] == 1u) {
@@ -574,9 +592,10 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const 
     if ((handle->anyhit != 0u) != AH) return;
     const uint32_t end = min(k.counters->nslots, k.cap_slots);
     const uint32_t nl = min(P->lights.count, k.nl_cap);
-    const uint32_t n_items = end > k.level_start ? (end - k.level_start) * max(nl, 1u) : 0u;
-    WShadowWork<AH> work(k, handle, nl);
-    trace_persistent(work, n_items, k.fetch, nullptr);
+    const uint32_t level_start = w_level_start(k);
+    const uint32_t n_items = end > level_start ? (end - level_start) * max(nl, 1u) : 0u;
+    WShadowWork<AH> work(k, handle, nl, level_start);
+    trace_persistent(work, n_items, w_fetch(k, 1u), nullptr);
 }
 
 // ---- COMBINE: fold the levels of a BLEND pixel back to front, as the recursion of __closesthit__radiance returns -----------------------
@@ -606,6 +625,30 @@ __global__ void __launch_bounds__(128) w_combine_kernel(const __grid_constant__ 
         }
         w_write_pixel(P, k.slots[ids[0]].pixel, R);
     }
+}
+
+// last kernel of a BLEND level: the next level traces the continuation rays SHADE listed, its hit slots start behind all slots so far
+__global__ void w_next_level_kernel(const __grid_constant__ WK k, cudaGraphConditionalHandle cond)
+{
+    WCounters* c = k.counters;
+    c->n_items = c->ncont;
+    c->level_start = min(c->nslots, k.cap_slots);
+    c->ncont = 0u;
+    c->level += 1u;
+    cudaGraphSetConditional(cond, (c->n_items != 0u && c->level < W_MAX_TRACE_DEPTH) ? 1u : 0u);
+}
+
+struct WLoopCache {   // the instantiated level loop of the last BLEND launch shape (one per context)
+    WK key;
+    unsigned grids[3] = {0, 0, 0};
+    LoopGraph* loop = nullptr;
+};
+void whitted_release(b200rt_context ctx)
+{
+    if (!ctx->w_loop) return;
+    delete ctx->w_loop->loop;
+    delete ctx->w_loop;
+    ctx->w_loop = nullptr;
 }
 
 // ---- host --------------------------------------------------------------------------------------------------------------------------
@@ -685,6 +728,7 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     ws_acquire(ctx, s);
     char* W = (char*)ctx->ws.ptr;
     WK k;
+    memset(&k, 0, sizeof(k));  // compared byte-wise with the cached loop's key
     k.params = (const WParams*)d_params;
     k.width = width; k.height = height; k.nl_cap = nl; k.level = 0; k.level_start = 0; k.cap_slots = (uint32_t)cap;
     k.hg_base = (const char*)sbt->hitgroupRecordBase; k.hg_stride = sbt->hitgroupRecordStrideInBytes; k.hg_count = sbt->hitgroupRecordCount;
@@ -698,35 +742,47 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     k.arrived = (unsigned int*)(W + o_arr);
     k.async_flags = flags;
     unsigned int* cursors = (unsigned int*)(W + o_cnt + 64);  // two per level
-    B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters + all work-item cursors of the frame
-    WCounters* h_cnt = (WCounters*)((char*)ctx->pinned + 512);
+    B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters, loop state and all work-item cursors of the frame
+    k.fetch = cursors;
     w_raygen_kernel<<<div_up(npix, 256), 256, 0, s>>>(k, npix);
     B2_LAUNCH_CHECK(ctx);
-    uint32_t n_items = npix, level_start = 0;  // level 0: an upper bound (grid sizing); the kernels read the live counts
-    for (uint32_t level = 0; level < W_MAX_TRACE_DEPTH; ++level) {
-        k.level = level;
-        k.level_start = level_start;
-        k.fetch = cursors + 2 * level;
-        w_primary_kernel<false><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+    const unsigned g_primary = w_persistent_grid(ctx, k_primary, npix), g_shadow = w_persistent_grid(ctx, k_shadow, (uint64_t)npix * nlp);
+    const unsigned g_shade = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 16));
+    if (!blend) {
+        w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
         B2_LAUNCH_CHECK(ctx);
-        w_primary_kernel<true><<<w_persistent_grid(ctx, k_primary, n_items), COOP_BLOCK, 0, s>>>(k, n_items);
+        w_primary_kernel<true><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
         B2_LAUNCH_CHECK(ctx);
-        const unsigned shade_grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n_items, 128), (uint64_t)ctx->sm_count * 16));
-        w_shade_kernel<<<shade_grid, 128, 0, s>>>(k);
+        w_shade_kernel<<<g_shade, 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
-        k.fetch = cursors + 2 * level + 1;
-        w_shadow_kernel<false><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
+        w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
-        w_shadow_kernel<true><<<w_persistent_grid(ctx, k_shadow, (uint64_t)n_items * nlp), COOP_BLOCK, 0, s>>>(k);
+        w_shadow_kernel<true><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
-        if (!blend) break;
-        // BLEND scenes: how many continuations did this level start?  (the only host synchronisation of a whitted launch)
-        B2_CUDA(ctx, cudaMemcpyAsync(h_cnt, k.counters, sizeof(WCounters), cudaMemcpyDeviceToHost, s));
-        B2_CUDA(ctx, cudaStreamSynchronize(s));
-        if (h_cnt->ncont == 0 || level + 1 == W_MAX_TRACE_DEPTH) break;
-        n_items = h_cnt->ncont;
-        level_start = std::min<uint32_t>(h_cnt->nslots, (uint32_t)cap);
-        B2_CUDA(ctx, cudaMemsetAsync(&k.counters->ncont, 0, sizeof(unsigned int), s));
+    } else {
+        // BLEND scenes: how many continuation rays a level starts is known on the device only, so the levels run as a device-side loop
+        // (CUDA graph, conditional WHILE: loop_graph.h) — no host read-back, the launch stays asynchronous.  The loop is instantiated
+        // once per launch shape and relaunched every subframe.
+        if (!ctx->w_loop) ctx->w_loop = new WLoopCache();
+        WLoopCache& lc = *ctx->w_loop;
+        if (!lc.loop || memcmp(&lc.key, &k, sizeof(WK)) || lc.grids[0] != g_primary || lc.grids[1] != g_shade || lc.grids[2] != g_shadow) {
+            if (lc.loop) { park_loop(ctx, lc.loop); lc.loop = nullptr; }   // may still be running: destroyed once it has finished
+            retire_loops(ctx, false);
+            LoopGraph* g = new LoopGraph(ctx);
+            lc.loop = g;
+            memcpy(&lc.key, &k, sizeof(WK));
+            lc.grids[0] = g_primary; lc.grids[1] = g_shade; lc.grids[2] = g_shadow;
+            uint32_t n0 = npix;
+            if ((rc = g->begin())) return rc;
+            if ((rc = g->add((const void*)w_primary_kernel<false>, g_primary, COOP_BLOCK, 0, k, n0))) return rc;
+            if ((rc = g->add((const void*)w_primary_kernel<true>, g_primary, COOP_BLOCK, 0, k, n0))) return rc;
+            if ((rc = g->add((const void*)w_shade_kernel, g_shade, 128, 0, k))) return rc;
+            if ((rc = g->add((const void*)w_shadow_kernel<false>, g_shadow, COOP_BLOCK, 0, k))) return rc;
+            if ((rc = g->add((const void*)w_shadow_kernel<true>, g_shadow, COOP_BLOCK, 0, k))) return rc;
+            if ((rc = g->add((const void*)w_next_level_kernel, 1, 1, 0, k, g->cond()))) return rc;
+        }
+        if ((rc = lc.loop->launch(s))) return rc;
+        ctx->launches += 1;
     }
     if (blend) {
         w_combine_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 8)), 128, 0, s>>>(k);

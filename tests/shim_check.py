@@ -30,7 +30,7 @@ def same(a, b, what):
 # optixPathTracer and optixMultiGPU programs
 for mg in (None, (0, 1)):
     b, s = host.PathTracer(bctx, 96, 64, 4, multigpu=mg), host.PathTracer(sctx, 96, 64, 4, multigpu=mg)
-    b.sample_groups = 4   # what optixLaunch on the shim uses unless B200RT_SAMPLE_GROUPS says otherwise
+    b.sample_groups = 1   # what optixLaunch on the shim uses unless B200RT_SAMPLE_GROUPS says otherwise: the reference's summation order
     for sub in range(2):
         b.launch_subframe(sub)
         s.launch_subframe(sub)

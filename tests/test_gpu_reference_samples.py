@@ -106,7 +106,7 @@ def test_optixRaycasting_binary_on_the_shim(optix, tmp_path, model):
     _need("optixRaycasting")
     if not (REF / "SDK" / "data" / model).exists():
         pytest.skip(f"{model} not in baseline/_ref/SDK/data")
-    pics = _both("optixRaycasting", lambda d: ["-f", str(d / "out"), "-m", model, "-w", "800"], tmp_path, ["out.ppm", "out_translated.ppm"])
+    pics = _both("optixRaycasting", lambda d: ["-f", str(d / "out"), "-m", str(REF / "SDK" / "data" / model), "-w", "800"], tmp_path, ["out.ppm", "out_translated.ppm"])
     for a, b in zip(pics[False], pics[True]):
         assert a.shape == b.shape and (a != a[0, 0]).any()
         # Hit.t is truncated to an integer and shaded by the interpolated normal: identical up to the normal's last bits
@@ -119,7 +119,7 @@ def test_optixMeshViewer_binary_on_the_shim(optix, tmp_path, model):
     _need("optixMeshViewer")
     if not (REF / "SDK" / "data" / model).exists():
         pytest.skip(f"{model} not in baseline/_ref/SDK/data")
-    pics = _both("optixMeshViewer", lambda d: ["--file", str(d / "out.ppm"), "--no-gl-interop", "--model", model, "--dim=640x480"], tmp_path, ["out.ppm"])
+    pics = _both("optixMeshViewer", lambda d: ["--file", str(d / "out.ppm"), "--no-gl-interop", "--model", str(REF / "SDK" / "data" / model), "--dim=640x480"], tmp_path, ["out.ppm"])
     a, b = pics[False][0], pics[True][0]
     assert a.shape == (480, 640, 3) and a.std() > 5
     assert _psnr(a, b) > 40, _psnr(a, b)
@@ -149,22 +149,23 @@ def test_load_gltf_matches_sutil_loadScene(tmp_path, model):
     got = host.load_gltf(path)
     assert len(got["meshes"]) == len(ref["meshes"]) and len(got["instances"]) == len(ref["instances"])
     f32 = lambda v, n: np.asarray(v, np.float32).reshape(-1, n)
+    bits = lambda v, n: np.asarray(v, np.uint32).view(np.float32).reshape(-1, n)  # vertex attributes are dumped as fp32 bit patterns
     for gm, rm in zip(got["meshes"], ref["meshes"]):
         assert len(gm["primitives"]) == len(rm["primitives"])
         assert np.array_equal(np.concatenate(gm["aabb"]).astype(np.float32), np.asarray(rm["aabb"], np.float32))
         for gp, rp in zip(gm["primitives"], rm["primitives"]):
-            assert np.array_equal(gp["positions"].view(np.uint32), f32(rp["positions"], 3).view(np.uint32))
+            assert np.array_equal(gp["positions"].view(np.uint32), bits(rp["positions"], 3).view(np.uint32))
             if rp["normals"]:
-                assert np.array_equal(gp["normals"].view(np.uint32), f32(rp["normals"], 3).view(np.uint32))
+                assert np.array_equal(gp["normals"].view(np.uint32), bits(rp["normals"], 3).view(np.uint32))
             else:
                 assert gp["normals"] is None
             for k, key in enumerate(("texcoords0", "texcoords1")):
                 if rp[key]:
-                    assert np.array_equal(gp["texcoords"][k].view(np.uint32), f32(rp[key], 2).view(np.uint32))
+                    assert np.array_equal(gp["texcoords"][k].view(np.uint32), bits(rp[key], 2).view(np.uint32))
                 else:
                     assert gp["texcoords"][k] is None
             if rp["colors"]:
-                assert np.array_equal(gp["colors"].view(np.uint32), f32(rp["colors"], 4).view(np.uint32))
+                assert np.array_equal(gp["colors"].view(np.uint32), bits(rp["colors"], 4).view(np.uint32))
             else:
                 assert gp.get("colors") is None
             assert np.array_equal(np.asarray(gp["indices"], np.uint32), np.asarray(rp["indices"], np.uint32))
