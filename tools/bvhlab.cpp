@@ -251,6 +251,53 @@ static void build_ploc(const Mesh& m, BinTree& t, int R)
     t.root = cl[0];
 }
 
+
+// Bottom-up tree rotations (Kensler 2008) as a SAH refit of a finished binary hierarchy: in post-order, every internal node considers
+// exchanging one child with a grandchild on the other side (four candidates) and takes the one that shrinks the changed child's surface
+// area the most.  The thread that finishes a node owns the whole subtree below it, so the GPU form is the refit kernel's second-arrival
+// walk with this step added (no further synchronisation).
+static int rotate_pass(BinTree& t)
+{
+    const int ni = t.n - 1;
+    std::vector<int> st{t.root}, order;
+    while (!st.empty()) { int x = st.back(); st.pop_back(); if (x >= ni) continue; order.push_back(x); st.push_back(t.left[x]); st.push_back(t.right[x]); }
+    auto cnt = [&](int id) { return id >= ni ? 1 : t.count[id]; };
+    int done = 0;
+    for (size_t k = order.size(); k-- > 0;) {
+        const int x = order[k];
+        int L = t.left[x], R = t.right[x];
+        float best = 0.f; int which = -1;
+        auto unite = [&](int a, int b) { Box u = t.box[a]; u.grow(t.box[b]); return u.area(); };
+        if (L < ni) {
+            const float aL = t.box[L].area();
+            const float c0 = unite(R, t.right[L]) - aL;   // R <-> LL : L' = (R, LR)
+            const float c1 = unite(t.left[L], R) - aL;    // R <-> LR : L' = (LL, R)
+            if (c0 < best) { best = c0; which = 0; }
+            if (c1 < best) { best = c1; which = 1; }
+        }
+        if (R < ni) {
+            const float aR = t.box[R].area();
+            const float c2 = unite(L, t.right[R]) - aR;   // L <-> RL : R' = (L, RR)
+            const float c3 = unite(t.left[R], L) - aR;    // L <-> RR : R' = (RL, L)
+            if (c2 < best) { best = c2; which = 2; }
+            if (c3 < best) { best = c3; which = 3; }
+        }
+        if (which >= 0) {
+            ++done;
+            if (which == 0) { const int g = t.left[L]; t.left[L] = R; t.right[x] = g; }
+            else if (which == 1) { const int g = t.right[L]; t.right[L] = R; t.right[x] = g; }
+            else if (which == 2) { const int g = t.left[R]; t.left[R] = L; t.left[x] = g; }
+            else { const int g = t.right[R]; t.right[R] = L; t.left[x] = g; }
+            const int c = which < 2 ? L : R;
+            Box b = t.box[t.left[c]]; b.grow(t.box[t.right[c]]);
+            t.box[c] = b; t.count[c] = cnt(t.left[c]) + cnt(t.right[c]);
+        }
+        Box b = t.box[t.left[x]]; b.grow(t.box[t.right[x]]);
+        t.box[x] = b; t.count[x] = cnt(t.left[x]) + cnt(t.right[x]);
+    }
+    return done;
+}
+
 // ---- 8-wide collapse ----------------------------------------------------------------------------------------------------------------
 struct WNode {
     int nchild = 0;
@@ -501,6 +548,7 @@ int main(int argc, char** argv)
     uint64_t T = 2000000;
     std::string hier = "lbvh";
     CollapseOpt co;
+    int rotate = 0;
     int W = 320, H = 180, ploc_r = 16, threads = (int)std::thread::hardware_concurrency();
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -512,6 +560,7 @@ int main(int argc, char** argv)
         else if (a == "--ctri") co.ctri = (float)atof(next().c_str());
         else if (a == "--leaf") co.leaf = atoi(next().c_str());
         else if (a == "--noquant") co.quant = false;
+        else if (a == "--rotate") rotate = atoi(next().c_str());
         else if (a == "--ploc-radius") ploc_r = atoi(next().c_str());
         else if (a == "--res") { std::string r = next(); sscanf(r.c_str(), "%dx%d", &W, &H); }
         else if (a == "--threads") threads = atoi(next().c_str());
@@ -528,6 +577,7 @@ int main(int argc, char** argv)
     else if (hier == "sah") build_sah(m, bt);
     else if (hier == "ploc") build_ploc(m, bt, ploc_r);
     else { fprintf(stderr, "unknown --hier\n"); return 1; }
+    for (int r = 0; r < rotate; ++r) { const int d = rotate_pass(bt); fprintf(stderr, "rotate pass %d: %d rotations\n", r, d); }
     auto t2 = now();
     Wide w;
     collapse(bt, w, co);
