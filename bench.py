@@ -33,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 PT_WORKLOADS = ("synthetic", "cornell")
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -55,7 +55,17 @@ def parse():
                          "auto = optix when it can be initialised")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the cpu_baseline sample")
-    return ap.parse_args()
+    a = ap.parse_args(argv)
+    if a.width is None:
+        a.width, a.height = {"synthetic": (3840, 2160), "cornell": (768, 768), "duck_raycast": (1040, None), "whitted_duck": (1920, 1080),
+                             "playground": (1920, 1080)}[a.workload]
+    if a.spl is None:
+        a.spl = {"synthetic": 16, "cornell": 16, "duck_raycast": 1, "whitted_duck": 1, "playground": 8}[a.workload]
+    if a.ray_sort is None:
+        a.ray_sort = 0
+    if a.sample_groups is None:
+        a.sample_groups = 8 if a.workload == "synthetic" else 4   # measured best on one B200 (gpurun_out/sg_*.json); any value gives the same image on any N
+    return a
 
 
 def workload_name(a):
@@ -466,6 +476,7 @@ def run_gpu(a, rank, world, local_rank, impl):
 
     # ---- e2e: same steps through the public call with host buffers (Params H2D from pinned memory is part of
     # launch_subframe; the frame comes back to pinned host memory every step)
+    step(a.warmup + 2 * a.steps, want_host_frame=True)  # untimed: the first copy into the pinned frame buffer pays its one-time mapping cost
     barrier()
     evs = []
     for sub in e2e_subs:
@@ -478,6 +489,8 @@ def run_gpu(a, rank, world, local_rank, impl):
         evs.append((s0, s1))
     barrier()
     e2e_ms = sum(s0.elapsed_time(s1) for s0, s1 in evs)
+    if os.environ.get("B200RT_BENCH_DEBUG"):
+        print("[bench debug] e2e per step (ms): " + " ".join(f"{s0.elapsed_time(s1):.3f}" for s0, s1 in evs), file=sys.stderr)
     e2e_rays = sum(job.rays(sub) for sub in e2e_subs)
 
     def allmax(x):
@@ -610,15 +623,6 @@ def raycast_roofline(job, ctx, ms_per_step, hbm_peak, peak_src):
 
 def main():
     a = parse()
-    if a.width is None:
-        a.width, a.height = {"synthetic": (3840, 2160), "cornell": (768, 768), "duck_raycast": (1040, None), "whitted_duck": (1920, 1080),
-                             "playground": (1920, 1080)}[a.workload]
-    if a.spl is None:
-        a.spl = {"synthetic": 16, "cornell": 16, "duck_raycast": 1, "whitted_duck": 1, "playground": 8}[a.workload]
-    if a.ray_sort is None:
-        a.ray_sort = 0
-    if a.sample_groups is None:
-        a.sample_groups = 8 if a.workload == "synthetic" else 4   # measured best on one B200 (gpurun_out/sg_*.json); any value gives the same image on any N
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -71,6 +71,10 @@ extern "C" {
 #define B200RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES (1u << 5)
 #define B200RT_RAY_FLAG_CULL_DISABLED_ANYHIT (1u << 6)
 #define B200RT_RAY_FLAG_CULL_ENFORCED_ANYHIT (1u << 7)
+/* optixTrace's visibilityMask argument (8 bits, include/optix_types.h OptixVisibilityMask; SDK/imgui_test/optixTriangle.cu traces with 255,
+ * optixPathTracer.cu:181,209 and optixRaycasting.cu with 1): OR it into a ray_flags word with this macro.  An instance is traversed when
+ * (OptixInstance::visibilityMask & ray mask) != 0.  The field is stored XOR 1, so a flags word without it means mask 1. */
+#define B200RT_RAY_VISIBILITY_MASK(m) (((((unsigned int)(m)) ^ 1u) & 0xffu) << 16)
 /* instance flags (b200rt_instance.flags), reference include/optix_types.h:1088-1115 */
 #define B200RT_INSTANCE_FLAG_NONE 0u
 #define B200RT_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING (1u << 0)

@@ -76,6 +76,11 @@ struct ExtHit { float t; uint32_t prim; uint32_t inst; float b1; float b2; };
 // 0 = the triangle's own OPTIX_GEOMETRY_FLAG_DISABLE_ANYHIT decides.  Precedence as documented in include/optix_types.h:1088-1108 and
 // 1794-1806: ray flags over instance flags over geometry flags.  OPTIX_INSTANCE_FLAG_DISABLE_TRIANGLE_FACE_CULLING drops the two
 // face-cull bits, OPTIX_INSTANCE_FLAG_FLIP_TRIANGLE_FACING swaps them.  Same function in oracle.cpp (cull_word).
+// The ray's 8-bit OptixVisibilityMask (include/optix_types.h OptixVisibilityMask; optixTrace's visibilityMask argument) travels in bits
+// 16-23 of the ray-flags word, stored XOR 1 so that a flags word without the field means mask 1 — what optixPathTracer, optixRaycasting
+// and whitted trace with (B200RT_RAY_VISIBILITY_MASK in b200rt.h).  An instance is traversed when (instance mask & ray mask) != 0.
+__host__ __device__ __forceinline__ uint32_t ray_visibility(uint32_t ray_flags) { return ((ray_flags >> 16) ^ 1u) & 0xffu; }
+
 __host__ __device__ __forceinline__ uint32_t cull_word(uint32_t ray_flags, uint32_t inst_flags)
 {
     uint32_t c = ray_flags & 0xf0u;

@@ -828,6 +828,16 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
     }
 }
 
+// B200RT_BUILD_TIMING=2: a one-thread kernel between the kernels of the collapse loop's body adds the time since the previous stamp to
+// acc[1 + k] (nanoseconds of %globaltimer); acc[0] is the previous stamp.  Debug aid: the kernels of a WHILE body cannot be bracketed by events.
+__global__ void stamp_kernel(unsigned long long* acc, int k)
+{
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (k >= 0) acc[1 + k] += now - acc[0];
+    acc[0] = now;
+}
+
 __global__ void collapse_advance_kernel(CollapseState* st, uint32_t max_nodes, cudaGraphConditionalHandle cond)
 {
     const unsigned long long tot = st->total;
@@ -1169,6 +1179,7 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     // bits per axis of the Morton key = radix passes of the sort (8 bits each): 30 / 48 / 54 / 63 bits -> 4 / 6 / 7 / 8 passes.  2^18 cells
     // per axis separate the centroids of 10^8 triangles as well as 2^21 do; the eighth pass is for inputs beyond that.
     p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 22) ? 16 : (n < (1u << 27) ? 18 : 21));
+    if (const char* e = getenv("B200RT_MORTON_BITS")) p.morton_bits = std::min(std::max(atoi(e), 4), 21);  // A/B runs
     const size_t N = std::max<size_t>(n, 1);
     const size_t W = N / 4 + 2;  // widest possible level (every wide node roots >= 4 triangles)
     size_t off = 0;
@@ -1393,18 +1404,36 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             collapse_init_kernel<<<1, 1, 0, s>>>(d_cst, work[0], 0u, cl[0], cl[1], ploc ? d_ploc : nullptr);  // radix tree: internal node 0, or leaf 0 when N == 1
             B2_LAUNCH_CHECK(ctx);
             // ---- collapse, level by level
+            static const bool body_timing = [] { const char* e = getenv("B200RT_BUILD_TIMING"); return e && atoi(e) >= 2; }();
+            unsigned long long* d_stamps = nullptr;
+            if (body_timing) {
+                cudaMalloc(&d_stamps, 8 * sizeof(unsigned long long));
+                cudaMemsetAsync(d_stamps, 0, 8 * sizeof(unsigned long long), s);
+                stamp_kernel<<<1, 1, 0, s>>>(d_stamps, -1);
+            }
             {
                 LoopGraph& g = *new LoopGraph(ctx);
                 park_loop(ctx, &g);
                 if ((rc = g.begin())) return rc;
                 if ((rc = g.add((const void*)collapse_plan_kernel, wide_grid, 128, 0, (const CollapseState*)d_cst, (const uint32_t*)work[0], (const uint32_t*)work[1], (int)N,
                                 (const float4*)box_lo, (const float4*)box_hi, (const int2*)range, (const uint8_t*)height, child_tmp, counts, max_wide_depth()))) return rc;
+                if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 0))) return rc;
                 if ((rc = dscan_add<unsigned long long>(g, counts, &d_cst->nwork, dsums, &d_cst->total))) return rc;
+                if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 1))) return rc;
                 if ((rc = g.add((const void*)collapse_emit_kernel, wide_grid, 128, 0, d_cst, p.max_nodes, (int)N, (const float4*)box_lo, (const float4*)box_hi,
                                 (const int2*)range, (const int*)child_tmp, (const unsigned long long*)counts, work[0], work[1], dest, nodes_out, p.node_bytes))) return rc;
+                if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 2))) return rc;
                 if ((rc = g.add((const void*)collapse_advance_kernel, 1, 1, 0, d_cst, p.max_nodes, g.cond()))) return rc;
+                if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 3))) return rc;
                 if ((rc = g.launch(s))) return rc;
                 ctx->launches += 1;
+            }
+            if (body_timing) {
+                unsigned long long h[8];
+                cudaMemcpy(h, d_stamps, sizeof(h), cudaMemcpyDeviceToHost);
+                cudaFree(d_stamps);
+                fprintf(stderr, "[b200rt build] collapse body: plan %.3f ms, scan %.3f ms, emit %.3f ms, advance + loop %.3f ms\n", h[1] * 1e-6, h[2] * 1e-6, h[3] * 1e-6,
+                        h[4] * 1e-6);
             }
             mark();  // collapse
             // triangles go right after the node capacity region; compaction later closes the gap

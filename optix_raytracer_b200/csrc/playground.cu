@@ -421,7 +421,7 @@ int launch_playground(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_par
         B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(PGCounters), s));
         pg_raygen_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, smp, nlanes, rays, cand, payload, cnt, hp.samples_per_frame, hp.nlights, flags);
         B2_LAUNCH_CHECK(ctx);
-        rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)rays, nlanes, &cnt->ncand, 1, 0, 0u, (b200rt_deviceptr)hits, 0, 0, handle_dev);
+        rc = trace_buffer(ctx, s, 0, (b200rt_deviceptr)rays, nlanes, &cnt->ncand, 1, 0, B200RT_RAY_VISIBILITY_MASK(255) /* optixTriangle.cu:130 */, (b200rt_deviceptr)hits, 0, 0, handle_dev);
         if (rc) return rc;
         pg_shade_kernel<<<lgrid, 256, 0, s>>>(dp, width, height, nlanes, rays, cand, hits, payload, probes, ndw, info, cnt, hp.nlights);
         B2_LAUNCH_CHECK(ctx);

@@ -93,8 +93,8 @@ struct RayWork {
 
     __device__ __forceinline__ uint32_t cull_flags(uint32_t i) const
     {
-        const uint32_t f = ray_flags & 0xf3u;  // CULL_* and DISABLE / ENFORCE_ANYHIT (traverse.cuh: cull_word)
-        return (flag_period && (i % flag_period) == flag_period - 1u) ? (f & 0x33u) : f;
+        const uint32_t f = ray_flags & 0xff00f3u;  // CULL_* and DISABLE / ENFORCE_ANYHIT (accel.h: cull_word), visibility mask (ray_visibility)
+        return (flag_period && (i % flag_period) == flag_period - 1u) ? (f & 0xff0033u) : f;
     }
     __device__ __forceinline__ bool anyhit(uint32_t prim, uint32_t sbt, uint32_t inst, uint32_t pack, float b1, float b2, float& factor) const
     {

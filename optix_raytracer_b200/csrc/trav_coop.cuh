@@ -301,7 +301,7 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
     const uint32_t n = h->num_instances;
     for (uint32_t k = first_inst; k < n; ++k) {
         const InstanceRecord* ir = recs + k;
-        if (!(ir->mask & 1u)) continue;
+        if (!(ir->mask & ray_visibility(cull))) continue;
         s.inst = k;
         const uint32_t c = cull_word(cull, ir->flags);  // the instance's face-culling / facing / any-hit flags
         // instances are tested at their bounds always: with several of them a ray passes most of them by

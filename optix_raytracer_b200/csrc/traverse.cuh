@@ -290,7 +290,7 @@ __device__ __forceinline__ bool trace_handle(const AccelHeader* __restrict__ h, 
     const uint32_t n = h->num_instances;
     for (uint32_t k = 0; k < n; ++k) {
         const InstanceRecord* ir = recs + k;
-        if (!(ir->mask & 1u)) continue;
+        if (!(ir->mask & ray_visibility(ray_flags))) continue;
         const float3 oo = xform_point(ir->inv, o), dd = xform_vec(ir->inv, d);
         RayHit cand = hit;
         const uint32_t c = cull_word(ray_flags, ir->flags);

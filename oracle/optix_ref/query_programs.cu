@@ -33,12 +33,12 @@ extern "C" __global__ void __raygen__query()
     unsigned int p0 = 0xbf800000u /* t = -1 */, p1 = 0xffffffffu, p2 = 0xffffffffu, p3 = 0u, p4 = 0u;
     if (params.any_hit) {
         p0 = 0u;
-        optixTrace(params.handle, make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), a.w, b.w, 0.0f, OptixVisibilityMask(1),
-                   params.ray_flags | OPTIX_RAY_FLAG_TERMINATE_ON_FIRST_HIT | OPTIX_RAY_FLAG_DISABLE_ANYHIT, 0, 0, 0, p0, p1, p2, p3, p4);
+        optixTrace(params.handle, make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), a.w, b.w, 0.0f, OptixVisibilityMask(((params.ray_flags >> 16) ^ 1u) & 0xffu),
+                   (params.ray_flags & 0xffffu) | OPTIX_RAY_FLAG_TERMINATE_ON_FIRST_HIT | OPTIX_RAY_FLAG_DISABLE_ANYHIT, 0, 0, 0, p0, p1, p2, p3, p4);
         params.out[i] = p0;
     } else {
-        optixTrace(params.handle, make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), a.w, b.w, 0.0f, OptixVisibilityMask(1),
-                   params.ray_flags | OPTIX_RAY_FLAG_DISABLE_ANYHIT, 0, 0, 0, p0, p1, p2, p3, p4);
+        optixTrace(params.handle, make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), a.w, b.w, 0.0f, OptixVisibilityMask(((params.ray_flags >> 16) ^ 1u) & 0xffu),
+                   (params.ray_flags & 0xffffu) | OPTIX_RAY_FLAG_DISABLE_ANYHIT, 0, 0, 0, p0, p1, p2, p3, p4);
         unsigned int* o = params.out + 5 * i;
         o[0] = p0; o[1] = p1; o[2] = p2; o[3] = p3; o[4] = p4;
     }

@@ -430,7 +430,7 @@ static SceneHit trace_scene(Scene& s, f3 o, f3 d, float tmin, float tmax, uint32
     }
     for (uint32_t k = 0; k < s.insts.size(); ++k) {
         const Instance& in = s.insts[k];
-        if (!(in.mask & 1u)) continue;  // every ray on the path is traced with OptixVisibilityMask(1) or (255): bit 0 decides
+        if (!(in.mask & ((ray_flags >> 16 ^ 1u) & 0xffu))) continue;  // OptixVisibilityMask of the ray in bits 16-23 of the flags word, stored XOR 1 (absent = mask 1)
         HitRec b{r.t, 0, 0, 0, 0};
         // a later instance only wins with strictly smaller t (lower instance index wins ties)
         if (trace_geom<ANY, STATS>(s.geoms[in.geom], xform_point(in.inv, o), xform_vec(in.inv, d), tmin, b, cull_word(ray_flags, in.flags))) {
@@ -1020,7 +1020,7 @@ uint64_t orc_playground(void* scene, const void* camera92, const void* lights44,
                     org = mk(fm(ly, cv.x, fm(lx, cu.x, eye.x)), fm(ly, cv.y, fm(lx, cu.y, eye.y)), fm(ly, cv.z, fm(lx, cu.z, eye.z)));
                 }
                 ++nrays[(size_t)tid];
-                const SceneHit h = trace_scene<false>(*s, org, dir, 0.0f, 1e16f, 0u);
+                const SceneHit h = trace_scene<false>(*s, org, dir, 0.0f, 1e16f, (255u ^ 1u) << 16 /* OptixVisibilityMask(255), optixTriangle.cu:130 */);
                 if (!h.hit) {
                     result = result + mk(fm(dir.x, 0.5f, 0.5f), fm(dir.y, 0.5f, 0.5f), fm(dir.z, 0.5f, 0.5f));
                     continue;

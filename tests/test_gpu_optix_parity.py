@@ -74,8 +74,9 @@ def test_duck_raycasting_matches_the_reference_programs_on_optix(ctxs):
     bctx, octx = ctxs
     sc = common.duck_scene()
     b, o = host.Raycaster(bctx, sc), host.Raycaster(octx, sc)
-    b.buffer_rays(640)
-    o.buffer_rays(640)
+    # BASELINE.json configs[1] at full size: the sample's default width gives two batches of 1 006 720 rays
+    assert b.buffer_rays(1040) > 1_000_000
+    o.buffer_rays(1040)
     b.launch()
     o.launch(want_ext=False)
     torch.cuda.synchronize()
@@ -99,7 +100,7 @@ def test_alpha_mask_raycasting_matches_the_reference_anyhit_on_optix(ctxs):
     b, o = host.Raycaster(bctx, sc), host.Raycaster(octx, sc)
     opaque = host.Raycaster(bctx, common.duck_scene())
     for r in (b, o, opaque):
-        r.buffer_rays(640)
+        r.buffer_rays(1040)
     b.launch()
     o.launch(want_ext=False)
     opaque.launch()
@@ -123,7 +124,8 @@ def test_cornell_image_matches_optix_at_the_same_seeds(ctxs, mode):
     from optix_raytracer_b200 import host
     bctx, octx = ctxs
     mg = (0, 1) if mode else None
-    b, o = host.PathTracer(bctx, 256, 256, 16, multigpu=mg), host.PathTracer(octx, 256, 256, 16, multigpu=mg)
+    # BASELINE.json configs[0] at full size: 768 x 768, 16 samples per launch
+    b, o = host.PathTracer(bctx, 768, 768, 16, multigpu=mg), host.PathTracer(octx, 768, 768, 16, multigpu=mg)
     for sub in range(2):
         b.launch_subframe(sub)
         o.launch_subframe(sub)
@@ -262,3 +264,17 @@ def test_face_culling_and_instance_flags_match_optix(ctxs):
             counts[(rf, is_ias)] = int(ho.sum())
     for is_ias in (False, True):
         assert 0 < counts[(16, is_ias)] < counts[(0, is_ias)] and 0 < counts[(32, is_ias)] < counts[(0, is_ias)]
+    # optixTrace's 8-bit visibility mask against OptixInstance::visibilityMask (B200RT_RAY_VISIBILITY_MASK: bits 16-23, XOR 1)
+    masks2 = [1, 2, 6, 255]
+    ias2 = [ctx.build_accel([ctx.instance_input([(m, 0, acc[0], k, f) for m, f, k in zip(xfs, iflags, masks2)])], compact=False) for ctx, acc in zip((bctx, octx), accels)]
+    for vis in (1, 2, 4, 255, 0):
+        rf = ((vis ^ 1) & 0xff) << 16
+        got = host.ext_hits_to_numpy(bctx.trace_closest(ias2[0], d, ray_flags=rf | 1))
+        ref = host.ext_hits_to_numpy(octx.trace_closest(ias2[1], d, ray_flags=rf, is_ias=True))
+        hb, ho = got["t"] >= 0, ref["t"] >= 0
+        assert (hb != ho).mean() < 2e-4, f"visibility mask {vis}: {(hb != ho).sum()} rays disagree on hit / miss"
+        both = hb & ho
+        assert both.any() == bool(vis)
+        if vis:
+            assert (got["inst"][both] != ref["inst"][both]).mean() < 2e-4 and (got["prim"][both] != ref["prim"][both]).mean() < 2e-4
+        assert set(np.unique(ref["inst"][ho]).tolist()) == {k for k, m in enumerate(masks2) if m & vis}, f"visibility mask {vis}: instances OptiX reports"

@@ -262,6 +262,18 @@ def test_ray_and_instance_flags_vs_oracle(ctx, orc):
             occ = ctx.trace_any(accel, d_rays_any, ray_flags=rf | 4).cpu().numpy().astype(bool)
             assert np.array_equal(occ, scene.trace(rays_any, any_hit=True, ray_flags=rf)["occluded"]), f"{what} occlusion, ray_flags {rf:#x}"
             seen.add((what, rf, int((ref["t"] >= 0).sum())))
+    # the ray's 8-bit visibility mask (bits 16-23 of the flags word, XOR 1): instance k is traversed when (its mask & the ray's) != 0
+    masks2 = [1, 2, 4, 3, 6, 255, 0]
+    ias2 = ctx.build_accel([ctx.instance_input([(m, 0, gas, k, f) for m, f, k in zip(xfs, iflags, masks2)])], compact=False)
+    scene_ias2 = orc.Scene(tris, sbt, instances=[(m, f, k) for m, f, k in zip(xfs, iflags, masks2)], geom_flags=tri_flags)
+    for vis in (1, 2, 4, 6, 8, 255, 0):
+        rf = ((vis ^ 1) & 0xff) << 16
+        ref = scene_ias2.trace(rays, ray_flags=rf)
+        _assert_hits_equal(host.ext_hits_to_numpy(ctx.trace_closest(ias2, d_rays, ray_flags=rf)), ref, f"ray visibility mask {vis}")
+        occ = ctx.trace_any(ias2, d_rays_any, ray_flags=rf | 4).cpu().numpy().astype(bool)
+        assert np.array_equal(occ, scene_ias2.trace(rays_any, any_hit=True, ray_flags=rf)["occluded"]), f"occlusion, ray visibility mask {vis}"
+        visible = {k for k, m in enumerate(masks2) if m & vis}
+        assert set(np.unique(ref["inst"][ref["t"] >= 0]).tolist()) == visible, f"ray visibility mask {vis}: instances hit"
     # the flags do something: the hit counts differ between the settings, and the invisible instance is never reported
     assert len({c for w, rf, c in seen if w == "ias"}) >= 6
     assert not np.any(scene_ias.trace(rays)["inst"][scene_ias.trace(rays)["t"] >= 0] == 6)

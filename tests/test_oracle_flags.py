@@ -75,6 +75,24 @@ def test_per_triangle_geometry_flags_and_mask():
     assert not hit(orc.Scene(TRI, None, instances=[(IDENT, 0, 0)]), FROM_FRONT, 0)
 
 
+def test_ray_visibility_mask():
+    """optixTrace's 8-bit visibilityMask against OptixInstance::visibilityMask: an instance is traversed when the two share a bit
+    (reference include/optix_types.h OptixVisibilityMask; SDK/imgui_test/optixTriangle.cu:130 traces with 255, the other samples with 1).
+    include/b200rt.h carries the ray's mask in bits 16-23 of the flags word, XOR 1, so that a word without the field means mask 1."""
+    vis = lambda m: ((m ^ 1) & 0xff) << 16
+    behind = TRI + np.array([0, 0, -0.5], np.float32)
+    s = orc.Scene(np.concatenate([TRI, behind]), None, instances=[(IDENT, 0, 2), (np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, -2], np.float32), 0, 5)])
+    # instance 0 (mask 2) holds both triangles at z = 0 / -0.5; instance 1 (mask 5) the same, two units further back
+    assert s.trace(FROM_FRONT)["inst"][0] == 1 and s.trace(FROM_FRONT)["t"][0] == 3.0          # default mask 1: only instance 1
+    assert s.trace(FROM_FRONT, ray_flags=vis(1))["inst"][0] == 1
+    assert s.trace(FROM_FRONT, ray_flags=vis(2))["inst"][0] == 0 and s.trace(FROM_FRONT, ray_flags=vis(2))["t"][0] == 1.0
+    assert s.trace(FROM_FRONT, ray_flags=vis(255))["inst"][0] == 0
+    assert s.trace(FROM_FRONT, ray_flags=vis(4))["inst"][0] == 1
+    assert not hit(s, FROM_FRONT, vis(8)) and not hit(s, FROM_FRONT, vis(0))
+    # the field rides along with the other flags
+    assert not hit(s, FROM_BACK, vis(2) | R_CULL_BACK) and hit(s, FROM_BACK, vis(2))
+
+
 def test_flag_word_of_the_library_equals_the_oracles():
     """accel.h: cull_word (what the device triangle tests see) against oracle.cpp: cull_word, over every combination of the eight ray-flag
     bits and the four instance-flag bits that concern triangles — a host function of the C ABI, no GPU involved."""
