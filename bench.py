@@ -595,13 +595,15 @@ def pt_roofline(a, job, world, L, info, hbm_peak, peak_src, accel_build_ms):
             "visit_counts_source": "instrumented pt_trace_kernel on this repo's BVH8 (B200RT_PT_STATS_TRAVERSAL); the oracle-side counts on its own "
                                    "SAH tree are in profiles/ (tools/bvhlab)"}
     if accel_build_ms:
-        # B_build of SURVEY 8(d), for the variant built: gather 36 B read + 48 B write per triangle, Morton 48 + 12, `passes` radix passes of
-        # 8 B histogram read + 12 B read + 12 B write per key, leaf boxes 48 + 32, hierarchy ~100 B per internal node, nodes written once,
-        # triangle records 48 + 8 read, 48 written
+        # B_build of SURVEY 8(d), for the variant built (bvh_build.cu), per triangle: gather 36 B read + 48 B written, Morton keys 48 + 12,
+        # `passes` radix passes of 8 B histogram read + 12 B read + 12 B written, the radix tree with its boxes in one bottom-up pass (leaf:
+        # 52 read + 32 written; internal node: sibling box 32 read, own box 32 written, 24 B of exchange words, 16 B of keys), triangle
+        # records 8 + 48 read + 48 written; per wide node: the plan looks at ~14 boxes of 32 B and writes 40 B, the emit reads them (8 x 32 +
+        # 40) and writes the node
         T = int(info.num_triangles)
-        bits = 10 if T < (1 << 14) else (16 if T < (1 << 22) else (18 if T < (1 << 27) else 21))
+        bits = 10 if T < (1 << 14) else (16 if T < (1 << 27) else 21)
         passes = (3 * bits + 7) // 8
-        b_build = T * (36 + 48 + 48 + 12 + passes * 32 + 48 + 32 + 100 + 48 + 8 + 48) + int(info.num_nodes) * node_bytes
+        b_build = T * (36 + 48 + 48 + 12 + passes * 32 + 52 + 32 + 104 + 8 + 48 + 48) + int(info.num_nodes) * (14 * 32 + 40 + 8 * 32 + 40 + node_bytes)
         roof["build"] = {"bound": "hbm", "kernel": "b200rt_accel_build (all kernels of one build)", "algorithmic_bytes": b_build, "ms": accel_build_ms,
                          "achieved": b_build / (accel_build_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": b_build / (accel_build_ms * 1e-3) / 1e9 / hbm_peak, "radix_passes": passes}

@@ -532,36 +532,86 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
     return __clzll((long long)(a ^ b));
 }
 
-__global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ keys, int n, float4* __restrict__ box_lo,
-                                                      float4* __restrict__ box_hi, int* __restrict__ parent, int2* __restrict__ range)
+// Boxes of the binary hierarchy: {lo.xyz, left child} {hi.xyz, right child} of node id side by side (32 bytes, one DRAM sector), reached
+// through two strided views so that kernels keep writing box_lo[id] / box_hi[id].  Side by side because every consumer (bottom-up
+// union, clustering, collapse) wants both halves of a box it fetches by a data-dependent id: two arrays cost two sectors per box.
+struct BoxArr {
+    float4* p;
+    __device__ __forceinline__ float4& operator[](size_t i) const { return p[2 * i]; }
+};
+// The two child words also say how many leaves the node holds, as far as the collapse cares (a subtree of at most three triangles
+// becomes a leaf child, anything larger an inner child): bit 31 of lo.w = "at most three", bit 31 of hi.w = "exactly three" (else two).
+// With that the collapse never touches a second per-node array: one sector per node it looks at.
+constexpr uint32_t CHILD_ID_MASK = 0x7fffffffu;
+__device__ __forceinline__ int child_id(float w) { return (int)(__float_as_uint(w) & CHILD_ID_MASK); }
+__device__ __forceinline__ int leaves_upto4(float lo_w, float hi_w)  // 2, 3, or 4 for "more than three"
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-    const int dmin = delta(keys, n, i, i - d);
-    int lmax = 2;
-    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-    const int j = i + l * d;
-    const int dnode = delta(keys, n, i, j);
-    int s = 0;
-    int t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    const int gamma = i + s * d + min(d, 0);
-    const int first = min(i, j), last = max(i, j);
-    const int left = (first == gamma) ? (n - 1 + gamma) : gamma;
-    const int right = (last == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-    box_lo[i].w = __int_as_float(left);
-    box_hi[i].w = __int_as_float(right);
-    parent[left] = i;
-    parent[right] = i;
-    if (i == 0) parent[0] = -1;
-    range[i] = make_int2(first, last - first + 1);
+    return (__float_as_uint(lo_w) >> 31) ? 2 + (int)(__float_as_uint(hi_w) >> 31) : 4;
+}
+__device__ __forceinline__ float child_word_lo(int left, int leaves) { return __uint_as_float((uint32_t)left | (leaves <= 3 ? 0x80000000u : 0u)); }
+__device__ __forceinline__ float child_word_hi(int right, int leaves) { return __uint_as_float((uint32_t)right | (leaves == 3 ? 0x80000000u : 0u)); }
+
+// The radix tree over the sorted keys (Karras 2012: node = maximal range of leaves with a common key prefix; equal keys are told apart by
+// their position) AND its boxes in ONE bottom-up pass (Apetrei 2014): a thread starts at leaf s with the range [s, s] and its box in
+// registers.  The parent of a range [l, r] is the split position next to it whose keys differ least — p = r (the range is p's left
+// child) when key[r] ^ key[r+1] < key[l-1] ^ key[l], else p = l - 1 (right child); for a valid range the two differences never have the
+// same leading bit, so the comparison is strict.  The thread leaves its node id and its far bound in p's record, then swaps its
+// subtree height into p's arrival word: the first of the two children to arrive stops, the second finds its sibling's id, bound and
+// height there, reads the sibling's box (one sector), and goes on as node p with the union in registers.  Compared with the two-kernel
+// form this replaces (top-down binary searches for every node, then a bottom-up pass re-reading both children's boxes through parent
+// pointers) a node costs one box read instead of two, no searches and no parent array: leaf boxes + hierarchy 6.35 -> 4.34 ms for 50 M
+// triangles (profiles/r02_build.md).  Same tree: internal node p's children are [l, p] and [p + 1, r]; only the numbering differs (p is
+// the split position, the root is whichever node ends up with [0, n - 1] and goes to *root_out).  `range` is only the place where the two
+// children of a node leave their far bounds for each other.  A subtree of two or three leaves starts at the sorted position its left
+// child names (a leaf's own position; an inner left child of two leaves [q, q + 1] is node q): the collapse reads it from there
+// (collapse_emit_kernel).
+__device__ __forceinline__ bool split_less(const uint64_t* __restrict__ keys, int a, int b)  // is the key step at position a smaller than the one at b?
+{
+    const uint64_t xa = __ldg(keys + a) ^ __ldg(keys + a + 1), xb = __ldg(keys + b) ^ __ldg(keys + b + 1);
+    if (xa != xb) return xa < xb;
+    return (uint32_t)(a ^ (a + 1)) < (uint32_t)(b ^ (b + 1));  // both steps zero (duplicate keys): the positions decide, as in Karras's delta
+}
+
+constexpr uint32_t ARRIVED = 0x80000000u;
+
+__global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
+                                                          const BoxArr box_lo, const BoxArr box_hi, int2* range, uint32_t* arrive, uint8_t* __restrict__ height,
+                                                          uint32_t* __restrict__ root_out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const size_t g = vals[s];
+    const float4 a = tri_tmp[3 * g], b = tri_tmp[3 * g + 1], c = tri_tmp[3 * g + 2];
+    float lx = fminf(a.x, fminf(b.x, c.x)), ly = fminf(a.y, fminf(b.y, c.y)), lz = fminf(a.z, fminf(b.z, c.z));
+    float hx = fmaxf(a.x, fmaxf(b.x, c.x)), hy = fmaxf(a.y, fmaxf(b.y, c.y)), hz = fmaxf(a.z, fmaxf(b.z, c.z));
+    int id = n - 1 + s, l = s, r = s, h = 0;
+    box_lo[id] = make_float4(lx, ly, lz, 0.f);
+    box_hi[id] = make_float4(hx, hy, hz, 0.f);
+    for (;;) {
+        if (l == 0 && r == n - 1) { *root_out = (uint32_t)id; return; }
+        const bool left_child = l == 0 || (r != n - 1 && split_less(keys, r, l - 1));
+        const int p = left_child ? r : l - 1;
+        // what the sibling needs from this subtree: its node id (into the parent's child slot) and its far bound
+        volatile float* slot_w = &(left_child ? box_lo[p] : box_hi[p]).w;
+        volatile int* bound = left_child ? &range[p].x : &range[p].y;
+        *slot_w = __int_as_float(id);
+        *bound = left_child ? l : r;
+        __threadfence();
+        const uint32_t old = atomicExch(&arrive[p], ARRIVED | (uint32_t)h);
+        if (!(old & ARRIVED)) return;  // first arrival: the sibling subtree is not finished yet, its thread will carry on
+        // second arrival: the sibling's stores are visible (its fence precedes its exchange); read them past the L1
+        const int sib = __float_as_int(__ldcg(&(left_child ? box_hi[p] : box_lo[p]).w));
+        const int far = __ldcg(left_child ? &range[p].y : &range[p].x);
+        const float4 slo = __ldcg(&box_lo[sib]), shi = __ldcg(&box_hi[sib]);
+        lx = fminf(lx, slo.x); ly = fminf(ly, slo.y); lz = fminf(lz, slo.z);
+        hx = fmaxf(hx, shi.x); hy = fmaxf(hy, shi.y); hz = fmaxf(hz, shi.z);
+        h = min(max(h, (int)(old & 0xffu)) + 1, 255);
+        if (left_child) r = far; else l = far;
+        box_lo[p] = make_float4(lx, ly, lz, child_word_lo(left_child ? id : sib, r - l + 1));
+        box_hi[p] = make_float4(hx, hy, hz, child_word_hi(left_child ? sib : id, r - l + 1));
+        height[p] = (uint8_t)h;   // subtree height (edges to the deepest leaf): what the collapse's depth guard reads
+        id = p;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,7 +641,7 @@ struct PlocState {
 constexpr uint32_t PLOC_POSITIONAL_ROUND = 64;
 
 __global__ void __launch_bounds__(PLOC_THREADS) ploc_nearest_kernel(const uint32_t* __restrict__ cl0, const uint32_t* __restrict__ cl1, const PlocState* __restrict__ st,
-                                                                     const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, uint32_t* __restrict__ nearest)
+                                                                     const BoxArr box_lo, const BoxArr box_hi, uint32_t* __restrict__ nearest)
 {
     __shared__ float4 slo[PLOC_THREADS + 2 * PLOC_RADIUS], shi[PLOC_THREADS + 2 * PLOC_RADIUS];
     const uint32_t n = st->n;
@@ -640,8 +690,7 @@ __global__ void __launch_bounds__(256) ploc_flag_kernel(const uint32_t* __restri
 
 __global__ void __launch_bounds__(256) ploc_merge_kernel(uint32_t* __restrict__ cl0, uint32_t* __restrict__ cl1, const uint32_t* __restrict__ nearest,
                                                           const PlocState* __restrict__ st, const unsigned long long* __restrict__ excl, int ninternal,
-                                                          float4* __restrict__ box_lo, float4* __restrict__ box_hi, int2* __restrict__ range,
-                                                          uint8_t* __restrict__ height)
+                                                          const BoxArr box_lo, const BoxArr box_hi, uint8_t* __restrict__ height)
 {
     const uint32_t n = st->n, node_base = st->node_base;
     const uint32_t* __restrict__ clusters = st->cc ? cl1 : cl0;
@@ -656,11 +705,11 @@ __global__ void __launch_bounds__(256) ploc_merge_kernel(uint32_t* __restrict__ 
         const uint32_t id = node_base + (uint32_t)(e & 0xffffffffu);
         const uint32_t a = clusters[i], b = clusters[j];
         const float4 alo = box_lo[a], ahi = box_hi[a], blo = box_lo[b], bhi = box_hi[b];
-        const int ca = (int)a < ninternal ? range[a].y : 1, cb = (int)b < ninternal ? range[b].y : 1;
+        const int ca = (int)a < ninternal ? leaves_upto4(alo.w, ahi.w) : 1, cb = (int)b < ninternal ? leaves_upto4(blo.w, bhi.w) : 1;
         const int ha = (int)a < ninternal ? height[a] : 0, hb = (int)b < ninternal ? height[b] : 0;
-        box_lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float((int)a));
-        box_hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), __int_as_float((int)b));
-        range[id] = make_int2(-1, ca + cb);  // x: leaves of a PLOC node are not a range of sorted positions (collapse walks small subtrees)
+        // (the leaves of a clustered node are not a range of sorted positions: the collapse walks its small subtrees)
+        box_lo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), child_word_lo((int)a, min(ca + cb, 4)));
+        box_hi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), child_word_hi((int)b, min(ca + cb, 4)));
         height[id] = (uint8_t)min(max(ha, hb) + 1, 255);
         out[pos] = id;
     }
@@ -689,7 +738,7 @@ __global__ void ploc_init_kernel(uint32_t* clusters, uint32_t n, PlocState* st)
 // 5. refit
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leaf_boxes_kernel(const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
-                                                          float4* __restrict__ box_lo, float4* __restrict__ box_hi)
+                                                          const BoxArr box_lo, const BoxArr box_hi)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -697,32 +746,6 @@ __global__ void __launch_bounds__(256) leaf_boxes_kernel(const float4* __restric
     const float4 a = tri_tmp[3 * g], b = tri_tmp[3 * g + 1], c = tri_tmp[3 * g + 2];
     box_lo[n - 1 + s] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
     box_hi[n - 1 + s] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
-}
-
-__global__ void __launch_bounds__(256) refit_kernel(int n, float4* box_lo, float4* box_hi, const int* __restrict__ parent,
-                                                     uint32_t* __restrict__ arrive, uint8_t* height)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    int node = parent[n - 1 + s];
-    while (node >= 0) {
-        __threadfence();
-        if (atomicAdd(&arrive[node], 1u) == 0u) return;  // first arrival: sibling subtree not ready yet
-        const volatile float4* vlo = box_lo;
-        const volatile float4* vhi = box_hi;
-        const int l = __float_as_int(vlo[node].w), r = __float_as_int(vhi[node].w);
-        const float llx = vlo[l].x, lly = vlo[l].y, llz = vlo[l].z, lhx = vhi[l].x, lhy = vhi[l].y, lhz = vhi[l].z;
-        const float rlx = vlo[r].x, rly = vlo[r].y, rlz = vlo[r].z, rhx = vhi[r].x, rhy = vhi[r].y, rhz = vhi[r].z;
-        // subtree height (edges to the deepest leaf): what the collapse needs to keep the wide tree within the traversal stack; read with
-        // the boxes so that the loads are in flight together
-        const volatile uint8_t* vh = height;
-        const int hl = l < n - 1 ? vh[l] : 0, hr = r < n - 1 ? vh[r] : 0;
-        const int next = parent[node];
-        box_lo[node] = make_float4(fminf(llx, rlx), fminf(lly, rly), fminf(llz, rlz), __int_as_float(l));
-        box_hi[node] = make_float4(fmaxf(lhx, rhx), fmaxf(lhy, rhy), fmaxf(lhz, rhz), __int_as_float(r));
-        height[node] = (uint8_t)min(max(hl, hr) + 1, 255);
-        node = next;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -756,9 +779,8 @@ __device__ __forceinline__ int levels_needed(int h) { return (h + 2) / 3 + 1; }
 static_assert((93 + 2) / 3 + 1 <= MAX_WIDE_DEPTH, "the traversal stack must hold the deepest tree the builder can make");
 
 __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState* __restrict__ st, const uint32_t* __restrict__ work0,
-                                                             const uint32_t* __restrict__ work1, int n, const float4* __restrict__ box_lo,
-                                                             const float4* __restrict__ box_hi, const int2* __restrict__ range,
-                                                             const uint8_t* __restrict__ height, int* __restrict__ child_tmp,
+                                                             const uint32_t* __restrict__ work1, int n, const BoxArr box_lo,
+                                                             const BoxArr box_hi, const uint8_t* __restrict__ height, int* __restrict__ child_tmp,
                                                              unsigned long long* __restrict__ counts, int max_depth)
 {
     const uint32_t nwork = st->nwork;
@@ -772,14 +794,14 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
         int m = 0;
         auto push = [&](int id) {
             ids[m] = id;
-            if (id < ninternal) { cnt[m] = range[id].y; area[m] = box_area(box_lo[id], box_hi[id]); }
+            if (id < ninternal) { const float4 lo = box_lo[id], hi = box_hi[id]; cnt[m] = leaves_upto4(lo.w, hi.w); area[m] = box_area(lo, hi); }
             else { cnt[m] = 1; area[m] = -1.0f; }
             ++m;
         };
         const int root = (int)work[i];
         int hroot = 0;
         if (root >= ninternal) push(root);  // single-triangle scene
-        else { hroot = height[root]; push(__float_as_int(box_lo[root].w)); push(__float_as_int(box_hi[root].w)); }
+        else { hroot = height[root]; push(child_id(box_lo[root].w)); push(child_id(box_hi[root].w)); }
         // depth guard: a subtree too tall for the levels that are left opens its tallest children first until every child is at least 3
         // lower than the root (7 openings always suffice); this takes precedence over the surface-area order below
         // (heights are read here only: one load per wide node on the ordinary path)
@@ -793,7 +815,7 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
                 }
                 if (best < 0) break;
                 const int id = ids[best];
-                const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
+                const int l = child_id(box_lo[id].w), r = child_id(box_hi[id].w);
                 const int save = m;
                 m = best; push(l);
                 m = save; push(r);
@@ -811,7 +833,7 @@ __global__ void __launch_bounds__(128) collapse_plan_kernel(const CollapseState*
                 }
                 if (best < 0) break;
                 const int id = ids[best];
-                const int l = __float_as_int(box_lo[id].w), r = __float_as_int(box_hi[id].w);
+                const int l = child_id(box_lo[id].w), r = child_id(box_hi[id].w);
                 const int save = m;
                 m = best; push(l);
                 m = save; push(r);
@@ -853,157 +875,178 @@ __global__ void collapse_advance_kernel(CollapseState* st, uint32_t max_nodes, c
     cudaGraphSetConditional(cond, (st->nwork > 0u && !st->error) ? 1u : 0u);
 }
 
+// Eight lanes per wide node, one per child: the child boxes arrive as one coalesced read of the plan's ids and eight independent box
+// fetches; the union is the box of the binary node the wide node stands for (read, not reduced); every lane scores the eight slots for
+// its own child and the greedy assignment costs one shuffle per child; the slot-ordered masks (inner children, triangle counts) are one
+// packed OR-reduction; and every lane stores its child's bytes straight into the node image (the byte stores of a group coalesce).
+// (One thread per node held all eight boxes and the whole node image in registers and local memory: 136 registers, 752 bytes of
+// stack, 3.6 of the 6.4 ms the collapse took on 50 M triangles; profiles/r02_build.md.)
 __global__ void __launch_bounds__(128) collapse_emit_kernel(CollapseState* __restrict__ st, uint32_t max_nodes, int n,
-                                                             const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
-                                                             const int2* __restrict__ range, const int* __restrict__ child_tmp,
+                                                             const BoxArr box_lo, const BoxArr box_hi, int scattered_leaves,
+                                                             const int* __restrict__ child_tmp,
                                                              const unsigned long long* __restrict__ excl, uint32_t* __restrict__ work0,
                                                              uint32_t* __restrict__ work1, uint32_t* __restrict__ dest, uint4* __restrict__ nodes_out,
                                                              uint32_t node_bytes)
 {
     const uint32_t nwork = st->nwork, level_start = st->level_start, next_level_start = level_start + nwork, tri_cursor = st->tri_cursor;
+    const uint32_t* __restrict__ work = st->wcur ? work1 : work0;
     uint32_t* __restrict__ next_work = st->wcur ? work0 : work1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
-    const uint32_t node_index = level_start + i;
-    if (node_index >= max_nodes) { st->error = 1u; continue; }
     const int ninternal = n - 1;
-    const unsigned long long ex = excl[i];
-    const uint32_t child_base = next_level_start + (uint32_t)(ex >> 32);
-    const uint32_t tri_base = tri_cursor + (uint32_t)(ex & 0xffffffffu);
-    if (child_base > max_nodes - min(max_nodes, 8u)) { st->error = 1u; continue; }  // its children would not fit: the level check reports it
+    const uint32_t sub = threadIdx.x & 7u;               // lane within the node's group = child index k
+    const uint32_t gbase = threadIdx.x & 24u;            // first lane of the group within the warp
+    const uint32_t gmask = 0xffu << gbase;
+    constexpr uint32_t GROUPS = 128 / 8;
+    for (uint32_t i = blockIdx.x * GROUPS + (threadIdx.x >> 3); i < nwork; i += gridDim.x * GROUPS) {
+        const uint32_t node_index = level_start + i;
+        if (node_index >= max_nodes) { st->error = 1u; continue; }
+        const unsigned long long ex = excl[i];
+        const uint32_t child_base = next_level_start + (uint32_t)(ex >> 32);
+        const uint32_t tri_base = tri_cursor + (uint32_t)(ex & 0xffffffffu);
+        if (child_base > max_nodes - min(max_nodes, 8u)) { st->error = 1u; continue; }  // its children would not fit: the level check reports it
 
-    int ids[8];
-    float4 clo[8], chi[8];
-    int m = 0;
-    float3 Lo = f3(INFINITY, INFINITY, INFINITY), Hi = f3(-INFINITY, -INFINITY, -INFINITY);
-    for (int k = 0; k < 8; ++k) {
-        const int id = child_tmp[(size_t)i * 8 + k];
-        if (id < 0) break;
-        ids[m] = id; clo[m] = box_lo[id]; chi[m] = box_hi[id];
-        Lo = f3(fminf(Lo.x, clo[m].x), fminf(Lo.y, clo[m].y), fminf(Lo.z, clo[m].z));
-        Hi = f3(fmaxf(Hi.x, chi[m].x), fmaxf(Hi.y, chi[m].y), fmaxf(Hi.z, chi[m].z));
-        ++m;
-    }
-    // conservative padding: 2^-16 of the largest extent on every side (covers the rounding of the
-    // slab arithmetic in traverse.cuh; see DESIGN.md "why box tests never cull a true hit")
-    const float maxext = fmaxf(fmaxf(Hi.x - Lo.x, Hi.y - Lo.y), Hi.z - Lo.z);
-    // The pad is applied with directed rounding: far from the origin it is smaller than the spacing of the coordinates (extent 4 at 1e6:
-    // pad 6e-5 against an ulp of 0.0625) and a round-to-nearest `hi + pad` would hand back `hi` — an unpadded box, which the slab test
-    // with clamped zero direction components rejects for a ray lying exactly in one of its face planes.  Rounded outwards, every box
-    // grows by at least one ulp on every side.
-    const float pad = fmaxf(maxext * 1.52587890625e-5f, 1e-30f);
-    const float3 P = f3(__fsub_rd(Lo.x, pad), __fsub_rd(Lo.y, pad), __fsub_rd(Lo.z, pad));
-    // grid exponent per axis: smallest e with 255 * 2^e >= padded extent
-    uint32_t eb[3];
-    float scale[3];
-    const float Pa[3] = {P.x, P.y, P.z};
-    const float Ha[3] = {__fadd_ru(Hi.x, pad), __fadd_ru(Hi.y, pad), __fadd_ru(Hi.z, pad)};
-    const float ext3[3] = {__fsub_ru(Ha[0], P.x), __fsub_ru(Ha[1], P.y), __fsub_ru(Ha[2], P.z)};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float v = ext3[a] * (1.0000002f / 255.0f);
-        const uint32_t bits = __float_as_uint(v);
-        uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
-        e = min(max(e, 1u), 254u);
-        while (e < 254u && fm(255.0f, __uint_as_float(e << 23), Pa[a]) < Ha[a]) ++e;
-        eb[a] = e;
-        scale[a] = __uint_as_float(e << 23);
-    }
-    // slot assignment: greedy, each child takes the free slot whose octant sign vector best matches
-    // its centroid offset (slot bit 4/2/1 set = child on the +x/+y/+z side)
-    const float3 ctr = f3(0.5f * (Lo.x + Hi.x), 0.5f * (Lo.y + Hi.y), 0.5f * (Lo.z + Hi.z));
-    int child_in_slot[8];
-#pragma unroll
-    for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
-    for (int k = 0; k < m; ++k) {
-        const float ox = 0.5f * (clo[k].x + chi[k].x) - ctr.x, oy = 0.5f * (clo[k].y + chi[k].y) - ctr.y,
-                    oz = 0.5f * (clo[k].z + chi[k].z) - ctr.z;
-        int bs = -1;
-        float bc = -INFINITY;
-        for (int s = 0; s < 8; ++s) {
-            if (child_in_slot[s] >= 0) continue;
-            const float c = ((s & 4) ? ox : -ox) + ((s & 2) ? oy : -oy) + ((s & 1) ? oz : -oz);
-            if (c > bc) { bc = c; bs = s; }
-        }
-        child_in_slot[bs] = k;
-    }
-    uint32_t imask = 0;
-    uint32_t meta[8], qlo[3][8], qhi[3][8];
-    float flo[3][8], fhi[3][8];  // Node8F: offsets from P, rounded outwards
-    uint32_t int_k = 0, tri_off = 0;
-    for (int s = 0; s < 8; ++s) {
-        const int k = child_in_slot[s];
-        meta[s] = 0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { qlo[a][s] = 255u; qhi[a][s] = 0u; flo[a][s] = 0.0f; fhi[a][s] = 0.0f; }
-        if (k < 0) continue;
-        const int id = ids[k];
-        const float lo3[3] = {__fsub_rd(clo[k].x, pad), __fsub_rd(clo[k].y, pad), __fsub_rd(clo[k].z, pad)};
-        const float hi3[3] = {__fadd_ru(chi[k].x, pad), __fadd_ru(chi[k].y, pad), __fadd_ru(chi[k].z, pad)};
+        const int kid = child_tmp[(size_t)i * 8 + sub];   // the plan lists the children densely from 0
+        const bool used = kid >= 0;
+        const int m = __popc(__ballot_sync(gmask, used) & gmask);
+        float4 klo = make_float4(0.f, 0.f, 0.f, 0.f), khi = klo;
+        if (used) { klo = box_lo[kid]; khi = box_hi[kid]; }
+        // the children's union is the box of the binary node this wide node stands for (min / max are exact: bit for bit the same)
+        const uint32_t root = work[i];
+        const float4 rlo = box_lo[root], rhi = box_hi[root];
+        const float3 Lo = f3(rlo.x, rlo.y, rlo.z), Hi = f3(rhi.x, rhi.y, rhi.z);
+        // conservative padding: 2^-16 of the largest extent on every side (covers the rounding of the
+        // slab arithmetic in traverse.cuh; see DESIGN.md "why box tests never cull a true hit")
+        const float maxext = fmaxf(fmaxf(Hi.x - Lo.x, Hi.y - Lo.y), Hi.z - Lo.z);
+        // The pad is applied with directed rounding: far from the origin it is smaller than the spacing of the coordinates (extent 4 at 1e6:
+        // pad 6e-5 against an ulp of 0.0625) and a round-to-nearest `hi + pad` would hand back `hi` — an unpadded box, which the slab test
+        // with clamped zero direction components rejects for a ray lying exactly in one of its face planes.  Rounded outwards, every box
+        // grows by at least one ulp on every side.
+        const float pad = fmaxf(maxext * 1.52587890625e-5f, 1e-30f);
+        const float3 P = f3(__fsub_rd(Lo.x, pad), __fsub_rd(Lo.y, pad), __fsub_rd(Lo.z, pad));
+        // grid exponent per axis: smallest e with 255 * 2^e >= padded extent
+        uint32_t eb[3];
+        float scale[3], inv_scale[3];
+        const float Pa[3] = {P.x, P.y, P.z};
+        const float Ha[3] = {__fadd_ru(Hi.x, pad), __fadd_ru(Hi.y, pad), __fadd_ru(Hi.z, pad)};
+        const float ext3[3] = {__fsub_ru(Ha[0], P.x), __fsub_ru(Ha[1], P.y), __fsub_ru(Ha[2], P.z)};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            if (node_bytes == NODE8F_BYTES) {
-                // plane = P + off in exact arithmetic (the traversal evaluates (P + off - o) / d as fma(off, 1/d, (P - o) * (1/d)) and
-                // never forms P + off in floating point): rounding the differences outwards keeps the padded box enclosed
-                flo[a][s] = __fsub_rd(lo3[a], Pa[a]);
-                fhi[a][s] = __fsub_ru(hi3[a], Pa[a]);
-                continue;
-            }
-            int ql = (int)floorf((lo3[a] - Pa[a]) / scale[a]);
-            ql = min(max(ql, 0), 255);
-            while (ql > 0 && fm((float)ql, scale[a], Pa[a]) > lo3[a]) --ql;
-            int qh = (int)ceilf((hi3[a] - Pa[a]) / scale[a]);
-            qh = min(max(qh, 0), 255);
-            while (qh < 255 && fm((float)qh, scale[a], Pa[a]) < hi3[a]) ++qh;
-            qlo[a][s] = (uint32_t)ql;
-            qhi[a][s] = (uint32_t)qh;
+            const float v = ext3[a] * (1.0000002f / 255.0f);
+            const uint32_t bits = __float_as_uint(v);
+            uint32_t e = (bits >> 23) + ((bits & 0x7fffffu) ? 1u : 0u);
+            e = min(max(e, 1u), 254u);
+            while (e < 254u && fm(255.0f, __uint_as_float(e << 23), Pa[a]) < Ha[a]) ++e;
+            eb[a] = e;
+            scale[a] = __uint_as_float(e << 23);
+            inv_scale[a] = e < 254u ? __uint_as_float((254u - e) << 23) : __uint_as_float(0x00400000u);   // 2^(127 - e), exact: x * inv == x / scale
         }
-        int count, first;
-        if (id < ninternal) { const int2 r = range[id]; first = r.x; count = r.y; }
-        else { first = id - ninternal; count = 1; }
-        if (id < ninternal && count > 3) {
-            imask |= 1u << s;
-            meta[s] = (1u << 5) | (24u + (uint32_t)s);
-            next_work[(child_base - next_level_start) + int_k] = (uint32_t)id;
-            ++int_k;
-        } else {
+        // ---- slot assignment: greedy in child order, each child takes the free slot whose octant sign vector best matches its centroid
+        // offset (slot bit 4/2/1 set = child on the +x/+y/+z side; ties: the lower slot).  Every lane scores the eight slots for its
+        // own child; child k's pick goes round with one shuffle.
+        const float3 ctr = f3(0.5f * (Lo.x + Hi.x), 0.5f * (Lo.y + Hi.y), 0.5f * (Lo.z + Hi.z));
+        const float ox = 0.5f * (klo.x + khi.x) - ctr.x, oy = 0.5f * (klo.y + khi.y) - ctr.y, oz = 0.5f * (klo.z + khi.z) - ctr.z;
+        float score[8];
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) score[sl] = ((sl & 4) ? ox : -ox) + ((sl & 2) ? oy : -oy) + ((sl & 1) ? oz : -oz);
+        uint32_t taken = 0u;
+        int slot = -1;
+        for (int k = 0; k < m; ++k) {
+            int bs = -1;
+            float bc = -INFINITY;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl)
+                if (!((taken >> sl) & 1u) && score[sl] > bc) { bc = score[sl]; bs = sl; }
+            if (bs < 0) bs = __ffs(~taken & 0xffu) - 1;   // scores that are not numbers: any free slot
+            const int pick = __shfl_sync(gmask, bs, gbase + k);
+            taken |= 1u << pick;
+            if ((int)sub == k) slot = pick;
+        }
+        if (!used) slot = __fns(~taken & 0xffu, 0u, (int)sub - m + 1);   // the lanes without a child fill the empty slots with "no child"
+        // ---- this lane's child in its slot
+        uint32_t qlo[3] = {255u, 255u, 255u}, qhi[3] = {0u, 0u, 0u};
+        float flo[3] = {0.f, 0.f, 0.f}, fhi[3] = {0.f, 0.f, 0.f};  // Node8F: offsets from P, rounded outwards
+        int count = 0, first = 0;
+        bool inner = false;
+        if (used) {
+            const float lo3[3] = {__fsub_rd(klo.x, pad), __fsub_rd(klo.y, pad), __fsub_rd(klo.z, pad)};
+            const float hi3[3] = {__fadd_ru(khi.x, pad), __fadd_ru(khi.y, pad), __fadd_ru(khi.z, pad)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (node_bytes == NODE8F_BYTES) {
+                    // plane = P + off in exact arithmetic (the traversal evaluates (P + off - o) / d as fma(off, 1/d, (P - o) * (1/d)) and
+                    // never forms P + off in floating point): rounding the differences outwards keeps the padded box enclosed
+                    flo[a] = __fsub_rd(lo3[a], Pa[a]);
+                    fhi[a] = __fsub_ru(hi3[a], Pa[a]);
+                    continue;
+                }
+                int ql = (int)floorf((lo3[a] - Pa[a]) * inv_scale[a]);
+                ql = min(max(ql, 0), 255);
+                while (ql > 0 && fm((float)ql, scale[a], Pa[a]) > lo3[a]) --ql;
+                int qh = (int)ceilf((hi3[a] - Pa[a]) * inv_scale[a]);
+                qh = min(max(qh, 0), 255);
+                while (qh < 255 && fm((float)qh, scale[a], Pa[a]) < hi3[a]) ++qh;
+                qlo[a] = (uint32_t)ql;
+                qhi[a] = (uint32_t)qh;
+            }
+            if (kid < ninternal) {
+                count = leaves_upto4(klo.w, khi.w);
+                // two or three leaves: consecutive sorted positions from the one the left child names (radix tree), or wherever the
+                // clustering found them (scattered_leaves: walk the subtree)
+                const int left = child_id(klo.w);
+                first = scattered_leaves ? -1 : (left >= ninternal ? left - ninternal : left);
+            } else { first = kid - ninternal; count = 1; }
+            inner = kid < ninternal && count > 3;
+        }
+        // slot-ordered masks in one OR-reduction: inner children | leaf children with an odd count << 8 | with two or three << 16
+        const uint32_t lcount = (used && !inner) ? (uint32_t)count : 0u;   // 0 .. 3 triangles in a leaf child
+        uint32_t masks = ((inner ? 1u : 0u) | ((lcount & 1u) << 8) | ((lcount >> 1) << 16)) << slot;
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) masks |= __shfl_xor_sync(gmask, masks, d);
+        const uint32_t imask = masks & 0xffu, c0 = (masks >> 8) & 0xffu, c1 = (masks >> 16) & 0xffu;
+        const uint32_t below = (1u << slot) - 1u;
+        const uint32_t tri_off = (uint32_t)__popc(c0 & below) + 2u * (uint32_t)__popc(c1 & below);   // triangles of the leaf children in lower slots
+        uint32_t meta = 0u;
+        if (inner) {
+            meta = (1u << 5) | (24u + (uint32_t)slot);
+            next_work[(child_base - next_level_start) + (uint32_t)__popc(imask & below)] = (uint32_t)kid;
+        } else if (used) {
             const uint32_t unary = count == 1 ? 1u : (count == 2 ? 3u : 7u);
-            meta[s] = (unary << 5) | tri_off;
+            meta = (unary << 5) | tri_off;
             if (first >= 0) {
                 for (int j = 0; j < count; ++j) dest[first + j] = tri_base + tri_off + (uint32_t)j;
             } else {
                 // PLOC subtree of 2 or 3 leaves: its leaves are not consecutive sorted positions, walk it (left to right)
-                int stack2[4] = {id, -1, -1, -1};
+                int stack2[4] = {kid, -1, -1, -1};
                 int sp2 = 1, j = 0;
                 while (sp2 > 0) {
                     const int nd = stack2[--sp2];
                     if (nd >= ninternal) { dest[nd - ninternal] = tri_base + tri_off + (uint32_t)j; ++j; continue; }
-                    stack2[sp2++] = __float_as_int(box_hi[nd].w);
-                    stack2[sp2++] = __float_as_int(box_lo[nd].w);
+                    stack2[sp2++] = child_id(box_hi[nd].w);
+                    stack2[sp2++] = child_id(box_lo[nd].w);
                 }
             }
-            tri_off += (uint32_t)count;
         }
-    }
-    auto pack4 = [](const uint32_t* b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
-    if (node_bytes == NODE8F_BYTES) {
-        uint4* out = nodes_out + (size_t)node_index * (NODE8F_BYTES / 16);
-        out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), imask);
-        out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+        // ---- the node image.  Words 0-5 (both formats): origin, exponents | inner mask, child base, triangle base; bytes 24-31: meta
+        uint32_t* out = (uint32_t*)((char*)nodes_out + (size_t)node_index * node_bytes);
+        uint8_t* outb = (uint8_t*)out;
+        const uint32_t w3 = node_bytes == NODE8F_BYTES ? imask : (eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+        const uint32_t head = sub == 0u ? __float_as_uint(P.x) : sub == 1u ? __float_as_uint(P.y) : sub == 2u ? __float_as_uint(P.z) : sub == 3u ? w3 : sub == 4u ? child_base : tri_base;
+        if (sub < 6u) out[sub] = head;
+        outb[24 + slot] = (uint8_t)meta;
+        if (node_bytes == NODE8F_BYTES) {
+            // plane-major: [lo x][lo y][lo z][hi x][hi y][hi z], eight floats each
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                out[8 + 8 * a + slot] = __float_as_uint(flo[a]);
+                out[32 + 8 * a + slot] = __float_as_uint(fhi[a]);
+            }
+            continue;
+        }
+        // Node8 bytes 32-79: six planes (lo x, lo y, lo z, hi x, hi y, hi z) of eight slot bytes
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            out[2 + 2 * a] = make_uint4(__float_as_uint(flo[a][0]), __float_as_uint(flo[a][1]), __float_as_uint(flo[a][2]), __float_as_uint(flo[a][3]));
-            out[3 + 2 * a] = make_uint4(__float_as_uint(flo[a][4]), __float_as_uint(flo[a][5]), __float_as_uint(flo[a][6]), __float_as_uint(flo[a][7]));
-            out[8 + 2 * a] = make_uint4(__float_as_uint(fhi[a][0]), __float_as_uint(fhi[a][1]), __float_as_uint(fhi[a][2]), __float_as_uint(fhi[a][3]));
-            out[9 + 2 * a] = make_uint4(__float_as_uint(fhi[a][4]), __float_as_uint(fhi[a][5]), __float_as_uint(fhi[a][6]), __float_as_uint(fhi[a][7]));
+            outb[32 + 8 * a + slot] = (uint8_t)qlo[a];
+            outb[56 + 8 * a + slot] = (uint8_t)qhi[a];
         }
-        continue;
-    }
-    uint4* out = nodes_out + (size_t)node_index * 5;
-    out[0] = make_uint4(__float_as_uint(P.x), __float_as_uint(P.y), __float_as_uint(P.z), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
-    out[1] = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
-    out[2] = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
-    out[3] = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
-    out[4] = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
     }
 }
 
@@ -1036,12 +1079,12 @@ __global__ void write_header_kernel(AccelHeader* h, AccelHeader v, const uint32_
     if (emit1) *emit1 = compacted;
 }
 
-// first work item of the collapse: the root of the binary hierarchy (radix tree: internal node 0, or leaf 0 of a one-triangle input;
-// clustering: the last cluster standing)
-__global__ void collapse_init_kernel(CollapseState* st, uint32_t* work0, uint32_t root, const uint32_t* cl0, const uint32_t* cl1, const PlocState* ploc)
+// first work item of the collapse: the root of the binary hierarchy (radix tree: *root_dev; clustering: the last cluster standing)
+__global__ void collapse_init_kernel(CollapseState* st, uint32_t* work0, const uint32_t* root_dev, const uint32_t* cl0, const uint32_t* cl1, const PlocState* ploc)
 {
     CollapseState z = {};
     z.nwork = 1u;
+    uint32_t root = ploc ? 0u : *root_dev;  // radix tree: the node that ended up with the whole range (leaf 0 of a one-triangle input)
     if (ploc) {
         root = (ploc->cc ? cl1 : cl0)[0];
         if (ploc->error || ploc->n != 1u) z.error = 3u;
@@ -1110,7 +1153,7 @@ struct BuildPlan {
     uint32_t rs_blocks = 0;
     int morton_bits = 21;
     // temp offsets
-    size_t off_inputs, off_flags, off_bounds, off_state, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box_lo, off_box_hi,
+    size_t off_inputs, off_flags, off_bounds, off_state, off_tri_tmp, off_keys0, off_keys1, off_vals0, off_vals1, off_box,
         off_parent, off_range, off_arrive, off_dest, off_hist, off_scan_tmp, off_work0, off_work1, off_child_tmp, off_counts, off_height, off_dsums;
     size_t temp_bytes = 0, out_bytes = 0;
     uint32_t node_bytes = NODE8_BYTES;
@@ -1176,9 +1219,10 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.total_sbt = (uint32_t)sbt;
     p.max_nodes = (uint32_t)(2 * n / 3 + 16);
     p.rs_blocks = std::max(1u, div_up(n, RS_TILE));
-    // bits per axis of the Morton key = radix passes of the sort (8 bits each): 30 / 48 / 54 / 63 bits -> 4 / 6 / 7 / 8 passes.  2^18 cells
-    // per axis separate the centroids of 10^8 triangles as well as 2^21 do; the eighth pass is for inputs beyond that.
-    p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 22) ? 16 : (n < (1u << 27) ? 18 : 21));
+    // bits per axis of the Morton key = radix passes of the sort (8 bits each): 30 / 48 / 63 bits -> 4 / 6 / 8 passes.  2^16 cells per axis
+    // separate the centroids of 5 * 10^7 triangles as well as 2^18 do (same node visits per ray to five digits, one pass = 0.8 ms less:
+    // profiles/r02_build.md); the 63-bit key is for inputs beyond 2^27 triangles.
+    p.morton_bits = n < (1u << 14) ? 10 : (n < (1u << 27) ? 16 : 21);
     if (const char* e = getenv("B200RT_MORTON_BITS")) p.morton_bits = std::min(std::max(atoi(e), 4), 21);  // A/B runs
     const size_t N = std::max<size_t>(n, 1);
     const size_t W = N / 4 + 2;  // widest possible level (every wide node roots >= 4 triangles)
@@ -1187,16 +1231,14 @@ static int make_plan(b200rt_context ctx, const b200rt_build_input* inputs, unsig
     p.off_inputs = take(sizeof(DevInput) * std::max(1u, num_inputs));
     p.off_flags = take(4 * std::max<size_t>(sbt, 1));
     p.off_bounds = take(64);
-    p.off_state = take(256);      // PlocState at 0, CollapseState at 128
+    p.off_state = take(256);      // PlocState at 0, CollapseState at 128, root of the radix tree at 192
     p.off_dsums = take(8 * DS_BLOCKS);
     p.off_tri_tmp = take(48 * N);
     p.off_keys0 = take(8 * N);
     p.off_keys1 = take(8 * N);
     p.off_vals0 = take(4 * N);
     p.off_vals1 = take(4 * N);
-    p.off_box_lo = take(16 * 2 * N);
-    p.off_box_hi = take(16 * 2 * N);
-    p.off_parent = take(4 * 2 * N);
+    p.off_box = take(32 * 2 * N);
     p.off_range = take(8 * N);
     p.off_arrive = take(4 * N);
     p.off_dest = take(4 * N);
@@ -1313,9 +1355,8 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
         float4* tri_tmp = (float4*)(T + p.off_tri_tmp);
         uint64_t* keys[2] = {(uint64_t*)(T + p.off_keys0), (uint64_t*)(T + p.off_keys1)};
         uint32_t* vals[2] = {(uint32_t*)(T + p.off_vals0), (uint32_t*)(T + p.off_vals1)};
-        float4* box_lo = (float4*)(T + p.off_box_lo);
-        float4* box_hi = (float4*)(T + p.off_box_hi);
-        int* parent = (int*)(T + p.off_parent);
+        const BoxArr box_lo{(float4*)(T + p.off_box)}, box_hi{(float4*)(T + p.off_box) + 1};   // interleaved: see BoxArr
+        uint32_t* d_root = (uint32_t*)(T + p.off_state + 192);
         int2* range = (int2*)(T + p.off_range);
         uint32_t* arrive = (uint32_t*)(T + p.off_arrive);
         uint32_t* dest = (uint32_t*)(T + p.off_dest);
@@ -1366,14 +1407,14 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 cur ^= 1;
             }
             mark();  // gather + Morton + sort
-            leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
-            B2_LAUNCH_CHECK(ctx);
             // No host read-back from here on: optixAccelBuild is asynchronous, so the rounds of the clustering and the levels of
             // the collapse, whose counts only the device knows, run as device-side loops (CUDA graphs with a conditional WHILE node).
             const unsigned wide_grid = std::max(1u, std::min(div_up(N, 128), (unsigned)ctx->sm_count * 16u));
             const bool ploc = use_ploc(options, N) && N > 1;
             uint32_t* cl[2] = {nullptr, nullptr};
             if (ploc) {
+                leaf_boxes_kernel<<<div_up(N, 256), 256, 0, s>>>(tri_tmp, vals[cur], (int)N, box_lo, box_hi);
+                B2_LAUNCH_CHECK(ctx);
                 // the sort's key buffers are free now: cluster ping-pong in one, the scan words in the other
                 cl[0] = (uint32_t*)keys[cur]; cl[1] = (uint32_t*)keys[cur] + N;
                 unsigned long long* flags = (unsigned long long*)keys[cur ^ 1];
@@ -1385,23 +1426,21 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 park_loop(ctx, &g);
                 if ((rc = g.begin())) return rc;
                 if ((rc = g.add((const void*)ploc_nearest_kernel, pgrid, PLOC_THREADS, 0, (const uint32_t*)cl[0], (const uint32_t*)cl[1], (const PlocState*)d_ploc,
-                                (const float4*)box_lo, (const float4*)box_hi, nearest))) return rc;
+                                box_lo, box_hi, nearest))) return rc;
                 if ((rc = g.add((const void*)ploc_flag_kernel, pgrid, 256, 0, (const uint32_t*)nearest, (const PlocState*)d_ploc, flags))) return rc;
                 if ((rc = dscan_add<unsigned long long>(g, flags, &d_ploc->n, dsums, &d_ploc->total))) return rc;
                 if ((rc = g.add((const void*)ploc_merge_kernel, pgrid, 256, 0, cl[0], cl[1], (const uint32_t*)nearest, (const PlocState*)d_ploc,
-                                (const unsigned long long*)flags, (int)N - 1, box_lo, box_hi, range, height))) return rc;
+                                (const unsigned long long*)flags, (int)N - 1, box_lo, box_hi, height))) return rc;
                 if ((rc = g.add((const void*)ploc_advance_kernel, 1, 1, 0, d_ploc, g.cond()))) return rc;
                 if ((rc = g.launch(s))) return rc;
                 ctx->launches += 1;
-            } else if (N > 1) {
-                karras_kernel<<<div_up(N - 1, 256), 256, 0, s>>>(keys[cur], (int)N, box_lo, box_hi, parent, range);
-                B2_LAUNCH_CHECK(ctx);
+            } else {
                 B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
-                refit_kernel<<<div_up(N, 256), 256, 0, s>>>((int)N, box_lo, box_hi, parent, arrive, height);
+                radix_tree_kernel<<<div_up(N, 256), 256, 0, s>>>(keys[cur], tri_tmp, vals[cur], (int)N, box_lo, box_hi, range, arrive, height, d_root);
                 B2_LAUNCH_CHECK(ctx);
             }
             mark();  // leaf boxes + binary hierarchy
-            collapse_init_kernel<<<1, 1, 0, s>>>(d_cst, work[0], 0u, cl[0], cl[1], ploc ? d_ploc : nullptr);  // radix tree: internal node 0, or leaf 0 when N == 1
+            collapse_init_kernel<<<1, 1, 0, s>>>(d_cst, work[0], d_root, cl[0], cl[1], ploc ? d_ploc : nullptr);
             B2_LAUNCH_CHECK(ctx);
             // ---- collapse, level by level
             static const bool body_timing = [] { const char* e = getenv("B200RT_BUILD_TIMING"); return e && atoi(e) >= 2; }();
@@ -1416,12 +1455,13 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 park_loop(ctx, &g);
                 if ((rc = g.begin())) return rc;
                 if ((rc = g.add((const void*)collapse_plan_kernel, wide_grid, 128, 0, (const CollapseState*)d_cst, (const uint32_t*)work[0], (const uint32_t*)work[1], (int)N,
-                                (const float4*)box_lo, (const float4*)box_hi, (const int2*)range, (const uint8_t*)height, child_tmp, counts, max_wide_depth()))) return rc;
+                                box_lo, box_hi, (const uint8_t*)height, child_tmp, counts, max_wide_depth()))) return rc;
                 if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 0))) return rc;
                 if ((rc = dscan_add<unsigned long long>(g, counts, &d_cst->nwork, dsums, &d_cst->total))) return rc;
                 if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 1))) return rc;
-                if ((rc = g.add((const void*)collapse_emit_kernel, wide_grid, 128, 0, d_cst, p.max_nodes, (int)N, (const float4*)box_lo, (const float4*)box_hi,
-                                (const int2*)range, (const int*)child_tmp, (const unsigned long long*)counts, work[0], work[1], dest, nodes_out, p.node_bytes))) return rc;
+                const unsigned emit_grid = std::max(1u, std::min(div_up(N, 64), (unsigned)ctx->sm_count * 8u));  // 16 nodes per CTA and sweep
+                if ((rc = g.add((const void*)collapse_emit_kernel, emit_grid, 128, 0, d_cst, p.max_nodes, (int)N, box_lo, box_hi, ploc ? 1 : 0,
+                                (const int*)child_tmp, (const unsigned long long*)counts, work[0], work[1], dest, nodes_out, p.node_bytes))) return rc;
                 if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 2))) return rc;
                 if ((rc = g.add((const void*)collapse_advance_kernel, 1, 1, 0, d_cst, p.max_nodes, g.cond()))) return rc;
                 if (body_timing && (rc = g.add((const void*)stamp_kernel, 1, 1, 0, d_stamps, 3))) return rc;
