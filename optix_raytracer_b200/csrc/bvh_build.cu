@@ -384,7 +384,13 @@ __global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // 3. LSD radix sort, 8-bit digits, stable.  One block owns one tile of RS_TILE consecutive keys.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_IPT = 16, RS_TILE = RS_THREADS * RS_IPT;
+#ifndef B200RT_RS_IPT
+#define B200RT_RS_IPT 16
+#endif
+#ifndef B200RT_RS_MIN_CTAS
+#define B200RT_RS_MIN_CTAS 3
+#endif
+constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32, RS_IPT = B200RT_RS_IPT, RS_TILE = RS_THREADS * RS_IPT;
 
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift,
@@ -410,7 +416,7 @@ template <typename K>
 constexpr size_t rs_scatter_smem() { return (size_t)RS_TILE * (sizeof(K) + sizeof(uint32_t)); }
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, B200RT_RS_MIN_CTAS) rs_scatter_kernel(const K* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                                  K* __restrict__ kout, uint32_t* __restrict__ vout, uint32_t n,
                                                                  int shift, const uint32_t* __restrict__ offs, uint32_t nblocks)
 {
