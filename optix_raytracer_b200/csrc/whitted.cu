@@ -213,6 +213,7 @@ struct WK {
     uint32_t width, height, nl_cap, level, level_start, cap_slots;
     const char* hg_base;
     uint32_t hg_stride, hg_count;
+    uint32_t raygen_traverses;  // 1: RAYGEN traverses the camera rays of an opaque scene itself (launches without BLEND levels)
     uint32_t blend_levels;  // 1: the BLEND levels are run (the host found such a material; level / level_start / fetch come from the
                             //    device-side loop state in WCounters); 0: one level, and SHADE flags a BLEND material as an error
     WCounters* counters;
@@ -264,33 +265,6 @@ __device__ __forceinline__ void w_write_pixel(const WParams& P, uint32_t pixel, 
 __device__ __forceinline__ uint32_t w_inst_sbt(const AccelHeader* handle, uint32_t inst)
 {
     return handle->kind == ACCEL_KIND_IAS ? ((const InstanceRecord*)((const char*)handle + handle->inst_off) + inst)->sbt_offset : 0u;
-}
-
-// ---- RAYGEN: one thread per pixel — the camera ray against the bounds of the scene -----------------------------------------------------
-// A model viewer's camera rays mostly pass the model by.  Those pixels are finished right here, by 2 M independent threads (the miss
-// program and the raygen tail: whitted.cu:84-97,139-142); only the rays that reach the (padded, hence conservative: trav_coop.cuh
-// trav_begin<BOUNDS>) scene bounds become work items of the persistent traversal, whose lanes take one item at a time and would
-// otherwise spend their time on the latency of fetch -> set-up -> accum read for rays that hit nothing (measured: 150 us of a 270 us
-// frame, profiles/r01_whitted_launches.md).
-__global__ void __launch_bounds__(256) w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool candidate = false;
-    if (i < npix) {
-        const WParams& P = *k.params;
-        const AccelHeader* h = (const AccelHeader*)P.handle;
-        float3 o, d;
-        w_camera_ray(P, k.width, k.height, i, o, d);
-        candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
-        if (!candidate) w_write_pixel(P, i, P.miss_color);
-    }
-    const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
-    if (!mask) return;
-    const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&k.counters->nprimary, (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (candidate) k.primary[base + __popc(mask & ((1u << lane) - 1u))] = i;
 }
 
 // ---- PRIMARY: radiance rays of one level ---------------------------------------------------------------------------------------------
@@ -380,6 +354,58 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const
     n_items = level == 0 ? k.counters->nprimary : k.counters->n_items;  // counted by RAYGEN / by the previous level's SHADE
     WPrimaryWork<AH> work(k, handle, level);
     trace_persistent(work, n_items, w_fetch(k, 0u), nullptr);
+}
+
+// ---- RAYGEN: one thread per pixel — the camera ray against the bounds of the scene -----------------------------------------------------
+// A model viewer's camera rays mostly pass the model by.  Those pixels are finished right here, by 2 M independent threads (the miss
+// program and the raygen tail: whitted.cu:84-97,139-142).  What happens to the rays that reach the (padded, hence conservative:
+// trav_coop.cuh trav_begin<BOUNDS>) scene bounds depends on the scene:
+//   * by default the pixel becomes a work item of the persistent traversal (w_primary_kernel), whose lanes take one item at a time and
+//     would otherwise spend their time on the latency of fetch -> set-up -> accum read for rays that hit nothing (measured: 150 us of a
+//     270 us frame, profiles/r01_whitted_launches.md);
+//   * B200RT_WHITTED_INLINE=1, opaque scene (WK::raygen_traverses): the thread traverses its ray on the spot (trav_coop.cuh:
+//     trace_one_per_thread), and the probes run one per thread too (w_shadow_simple_kernel).  Camera rays in pixel order are coherent,
+//     which made this form the faster one for optixRaycasting's ray buffers (raycast.cu); here it is not: Duck 1080p, RAYGEN + PRIMARY
+//     37 + 86 us -> 117 us in one launch, SHADOW 77 -> 99 us, frame 0.248 -> 0.257 ms (profiles/r02_small_scenes.md).  Of 2 M pixels
+//     170 k reach the model: the traversing warps are partly empty and alone on their SM, while the persistent form packs the rays.
+struct WPixelWork : WPrimaryWork<false> {
+    __device__ WPixelWork(const WK& k_, const AccelHeader* h) : WPrimaryWork<false>(k_, h, 0u) {}
+    __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
+    {
+        pixel = item; parent = -1;
+        float3 o, d;
+        float tmin;
+        ray(o, d, tmin);
+        s.best.t = 1e16f;
+        if (!trav_begin_handle<true>(s, my_ray, handle, o, d, tmin, 0u, B200RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES & 0xf0u, 0u)) { commit(s, false); return false; }
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(128) w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const WParams& P = *k.params;
+    const AccelHeader* h = (const AccelHeader*)P.handle;
+    bool candidate = false;
+    if (i < npix) {
+        float3 o, d;
+        w_camera_ray(P, k.width, k.height, i, o, d);
+        candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
+        if (!candidate) w_write_pixel(P, i, P.miss_color);
+    }
+    if (h->anyhit == 0u && k.raygen_traverses) {   // uniform over the launch
+        WPixelWork work(k, h);
+        trace_one_per_thread(work, i, candidate, nullptr);
+        return;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
+    if (!mask) return;
+    const uint32_t lane = threadIdx.x & 31u, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&k.counters->nprimary, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (candidate) k.primary[base + __popc(mask & ((1u << lane) - 1u))] = i;
 }
 
 // ---- SHADE: __closesthit__radiance up to the shadow rays, one thread per hit slot of the level --------------------------------------
@@ -598,6 +624,22 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const 
     trace_persistent(work, n_items, w_fetch(k, 1u), nullptr);
 }
 
+// The probes of an opaque scene on the one-ray-per-thread driver: the hit slots are in (roughly) pixel order, so neighbouring probes
+// start next to each other and aim at the same light — coherent like the camera rays (see w_raygen_kernel).  Grid-stride over the
+// items, whose count only the device knows.
+__global__ void __launch_bounds__(128) w_shadow_simple_kernel(const __grid_constant__ WK k)
+{
+    const WParams* P = k.params;
+    const AccelHeader* handle = (const AccelHeader*)P->handle;
+    if (handle->anyhit != 0u) return;
+    const uint32_t end = min(k.counters->nslots, k.cap_slots);
+    const uint32_t nl = min(P->lights.count, k.nl_cap);
+    const uint32_t level_start = w_level_start(k);
+    const uint32_t n_items = end > level_start ? (end - level_start) * max(nl, 1u) : 0u;
+    WShadowWork<false> work(k, handle, nl, level_start);
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) trace_one_per_thread(work, item, true, nullptr);
+}
+
 // ---- COMBINE: fold the levels of a BLEND pixel back to front, as the recursion of __closesthit__radiance returns -----------------------
 __global__ void __launch_bounds__(128) w_combine_kernel(const __grid_constant__ WK k)
 {
@@ -744,18 +786,24 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     unsigned int* cursors = (unsigned int*)(W + o_cnt + 64);  // two per level
     B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters, loop state and all work-item cursors of the frame
     k.fetch = cursors;
-    w_raygen_kernel<<<div_up(npix, 256), 256, 0, s>>>(k, npix);
+    // B200RT_WHITTED_INLINE=1: opaque scenes on the one-ray-per-thread kernels (measured slower than the persistent ones, see w_raygen_kernel)
+    static const bool persistent_opaque = [] { const char* e = getenv("B200RT_WHITTED_INLINE"); return !(e && atoi(e) != 0); }();
+    k.raygen_traverses = (!blend && !persistent_opaque) ? 1u : 0u;
+    w_raygen_kernel<<<div_up(npix, 128), 128, 0, s>>>(k, npix);
     B2_LAUNCH_CHECK(ctx);
     const unsigned g_primary = w_persistent_grid(ctx, k_primary, npix), g_shadow = w_persistent_grid(ctx, k_shadow, (uint64_t)npix * nlp);
     const unsigned g_shade = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 16));
     if (!blend) {
-        w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
-        B2_LAUNCH_CHECK(ctx);
+        // Both instantiations of the persistent kernels are enqueued: which kind the traversable is, is read on the device
+        // (AccelHeader::anyhit), each kernel returns at once unless it is its kind, so the choice cannot go stale when another handle is
+        // written into the same LaunchParams.  (B200RT_WHITTED_INLINE: opaque scenes on the one-ray-per-thread kernels instead.)
         w_primary_kernel<true><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
         B2_LAUNCH_CHECK(ctx);
+        if (persistent_opaque) { w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix); B2_LAUNCH_CHECK(ctx); }
         w_shade_kernel<<<g_shade, 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
-        w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
+        if (persistent_opaque) w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
+        else w_shadow_simple_kernel<<<std::max(1u, std::min(div_up((uint64_t)npix * nlp, 128), (unsigned)ctx->sm_count * 8u)), 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         w_shadow_kernel<true><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);

@@ -1,4 +1,4 @@
-for lib in optix_raytracer_b200/libb200rt.so gpurun_variants/*.so; do
-  echo "== $lib"
-  B200RT_LIB_PATH=$PWD/$lib B200RT_BUILD_TIMING=1 timeout 120 python tools/build_once.py --reps 3 2>&1 | grep "b200rt build\|build 2" | tail -2
+for v in 0 1; do
+B200RT_WHITTED_PERSISTENT=$v ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_whitted_$v.csv python tools/run_whitted.py opaque > /dev/null 2>&1
+python tools/ncu_launch_summary.py gpurun_out/launches_whitted_$v.csv | head -12
 done
