@@ -64,7 +64,12 @@ def parse(argv=None):
     if a.ray_sort is None:
         a.ray_sort = 0
     if a.sample_groups is None:
-        a.sample_groups = 8 if a.workload == "synthetic" else 4   # measured best on one B200 (gpurun_out/sg_*.json); any value gives the same image on any N
+        # lanes per launch index (fp32 summation order of a pixel's samples; the rays traced are the same for any value).  One GPU: 8 on the
+        # bench scene (16 is 0.6 % faster for twice the lane state, 20 GB), 4 on the small ones.  With the image split over N > 1 GPUs a rank
+        # holds 1/N of the launch indices, so 16 groups keep its launches as wide as one GPU's (and its lane state below one GPU's):
+        # measured 8 GPUs 16026 -> 16538 Mrays/s, 4 GPUs 8272 -> 8459 (profiles/r02_scaling.md).
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        a.sample_groups = (8 if world == 1 else 16) if a.workload == "synthetic" else 4
     return a
 
 
