@@ -68,10 +68,10 @@ int ensure_workspace(b200rt_context ctx, size_t bytes, cudaStream_t stream)
 
 using namespace b200rt;
 
-#define CTX_CHECK(ctx)                                           \
-    do {                                                         \
-        if (!(ctx)) return B200RT_ERROR_INVALID_DEVICE_CONTEXT;  \
-    } while (0)
+// every entry point that takes a context holds its mutex for the call: set_error writes ctx->last_error, launches share the workspace
+#define CTX_CHECK(ctx)                                        \
+    if (!(ctx)) return B200RT_ERROR_INVALID_DEVICE_CONTEXT;   \
+    std::lock_guard<std::recursive_mutex> b2_ctx_lock((ctx)->mu)
 
 extern "C" {
 
@@ -232,7 +232,7 @@ int b200rt_accel_build(b200rt_context ctx, b200rt_stream stream, const b200rt_ac
                        size_t output_bytes, b200rt_traversable* handle, const b200rt_accel_emit_desc* emitted, unsigned int num_emitted)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return accel_build(ctx, (cudaStream_t)stream, options, inputs, num_inputs, temp_buffer, temp_bytes, output_buffer, output_bytes, handle,
                        emitted, num_emitted);
 }
@@ -261,7 +261,7 @@ int b200rt_launch_pathtracer(b200rt_context ctx, b200rt_stream stream, b200rt_de
                              unsigned int width, unsigned int height, const b200rt_pt_options* options)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return launch_pathtracer(ctx, (cudaStream_t)stream, d_params, sbt, width, height, options, 0);
 }
 
@@ -269,7 +269,7 @@ int b200rt_launch_multigpu(b200rt_context ctx, b200rt_stream stream, b200rt_devi
                            unsigned int num_samples, const b200rt_pt_options* options)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return launch_pathtracer(ctx, (cudaStream_t)stream, d_params, sbt, num_samples, 1, options, 1);
 }
 
@@ -331,7 +331,7 @@ int b200rt_trace_stats(b200rt_context ctx, b200rt_stream stream, b200rt_traversa
                        uint64_t* nodes_fetched, uint64_t* tris_tested)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return trace_stats(ctx, (cudaStream_t)stream, handle, rays, n, nodes_fetched, tris_tested);
 }
 
@@ -346,7 +346,7 @@ int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_devic
                           unsigned int width, unsigned int height)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return launch_whitted(ctx, (cudaStream_t)stream, d_params, sbt, width, height);
 }
 
@@ -367,7 +367,7 @@ int b200rt_launch_playground(b200rt_context ctx, b200rt_stream stream, b200rt_de
                              const b200rt_pt_options* options)
 {
     CTX_CHECK(ctx);
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     return launch_playground(ctx, (cudaStream_t)stream, d_params, width, height, options);
 }
 

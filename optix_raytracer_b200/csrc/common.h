@@ -41,7 +41,7 @@ struct b200rt_context_t {
     std::vector<b200rt::LoopGraph*> loops;      // build loops in flight (loop_graph.h)
     b200rt::WLoopCache* w_loop = nullptr;       // the BLEND level loop of the whitted launches (whitted.cu)
     b200rt::PTGraphCache* pt_graphs = nullptr;  // instantiated wavefront-loop graphs of the path-tracer launches (pathtracer.cu)
-    std::mutex mu;
+    std::recursive_mutex mu;  // held by every C ABI entry point that takes the context (CTX_CHECK): last_error, the workspace and the caches are per context
     std::vector<cudaEvent_t> timing_events;  // pool for B200RT_PT_STATS_TIMING
     unsigned int counter_slot = 0;  // rotating fetch-counter slot for persistent ray launches
     // whitted launches: light count the workspace was sized for, learnt from the first launch with a given d_params (whitted.cu)

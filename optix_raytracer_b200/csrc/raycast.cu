@@ -316,7 +316,7 @@ int trace_closest(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle,
     B2_REQUIRE(ctx, handle && (n == 0 || (rays && ext)) && n < (1ull << 32), "bad argument");
     DeviceGuard guard(ctx->device);
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
@@ -333,7 +333,7 @@ int trace_any(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b20
     B2_REQUIRE(ctx, handle && (n == 0 || (rays && occ)) && n < (1ull << 32), "bad argument");
     DeviceGuard guard(ctx->device);
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;
@@ -355,7 +355,10 @@ int trace_stats(b200rt_context ctx, cudaStream_t s, b200rt_traversable handle, b
     unsigned long long* d_stats = (unsigned long long*)ctx->ws.ptr;
     ExtHit* scratch = nullptr;
     B2_CUDA(ctx, cudaMalloc(&scratch, sizeof(ExtHit) * std::max<uint64_t>(n, 1)));
-    B2_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
+    {
+        const cudaError_t e0 = cudaMemsetAsync(d_stats, 0, 16, s);
+        if (e0 != cudaSuccess) { cudaFree(scratch); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "trace_stats: %s", cudaGetErrorString(e0)); }
+    }
     if (n) {
         trace_rays_kernel<0, true, false><<<persistent_grid_rays<0, true>(ctx, n), COOP_BLOCK, 0, s>>>(
             (const AccelHeader*)handle, (const float4*)rays, (uint32_t)n, 0u, scratch, nullptr, nullptr, nullptr, 0, 0, counter, d_stats, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, 0u);
@@ -381,7 +384,7 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     const uint64_t n = (uint64_t)width * height;
     B2_REQUIRE(ctx, n < (1ull << 32), "launch too large");
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     unsigned int* counter = nullptr;
     int rc = next_counter(ctx, s, &counter);
     if (rc) return rc;

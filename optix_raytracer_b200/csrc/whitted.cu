@@ -850,7 +850,10 @@ int texture_create(b200rt_context ctx, int width, int height, const void* rgba8,
     cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
     cudaArray_t arr = nullptr;
     B2_CUDA(ctx, cudaMallocArray(&arr, &cd, width, height));
-    B2_CUDA(ctx, cudaMemcpy2DToArray(arr, 0, 0, rgba8, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice));
+    {
+        const cudaError_t e = cudaMemcpy2DToArray(arr, 0, 0, rgba8, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFreeArray(arr); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "texture upload: %s", cudaGetErrorString(e)); }
+    }
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = arr;
@@ -867,7 +870,10 @@ int texture_create(b200rt_context ctx, int width, int height, const void* rgba8,
     td.borderColor[0] = 1.0f;
     td.sRGB = 0;
     cudaTextureObject_t tex = 0;
-    B2_CUDA(ctx, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    {
+        const cudaError_t e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        if (e != cudaSuccess) { cudaFreeArray(arr); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "cudaCreateTextureObject: %s", cudaGetErrorString(e)); }
+    }
     *tex_out = (uint64_t)tex;
     *array_out = (uint64_t)(uintptr_t)arr;
     return 0;
