@@ -465,3 +465,51 @@ def test_a_million_coincident_triangles_build_and_trace(ctx, orc):
     got = host.ext_hits_to_numpy(ctx.trace_closest(accel, ctx.to_device(rays)))
     # the closest hit among equal t is the lowest ordinal: primitive 0
     assert got["t"][0] == 4.0 and got["prim"][0] == 0 and got["t"][1] < 0 and got["t"][2] == 1.0 and got["prim"][2] == 0
+
+
+def test_raycast_helper_kernels_equal_the_reference_kernels(ctx):
+    """b200rt_create_rays_ortho / b200rt_translate_rays / b200rt_shade_hits against the reference's OWN plain-CUDA
+    kernels (SDK/optixRaycasting/optixRaycastingKernels.cu:42-115), compiled where they lie with the reference's nvcc flags into
+    oracle/_ref/librefraycast.so (oracle/ref_raycast_kernels.cu): ray buffers and the shaded image are identical bit for bit, for the
+    Duck's bounding box at the sample's default width and for an awkward box / size."""
+    import ctypes as C
+    import pathlib
+    from optix_raytracer_b200 import host
+    so = pathlib.Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "librefraycast.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/librefraycast.so not built (make -C oracle needs /root/reference)")
+    ref = C.CDLL(str(so))
+    f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+    dev = ctx.torch_device
+    rng = np.random.default_rng(41)
+    sc = common.duck_scene()
+    cases = [(1040, np.asarray(sc["bbox_min"], np.float32), np.asarray(sc["bbox_max"], np.float32))] if "bbox_min" in sc else []
+    cases += [(1040, np.array([-86.3, 9.9, -61.4], np.float32), np.array([96.2, 164.0, 53.9], np.float32)),
+              (333, np.array([1e3 + 0.1, -7.77, 0.0], np.float32), np.array([1e3 + 3.3, 1.23, 1e-3], np.float32))]
+    for width, bbmin, bbmax in cases:
+        span = bbmax - bbmin
+        height = int(np.float32(width) * span[1] / span[0])
+        n = width * height
+        mine = torch.zeros((n, 8), dtype=torch.float32, device=dev)
+        theirs = torch.zeros((n, 8), dtype=torch.float32, device=dev)
+        ctx.check(ctx.lib.b200rt_create_rays_ortho(ctx.h, ctx.stream, mine.data_ptr(), width, height, f3(bbmin), f3(bbmax), 0.05), "create_rays_ortho")
+        torch.cuda.synchronize()
+        assert ref.ref_create_rays_ortho(C.c_void_p(theirs.data_ptr()), width, height, f3(bbmin), f3(bbmax), C.c_float(0.05)) == 0
+        assert torch.equal(mine.view(torch.int32), theirs.view(torch.int32)), f"createRaysOrtho differs ({width}x{height})"
+        off = (span * np.array([0.2, 0, 0], np.float32)).astype(np.float32)
+        ctx.check(ctx.lib.b200rt_translate_rays(ctx.h, ctx.stream, mine.data_ptr(), n, f3(off)), "translate_rays")
+        torch.cuda.synchronize()
+        assert ref.ref_translate_rays(C.c_void_p(theirs.data_ptr()), n, f3(off)) == 0
+        assert torch.equal(mine.view(torch.int32), theirs.view(torch.int32)), "translateRays differs"
+        # hits: a mix of misses (t = -1) and unit normals
+        hits = np.zeros((n, 4), np.float32)
+        hits[:, 0] = np.where(rng.random(n) < 0.4, -1.0, rng.random(n) * 100).astype(np.float32)
+        nrm = rng.normal(size=(n, 3)).astype(np.float32)
+        hits[:, 1:] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+        d_hits = ctx.to_device(hits)
+        img_mine = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        img_theirs = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        ctx.check(ctx.lib.b200rt_shade_hits(ctx.h, ctx.stream, img_mine.data_ptr(), n, d_hits.data_ptr()), "shade_hits")
+        torch.cuda.synchronize()
+        assert ref.ref_shade_hits(C.c_void_p(img_theirs.data_ptr()), n, C.c_void_p(d_hits.data_ptr())) == 0
+        assert torch.equal(img_mine.view(torch.int32), img_theirs.view(torch.int32)), "shadeHits differs"
