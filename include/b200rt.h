@@ -335,6 +335,14 @@ int b200rt_launch_whitted(b200rt_context ctx, b200rt_stream stream, b200rt_devic
 int b200rt_texture_create(b200rt_context ctx, int width, int height, const void* rgba8, int address_s, int address_t,
                           int linear_filter, uint64_t* texture_object, uint64_t* cuda_array);
 int b200rt_texture_destroy(b200rt_context ctx, uint64_t texture_object, uint64_t cuda_array);
+/* A texture object of ctx's device over an EXISTING CUDA array with the sampler state of b200rt_texture_create.  The array may live on
+ * another device that ctx's device has peer access to (b200rt_enable_peer_access): optixNVLink's texture sharing keeps one copy of a
+ * texture per P2P island and defines a sampler over it on every device of the island (defineTextureOnDevice / loadTexture, reference
+ * SDK/optixNVLink/optixNVLink.cpp:1446-1468,1522-1561).  Destroy with b200rt_texture_destroy(ctx, texture_object, 0): the array
+ * belongs to the context that created it.  One process drives the devices (the reference's model); CUDA arrays cannot cross
+ * processes, so with one process per GPU every rank loads its own copy. */
+int b200rt_texture_view(b200rt_context ctx, uint64_t cuda_array, int address_s, int address_t, int linear_filter,
+                        uint64_t* texture_object);
 
 /* imgui_test ("playground") launch: optixLaunch(pipeline, stream, d_param, sizeof(Params)=128, &sbt, buf_width, buf_height, 1)
  * (reference SDK/imgui_test/tracer_window.cpp:96-105) + the programs of SDK/imgui_test/optixTriangle.cu:103-268.

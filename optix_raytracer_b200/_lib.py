@@ -138,6 +138,7 @@ SYMBOLS = {
     "b200rt_launch_whitted": (i32, [vp, vp, u64, C.POINTER(ShaderBindingTable), u32, u32]),
     "b200rt_texture_create": (i32, [vp, i32, i32, vp, i32, i32, i32, C.POINTER(u64), C.POINTER(u64)]),
     "b200rt_texture_destroy": (i32, [vp, u64, u64]),
+    "b200rt_texture_view": (i32, [vp, u64, i32, i32, i32, C.POINTER(u64)]),
     "b200rt_launch_playground": (i32, [vp, vp, u64, u32, u32, C.POINTER(PTOptions)]),
     "b200rt_generate_playground_scene": (i32, [vp, vp, u32, u32, u64, u64, u64, C.POINTER(u64)]),
     "b200rt_triangle_flag_word": (u32, [u32, u32]),

@@ -357,6 +357,12 @@ int b200rt_texture_create(b200rt_context ctx, int width, int height, const void*
     return texture_create(ctx, width, height, rgba8, address_s, address_t, linear_filter, texture_object, cuda_array);
 }
 
+int b200rt_texture_view(b200rt_context ctx, uint64_t cuda_array, int address_s, int address_t, int linear_filter, uint64_t* texture_object)
+{
+    CTX_CHECK(ctx);
+    return texture_view(ctx, cuda_array, address_s, address_t, linear_filter, texture_object);
+}
+
 int b200rt_texture_destroy(b200rt_context ctx, uint64_t texture_object, uint64_t cuda_array)
 {
     CTX_CHECK(ctx);

@@ -31,6 +31,7 @@ int launch_whitted(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, cons
 void whitted_release(b200rt_context);  // destroys the context's BLEND level loop
 int texture_create(b200rt_context, int, int, const void*, int, int, int, uint64_t*, uint64_t*);
 int texture_destroy(b200rt_context, uint64_t, uint64_t);
+int texture_view(b200rt_context, uint64_t, int, int, int, uint64_t*);
 // playground.cu
 int launch_playground(b200rt_context, cudaStream_t, b200rt_deviceptr d_params, unsigned, unsigned, const b200rt_pt_options*);
 int generate_playground_scene(b200rt_context, cudaStream_t, uint32_t rows, uint32_t seed, b200rt_deviceptr, b200rt_deviceptr, b200rt_deviceptr, uint64_t*);

@@ -842,21 +842,16 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
 
 // sutil::Scene::addImage + addSampler (SDK/sutil/Scene.cpp:576-652): 8-bit RGBA image -> CUDA array -> texture object with
 // normalised coordinates, normalised-float reads, the given address modes and filter.  Returns the cudaTextureObject_t.
-int texture_create(b200rt_context ctx, int width, int height, const void* rgba8, int address_s, int address_t, int linear, uint64_t* tex_out,
-                   uint64_t* array_out)
+// A texture object of THIS context's device over an existing CUDA array — the array may live on another device the context's device
+// has peer access to: optixNVLink keeps one copy of a texture per P2P island and gives every device of the island its own sampler over
+// it (defineTextureOnDevice / loadTexture, SDK/optixNVLink/optixNVLink.cpp:1446-1468,1522-1561).  Same sampler state as texture_create.
+int texture_view(b200rt_context ctx, uint64_t cuda_array, int address_s, int address_t, int linear, uint64_t* tex_out)
 {
-    B2_REQUIRE(ctx, width > 0 && height > 0 && rgba8 && tex_out && array_out, "bad argument");
+    B2_REQUIRE(ctx, cuda_array && tex_out, "bad argument");
     DeviceGuard guard(ctx->device);
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
-    cudaArray_t arr = nullptr;
-    B2_CUDA(ctx, cudaMallocArray(&arr, &cd, width, height));
-    {
-        const cudaError_t e = cudaMemcpy2DToArray(arr, 0, 0, rgba8, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFreeArray(arr); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "texture upload: %s", cudaGetErrorString(e)); }
-    }
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = arr;
+    rd.res.array.array = (cudaArray_t)(uintptr_t)cuda_array;
     cudaTextureDesc td = {};
     td.addressMode[0] = (cudaTextureAddressMode)address_s;
     td.addressMode[1] = (cudaTextureAddressMode)address_t;
@@ -870,11 +865,26 @@ int texture_create(b200rt_context ctx, int width, int height, const void* rgba8,
     td.borderColor[0] = 1.0f;
     td.sRGB = 0;
     cudaTextureObject_t tex = 0;
-    {
-        const cudaError_t e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
-        if (e != cudaSuccess) { cudaFreeArray(arr); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "cudaCreateTextureObject: %s", cudaGetErrorString(e)); }
-    }
+    const cudaError_t e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "cudaCreateTextureObject: %s", cudaGetErrorString(e));
     *tex_out = (uint64_t)tex;
+    return 0;
+}
+
+int texture_create(b200rt_context ctx, int width, int height, const void* rgba8, int address_s, int address_t, int linear, uint64_t* tex_out,
+                   uint64_t* array_out)
+{
+    B2_REQUIRE(ctx, width > 0 && height > 0 && rgba8 && tex_out && array_out, "bad argument");
+    DeviceGuard guard(ctx->device);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    B2_CUDA(ctx, cudaMallocArray(&arr, &cd, width, height));
+    {
+        const cudaError_t e = cudaMemcpy2DToArray(arr, 0, 0, rgba8, (size_t)width * 4, (size_t)width * 4, height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFreeArray(arr); return set_error(ctx, B200RT_ERROR_CUDA_ERROR, "texture upload: %s", cudaGetErrorString(e)); }
+    }
+    const int rc = texture_view(ctx, (uint64_t)(uintptr_t)arr, address_s, address_t, linear, tex_out);
+    if (rc) { cudaFreeArray(arr); return rc; }
     *array_out = (uint64_t)(uintptr_t)arr;
     return 0;
 }

@@ -56,6 +56,10 @@ class Context:
             raise B200RTError(f"{what}: {self.lib.b200rt_error_name(rc).decode()} "
                               f"({self.lib.b200rt_last_error_message(self.h).decode()})")
 
+    def enable_peer_access(self, peer_device):
+        """enablePeerAccess (SDK/optixNVLink/optixNVLink.cpp:1852-1866): this context's device may read and write `peer_device`'s memory."""
+        self.check(self.lib.b200rt_enable_peer_access(self.h, int(peer_device)), "enable_peer_access")
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.b200rt_context_destroy(self.h)
@@ -671,6 +675,48 @@ def create_scene_textures(ctx, scene):
     return tex_objects, handles
 
 
+def create_scene_textures_shared(ctxs, scene, islands, share=True):
+    """optixNVLink's texture sharing for ONE process driving several devices (loadTextures, SDK/optixNVLink/optixNVLink.cpp:1501-1590):
+    each P2P island keeps one CUDA array per texture, on its device with the least texture memory so far; the other devices of the island
+    get their own texture object over that array (b200rt_texture_view) and sample it over NVLink.  `ctxs`: one Context per device, in
+    device order, peer access enabled inside the islands (Context.enable_peer_access).  Returns a list, one entry per context, of what
+    create_scene_textures returns: ({texture index: cudaTextureObject_t or None}, [(context, texture, array)] to destroy), plus the
+    per-device texture bytes."""
+    from . import topology
+    wrap = {10497: 0, 33071: 1, 33648: 2}
+    tex = scene.get("textures", [])
+    imgs = [scene["images"][t["source"]] if t.get("source") is not None else None for t in tex]
+    sizes = [0.0 if im is None else float(im.shape[0] * im.shape[1] * 4) for im in imgs]
+    owners, usage = topology.plan_texture_sharing(islands, sizes, len(ctxs), share)
+    out = [({}, []) for _ in ctxs]
+    for ti, (t, img) in enumerate(zip(tex, imgs)):
+        if img is None:
+            for objs, _ in out:
+                objs[ti] = None
+            continue
+        smp = scene["samplers"][t["sampler"]] if t.get("sampler") is not None and scene.get("samplers") else {}
+        linear = 0 if smp.get("magFilter") == 9728 else 1
+        ws, wt = wrap.get(smp.get("wrapS", 10497), 0), wrap.get(smp.get("wrapT", 10497), 0)
+        arrays = {}
+        for d in sorted(set(owners[ti])):   # the copies first
+            c = ctxs[d]
+            to, arr = C.c_uint64(), C.c_uint64()
+            c.check(c.lib.b200rt_texture_create(c.h, img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p), ws, wt, linear, C.byref(to), C.byref(arr)),
+                    "texture_create")
+            arrays[d] = arr.value
+            out[d][0][ti] = to.value
+            out[d][1].append((c, to.value, arr.value))
+        for d, own in enumerate(owners[ti]):  # then the views of the other devices of the island
+            if own == d:
+                continue
+            c = ctxs[d]
+            to = C.c_uint64()
+            c.check(c.lib.b200rt_texture_view(c.h, arrays[own], ws, wt, linear, C.byref(to)), "texture_view")
+            out[d][0][ti] = to.value
+            out[d][1].append((c, to.value, 0))
+    return out, usage
+
+
 def build_scene_meshes(ctx, scene, tex_objects):
     """Scene::buildMeshAccels (Scene.cpp:817-1132) + the whitted::HitGroupData payload of every primitive group: one GAS per mesh, one build
     input per primitive group with the geometry flags of its material (Scene.cpp:904-966: OPAQUE -> DISABLE_ANYHIT, MASK -> NONE, BLEND ->
@@ -1004,11 +1050,13 @@ def pack_material(m, tex_objects):
 class MeshViewer:
     """Mirror of optixMeshViewer's state for a scene dict as load_gltf returns it (textures optional: `images` entries may be None)."""
 
-    def __init__(self, ctx, scene, width, height):
+    def __init__(self, ctx, scene, width, height, textures=None):
+        """textures: (texture objects, handles) made elsewhere — create_scene_textures_shared's entry for this context — instead of a
+        private copy of every texture."""
         self.ctx, self.scene, self.width, self.height = ctx, scene, width, height
         dev = ctx.torch_device
         self.programs = ctx.prepare_programs("whitted")
-        self.tex_objects, self._tex_handles = create_scene_textures(ctx, scene)
+        self.tex_objects, self._tex_handles = textures if textures is not None else create_scene_textures(ctx, scene)
         self.mesh_accels, mesh_records, self.keep = build_scene_meshes(ctx, scene, self.tex_objects)
         # createSBT (Scene.cpp:1405-1433): per INSTANCE, per primitive group: radiance record + occlusion record (same data)
         records, inst = [], []

@@ -80,6 +80,34 @@ def island_of(islands: Sequence[int], device: int) -> int:
     return 1 << device
 
 
+def plan_texture_sharing(islands: Sequence[int], texture_bytes: Sequence[float], num_devices: int, share: bool = True):
+    """loadTextures / loadTexture / getIslandDeviceWithLowestTextureUsage (:1501-1590): where the copies of every texture go.
+    With sharing, each P2P island keeps ONE copy of a texture, on the device of the island that holds the least texture memory so far
+    (the first such device in index order), and every other device of the island samples that copy through its own texture object;
+    without, every device loads its own.  Returns (owners, usage): owners[t][d] = the device whose array device d samples for texture t
+    (d itself where it holds a copy), usage[d] = bytes of texture arrays on device d."""
+    usage = [0.0] * num_devices
+    owners = []
+    for size in texture_bytes:
+        own = [None] * num_devices
+        if share:
+            for isl in islands:
+                best, best_usage = 0, float("inf")   # the reference starts from device 0 and takes a strictly lower usage only
+                for d in range(isl.bit_length()):
+                    if isl >> d & 1 and usage[d] < best_usage:
+                        best, best_usage = d, usage[d]
+                usage[best] += size
+                for d in range(isl.bit_length()):
+                    if isl >> d & 1:
+                        own[d] = best
+        else:
+            for d in range(num_devices):
+                usage[d] += size
+                own[d] = d
+        owners.append(own)
+    return owners, usage
+
+
 def format_islands(islands: Sequence[int]) -> str:
     """printIsland's text: "P2P ISLANDS: {0,1,2,3} {4}"."""
     return "P2P ISLANDS: " + " ".join("{" + ",".join(str(b) for b in range(isl.bit_length()) if isl >> b & 1) + "}" for isl in islands)

@@ -152,6 +152,57 @@ def test_one_thread_keeps_two_devices_busy_and_the_split_frame_equals_the_whole(
         c.close()
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_textures_shared_across_a_p2p_island_render_the_same_frames():
+    """optixNVLink's texture sharing (loadTextures, SDK/optixNVLink/optixNVLink.cpp:1501-1590): one process drives two
+    devices of one P2P island, the Duck's base-colour texture lives on ONE of them (the one with the least texture memory) and the other
+    samples it over NVLink through its own texture object (b200rt_texture_view).  The viewer's frames on the device WITHOUT a copy equal,
+    bit for bit, the frames it renders from a private copy; a second texture goes to the other device (least usage)."""
+    from optix_raytracer_b200 import host, topology
+    from tests import common
+    if not (torch.cuda.can_device_access_peer(0, 1) and torch.cuda.can_device_access_peer(1, 0)):
+        pytest.skip("devices 0 and 1 have no peer access")
+    ctxs = [host.Context(d) for d in range(2)]
+    ctxs[0].enable_peer_access(1)
+    ctxs[1].enable_peer_access(0)
+    islands = topology.compute_p2p_islands(topology.peers_from_cuda(2, torch.cuda.can_device_access_peer))
+    assert islands == [0b11]
+    sc = common.duck_scene()
+    shared, usage = host.create_scene_textures_shared(ctxs, sc, islands)
+    assert usage[0] == float(sc["images"][0].size) and usage[1] == 0.0, usage     # one copy in the island, on device 0
+    assert shared[1][1][0][2] == 0 and shared[0][1][0][2] != 0                      # device 1 holds a view (no array of its own)
+    W, H = 960, 540
+    with torch.cuda.device(1):
+        mv_shared = host.MeshViewer(ctxs[1], sc, W, H, textures=shared[1])
+        mv_own = host.MeshViewer(ctxs[1], sc, W, H)
+        mv_plain = host.MeshViewer(ctxs[1], common.duck_scene(textured=False), W, H)
+        for sub in range(3):
+            for mv in (mv_shared, mv_own, mv_plain):
+                mv.launch_subframe(sub)
+        torch.cuda.synchronize(1)
+        assert torch.equal(mv_shared.frame, mv_own.frame) and torch.equal(mv_shared.accum.view(torch.int32), mv_own.accum.view(torch.int32))
+        assert not torch.equal(mv_shared.frame, mv_plain.frame), "the texture does not show in the frame: the test would not see a broken view"
+    with torch.cuda.device(0):
+        mv0 = host.MeshViewer(ctxs[0], sc, W, H, textures=shared[0])
+        for sub in range(3):
+            mv0.launch_subframe(sub)
+        torch.cuda.synchronize(0)
+        assert torch.equal(mv0.frame.cpu(), mv_own.frame.cpu())
+    # a scene with two textures: the second copy goes to the device that holds less
+    sc2 = common.duck_scene()
+    sc2["images"] = [sc2["images"][0], sc2["images"][0][::-1].copy()]
+    sc2["textures"] = [{"sampler": 0, "source": 0}, {"sampler": 0, "source": 1}]
+    shared2, usage2 = host.create_scene_textures_shared(ctxs, sc2, islands)
+    assert usage2[0] == usage2[1] > 0
+    for per_ctx in (shared[0], shared[1], shared2[0], shared2[1]):
+        for c, tex, arr in per_ctx[1]:
+            c.lib.b200rt_texture_destroy(c.h, tex, arr)
+    for mv in (mv_own, mv_plain):
+        mv.close()
+    for c in ctxs:
+        c.close()
+
+
 def test_accel_build_and_compact_do_not_wait_for_the_device():
     """optixAccelBuild / optixAccelCompact are asynchronous: the level and clustering loops run on the device (CUDA graphs)."""
     from optix_raytracer_b200 import host, _lib as L

@@ -27,3 +27,20 @@ def test_peers_from_nvlink_links_bridge_and_switch():
     assert peers == [0b010, 0b001, 0]
     assert T.compute_p2p_islands(peers) == [0b011, 0b100]
     assert T.compute_p2p_islands(T.peers_from_links(ids, sw, require_nvlink=False)) == [0b111]
+
+
+def test_texture_sharing_plan_follows_optixNVLink():
+    """loadTexture / getIslandDeviceWithLowestTextureUsage (SDK/optixNVLink/optixNVLink.cpp:1501-1561): one copy per island on the device
+    with the least texture memory so far (the first such device; the scan starts from device 0 with a strict comparison), views for the
+    rest of the island; without sharing every device loads its own."""
+    islands = [0b0011, 0b1100]
+    owners, usage = T.plan_texture_sharing(islands, [4.0, 4.0, 2.0], 4)
+    assert owners == [[0, 0, 2, 2], [1, 1, 3, 3], [0, 0, 2, 2]]
+    assert usage == [6.0, 4.0, 6.0, 4.0]
+    owners, usage = T.plan_texture_sharing([0b1111], [1.0] * 5, 4)
+    assert [o[0] for o in owners] == [0, 1, 2, 3, 0] and usage == [2.0, 1.0, 1.0, 1.0]
+    owners, usage = T.plan_texture_sharing(islands, [4.0, 4.0], 4, share=False)
+    assert owners == [[0, 1, 2, 3]] * 2 and usage == [8.0] * 4
+    # a lone device is its own island
+    owners, usage = T.plan_texture_sharing([0b011, 0b100], [3.0], 3)
+    assert owners == [[0, 0, 2]] and usage == [3.0, 0.0, 3.0]
