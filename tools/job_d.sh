@@ -1,2 +1,7 @@
-B200RT_PT_HOST_LOOP=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:pt_trace --csv --log-file gpurun_out/trace_dram_r02.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/trace_dram_r02.log 2>&1
-grep -c pt_trace gpurun_out/trace_dram_r02.csv
+( time python -c "import __graft_entry__ as g; g.smoke()" ) 2>&1 | tail -5
+( time python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2>&1 | tail -3
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'], d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['build']['ms'], d['gpu_launches'], d['clocks'])"
+( time python bench.py --impl reference > gpurun_out/bench_default_ref.json 2> gpurun_out/bench_default_ref.err ) 2>&1 | tail -3
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_default_ref.json').read().strip().splitlines()[-1]); print(d['impl'], d['reference_class'], d['value'], d['e2e']['value'])"
