@@ -528,13 +528,14 @@ int radix_sort_pairs32(b200rt_context ctx, cudaStream_t s, uint32_t* keys[2], ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4. Radix tree.  Node ids: internal p in [0, N-1) is the node whose split lies between sorted positions p and p + 1; the leaf at
-// sorted position s is (N-1)+s.
+// 4. Karras hierarchy.  Node ids: internal i in [0, N-1), leaf at sorted position s is (N-1)+s.
 // ---------------------------------------------------------------------------------------------
-// length of the common prefix of two (key, position) pairs: Karras's delta, equal keys told apart by their positions
-__device__ __forceinline__ int prefix_len(uint64_t ka, uint64_t kb, int ia, int ib)
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j)
 {
-    return ka != kb ? __clzll((long long)(ka ^ kb)) : 64 + __clz((uint32_t)ia ^ (uint32_t)ib);
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
 }
 
 // Boxes of the binary hierarchy: {lo.xyz, left child} {hi.xyz, right child} of node id side by side (32 bytes, one DRAM sector), reached
@@ -570,31 +571,21 @@ __device__ __forceinline__ float child_word_hi(int right, int leaves) { return _
 // children of a node leave their far bounds for each other.  A subtree of two or three leaves starts at the sorted position its left
 // child names (a leaf's own position; an inner left child of two leaves [q, q + 1] is node q): the collapse reads it from there
 // (collapse_emit_kernel).
-constexpr uint32_t ARRIVED = 0x80000000u;
-constexpr int RT_CHUNK = 256;   // leaves per CTA of radix_tree_kernel = its block size
-
-// Chunk-local fast path.  A CTA owns the leaves [lo, hi) of one chunk.  A node whose whole range lies inside the chunk — true for all but
-// a handful of the chunk's 255 splits — is only ever visited by threads of this CTA, so its two children meet through SHARED memory
-// (ids, far bounds, arrival word, and the boxes of every leaf and node of the chunk): block-scope fence, shared-memory exchange, no
-// global round trips.  Whether node p's range stays inside the chunk follows from the keys alone: the range is every leaf sharing the
-// prefix of (p, p + 1), so it is inside iff neither the leaf before the chunk nor the leaf after it shares that prefix.  Nodes that
-// reach across chunks take the global path of the comment above.  Every node's box still goes to global memory once (the collapse
-// reads it); what disappears is the 150 B per node of exchange traffic and the chain of ~1 us round trips per level: 4.34 -> 1.9 ms for
-// 50 M triangles (profiles/r02_build.md).
-__global__ void __launch_bounds__(RT_CHUNK) radix_tree_kernel(const uint64_t* __restrict__ keys, const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
-                                                               const BoxArr box_lo, const BoxArr box_hi, int2* range, uint32_t* arrive, uint8_t* __restrict__ height,
-                                                               uint32_t* __restrict__ root_out)
+__device__ __forceinline__ bool split_less(const uint64_t* __restrict__ keys, int a, int b)  // is the key step at position a smaller than the one at b?
 {
-    __shared__ float s_box[2 * RT_CHUNK][6];   // [0, CHUNK): leaves by position - lo; [CHUNK, 2 CHUNK): nodes by split - lo
-    __shared__ int s_child[RT_CHUNK][2];       // what the left / right child left for its sibling: its node id ...
-    __shared__ int s_bound[RT_CHUNK][2];       // ... and its far bound
-    __shared__ unsigned int s_arrive[RT_CHUNK];
-    const int lo = blockIdx.x * RT_CHUNK, hi = min(lo + RT_CHUNK, n);
-    s_arrive[threadIdx.x] = 0u;
-    __syncthreads();
-    const int s = lo + (int)threadIdx.x;
+    const uint64_t xa = __ldg(keys + a) ^ __ldg(keys + a + 1), xb = __ldg(keys + b) ^ __ldg(keys + b + 1);
+    if (xa != xb) return xa < xb;
+    return (uint32_t)(a ^ (a + 1)) < (uint32_t)(b ^ (b + 1));  // both steps zero (duplicate keys): the positions decide, as in Karras's delta
+}
+
+constexpr uint32_t ARRIVED = 0x80000000u;
+
+__global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, const float4* __restrict__ tri_tmp, const uint32_t* __restrict__ vals, int n,
+                                                          const BoxArr box_lo, const BoxArr box_hi, int2* range, uint32_t* arrive, uint8_t* __restrict__ height,
+                                                          uint32_t* __restrict__ root_out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const uint64_t key_before = lo > 0 ? __ldg(keys + lo - 1) : 0ull, key_after = hi < n ? __ldg(keys + hi) : 0ull;
     const size_t g = vals[s];
     const float4 a = tri_tmp[3 * g], b = tri_tmp[3 * g + 1], c = tri_tmp[3 * g + 2];
     float lx = fminf(a.x, fminf(b.x, c.x)), ly = fminf(a.y, fminf(b.y, c.y)), lz = fminf(a.z, fminf(b.z, c.z));
@@ -602,65 +593,29 @@ __global__ void __launch_bounds__(RT_CHUNK) radix_tree_kernel(const uint64_t* __
     int id = n - 1 + s, l = s, r = s, h = 0;
     box_lo[id] = make_float4(lx, ly, lz, 0.f);
     box_hi[id] = make_float4(hx, hy, hz, 0.f);
-    {
-        volatile float* sb = s_box[threadIdx.x];
-        sb[0] = lx; sb[1] = ly; sb[2] = lz; sb[3] = hx; sb[4] = hy; sb[5] = hz;
-    }
     for (;;) {
         if (l == 0 && r == n - 1) { *root_out = (uint32_t)id; return; }
-        // parent: the neighbouring split whose keys differ least (the longer common prefix)
-        bool left_child;
-        uint64_t kp, kp1;   // keys on the two sides of the parent's split
-        if (l == 0) { left_child = true; kp = __ldg(keys + r); kp1 = __ldg(keys + r + 1); }
-        else if (r == n - 1) { left_child = false; kp = __ldg(keys + l - 1); kp1 = __ldg(keys + l); }
-        else {
-            const uint64_t kr = __ldg(keys + r), kr1 = __ldg(keys + r + 1), kl1 = __ldg(keys + l - 1), kl = __ldg(keys + l);
-            left_child = prefix_len(kr, kr1, r, r + 1) > prefix_len(kl1, kl, l - 1, l);   // never equal for a valid range
-            kp = left_child ? kr : kl1; kp1 = left_child ? kr1 : kl;
-        }
+        const bool left_child = l == 0 || (r != n - 1 && split_less(keys, r, l - 1));
         const int p = left_child ? r : l - 1;
-        const int dnode = prefix_len(kp, kp1, p, p + 1);
-        const bool local = p >= lo && p + 1 < hi && (lo == 0 || prefix_len(key_before, kp, lo - 1, p) < dnode) && (hi == n || prefix_len(kp, key_after, p, hi) < dnode);
-        int sib, far;
-        float slx, sly, slz, shx, shy, shz;
-        uint32_t old;
-        if (local) {
-            const int q = p - lo, side = left_child ? 0 : 1;
-            ((volatile int*)s_child[q])[side] = id;
-            ((volatile int*)s_bound[q])[side] = left_child ? l : r;
-            __threadfence_block();
-            old = atomicExch(&s_arrive[q], ARRIVED | (uint32_t)h);
-            if (!(old & ARRIVED)) return;  // first arrival: the sibling's thread will carry on
-            sib = ((volatile int*)s_child[q])[side ^ 1];
-            far = ((volatile int*)s_bound[q])[side ^ 1];
-            const volatile float* sb = s_box[sib >= n - 1 ? sib - (n - 1) - lo : RT_CHUNK + sib - lo];
-            slx = sb[0]; sly = sb[1]; slz = sb[2]; shx = sb[3]; shy = sb[4]; shz = sb[5];
-        } else {
-            // what the sibling needs from this subtree: its node id (into the parent's child slot) and its far bound
-            volatile float* slot_w = &(left_child ? box_lo[p] : box_hi[p]).w;
-            volatile int* bound = left_child ? &range[p].x : &range[p].y;
-            *slot_w = __int_as_float(id);
-            *bound = left_child ? l : r;
-            __threadfence();
-            old = atomicExch(&arrive[p], ARRIVED | (uint32_t)h);
-            if (!(old & ARRIVED)) return;  // first arrival: the sibling subtree is not finished yet, its thread will carry on
-            // second arrival: the sibling's stores are visible (its fence precedes its exchange); read them past the L1
-            sib = __float_as_int(__ldcg(&(left_child ? box_hi[p] : box_lo[p]).w));
-            far = __ldcg(left_child ? &range[p].y : &range[p].x);
-            const float4 slo = __ldcg(&box_lo[sib]), shi = __ldcg(&box_hi[sib]);
-            slx = slo.x; sly = slo.y; slz = slo.z; shx = shi.x; shy = shi.y; shz = shi.z;
-        }
-        lx = fminf(lx, slx); ly = fminf(ly, sly); lz = fminf(lz, slz);
-        hx = fmaxf(hx, shx); hy = fmaxf(hy, shy); hz = fmaxf(hz, shz);
+        // what the sibling needs from this subtree: its node id (into the parent's child slot) and its far bound
+        volatile float* slot_w = &(left_child ? box_lo[p] : box_hi[p]).w;
+        volatile int* bound = left_child ? &range[p].x : &range[p].y;
+        *slot_w = __int_as_float(id);
+        *bound = left_child ? l : r;
+        __threadfence();
+        const uint32_t old = atomicExch(&arrive[p], ARRIVED | (uint32_t)h);
+        if (!(old & ARRIVED)) return;  // first arrival: the sibling subtree is not finished yet, its thread will carry on
+        // second arrival: the sibling's stores are visible (its fence precedes its exchange); read them past the L1
+        const int sib = __float_as_int(__ldcg(&(left_child ? box_hi[p] : box_lo[p]).w));
+        const int far = __ldcg(left_child ? &range[p].y : &range[p].x);
+        const float4 slo = __ldcg(&box_lo[sib]), shi = __ldcg(&box_hi[sib]);
+        lx = fminf(lx, slo.x); ly = fminf(ly, slo.y); lz = fminf(lz, slo.z);
+        hx = fmaxf(hx, shi.x); hy = fmaxf(hy, shi.y); hz = fmaxf(hz, shi.z);
         h = min(max(h, (int)(old & 0xffu)) + 1, 255);
         if (left_child) r = far; else l = far;
         box_lo[p] = make_float4(lx, ly, lz, child_word_lo(left_child ? id : sib, r - l + 1));
         box_hi[p] = make_float4(hx, hy, hz, child_word_hi(left_child ? sib : id, r - l + 1));
         height[p] = (uint8_t)h;   // subtree height (edges to the deepest leaf): what the collapse's depth guard reads
-        if (p >= lo && p < lo + RT_CHUNK) {
-            volatile float* sb = s_box[RT_CHUNK + p - lo];
-            sb[0] = lx; sb[1] = ly; sb[2] = lz; sb[3] = hx; sb[4] = hy; sb[5] = hz;
-        }
         id = p;
     }
 }
@@ -1487,7 +1442,7 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
                 ctx->launches += 1;
             } else {
                 B2_CUDA(ctx, cudaMemsetAsync(arrive, 0, 4 * (size_t)N, s));
-                radix_tree_kernel<<<div_up(N, RT_CHUNK), RT_CHUNK, 0, s>>>(keys[cur], tri_tmp, vals[cur], (int)N, box_lo, box_hi, range, arrive, height, d_root);
+                radix_tree_kernel<<<div_up(N, 256), 256, 0, s>>>(keys[cur], tri_tmp, vals[cur], (int)N, box_lo, box_hi, range, arrive, height, d_root);
                 B2_LAUNCH_CHECK(ctx);
             }
             mark();  // leaf boxes + binary hierarchy
