@@ -602,8 +602,7 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
         volatile int* bound = left_child ? &range[p].x : &range[p].y;
         *slot_w = __int_as_float(id);
         *bound = left_child ? l : r;
-        __threadfence();
-        const uint32_t old = atomicExch(&arrive[p], ARRIVED | (uint32_t)h);
+        const uint32_t old = atomic_exch_release(&arrive[p], ARRIVED | (uint32_t)h);   // release: the two stores above are visible first (common.h)
         if (!(old & ARRIVED)) return;  // first arrival: the sibling subtree is not finished yet, its thread will carry on
         // second arrival: the sibling's stores are visible (its fence precedes its exchange); read them past the L1
         const int sib = __float_as_int(__ldcg(&(left_child ? box_hi[p] : box_lo[p]).w));

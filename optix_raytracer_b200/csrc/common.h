@@ -119,4 +119,24 @@ struct DeviceGuard {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline unsigned int div_up(size_t n, size_t d) { return (unsigned int)((n + d - 1) / d); }
 
+#ifdef __CUDACC__
+// Release-ordered atomics for "write a result, then count yourself in" protocols.  __threadfence() is fence.sc.gpu, which on sm_100 is
+// MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL — it invalidates the SM's WHOLE L1 every time (in a traversal kernel: the BVH nodes of every warp
+// on the SM; in the tree builder: 7 GB of keys re-read from DRAM and a kernel that ran 6 ms instead of 1).  A release on the atomic is
+// all such a protocol needs from the writer (MEMBAR.ALL.GPU, no invalidation); the reader that takes the last ticket reads the others'
+// results past the L1 (__ldcg / volatile), behind the control dependency on the ticket.
+__device__ __forceinline__ unsigned int atomic_exch_release(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.release.gpu.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned int atomic_add_release(unsigned int* p, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+#endif
+
 }  // namespace b200rt

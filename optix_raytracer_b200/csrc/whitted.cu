@@ -580,9 +580,9 @@ struct WShadowWork {
     {
         // occluded -> the attenuation is never committed (0), else the pending product (whitted_cuda.h:155-158)
         if (li < nl) k.att[(size_t)slot * nl + li] = found ? 0.0f : (float)att;
-        __threadfence();
-        if (atomicAdd(&k.arrived[slot], 1u) != per_slot - 1u) return;
-        __threadfence();
+        // release on the ticket (no __threadfence: it would invalidate the L1 the traversal lives in, common.h); the last item reads the
+        // others' attenuations with volatile loads, behind the control dependency on its ticket
+        if (atomic_add_release(&k.arrived[slot], 1u) != per_slot - 1u) return;
         // last item of the slot: result += light.color * attenuation * intensity * N_dot_L * (diff + spec) in light order (whitted.cu:249-256)
         const float4 b = k.base[slot];
         float3 result = f3(b.x, b.y, b.z);
