@@ -1097,17 +1097,17 @@ class MeshViewer:
         self.frame = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
         self.params = WLaunchParams(width, height, 0, self.accum.data_ptr(), self.frame.data_ptr(), 0, 0.0, _f3(self.eye), _f3(U), _f3(V), _f3(W),
                                     self.d_lights.data_ptr(), 2, 0, 0, _f3([0.1, 0.1, 0.1]), self.ias.handle)
-        self.h_params = torch.empty(128, dtype=torch.uint8).pin_memory()
-        self.d_params = torch.empty(128, dtype=torch.uint8, device=dev)
+        self.uploader = ParamsUploader(128, dev)
+        self.d_params = self.uploader.d
 
     def launch_subframe(self, subframe_index=None):
         """launchSubframe (optixMeshViewer.cpp:283-308)."""
         if subframe_index is not None:
             self.params.subframe_index = subframe_index
-        # pageable source, like the reference's cudaMemcpyAsync(d_params, &params, ...) (optixMeshViewer.cpp:289-293): the runtime stages it
-        # before returning, so the host may change `params` for the next subframe while this launch is still queued (whitted launches do
-        # not synchronise the stream)
-        self.d_params.copy_(torch.from_numpy(np.frombuffer(bytes(self.params), np.uint8).copy()))
+        # the reference's cudaMemcpyAsync(d_params, &params, ...) (optixMeshViewer.cpp:289-293) from a ring of pinned staging blocks: the host
+        # may change `params` for the next subframe while this launch is still queued, and nothing here waits for the device (a torch copy
+        # from pageable memory synchronises the stream)
+        self.uploader.upload(self.params)
         self.ctx.launch_whitted(self.programs, self.d_params.data_ptr(), 128, self.sbt, self.width, self.height)
 
     def close(self):
