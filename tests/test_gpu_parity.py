@@ -513,3 +513,39 @@ def test_raycast_helper_kernels_equal_the_reference_kernels(ctx):
         torch.cuda.synchronize()
         assert ref.ref_shade_hits(C.c_void_p(img_theirs.data_ptr()), n, C.c_void_p(d_hits.data_ptr())) == 0
         assert torch.equal(img_mine.view(torch.int32), img_theirs.view(torch.int32)), "shadeHits differs"
+
+
+def test_empty_and_tiny_inputs(ctx, orc):
+    """The sizes no sample uses but a drop-in has to survive: a GAS without triangles (every ray misses, nothing is occluded), a ray
+    buffer without rays, an IAS without instances, and GAS of one / two / three triangles (root = leaf; the smallest inner nodes) on both
+    hierarchies — hit records equal the oracle's."""
+    from optix_raytracer_b200 import host
+    rng = np.random.default_rng(3)
+    rays = common.random_rays(rng, 4096, [-2, -2, -2], [2, 2, 2])
+    d_rays = ctx.to_device(rays)
+    empty = ctx.build_accel([ctx.triangle_input(torch.zeros((0, 3), dtype=torch.float32, device=ctx.torch_device), vertex_stride=12)])
+    assert empty.info().num_triangles == 0
+    got = host.ext_hits_to_numpy(ctx.trace_closest(empty, d_rays))
+    assert (got["t"] < 0).all() and not ctx.trace_any(empty, d_rays).cpu().numpy().any()
+    ias0 = ctx.build_accel([ctx.instance_input([])], compact=False)
+    assert (host.ext_hits_to_numpy(ctx.trace_closest(ias0, d_rays))["t"] < 0).all()
+    none = ctx.to_device(np.zeros((0, 8), np.float32))
+    for n in (1, 2, 3, 5):
+        c = rng.random((n, 1, 3), dtype=np.float32) * 2 - 1
+        tris = (c + (rng.random((n, 3, 3), dtype=np.float32) - 0.5) * 1.5).astype(np.float32)
+        scene = orc.Scene(tris)
+        ref = scene.trace(rays)
+        for hier in ("lbvh", "ploc"):
+            import os
+            os.environ["B200RT_HIERARCHY"] = hier
+            try:
+                acc = ctx.build_accel([ctx.triangle_input(ctx.to_device(tris.reshape(-1, 3)), vertex_stride=12)])
+            finally:
+                os.environ.pop("B200RT_HIERARCHY", None)
+            _assert_hits_equal(host.ext_hits_to_numpy(ctx.trace_closest(acc, d_rays)), ref, f"{n} triangles, {hier}")
+            assert ctx.trace_closest(acc, none).shape[0] == 0
+            ias = ctx.build_accel([ctx.instance_input([(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), 0, acc), (np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), 0, empty)])],
+                                  compact=False)
+            got = host.ext_hits_to_numpy(ctx.trace_closest(ias, d_rays))
+            assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32)), f"{n} triangles instanced next to an empty GAS"
+        assert (ref["t"] >= 0).any()
