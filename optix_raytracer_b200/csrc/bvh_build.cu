@@ -1329,8 +1329,9 @@ int accel_build(b200rt_context ctx, cudaStream_t s, const b200rt_accel_build_opt
             const auto& t = inputs[i].triangleArray;
             DevInput& d = dev[i];
             memset(&d, 0, sizeof(d));
-            B2_REQUIRE(ctx, t.vertexBuffers && t.vertexBuffers[0], "build input %u: null vertex buffer", i);
-            d.verts = (const char*)t.vertexBuffers[0];
+            // an input without triangles may come with a null buffer (an empty cudaMalloc / tensor); one with triangles may not
+            B2_REQUIRE(ctx, count_tris(t) == 0 || (t.vertexBuffers && t.vertexBuffers[0]), "build input %u: null vertex buffer", i);
+            d.verts = t.vertexBuffers ? (const char*)t.vertexBuffers[0] : nullptr;
             d.vstride = t.vertexStrideInBytes ? t.vertexStrideInBytes : 12u;
             const bool indexed = t.indexFormat != B200RT_INDICES_FORMAT_NONE && t.indexBuffer;
             d.indices = indexed ? (const char*)t.indexBuffer : nullptr;
