@@ -367,8 +367,8 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
                 const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
                 const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
                 if (cmin <= cmax * BOX_SLACK) {
-                    const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
-                    const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+                    const uint32_t cb = __byte_perm(child_bits4, 0u, 0x4440u | (uint32_t)j);   // byte j, one PRMT (the shift-and-mask form is two instructions)
+                    const uint32_t bi = __byte_perm(bit_index4, 0u, 0x4440u | (uint32_t)j);
                     hitmask |= cb << bi;
                 }
             }
@@ -426,8 +426,8 @@ __device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
             if (cmin <= cmax * BOX_SLACK) {
-                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
-                const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+                const uint32_t cb = __byte_perm(child_bits4, 0u, 0x4440u | (uint32_t)j);   // byte j, one PRMT (the shift-and-mask form is two instructions)
+                const uint32_t bi = __byte_perm(bit_index4, 0u, 0x4440u | (uint32_t)j);
                 hitmask |= cb << bi;
             }
         }
