@@ -284,12 +284,16 @@ __global__ void __launch_bounds__(256) pt_init_kernel(const void* __restrict__ p
 // then pending shadow rays (any-hit).  Every item is a ray, so a refill never comes back empty-handed.
 // The launches take a GAS handle (the reference pipelines are built with OPTIX_TRAVERSABLE_GRAPH_FLAG_ALLOW_SINGLE_GAS,
 // optixPathTracer.cpp:702 / optixMultiGPU.cpp:794); an IAS handle is traversed instance by instance all the same.
+#ifndef B200RT_PT_SMEM_STACK
+#define B200RT_PT_SMEM_STACK 0   // bottom entries of the traversal stack kept in shared memory (trav_coop.cuh: TStack)
+#endif
 template <int MODE>
 struct PTWork {
     static constexpr bool CONTINUES = false;
     static constexpr bool NODE_POLICY = B200RT_NODE_KEEP_MB > 0;
     __device__ __forceinline__ uint64_t node_policy() const { return node_policy_for(f.handle); }
     static constexpr bool ANYHIT = false;  // the Cornell programs have no any-hit (optixPathTracer.cpp:748-767)
+    static constexpr int SMEM_STACK = B200RT_PT_SMEM_STACK;
     const Frame& f;
     const Lanes& L;
     uint32_t n_ext;

@@ -125,6 +125,15 @@ __device__ __forceinline__ uint4 node_load(const uint4* p, uint64_t pol)
     }
 }
 
+// Prefetches into L2 for the scene that lives in HBM (Node8 hierarchies): see trav_node_step_q8 and the parking of triangle groups.
+#ifndef B200RT_SIB_PREFETCH
+#define B200RT_SIB_PREFETCH 0   // sectors asked for per deferred sibling node: 1 = first, 2 = first and last, 3 = all three of the 80 bytes
+#endif
+#ifndef B200RT_TRI_PREFETCH
+#define B200RT_TRI_PREFETCH 0   // 1: the first and the last record of a parked triangle group; 2: every 64 bytes of the span (at most 4)
+#endif
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct Trav {
     const uint4* nodes;
     const float4* tris;     // unused (and dead) in kernels that keep it in the lane's shared slot (SMEM_STATE)
@@ -147,29 +156,50 @@ struct Trav {
 // the entry below, which has the whole next node visit to arrive; a push stores the old top and keeps the new one.  Measured on the
 // bench: 2083 -> 1931 Mrays/s — under the 64-register cap of 8 CTAs per SM the kernel spills 190 instead of 10 bytes per thread, which
 // costs more than the exposed pop.  Off by default; the helpers keep both forms.
-__device__ __forceinline__ void stack_push(Trav& s, uint2* __restrict__ stack, uint2 e)
+// The stack itself: entries [0, NS) live in shared memory (one column per thread, rows COOP_BLOCK apart: conflict-free 64-bit accesses),
+// the rest in local memory.  NS = 0: all of it in local memory.  A pop from local memory goes through the node-filled L1 and misses it
+// more often than not; a pop from shared memory takes a fixed ~25 cycles and leaves the L1 to the nodes (Work::SMEM_STACK).
+template <int NS>
+struct TStack {
+    uint2 loc[TRAV_STACK - NS];
+    uint2* shm;
+    __device__ __forceinline__ void put(int i, uint2 e)
+    {
+        if (NS > 0 && i < NS) shm[i * COOP_BLOCK] = e;
+        else loc[i - NS] = e;
+    }
+    __device__ __forceinline__ uint2 get(int i) const
+    {
+        if (NS > 0 && i < NS) return shm[i * COOP_BLOCK];
+        return loc[i - NS];
+    }
+};
+template <int NS>
+__device__ __forceinline__ void stack_push(Trav& s, TStack<NS>& stack, uint2 e)
 {
 #if B200RT_STACK_TOP
-    if (s.sp > 0) stack[s.sp - 1] = s.top;
+    if (s.sp > 0) stack.put(s.sp - 1, s.top);
     s.top = e;
     ++s.sp;
 #else
-    stack[s.sp++] = e;
+    stack.put(s.sp++, e);
 #endif
 }
-__device__ __forceinline__ uint2 stack_peek(const Trav& s, const uint2* __restrict__ stack)
+template <int NS>
+__device__ __forceinline__ uint2 stack_peek(const Trav& s, const TStack<NS>& stack)
 {
 #if B200RT_STACK_TOP
     return s.top;
 #else
-    return stack[s.sp - 1];
+    return stack.get(s.sp - 1);
 #endif
 }
-__device__ __forceinline__ void stack_drop(Trav& s, const uint2* __restrict__ stack)  // remove the top entry
+template <int NS>
+__device__ __forceinline__ void stack_drop(Trav& s, const TStack<NS>& stack)  // remove the top entry
 {
     --s.sp;
 #if B200RT_STACK_TOP
-    if (s.sp > 0) s.top = stack[s.sp - 1];
+    if (s.sp > 0) s.top = stack.get(s.sp - 1);
 #endif
 }
 
@@ -312,17 +342,28 @@ __device__ __forceinline__ bool trav_begin_handle(Trav& s, float* __restrict__ m
 }
 
 // One node visit; returns the triangle group of the visited node (mask 0 = none).
-template <bool POLICY = false>
-__device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ stack, TravStats* st, uint64_t pol = 0)
+template <bool POLICY = false, int NS = 0>
+__device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, TStack<NS>& stack, TravStats* st, uint64_t pol = 0)
 {
     const uint32_t hits_imask = s.ngroup.y;
     const uint32_t bit = 31u - __clz(hits_imask);
     const uint32_t child_base = s.ngroup.x;
     s.ngroup.y &= ~(1u << bit);
+    const uint32_t octinv = (s.pack >> 8) & 7u;
     if (s.ngroup.y & NODE_BITS) {
         if (s.sp < TRAV_STACK) stack_push(s, stack, s.ngroup);
+#if B200RT_SIB_PREFETCH
+        // The group's next child WILL be visited (a popped group's best child is fetched without another look at its distance), but only
+        // after the whole subtree entered now: its node is asked into L2 here, a subtree's time ahead of the fetch.
+        const uint32_t bit2 = 31u - __clz(s.ngroup.y);
+        const uint32_t slot2 = (bit2 - 24u) ^ octinv;
+        const uint32_t rel2 = __popc(hits_imask & ~(0xffffffffu << slot2));
+        const char* pp = (const char*)(s.nodes + (size_t)(child_base + rel2) * 5u);
+        prefetch_l2_line(pp);
+        if (B200RT_SIB_PREFETCH >= 2) prefetch_l2_line(pp + 64);
+        if (B200RT_SIB_PREFETCH >= 3) prefetch_l2_line(pp + 32);
+#endif
     }
-    const uint32_t octinv = (s.pack >> 8) & 7u;
     const uint32_t slot = (bit - 24u) ^ octinv;
     const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot));
     const uint4* np = s.nodes + (size_t)(child_base + rel) * 5u;
@@ -380,7 +421,8 @@ __device__ __forceinline__ uint2 trav_node_step_q8(Trav& s, uint2* __restrict__ 
 
 // Node8F visit: the child planes are fp32 offsets from the node origin, stored plane-major; the near / far plane arrays are picked
 // by ADDRESS from the ray's direction signs, so there is neither a decode nor a select per plane — 6 FFMA + 4 FMNMX per child.
-__device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__ stack, TravStats* st)
+template <int NS = 0>
+__device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, TStack<NS>& stack, TravStats* st)
 {
     const uint32_t hits_imask = s.ngroup.y;
     const uint32_t bit = 31u - __clz(hits_imask);
@@ -436,10 +478,10 @@ __device__ __forceinline__ uint2 trav_node_step_f32(Trav& s, uint2* __restrict__
     return make_uint2(n1.y, hitmask & 0x00ffffffu);
 }
 
-template <bool POLICY = false>
-__device__ __forceinline__ uint2 trav_node_step(Trav& s, uint2* __restrict__ stack, TravStats* st, uint64_t pol = 0)
+template <bool POLICY = false, int NS = 0>
+__device__ __forceinline__ uint2 trav_node_step(Trav& s, TStack<NS>& stack, TravStats* st, uint64_t pol = 0)
 {
-    return (s.pack & TP_F32) ? trav_node_step_f32(s, stack, st) : trav_node_step_q8<POLICY>(s, stack, st, pol);
+    return (s.pack & TP_F32) ? trav_node_step_f32<NS>(s, stack, st) : trav_node_step_q8<POLICY, NS>(s, stack, st, pol);
 }
 
 // TERMINATE_ON_FIRST_HIT rays stop at the first accepted hit: no further instance is traversed
@@ -494,10 +536,19 @@ template <class Work, class = void> struct CoopHasSmemState { static constexpr b
 template <class Work> struct CoopHasSmemState<Work, decltype((void)Work::SMEM_STATE)> { static constexpr bool value = Work::SMEM_STATE; };
 template <class Work> constexpr bool coop_smem_state() { return CoopHasSmemState<Work>::value; }
 
+//   static constexpr int SMEM_STACK (optional)                     entries of the traversal stack kept in shared memory (TStack)
+template <class Work, class = void> struct CoopHasSmemStack { static constexpr int value = 0; };
+template <class Work> struct CoopHasSmemStack<Work, decltype((void)Work::SMEM_STACK)> { static constexpr int value = Work::SMEM_STACK; };
+template <class Work> constexpr int coop_smem_stack() { return CoopHasSmemStack<Work>::value; }
+template <int NS> struct CoopSharedStack { uint2 e[NS][COOP_BLOCK]; };
+template <> struct CoopSharedStack<0> {};
+
 template <class Work>
 __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, unsigned int* __restrict__ fetch_counter, TravStats* st)
 {
     constexpr bool SM = coop_smem_state<Work>();
+    constexpr int NS = coop_smem_stack<Work>();
+    __shared__ CoopSharedStack<NS> shs;
     constexpr int RAY_S_STRIDE = ray_s_stride<SM>();
     __shared__ CoopShared<RAY_S_STRIDE> sh;
     __shared__ CoopSharedAnyHit<Work::ANYHIT> sha;
@@ -511,7 +562,8 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     float* my_ray = &sh.ray[wid][lane * RAY_S_STRIDE];
-    uint2 stack[TRAV_STACK];
+    TStack<NS> stack;
+    if constexpr (NS > 0) stack.shm = &shs.e[0][threadIdx.x];
     Trav s;
     s.tgroup = make_uint2(0u, 0u);
     s.ngroup = make_uint2(0u, 0u);
@@ -589,12 +641,12 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                     if (e.y & NODE_BITS) { s.ngroup = e; stack_drop(s, stack); break; }
                     if (s.tgroup.y == 0u) { s.tgroup = e; stack_drop(s, stack); continue; }
                     if (B200RT_LOOKTHROUGH && s.sp >= 2) {
-                        const uint2 below = stack[s.sp - 2];
+                        const uint2 below = stack.get(s.sp - 2);
                         if (below.y & NODE_BITS) {
                             // take the node group from under the triangle group, which stays on top
                             s.ngroup = below;
 #if !B200RT_STACK_TOP
-                            stack[s.sp - 2] = e;
+                            stack.put(s.sp - 2, e);
 #endif
                             --s.sp;
                             break;
@@ -612,8 +664,24 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
             __syncwarp();
             // ---- phase B: one node visit for every lane that has node work
             if (has && (s.ngroup.y & NODE_BITS)) {
-                const uint2 nt = trav_node_step<NODE_POLICY>(s, stack, st, node_pol);
+                const uint2 nt = trav_node_step<NODE_POLICY, NS>(s, stack, st, node_pol);
                 if (nt.y) {
+#if B200RT_TRI_PREFETCH
+                    // the parked group's records are read by other lanes, several node visits from now: ask them into L2 meanwhile
+                    if (tri_stream) {
+                        const uint32_t hi = 31u - __clz(nt.y), lo = (uint32_t)__ffs((int)nt.y) - 1u;
+                        const char* t0 = (const char*)(lane_tris<SM>(s, my_ray) + (size_t)(nt.x + lo) * 3u);
+                        const uint32_t span = (hi - lo) * 48u + 48u;   // bytes from the first record's start to the last one's end
+                        prefetch_l2_line(t0);
+                        if (B200RT_TRI_PREFETCH == 1) {
+                            prefetch_l2_line(t0 + span - 16u);
+                        } else {
+                            if (span > 64u) prefetch_l2_line(t0 + 64);
+                            if (span > 128u) prefetch_l2_line(t0 + 128);
+                            prefetch_l2_line(t0 + span - 16u);
+                        }
+                    }
+#endif
                     if (s.tgroup.y == 0u) s.tgroup = nt;
                     else if (s.sp < TRAV_STACK) stack_push(s, stack, nt);  // second parked group: goes on the stack (no NODE_BITS marks it)
                     else {
@@ -740,6 +808,23 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
     }
 }
 
+// A warp's tile of launch indices for kernels that run one launch index per thread over a width x height launch: TILE_W x TILE_H
+// neighbours instead of 32 consecutive indices of a row (rays of a tile walk the same nodes more often); a CTA of 128 threads is 2 x 2 tiles.
+#ifndef B200RT_TILE_W
+#define B200RT_TILE_W 8
+#endif
+#ifndef B200RT_TILE_CTA_WARPS
+#define B200RT_TILE_CTA_WARPS 4   // 4: a CTA is 2 x 2 tiles, 2: 2 x 1, 1: one tile
+#endif
+constexpr uint32_t TILE_W = B200RT_TILE_W, TILE_H = 32u / TILE_W, TILE_CTA_THREADS = 32u * B200RT_TILE_CTA_WARPS;
+constexpr uint32_t CTA_TILE_W = (B200RT_TILE_CTA_WARPS >= 2 ? 2u : 1u) * TILE_W, CTA_TILE_H = (B200RT_TILE_CTA_WARPS >= 4 ? 2u : 1u) * TILE_H;
+__device__ __forceinline__ void tile_xy(uint32_t& x, uint32_t& y)
+{
+    const uint32_t wrp = threadIdx.x >> 5, ln = threadIdx.x & 31u;
+    x = blockIdx.x * CTA_TILE_W + (wrp & 1u) * TILE_W + ln % TILE_W;
+    y = blockIdx.y * CTA_TILE_H + (wrp >> 1) * TILE_H + ln / TILE_W;
+}
+
 // ---- one ray per thread ---------------------------------------------------------------------------------------------------------------
 // The same traversal state machine without the warp-cooperative machinery: every thread takes ONE work item, visits its nodes and tests
 // the triangles of a leaf group as it meets them.  For COHERENT ray buffers (orthographic / camera rays in pixel order) the lanes of a
@@ -753,7 +838,7 @@ __device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, 
     static_assert(!Work::ANYHIT && !Work::CONTINUES, "any-hit / continuing launches use trace_persistent");
     constexpr bool SM = coop_smem_state<Work>();
     float my_ray[ray_s_stride<SM>()];   // registers here: every index is a compile-time constant
-    uint2 stack[TRAV_STACK];
+    TStack<0> stack;
     Trav s;
     s.tgroup = make_uint2(0u, 0u);
     s.ngroup = make_uint2(0u, 0u);

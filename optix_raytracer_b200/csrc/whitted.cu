@@ -382,9 +382,29 @@ struct WPixelWork : WPrimaryWork<false> {
     }
 };
 
-__global__ void __launch_bounds__(128) w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
+#ifndef B200RT_WHITTED_TILED
+#define B200RT_WHITTED_TILED 1
+#endif
+#ifndef B200RT_WHITTED_INLINE_DEFAULT
+#define B200RT_WHITTED_INLINE_DEFAULT 1   // measured with tiles: 0 0.243, 1 0.227, 2 0.255, 3 0.226 ms (Duck 1080p)
+#endif
+// A warp takes an 8 x 4 tile of pixels (a CTA 16 x 8), so the candidates a warp appends to the PRIMARY work list are neighbours in both
+// directions: the 32 camera rays a PRIMARY warp picks up together walk the same nodes more often than 32 pixels of one row do.
+#ifdef B200RT_WRAYGEN_MIN_CTAS
+#define W_RAYGEN_BOUNDS __launch_bounds__(128, B200RT_WRAYGEN_MIN_CTAS)
+#else
+#define W_RAYGEN_BOUNDS __launch_bounds__(128)   // 80 registers
+#endif
+__global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
 {
+#if B200RT_WHITTED_TILED
+    uint32_t tx, ty;
+    tile_xy(tx, ty);
+    const bool inside = tx < k.width && ty < k.height;
+    const uint32_t i = inside ? ty * k.width + tx : npix;
+#else
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+#endif
     const WParams& P = *k.params;
     const AccelHeader* h = (const AccelHeader*)P.handle;
     bool candidate = false;
@@ -787,9 +807,15 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters, loop state and all work-item cursors of the frame
     k.fetch = cursors;
     // B200RT_WHITTED_INLINE=1: opaque scenes on the one-ray-per-thread kernels (measured slower than the persistent ones, see w_raygen_kernel)
-    static const bool persistent_opaque = [] { const char* e = getenv("B200RT_WHITTED_INLINE"); return !(e && atoi(e) != 0); }();
-    k.raygen_traverses = (!blend && !persistent_opaque) ? 1u : 0u;
+    // bit 0: RAYGEN traverses its own camera ray, bit 1: the probes run one per thread
+    static const int inline_mask = [] { const char* e = getenv("B200RT_WHITTED_INLINE"); return e ? atoi(e) : B200RT_WHITTED_INLINE_DEFAULT; }();
+    const bool inline_primary = (inline_mask & 1) != 0, inline_shadow = (inline_mask & 2) != 0;
+    k.raygen_traverses = (!blend && inline_primary) ? 1u : 0u;
+#if B200RT_WHITTED_TILED
+    w_raygen_kernel<<<dim3(div_up(k.width, CTA_TILE_W), div_up(k.height, CTA_TILE_H)), TILE_CTA_THREADS, 0, s>>>(k, npix);
+#else
     w_raygen_kernel<<<div_up(npix, 128), 128, 0, s>>>(k, npix);
+#endif
     B2_LAUNCH_CHECK(ctx);
     const unsigned g_primary = w_persistent_grid(ctx, k_primary, npix), g_shadow = w_persistent_grid(ctx, k_shadow, (uint64_t)npix * nlp);
     const unsigned g_shade = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(div_up(npix, 128), (uint64_t)ctx->sm_count * 16));
@@ -799,10 +825,10 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         // written into the same LaunchParams.  (B200RT_WHITTED_INLINE: opaque scenes on the one-ray-per-thread kernels instead.)
         w_primary_kernel<true><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
         B2_LAUNCH_CHECK(ctx);
-        if (persistent_opaque) { w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix); B2_LAUNCH_CHECK(ctx); }
+        if (!inline_primary) { w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix); B2_LAUNCH_CHECK(ctx); }
         w_shade_kernel<<<g_shade, 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
-        if (persistent_opaque) w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
+        if (!inline_shadow) w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
         else w_shadow_simple_kernel<<<std::max(1u, std::min(div_up((uint64_t)npix * nlp, 128), (unsigned)ctx->sm_count * 8u)), 128, 0, s>>>(k);
         B2_LAUNCH_CHECK(ctx);
         w_shadow_kernel<true><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
