@@ -442,8 +442,11 @@ __global__ void __launch_bounds__(256) pt_resolve_kernel(const void* __restrict_
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+#ifndef B200RT_SHADE_HOIST
+#define B200RT_SHADE_HOIST 1
+#endif
 #ifndef B200RT_SHADE_MIN_CTAS
-#define B200RT_SHADE_MIN_CTAS 2
+#define B200RT_SHADE_MIN_CTAS 3   // 79 registers, 12 bytes spilled; bench 2 / 3 / 4 CTAs per SM: 2173 / 2186 / 2171 Mrays/s (with the hoisted loads; 2158 before them)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(const void* __restrict__ params, Lanes L, int cur, const char* __restrict__ hg_base,
@@ -506,6 +509,12 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
             float4 rd = L.ray_d[lane];
             uint32_t flags = __float_as_uint(rd.w);
             float4 resv = L.res[lane];
+#if B200RT_SHADE_HOIST
+            // every line of the lane's state is asked for at once (a lane that only waits for its last shadow ray, or missed, reads a few
+            // bytes it does not need): one round trip to memory less in the chain queue -> state -> hit -> vertices
+            const float4 ro_early = L.ray_o[lane], att_early = L.att[lane];
+            const uint2 hp_early = L.hitp[lane];
+#endif
             float3 result = f3(resv.x, resv.y, resv.z);
             int px, py;
             lane_pixel<MODE>(f, lane, px, py);
@@ -513,8 +522,13 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                 // the last shadow ray of the lane has been resolved by TRACE: write the pixel
                 finalize_lane<MODE>(f, L, lane, px, py, result);
             } else {
+#if B200RT_SHADE_HOIST
+                const float4 ro = ro_early;
+                float4 attv = att_early;
+#else
                 const float4 ro = L.ray_o[lane];
                 float4 attv = L.att[lane];
+#endif
                 float3 att = f3(attv.x, attv.y, attv.z);
                 uint32_t seed = __float_as_uint(ro.w);
                 uint32_t pixel_seed = __float_as_uint(attv.w);
@@ -538,7 +552,11 @@ __global__ void __launch_bounds__(256, B200RT_SHADE_MIN_CTAS) pt_shade_kernel(co
                     done = true;
                 } else {
                     // __closesthit__radiance (optixPathTracer.cu:338-413 / optixMultiGPU.cu:312-385)
+#if B200RT_SHADE_HOIST
+                    const uint2 hp = hp_early;
+#else
                     const uint2 hp = L.hitp[lane];
+#endif
                     uint32_t rec_idx = (hp.y & TRI_SBT_MASK) * RAY_TYPES;
                     if (rec_idx >= hg_count) rec_idx = hg_count - 1;
                     const HitGroupData* rt = (const HitGroupData*)(hg_base + (size_t)rec_idx * hg_stride + B200RT_SBT_RECORD_HEADER_SIZE);

@@ -86,6 +86,20 @@ struct PGCounters { unsigned int nhit; unsigned int ncand; unsigned int pad[2]; 
 struct PGAsyncFlags { unsigned int params_changed; };
 constexpr size_t PG_ASYNC_FLAGS_OFFSET = 1536;  // inside ctx->pinned (whitted.cu: 1024, pathtracer.cu: 2048)
 
+// lane index within a sample -> pixel: tile order (trav_coop.cuh), so that the candidate rays a traversal warp picks up together are
+// 2-D neighbours; every kernel of the frame uses this one mapping
+#ifndef B200RT_PG_TILED
+#define B200RT_PG_TILED 0   // measured neutral (imgui_test close camera 15.78 vs 15.81 ms): left off
+#endif
+__device__ __forceinline__ void pg_pixel(uint32_t i, uint32_t width, uint32_t height, uint32_t& ix, uint32_t& iy)
+{
+#if B200RT_PG_TILED
+    tile_order_xy(i, width, height, ix, iy);
+#else
+    ix = i % width; iy = i / width;
+#endif
+}
+
 // ---- RAYGEN: Camera::compute_ray (camera.h:127-144) --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restrict__ params, uint32_t width, uint32_t height, uint32_t sample0,
                                                          uint32_t nlanes, float4* __restrict__ rays, uint32_t* __restrict__ cand,
@@ -101,7 +115,8 @@ __global__ void __launch_bounds__(256) pg_raygen_kernel(const PGParams* __restri
     const PGCamera cam = *P.camera;
     const uint32_t npix = width * height;
     const uint32_t i = lane % npix, sample = sample0 + lane / npix;
-    const uint32_t ix = i % width, iy = i / width;
+    uint32_t ix, iy;
+    pg_pixel(i, width, height, ix, iy);
     uint32_t seed = tea4(ix + width * iy, P.dt);
     float dx = fm(2.0f, fdiv((float)ix, (float)width), -1.0f), dy = fm(2.0f, fdiv((float)iy, (float)height), -1.0f);
     if (cam.ortho) {
@@ -191,7 +206,8 @@ __global__ void __launch_bounds__(256) pg_shade_kernel(const PGParams* __restric
                         fm(b0, N[3 * vo + 1], fm(h.b2, N[3 * (vo + 2) + 1], h.b1 * N[3 * (vo + 1) + 1])),
                         fm(b0, N[3 * vo + 2], fm(h.b2, N[3 * (vo + 2) + 2], h.b1 * N[3 * (vo + 1) + 2])));
     const float3 Pp = f3(fm(n.x, 0.0001f, fm(h.t, rd.x, ro.x)), fm(n.y, 0.0001f, fm(h.t, rd.y, ro.y)), fm(n.z, 0.0001f, fm(h.t, rd.z, ro.z)));
-    const uint32_t ix = i % width, iy = i / width;
+    uint32_t ix, iy;
+    pg_pixel(i, width, height, ix, iy);
     uint32_t seed = tea4(ix + width * iy, P.dt);
     const size_t pb = (size_t)k * (size_t)(nl + 1);
     for (int li = 0; li < nl; ++li) {
@@ -272,7 +288,8 @@ __global__ void __launch_bounds__(256) pg_finish_kernel(const PGParams* __restri
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= width * height) return;
     const PGParams P = *params;
-    const uint32_t ix = i % width, iy = i / width;
+    uint32_t ix, iy;
+    pg_pixel(i, width, height, ix, iy);
     const size_t index = (size_t)iy * P.image_width + ix;
     const float4 s = sum[i];
     float3 f = f3(s.x, s.y, s.z);

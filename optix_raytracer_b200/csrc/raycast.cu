@@ -243,18 +243,18 @@ __global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_ke
 #else
 #define RAYCAST_SIMPLE_BOUNDS __launch_bounds__(128)   // 72 registers
 #endif
-template <bool TILED>
+template <bool TILED, bool AH>
 __global__ void RAYCAST_SIMPLE_BOUNDS raycast_simple_kernel(const RaycastParamsDev* __restrict__ rc_params, uint32_t n, uint32_t width, uint32_t height,
                                                               ExtHit* __restrict__ ext, const char* __restrict__ hg_base, uint32_t hg_stride, uint32_t hg_count,
                                                               uint32_t dual)
 {
     const RaycastParamsDev P = *rc_params;
-    RayWork<2, false> w;
-    w.ah = AnyHitCfg{nullptr, 0u, 0u, AH_NONE};
+    RayWork<2, AH> w;
+    w.ah = AH ? AnyHitCfg{hg_base, hg_stride, hg_count, AH_TEXTURE_MASK} : AnyHitCfg{nullptr, 0u, 0u, AH_NONE};
     w.att = 1.0;
     w.flag_period = 0;
     w.handle = (const AccelHeader*)P.handle; w.rays = P.rays; w.hits = P.hits;
-    if (dual && w.handle->anyhit != 0u) return;
+    if (dual && (w.handle->anyhit != 0u) != AH) return;
     w.ray_flags = 0u; w.ext = ext; w.occluded = nullptr;
     w.hg_base = hg_base; w.hg_stride = hg_stride; w.hg_count = hg_count; w.item = 0;
     if (TILED) {
@@ -412,26 +412,38 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     // at all is decided on the device (trace_rays_kernel), so the launch never waits for anything
     const bool full_records = sbt->hitgroupRecordStrideInBytes >= 32 + 352;
     const uint32_t dual = full_records ? 1u : 0u;
-    // B200RT_RAYCAST_DRIVER=coop puts the launch back on the persistent cooperative driver (A/B runs; buffers of incoherent rays)
-    static const bool coop = [] { const char* e = getenv("B200RT_RAYCAST_DRIVER"); return e && !strcmp(e, "coop"); }();
-    if (coop)
+    // B200RT_RAYCAST_DRIVER=coop puts the launch back on the persistent cooperative driver (A/B runs; buffers of incoherent rays);
+    // B200RT_RAYCAST_DRIVER=coop_ah only its any-hit half
+    static const int coop = [] { const char* e = getenv("B200RT_RAYCAST_DRIVER"); return !e ? 0 : !strcmp(e, "coop") ? 3 : !strcmp(e, "coop_ah") ? 2 : 0; }();
+    const bool tiled = height >= TILE_H && div_up(height, CTA_TILE_H) <= 65535u && B200RT_RAYCAST_TILED;
+    const dim3 g_tiled(div_up(width, CTA_TILE_W), div_up(height, CTA_TILE_H));
+    const char* hg = (const char*)sbt->hitgroupRecordBase;
+    const uint32_t hg_stride = sbt->hitgroupRecordStrideInBytes, hg_count = sbt->hitgroupRecordCount;
+    const AnyHitCfg ah{hg, hg_stride, hg_count, AH_TEXTURE_MASK};
+    // the plain instantiation, then (records long enough for the any-hit program) the any-hit one: each returns at once unless the
+    // traversable is its kind (trace_rays_kernel)
+    if (coop & 1)
         trace_rays_kernel<2, false, false><<<persistent_grid_rays<2, false, false>(ctx, n), COOP_BLOCK, 0, s>>>(
-            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
-    else if (height >= TILE_H && div_up(height, CTA_TILE_H) <= 65535u && B200RT_RAYCAST_TILED)
-        raycast_simple_kernel<true><<<dim3(div_up(width, CTA_TILE_W), div_up(height, CTA_TILE_H)), TILE_CTA_THREADS, 0, s>>>(
-            (const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, (const char*)sbt->hitgroupRecordBase,
-            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, dual);
+            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, hg, hg_stride, hg_count, counter, nullptr, nullptr, 1u, 0u,
+            AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
+    else if (tiled)
+        raycast_simple_kernel<true, false><<<g_tiled, TILE_CTA_THREADS, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
+                                                                                 hg_stride, hg_count, dual);
     else
-        raycast_simple_kernel<false><<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext,
-                                                                    (const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes,
-                                                                    sbt->hitgroupRecordCount, dual);
+        raycast_simple_kernel<false, false><<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg, hg_stride,
+                                                                           hg_count, dual);
     if (full_records) {
         B2_LAUNCH_CHECK(ctx);
-        const AnyHitCfg ah{(const char*)sbt->hitgroupRecordBase, sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, AH_TEXTURE_MASK};
-        trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
-            nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, (const char*)sbt->hitgroupRecordBase,
-            sbt->hitgroupRecordStrideInBytes, sbt->hitgroupRecordCount, counter, nullptr, nullptr, 1u, 0u, ah, dual);
+        if (coop & 2)
+            trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
+                nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, hg, hg_stride, hg_count, counter, nullptr, nullptr, 1u, 0u,
+                ah, dual);
+        else if (tiled)
+            raycast_simple_kernel<true, true><<<g_tiled, TILE_CTA_THREADS, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
+                                                                                    hg_stride, hg_count, dual);
+        else
+            raycast_simple_kernel<false, true><<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
+                                                                              hg_stride, hg_count, dual);
     }
     B2_LAUNCH_CHECK(ctx);
     return 0;

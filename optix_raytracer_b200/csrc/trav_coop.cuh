@@ -825,18 +825,32 @@ __device__ __forceinline__ void tile_xy(uint32_t& x, uint32_t& y)
     y = blockIdx.y * CTA_TILE_H + (wrp >> 1) * TILE_H + ln / TILE_W;
 }
 
+// The same order for launches whose lanes are a flat index: index -> pixel, bands of TILE_H rows cut into TILE_W x TILE_H tiles, a
+// bijection of [0, width * height) for any size (columns beyond the last whole tile of a band and the rows of a last partial band
+// follow in row order).  Work lists compacted in lane order then hold 2-D neighbours next to each other.
+__device__ __forceinline__ void tile_order_xy(uint32_t i, uint32_t width, uint32_t height, uint32_t& x, uint32_t& y)
+{
+    const uint32_t band_sz = TILE_H * width, band = i / band_sz, r = i - band * band_sz;
+    const uint32_t wt = width - width % TILE_W;
+    if ((band + 1u) * TILE_H > height) { x = i % width; y = i / width; return; }
+    if (r < TILE_H * wt) { const uint32_t t = r / 32u, k = r % 32u; x = t * TILE_W + k % TILE_W; y = band * TILE_H + k / TILE_W; }
+    else { const uint32_t q = r - TILE_H * wt, wr = width - wt; x = wt + q % wr; y = band * TILE_H + q / wr; }
+}
+
 // ---- one ray per thread ---------------------------------------------------------------------------------------------------------------
 // The same traversal state machine without the warp-cooperative machinery: every thread takes ONE work item, visits its nodes and tests
 // the triangles of a leaf group as it meets them.  For COHERENT ray buffers (orthographic / camera rays in pixel order) the lanes of a
 // warp walk the same nodes anyway, so there is nothing for the cooperative rounds to repair, and their bookkeeping (shared-memory unit
 // lists, prefix sums, refills) is pure cost: optixRaycasting's two 1 M-ray ortho batches on the Duck took 0.35 ms on the persistent
-// driver, against OptiX's 0.33 (profiles/r02_small_scenes.md).  Incoherent rays stay on trace_persistent.  Same Work concept (no any-hit
-// programs: ANYHIT launches stay on the cooperative driver), same tri_unit arithmetic, same hit rule: bit-identical results.
+// driver, against OptiX's 0.33 (profiles/r02_small_scenes.md).  Incoherent rays stay on trace_persistent.  Same Work concept (an any-hit program
+// runs on the lane that tested the triangle — its own), same tri_unit arithmetic, same hit rule: bit-identical results.
 template <class Work>
 __device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, bool valid, TravStats* st)
 {
-    static_assert(!Work::ANYHIT && !Work::CONTINUES, "any-hit / continuing launches use trace_persistent");
+    static_assert(!Work::CONTINUES, "continuing launches use trace_persistent");
     constexpr bool SM = coop_smem_state<Work>();
+    bool ah_on = false;  // uniform: the launch has any-hit programs AND the traversable holds geometry that runs them
+    if constexpr (Work::ANYHIT) ah_on = work.anyhit_enabled();
     float my_ray[ray_s_stride<SM>()];   // registers here: every index is a compile-time constant
     TStack<0> stack;
     Trav s;
@@ -856,7 +870,16 @@ __device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, 
                 const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                 if (st) st->tris++;
                 float t, b1, b2;
-                if (tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2)) {
+                bool uh = tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2);
+                if constexpr (Work::ANYHIT) {
+                    // the candidate's any-hit program runs right here: this lane has everything it needs
+                    if (ah_on && uh && !anyhit_off(__float_as_uint(q1.w) >> TRI_FLAG_SHIFT, __float_as_uint(my_ray[8]))) {
+                        float fac;
+                        uh = work.anyhit(__float_as_uint(q0.w), __float_as_uint(q1.w) & TRI_SBT_MASK, s.inst, s.pack, b1, b2, fac);
+                        if (fac != 1.0f) work.attenuate(fac);
+                    }
+                }
+                if (uh) {
                     const uint32_t ord = __float_as_uint(q2.w);
                     if (t < s.best.t || ((s.pack & TP_FOUND) && ord < s.best.ord)) {
                         s.best.t = t; s.best.ord = ord;

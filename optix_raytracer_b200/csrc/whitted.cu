@@ -385,6 +385,9 @@ struct WPixelWork : WPrimaryWork<false> {
 #ifndef B200RT_WHITTED_TILED
 #define B200RT_WHITTED_TILED 1
 #endif
+#ifndef B200RT_WHITTED_SCREEN_RECT
+#define B200RT_WHITTED_SCREEN_RECT 1
+#endif
 #ifndef B200RT_WHITTED_INLINE_DEFAULT
 #define B200RT_WHITTED_INLINE_DEFAULT 1   // measured with tiles: 0 0.243, 1 0.227, 2 0.255, 3 0.226 ms (Duck 1080p)
 #endif
@@ -408,10 +411,42 @@ __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, ui
     const WParams& P = *k.params;
     const AccelHeader* h = (const AccelHeader*)P.handle;
     bool candidate = false;
+#if B200RT_WHITTED_TILED && B200RT_WHITTED_SCREEN_RECT
+    // Most pixels of a model viewer lie outside the picture of the scene bounds: they do not need a camera ray (tea<4>, two IEEE
+    // divisions, a normalisation) and a slab test to learn that.  Every warp projects the eight corners of the padded bounds (lanes
+    // 0-7; plain fp32 arithmetic, the rectangle is widened by two pixels) and takes their bounding rectangle in pixel coordinates: a
+    // ray that reaches the box — a convex body in front of the eye — goes through a pixel inside it.  Any corner beside or behind
+    // the eye, or a non-finite value: the rectangle is the whole frame.
+    bool in_rect;
+    {
+        const uint32_t c = threadIdx.x & 7u;
+        const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
+        const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 2.44140625e-04f;   // four times ray_reaches_bounds' 2^-14
+        const float3 q = f3(((c & 1u) ? hx + pad : lx - pad) - P.eye.x, ((c & 2u) ? hy + pad : ly - pad) - P.eye.y, ((c & 4u) ? hz + pad : lz - pad) - P.eye.z);
+        // q = a U + b V + w W  ->  the pixel's (dx, dy) = (a / w, b / w)
+        const float3 vxw = cross(P.V, P.W), qxw = cross(q, P.W), vxq = cross(P.V, q);
+        const float det = dot(P.U, vxw);
+        const float a = dot(q, vxw) / det, b = dot(P.U, qxw) / det, w = dot(P.U, vxq) / det;
+        float fx = (a / w + 1.0f) * 0.5f * (float)k.width, fy = (b / w + 1.0f) * 0.5f * (float)k.height;
+        bool bad = !(w > 1e-6f * length(q)) || !(fabsf(fx) < 1e9f) || !(fabsf(fy) < 1e9f);
+        float x0 = fx, x1 = fx, y0 = fy, y1 = fy;
+#pragma unroll
+        for (int off = 4; off; off >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, off)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, off));
+            y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, off)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, off));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        in_rect = bad || ((float)tx >= floorf(x0) - 2.0f && (float)tx <= floorf(x1) + 2.0f && (float)ty >= floorf(y0) - 2.0f && (float)ty <= floorf(y1) + 2.0f);
+    }
+#else
+    const bool in_rect = true;
+#endif
     if (i < npix) {
-        float3 o, d;
-        w_camera_ray(P, k.width, k.height, i, o, d);
-        candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
+        if (in_rect) {
+            float3 o, d;
+            w_camera_ray(P, k.width, k.height, i, o, d);
+            candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
+        }
         if (!candidate) w_write_pixel(P, i, P.miss_color);
     }
     if (h->anyhit == 0u && k.raygen_traverses) {   // uniform over the launch
