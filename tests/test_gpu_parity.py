@@ -362,8 +362,31 @@ def test_playground_bit_exact(ctx, orc, aperture, ortho):
         assert np.abs(pg.image.cpu().numpy().astype(np.int32) - image.astype(np.int32)).max() <= 1
 
 
-@pytest.mark.parametrize("alpha_mode,double_sided", [(0, False), (2, False), (2, True)])
-def test_whitted_untextured_bit_exact(ctx, orc, alpha_mode, double_sided):
+@pytest.mark.parametrize("alpha_mode", [0, 1])
+def test_raycast_launch_shapes_agree(ctx, alpha_mode):
+    """optixRaycasting's launch takes optixLaunch's width x height; the one-ray-per-thread kernel gives a warp an 8 x 4 tile of launch
+    indices (raycast.cu).  Sizes that are no multiple of the tile, and the flat n x 1 launch of the same buffer (rows of 32 indices), must
+    fill the same Hit / ext records — with and without an any-hit program (alpha MASK)."""
+    from optix_raytracer_b200 import host
+    sc = common.duck_scene() if alpha_mode == 0 else common.duck_alpha_scene(1)
+    rc = host.Raycaster(ctx, sc)
+    for width in (37, 101):
+        n = rc.buffer_rays(width)
+        assert rc.height % 4 != 0 or width % 8 != 0
+        rc.launch()
+        torch.cuda.synchronize()
+        tiled_hits, tiled_ext = rc.hits.clone(), rc.ext.clone()
+        assert (tiled_hits[:, 0] >= 0).float().mean() > 0.2
+        rc.hits.fill_(-7.0); rc.ext.fill_(-7)
+        ctx.launch_raycast(rc.programs, rc.d_params.data_ptr(), rc.sbt, n, 1, rc.ext.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(tiled_hits.view(torch.int32), rc.hits.view(torch.int32)), f"width {width}: Hit buffers of the two launch shapes differ"
+        assert torch.equal(tiled_ext, rc.ext), f"width {width}: ext records of the two launch shapes differ"
+    rc.close()
+
+
+@pytest.mark.parametrize("alpha_mode,double_sided,size", [(0, False, (160, 120)), (0, False, (157, 83)), (2, False, (160, 120)), (2, True, (160, 120))])
+def test_whitted_untextured_bit_exact(ctx, orc, alpha_mode, double_sided, size):
     """optixMeshViewer (BASELINE.json configs[2]) on the Duck with its texture removed: accum bit-exact against the oracle over
     two subframes (pixel-centre ray, then jittered + running mean), frame within 1 LSB.  alpha_mode 2 = ALPHA_MODE_BLEND with
     base-colour alpha 0.6: every hit continues behind itself (whitted.cu:266-286); doubleSided lifts the back-face culling of the
@@ -373,7 +396,7 @@ def test_whitted_untextured_bit_exact(ctx, orc, alpha_mode, double_sided):
     sc = common.duck_scene(textured=False)
     if alpha_mode:
         sc["materials"][0].update({"alpha_mode": alpha_mode, "double_sided": double_sided, "base_color": [1.0, 0.9, 0.8, 0.6]})
-    w, h = 160, 120
+    w, h = size   # 157 x 83: no multiple of RAYGEN's 8 x 4 pixel tiles (whitted.cu)
     mv = host.MeshViewer(ctx, sc, w, h)
     prim = sc["meshes"][0]["primitives"][0]
     tris, nrm = common.deindex(prim)
