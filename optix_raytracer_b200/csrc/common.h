@@ -6,6 +6,7 @@
 
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200rt.h"
@@ -120,6 +121,34 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline unsigned int div_up(size_t n, size_t d) { return (unsigned int)((n + d - 1) / d); }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch for chains of short kernels on one stream (the viewer's frame: seven launches for 0.22 ms).  A kernel
+// launched with launch_chain may be made resident while its predecessor is still running; it calls chain_enter() first thing, which
+// (a) lets ITS successor do the same and (b) waits until the predecessor has finished and its writes are visible.  Every kernel of a
+// chain must call chain_enter() — also one that returns at once — because a kernel's wait only covers the kernel right before it; the
+// ones further back are covered by that kernel having waited in turn.  Without the launch attribute both instructions do nothing.
+// B200RT_PDL=0 launches the chains the plain way.
+__device__ __forceinline__ void chain_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool chain_launches_enabled()
+{
+    static const bool on = [] { const char* e = getenv("B200RT_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = chain_launches_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 // Release-ordered atomics for "write a result, then count yourself in" protocols.  __threadfence() is fence.sc.gpu, which on sm_100 is
 // MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL — it invalidates the SM's WHOLE L1 every time (in a traversal kernel: the BVH nodes of every warp
 // on the SM; in the tree builder: 7 GB of keys re-read from DRAM and a kernel that ran 6 ms instead of 1).  A release on the atomic is

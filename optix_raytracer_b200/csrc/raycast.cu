@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(COOP_BLOCK, B200RT_RAY_MIN_CTAS) trace_rays_ke
                                                           unsigned long long* __restrict__ stats, const unsigned int* __restrict__ n_dev,
                                                           uint32_t n_mult, uint32_t flag_period, AnyHitCfg ah, uint32_t dual)
 {
+    chain_enter();
     if (n_dev) n = min(n, *n_dev * n_mult);  // ray count produced on the device by an earlier stage (playground.cu)
     if (KIND != 2 && hg_base) handle = (const AccelHeader*)*(const uint64_t*)hg_base;  // traversable handle read from device memory (whitted.cu)
     RayWork<KIND, AH> w;
@@ -248,6 +249,7 @@ __global__ void RAYCAST_SIMPLE_BOUNDS raycast_simple_kernel(const RaycastParamsD
                                                               ExtHit* __restrict__ ext, const char* __restrict__ hg_base, uint32_t hg_stride, uint32_t hg_count,
                                                               uint32_t dual)
 {
+    chain_enter();
     const RaycastParamsDev P = *rc_params;
     RayWork<2, AH> w;
     w.ah = AH ? AnyHitCfg{hg_base, hg_stride, hg_count, AH_TEXTURE_MASK} : AnyHitCfg{nullptr, 0u, 0u, AH_NONE};
@@ -404,9 +406,6 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     B2_REQUIRE(ctx, n < (1ull << 32), "launch too large");
     if (n == 0) return 0;
     std::lock_guard<std::recursive_mutex> lock(ctx->mu);
-    unsigned int* counter = nullptr;
-    int rc = next_counter(ctx, s, &counter);
-    if (rc) return rc;
     // __anyhit__texture_mask (optixRaycasting.cu:89-102) needs the material and the texture coordinates of whitted::HitGroupData (a
     // record too short to hold them runs without any-hit programs); whether the traversable holds geometry that runs any-hit programs
     // at all is decided on the device (trace_rays_kernel), so the launch never waits for anything
@@ -415,6 +414,11 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     // B200RT_RAYCAST_DRIVER=coop puts the launch back on the persistent cooperative driver (A/B runs; buffers of incoherent rays);
     // B200RT_RAYCAST_DRIVER=coop_ah only its any-hit half
     static const int coop = [] { const char* e = getenv("B200RT_RAYCAST_DRIVER"); return !e ? 0 : !strcmp(e, "coop") ? 3 : !strcmp(e, "coop_ah") ? 2 : 0; }();
+    unsigned int* counter = nullptr;   // work-item cursor: the persistent kernels only
+    if (coop) {
+        const int rc = next_counter(ctx, s, &counter);
+        if (rc) return rc;
+    }
     const bool tiled = height >= TILE_H && div_up(height, CTA_TILE_H) <= 65535u && B200RT_RAYCAST_TILED;
     const dim3 g_tiled(div_up(width, CTA_TILE_W), div_up(height, CTA_TILE_H));
     const char* hg = (const char*)sbt->hitgroupRecordBase;
@@ -427,11 +431,11 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
             nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, hg, hg_stride, hg_count, counter, nullptr, nullptr, 1u, 0u,
             AnyHitCfg{nullptr, 0u, 0u, AH_NONE}, dual);
     else if (tiled)
-        raycast_simple_kernel<true, false><<<g_tiled, TILE_CTA_THREADS, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
-                                                                                 hg_stride, hg_count, dual);
+        B2_CUDA(ctx, launch_chain(raycast_simple_kernel<true, false>, g_tiled, dim3(TILE_CTA_THREADS), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
+                                  (ExtHit*)ext, hg, hg_stride, hg_count, dual));
     else
-        raycast_simple_kernel<false, false><<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg, hg_stride,
-                                                                           hg_count, dual);
+        B2_CUDA(ctx, launch_chain(raycast_simple_kernel<false, false>, dim3(div_up(n, 128)), dim3(128), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
+                                  (ExtHit*)ext, hg, hg_stride, hg_count, dual));
     if (full_records) {
         B2_LAUNCH_CHECK(ctx);
         if (coop & 2)
@@ -439,11 +443,11 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                 nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, hg, hg_stride, hg_count, counter, nullptr, nullptr, 1u, 0u,
                 ah, dual);
         else if (tiled)
-            raycast_simple_kernel<true, true><<<g_tiled, TILE_CTA_THREADS, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
-                                                                                    hg_stride, hg_count, dual);
+            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<true, true>, g_tiled, dim3(TILE_CTA_THREADS), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
+                                      (ExtHit*)ext, hg, hg_stride, hg_count, dual));
         else
-            raycast_simple_kernel<false, true><<<div_up(n, 128), 128, 0, s>>>((const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg,
-                                                                              hg_stride, hg_count, dual);
+            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<false, true>, dim3(div_up(n, 128)), dim3(128), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
+                                      (ExtHit*)ext, hg, hg_stride, hg_count, dual));
     }
     B2_LAUNCH_CHECK(ctx);
     return 0;

@@ -348,6 +348,7 @@ struct WPrimaryWork {
 template <bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const __grid_constant__ WK k, uint32_t n_items)
 {
+    chain_enter();
     const AccelHeader* handle = (const AccelHeader*)k.params->handle;
     if ((handle->anyhit != 0u) != AH) return;
     const uint32_t level = w_level(k);
@@ -400,6 +401,7 @@ struct WPixelWork : WPrimaryWork<false> {
 #endif
 __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, uint32_t npix)
 {
+    chain_enter();
 #if B200RT_WHITTED_TILED
     uint32_t tx, ty;
     tile_xy(tx, ty);
@@ -466,6 +468,7 @@ __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, ui
 // ---- SHADE: __closesthit__radiance up to the shadow rays, one thread per hit slot of the level --------------------------------------
 __global__ void __launch_bounds__(128) w_shade_kernel(const __grid_constant__ WK k)
 {
+    chain_enter();
     const WParams P = *k.params;
     const uint32_t end = min(k.counters->nslots, k.cap_slots);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -668,6 +671,7 @@ struct WShadowWork {
 template <bool AH>
 __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const __grid_constant__ WK k)
 {
+    chain_enter();
     const WParams* P = k.params;
     const AccelHeader* handle = (const AccelHeader*)P->handle;
     if ((handle->anyhit != 0u) != AH) return;
@@ -684,6 +688,7 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_shadow_kernel(const 
 // items, whose count only the device knows.
 __global__ void __launch_bounds__(128) w_shadow_simple_kernel(const __grid_constant__ WK k)
 {
+    chain_enter();
     const WParams* P = k.params;
     const AccelHeader* handle = (const AccelHeader*)P->handle;
     if (handle->anyhit != 0u) return;
@@ -846,10 +851,11 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     static const int inline_mask = [] { const char* e = getenv("B200RT_WHITTED_INLINE"); return e ? atoi(e) : B200RT_WHITTED_INLINE_DEFAULT; }();
     const bool inline_primary = (inline_mask & 1) != 0, inline_shadow = (inline_mask & 2) != 0;
     k.raygen_traverses = (!blend && inline_primary) ? 1u : 0u;
+    // the kernels of a frame without BLEND levels are a chain of programmatic dependent launches (common.h: launch_chain)
 #if B200RT_WHITTED_TILED
-    w_raygen_kernel<<<dim3(div_up(k.width, CTA_TILE_W), div_up(k.height, CTA_TILE_H)), TILE_CTA_THREADS, 0, s>>>(k, npix);
+    B2_CUDA(ctx, launch_chain(w_raygen_kernel, dim3(div_up(k.width, CTA_TILE_W), div_up(k.height, CTA_TILE_H)), dim3(TILE_CTA_THREADS), s, k, npix));
 #else
-    w_raygen_kernel<<<div_up(npix, 128), 128, 0, s>>>(k, npix);
+    B2_CUDA(ctx, launch_chain(w_raygen_kernel, dim3(div_up(npix, 128)), dim3(128), s, k, npix));
 #endif
     B2_LAUNCH_CHECK(ctx);
     const unsigned g_primary = w_persistent_grid(ctx, k_primary, npix), g_shadow = w_persistent_grid(ctx, k_shadow, (uint64_t)npix * nlp);
@@ -858,15 +864,15 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         // Both instantiations of the persistent kernels are enqueued: which kind the traversable is, is read on the device
         // (AccelHeader::anyhit), each kernel returns at once unless it is its kind, so the choice cannot go stale when another handle is
         // written into the same LaunchParams.  (B200RT_WHITTED_INLINE: opaque scenes on the one-ray-per-thread kernels instead.)
-        w_primary_kernel<true><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix);
+        B2_CUDA(ctx, launch_chain(w_primary_kernel<true>, dim3(g_primary), dim3(COOP_BLOCK), s, k, npix));
         B2_LAUNCH_CHECK(ctx);
-        if (!inline_primary) { w_primary_kernel<false><<<g_primary, COOP_BLOCK, 0, s>>>(k, npix); B2_LAUNCH_CHECK(ctx); }
-        w_shade_kernel<<<g_shade, 128, 0, s>>>(k);
+        if (!inline_primary) { B2_CUDA(ctx, launch_chain(w_primary_kernel<false>, dim3(g_primary), dim3(COOP_BLOCK), s, k, npix)); B2_LAUNCH_CHECK(ctx); }
+        B2_CUDA(ctx, launch_chain(w_shade_kernel, dim3(g_shade), dim3(128), s, k));
         B2_LAUNCH_CHECK(ctx);
-        if (!inline_shadow) w_shadow_kernel<false><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
-        else w_shadow_simple_kernel<<<std::max(1u, std::min(div_up((uint64_t)npix * nlp, 128), (unsigned)ctx->sm_count * 8u)), 128, 0, s>>>(k);
+        if (!inline_shadow) B2_CUDA(ctx, launch_chain(w_shadow_kernel<false>, dim3(g_shadow), dim3(COOP_BLOCK), s, k));
+        else B2_CUDA(ctx, launch_chain(w_shadow_simple_kernel, dim3(std::max(1u, std::min(div_up((uint64_t)npix * nlp, 128), (unsigned)ctx->sm_count * 8u))), dim3(128), s, k));
         B2_LAUNCH_CHECK(ctx);
-        w_shadow_kernel<true><<<g_shadow, COOP_BLOCK, 0, s>>>(k);
+        B2_CUDA(ctx, launch_chain(w_shadow_kernel<true>, dim3(g_shadow), dim3(COOP_BLOCK), s, k));
         B2_LAUNCH_CHECK(ctx);
     } else {
         // BLEND scenes: how many continuation rays a level starts is known on the device only, so the levels run as a device-side loop
