@@ -577,6 +577,9 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
     // 0.424 ms, Cornell 6.54 -> 7.03 ms).
     uint32_t loc_next = 0, loc_end = 0;
     const uint32_t chunk = n_items / (gridDim.x * (uint32_t)COOP_BLOCK) >= 64u ? (uint32_t)B200RT_FETCH_CHUNK : 0u;
+    // (Measured and taken out again: a warp's first 32 items assigned by position, the cursor handing out what lies beyond the grid's
+    // first round — one atomic round trip less per warp, but one more live value in a kernel capped at 64 registers: 8 -> 62 bytes
+    // spilled, bench 2184 -> 2015 Mrays/s, nothing gained on the viewer's probes it was meant for.)
 #endif
     for (;;) {
         // ---- commit finished rays together, then every lane without a ray takes the next work item

@@ -251,15 +251,20 @@ __device__ __forceinline__ void w_camera_ray(const WParams& P, uint32_t width, u
 }
 
 // tail of __raygen__pinhole (whitted.cu:84-97)
-__device__ __forceinline__ void w_write_pixel(const WParams& P, uint32_t pixel, float3 result)
+__device__ __forceinline__ void w_write_pixel(const WParams& P, uint32_t pixel, float3 result, float4 prev)   // prev = accum_buffer[pixel], read by the caller
 {
     if (P.subframe_index > 0) {
         const float a = fdiv(1.0f, (float)(P.subframe_index + 1u));
-        const float4 prev = P.accum_buffer[pixel];
         result = f3(fm(a, result.x - prev.x, prev.x), fm(a, result.y - prev.y, prev.y), fm(a, result.z - prev.z, prev.z));
     }
     P.accum_buffer[pixel] = make_float4(result.x, result.y, result.z, 1.0f);
     if (P.frame_buffer) P.frame_buffer[pixel] = make_color(result);
+}
+__device__ __forceinline__ void w_write_pixel(const WParams& P, uint32_t pixel, float3 result)
+{
+    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.subframe_index > 0) prev = P.accum_buffer[pixel];
+    w_write_pixel(P, pixel, result, prev);
 }
 
 __device__ __forceinline__ uint32_t w_inst_sbt(const AccelHeader* handle, uint32_t inst)
@@ -425,12 +430,12 @@ __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, ui
         const float lx = h->bounds[0], ly = h->bounds[1], lz = h->bounds[2], hx = h->bounds[3], hy = h->bounds[4], hz = h->bounds[5];
         const float pad = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz) * 2.44140625e-04f;   // four times ray_reaches_bounds' 2^-14
         const float3 q = f3(((c & 1u) ? hx + pad : lx - pad) - P.eye.x, ((c & 2u) ? hy + pad : ly - pad) - P.eye.y, ((c & 4u) ? hz + pad : lz - pad) - P.eye.z);
-        // q = a U + b V + w W  ->  the pixel's (dx, dy) = (a / w, b / w)
+        // q = a U + b V + w W  ->  the pixel's (dx, dy) = (a / w, b / w): Cramer's rule, whose common denominator cancels in the ratios
         const float3 vxw = cross(P.V, P.W), qxw = cross(q, P.W), vxq = cross(P.V, q);
-        const float det = dot(P.U, vxw);
-        const float a = dot(q, vxw) / det, b = dot(P.U, qxw) / det, w = dot(P.U, vxq) / det;
-        float fx = (a / w + 1.0f) * 0.5f * (float)k.width, fy = (b / w + 1.0f) * 0.5f * (float)k.height;
-        bool bad = !(w > 1e-6f * length(q)) || !(fabsf(fx) < 1e9f) || !(fabsf(fy) < 1e9f);
+        const float det = dot(P.U, vxw), an = dot(q, vxw), bn = dot(P.U, qxw), wn = dot(P.U, vxq);
+        const float fx = (__fdividef(an, wn) + 1.0f) * 0.5f * (float)k.width, fy = (__fdividef(bn, wn) + 1.0f) * 0.5f * (float)k.height;
+        // in front of the eye by a margin: w = wn / det > 1e-6 |q| (the 1-norm stands in for the length)
+        bool bad = !(wn * copysignf(1.0f, det) > 1e-6f * (fabsf(q.x) + fabsf(q.y) + fabsf(q.z)) * fabsf(det)) || !(fabsf(fx) < 1e9f) || !(fabsf(fy) < 1e9f);
         float x0 = fx, x1 = fx, y0 = fy, y1 = fy;
 #pragma unroll
         for (int off = 4; off; off >>= 1) {
@@ -444,12 +449,15 @@ __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, ui
     const bool in_rect = true;
 #endif
     if (i < npix) {
+        // the miss program's read of the running mean is asked for before the camera ray is made, not after
+        float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.subframe_index > 0) prev = P.accum_buffer[i];
         if (in_rect) {
             float3 o, d;
             w_camera_ray(P, k.width, k.height, i, o, d);
             candidate = ray_reaches_bounds(h, o, d, 0.0f, 1e16f);
         }
-        if (!candidate) w_write_pixel(P, i, P.miss_color);
+        if (!candidate) w_write_pixel(P, i, P.miss_color, prev);
     }
     if (h->anyhit == 0u && k.raygen_traverses) {   // uniform over the launch
         WPixelWork work(k, h);
@@ -616,13 +624,17 @@ struct WShadowWork {
         slot = level_start + item / per_slot;
         li = item % per_slot;
         att = 1.0;
-        if (li < nl && k.kinds[(size_t)slot * nl + li] == 1u) {
+        if (li < nl) {
+            // kind and probe are asked for together (a term without a probe reads two lines it does not need)
             const size_t idx = (size_t)slot * nl + li;
+            const uint32_t kind = k.kinds[idx];
             const float4 po = k.probes[2 * idx], pd = k.probes[2 * idx + 1];
+            if (kind == 1u) {
             s.best.t = pd.w;
             // traceOcclusion (whitted_cuda.h:127-159): TERMINATE_ON_FIRST_HIT | DISABLE_CLOSESTHIT, no face culling
             if (trav_begin_handle(s, my_ray, handle, f3(po.x, po.y, po.z), f3(pd.x, pd.y, pd.z), po.w, TP_ANY, 0u, 0u)) return true;
             // nothing to traverse: the miss program commits the untouched attenuation
+            }
         }
         commit(s, false);
         return false;
@@ -637,26 +649,28 @@ struct WShadowWork {
     __device__ __forceinline__ void commit(const Trav&, bool found)
     {
         // occluded -> the attenuation is never committed (0), else the pending product (whitted_cuda.h:155-158)
-        if (li < nl) k.att[(size_t)slot * nl + li] = found ? 0.0f : (float)att;
-        // release on the ticket (no __threadfence: it would invalidate the L1 the traversal lives in, common.h); the last item reads the
-        // others' attenuations with volatile loads, behind the control dependency on its ticket
-        if (atomic_add_release(&k.arrived[slot], 1u) != per_slot - 1u) return;
-        // last item of the slot: result += light.color * attenuation * intensity * N_dot_L * (diff + spec) in light order (whitted.cu:249-256)
+        const float my_att = found ? 0.0f : (float)att;
+        if (li < nl) k.att[(size_t)slot * nl + li] = my_att;
+        // what the item that completes the slot needs is asked for before the ticket, not behind it (with one light every item is that item)
         const float4 b = k.base[slot];
+        const WSlot h = k.slots[slot];
+        // release on the ticket (no __threadfence: it would invalidate the L1 the traversal lives in, common.h); the last item reads the
+        // others' attenuations with volatile loads, behind the control dependency on its ticket.  One item per slot: no ticket.
+        if (per_slot > 1u && atomic_add_release(&k.arrived[slot], 1u) != per_slot - 1u) return;
+        // last item of the slot: result += light.color * attenuation * intensity * N_dot_L * (diff + spec) in light order (whitted.cu:249-256)
         float3 result = f3(b.x, b.y, b.z);
         for (uint32_t l = 0; l < nl; ++l) {
             const size_t idx = (size_t)slot * nl + l;
             const uint32_t kind = k.kinds[idx];
             if (kind == 2) { const float4 c = k.t0[idx]; result = f3(result.x + c.x, result.y + c.y, result.z + c.z); }
             else if (kind == 1) {
-                const float a = *(volatile const float*)&k.att[idx];
+                const float a = l == li ? my_att : *(volatile const float*)&k.att[idx];
                 if (a > 0.0f) {
                     const float4 c = k.t0[idx], d = k.t1[idx];
                     result = f3(result.x + (((c.x * a) * c.w) * d.w) * d.x, result.y + (((c.y * a) * c.w) * d.w) * d.y, result.z + (((c.z * a) * c.w) * d.w) * d.z);
                 }
             }
         }
-        const WSlot h = k.slots[slot];
         if (h.flags & WS_BLEND) {
             const float alpha = b.w;  // base_color.w
             k.result[slot] = make_float4(result.x * alpha, result.y * alpha, result.z * alpha, h.one_minus_alpha);
