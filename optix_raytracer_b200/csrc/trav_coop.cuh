@@ -508,6 +508,47 @@ __device__ __forceinline__ bool tri_unit(const float* __restrict__ r, const floa
     return hit;
 }
 
+// tri_unit with the ray's axis permutation as compile-time constants: the nine component selections of the watertight test (sel3: two
+// predicated moves each) fold away.  Same operations on the same values, so the same bits.  For kernels whose warps agree on the
+// permutation — coherent rays, one per thread — the six-way branch around it is uniform; the cooperative rounds, whose lanes test
+// triangles for rays of any direction, keep the dynamic form.
+template <int KX, int KY, int KZ>
+__device__ __forceinline__ bool tri_unit_k(const float* __restrict__ r, const float4 q0, const float4 q1, const float4 q2, float tfar, float& t_out,
+                                           float& b1, float& b2)
+{
+    TriRay tr;
+    tr.o = f3(r[0], r[1], r[2]);
+    tr.Sx = r[3]; tr.Sy = r[4]; tr.Sz = r[5];
+    tr.kx = KX; tr.ky = KY; tr.kz = KZ;
+    RayHit tmp;
+    tmp.t = tfar;
+    tmp.ord = 0xffffffffu;
+    bool found = true;
+    const bool hit = tri_test<false>(tr, q0, q1, q2, r[7], tmp, found, __float_as_uint(r[8]));
+    t_out = tmp.t; b1 = tmp.b1; b2 = tmp.b2;
+    return hit;
+}
+#ifndef B200RT_TRI_STATIC_AXES
+#define B200RT_TRI_STATIC_AXES 1
+#endif
+__device__ __forceinline__ bool tri_unit_by_axes(const float* __restrict__ r, const float4 q0, const float4 q1, const float4 q2, float tfar, float& t_out,
+                                                 float& b1, float& b2)
+{
+#if B200RT_TRI_STATIC_AXES
+    // kx | ky << 2 | kz << 4 (make_tri_ray: kz = dominant axis, kx = kz + 1, ky = kx + 1 mod 3, swapped for a negative dominant component)
+    switch (__float_as_uint(r[6]) & 0x3fu) {
+    case (1u | 2u << 2 | 0u << 4): return tri_unit_k<1, 2, 0>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    case (2u | 1u << 2 | 0u << 4): return tri_unit_k<2, 1, 0>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    case (2u | 0u << 2 | 1u << 4): return tri_unit_k<2, 0, 1>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    case (0u | 2u << 2 | 1u << 4): return tri_unit_k<0, 2, 1>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    case (0u | 1u << 2 | 2u << 4): return tri_unit_k<0, 1, 2>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    default: return tri_unit_k<1, 0, 2>(r, q0, q1, q2, tfar, t_out, b1, b2);
+    }
+#else
+    return tri_unit(r, q0, q1, q2, tfar, t_out, b1, b2);
+#endif
+}
+
 // Work concept:
 //   __device__ bool  fetch(uint32_t item, Trav& s, float* my_ray)  load item, set s.best.t = tmax, call trav_begin_handle; false = nothing to trace
 //   __device__ bool  next_instance(Trav& s, float* my_ray)         the traversal set up last has ended: set up the next instance of an IAS — or,
@@ -536,6 +577,11 @@ template <class Work, class = void> struct CoopHasSmemState { static constexpr b
 template <class Work> struct CoopHasSmemState<Work, decltype((void)Work::SMEM_STATE)> { static constexpr bool value = Work::SMEM_STATE; };
 template <class Work> constexpr bool coop_smem_state() { return CoopHasSmemState<Work>::value; }
 
+//   static constexpr bool COHERENT_AXES (optional)                 the rays of a warp mostly agree on their dominant axis (camera rays, probes
+//                                                                  towards one light): the rounds test with tri_unit_by_axes
+template <class Work, class = void> struct CoopHasCoherentAxes { static constexpr bool value = false; };
+template <class Work> struct CoopHasCoherentAxes<Work, decltype((void)Work::COHERENT_AXES)> { static constexpr bool value = Work::COHERENT_AXES; };
+template <class Work> constexpr bool coop_coherent_axes() { return CoopHasCoherentAxes<Work>::value; }
 //   static constexpr int SMEM_STACK (optional)                     entries of the traversal stack kept in shared memory (TStack)
 template <class Work, class = void> struct CoopHasSmemStack { static constexpr int value = 0; };
 template <class Work> struct CoopHasSmemStack<Work, decltype((void)Work::SMEM_STACK)> { static constexpr int value = Work::SMEM_STACK; };
@@ -759,7 +805,8 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
                         const float4* tp = (const float4*)(uintptr_t)tris_base + (size_t)sh.unit_tri[wid][lane] * 3u;
                         const float4 q0 = TRI_LOAD(tp), q1 = TRI_LOAD(tp + 1), q2 = TRI_LOAD(tp + 2);
                         if (st) st->tris++;
-                        uhit = tri_unit(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
+                        if constexpr (coop_coherent_axes<Work>()) uhit = tri_unit_by_axes(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
+                        else uhit = tri_unit(&sh.ray[wid][owner * RAY_S_STRIDE], q0, q1, q2, tfar, ut, ub1, ub2);
                         uord = __float_as_uint(q2.w); uprim = __float_as_uint(q0.w); usbt = __float_as_uint(q1.w);
                     }
                     if constexpr (Work::ANYHIT) {
@@ -873,7 +920,7 @@ __device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, 
                 const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
                 if (st) st->tris++;
                 float t, b1, b2;
-                bool uh = tri_unit(my_ray, q0, q1, q2, s.best.t, t, b1, b2);
+                bool uh = tri_unit_by_axes(my_ray, q0, q1, q2, s.best.t, t, b1, b2);
                 if constexpr (Work::ANYHIT) {
                     // the candidate's any-hit program runs right here: this lane has everything it needs
                     if (ah_on && uh && !anyhit_off(__float_as_uint(q1.w) >> TRI_FLAG_SHIFT, __float_as_uint(my_ray[8]))) {

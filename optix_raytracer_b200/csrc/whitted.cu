@@ -39,6 +39,10 @@
 #include "loop_graph.h"
 #include "anyhit.cuh"
 
+#ifndef B200RT_WHITTED_COHERENT_AXES
+#define B200RT_WHITTED_COHERENT_AXES 0   // axis-specialised triangle test in the cooperative rounds too: measured slower (opaque 0.195 vs 0.191 ms, MASK 0.293 vs 0.266: spills)
+#endif
+
 namespace b200rt {
 
 struct WBufView { uint64_t data; uint32_t count; uint16_t byte_stride; uint16_t elmt; };  // SDK/cuda/BufferView.h:32-38
@@ -277,6 +281,7 @@ template <bool AH>
 struct WPrimaryWork {
     static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
+    static constexpr bool COHERENT_AXES = B200RT_WHITTED_COHERENT_AXES != 0;   // camera rays
     const WK& k;
     const AccelHeader* handle;
     uint32_t level;
@@ -605,6 +610,7 @@ template <bool AH>
 struct WShadowWork {
     static constexpr bool CONTINUES = false;
     static constexpr bool ANYHIT = AH;
+    static constexpr bool COHERENT_AXES = B200RT_WHITTED_COHERENT_AXES != 0;   // probes of neighbouring hits towards the same light
     const WK& k;
     const AccelHeader* handle;
     uint32_t nl, per_slot, slot, li, level_start;
