@@ -894,6 +894,9 @@ __device__ __forceinline__ void tile_order_xy(uint32_t i, uint32_t width, uint32
 // lists, prefix sums, refills) is pure cost: optixRaycasting's two 1 M-ray ortho batches on the Duck took 0.35 ms on the persistent
 // driver, against OptiX's 0.33 (profiles/r02_small_scenes.md).  Incoherent rays stay on trace_persistent.  Same Work concept (an any-hit program
 // runs on the lane that tested the triangle — its own), same tri_unit arithmetic, same hit rule: bit-identical results.
+// (Measured and not kept: postponing the leaves — a lane parks its triangle group and the warp tests once 1/4, 1/2 or 3/4 of the lanes
+// still traversing hold one.  Triangle tests do run at 10 of 32 lanes here, but the warp-wide ballots, the idle parked lanes and 16 more
+// registers cost more: ray buffers 0.201 -> 0.228-0.232 ms, viewer 0.191 -> 0.195-0.202 ms; profiles/r02_session4_experiments.md.)
 template <class Work>
 __device__ __forceinline__ void trace_one_per_thread(Work& work, uint32_t item, bool valid, TravStats* st)
 {

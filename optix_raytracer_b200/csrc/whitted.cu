@@ -717,7 +717,9 @@ __global__ void __launch_bounds__(128) w_shadow_simple_kernel(const __grid_const
     const uint32_t level_start = w_level_start(k);
     const uint32_t n_items = end > level_start ? (end - level_start) * max(nl, 1u) : 0u;
     WShadowWork<false> work(k, handle, nl, level_start);
-    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) trace_one_per_thread(work, item, true, nullptr);
+    // the loop is uniform over the warp: trace_one_per_thread wants all 32 lanes, the last warp's spare ones with valid = false
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_items; base += gridDim.x * blockDim.x)
+        trace_one_per_thread(work, base + threadIdx.x, base + threadIdx.x < n_items, nullptr);
 }
 
 // ---- COMBINE: fold the levels of a BLEND pixel back to front, as the recursion of __closesthit__radiance returns -----------------------
