@@ -371,14 +371,14 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const
 // A model viewer's camera rays mostly pass the model by.  Those pixels are finished right here, by 2 M independent threads (the miss
 // program and the raygen tail: whitted.cu:84-97,139-142).  What happens to the rays that reach the (padded, hence conservative:
 // trav_coop.cuh trav_begin<BOUNDS>) scene bounds depends on the scene:
-//   * by default the pixel becomes a work item of the persistent traversal (w_primary_kernel), whose lanes take one item at a time and
-//     would otherwise spend their time on the latency of fetch -> set-up -> accum read for rays that hit nothing (measured: 150 us of a
-//     270 us frame, profiles/r01_whitted_launches.md);
-//   * B200RT_WHITTED_INLINE=1, opaque scene (WK::raygen_traverses): the thread traverses its ray on the spot (trav_coop.cuh:
-//     trace_one_per_thread), and the probes run one per thread too (w_shadow_simple_kernel).  Camera rays in pixel order are coherent,
-//     which made this form the faster one for optixRaycasting's ray buffers (raycast.cu); here it is not: Duck 1080p, RAYGEN + PRIMARY
-//     37 + 86 us -> 117 us in one launch, SHADOW 77 -> 99 us, frame 0.248 -> 0.257 ms (profiles/r02_small_scenes.md).  Of 2 M pixels
-//     170 k reach the model: the traversing warps are partly empty and alone on their SM, while the persistent form packs the rays.
+//   * opaque scene (WK::raygen_traverses; B200RT_WHITTED_INLINE bit 0, default on): the thread traverses its ray on the spot
+//     (trav_coop.cuh: trace_one_per_thread), and the probes run one per thread too (w_shadow_simple_kernel; bit 1, default on).  Camera
+//     rays in 8 x 4 pixel tiles are coherent, the probes of neighbouring hit slots start next to each other and aim at the same light.
+//     History on the Duck at 1080p: this form in rows of 32 pixels 0.257 ms against 0.248 for the persistent kernels; in tiles 0.227
+//     (probes persistent) / 0.226; with the axis-specialised triangle test 0.191-0.202 / 0.184-0.189 (profiles/r02_session4_experiments.md);
+//   * scene with any-hit geometry, or B200RT_WHITTED_INLINE=0: the pixel becomes a work item of the persistent traversal
+//     (w_primary_kernel), whose lanes take one item at a time and would otherwise spend their time on the latency of fetch -> set-up
+//     -> accum read for rays that hit nothing (measured: 150 us of a 270 us frame, profiles/r01_whitted_launches.md).
 struct WPixelWork : WPrimaryWork<false> {
     __device__ WPixelWork(const WK& k_, const AccelHeader* h) : WPrimaryWork<false>(k_, h, 0u) {}
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
@@ -400,7 +400,7 @@ struct WPixelWork : WPrimaryWork<false> {
 #define B200RT_WHITTED_SCREEN_RECT 1
 #endif
 #ifndef B200RT_WHITTED_INLINE_DEFAULT
-#define B200RT_WHITTED_INLINE_DEFAULT 1   // measured with tiles: 0 0.243, 1 0.227, 2 0.255, 3 0.226 ms (Duck 1080p)
+#define B200RT_WHITTED_INLINE_DEFAULT 3   // Duck 1080p: 0 0.243, 1 0.227, 2 0.255, 3 0.226 ms with tiles alone; with the axis-specialised triangle test of the one-ray-per-thread driver 1: 0.191-0.202, 3: 0.184-0.189
 #endif
 // A warp takes an 8 x 4 tile of pixels (a CTA 16 x 8), so the candidates a warp appends to the PRIMARY work list are neighbours in both
 // directions: the 32 camera rays a PRIMARY warp picks up together walk the same nodes more often than 32 pixels of one row do.
@@ -868,7 +868,7 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
     unsigned int* cursors = (unsigned int*)(W + o_cnt + 64);  // two per level
     B2_CUDA(ctx, cudaMemsetAsync(W + o_cnt, 0, 256, s));      // counters, loop state and all work-item cursors of the frame
     k.fetch = cursors;
-    // B200RT_WHITTED_INLINE=1: opaque scenes on the one-ray-per-thread kernels (measured slower than the persistent ones, see w_raygen_kernel)
+    // B200RT_WHITTED_INLINE: opaque scenes on the one-ray-per-thread kernels (see w_raygen_kernel)
     // bit 0: RAYGEN traverses its own camera ray, bit 1: the probes run one per thread
     static const int inline_mask = [] { const char* e = getenv("B200RT_WHITTED_INLINE"); return e ? atoi(e) : B200RT_WHITTED_INLINE_DEFAULT; }();
     const bool inline_primary = (inline_mask & 1) != 0, inline_shadow = (inline_mask & 2) != 0;
