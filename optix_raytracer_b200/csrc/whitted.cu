@@ -379,8 +379,10 @@ __global__ void __launch_bounds__(COOP_BLOCK, W_MIN_CTAS) w_primary_kernel(const
 //   * scene with any-hit geometry, or B200RT_WHITTED_INLINE=0: the pixel becomes a work item of the persistent traversal
 //     (w_primary_kernel), whose lanes take one item at a time and would otherwise spend their time on the latency of fetch -> set-up
 //     -> accum read for rays that hit nothing (measured: 150 us of a 270 us frame, profiles/r01_whitted_launches.md).
-struct WPixelWork : WPrimaryWork<false> {
-    __device__ WPixelWork(const WK& k_, const AccelHeader* h) : WPrimaryWork<false>(k_, h, 0u) {}
+template <bool AH>
+struct WPixelWork : WPrimaryWork<AH> {
+    using WPrimaryWork<AH>::pixel; using WPrimaryWork<AH>::parent; using WPrimaryWork<AH>::handle; using WPrimaryWork<AH>::ray; using WPrimaryWork<AH>::commit;
+    __device__ WPixelWork(const WK& k_, const AccelHeader* h) : WPrimaryWork<AH>(k_, h, 0u) {}
     __device__ __forceinline__ bool fetch(uint32_t item, Trav& s, float* my_ray)
     {
         pixel = item; parent = -1;
@@ -398,6 +400,9 @@ struct WPixelWork : WPrimaryWork<false> {
 #endif
 #ifndef B200RT_WHITTED_SCREEN_RECT
 #define B200RT_WHITTED_SCREEN_RECT 1
+#endif
+#ifndef B200RT_WHITTED_INLINE_ANYHIT
+#define B200RT_WHITTED_INLINE_ANYHIT 1
 #endif
 #ifndef B200RT_WHITTED_INLINE_DEFAULT
 #define B200RT_WHITTED_INLINE_DEFAULT 3   // Duck 1080p: 0 0.243, 1 0.227, 2 0.255, 3 0.226 ms with tiles alone; with the axis-specialised triangle test of the one-ray-per-thread driver 1: 0.191-0.202, 3: 0.184-0.189
@@ -464,10 +469,17 @@ __global__ void W_RAYGEN_BOUNDS w_raygen_kernel(const __grid_constant__ WK k, ui
         }
         if (!candidate) w_write_pixel(P, i, P.miss_color, prev);
     }
-    if (h->anyhit == 0u && k.raygen_traverses) {   // uniform over the launch
-        WPixelWork work(k, h);
+    if (k.raygen_traverses) {   // uniform over the launch
+        if (h->anyhit == 0u) {
+            WPixelWork<false> work(k, h);
+            trace_one_per_thread(work, i, candidate, nullptr);
+            return;
+        }
+#if B200RT_WHITTED_INLINE_ANYHIT
+        WPixelWork<true> work(k, h);   // the candidate's any-hit program (__anyhit__radiance) runs on the traversing lane
         trace_one_per_thread(work, i, candidate, nullptr);
         return;
+#endif
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, candidate);
     if (!mask) return;
