@@ -259,7 +259,22 @@ __global__ void RAYCAST_SIMPLE_BOUNDS raycast_simple_kernel(const RaycastParamsD
     if (dual && (w.handle->anyhit != 0u) != AH) return;
     w.ray_flags = 0u; w.ext = ext; w.occluded = nullptr;
     w.hg_base = hg_base; w.hg_stride = hg_stride; w.hg_count = hg_count; w.item = 0;
-    if (TILED) {
+    if (AH) {
+        // The any-hit instantiation is enqueued behind the plain one for every launch whose records could hold an any-hit program and
+        // returns above unless the scene has such geometry: it is launched as a small 1-D grid that walks the CTA tiles (rows of 128
+        // indices), so that the launch that does nothing is a thousand CTAs, not one per tile.
+        if (TILED) {
+            const uint32_t tiles_x = (width + CTA_TILE_W - 1u) / CTA_TILE_W, tiles = tiles_x * ((height + CTA_TILE_H - 1u) / CTA_TILE_H);
+            for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                uint32_t x, y;
+                tile_xy(t % tiles_x, t / tiles_x, x, y);
+                trace_one_per_thread(w, y * width + x, x < width && y < height, nullptr);
+            }
+        } else {
+            for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+                trace_one_per_thread(w, base + threadIdx.x, base + threadIdx.x < n, nullptr);
+        }
+    } else if (TILED) {
         uint32_t x, y;
         tile_xy(x, y);
         trace_one_per_thread(w, y * width + x, x < width && y < height, nullptr);
@@ -438,16 +453,22 @@ int launch_raycast(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
                                   (ExtHit*)ext, hg, hg_stride, hg_count, dual));
     if (full_records) {
         B2_LAUNCH_CHECK(ctx);
+        // CTAs of the any-hit instantiation: B200RT_RAYCAST_AH_CTAS per SM, each walking its share of the tiles.  Measured on the Duck
+        // (7 865 tiles; opaque scene, where this launch does nothing / MASK scene, where it does everything): one CTA per tile 0.203 /
+        // 0.263 ms, 32 per SM 0.200 / 0.253, 24 per SM 0.200 / 0.254, 16 per SM 0.199 / 0.257, 8 per SM 0.197 / 0.277, 6 per SM (one
+        // resident wave) 0.197 / 0.287.
+        static const unsigned ah_per_sm = [] { const char* e = getenv("B200RT_RAYCAST_AH_CTAS"); return e && atoi(e) > 0 ? (unsigned)atoi(e) : 24u; }();
+        const unsigned ah_resident = (unsigned)ctx->sm_count * ah_per_sm;
         if (coop & 2)
             trace_rays_kernel<2, false, true><<<persistent_grid_rays<2, false, true>(ctx, n), COOP_BLOCK, 0, s>>>(
                 nullptr, nullptr, (uint32_t)n, 0u, (ExtHit*)ext, nullptr, (const RaycastParamsDev*)d_params, hg, hg_stride, hg_count, counter, nullptr, nullptr, 1u, 0u,
                 ah, dual);
         else if (tiled)
-            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<true, true>, g_tiled, dim3(TILE_CTA_THREADS), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
-                                      (ExtHit*)ext, hg, hg_stride, hg_count, dual));
+            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<true, true>, dim3(std::min(g_tiled.x * g_tiled.y, ah_resident)), dim3(TILE_CTA_THREADS), s,
+                                      (const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg, hg_stride, hg_count, dual));
         else
-            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<false, true>, dim3(div_up(n, 128)), dim3(128), s, (const RaycastParamsDev*)d_params, (uint32_t)n, width, height,
-                                      (ExtHit*)ext, hg, hg_stride, hg_count, dual));
+            B2_CUDA(ctx, launch_chain(raycast_simple_kernel<false, true>, dim3(std::min(div_up(n, 128), ah_resident)), dim3(128), s,
+                                      (const RaycastParamsDev*)d_params, (uint32_t)n, width, height, (ExtHit*)ext, hg, hg_stride, hg_count, dual));
     }
     B2_LAUNCH_CHECK(ctx);
     return 0;

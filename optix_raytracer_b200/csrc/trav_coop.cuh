@@ -868,12 +868,13 @@ __device__ __forceinline__ void trace_persistent(Work& work, uint32_t n_items, u
 #endif
 constexpr uint32_t TILE_W = B200RT_TILE_W, TILE_H = 32u / TILE_W, TILE_CTA_THREADS = 32u * B200RT_TILE_CTA_WARPS;
 constexpr uint32_t CTA_TILE_W = (B200RT_TILE_CTA_WARPS >= 2 ? 2u : 1u) * TILE_W, CTA_TILE_H = (B200RT_TILE_CTA_WARPS >= 4 ? 2u : 1u) * TILE_H;
-__device__ __forceinline__ void tile_xy(uint32_t& x, uint32_t& y)
+__device__ __forceinline__ void tile_xy(uint32_t bx, uint32_t by, uint32_t& x, uint32_t& y)   // CTA tile (bx, by)
 {
     const uint32_t wrp = threadIdx.x >> 5, ln = threadIdx.x & 31u;
-    x = blockIdx.x * CTA_TILE_W + (wrp & 1u) * TILE_W + ln % TILE_W;
-    y = blockIdx.y * CTA_TILE_H + (wrp >> 1) * TILE_H + ln / TILE_W;
+    x = bx * CTA_TILE_W + (wrp & 1u) * TILE_W + ln % TILE_W;
+    y = by * CTA_TILE_H + (wrp >> 1) * TILE_H + ln / TILE_W;
 }
+__device__ __forceinline__ void tile_xy(uint32_t& x, uint32_t& y) { tile_xy(blockIdx.x, blockIdx.y, x, y); }
 
 // The same order for launches whose lanes are a flat index: index -> pixel, bands of TILE_H rows cut into TILE_W x TILE_H tiles, a
 // bijection of [0, width * height) for any size (columns beyond the last whole tile of a band and the rows of a last partial band
