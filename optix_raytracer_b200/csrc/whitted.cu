@@ -898,8 +898,9 @@ int launch_whitted(b200rt_context ctx, cudaStream_t s, b200rt_deviceptr d_params
         // Both instantiations of the persistent kernels are enqueued: which kind the traversable is, is read on the device
         // (AccelHeader::anyhit), each kernel returns at once unless it is its kind, so the choice cannot go stale when another handle is
         // written into the same LaunchParams.  (B200RT_WHITTED_INLINE: opaque scenes on the one-ray-per-thread kernels instead.)
-        B2_CUDA(ctx, launch_chain(w_primary_kernel<true>, dim3(g_primary), dim3(COOP_BLOCK), s, k, npix));
-        B2_LAUNCH_CHECK(ctx);
+        // RAYGEN traverses the camera rays of either kind of scene itself (B200RT_WHITTED_INLINE bit 0 with INLINE_ANYHIT): nothing is left
+        // on the candidate list, so neither PRIMARY instantiation is launched — a fact of the configuration, not of the scene
+        if (!(inline_primary && B200RT_WHITTED_INLINE_ANYHIT)) { B2_CUDA(ctx, launch_chain(w_primary_kernel<true>, dim3(g_primary), dim3(COOP_BLOCK), s, k, npix)); B2_LAUNCH_CHECK(ctx); }
         if (!inline_primary) { B2_CUDA(ctx, launch_chain(w_primary_kernel<false>, dim3(g_primary), dim3(COOP_BLOCK), s, k, npix)); B2_LAUNCH_CHECK(ctx); }
         B2_CUDA(ctx, launch_chain(w_shade_kernel, dim3(g_shade), dim3(128), s, k));
         B2_LAUNCH_CHECK(ctx);
